@@ -1,0 +1,170 @@
+/*
+ * tfce_b200.h -- C ABI of libtfce_b200.so: the B200 (sm_100a) implementation of the
+ * TFCE_mediation permutation hot path (permuted OLS fit + t  ->  TFCE  ->  scaled max).
+ *
+ * The reference has no C/FFI plugin interface: its boundary is the Python API of two compiled
+ * extension modules.  Each entry point below names the reference
+ * interface it replaces (paths relative to /root/reference/tfce_mediation/); the ctypes
+ * binding a maintainer adds on the reference side is in INTEGRATION.md and shipped as
+ * tfce_mediation_b200/{tfce,cynumstats,pyfunc,tm_func}.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; tmb_last_error() then returns
+ *     a thread-local human-readable message.  No exceptions cross the ABI.
+ *   - *_host pointers are host memory owned by the caller; *_dev pointers are device memory on
+ *     the handle's device owned by the caller (the Python host layer allocates them with
+ *     PyTorch and passes tensor.data_ptr()).  `stream` is a cudaStream_t passed as void*
+ *     (NULL = the legacy default stream).  Calls taking a stream are asynchronous on it.
+ *   - handles are opaque, own their device state, and are not re-entrant.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef TFCE_B200_H
+#define TFCE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMB_ABI_VERSION 1
+#define TMB_F32 0
+#define TMB_F64 1
+
+typedef struct tmb_graph tmb_graph; /* one adjacency graph + (H, E): == a CreateAdjSet object  */
+typedef struct tmb_plan tmb_plan;   /* a set of graphs laid out along one statistic row          */
+
+/* status bits reported per TFCE map (tmb_plan_run `status_dev`, tmb_tfce_run return detail) */
+#define TMB_MAP_OK 0
+#define TMB_MAP_MAX_IS_ZERO 1   /* max == 0: the reference never returns (fast_tfce.hpp:34-39); we return zeros */
+#define TMB_MAP_STEP_OVERFLOW 2 /* threshold sequence longer than 127 steps (cannot happen for finite maxima)   */
+
+const char *tmb_last_error(void);
+int tmb_abi_version(void);
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int tmb_device_count(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t tmb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph  ==  tfce.pyx:24-42  `CreateAdjSet.__init__(H, E, pyAdjacency)`
+ * The Python layer flattens pyAdjacency (lists / sets / arrays, item order kept) into CSR.
+ * H and E are stored as C float exactly like tfce.pyx:27-33.  pow(n, E) for n = 0..V is
+ * tabulated on the host with the C library's double pow so that the increment
+ * (float)(pow((double)n,(double)E) * (double)powf(T,H)) of fast_tfce.hpp:70-77 is bit-identical.
+ * Out-of-range neighbour indices are rejected.  Directed entries are honoured with the
+ * reference's rule (entry a of adjacency[u] joins only if a activated before u).
+ * ------------------------------------------------------------------------------------------- */
+int tmb_graph_create(int device, int32_t V, const int64_t *indptr_host, const int32_t *indices_host,
+                     float H, float E, tmb_graph **out);
+int tmb_graph_destroy(tmb_graph *g);
+int tmb_graph_num_vertices(const tmb_graph *g, int32_t *V, int64_t *nnz);
+
+/* == tfce.pyx:44-45  `CreateAdjSet.run(image, enhn)`:  enhn[v] += TFCE(image)[v], fp32, host buffers.
+ * map_status (may be NULL) receives TMB_MAP_* bits. */
+int tmb_tfce_run(tmb_graph *g, const float *image_host, float *enhn_host, int *map_status);
+
+/* Test/inspection entry (parity of labels and extents): connected components
+ * of {v : image[v] > T_level} with T from the reference threshold sequence.  labels[v] = smallest
+ * vertex index in v's component or -1; extents[v] = component size or 0.  Host buffers. */
+int tmb_tfce_components(tmb_graph *g, const float *image_host, int level, int32_t *labels_host,
+                        int32_t *extents_host, float *threshold_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Plan: S graphs ("surfaces": lh/rh hemispheres, a voxel skeleton, mmr surfaces) laid along one
+ * statistic row; surface s covers columns [col_offset[s], col_offset[s] + V_s).
+ * weight_host[s] is NULL (weight 1) or V_s floats (vertex-density correction, vdensity_?h of
+ * STEP_1_vertex_tfce_multiple_regression.py:161-173).  max_slots bounds how many maps are in
+ * flight at once (workspace is max_slots * O(V_max)); 0 = library default.
+ *
+ * tmb_plan_run == the body of pyfunc.py:107-126 write_perm_maxTFCE_vertex / _voxel and of
+ * tm_func.py:160-182 for B statistic rows at once:
+ *   for each row b and surface s:  TFCE of +stat (and of -stat when two_sided), then
+ *   max_dev[(b*S + s)*2 + sign] = max_v fl32( fl32(tfce[v] * fl32(max(stat)/100)) * weight[v] )
+ * (0 when nothing is positive).  tfce_pos_dev / tfce_neg_dev (may be NULL) receive the unscaled
+ * TFCE maps, rows of leading dimension ld like stat_dev.  status_dev (may be NULL): int32 [B*S*2].
+ * ------------------------------------------------------------------------------------------- */
+int tmb_plan_create(int device, int S, tmb_graph *const *graphs, const int64_t *col_offset,
+                    const float *const *weight_host, int max_slots, tmb_plan **out);
+int tmb_plan_destroy(tmb_plan *p);
+int tmb_plan_run(tmb_plan *p, const float *stat_dev, int64_t ld, int B, int two_sided, float *max_dev,
+                 float *tfce_pos_dev, float *tfce_neg_dev, int32_t *status_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Permuted-design fit + t.  Replaces cynumstats.pyx:28-29 cy_lin_lstsqr_mat, :47-52 se_of_slope,
+ * :59-64 tval_int (and :66-74 calc_beta_se) for P designs at once.
+ *
+ * Y_dev: float32 (ydtype TMB_F32) or float64 (TMB_F64) [n, ldy] row-major subject-by-vertex data
+ *        (== merge_y; the reference feeds float64 in step 1 and float32 in the randomise step); ldy is a multiple of 128
+ *        covering V rounded up to 128 (pad columns zero); 16-byte aligned.
+ * At_dev: float64 [n, ldA]: column j*rp + i is row i of the j-th design's pseudo-inverse
+ *         (X_j'X_j)^-1 X_j' (k-major so one subject's coefficients are contiguous); rp is r padded
+ *         to 1, 2, 4 or 8 with zero columns; ldA is a multiple of 64 covering P*rp rounded up.
+ * G_dev:  float64 [P, r, r] = X_j'X_j ;  d_dev: float64 [P, r] = diag((X_j'X_j)^-1).
+ * yy_dev: float64 [V] = sum_i Y[i,v]^2 (tmb_glm_sumsq; colsum_dev optionally receives sum_i Y[i,v]).
+ * SSE = yy - b'Gb ; sigma2 = SSE/dof ; se = (float)sqrt(sigma2 * d)  (the fp32 rounding of
+ * cynumstats.pyx:49-51 is kept) ; t = b / (double)se.
+ * Rows [row0, row0 + nrows) of every design are written:
+ *   t32_dev  float32 [P, nrows, ldt]  and/or  t64_dev float64 [P, nrows, ldt]  (either may be NULL)
+ * nan_to_zero != 0 applies voxel_tfce_multiple_regression_randomise.py:109 (t[isnan] = 0).
+ * When the design has an intercept the host passes mean-centred designs (Frisch-Waugh), see
+ * DESIGN.md; yy is then the centred sum of squares (center = 1 in tmb_glm_sumsq).
+ * ------------------------------------------------------------------------------------------- */
+int tmb_glm_sumsq(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, int center, double *yy_dev,
+                  double *colsum_dev, void *stream);
+int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev, int64_t ldA,
+                  const double *G_dev, const double *d_dev, int P, int r, int rp, int row0, int nrows,
+                  double dof, const double *yy_dev, float *t32_dev, double *t64_dev, int64_t ldt,
+                  int nan_to_zero, void *stream);
+/* betas only == cynumstats.pyx:28-29 cy_lin_lstsqr_mat: beta64_dev float64 [nrows, ldt] for the nrows
+ * pseudo-inverse rows stored as the first nrows columns of At_dev (ldA a multiple of 64). */
+int tmb_glm_beta(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev, int64_t ldA,
+                 int nrows, double *beta64_dev, int64_t ldt, void *stream);
+
+/* Direct single-design fit with the reference's EXPLICIT residual pass (cynumstats.pyx:61), one
+ * vertex per thread; serves the API-parity entry points on one design:
+ *   cynumstats.pyx:59-64 tval_int, :66-74 calc_beta_se, :54-57 resid_covars, :31-36 calcF,
+ *   :109-112 cy_lin_lstsqr_mat_residual.
+ * X_dev float64 [n,k] row-major, pinv_dev float64 [k,n] row-major = (X'X)^-1 X', k <= 16.
+ * d_dev float64 [k] = diag of the caller's invXX (may be NULL when no t/se is requested).
+ * Outputs (each may be NULL): beta64/t64 float64 [k, ldt]; se32 float32 [k, ldt];
+ * resid64/resid32 [n, ldr]; sse float64 [V]; tss float64 [V] = sum_i (y_i - grand_mean)^2. */
+int tmb_glm_direct(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *X_dev,
+                   const double *pinv_dev, int k, const double *d_dev, double dof, double grand_mean,
+                   double *beta64_dev, double *t64_dev, float *se32_dev, int64_t ldt, double *resid64_dev,
+                   float *resid32_dev, int64_t ldr, double *sse_dev, double *tss_dev, void *stream);
+
+/* == cynumstats.pyx:47-52 se_of_slope: se32[j, v] = (float)sqrt(sigma2[v] * d[j]). */
+int tmb_se_of_slope(const double *sigma2_dev, int64_t V, const double *d_dev, int k, float *se32_dev, int64_t ld,
+                    void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sobel / Aroian / Goodman mediation z == pyfunc.py:130-162 calc_sobelz for P permutations.
+ * Path A and path B are two fits of the same data; their pseudo-inverse rows are stacked in one
+ * operand laid out like tmb_glm_tstat's At_dev with group width rp (1,2,4,8): columns
+ * j*rp + [0,rA) are path A's rows of permutation j, columns j*rp + rA + [0,rB) path B's.
+ * GA/dA [P,rA,rA]/[P,rA] and GB/dB [P,rB,rB]/[P,rB] as in tmb_glm_tstat; rowA/rowB select the
+ * coefficient whose t enters (calc_beta_se's a[1] / se[1], cynumstats.pyx:66-74).
+ * ta_scalar_dev (may be NULL): float64 [P] path-A t as a per-permutation scalar (medtype 'Y',
+ * where path A is scipy.stats.linregress(x, dep)); then rA may be 0.
+ * alg: 0 = aroian, 1 = sobel, 2 = goodman.   z32_dev float32 [P, ldt] and/or z64_dev float64.
+ * ------------------------------------------------------------------------------------------- */
+int tmb_sobelz(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev, int64_t ldA, int rp,
+               const double *GA_dev, const double *dA_dev, int rA, int rowA, double dofA, const double *GB_dev,
+               const double *dB_dev, int rB, int rowB, double dofB, const double *yy_dev,
+               const double *ta_scalar_dev, int P, int alg, float *z32_dev, double *z64_dev, int64_t ldt,
+               void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Voxel adjacency == pyfunc.py:48-76 create_adjac_voxel (variant 0) and
+ * tools/tm_mulitmodality_adjacency.py:40-66 (variant 1).  mask_host: uint8 [nx,ny,nz] C order.
+ * Two-call protocol: first with indices_host == NULL to obtain *num_voxel and *nnz, then with
+ * indptr_host int64 [num_voxel+1] and indices_host int32 [nnz].  conn is 26 or 6.
+ * ------------------------------------------------------------------------------------------- */
+int tmb_voxel_adjacency(int device, const uint8_t *mask_host, int nx, int ny, int nz, int conn, int variant,
+                        int32_t *num_voxel, int64_t *nnz, int64_t *indptr_host, int32_t *indices_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFCE_B200_H */

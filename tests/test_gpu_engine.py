@@ -1,0 +1,95 @@
+"""GPU parity of whole shuffles: fit -> TFCE -> scaled max against the oracle pipeline that restates
+vertex_tfce_multiple_regression_randomise.py:90-117 + pyfunc.py:107-126 and the mediation twin."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import helpers
+from tfce_mediation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _two_hemi_setup(level, n, k, seed, weight=False):
+    from tfce_mediation_b200.engine import Surface
+    from tfce_mediation_b200.tfce import CreateAdjSet
+    _, _, csr = helpers.ico(level)
+    V = csr[0].shape[0] - 1
+    rs = np.random.RandomState(seed)
+    y = np.concatenate([synth.subject_data(n, csr, seed, 3), synth.subject_data(n, csr, seed + 1, 3)], axis=1)
+    X = np.column_stack([np.ones(n), rs.standard_normal((n, k - 1))])
+    w = synth.vertex_density(synth.kring_csr(csr, 2)) if weight else None
+    surfs = [Surface(CreateAdjSet(2, 0.67, csr), 0, w), Surface(CreateAdjSet(2, 0.67, csr), V, w)]
+    return csr, V, y, X, surfs, w
+
+
+@pytest.mark.parametrize("k,weight", [(2, False), (4, True)])
+def test_regression_block_matches_oracle_pipeline(k, weight):
+    from tfce_mediation_b200.engine import PermutationEngine
+    n, P = 60, 12
+    csr, V, y, X, surfs, w = _two_hemi_setup(4, n, k, 10, weight)
+    eng = PermutationEngine(y, surfs, two_sided=True)
+    idx = np.stack([oracle.permutation_indices(2000 + p, n) for p in range(P)])
+    got = eng.regression_block(X, perm_idx=idx)                       # [P, C, S, 2]
+    assert got.shape == (P, k - 1, 2, 2)
+    run = helpers.oracle_run(2, 0.67, csr)
+    mask = np.ones(V, dtype=bool)
+    dens = 1 if w is None else w
+    for p in range(P):
+        nx = X[idx[p]]
+        t = oracle.tval_int(nx, np.linalg.inv(nx.T @ nx), y, n, k, 2 * V)
+        for c in range(k - 1):
+            for sg, sign in enumerate((1.0, -1.0)):
+                want = oracle.perm_max_vertex(t[c + 1] * sign, V, mask, mask, run, run, dens, dens)
+                have = max(got[p, c, 0, sg], got[p, c, 1, sg])
+                assert np.float32(want) == np.float32(have), (p, c, sg, want, have)
+                assert "%.4f" % want == "%.4f" % have
+
+
+@pytest.mark.parametrize("medtype", ["M", "I", "Y"])
+def test_mediation_block_matches_oracle_pipeline(medtype):
+    from tfce_mediation_b200.engine import PermutationEngine
+    n, P = 50, 6
+    csr, V, y, X, surfs, _ = _two_hemi_setup(4, n, 2, 20)
+    rs = np.random.RandomState(5)
+    pred_x = rs.standard_normal(n)
+    dep = 0.5 * pred_x + rs.standard_normal(n)
+    y = (y + 0.3 * pred_x[:, None] + 0.2 * dep[:, None]).astype(np.float32)
+    eng = PermutationEngine(y, surfs, two_sided=False)
+    idx = np.stack([oracle.permutation_indices(4000 + p, n) for p in range(P)])
+    got, z32, _ = eng.mediation_block(medtype, pred_x, dep, idx, want_maps=True)
+    got, z32 = got.cpu().numpy(), z32.cpu().numpy()[:, :2 * V]
+    run = helpers.oracle_run(2, 0.67, csr)
+    mask = np.ones(V, dtype=bool)
+    for p in range(P):
+        xp = pred_x[idx[p]]
+        dp = dep[idx[p]] if medtype == "Y" else dep
+        z = oracle.sobelz(medtype, xp, dp, y, n, 2 * V)
+        np.testing.assert_allclose(z32[p], z.astype(np.float32), rtol=1e-5, atol=1e-7)
+        want = oracle.perm_max_vertex(z, V, mask, mask, run, run)
+        have = max(got[p, 0], got[p, 1])
+        np.testing.assert_allclose(have, want, rtol=1e-5)
+
+
+def test_voxel_style_single_surface_nan_to_zero():
+    from tfce_mediation_b200.engine import PermutationEngine, Surface
+    from tfce_mediation_b200.tfce import CreateAdjSet
+    adj = helpers.grid_csr(30, 20)
+    csr = oracle.adjacency_to_csr(adj)
+    V, n, k, P = 600, 40, 3, 5
+    rs = np.random.RandomState(2)
+    y = rs.standard_normal((n, V)).astype(np.float32)
+    y[:, 17] = 0.0                                           # zero-variance voxel -> NaN t in the reference
+    X = np.column_stack([np.ones(n), rs.standard_normal((n, k - 1))])
+    eng = PermutationEngine(y, [Surface(CreateAdjSet(2, 0.5, adj), 0)], two_sided=True, nan_to_zero=True)
+    idx = np.stack([oracle.permutation_indices(3000 + p, n) for p in range(P)])
+    got = eng.regression_block(X, perm_idx=idx)
+    run = helpers.oracle_run(2, 0.5, csr)
+    for p in range(P):
+        nx = X[idx[p]]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = oracle.tval_int(nx, np.linalg.inv(nx.T @ nx), y, n, k, V)
+        t[np.isnan(t)] = 0                                   # voxel_tfce_multiple_regression_randomise.py:109
+        for c in range(k - 1):
+            assert np.float32(oracle.perm_max_voxel(t[c + 1], run)) == got[p, c, 0, 0]
+            assert np.float32(oracle.perm_max_voxel(t[c + 1] * -1, run)) == got[p, c, 0, 1]

@@ -1,0 +1,83 @@
+"""GPU parity: fit / t-statistic kernels against the numpy oracle (restating cynumstats.pyx).
+
+Tolerances: float64 results |dt| <= 1e-10 * max(1, |t|) (north_star: <= 1e-10 fp64);
+float32 t-maps fed to TFCE: <= 1e-5 relative hard gate and, as measured against the compiled
+reference, bit-identical (the number of differing float32 values is asserted to be tiny)."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, V, k, seed, mean=0.0, dtype=np.float32):
+    rs = np.random.RandomState(seed)
+    y = (rs.standard_normal((n, V)) + mean).astype(dtype)
+    X = np.column_stack([np.ones(n), rs.standard_normal((n, k - 1))])
+    return X, y
+
+
+def _close64(a, b, tol=1e-10):
+    return np.all(np.abs(a - b) <= tol * np.maximum(1, np.abs(b)))
+
+
+@pytest.mark.parametrize("n,V,k,mean,dtype", [(40, 777, 2, 0.0, np.float32), (100, 5000, 4, 2.5, np.float32),
+                                               (57, 1031, 3, -1.0, np.float64), (30, 129, 9, 0.0, np.float32)])
+def test_tval_int_matches_oracle(n, V, k, mean, dtype):
+    from tfce_mediation_b200 import cynumstats as cs
+    X, y = _data(n, V, k, 1, mean, dtype)
+    invXX = np.linalg.inv(X.T @ X)
+    got = cs.tval_int(X, invXX, y, n, k, V)
+    want = oracle.tval_int(X, invXX, y, n, k, V)
+    assert got.shape == want.shape and got.dtype == np.float64
+    assert _close64(got, want)
+    assert np.mean(got.astype(np.float32) != want.astype(np.float32)) < 1e-4
+
+
+def test_lstsq_beta_residuals_calcF_se():
+    from tfce_mediation_b200 import cynumstats as cs
+    n, V, k = 64, 2000, 4
+    X, y = _data(n, V, k, 2, 1.0)
+    assert _close64(cs.cy_lin_lstsqr_mat(X, y), oracle.lstsq_beta(X, y))
+    assert _close64(cs.cy_lin_lstsqr_mat(X, y[:, 3]), oracle.lstsq_beta(X, y[:, 3]))
+    b, sse = cs.cy_lin_lstsqr_mat_residual(X, y)
+    wb, wsse = oracle.lstsq_residual(X, y)
+    assert _close64(b, wb) and _close64(sse, wsse)
+    assert _close64(cs.calcF(X, y, n, k), oracle.calcF(X, y, n, k), 1e-9)
+    data = np.ascontiguousarray(y.T)                      # V x n like the reference's step-1 input
+    assert _close64(cs.resid_covars(X, data), oracle.resid_covars(X, data))
+    beta, se = cs.calc_beta_se(X[:, 1], y, n, V)
+    wbeta, wse = oracle.calc_beta_se(X[:, 1], y, n, V)
+    assert _close64(beta, wbeta) and se.dtype == np.float32
+    assert np.mean(se != wse) < 1e-4 and np.allclose(se, wse, rtol=1e-6)
+    sigma2 = np.abs(np.random.RandomState(0).standard_normal(V))
+    invXX = np.linalg.inv(X.T @ X)
+    assert np.array_equal(cs.se_of_slope(V, invXX, sigma2, k), oracle.se_of_slope(V, invXX, sigma2, k))
+
+
+@pytest.mark.parametrize("n,V,k,P", [(100, 10242, 2, 70), (48, 3001, 4, 9), (33, 515, 6, 130)])
+def test_engine_tstat_batch_matches_oracle(n, V, k, P):
+    import torch
+    from tfce_mediation_b200 import engine as eng
+    from tfce_mediation_b200._device import DeviceMatrix
+    X, y = _data(n, V, k, 3, 2.0)
+    rs = np.random.RandomState(7)
+    idx = np.stack([rs.permutation(n) for _ in range(P)])
+    Y = DeviceMatrix(y)
+    e = eng.PermutationEngine.__new__(eng.PermutationEngine)      # fit only: no TFCE plan needed
+    e.device, e.Y, e.nan_to_zero, e.h2d_bytes, e.d2h_bytes, e._pinned = Y.t.device, Y, False, 0, 0, {}
+    t32, t64 = e.tstat(eng.row_permuted_stack(X, idx), want_f64=True)
+    t32, t64 = t32.cpu().numpy()[:, :, :V], t64.cpu().numpy()[:, :, :V]
+    # and through explicit per-shuffle designs (the -v / mediation route)
+    t32b = e.tstat(eng.design_stack(np.stack([X[i] for i in idx]))).cpu().numpy()[:, :, :V]
+    bad = 0
+    for p in range(0, P, max(1, P // 6)):
+        nx = X[idx[p]]
+        want = oracle.tval_int(nx, np.linalg.inv(nx.T @ nx), y, n, k, V)[1:]
+        assert _close64(t64[p], want)
+        np.testing.assert_allclose(t32[p], want.astype(np.float32), rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(t32b[p], want.astype(np.float32), rtol=1e-5, atol=1e-7)
+        bad += int(np.sum(t32[p] != want.astype(np.float32)))
+    assert bad <= 2, "float32 t-maps are expected to be bit-identical to the reference (%d differ)" % bad
+    assert torch.cuda.is_available()

@@ -1,0 +1,74 @@
+// Shared helpers for libtfce_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+namespace tmb {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launch_count;
+
+inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+#define TMB_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            ::tmb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,     \
+                             __LINE__);                                                             \
+            return 1;                                                                               \
+        }                                                                                           \
+    } while (0)
+
+#define TMB_REQUIRE(cond, ...)                                                                      \
+    do {                                                                                            \
+        if (!(cond)) {                                                                              \
+            ::tmb::set_error(__VA_ARGS__);                                                          \
+            return 1;                                                                               \
+        }                                                                                           \
+    } while (0)
+
+// ---- per-surface descriptor consumed by the TFCE kernels (device-resident array) -------------
+struct SurfDesc {
+    const int64_t *indptr;  // [V+1]
+    const int32_t *indices; // [nnz]
+    const double *powE;     // [V+1]  pow((double)n, (double)E) tabulated with the host libm
+    const float *weight;    // [V] or nullptr
+    int64_t col_off;        // first column of this surface in a statistic row
+    int32_t V;
+    float H;
+};
+
+// per-launch parameters of the sweep kernel
+struct SweepParams {
+    const SurfDesc *surfs;
+    const int32_t *surf_order; // surfaces sorted by descending V (work items issue big ones first)
+    int S;
+    int B;
+    int two_sided;
+    int accumulate;   // acc starts from tfce_pos/tfce_neg contents (CreateAdjSet.run `+=` semantics)
+    const float *stat;
+    int64_t ld;
+    float *max_out;   // [B, S, 2] or nullptr
+    float *tfce_pos;  // [B, ld] or nullptr
+    float *tfce_neg;  // [B, ld] or nullptr
+    int32_t *status;  // [B, S, 2] or nullptr
+    // component inspection (tmb_tfce_components): stop after this level and write labels/extents
+    int stop_level;
+    int32_t *labels;
+    int32_t *extents;
+    float *threshold_out;
+    // workspace
+    char *workspace;
+    size_t slot_stride;
+    int32_t Vmax;
+    int *work_counter;
+};
+
+int launch_tfce_sweep(const SweepParams &p, int num_slots, cudaStream_t stream);
+size_t tfce_slot_bytes(int32_t Vmax);
+
+} // namespace tmb

@@ -1,0 +1,530 @@
+// Permuted-design OLS fit with fused SSE -> se -> t epilogue (sm_100a).
+//
+// Replaces cynumstats.pyx:28-29 (cy_lin_lstsqr_mat), :47-52 (se_of_slope), :59-64 (tval_int),
+// :66-74 (calc_beta_se) and the fit half of pyfunc.py:130-162 (calc_sobelz) for P designs at once.
+//
+// One dense fp64 contraction  B[P*rp, V] = At^T[P*rp, n] . Y[n, V]  with the stacked
+// pseudo-inverses of P permuted designs as the left operand, tiled 64 (design rows) x 128
+// (vertices) x 32 (subjects) per CTA.  A dedicated producer warp streams both operands into a
+// 3-stage shared-memory ring with bulk async copies (cp.async.bulk -> UBLKCP, completion on
+// mbarriers); 8 consumer warps run an 8x4 register tile of DFMAs each.  The betas never go to
+// HBM: the epilogue turns them into t (or Sobel z) in registers:
+//     SSE = yy - b'Gb,  sigma2 = SSE/dof,  se = fl32(sqrt(sigma2 * d)),  t = b / (double)se
+// keeping the reference's fp32 rounding of se (cynumstats.pyx:49-51).
+#include "common.cuh"
+
+namespace tmb {
+
+static constexpr int BM = 64;       // design rows per tile
+static constexpr int BN = 128;      // vertices per tile
+static constexpr int BK = 32;       // subjects per stage
+static constexpr int STAGES = 3;
+static constexpr int kConsumers = 256;
+static constexpr int kGlmThreads = kConsumers + 32;
+
+// ---------------------------------------------------------------- mbarrier / bulk-copy PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+struct GlmParams {
+    const void *Y; int y_is_f64; int n; int64_t V; int64_t ldy;
+    const double *At; int64_t ldA;
+    const double *G; const double *d;   // [P, r, r], [P, r]
+    int P, r, rp, row0, nrows;
+    double dof;
+    const double *yy;
+    float *t32; double *t64; int64_t ldt;
+    int nan_to_zero;
+    int mode;                           // 0 t-stat, 1 betas, 2 sobel
+    // sobel: rows [0, rA) of each design group are path A, rows [rA, rA+rB) path B
+    const double *GB; const double *dB; int rA, rB, rowA, rowB; double dofB;
+    const double *ta_scalar; int alg;
+};
+
+// sum_{a,b in [lo,lo+r)} acc[g*RP+a][c] * G[(a-lo)*r + (b-lo)] * acc[g*RP+b][c]; every loop is fully
+// unrolled with predicates so the accumulator tile stays in registers.
+template <int RP>
+__device__ __forceinline__ double quad_form(const double (&acc)[8][4], int g, int c, const double *__restrict__ G,
+                                            int lo, int r) {
+    double q = 0.0;
+#pragma unroll
+    for (int a = 0; a < RP; ++a) {
+        if (a >= lo && a < lo + r) {
+            double inner = 0.0;
+#pragma unroll
+            for (int b2 = 0; b2 < RP; ++b2)
+                if (b2 >= lo && b2 < lo + r) inner = __fma_rn(G[(a - lo) * r + (b2 - lo)], acc[g * RP + b2][c], inner);
+            q = __fma_rn(acc[g * RP + a][c], inner, q);
+        }
+    }
+    return q;
+}
+
+template <int RP>
+__device__ __forceinline__ double pick_row(const double (&acc)[8][4], int g, int c, int idx) {
+    double v = 0.0;
+#pragma unroll
+    for (int a = 0; a < RP; ++a)
+        if (a == idx) v = acc[g * RP + a][c];
+    return v;
+}
+
+// se = fl32(sqrt(sigma2 * d)) (cynumstats.pyx:49-51), t = beta / (double)se (cynumstats.pyx:63)
+__device__ __forceinline__ double t_from(double beta, double sse, double dof, double d) {
+    if (sse < 0.0) sse = 0.0;
+    const float se = __double2float_rn(__dsqrt_rn(__dmul_rn(__ddiv_rn(sse, dof), d)));
+    return __ddiv_rn(beta, (double)se);
+}
+
+template <int RP>
+__device__ __forceinline__ void epilogue(const GlmParams &p, const double (&acc)[8][4], int m_base, int64_t v_base) {
+    // thread owns design rows m_base .. m_base+7 and vertices v_base .. v_base+3
+    if (p.mode == 1) { // betas
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m_base + i;
+            if (m < p.P * RP) {
+                double *dst = p.t64 + (size_t)m * p.ldt + v_base;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (v_base + c < p.V) dst[c] = acc[i][c];
+            }
+        }
+        return;
+    }
+    double yy[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) yy[c] = (v_base + c < p.V) ? p.yy[v_base + c] : 0.0;
+
+#pragma unroll
+    for (int g = 0; g < 8 / RP; ++g) {
+        const int perm = m_base / RP + g;
+        if (perm >= p.P) continue;
+        if (p.mode == 0) {
+            const int r = p.r;
+            const double *G = p.G + (size_t)perm * r * r;
+            const double *dg = p.d + (size_t)perm * r;
+            double sse[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sse[c] = yy[c] - quad_form<RP>(acc, g, c, G, 0, r);
+#pragma unroll
+            for (int a = 0; a < RP; ++a) {
+                if (a < p.row0 || a >= p.row0 + p.nrows || a >= r) continue;
+                const double da = dg[a];
+                float o32[4];
+                double o64[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    double t = t_from(acc[g * RP + a][c], sse[c], p.dof, da);
+                    if (p.nan_to_zero && t != t) t = 0.0;
+                    if (v_base + c >= p.V) t = 0.0;
+                    o64[c] = t;
+                    o32[c] = __double2float_rn(t);
+                }
+                const size_t off = ((size_t)perm * p.nrows + (a - p.row0)) * p.ldt + v_base;
+                if (p.t32) *reinterpret_cast<float4 *>(p.t32 + off) = make_float4(o32[0], o32[1], o32[2], o32[3]);
+                if (p.t64) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) p.t64[off + c] = o64[c];
+                }
+            }
+        } else { // sobel (pyfunc.py:130-162)
+            const int rA = p.rA, rB = p.rB;
+            const double *GB = p.GB + (size_t)perm * rB * rB;
+            const double dBr = p.dB[(size_t)perm * rB + p.rowB];
+            float o32[4];
+            double o64[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                double ta;
+                if (p.ta_scalar) {
+                    ta = p.ta_scalar[perm];
+                } else {
+                    const double sseA = yy[c] - quad_form<RP>(acc, g, c, p.G + (size_t)perm * rA * rA, 0, rA);
+                    ta = t_from(pick_row<RP>(acc, g, c, p.rowA), sseA, p.dof, p.d[(size_t)perm * rA + p.rowA]);
+                }
+                const double sseB = yy[c] - quad_form<RP>(acc, g, c, GB, rA, rB);
+                const double tb = t_from(pick_row<RP>(acc, g, c, rA + p.rowB), sseB, p.dofB, dBr);
+                // 1/sqrt(1/tb^2 + 1/ta^2 (+|-) 1/(ta^2 tb^2)), evaluated in the reference's order
+                const double ta2 = __dmul_rn(ta, ta), tb2 = __dmul_rn(tb, tb);
+                double s = __dadd_rn(__ddiv_rn(1.0, tb2), __ddiv_rn(1.0, ta2));
+                const double cross = __ddiv_rn(1.0, __dmul_rn(ta2, tb2));
+                if (p.alg == 0) s = __dadd_rn(s, cross);
+                else if (p.alg == 2) s = __dsub_rn(s, cross);
+                double z = __ddiv_rn(1.0, __dsqrt_rn(s));
+                if (v_base + c >= p.V) z = 0.0;
+                o64[c] = z;
+                o32[c] = __double2float_rn(z);
+            }
+            const size_t off = (size_t)perm * p.ldt + v_base;
+            if (p.t32) *reinterpret_cast<float4 *>(p.t32 + off) = make_float4(o32[0], o32[1], o32[2], o32[3]);
+            if (p.t64) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) p.t64[off + c] = o64[c];
+            }
+        }
+    }
+}
+
+template <typename YT>
+__device__ __forceinline__ void load_y4(const YT *p, double (&y)[4]);
+template <>
+__device__ __forceinline__ void load_y4<float>(const float *p, double (&y)[4]) {
+    const float4 f = *reinterpret_cast<const float4 *>(p);
+    y[0] = (double)f.x; y[1] = (double)f.y; y[2] = (double)f.z; y[3] = (double)f.w;
+}
+template <>
+__device__ __forceinline__ void load_y4<double>(const double *p, double (&y)[4]) {
+    const double2 a = *reinterpret_cast<const double2 *>(p);
+    const double2 b = *reinterpret_cast<const double2 *>(p + 2);
+    y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y;
+}
+
+template <int RP, typename YT>
+__global__ void __launch_bounds__(kGlmThreads, 1) glm_tile_kernel(GlmParams p, int mtiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sA = reinterpret_cast<double *>(smem_raw);                             // [STAGES][BK][BM]
+    YT *sY = reinterpret_cast<YT *>(smem_raw + sizeof(double) * STAGES * BK * BM); // [STAGES][BK][BN]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + sizeof(double) * STAGES * BK * BM +
+                                                   sizeof(YT) * STAGES * BK * BN);
+    uint64_t *empty = full + STAGES;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int mt = tile % mtiles;
+    const int64_t vt = tile / mtiles;
+    const int m0 = mt * BM;
+    const int64_t v0 = vt * BN;
+    const int nchunks = (p.n + BK - 1) / BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kConsumers / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= kConsumers) {
+        // ===== producer warp: one elected lane issues the bulk copies =====
+        if (tid == kConsumers) {
+            for (int kc = 0; kc < nchunks; ++kc) {
+                const int s = kc % STAGES;
+                const int round = kc / STAGES;
+                mbar_wait(empty + s, (round & 1) ^ 1);
+                const int k0 = kc * BK;
+                const int rows = min(BK, p.n - k0);
+                mbar_expect_tx(full + s, (uint32_t)rows * (BM * 8 + BN * (uint32_t)sizeof(YT)));
+                for (int kk = 0; kk < rows; ++kk) {
+                    bulk_g2s(sA + ((size_t)s * BK + kk) * BM, p.At + (size_t)(k0 + kk) * p.ldA + m0, BM * 8, full + s);
+                    bulk_g2s(sY + ((size_t)s * BK + kk) * BN, reinterpret_cast<const YT *>(p.Y) + (size_t)(k0 + kk) * p.ldy + v0,
+                             BN * (uint32_t)sizeof(YT), full + s);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int tm = tid >> 5;  // 0..7  -> design rows tm*8 .. +7   (warp-uniform: A reads broadcast)
+    const int tn = tid & 31;  // 0..31 -> vertices tn*4 .. +3
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = 0.0;
+
+    for (int kc = 0; kc < nchunks; ++kc) {
+        const int s = kc % STAGES;
+        const int round = kc / STAGES;
+        mbar_wait(full + s, round & 1);
+        const int rows = min(BK, p.n - kc * BK);
+        const double *a_base = sA + (size_t)s * BK * BM + tm * 8;
+        const YT *y_base = sY + (size_t)s * BK * BN + tn * 4;
+#pragma unroll 4
+        for (int kk = 0; kk < rows; ++kk) {
+            const double2 a01 = *reinterpret_cast<const double2 *>(a_base + kk * BM);
+            const double2 a23 = *reinterpret_cast<const double2 *>(a_base + kk * BM + 2);
+            const double2 a45 = *reinterpret_cast<const double2 *>(a_base + kk * BM + 4);
+            const double2 a67 = *reinterpret_cast<const double2 *>(a_base + kk * BM + 6);
+            const double a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
+            double y[4];
+            load_y4<YT>(y_base + kk * BN, y);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = __fma_rn(a[i], y[c], acc[i][c]);
+        }
+        __syncwarp();
+        if (tn == 0) mbar_arrive(empty + s);
+    }
+    epilogue<RP>(p, acc, m0 + tm * 8, v0 + tn * 4);
+}
+
+// ---------------------------------------------------------------- per-vertex sum of squares
+template <typename YT>
+__global__ void glm_sumsq_kernel(const YT *__restrict__ Y, int n, int64_t V, int64_t ldy, int center,
+                                 double *__restrict__ yy, double *__restrict__ colsum) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += (double)Y[(size_t)i * ldy + v];
+    const double mean = center ? s / n : 0.0;
+    double q = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double c = (double)Y[(size_t)i * ldy + v] - mean;
+        q = __fma_rn(c, c, q);
+    }
+    if (yy) yy[v] = q;
+    if (colsum) colsum[v] = s;
+}
+
+// ---------------------------------------------------------------- direct per-vertex fit
+// One thread per vertex, subjects streamed coalesced across the warp: beta = pinv . y in registers,
+// then the explicit residual pass r_i = y_i - x_i . beta exactly as cynumstats.pyx:61 does it.
+// Serves the API-parity entry points (tval_int / calc_beta_se / resid_covars / calcF /
+// cy_lin_lstsqr_mat_residual on single designs); the permutation loop uses glm_tile_kernel.
+static constexpr int kMaxK = 16;
+struct DirectParams {
+    const void *Y; int y_is_f64; int n; int64_t V; int64_t ldy;
+    const double *X; const double *pinv; int k;
+    const double *d; double dof; double grand_mean;
+    double *beta64; double *t64; float *se32; int64_t ldt;
+    double *r64; float *r32; int64_t ldr;
+    double *sse; double *tss;
+};
+
+template <typename YT>
+__global__ void glm_direct_kernel(DirectParams p) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.V) return;
+    const YT *__restrict__ Y = reinterpret_cast<const YT *>(p.Y);
+    const int n = p.n, k = p.k;
+    double beta[kMaxK];
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) beta[j] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double y = (double)Y[(size_t)i * p.ldy + v];
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j)
+            if (j < k) beta[j] = __fma_rn(p.pinv[(size_t)j * n + i], y, beta[j]);
+    }
+    double sse = 0.0, tss = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double fit = 0.0;
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j)
+            if (j < k) fit = __fma_rn(p.X[(size_t)i * k + j], beta[j], fit);
+        const double y = (double)Y[(size_t)i * p.ldy + v];
+        const double res = y - fit;
+        if (p.r64) p.r64[(size_t)i * p.ldr + v] = res;
+        if (p.r32) p.r32[(size_t)i * p.ldr + v] = (float)res;
+        sse = __fma_rn(res, res, sse);
+        const double c = y - p.grand_mean;
+        tss = __fma_rn(c, c, tss);
+    }
+    if (p.sse) p.sse[v] = sse;
+    if (p.tss) p.tss[v] = tss;
+    const double sigma2 = __ddiv_rn(sse, p.dof);
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) {
+        if (j < k) {
+            if (p.beta64) p.beta64[(size_t)j * p.ldt + v] = beta[j];
+            if (p.d) {
+                const float se = __double2float_rn(__dsqrt_rn(__dmul_rn(sigma2, p.d[j])));
+                if (p.se32) p.se32[(size_t)j * p.ldt + v] = se;
+                if (p.t64) p.t64[(size_t)j * p.ldt + v] = __ddiv_rn(beta[j], (double)se);
+            }
+        }
+    }
+}
+
+// se[j, v] = fl32(sqrt(sigma2[v] * d[j]))   (cynumstats.pyx:47-52 se_of_slope, without the Python loop)
+__global__ void se_of_slope_kernel(const double *__restrict__ sigma2, int64_t V, const double *__restrict__ d, int k,
+                                   float *__restrict__ se, int64_t ld) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const double s = sigma2[v];
+    for (int j = 0; j < k; ++j) se[(size_t)j * ld + v] = __double2float_rn(__dsqrt_rn(__dmul_rn(s, d[j])));
+}
+
+template <typename YT>
+static size_t glm_smem_bytes() {
+    return sizeof(double) * STAGES * BK * BM + sizeof(YT) * STAGES * BK * BN + sizeof(uint64_t) * 2 * STAGES;
+}
+
+template <int RP, typename YT>
+static int launch_tile(const GlmParams &p, cudaStream_t stream) {
+    const int mtiles = (p.P * RP + BM - 1) / BM;
+    const int64_t vtiles = (p.V + BN - 1) / BN;
+    const int64_t tiles = (int64_t)mtiles * vtiles;
+    TMB_REQUIRE(tiles < (int64_t)INT32_MAX, "glm: too many tiles");
+    TMB_CUDA(cudaFuncSetAttribute(glm_tile_kernel<RP, YT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)glm_smem_bytes<YT>()));
+    glm_tile_kernel<RP, YT><<<(unsigned)tiles, kGlmThreads, glm_smem_bytes<YT>(), stream>>>(p, mtiles);
+    count_launch();
+    TMB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename YT>
+static int launch_glm_t(const GlmParams &p, cudaStream_t stream) {
+    switch (p.rp) {
+    case 1: return launch_tile<1, YT>(p, stream);
+    case 2: return launch_tile<2, YT>(p, stream);
+    case 4: return launch_tile<4, YT>(p, stream);
+    case 8: return launch_tile<8, YT>(p, stream);
+    default: set_error("glm: rp must be 1, 2, 4 or 8 (got %d)", p.rp); return 1;
+    }
+}
+
+int launch_glm(const GlmParams &p, cudaStream_t stream) {
+    TMB_REQUIRE(p.ldy % BN == 0 && p.ldy >= (p.V + BN - 1) / BN * BN,
+                "glm: ldy must be a multiple of %d covering V rounded up", BN);
+    TMB_REQUIRE(p.ldA % BM == 0 && p.ldA >= ((int64_t)p.P * p.rp + BM - 1) / BM * BM,
+                "glm: ldA must be a multiple of %d covering P*rp rounded up", BM);
+    TMB_REQUIRE(p.ldt % 4 == 0 && p.ldt >= (p.V + 3) / 4 * 4, "glm: ldt must be a multiple of 4 covering V");
+    TMB_REQUIRE((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.At) & 15) == 0,
+                "glm: Y and At must be 16-byte aligned");
+    TMB_REQUIRE(!p.t32 || (reinterpret_cast<uintptr_t>(p.t32) & 15) == 0, "glm: t32 must be 16-byte aligned");
+    return p.y_is_f64 ? launch_glm_t<double>(p, stream) : launch_glm_t<float>(p, stream);
+}
+
+} // namespace tmb
+
+// --------------------------------------------------------------------------------- C ABI
+#include "../../include/tfce_b200.h"
+using namespace tmb;
+
+static int dtype_is_f64(int ydtype, int *out) {
+    TMB_REQUIRE(ydtype == TMB_F32 || ydtype == TMB_F64, "ydtype must be TMB_F32 (0) or TMB_F64 (1)");
+    *out = ydtype == TMB_F64;
+    return 0;
+}
+
+extern "C" int tmb_glm_sumsq(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, int center,
+                             double *yy_dev, double *colsum_dev, void *stream) {
+    TMB_REQUIRE(Y_dev && (yy_dev || colsum_dev) && n > 0 && V > 0, "tmb_glm_sumsq: bad arguments");
+    int f64;
+    if (dtype_is_f64(ydtype, &f64)) return 1;
+    const int threads = 256;
+    const unsigned grid = (unsigned)((V + threads - 1) / threads);
+    if (f64)
+        glm_sumsq_kernel<double><<<grid, threads, 0, (cudaStream_t)stream>>>((const double *)Y_dev, n, V, ldy, center,
+                                                                          yy_dev, colsum_dev);
+    else
+        glm_sumsq_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>((const float *)Y_dev, n, V, ldy, center,
+                                                                         yy_dev, colsum_dev);
+    count_launch();
+    TMB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev,
+                             int64_t ldA, const double *G_dev, const double *d_dev, int P, int r, int rp, int row0,
+                             int nrows, double dof, const double *yy_dev, float *t32_dev, double *t64_dev,
+                             int64_t ldt, int nan_to_zero, void *stream) {
+    TMB_REQUIRE(Y_dev && At_dev && G_dev && d_dev && yy_dev && (t32_dev || t64_dev), "tmb_glm_tstat: null pointer");
+    TMB_REQUIRE(n > 0 && V > 0 && P > 0 && r >= 1 && r <= rp && row0 >= 0 && nrows >= 1 && row0 + nrows <= r,
+                "tmb_glm_tstat: bad shape (n=%d V=%lld P=%d r=%d rp=%d row0=%d nrows=%d)", n, (long long)V, P, r, rp,
+                row0, nrows);
+    GlmParams p{};
+    if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
+    p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.G = G_dev; p.d = d_dev;
+    p.P = P; p.r = r; p.rp = rp; p.row0 = row0; p.nrows = nrows; p.dof = dof; p.yy = yy_dev;
+    p.t32 = t32_dev; p.t64 = t64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 0;
+    return launch_glm(p, (cudaStream_t)stream);
+}
+
+extern "C" int tmb_glm_beta(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev,
+                            int64_t ldA, int nrows, double *beta64_dev, int64_t ldt, void *stream) {
+    TMB_REQUIRE(Y_dev && At_dev && beta64_dev && n > 0 && V > 0 && nrows > 0, "tmb_glm_beta: bad arguments");
+    GlmParams p{};
+    if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
+    p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.P = nrows; p.r = 1; p.rp = 1;
+    p.t64 = beta64_dev; p.ldt = ldt; p.mode = 1;
+    return launch_glm(p, (cudaStream_t)stream);
+}
+
+extern "C" int tmb_glm_direct(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *X_dev,
+                              const double *pinv_dev, int k, const double *d_dev, double dof, double grand_mean,
+                              double *beta64_dev, double *t64_dev, float *se32_dev, int64_t ldt, double *resid64_dev,
+                              float *resid32_dev, int64_t ldr, double *sse_dev, double *tss_dev, void *stream) {
+    TMB_REQUIRE(Y_dev && X_dev && pinv_dev && n > 0 && V > 0, "tmb_glm_direct: bad arguments");
+    TMB_REQUIRE(k >= 1 && k <= kMaxK, "tmb_glm_direct: k must be in 1..%d (got %d)", kMaxK, k);
+    TMB_REQUIRE(!(t64_dev || se32_dev) || d_dev, "tmb_glm_direct: t/se requested without diag(inv(X'X))");
+    DirectParams p{};
+    if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
+    p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.X = X_dev; p.pinv = pinv_dev; p.k = k; p.d = d_dev; p.dof = dof;
+    p.grand_mean = grand_mean; p.beta64 = beta64_dev; p.t64 = t64_dev; p.se32 = se32_dev; p.ldt = ldt;
+    p.r64 = resid64_dev; p.r32 = resid32_dev; p.ldr = ldr; p.sse = sse_dev; p.tss = tss_dev;
+    const int threads = 128;
+    const unsigned grid = (unsigned)((V + threads - 1) / threads);
+    if (p.y_is_f64) glm_direct_kernel<double><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
+    else glm_direct_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
+    count_launch();
+    TMB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tmb_se_of_slope(const double *sigma2_dev, int64_t V, const double *d_dev, int k, float *se32_dev,
+                               int64_t ld, void *stream) {
+    TMB_REQUIRE(sigma2_dev && d_dev && se32_dev && V > 0 && k > 0, "tmb_se_of_slope: bad arguments");
+    const int threads = 256;
+    se_of_slope_kernel<<<(unsigned)((V + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        sigma2_dev, V, d_dev, k, se32_dev, ld);
+    count_launch();
+    TMB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tmb_sobelz(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev,
+                          int64_t ldA, int rp, const double *GA_dev, const double *dA_dev, int rA, int rowA,
+                          double dofA, const double *GB_dev, const double *dB_dev, int rB, int rowB, double dofB,
+                          const double *yy_dev, const double *ta_scalar_dev, int P, int alg, float *z32_dev,
+                          double *z64_dev, int64_t ldt, void *stream) {
+    TMB_REQUIRE(Y_dev && At_dev && GB_dev && dB_dev && yy_dev && (z32_dev || z64_dev), "tmb_sobelz: null pointer");
+    TMB_REQUIRE(rA >= 0 && rB >= 1 && rA + rB <= rp && rowB >= 0 && rowB < rB &&
+                    (ta_scalar_dev || (rA >= 1 && rowA >= 0 && rowA < rA && GA_dev && dA_dev)),
+                "tmb_sobelz: bad shape");
+    TMB_REQUIRE(alg >= 0 && alg <= 2, "tmb_sobelz: alg must be 0 (aroian), 1 (sobel) or 2 (goodman)");
+    GlmParams p{};
+    if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
+    p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.G = GA_dev; p.d = dA_dev;
+    p.P = P; p.r = rA + rB; p.rp = rp; p.dof = dofA; p.yy = yy_dev; p.t32 = z32_dev; p.t64 = z64_dev; p.ldt = ldt;
+    p.mode = 2; p.GB = GB_dev; p.dB = dB_dev; p.rA = rA; p.rB = rB; p.rowA = rowA; p.rowB = rowB; p.dofB = dofB;
+    p.ta_scalar = ta_scalar_dev; p.alg = alg;
+    return launch_glm(p, (cudaStream_t)stream);
+}

@@ -1,0 +1,307 @@
+"""Batched permutation engine: the B200-first form of the reference's per-shuffle loop.
+
+The reference runs, per shuffle (vertex_tfce_multiple_regression_randomise.py:90-117,
+voxel_...:91-119, tm_func.py:144-185):
+    permute design -> tval_int -> for each contrast and sign: scatter, TFCE per surface, scaled max
+Here a block of P shuffles is one fused fit launch (tmb_glm_tstat, t-maps [P, C, V] straight into
+HBM, betas never written) followed by one TFCE launch over P*C*S work items (tmb_plan_run), with the
+subject data resident in HBM for the whole job.  Permutation index rows come from the caller (the
+drivers generate them with the reference's own numpy RNG calls), so results are reproducible.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._device import DeviceMatrix, TILE_M, round_up, to_host
+from .tfce import CreateAdjSet
+
+
+def _rp_for(r):
+    for rp in (1, 2, 4, 8):
+        if r <= rp:
+            return rp
+    raise ValueError("the batched fit supports at most 8 non-intercept regressors per design (got %d)" % r)
+
+
+class Surface(object):
+    """One TFCE graph laid on columns [col_offset, col_offset + V) of a statistic row."""
+
+    def __init__(self, adjset, col_offset, weight=None):
+        if not isinstance(adjset, CreateAdjSet):
+            raise TypeError("adjset must be a tfce_mediation_b200.tfce.CreateAdjSet")
+        self.adjset = adjset
+        self.col_offset = int(col_offset)
+        if weight is not None and np.ndim(weight) == 0:
+            weight = None if float(weight) == 1.0 else np.full(adjset.num_vertices, weight, dtype=np.float32)
+        if weight is not None:
+            weight = np.ascontiguousarray(weight, dtype=np.float32)
+            if weight.shape != (adjset.num_vertices,):
+                raise ValueError("weight must have one entry per vertex")
+        self.weight = weight
+
+
+class TfcePlan(object):
+    """tmb_plan handle: S surfaces along one statistic row."""
+
+    def __init__(self, surfaces, device=None, max_slots=0):
+        import torch
+        _lib.require_device()
+        self.surfaces = list(surfaces)
+        S = len(self.surfaces)
+        if S == 0:
+            raise ValueError("no surfaces")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        graphs = (ctypes.c_void_p * S)(*[s.adjset._handle for s in self.surfaces])
+        offs = (ctypes.c_int64 * S)(*[s.col_offset for s in self.surfaces])
+        wts = (ctypes.c_void_p * S)(*[(s.weight.ctypes.data if s.weight is not None else None) for s in self.surfaces])
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().tmb_plan_create(self.device.index or 0, S, graphs, offs, wts, int(max_slots),
+                                              ctypes.byref(h)))
+        self._handle = h
+        self.S = S
+        self.row_len = max(s.col_offset + s.adjset.num_vertices for s in self.surfaces)
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and _lib._lib is not None:
+            _lib._lib.tmb_plan_destroy(h)
+            self._handle = None
+
+    def run(self, stat, two_sided=True, want_maps=False, out_max=None):
+        """stat: CUDA float32 [B, ld].  Returns (max [B, S, 2] CUDA float32, status [B,S,2] int32, maps)."""
+        import torch
+        if not (stat.is_cuda and stat.dtype == torch.float32 and stat.dim() == 2 and stat.stride(1) == 1):
+            raise ValueError("stat must be a CUDA float32 [B, ld] tensor with unit column stride")
+        B, ld = int(stat.shape[0]), int(stat.stride(0))
+        mx = out_max if out_max is not None else torch.empty((B, self.S, 2), dtype=torch.float32, device=stat.device)
+        status = torch.empty((B, self.S, 2), dtype=torch.int32, device=stat.device)
+        pos = neg = None
+        if want_maps:
+            pos = torch.zeros((B, ld), dtype=torch.float32, device=stat.device)
+            neg = torch.zeros((B, ld), dtype=torch.float32, device=stat.device) if two_sided else None
+        _lib.check(_lib.lib().tmb_plan_run(self._handle, _lib.ptr(stat), ld, B, 1 if two_sided else 0, _lib.ptr(mx),
+                                           _lib.ptr(pos), _lib.ptr(neg), _lib.ptr(status), _lib.current_stream()))
+        return mx, status, (pos, neg)
+
+
+# ------------------------------------------------------------------------------------------ designs
+
+def has_intercept(X):
+    X = np.asarray(X)
+    return X.ndim >= 2 and X.shape[-1] >= 2 and bool(np.all(X[..., 0] == 1))
+
+
+def design_stack(Xs, center=True):
+    """Per-design normal-equation algebra on the host (k x k work only).
+
+    Xs: float64 [P, n, k] permuted designs (column 0 = intercept when center=True).
+    Returns dict(pinv [P, r, n], G [P, r, r], d [P, r], r, dof) where, with an intercept, the
+    regressors are mean-centred (Frisch-Waugh-Lovell: slopes, residuals and diag(inv(X'X)) of
+    the slopes are unchanged) and r = k - 1."""
+    Xs = np.asarray(Xs, dtype=np.float64)
+    P, n, k = Xs.shape
+    if center:
+        Z = Xs[:, :, 1:] - Xs[:, :, 1:].mean(axis=1, keepdims=True)
+    else:
+        Z = Xs
+    G = np.einsum("pni,pnj->pij", Z, Z)
+    Ginv = np.linalg.inv(G)
+    pinv = np.einsum("pij,pnj->pin", Ginv, Z)
+    d = np.einsum("pii->pi", Ginv).copy()
+    return dict(pinv=pinv, G=np.ascontiguousarray(G), d=np.ascontiguousarray(d), r=Z.shape[2], dof=float(n - k),
+                centered=bool(center))
+
+
+def row_permuted_stack(X, perm_idx, center=True):
+    """Same as design_stack for designs X[perm_idx[p]] (whole rows permuted): X'X is invariant, so
+    one pseudo-inverse is formed and its columns are gathered."""
+    X = np.asarray(X, dtype=np.float64)
+    perm_idx = np.asarray(perm_idx)
+    P = perm_idx.shape[0]
+    base = design_stack(X[None], center=center)
+    pinv = base["pinv"][0][:, perm_idx]                    # [r, P, n]
+    r = base["r"]
+    return dict(pinv=np.ascontiguousarray(pinv.transpose(1, 0, 2)), G=np.repeat(base["G"], P, axis=0),
+                d=np.repeat(base["d"], P, axis=0), r=r, dof=base["dof"], centered=bool(center))
+
+
+def pack_At(pinv, rp):
+    """[P, r, n] pseudo-inverse rows -> At float64 [n, ldA] with column p*rp + i = row i of design p."""
+    P, r, n = pinv.shape
+    ldA = round_up(P * rp, TILE_M)
+    At = np.zeros((n, ldA), dtype=np.float64)
+    At[:, :P * rp].reshape(n, P, rp)[:, :, :r] = pinv.transpose(2, 0, 1)
+    return At, ldA
+
+
+class PermutationEngine(object):
+    """Data resident in HBM + a TFCE plan; runs blocks of shuffles."""
+
+    def __init__(self, data, surfaces, two_sided=True, nan_to_zero=False, device=None, max_slots=0):
+        import torch
+        _lib.require_device()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.Y = data if isinstance(data, DeviceMatrix) else DeviceMatrix(data, device=self.device)
+        self.plan = TfcePlan(surfaces, device=self.device, max_slots=max_slots) if surfaces is not None else None
+        if self.plan is not None and self.plan.row_len > self.Y.V:
+            raise ValueError("surfaces cover %d columns but the data has %d" % (self.plan.row_len, self.Y.V))
+        self.two_sided = bool(two_sided)
+        self.nan_to_zero = bool(nan_to_zero)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._pinned = {}
+
+    # -- staging ---------------------------------------------------------------------------------
+    def _upload(self, name, host_array):
+        """Host -> device through a reused pinned staging buffer; bytes are counted for bench e2e."""
+        import torch
+        a = np.ascontiguousarray(host_array)
+        key = (name, a.shape, a.dtype.str)
+        ent = self._pinned.get(key)
+        if ent is None:
+            ent = [torch.empty(a.shape, dtype=torch.from_numpy(a).dtype).pin_memory(), None]
+            self._pinned[key] = ent
+        pin, ev = ent
+        if ev is not None:
+            ev.synchronize()          # the previous async copy out of this staging buffer has finished
+        pin.numpy()[...] = a
+        self.h2d_bytes += a.nbytes
+        dev = pin.to(self.device, non_blocking=True)
+        ent[1] = torch.cuda.Event()
+        ent[1].record()
+        return dev
+
+    def _download(self, t):
+        self.d2h_bytes += t.numel() * t.element_size()
+        return to_host(t)
+
+    # -- fit -------------------------------------------------------------------------------------
+    def tstat(self, stack, rows=None, want_f64=False):
+        """Fused fit+t for a design stack (design_stack / row_permuted_stack output).
+        Returns CUDA float32 [P, C, ld] (and float64 when want_f64)."""
+        import torch
+        P, r, n = stack["pinv"].shape
+        if n != self.Y.n:
+            raise ValueError("design has %d subjects, data has %d" % (n, self.Y.n))
+        rp = _rp_for(r)
+        row0, nrows = (0, r) if rows is None else (int(rows[0]), int(rows[1]))
+        At, ldA = pack_At(stack["pinv"], rp)
+        At_d = self._upload("At", At)
+        G_d = self._upload("G", stack["G"])
+        d_d = self._upload("d", stack["d"])
+        centered = stack.get("centered", True)
+        yy = self.Y.sumsq(centered)
+        t32 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float32, device=self.device)
+        t64 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
+        _lib.check(_lib.lib().tmb_glm_tstat(
+            _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA,
+            _lib.ptr(G_d), _lib.ptr(d_d), P, r, rp, row0, nrows, stack["dof"], _lib.ptr(yy), _lib.ptr(t32),
+            _lib.ptr(t64), self.Y.ld, 1 if self.nan_to_zero else 0, _lib.current_stream()))
+        return (t32, t64) if want_f64 else t32
+
+    # -- whole shuffles --------------------------------------------------------------------------
+    def regression_block(self, X, perm_idx=None, designs=None, want_maps=False, download=True):
+        """Regression + TFCE + scaled max for a block of shuffles.
+
+        Either perm_idx int [P, n] (designs X[perm_idx[p]], whole rows permuted) or designs
+        float64 [P, n, k] (arbitrary per-shuffle designs, e.g. the -v partial-column mode).
+        X / designs must carry the intercept in column 0, as every reference driver builds them
+        (np.column_stack([np.ones(n), pred_x])).
+        Returns float32 [P, C, S, 2]: per shuffle, contrast (= regressor 1..k-1), surface and sign
+        (+t, -t) the scaled TFCE maximum of pyfunc.py:116-118 / :125 / tm_func.py:173-182."""
+        if designs is not None:
+            designs = np.asarray(designs, dtype=np.float64)
+            if not has_intercept(designs):
+                raise ValueError("designs must have the intercept in column 0")
+            stack = design_stack(designs, center=True)
+        else:
+            X = np.asarray(X, dtype=np.float64)
+            if not has_intercept(X):
+                raise ValueError("X must have the intercept in column 0")
+            stack = row_permuted_stack(X, perm_idx, center=True)
+        t32 = self.tstat(stack)
+        P, C, ld = t32.shape
+        mx, status, maps = self.plan.run(t32.view(P * C, ld), two_sided=self.two_sided, want_maps=want_maps)
+        mx = mx.view(P, C, self.plan.S, 2)
+        self.last_status = status
+        if want_maps:
+            return mx, t32, maps
+        return self._download(mx) if download else mx
+
+    def sobelz(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", want_f64=False):
+        """Fused two-fit Sobel-family z for a block of shuffles (pyfunc.py:130-162).
+        Returns CUDA float32 [P, ld] (and float64 when want_f64)."""
+        import torch
+        n = self.Y.n
+        pred_x = np.asarray(pred_x, dtype=np.float64).reshape(n)
+        depend_y = np.asarray(depend_y, dtype=np.float64).reshape(n)
+        perm_idx = np.asarray(perm_idx)
+        P = perm_idx.shape[0]
+        xp = pred_x[perm_idx]                                       # [P, n]
+        ones = np.ones((P, n))
+        ta_scalar = None
+        if medtype in ("M", "I"):
+            dep = np.broadcast_to(depend_y, (P, n))
+            XA = np.stack([ones, xp], axis=2)
+            XB = np.stack([ones, dep, xp], axis=2) if medtype == "M" else np.stack([ones, xp, dep], axis=2)
+        elif medtype == "Y":
+            from scipy.stats import linregress
+            dep = depend_y[perm_idx]
+            ta_scalar = np.empty(P, dtype=np.float64)
+            for p in range(P):                                       # scalar path A, pyfunc.py:142
+                res = linregress(xp[p], dep[p])
+                ta_scalar[p] = res[0] / res[4]
+            XA = None
+            XB = np.stack([ones, dep, xp], axis=2)
+        else:
+            raise ValueError("Invalid mediation type")
+        sB = design_stack(XB, center=True)
+        if XA is not None:
+            sA = design_stack(XA, center=True)
+            rA = sA["r"]
+            pinv = np.concatenate([sA["pinv"], sB["pinv"]], axis=1)
+        else:
+            sA, rA = None, 0
+            pinv = sB["pinv"]
+        rB = sB["r"]
+        rp = _rp_for(rA + rB)
+        At, ldA = pack_At(pinv, rp)
+        At_d = self._upload("med_At", At)
+        GA_d = self._upload("med_GA", sA["G"]) if sA else None
+        dA_d = self._upload("med_dA", sA["d"]) if sA else None
+        GB_d = self._upload("med_GB", sB["G"])
+        dB_d = self._upload("med_dB", sB["d"])
+        ta_d = self._upload("med_ta", ta_scalar) if ta_scalar is not None else None
+        yy = self.Y.sumsq(True)
+        z32 = torch.empty((P, self.Y.ld), dtype=torch.float32, device=self.device)
+        z64 = torch.empty((P, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
+        algc = {"aroian": 0, "sobel": 1, "goodman": 2}.get(alg)
+        if algc is None:
+            raise ValueError("Unknown indirect test algorithm")
+        _lib.check(_lib.lib().tmb_sobelz(
+            _lib.ptr(self.Y.t), self.Y.dtype_code, n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA, rp,
+            _lib.ptr(GA_d), _lib.ptr(dA_d), rA, 0, sA["dof"] if sA else 1.0, _lib.ptr(GB_d), _lib.ptr(dB_d), rB, 0,
+            sB["dof"], _lib.ptr(yy), _lib.ptr(ta_d), P, algc, _lib.ptr(z32), _lib.ptr(z64), self.Y.ld,
+            _lib.current_stream()))
+        return (z32, z64) if want_f64 else z32
+
+    def mediation_block(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", want_maps=False, download=True):
+        """Sobel-z + one-sided TFCE + scaled max for a block of shuffles
+        (vertex_tfce_mediation_randomise.py:80-91, pyfunc.py:130-162).  Returns float32 [P, S]."""
+        z32 = self.sobelz(medtype, pred_x, depend_y, perm_idx, alg)
+        mx, status, maps = self.plan.run(z32, two_sided=False, want_maps=want_maps)
+        self.last_status = status
+        mx = mx[:, :, 0]
+        if want_maps:
+            return mx, z32, maps
+        return self._download(mx) if download else mx
+
+
+def sobelz_single(medtype, pred_x, depend_y, merge_y, alg="aroian"):
+    """calc_sobelz drop-in body: one design (identity permutation), float64 [V] on the host."""
+    merge_y = np.asarray(merge_y)
+    eng = PermutationEngine(merge_y, None)
+    n = eng.Y.n
+    _, z64 = eng.sobelz(medtype, pred_x, depend_y, np.arange(n)[None, :], alg, want_f64=True)
+    return to_host(z64[0, :eng.Y.V])
