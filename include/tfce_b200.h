@@ -90,6 +90,23 @@ int tmb_plan_destroy(tmb_plan *p);
 int tmb_plan_run(tmb_plan *p, const float *stat_dev, int64_t ld, int B, int two_sided, float *max_dev,
                  float *tfce_pos_dev, float *tfce_neg_dev, int32_t *status_dev, void *stream);
 
+/* Exact-libm mode.  The reference evaluates the height term with std::pow(float,float) (fast_tfce.hpp:70),
+ * i.e. the host C library's powf, which is NOT correctly rounded: about 6 in 10^4 thresholds differ from
+ * the exact square by one ulp, so bit-identical TFCE values require that very function.
+ *   tmb_plan_maxima:       max_dev[(b*S+s)*2 + sign] = max of +stat / -stat over surface s of row b (NaN ignored)
+ *   tmb_threshold_tables:  HOST function; for each maximum builds the reference's threshold sequence
+ *                          (T_0 = max, T_{i+1} = T_i - max/100 while T_i >= 0, fast_tfce.hpp:32-39) and
+ *                          HH_i = powf(T_i, H) into rows of 128 floats, plus step count, delta and TMB_MAP_* status
+ *   tmb_plan_run_tables:   tmb_plan_run consuming those tables (device copies) instead of computing
+ *                          correctly rounded ones on the device.
+ * tmb_tfce_run and tmb_tfce_components always use host tables (they have the host image anyway). */
+int tmb_plan_maxima(tmb_plan *p, const float *stat_dev, int64_t ld, int B, float *max_dev, void *stream);
+int tmb_threshold_tables(const float *maxima_host, const float *H_host, int count, int32_t *ns_host,
+                         float *delta_host, float *T_host, float *HH_host, int32_t *status_host);
+int tmb_plan_run_tables(tmb_plan *p, const float *stat_dev, int64_t ld, int B, int two_sided, const int32_t *ns_dev,
+                        const float *delta_dev, const float *T_dev, const float *HH_dev, const int32_t *tstatus_dev,
+                        float *max_dev, float *tfce_pos_dev, float *tfce_neg_dev, int32_t *status_dev, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Permuted-design fit + t.  Replaces cynumstats.pyx:28-29 cy_lin_lstsqr_mat, :47-52 se_of_slope,
  * :59-64 tval_int (and :66-74 calc_beta_se) for P designs at once.

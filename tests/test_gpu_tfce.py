@@ -173,3 +173,22 @@ def test_plan_two_sided_max_and_maps_bitexact():
             assert mx[b, s, 0] == want[0] and mx[b, s, 1] == want[1]
             assert np.array_equal(pos[b, off:off + V], oracle.tfce_run(H, E, csr, x))
             assert np.array_equal(neg[b, off:off + V], oracle.tfce_run(H, E, csr, -x))
+
+
+def test_plan_device_tables_match_correctly_rounded_oracle():
+    """exact_pow=False builds the threshold tables on the device with a correctly rounded height term;
+    checked bit-exactly against the oracle's correctly-rounded variant, and against the libm oracle within
+    the north_star tolerance (1e-5 relative; measured <= 2e-7)."""
+    import torch
+    from tfce_mediation_b200.engine import Surface, TfcePlan
+    _, _, csr = helpers.ico(5)
+    V = csr[0].shape[0] - 1
+    plan = TfcePlan([Surface(_adjset(2, 0.67, csr), 0)])
+    B = 6
+    stat = np.stack([helpers.smooth_map(csr, 100 + b, b % 4) for b in range(B)])
+    mx, status, (pos, neg) = plan.run(torch.from_numpy(stat).cuda(), two_sided=True, want_maps=True, exact_pow=False)
+    pos, neg = pos.cpu().numpy(), neg.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(pos[b], oracle.tfce_run(2, 0.67, csr, stat[b], correctly_rounded_height=True))
+        assert np.array_equal(neg[b], oracle.tfce_run(2, 0.67, csr, -stat[b], correctly_rounded_height=True))
+        np.testing.assert_allclose(pos[b], oracle.tfce_run(2, 0.67, csr, stat[b]), rtol=1e-5)

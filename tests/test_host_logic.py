@@ -1,0 +1,135 @@
+"""CPU: host-side logic of the product (no GPU compute) and the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from tests import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from tfce_mediation_b200 import _lib
+    L = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "tfce_b200.h")).read()
+    declared = set(re.findall(r"\b(tmb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.tmb_abi_version() == 1
+    assert isinstance(L.tmb_device_count(), int)
+    assert L.tmb_last_error() is not None
+
+
+def test_no_cpu_fallback_without_device():
+    from tfce_mediation_b200 import _lib
+    if _lib.lib().tmb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    from tfce_mediation_b200.tfce import CreateAdjSet
+    with pytest.raises(_lib.TmbError, match="no CPU fallback"):
+        CreateAdjSet(2, 1, [[1], [0]])
+    from tfce_mediation_b200 import cynumstats
+    with pytest.raises(_lib.TmbError):
+        cynumstats.tval_int(np.ones((3, 1)), np.ones((1, 1)), np.ones((3, 2), dtype=np.float32), 3, 1, 2)
+
+
+def test_graph_create_validates_on_host():
+    from tfce_mediation_b200 import _lib
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    indptr = np.array([0, 1, 2], dtype=np.int64)
+    bad = np.array([1, 5], dtype=np.int32)
+    rc = L.tmb_graph_create(0, 2, _lib.ptr(indptr), _lib.ptr(bad), 2.0, 1.0, ctypes.byref(h))
+    assert rc != 0 and b"out of range" in L.tmb_last_error()
+    bad_ptr = np.array([0, 2, 1], dtype=np.int64)
+    rc = L.tmb_graph_create(0, 2, _lib.ptr(bad_ptr), _lib.ptr(bad), 2.0, 1.0, ctypes.byref(h))
+    assert rc != 0 and b"monotone" in L.tmb_last_error()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "tfce_mediation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), f
+                assert "libtfce_oracle" not in src, f
+
+
+def test_adjacency_to_csr_accepts_lists_sets_arrays():
+    from tfce_mediation_b200._graph import adjacency_to_csr, csr_to_lists
+    adj = helpers.grid_csr(5, 4)
+    p, i = adjacency_to_csr(adj)
+    op, oi = oracle.adjacency_to_csr(adj)
+    assert np.array_equal(p, op) and np.array_equal(i, oi)
+    assert csr_to_lists(p, i) == adj
+    p2, i2 = adjacency_to_csr([set(a) for a in adj])
+    assert np.array_equal(p2, p) and sorted(i2.tolist()) == sorted(i.tolist())
+    arr = np.empty(len(adj), dtype=object)
+    for j, a in enumerate(adj):
+        arr[j] = np.array(a)
+    p3, i3 = adjacency_to_csr(arr)
+    assert np.array_equal(i3, i)
+    pe, ie = adjacency_to_csr([[], [], []])
+    assert pe.tolist() == [0, 0, 0, 0] and ie.shape == (0,)
+    with pytest.raises(ValueError):
+        adjacency_to_csr([[3], [0]])
+
+
+def test_induced_subgraph_preserves_tfce_of_kept_vertices():
+    from tfce_mediation_b200._graph import induced_subgraph
+    _, _, csr = helpers.ico(3)
+    V = csr[0].shape[0] - 1
+    rs = np.random.RandomState(0)
+    keep = rs.rand(V) < 0.8
+    sub = induced_subgraph(csr[0], csr[1], keep)
+    img = helpers.smooth_map(csr, 3, 2)
+    full = np.where(keep, img, 0).astype(np.float32)        # masked-out vertices carry 0 (pyfunc.py:108-113)
+    want = oracle.tfce_run(2, 0.67, csr, full)[keep]
+    got = oracle.tfce_run(2, 0.67, sub, np.ascontiguousarray(img[keep]))
+    assert np.array_equal(got, want)
+
+
+def test_design_stack_centering_is_exact_to_fp64_noise():
+    from tfce_mediation_b200.engine import design_stack, pack_At, row_permuted_stack
+    rs = np.random.RandomState(1)
+    n, V, k, P = 50, 400, 4, 5
+    y = (rs.standard_normal((n, V)) + 3.0).astype(np.float32)
+    X = np.column_stack([np.ones(n), rs.standard_normal((n, k - 1))])
+    idx = np.stack([rs.permutation(n) for _ in range(P)])
+    a = row_permuted_stack(X, idx)
+    b = design_stack(np.stack([X[i] for i in idx]))
+    np.testing.assert_allclose(a["pinv"], b["pinv"], rtol=1e-10, atol=1e-14)
+    yc = y.astype(np.float64)
+    yy = ((yc - yc.mean(0)) ** 2).sum(0)
+    for p in range(P):
+        nx = X[idx[p]]
+        want = oracle.tval_int(nx, np.linalg.inv(nx.T @ nx), y, n, k, V)[1:]
+        beta = a["pinv"][p] @ yc
+        sse = yy - np.einsum("iv,ij,jv->v", beta, a["G"][p], beta)
+        se = np.sqrt(sse / a["dof"] * a["d"][p][:, None]).astype(np.float32)
+        t = beta / se
+        assert np.all(np.abs(t - want) <= 1e-10 * np.maximum(1, np.abs(want)))
+        assert np.mean(t.astype(np.float32) != want.astype(np.float32)) < 1e-3
+    At, ldA = pack_At(a["pinv"], 4)
+    assert ldA % 64 == 0 and At.shape == (n, ldA)
+    assert np.array_equal(At[:, 4 * 2 + 1], a["pinv"][2, 1]) and not At[:, 4 * 2 + 3].any()
+
+
+def test_synth_shapes():
+    from tfce_mediation_b200 import synth
+    v, f = synth.icosphere(3)
+    assert v.shape == (642, 3) and f.shape == (1280, 3)
+    csr = synth.faces_to_csr(642, f)
+    deg = np.diff(csr[0])
+    assert deg.min() == 5 and deg.max() == 6 and csr[1].shape[0] == 3840
+    ref = oracle.vertex_adjacency(642, f)
+    assert all(set(csr[1][csr[0][i]:csr[0][i + 1]].tolist()) == ref[i] for i in range(642))
+    k2 = synth.kring_csr(csr, 2)
+    assert np.diff(k2[0]).min() > 6
+    assert synth.cap_mask(v, 600).sum() == 600

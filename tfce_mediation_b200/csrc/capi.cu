@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -36,10 +37,14 @@ struct tmb_graph {
     int64_t *d_indptr = nullptr;
     int32_t *d_indices = nullptr;
     double *d_powE = nullptr;
+    int32_t *d_vmap = nullptr;          // internal -> caller index (nullptr: identity)
+    std::vector<int32_t> vmap;          // host copy
+    bool symmetric = true;
     tmb_plan *self_plan = nullptr; // lazily created single-surface plan for tmb_tfce_run
     float *d_image = nullptr, *d_enhn = nullptr;
     int32_t *d_labels = nullptr, *d_extents = nullptr, *d_status = nullptr;
     float *d_thr = nullptr;
+    char *d_tabs = nullptr; // [ns(2) | status(2) | delta(2) | T(2x128) | HH(2x128)] for the single-map entry points
 };
 
 struct tmb_plan {
@@ -55,6 +60,7 @@ struct tmb_plan {
     char *d_workspace = nullptr;
     size_t slot_stride = 0;
     int *d_counter = nullptr;
+    unsigned long long *d_timing = nullptr; // TMB_PHASE_TIMING=1: per-phase cycle totals
 };
 
 extern "C" const char *tmb_last_error(void) { return g_error.c_str(); }
@@ -70,9 +76,58 @@ extern "C" int tmb_device_count(void) {
     return n;
 }
 
+
+// ---- host-side graph analysis (one-time, at CreateAdjSet construction) ---------------------------
+// Symmetric adjacency lets the sweep compare activation levels only; otherwise the reference's
+// directional rule (fast_tfce.hpp:47-65) is honoured with value comparisons.
+static bool csr_is_symmetric(int32_t V, const int64_t *indptr, const int32_t *indices) {
+    std::vector<int32_t> sorted(indices, indices + indptr[V]);
+    for (int32_t v = 0; v < V; ++v) std::sort(sorted.begin() + indptr[v], sorted.begin() + indptr[v + 1]);
+    for (int32_t u = 0; u < V; ++u)
+        for (int64_t e = indptr[u]; e < indptr[u + 1]; ++e) {
+            const int32_t a = indices[e];
+            if (a == u) continue;
+            if (!std::binary_search(sorted.begin() + indptr[a], sorted.begin() + indptr[a + 1], u)) return false;
+        }
+    return true;
+}
+
+// Reverse Cuthill-McKee ordering: neighbours end up close in index, so the random parent/level
+// lookups of one warp fall into a few cache lines.  Pure relabelling: TFCE values do not depend on
+// vertex numbering for symmetric graphs.  Returns internal -> caller index.
+static std::vector<int32_t> rcm_order(int32_t V, const int64_t *indptr, const int32_t *indices) {
+    std::vector<int32_t> order;
+    order.reserve(V);
+    std::vector<char> seen(V, 0);
+    std::vector<int32_t> by_degree(V);
+    std::iota(by_degree.begin(), by_degree.end(), 0);
+    auto deg = [&](int32_t v) { return indptr[v + 1] - indptr[v]; };
+    std::stable_sort(by_degree.begin(), by_degree.end(), [&](int32_t a, int32_t b) { return deg(a) < deg(b); });
+    std::vector<int32_t> nb;
+    for (int32_t start : by_degree) {
+        if (seen[start]) continue;
+        seen[start] = 1;
+        size_t head = order.size();
+        order.push_back(start);
+        while (head < order.size()) {
+            const int32_t v = order[head++];
+            nb.clear();
+            for (int64_t e = indptr[v]; e < indptr[v + 1]; ++e) {
+                const int32_t a = indices[e];
+                if (!seen[a]) { seen[a] = 1; nb.push_back(a); }
+            }
+            std::sort(nb.begin(), nb.end(), [&](int32_t a, int32_t b) { return deg(a) != deg(b) ? deg(a) < deg(b) : a < b; });
+            order.insert(order.end(), nb.begin(), nb.end());
+        }
+    }
+    std::reverse(order.begin(), order.end());
+    return order;
+}
+
 extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, const int32_t *indices, float H,
                                 float E, tmb_graph **out) {
     TMB_REQUIRE(out && indptr && V > 0, "tmb_graph_create: bad arguments (V=%d)", V);
+    TMB_REQUIRE(V < 0x00FFFFFF, "tmb_graph_create: at most %d vertices per graph are supported", 0x00FFFFFF - 1);
     TMB_REQUIRE(indptr[0] == 0, "tmb_graph_create: indptr[0] must be 0");
     for (int32_t v = 0; v < V; ++v)
         TMB_REQUIRE(indptr[v + 1] >= indptr[v], "tmb_graph_create: indptr not monotone at %d", v);
@@ -84,6 +139,29 @@ extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, co
     TMB_CUDA(cudaSetDevice(device));
     tmb_graph *g = new tmb_graph();
     g->device = device; g->V = V; g->nnz = nnz; g->H = H; g->E = E;
+    g->symmetric = csr_is_symmetric(V, indptr, indices);
+    // locality reordering (symmetric graphs only; TMB_NO_REORDER=1 disables it for A/B measurements)
+    const char *no_reorder = getenv("TMB_NO_REORDER");
+    std::vector<int64_t> r_indptr;
+    std::vector<int32_t> r_indices;
+    const int64_t *use_indptr = indptr;
+    const int32_t *use_indices = indices;
+    if (g->symmetric && !(no_reorder && no_reorder[0] == '1') && nnz > 0) {
+        g->vmap = rcm_order(V, indptr, indices);
+        std::vector<int32_t> inv(V);
+        for (int32_t i = 0; i < V; ++i) inv[g->vmap[i]] = i;
+        r_indptr.assign((size_t)V + 1, 0);
+        r_indices.resize((size_t)nnz);
+        for (int32_t i = 0; i < V; ++i) r_indptr[i + 1] = r_indptr[i] + (indptr[g->vmap[i] + 1] - indptr[g->vmap[i]]);
+        for (int32_t i = 0; i < V; ++i) {
+            const int32_t o = g->vmap[i];
+            int64_t w = r_indptr[i];
+            for (int64_t e = indptr[o]; e < indptr[o + 1]; ++e) r_indices[w++] = inv[indices[e]];
+            std::sort(r_indices.begin() + r_indptr[i], r_indices.begin() + r_indptr[i + 1]);
+        }
+        use_indptr = r_indptr.data();
+        use_indices = r_indices.data();
+    }
     // pow(n, E) table with the host C library: identical to the reference's
     // pow(c->size(), E) double overload (fast_tfce.hpp:77)
     std::vector<double> powE((size_t)V + 1);
@@ -98,12 +176,17 @@ extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, co
     if ((e = cudaMalloc(&g->d_indices, sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1))) != cudaSuccess)
         return fail("malloc", e);
     if ((e = cudaMalloc(&g->d_powE, sizeof(double) * ((size_t)V + 1))) != cudaSuccess) return fail("malloc", e);
-    if ((e = cudaMemcpy(g->d_indptr, indptr, sizeof(int64_t) * ((size_t)V + 1), cudaMemcpyHostToDevice)) != cudaSuccess)
+    if ((e = cudaMemcpy(g->d_indptr, use_indptr, sizeof(int64_t) * ((size_t)V + 1), cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail("memcpy", e);
-    if (nnz && (e = cudaMemcpy(g->d_indices, indices, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice)) != cudaSuccess)
+    if (nnz && (e = cudaMemcpy(g->d_indices, use_indices, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail("memcpy", e);
     if ((e = cudaMemcpy(g->d_powE, powE.data(), sizeof(double) * ((size_t)V + 1), cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail("memcpy", e);
+    if (!g->vmap.empty()) {
+        if ((e = cudaMalloc(&g->d_vmap, sizeof(int32_t) * (size_t)V)) != cudaSuccess) return fail("malloc", e);
+        if ((e = cudaMemcpy(g->d_vmap, g->vmap.data(), sizeof(int32_t) * (size_t)V, cudaMemcpyHostToDevice)) != cudaSuccess)
+            return fail("memcpy", e);
+    }
     *out = g;
     return 0;
 }
@@ -112,9 +195,9 @@ extern "C" int tmb_graph_destroy(tmb_graph *g) {
     if (!g) return 0;
     cudaSetDevice(g->device);
     if (g->self_plan) tmb_plan_destroy(g->self_plan);
-    cudaFree(g->d_indptr); cudaFree(g->d_indices); cudaFree(g->d_powE);
+    cudaFree(g->d_indptr); cudaFree(g->d_indices); cudaFree(g->d_powE); cudaFree(g->d_vmap);
     cudaFree(g->d_image); cudaFree(g->d_enhn); cudaFree(g->d_labels); cudaFree(g->d_extents);
-    cudaFree(g->d_status); cudaFree(g->d_thr);
+    cudaFree(g->d_status); cudaFree(g->d_thr); cudaFree(g->d_tabs);
     delete g;
     return 0;
 }
@@ -149,8 +232,16 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { set_error("tmb_plan_create: %s", cudaGetErrorString(e)); delete p; return 1; }
-    p->num_slots = max_slots > 0 ? max_slots : prop.multiProcessorCount * 2;
     p->slot_stride = tfce_slot_bytes(p->Vmax);
+    p->num_slots = max_slots > 0 ? max_slots : prop.multiProcessorCount * 2;
+    {   // keep the workspace within a quarter of the free HBM (huge merged graphs get fewer slots)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t budget = free_b / 4;
+            const size_t fit = std::max<size_t>(1, budget / std::max<size_t>(p->slot_stride, 1));
+            if ((size_t)p->num_slots > fit) p->num_slots = (int)fit;
+        }
+    }
     auto fail = [&](const char *what, cudaError_t err) {
         set_error("tmb_plan_create: %s: %s", what, cudaGetErrorString(err));
         tmb_plan_destroy(p);
@@ -159,15 +250,26 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
     for (int s = 0; s < S; ++s) {
         const tmb_graph *g = graphs[s];
         if (weight_host && weight_host[s]) {
+            std::vector<float> w(weight_host[s], weight_host[s] + g->V);
+            if (!g->vmap.empty())
+                for (int32_t i = 0; i < g->V; ++i) w[i] = weight_host[s][g->vmap[i]];
             if ((e = cudaMalloc(&p->d_weights[s], sizeof(float) * (size_t)g->V)) != cudaSuccess) return fail("malloc", e);
-            if ((e = cudaMemcpy(p->d_weights[s], weight_host[s], sizeof(float) * (size_t)g->V, cudaMemcpyHostToDevice)) != cudaSuccess)
+            if ((e = cudaMemcpy(p->d_weights[s], w.data(), sizeof(float) * (size_t)g->V, cudaMemcpyHostToDevice)) != cudaSuccess)
                 return fail("memcpy", e);
         }
-        descs[s] = SurfDesc{g->d_indptr, g->d_indices, g->d_powE, p->d_weights[s], col_offset[s], g->V, g->H};
+        descs[s] = SurfDesc{g->d_indptr, g->d_indices, g->d_powE, p->d_weights[s], g->d_vmap, col_offset[s], g->V, g->H,
+                            g->symmetric ? 0 : 1};
     }
     if ((e = cudaMalloc(&p->d_surfs, sizeof(SurfDesc) * S)) != cudaSuccess) return fail("malloc", e);
     if ((e = cudaMalloc(&p->d_order, sizeof(int32_t) * S)) != cudaSuccess) return fail("malloc", e);
     if ((e = cudaMalloc(&p->d_counter, sizeof(int))) != cudaSuccess) return fail("malloc", e);
+    {
+        const char *pt = getenv("TMB_PHASE_TIMING");
+        if (pt && pt[0] == '1') {
+            if ((e = cudaMalloc(&p->d_timing, sizeof(unsigned long long) * 8)) != cudaSuccess) return fail("malloc", e);
+            cudaMemset(p->d_timing, 0, sizeof(unsigned long long) * 8);
+        }
+    }
     if ((e = cudaMalloc(&p->d_workspace, p->slot_stride * (size_t)p->num_slots)) != cudaSuccess) return fail("malloc workspace", e);
     if ((e = cudaMemcpy(p->d_surfs, descs.data(), sizeof(SurfDesc) * S, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("memcpy", e);
     if ((e = cudaMemcpy(p->d_order, order.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("memcpy", e);
@@ -178,21 +280,42 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
 extern "C" int tmb_plan_destroy(tmb_plan *p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
+    if (p->d_timing) {
+        unsigned long long t[8];
+        if (cudaMemcpy(t, p->d_timing, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            static const char *names[7] = {"tables", "levels+sort", "X: P2bc+P1", "Y: P2a", "tail", "node walk", "finalize"};
+            double tot = 0;
+            for (int i = 0; i < 7; ++i) tot += (double)t[i];
+            fprintf(stderr, "[tmb phase timing] total %.3e cycles, nodes %llu\n", tot, t[7]);
+            for (int i = 0; i < 7; ++i) fprintf(stderr, "  %-12s %6.2f%%\n", names[i], tot > 0 ? 100.0 * t[i] / tot : 0.0);
+        }
+        cudaFree(p->d_timing);
+    }
     for (float *w : p->d_weights) cudaFree(w);
     cudaFree(p->d_surfs); cudaFree(p->d_order); cudaFree(p->d_counter); cudaFree(p->d_workspace);
     delete p;
     return 0;
 }
 
+struct TableSet {
+    const int32_t *ns = nullptr;
+    const float *delta = nullptr;
+    const float *T = nullptr;
+    const float *HH = nullptr;
+    const int32_t *status = nullptr;
+};
+
 static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int two_sided, int accumulate,
                        float *max_dev, float *tfce_pos, float *tfce_neg, int32_t *status, int stop_level,
-                       int32_t *labels, int32_t *extents, float *thr, cudaStream_t stream) {
+                       int32_t *labels, int32_t *extents, float *thr, cudaStream_t stream,
+                       const TableSet *tabs = nullptr) {
     SweepParams sp{};
+    if (tabs) { sp.tab_ns = tabs->ns; sp.tab_delta = tabs->delta; sp.tab_T = tabs->T; sp.tab_HH = tabs->HH; sp.tab_status = tabs->status; }
     sp.surfs = p->d_surfs; sp.surf_order = p->d_order; sp.S = p->S; sp.B = B; sp.two_sided = two_sided;
     sp.accumulate = accumulate; sp.stat = stat; sp.ld = ld; sp.max_out = max_dev; sp.tfce_pos = tfce_pos;
     sp.tfce_neg = tfce_neg; sp.status = status; sp.stop_level = stop_level; sp.labels = labels;
     sp.extents = extents; sp.threshold_out = thr; sp.workspace = p->d_workspace; sp.slot_stride = p->slot_stride;
-    sp.Vmax = p->Vmax; sp.work_counter = p->d_counter;
+    sp.Vmax = p->Vmax; sp.work_counter = p->d_counter; sp.timing = p->d_timing;
     return launch_tfce_sweep(sp, p->num_slots, stream);
 }
 
@@ -208,6 +331,63 @@ extern "C" int tmb_plan_run(tmb_plan *p, const float *stat_dev, int64_t ld, int 
                        nullptr, nullptr, (cudaStream_t)stream);
 }
 
+
+// Threshold sequence and height terms of fast_tfce.hpp:32-39,70 computed on the HOST with the very
+// call the reference compiles to (std::pow(float, float) == libm powf, which is not correctly
+// rounded: about 6 in 10^4 thresholds differ from the exact square by one ulp).
+static void host_tables(float mx, float H, int32_t *ns_out, float *delta_out, float *T, float *HH,
+                        int32_t *status_out) {
+    int ns = 0, st = 0;
+    volatile float d = 0.f;
+    if (mx >= 0.f) {
+        d = mx / 100;
+        if (d == 0.f) {
+            st = TMB_MAP_MAX_IS_ZERO;
+        } else {
+            for (volatile float t = mx; t >= 0.f; t -= d) {
+                if (ns == 128) { st = TMB_MAP_STEP_OVERFLOW; ns = 0; break; }
+                const float tc = t;
+                T[ns] = tc;
+                HH[ns] = std::pow(tc, H);
+                ++ns;
+            }
+        }
+    }
+    *ns_out = ns; *delta_out = d; *status_out = st;
+}
+
+extern "C" int tmb_threshold_tables(const float *maxima_host, const float *H_host, int count, int32_t *ns_host,
+                                    float *delta_host, float *T_host, float *HH_host, int32_t *status_host) {
+    TMB_REQUIRE(maxima_host && H_host && ns_host && delta_host && T_host && HH_host && status_host && count >= 0,
+                "tmb_threshold_tables: bad arguments");
+    for (int i = 0; i < count; ++i)
+        host_tables(maxima_host[i], H_host[i], ns_host + i, delta_host + i, T_host + (size_t)i * 128,
+                    HH_host + (size_t)i * 128, status_host + i);
+    return 0;
+}
+
+extern "C" int tmb_plan_maxima(tmb_plan *p, const float *stat_dev, int64_t ld, int B, float *max_dev, void *stream) {
+    TMB_REQUIRE(p && stat_dev && max_dev && B >= 0, "tmb_plan_maxima: bad arguments");
+    TMB_CUDA(cudaSetDevice(p->device));
+    return launch_tfce_maxima(p->d_surfs, p->S, stat_dev, ld, B, max_dev, (cudaStream_t)stream);
+}
+
+extern "C" int tmb_plan_run_tables(tmb_plan *p, const float *stat_dev, int64_t ld, int B, int two_sided,
+                                   const int32_t *ns_dev, const float *delta_dev, const float *T_dev,
+                                   const float *HH_dev, const int32_t *tstatus_dev, float *max_dev,
+                                   float *tfce_pos_dev, float *tfce_neg_dev, int32_t *status_dev, void *stream) {
+    TMB_REQUIRE(p && stat_dev && B >= 0 && ns_dev && delta_dev && T_dev && HH_dev && tstatus_dev,
+                "tmb_plan_run_tables: bad arguments");
+    TMB_REQUIRE(max_dev || tfce_pos_dev || tfce_neg_dev, "tmb_plan_run_tables: no output requested");
+    for (int s = 0; s < p->S; ++s)
+        TMB_REQUIRE(p->col_offset[s] + p->graphs[s]->V <= ld, "tmb_plan_run_tables: surface %d exceeds row length %lld",
+                    s, (long long)ld);
+    TMB_CUDA(cudaSetDevice(p->device));
+    TableSet t; t.ns = ns_dev; t.delta = delta_dev; t.T = T_dev; t.HH = HH_dev; t.status = tstatus_dev;
+    return plan_launch(p, stat_dev, ld, B, two_sided, 0, max_dev, tfce_pos_dev, tfce_neg_dev, status_dev, -1, nullptr,
+                       nullptr, nullptr, (cudaStream_t)stream, &t);
+}
+
 static int ensure_self_plan(tmb_graph *g) {
     if (g->self_plan) return 0;
     TMB_CUDA(cudaSetDevice(g->device));
@@ -220,6 +400,24 @@ static int ensure_self_plan(tmb_graph *g) {
     TMB_CUDA(cudaMalloc(&g->d_extents, sizeof(int32_t) * (size_t)g->V));
     TMB_CUDA(cudaMalloc(&g->d_status, sizeof(int32_t) * 2));
     TMB_CUDA(cudaMalloc(&g->d_thr, sizeof(float)));
+    TMB_CUDA(cudaMalloc(&g->d_tabs, sizeof(int32_t) * 4 + sizeof(float) * (2 + 4 * 128)));
+    return 0;
+}
+
+// tables for ONE host image (positive side only): exact libm arithmetic, uploaded to g->d_tabs
+static int upload_single_tables(tmb_graph *g, const float *image_host, TableSet *t) {
+    float mx = -INFINITY;
+    for (int32_t v = 0; v < g->V; ++v) mx = std::fmax(mx, image_host[v]); // fmax ignores NaN
+    struct { int32_t ns[2]; int32_t st[2]; float delta[2]; float T[2][128]; float HH[2][128]; } h;
+    memset(&h, 0, sizeof(h));
+    host_tables(mx, g->H, &h.ns[0], &h.delta[0], h.T[0], h.HH[0], &h.st[0]);
+    TMB_CUDA(cudaMemcpy(g->d_tabs, &h, sizeof(h), cudaMemcpyHostToDevice));
+    char *base = g->d_tabs;
+    t->ns = reinterpret_cast<const int32_t *>(base);
+    t->status = reinterpret_cast<const int32_t *>(base + sizeof(int32_t) * 2);
+    t->delta = reinterpret_cast<const float *>(base + sizeof(int32_t) * 4);
+    t->T = reinterpret_cast<const float *>(base + sizeof(int32_t) * 4 + sizeof(float) * 2);
+    t->HH = t->T + 2 * 128;
     return 0;
 }
 
@@ -229,9 +427,15 @@ extern "C" int tmb_tfce_run(tmb_graph *g, const float *image_host, float *enhn_h
     const size_t bytes = sizeof(float) * (size_t)g->V;
     TMB_CUDA(cudaMemcpy(g->d_image, image_host, bytes, cudaMemcpyHostToDevice));
     TMB_CUDA(cudaMemcpy(g->d_enhn, enhn_host, bytes, cudaMemcpyHostToDevice));
-    // one-sided, accumulate into enhn like the reference's `enhn[v] += increment`
-    if (plan_launch(g->self_plan, g->d_image, g->V, 1, 0, 1, nullptr, g->d_enhn, nullptr, g->d_status, -1, nullptr,
-                    nullptr, nullptr, nullptr))
+    // one-sided; accumulate into enhn like the reference's `enhn[v] += increment`.  Callers always pass
+    // zeros (pyfunc.py:110-111,123): then the per-node walk is exact and cheaper; a non-zero enhn takes
+    // the per-vertex walk that starts every sum from enhn[v].
+    bool all_zero = true;
+    for (int32_t v = 0; v < g->V && all_zero; ++v) all_zero = (enhn_host[v] == 0.0f) && !std::signbit(enhn_host[v]);
+    TableSet tabs;
+    if (upload_single_tables(g, image_host, &tabs)) return 1;
+    if (plan_launch(g->self_plan, g->d_image, g->V, 1, 0, all_zero ? 0 : 1, nullptr, g->d_enhn, nullptr, g->d_status,
+                    -1, nullptr, nullptr, nullptr, nullptr, &tabs))
         return 1;
     TMB_CUDA(cudaMemcpy(enhn_host, g->d_enhn, bytes, cudaMemcpyDeviceToHost));
     int32_t st[2] = {0, 0};
@@ -246,11 +450,21 @@ extern "C" int tmb_tfce_components(tmb_graph *g, const float *image_host, int le
     if (ensure_self_plan(g)) return 1;
     const size_t bytes = sizeof(float) * (size_t)g->V;
     TMB_CUDA(cudaMemcpy(g->d_image, image_host, bytes, cudaMemcpyHostToDevice));
+    TableSet tabs;
+    if (upload_single_tables(g, image_host, &tabs)) return 1;
     if (plan_launch(g->self_plan, g->d_image, g->V, 1, 0, 0, nullptr, nullptr, nullptr, nullptr, level, g->d_labels,
-                    g->d_extents, g->d_thr, nullptr))
+                    g->d_extents, g->d_thr, nullptr, &tabs))
         return 1;
     TMB_CUDA(cudaMemcpy(labels_host, g->d_labels, sizeof(int32_t) * (size_t)g->V, cudaMemcpyDeviceToHost));
     TMB_CUDA(cudaMemcpy(extents_host, g->d_extents, sizeof(int32_t) * (size_t)g->V, cudaMemcpyDeviceToHost));
+    if (!g->vmap.empty()) {
+        // the kernel labels a component by its smallest INTERNAL index; canonical = smallest caller index
+        std::vector<int32_t> canon((size_t)g->V, INT32_MAX);
+        for (int32_t o = 0; o < g->V; ++o)
+            if (labels_host[o] >= 0) canon[labels_host[o]] = std::min(canon[labels_host[o]], o);
+        for (int32_t o = 0; o < g->V; ++o)
+            if (labels_host[o] >= 0) labels_host[o] = canon[labels_host[o]];
+    }
     if (threshold_out) TMB_CUDA(cudaMemcpy(threshold_out, g->d_thr, sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -36,10 +36,12 @@ struct SurfDesc {
     const int64_t *indptr;  // [V+1]
     const int32_t *indices; // [nnz]
     const double *powE;     // [V+1]  pow((double)n, (double)E) tabulated with the host libm
-    const float *weight;    // [V] or nullptr
+    const float *weight;    // [V] or nullptr (internal vertex order)
+    const int32_t *vmap;    // [V] internal (locality-reordered) index -> caller's index, or nullptr
     int64_t col_off;        // first column of this surface in a statistic row
     int32_t V;
     float H;
+    int32_t directed;       // adjacency is not symmetric: honour the reference's directional join rule
 };
 
 // per-launch parameters of the sweep kernel
@@ -61,6 +63,14 @@ struct SweepParams {
     int32_t *labels;
     int32_t *extents;
     float *threshold_out;
+    // optional host-computed threshold tables (exact libm powf, see tmb_threshold_tables):
+    // entry e = (b*S + s)*2 + sign;  T/HH rows of 128 floats
+    const int32_t *tab_ns;
+    const float *tab_delta;
+    const float *tab_T;
+    const float *tab_HH;
+    const int32_t *tab_status;
+    unsigned long long *timing; // optional [8] per-phase cycle totals (development aid), or nullptr
     // workspace
     char *workspace;
     size_t slot_stride;
@@ -69,6 +79,8 @@ struct SweepParams {
 };
 
 int launch_tfce_sweep(const SweepParams &p, int num_slots, cudaStream_t stream);
+int launch_tfce_maxima(const SurfDesc *surfs, int S, const float *stat, int64_t ld, int B, float *max_out,
+                       cudaStream_t stream);
 size_t tfce_slot_bytes(int32_t Vmax);
 
 } // namespace tmb

@@ -341,7 +341,12 @@ __global__ void glm_direct_kernel(DirectParams p) {
         for (int j = 0; j < kMaxK; ++j)
             if (j < k) beta[j] = __fma_rn(p.pinv[(size_t)j * n + i], y, beta[j]);
     }
+    // Sums follow the reference's evaluation order: Python/numpy add the rows one after another
+    // (cynumstats.pyx:34-35,61).  For float32 data the reference's TSS is float32 arithmetic
+    // ((y - np.mean(y))**2 stays float32), reproduced here with explicit fp32 ops.
     double sse = 0.0, tss = 0.0;
+    float tss32 = 0.f;
+    const float gm32 = (float)p.grand_mean;
     for (int i = 0; i < n; ++i) {
         double fit = 0.0;
 #pragma unroll
@@ -351,12 +356,17 @@ __global__ void glm_direct_kernel(DirectParams p) {
         const double res = y - fit;
         if (p.r64) p.r64[(size_t)i * p.ldr + v] = res;
         if (p.r32) p.r32[(size_t)i * p.ldr + v] = (float)res;
-        sse = __fma_rn(res, res, sse);
-        const double c = y - p.grand_mean;
-        tss = __fma_rn(c, c, tss);
+        sse = __dadd_rn(sse, __dmul_rn(res, res));
+        if (sizeof(YT) == 4) {
+            const float c = __fsub_rn((float)y, gm32);
+            tss32 = __fadd_rn(tss32, __fmul_rn(c, c));
+        } else {
+            const double c = y - p.grand_mean;
+            tss = __dadd_rn(tss, __dmul_rn(c, c));
+        }
     }
     if (p.sse) p.sse[v] = sse;
-    if (p.tss) p.tss[v] = tss;
+    if (p.tss) p.tss[v] = (sizeof(YT) == 4) ? (double)tss32 : tss;
     const double sigma2 = __ddiv_rn(sse, p.dof);
 #pragma unroll
     for (int j = 0; j < kMaxK; ++j) {

@@ -8,18 +8,25 @@
 //   * thresholds T_0 = max, T_{i+1} = fl32(T_i - fl32(max/100)) while T_i >= 0   (fast_tfce.hpp:32-39)
 //   * vertex v is active at step i iff x_v > T_i (strict)                         (:41)
 //   * a directed entry a of adjacency[u] joins u and a iff a was activated before u (:47-65);
-//     here "before" = larger value, ties broken by smaller index
+//     "before" = larger value, ties broken by smaller index.  For symmetric adjacency (checked on
+//     the host at graph creation) only activation LEVELS matter, which is what the fast path uses.
 //   * every component c of step i adds fl32( pow((double)|c|,(double)E) * (double)fl32(T_i^H) )
 //     to each member by a sequential fp32 add in descending-T order              (:70-84)
 // pow(|c|, E) comes from a table computed on the host with the C library, so increments are
 // bit-identical to the reference.
 //
-// Sweep (V1):  per level i
-//   P1  newly activated vertices hook into earlier-activated neighbours (lock-free union-find,
-//       larger root index under smaller; roots are therefore the smallest index of a component)
-//   P2  sizes: every new vertex adds 1 to its final root; every root hooked in this level adds
-//       its frozen size to its final root
-//   P3  every active vertex adds the increment of its component
+// Algorithm (V2).  Vertices are bucketed by activation level (counting sort).  Levels are swept in
+// order; per level only the NEWLY activated vertices do work:
+//   P1   hook new vertices into earlier-activated neighbours (lock-free union-find; larger root
+//        index under smaller, so a root is the smallest index of its component)
+//   P2a  sizes + component-tree bookkeeping: every component whose membership changed in this
+//        level gets a new tree node (size, level); warp-aggregated atomics
+//   P2bc links the previous nodes of merged/grown components to the new node and records each new
+//        vertex's leaf node.  It touches no union-find state, so it runs in the same barrier
+//        interval as P1 of the NEXT level: two __syncthreads per level.
+// The per-vertex TFCE value is then a walk from the vertex's leaf node to the root of the component
+// tree, adding one increment per level in the reference's order.  All vertices that share a leaf
+// share the value, so the walk is done once per node.  Nothing is visited per (vertex, level).
 #include "common.cuh"
 
 #include <cfloat>
@@ -28,11 +35,13 @@ namespace tmb {
 
 static constexpr int kSweepThreads = 512;
 static constexpr int kMaxSteps = 128;
+static constexpr int kNone = 0x00FFFFFF; // "no parent" in the 24-bit parent field of a node
+static constexpr int kPending = -2;
 
 __device__ __forceinline__ int ld_cg(const int *p) { return __ldcg(p); }
 
-// union-find with path halving.  All reads go to L2 (ld.cg) so they are coherent with the
-// atomicCAS hooks issued by other warps of the CTA.
+// union-find with path halving.  Reads go to L2 (ld.cg) so they are coherent with the atomicCAS
+// hooks issued by other warps of the CTA.
 __device__ __forceinline__ int uf_find(int *parent, int v) {
     int cur = v;
     int p = ld_cg(parent + cur);
@@ -47,27 +56,39 @@ __device__ __forceinline__ int uf_find(int *parent, int v) {
 
 struct SlotWs {
     int *parent;
-    int *size;
-    float *acc;
-    int *order;  // vertex | sign<<31, grouped by activation level
-    int *mlist;  // roots hooked during the current level
+    int *size;      // component size at its root; reused as float node values after the sweep
+    int *curnode;   // root -> node id of its component's current tree node
+    int *leaf;      // vertex -> leaf node (holds the root between P2a and P2bc)
+    int *order;     // vertices grouped by activation level
+    int2 *nodes;    // {size, (sign<<31)|(level<<24)|parent}
+    int2 *mlist[2]; // {hooked older root, its final root}   (double buffered across levels)
+    int2 *clist;    // {changed root, its previous node}
+    unsigned char *lev8; // activation level (bits 0..6) | sign (bit 7); 0 = never active
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 size_t tfce_slot_bytes(int32_t Vmax) {
-    size_t per = align_up(sizeof(int) * (size_t)Vmax, 256);
-    return per * 5;
+    const size_t per4 = align_up(sizeof(int) * (size_t)Vmax, 256);
+    const size_t per8 = align_up(sizeof(int2) * (size_t)Vmax, 256);
+    return per4 * 5 + per8 * 4 + align_up((size_t)Vmax, 256);
 }
 
 __device__ __forceinline__ SlotWs carve(char *base, int32_t Vmax) {
-    size_t per = align_up(sizeof(int) * (size_t)Vmax, 256);
+    const size_t per4 = align_up(sizeof(int) * (size_t)Vmax, 256);
+    const size_t per8 = align_up(sizeof(int2) * (size_t)Vmax, 256);
     SlotWs w;
     w.parent = reinterpret_cast<int *>(base);
-    w.size = reinterpret_cast<int *>(base + per);
-    w.acc = reinterpret_cast<float *>(base + 2 * per);
-    w.order = reinterpret_cast<int *>(base + 3 * per);
-    w.mlist = reinterpret_cast<int *>(base + 4 * per);
+    w.size = reinterpret_cast<int *>(base + per4);
+    w.curnode = reinterpret_cast<int *>(base + 2 * per4);
+    w.leaf = reinterpret_cast<int *>(base + 3 * per4);
+    w.order = reinterpret_cast<int *>(base + 4 * per4);
+    char *b8 = base + 5 * per4;
+    w.nodes = reinterpret_cast<int2 *>(b8);
+    w.mlist[0] = reinterpret_cast<int2 *>(b8 + per8);
+    w.mlist[1] = reinterpret_cast<int2 *>(b8 + 2 * per8);
+    w.clist = reinterpret_cast<int2 *>(b8 + 3 * per8);
+    w.lev8 = reinterpret_cast<unsigned char *>(b8 + 4 * per8);
     return w;
 }
 
@@ -75,6 +96,33 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// Sum of the increments along the component-tree path that starts at node j, in the reference's
+// order (descending threshold), starting from acc.
+__device__ __forceinline__ float walk_path(const int2 *__restrict__ nodes, const double *__restrict__ powE,
+                                           const float (*sHH)[kMaxSteps], const int *sNs, int j, float acc) {
+    int2 rec = nodes[j];
+    for (;;) {
+        const int pk = rec.y;
+        const int par = pk & kNone;
+        const int lv = (pk >> 24) & 0x7f;
+        const int sg = (pk >> 31) & 1;
+        int2 prec = make_int2(0, 0);
+        int endl;
+        if (par == kNone) {
+            endl = sNs[sg];
+        } else {
+            prec = nodes[par];
+            endl = (prec.y >> 24) & 0x7f;
+        }
+        const double pw = powE[rec.x];
+        const float *hh = sHH[sg];
+        for (int l = lv; l < endl; ++l) acc = __fadd_rn(acc, __double2float_rn(__dmul_rn(pw, (double)hh[l])));
+        if (par == kNone) break;
+        rec = prec;
+    }
+    return acc;
 }
 
 __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParams P) {
@@ -88,11 +136,12 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
     __shared__ float sRed[2][kSweepThreads / 32];
     __shared__ int sItem;
     __shared__ int sMcount[2];
+    __shared__ int sCcount[2];
 
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5;
-    SlotWs ws = carve(P.workspace + (size_t)blockIdx.x * P.slot_stride, P.Vmax);
+    const SlotWs ws = carve(P.workspace + (size_t)blockIdx.x * P.slot_stride, P.Vmax);
     const int total_items = P.B * P.S;
 
     for (;;) {
@@ -103,60 +152,88 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
         const int s = P.surf_order[item / P.B];
         const int b = item % P.B;
         const SurfDesc sd = P.surfs[s];
+        long long tk = P.timing ? clock64() : 0;
+#define TMB_TICK(i)                                                                  \
+        if (P.timing && tid == 0) {                                                  \
+            const long long now = clock64();                                         \
+            atomicAdd(P.timing + (i), (unsigned long long)(now - tk));               \
+            tk = now;                                                                \
+        }
         const int V = sd.V;
         const float *__restrict__ x = P.stat + (size_t)b * P.ld + sd.col_off;
         const int64_t *__restrict__ indptr = sd.indptr;
         const int32_t *__restrict__ indices = sd.indices;
+        const int32_t *__restrict__ vmap = sd.vmap; // internal (reordered) index -> caller's index, or null
+        const bool directed = sd.directed != 0;
 
-        // ---- maxima of +x and -x (NaN ignored: fmaxf returns the non-NaN operand) -------------
-        float mp = -INFINITY, mn = -INFINITY;
-        for (int v = tid; v < V; v += nthr) {
-            float xv = x[v];
-            mp = fmaxf(mp, xv);
-            mn = fmaxf(mn, -xv);
-        }
-        mp = warp_max(mp);
-        mn = warp_max(mn);
-        if (lane == 0) { sRed[0][wid] = mp; sRed[1][wid] = mn; }
         if (tid < kMaxSteps) sCount[tid] = 0;
-        if (tid == 0) { sMcount[0] = 0; sMcount[1] = 0; }
-        __syncthreads();
-        // ---- threshold tables: one thread per sign, same fp32 ops as fast_tfce.hpp:32-39 -------
-        if (tid == 0 || tid == 32) {
-            const int sg = tid ? 1 : 0;
-            float mx = -INFINITY;
-            for (int w = 0; w < nthr / 32; ++w) mx = fmaxf(mx, sRed[sg][w]);
-            int ns = 0, st = 0;
-            float d = 0.f;
-            if ((sg == 0 || P.two_sided) && mx >= 0.f) {
-                d = __fdiv_rn(mx, 100.0f);
-                if (d == 0.f) {
-                    st = 1; // TMB_MAP_MAX_IS_ZERO: the reference would spin forever
-                } else {
-                    float T = mx;
-                    while (T >= 0.f) {
-                        if (ns == kMaxSteps) { st = 2; ns = 0; break; }
-                        sT[sg][ns] = T;
-                        sHH[sg][ns] = (sd.H == 2.0f) ? __fmul_rn(T, T)
-                                                      : (float)pow((double)T, (double)sd.H);
-                        ++ns;
-                        T = __fsub_rn(T, d);
+        if (tid == 0) { sMcount[0] = sMcount[1] = 0; sCcount[0] = sCcount[1] = 0; }
+        if (P.tab_ns) {
+            // ---- threshold tables computed on the host with the C library's powf (bit-identical to the
+            //      reference's std::pow(float,float), which is not correctly rounded) ------------------
+            const size_t e0 = ((size_t)b * P.S + s) * 2;
+            for (int i = tid; i < 2 * kMaxSteps; i += nthr) {
+                const int sg = i / kMaxSteps, l = i % kMaxSteps;
+                sT[sg][l] = P.tab_T[(e0 + sg) * kMaxSteps + l];
+                sHH[sg][l] = P.tab_HH[(e0 + sg) * kMaxSteps + l];
+            }
+            if (tid < 2) {
+                const bool on = (tid == 0) || P.two_sided;
+                sNs[tid] = on ? P.tab_ns[e0 + tid] : 0;
+                sDelta[tid] = P.tab_delta[e0 + tid];
+                sStatus[tid] = on ? P.tab_status[e0 + tid] : 0;
+            }
+            __syncthreads();
+        } else {
+            // ---- maxima of +x and -x (NaN ignored: fmaxf returns the non-NaN operand) -------------
+            float mp = -INFINITY, mn = -INFINITY;
+            for (int v = tid; v < V; v += nthr) {
+                float xv = x[v];
+                mp = fmaxf(mp, xv);
+                mn = fmaxf(mn, -xv);
+            }
+            mp = warp_max(mp);
+            mn = warp_max(mn);
+            if (lane == 0) { sRed[0][wid] = mp; sRed[1][wid] = mn; }
+            __syncthreads();
+            // ---- threshold tables on the device: same fp32 ops as fast_tfce.hpp:32-39, with the height
+            //      term correctly rounded (T*T for H == 2) ----------------------------------------------
+            if (tid == 0 || tid == 32) {
+                const int sg = tid ? 1 : 0;
+                float mx = -INFINITY;
+                for (int w = 0; w < nthr / 32; ++w) mx = fmaxf(mx, sRed[sg][w]);
+                int ns = 0, st = 0;
+                float d = 0.f;
+                if ((sg == 0 || P.two_sided) && mx >= 0.f) {
+                    d = __fdiv_rn(mx, 100.0f);
+                    if (d == 0.f) {
+                        st = 1; // TMB_MAP_MAX_IS_ZERO: the reference would spin forever
+                    } else {
+                        float T = mx;
+                        while (T >= 0.f) {
+                            if (ns == kMaxSteps) { st = 2; ns = 0; break; }
+                            sT[sg][ns] = T;
+                            sHH[sg][ns] = (sd.H == 2.0f) ? __fmul_rn(T, T)
+                                                          : (float)pow((double)T, (double)sd.H);
+                            ++ns;
+                            T = __fsub_rn(T, d);
+                        }
                     }
                 }
+                sNs[sg] = ns;
+                sDelta[sg] = d;
+                sStatus[sg] = st;
             }
-            sNs[sg] = ns;
-            sDelta[sg] = d;
-            sStatus[sg] = st;
+            __syncthreads();
         }
-        __syncthreads();
         const int ns0 = sNs[0], ns1 = sNs[1];
         const int nlev = max(ns0, ns1); // levels 1 .. nlev-1 carry activations
+        TMB_TICK(0)
 
         // ---- activation level per vertex + histogram ------------------------------------------
-        // order[] temporarily holds the level; parent/size/acc are initialised for every vertex
         for (int v = tid; v < V; v += nthr) {
-            float xv = x[v];
-            int lev = 0;
+            const float xv = x[vmap ? vmap[v] : v];
+            int code = 0;
             if (xv > 0.f || xv < 0.f) {
                 const int sg = xv < 0.f;
                 const int ns = sg ? ns1 : ns0;
@@ -167,138 +244,214 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
                     int mid = (lo + hi) >> 1;
                     if (ax > T[mid]) hi = mid; else lo = mid + 1;
                 }
-                if (lo < ns) { lev = lo; atomicAdd(&sCount[lev], 1); }
+                if (lo < ns) { code = lo | (sg << 7); atomicAdd(&sCount[lo], 1); }
             }
-            ws.order[v] = lev; // staged; rewritten by the scatter below via mlist as scratch
+            ws.lev8[v] = (unsigned char)code;
             ws.parent[v] = v;
             ws.size[v] = 0;
+            ws.curnode[v] = -1;
         }
         __syncthreads();
         if (tid == 0) {
             int run = 0;
-            sStart[0] = 0; sStart[1] = 0;
+            sStart[0] = 0;
             for (int l = 1; l < kMaxSteps; ++l) { int c = sCount[l]; sStart[l] = run; sCount[l] = run; run += c; }
             sStart[kMaxSteps] = run;
         }
         __syncthreads();
-        // scatter into mlist (scratch), then swap roles: mlist <-> order by pointer
         for (int v = tid; v < V; v += nthr) {
-            int lev = ws.order[v];
-            if (lev > 0) {
-                int pos = atomicAdd(&sCount[lev], 1);
-                ws.mlist[pos] = v | ((x[v] < 0.f) ? 0x80000000 : 0);
-            }
+            const int lev = ws.lev8[v] & 0x7f;
+            if (lev > 0) ws.order[atomicAdd(&sCount[lev], 1)] = v;
         }
         __syncthreads();
-        { int *t = ws.order; ws.order = ws.mlist; ws.mlist = t; }
         const int total_active = sStart[kMaxSteps];
-
-        // acc init (CreateAdjSet.run accumulates into enhn)
-        for (int idx = tid; idx < total_active; idx += nthr) {
-            int e = ws.order[idx];
-            int u = e & 0x7fffffff;
-            float a0 = 0.f;
-            if (P.accumulate) {
-                float *dst = (e < 0) ? P.tfce_neg : P.tfce_pos;
-                if (dst) a0 = dst[(size_t)b * P.ld + sd.col_off + u];
-            }
-            ws.acc[u] = a0;
-        }
-        __syncthreads();
+        TMB_TICK(1)
 
         const int last_level = (P.stop_level >= 0) ? min(P.stop_level, nlev - 1) : nlev - 1;
-        for (int lev = 1; lev <= last_level; ++lev) {
-            const int beg = sStart[lev];
-            const int end = sStart[lev + 1];
-            // ---- P1: hook new vertices into earlier-activated neighbours -----------------------
+        // pending P2bc work of the previous non-empty level (uniform across the CTA)
+        bool pend = false;
+        int pend_beg = 0, pend_end = 0, pend_buf = 0, pend_nodebase = 0, pend_lev = 0;
+        int node_base = 0;
+        int buf = 0;
+
+        for (int lev = 1; lev <= last_level + 1; ++lev) {
+            const bool have_level = lev <= last_level;
+            const int beg = have_level ? sStart[lev] : 0;
+            const int end = have_level ? sStart[lev + 1] : 0;
+            if (have_level && end == beg) continue; // nothing activates: partition unchanged
+            // ================= interval X: P2bc(previous level)  +  P1(this level) ===============
+            if (pend) {
+                const int ccount = sCcount[pend_buf];
+                const int mcount = sMcount[pend_buf];
+                for (int c = tid; c < ccount; c += nthr) {
+                    const int2 e = ws.clist[c];
+                    const int r = e.x, old = e.y;
+                    const int j = pend_nodebase + c;
+                    const int sg = ws.lev8[r] >> 7;
+                    ws.nodes[j] = make_int2(ld_cg(ws.size + r), (sg << 31) | (pend_lev << 24) | kNone);
+                    if (old >= 0) ws.nodes[old].y = (ws.nodes[old].y & 0xFF000000) | j;
+                }
+                const int2 *ml = ws.mlist[pend_buf];
+                for (int m = tid; m < mcount; m += nthr) {
+                    const int2 e = ml[m];
+                    const int o = ld_cg(ws.curnode + e.x);
+                    const int jn = ld_cg(ws.curnode + e.y);
+                    ws.nodes[o].y = (ws.nodes[o].y & 0xFF000000) | jn;
+                }
+                for (int idx = pend_beg + tid; idx < pend_end; idx += nthr) {
+                    const int u = ws.order[idx];
+                    ws.leaf[u] = ld_cg(ws.curnode + ws.leaf[u]);
+                }
+            }
+            if (!have_level) break;
+            int2 *mcur = ws.mlist[buf];
             for (int idx = beg + tid; idx < end; idx += nthr) {
-                const int e = ws.order[idx];
-                const int u = e & 0x7fffffff;
-                const bool neg = e < 0;
-                const float xu = x[u];
+                const int u = ws.order[idx];
+                const int cu = ws.lev8[u];
+                const float xu = directed ? x[u] : 0.f;
                 const int64_t r0 = indptr[u], r1 = indptr[u + 1];
+                int ru = u;
                 for (int64_t k = r0; k < r1; ++k) {
                     const int a = indices[k];
-                    const float xa = x[a];
-                    const bool earlier = neg ? (xa < xu || (xa == xu && a < u))
-                                             : (xa > xu || (xa == xu && a < u));
+                    const int ca = ws.lev8[a];
+                    if (ca == 0 || ((ca ^ cu) & 0x80)) continue; // inactive or other sign
+                    bool earlier;
+                    if (ca != cu) {
+                        earlier = ca < cu; // same sign: smaller level == activated at a higher threshold
+                    } else if (directed) {
+                        const float xa = x[a];
+                        earlier = (cu & 0x80) ? (xa < xu || (xa == xu && a < u)) : (xa > xu || (xa == xu && a < u));
+                    } else {
+                        earlier = a < u;   // symmetric graph: the pair is seen from both ends, join once
+                    }
                     if (!earlier) continue;
-                    int ru = uf_find(ws.parent, u);
+                    ru = uf_find(ws.parent, ru);
                     int ra = uf_find(ws.parent, a);
                     while (ru != ra) {
-                        if (ru < ra) { int t = ru; ru = ra; ra = t; }
-                        const int old = atomicCAS(ws.parent + ru, ru, ra);
-                        if (old == ru) {
-                            if (ld_cg(ws.size + ru) > 0) { // an older component lost its root
-                                int m = atomicAdd(&sMcount[lev & 1], 1);
-                                ws.mlist[m] = ru;
+                        const int hi = max(ru, ra), lo = min(ru, ra);
+                        const int old = atomicCAS(ws.parent + hi, hi, lo);
+                        if (old == hi) {
+                            if ((ws.lev8[hi] & 0x7f) != lev) { // an older component lost its root
+                                const int m = atomicAdd(&sMcount[buf], 1);
+                                mcur[m] = make_int2(hi, -1);
                             }
+                            ru = lo;
                             break;
                         }
-                        ru = uf_find(ws.parent, old);
-                        ra = uf_find(ws.parent, ra);
+                        // hi was hooked by someone else meanwhile: climb from its real parent
+                        const int nh = uf_find(ws.parent, old);
+                        if (hi == ru) { ru = nh; ra = uf_find(ws.parent, ra); }
+                        else          { ra = nh; ru = uf_find(ws.parent, ru); }
                     }
                 }
             }
             __syncthreads();
-            // ---- P2: sizes ---------------------------------------------------------------------
-            const int mcount = sMcount[lev & 1];
-            if (tid == 0) sMcount[(lev + 1) & 1] = 0; // next level's list (first used after two more barriers)
-            for (int idx = beg + tid; idx < end; idx += nthr) {
-                const int u = ws.order[idx] & 0x7fffffff;
-                const int r = uf_find(ws.parent, u);
-                atomicAdd(ws.size + r, 1);
-            }
-            for (int m = tid; m < mcount; m += nthr) {
-                const int h = ws.mlist[m];
-                const int r = uf_find(ws.parent, h);
-                atomicAdd(ws.size + r, ld_cg(ws.size + h));
+            TMB_TICK(2)
+            // ================= interval Y: P2a(this level) ======================================
+            {
+                const int mcount = sMcount[buf];
+                // the other buffer was consumed by P2bc in interval X: recycle it for the next level
+                if (tid == 0) { sMcount[buf ^ 1] = 0; sCcount[buf ^ 1] = 0; }
+                const int span = end - beg;
+                const int iters = (span + nthr - 1) / nthr;
+                for (int it = 0; it < iters; ++it) { // warp-uniform trip count (match_any below)
+                    const int idx = beg + it * nthr + tid;
+                    const bool valid = idx < end;
+                    int r = -1 - lane; // distinct dummy keys for idle lanes
+                    int u = 0;
+                    if (valid) {
+                        u = ws.order[idx];
+                        r = uf_find(ws.parent, u);
+                        ws.leaf[u] = r;
+                    }
+                    const unsigned peers = __match_any_sync(0xffffffffu, r);
+                    if (valid && lane == (__ffs(peers) - 1)) {
+                        atomicAdd(ws.size + r, __popc(peers));
+                        int old = ld_cg(ws.curnode + r);
+                        for (;;) {
+                            if (old >= node_base || old == kPending) break; // claimed in this level
+                            const int prev = atomicCAS(ws.curnode + r, old, kPending);
+                            if (prev == old) {
+                                const int pos = atomicAdd(&sCcount[buf], 1);
+                                ws.clist[pos] = make_int2(r, old);
+                                atomicExch(ws.curnode + r, node_base + pos);
+                                break;
+                            }
+                            old = prev;
+                        }
+                    }
+                }
+                for (int m = tid; m < mcount; m += nthr) {
+                    const int h = mcur[m].x;
+                    const int r = uf_find(ws.parent, h);
+                    mcur[m].y = r;
+                    atomicAdd(ws.size + r, ld_cg(ws.size + h));
+                }
             }
             __syncthreads();
-            if (P.stop_level >= 0) continue; // components only: no accumulation
-            // ---- P3: every active vertex receives its component's increment --------------------
-            const float hh0 = (lev < ns0) ? sHH[0][lev] : 0.f;
-            const float hh1 = (lev < ns1) ? sHH[1][lev] : 0.f;
-            for (int idx = tid; idx < end; idx += nthr) {
-                const int e = ws.order[idx];
-                const int u = e & 0x7fffffff;
-                const bool neg = e < 0;
-                if (lev >= (neg ? ns1 : ns0)) continue;
-                const int r = uf_find(ws.parent, u);
-                const int n = ld_cg(ws.size + r);
-                const float inc = __double2float_rn(__dmul_rn(sd.powE[n], (double)(neg ? hh1 : hh0)));
-                ws.acc[u] = __fadd_rn(ws.acc[u], inc);
-            }
-            __syncthreads();
+            TMB_TICK(3)
+            pend = true; pend_beg = beg; pend_end = end; pend_buf = buf; pend_nodebase = node_base; pend_lev = lev;
+            node_base += sCcount[buf];
+            buf ^= 1;
         }
+        __syncthreads();
+        TMB_TICK(4)
+        const int num_nodes = node_base;
 
         // ---- outputs -----------------------------------------------------------------------------
         if (P.stop_level >= 0) {
-            __syncthreads();
-            for (int v = tid; v < V; v += nthr) { P.labels[v] = -1; P.extents[v] = 0; }
-            __syncthreads();
-            const int endl = (last_level >= 0) ? sStart[last_level + 1] : 0;
-            for (int idx = tid; idx < endl; idx += nthr) {
-                const int e = ws.order[idx];
-                if (e < 0) continue; // inspection is one-sided (+ map)
-                const int u = e & 0x7fffffff;
-                const int r = uf_find(ws.parent, u);
-                P.labels[u] = r;
-                P.extents[u] = ld_cg(ws.size + r);
+            for (int v = tid; v < V; v += nthr) {
+                const int o = vmap ? vmap[v] : v;
+                int lab = -1, ext = 0;
+                const int code = ws.lev8[v];
+                if (code != 0 && !(code & 0x80) && (code & 0x7f) <= last_level) { // inspection is one-sided (+ map)
+                    const int r = uf_find(ws.parent, v);
+                    lab = r;
+                    ext = ld_cg(ws.size + r);
+                }
+                P.labels[o] = lab;   // root == smallest INTERNAL index; canonicalised on the host when reordered
+                P.extents[o] = ext;
             }
             if (tid == 0 && P.threshold_out)
                 *P.threshold_out = (P.stop_level < ns0) ? sT[0][P.stop_level] : NAN;
         } else {
+            float *nodeval = reinterpret_cast<float *>(ws.size);
+            const bool per_vertex_walk = P.accumulate != 0;
+            if (!per_vertex_walk) {
+                for (int j = tid; j < num_nodes; j += nthr)
+                    nodeval[j] = walk_path(ws.nodes, sd.powE, sHH, sNs, j, 0.f);
+                __syncthreads();
+                TMB_TICK(5)
+                if (P.timing && tid == 0) { atomicAdd(P.timing + 7, (unsigned long long)num_nodes); }
+            }
             float m0 = 0.f, m1 = 0.f;
             const float d0 = sDelta[0], d1 = sDelta[1];
             const float *__restrict__ w = sd.weight;
+            const bool want_maps = (P.tfce_pos != nullptr) || (P.tfce_neg != nullptr);
+            if (want_maps && !P.accumulate) {
+                for (int v = tid; v < V; v += nthr) {
+                    const size_t o = (size_t)b * P.ld + sd.col_off + v;
+                    if (P.tfce_pos) P.tfce_pos[o] = 0.f;
+                    if (P.tfce_neg) P.tfce_neg[o] = 0.f;
+                }
+                __syncthreads();
+            }
             for (int idx = tid; idx < total_active; idx += nthr) {
-                const int e = ws.order[idx];
-                const int u = e & 0x7fffffff;
-                const bool neg = e < 0;
-                float val = __fmul_rn(ws.acc[u], neg ? d1 : d0);
-                if (w) val = __fmul_rn(val, w[u]);
-                if (neg) m1 = fmaxf(m1, val); else m0 = fmaxf(m0, val);
+                const int u = ws.order[idx];
+                const bool neg = (ws.lev8[u] & 0x80) != 0;
+                const size_t o = (size_t)b * P.ld + sd.col_off + (vmap ? vmap[u] : u);
+                float *dst = neg ? P.tfce_neg : P.tfce_pos;
+                float val;
+                if (per_vertex_walk) {
+                    // CreateAdjSet.run semantics: enhn[v] += inc, one add per level, starting from enhn[v]
+                    val = walk_path(ws.nodes, sd.powE, sHH, sNs, ws.leaf[u], dst ? dst[o] : 0.f);
+                } else {
+                    val = nodeval[ws.leaf[u]];
+                }
+                if (dst) dst[o] = val;
+                float sc = __fmul_rn(val, neg ? d1 : d0);
+                if (w) sc = __fmul_rn(sc, w[u]);
+                if (neg) m1 = fmaxf(m1, sc); else m0 = fmaxf(m0, sc);
             }
             m0 = warp_max(m0);
             m1 = warp_max(m1);
@@ -312,26 +465,44 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
                 if (P.max_out) { P.max_out[o] = a; P.max_out[o + 1] = c; }
                 if (P.status) { P.status[o] = sStatus[0]; P.status[o + 1] = sStatus[1]; }
             }
-            // full maps (unscaled TFCE), inactive vertices are 0 (or untouched when accumulating)
-            if (P.tfce_pos || P.tfce_neg) {
-                if (!P.accumulate) {
-                    for (int v = tid; v < V; v += nthr) {
-                        const size_t o = (size_t)b * P.ld + sd.col_off + v;
-                        if (P.tfce_pos) P.tfce_pos[o] = 0.f;
-                        if (P.tfce_neg) P.tfce_neg[o] = 0.f;
-                    }
-                    __syncthreads();
-                }
-                for (int idx = tid; idx < total_active; idx += nthr) {
-                    const int e = ws.order[idx];
-                    const int u = e & 0x7fffffff;
-                    float *dst = (e < 0) ? P.tfce_neg : P.tfce_pos;
-                    if (dst) dst[(size_t)b * P.ld + sd.col_off + u] = ws.acc[u];
-                }
-            }
         }
         __syncthreads();
+        TMB_TICK(6)
+#undef TMB_TICK
     }
+}
+
+// per (row, surface): max of +x and of -x, NaN ignored -- the inputs of the host threshold tables
+__global__ void tfce_maxima_kernel(const SurfDesc *__restrict__ surfs, int S, const float *__restrict__ stat,
+                                   int64_t ld, float *__restrict__ max_out) {
+    __shared__ float sRed[2][8];
+    const int b = blockIdx.x / S, s = blockIdx.x % S;
+    const SurfDesc sd = surfs[s];
+    const float *__restrict__ x = stat + (size_t)b * ld + sd.col_off;
+    float mp = -INFINITY, mn = -INFINITY;
+    for (int v = threadIdx.x; v < sd.V; v += blockDim.x) {
+        const float xv = x[v];
+        mp = fmaxf(mp, xv);
+        mn = fmaxf(mn, -xv);
+    }
+    mp = warp_max(mp);
+    mn = warp_max(mn);
+    if ((threadIdx.x & 31) == 0) { sRed[0][threadIdx.x >> 5] = mp; sRed[1][threadIdx.x >> 5] = mn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)blockDim.x / 32; ++w) { mp = fmaxf(mp, sRed[0][w]); mn = fmaxf(mn, sRed[1][w]); }
+        max_out[(size_t)blockIdx.x * 2] = mp;
+        max_out[(size_t)blockIdx.x * 2 + 1] = mn;
+    }
+}
+
+int launch_tfce_maxima(const SurfDesc *surfs, int S, const float *stat, int64_t ld, int B, float *max_out,
+                       cudaStream_t stream) {
+    if (B * S <= 0) return 0;
+    tfce_maxima_kernel<<<B * S, 256, 0, stream>>>(surfs, S, stat, ld, max_out);
+    count_launch();
+    TMB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int launch_tfce_sweep(const SweepParams &p, int num_slots, cudaStream_t stream) {

@@ -61,6 +61,10 @@ class TfcePlan(object):
         self._handle = h
         self.S = S
         self.row_len = max(s.col_offset + s.adjset.num_vertices for s in self.surfaces)
+        self._H = np.array([s.adjset.H for s in self.surfaces], dtype=np.float32)
+        self.exact_pow = True
+        self._stage = {}
+        self._inflight = None
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -68,11 +72,19 @@ class TfcePlan(object):
             _lib._lib.tmb_plan_destroy(h)
             self._handle = None
 
-    def run(self, stat, two_sided=True, want_maps=False, out_max=None):
-        """stat: CUDA float32 [B, ld].  Returns (max [B, S, 2] CUDA float32, status [B,S,2] int32, maps)."""
+    def run(self, stat, two_sided=True, want_maps=False, out_max=None, exact_pow=None):
+        """stat: CUDA float32 [B, ld].  Returns (max [B, S, 2] CUDA float32, status [B,S,2] int32, maps).
+
+        exact_pow (default: self.exact_pow = True): build the threshold/height tables on the host with the C
+        library's powf -- the very call the reference makes (fast_tfce.hpp:70) -- so TFCE values are
+        bit-identical to the reference; costs one tiny maxima kernel + a host round trip per block.
+        exact_pow=False computes correctly rounded tables on the device (no host sync); values then differ
+        from the reference by <= 1-2 ulp on the ~6% of maps where libm's powf(T, 2) != T*T."""
         import torch
         if not (stat.is_cuda and stat.dtype == torch.float32 and stat.dim() == 2 and stat.stride(1) == 1):
             raise ValueError("stat must be a CUDA float32 [B, ld] tensor with unit column stride")
+        if exact_pow is None:
+            exact_pow = self.exact_pow
         B, ld = int(stat.shape[0]), int(stat.stride(0))
         mx = out_max if out_max is not None else torch.empty((B, self.S, 2), dtype=torch.float32, device=stat.device)
         status = torch.empty((B, self.S, 2), dtype=torch.int32, device=stat.device)
@@ -80,9 +92,41 @@ class TfcePlan(object):
         if want_maps:
             pos = torch.zeros((B, ld), dtype=torch.float32, device=stat.device)
             neg = torch.zeros((B, ld), dtype=torch.float32, device=stat.device) if two_sided else None
-        _lib.check(_lib.lib().tmb_plan_run(self._handle, _lib.ptr(stat), ld, B, 1 if two_sided else 0, _lib.ptr(mx),
-                                           _lib.ptr(pos), _lib.ptr(neg), _lib.ptr(status), _lib.current_stream()))
+        L = _lib.lib()
+        stream = _lib.current_stream()
+        if not exact_pow:
+            _lib.check(L.tmb_plan_run(self._handle, _lib.ptr(stat), ld, B, 1 if two_sided else 0, _lib.ptr(mx),
+                                      _lib.ptr(pos), _lib.ptr(neg), _lib.ptr(status), stream))
+            return mx, status, (pos, neg)
+        cnt = B * self.S * 2
+        maxima = torch.empty((cnt,), dtype=torch.float32, device=stat.device)
+        _lib.check(L.tmb_plan_maxima(self._handle, _lib.ptr(stat), ld, B, _lib.ptr(maxima), stream))
+        mh = maxima.cpu().numpy()                                    # the one host round trip of the block
+        Hs = np.ascontiguousarray(np.tile(np.repeat(self._H, 2), B), dtype=np.float32)
+        tab = self._table_stage(cnt)
+        _lib.check(L.tmb_threshold_tables(_lib.ptr(mh), _lib.ptr(Hs), cnt, _lib.ptr(tab["ns"]), _lib.ptr(tab["delta"]),
+                                          _lib.ptr(tab["T"]), _lib.ptr(tab["HH"]), _lib.ptr(tab["st"])))
+        d = {k: v.to(stat.device, non_blocking=True) for k, v in tab.items()}
+        _lib.check(L.tmb_plan_run_tables(self._handle, _lib.ptr(stat), ld, B, 1 if two_sided else 0, _lib.ptr(d["ns"]),
+                                         _lib.ptr(d["delta"]), _lib.ptr(d["T"]), _lib.ptr(d["HH"]), _lib.ptr(d["st"]),
+                                         _lib.ptr(mx), _lib.ptr(pos), _lib.ptr(neg), _lib.ptr(status), stream))
+        self._inflight = d   # keep the device tables alive until the next call on this stream
         return mx, status, (pos, neg)
+
+    def _table_stage(self, cnt):
+        """Pinned host staging for the threshold tables (reused; guarded by an event)."""
+        import torch
+        ent = self._stage.get(cnt)
+        if ent is None:
+            ent = dict(ns=torch.empty((cnt,), dtype=torch.int32).pin_memory(),
+                       delta=torch.empty((cnt,), dtype=torch.float32).pin_memory(),
+                       T=torch.empty((cnt, 128), dtype=torch.float32).pin_memory(),
+                       HH=torch.empty((cnt, 128), dtype=torch.float32).pin_memory(),
+                       st=torch.empty((cnt,), dtype=torch.int32).pin_memory())
+            self._stage[cnt] = ent
+        else:
+            torch.cuda.current_stream().synchronize()   # previous async copies out of the staging are done
+        return ent
 
 
 # ------------------------------------------------------------------------------------------ designs

@@ -1,0 +1,73 @@
+"""Shared pieces of the randomise drivers."""
+import os
+from time import time
+
+import numpy as np
+
+from .. import parallel
+from .._graph import adjacency_to_csr, induced_subgraph
+
+BLOCK = 256      # shuffles per engine call
+
+
+def load(path):
+    return np.load(path, allow_pickle=True)
+
+
+def append_rows(path, rows, fmt):
+    """One formatted value per line, appended -- what the reference's `echo ... >> file` produces."""
+    with open(path, "a") as f:
+        for r in rows:
+            f.write((fmt % r) + "\n")
+
+
+def reference_seed(iter_perm, seed):
+    """The reference seeds with int(iter_perm*1000 + time()) (e.g. vertex_..._randomise.py:91), which is not
+    reproducible; `--seed S` replaces time() by S so two runs (and the CPU oracle) see the same stream."""
+    return int(iter_perm * 1000 + (time() if seed is None else seed))
+
+
+def draw_row_permutation(n):
+    return np.random.permutation(list(range(n)))
+
+
+def draw_block_permutation(block_list, indexer):
+    """Exchangeability blocks (vertex_..._randomise.py:98-103): shuffle the block order, then within blocks."""
+    randindex = []
+    for block in np.random.permutation(list(np.unique(block_list))):
+        randindex.append(np.random.permutation(indexer[block_list == block]))
+    return np.concatenate(randindex)
+
+
+def masked_surface(adjacency, H, E, keep=None, weight=None, col_offset=0):
+    """CreateAdjSet + Surface for the vertices selected by boolean mask `keep` (None = all)."""
+    from ..engine import Surface
+    from ..tfce import CreateAdjSet
+    indptr, indices = adjacency_to_csr(adjacency)
+    if keep is not None:
+        keep = np.asarray(keep, dtype=bool)
+        indptr, indices = induced_subgraph(indptr, indices, keep)
+    w = None
+    if weight is not None and np.ndim(weight) > 0:
+        w = np.asarray(weight, dtype=np.float32)
+        if keep is not None:
+            w = w[keep]
+    elif weight is not None and float(weight) != 1.0:
+        w = float(weight)
+    return Surface(CreateAdjSet(H, E, (indptr, indices)), col_offset, w)
+
+
+def shard(first, last):
+    rank, ws, _ = parallel.world()
+    if ws > 1:
+        parallel.init_process_group()
+    a, b = parallel.shard_range(first, last, rank, ws)
+    return rank, ws, a, b
+
+
+def chunks(a, b, size=BLOCK):
+    p = a
+    while p <= b:
+        q = min(b, p + size - 1)
+        yield p, q
+        p = q + 1
