@@ -43,3 +43,4 @@ print("tfce: %.3f ms for %d maps x 2 hemis x 2 signs -> %.1f us/shuffle" % (ms_t
 ms_all, _ = timed(lambda: eng.regression_block(X, perm_idx=idx))
 print("block e2e (host algebra + h2d + fit + tfce + d2h): %.3f ms -> %.1f shuffles/s" % (ms_all, P / ms_all * 1e3), flush=True)
 print("launches", _lib.launch_count())
+eng.plan.__del__()   # prints the TMB_PHASE_TIMING summary (if enabled)

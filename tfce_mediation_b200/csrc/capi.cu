@@ -124,6 +124,31 @@ static std::vector<int32_t> rcm_order(int32_t V, const int64_t *indptr, const in
     return order;
 }
 
+// Patch ordering: walk the RCM order and grow compact BFS blobs of up to `patch` still-unassigned
+// vertices; blobs get consecutive ids.  Most neighbours of a vertex then sit within the same few
+// hundred bytes, and consecutive blobs stay adjacent on the surface.
+static std::vector<int32_t> patch_order(int32_t V, const int64_t *indptr, const int32_t *indices, int patch) {
+    const std::vector<int32_t> base = rcm_order(V, indptr, indices);
+    std::vector<char> done(V, 0);
+    std::vector<int32_t> order;
+    order.reserve(V);
+    for (int32_t seed : base) {
+        if (done[seed]) continue;
+        const size_t start = order.size();
+        done[seed] = 1;
+        order.push_back(seed);
+        size_t head = start;
+        while (head < order.size() && order.size() - start < (size_t)patch) {
+            const int32_t v = order[head++];
+            for (int64_t e = indptr[v]; e < indptr[v + 1] && order.size() - start < (size_t)patch; ++e) {
+                const int32_t a = indices[e];
+                if (!done[a]) { done[a] = 1; order.push_back(a); }
+            }
+        }
+    }
+    return order;
+}
+
 extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, const int32_t *indices, float H,
                                 float E, tmb_graph **out) {
     TMB_REQUIRE(out && indptr && V > 0, "tmb_graph_create: bad arguments (V=%d)", V);
@@ -142,12 +167,16 @@ extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, co
     g->symmetric = csr_is_symmetric(V, indptr, indices);
     // locality reordering (symmetric graphs only; TMB_NO_REORDER=1 disables it for A/B measurements)
     const char *no_reorder = getenv("TMB_NO_REORDER");
+    const char *reorder_mode = getenv("TMB_REORDER"); // "rcm" | "patch<N>" (default patch64)
     std::vector<int64_t> r_indptr;
     std::vector<int32_t> r_indices;
     const int64_t *use_indptr = indptr;
     const int32_t *use_indices = indices;
     if (g->symmetric && !(no_reorder && no_reorder[0] == '1') && nnz > 0) {
-        g->vmap = rcm_order(V, indptr, indices);
+        int patch = 64;
+        if (reorder_mode && strncmp(reorder_mode, "patch", 5) == 0 && atoi(reorder_mode + 5) > 0) patch = atoi(reorder_mode + 5);
+        if (reorder_mode && strcmp(reorder_mode, "rcm") == 0) g->vmap = rcm_order(V, indptr, indices);
+        else g->vmap = patch_order(V, indptr, indices, patch);
         std::vector<int32_t> inv(V);
         for (int32_t i = 0; i < V; ++i) inv[g->vmap[i]] = i;
         r_indptr.assign((size_t)V + 1, 0);
@@ -233,7 +262,12 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { set_error("tmb_plan_create: %s", cudaGetErrorString(e)); delete p; return 1; }
     p->slot_stride = tfce_slot_bytes(p->Vmax);
-    p->num_slots = max_slots > 0 ? max_slots : prop.multiProcessorCount * 2;
+    {
+        int threads, per_sm;
+        size_t dyn;
+        tfce_sweep_geometry(p->Vmax, prop.multiProcessorCount, &threads, &per_sm, &dyn);
+        p->num_slots = max_slots > 0 ? max_slots : prop.multiProcessorCount * per_sm;
+    }
     {   // keep the workspace within a quarter of the free HBM (huge merged graphs get fewer slots)
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
@@ -316,6 +350,10 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
     sp.tfce_neg = tfce_neg; sp.status = status; sp.stop_level = stop_level; sp.labels = labels;
     sp.extents = extents; sp.threshold_out = thr; sp.workspace = p->d_workspace; sp.slot_stride = p->slot_stride;
     sp.Vmax = p->Vmax; sp.work_counter = p->d_counter; sp.timing = p->d_timing;
+    {
+        const char *pc = getenv("TMB_PARENT_UNCACHED");
+        sp.flags = (pc && pc[0] == '1') ? 0 : 1; // bit 0: union-find loads may use L1 (see uf_find)
+    }
     return launch_tfce_sweep(sp, p->num_slots, stream);
 }
 
@@ -457,8 +495,9 @@ extern "C" int tmb_tfce_components(tmb_graph *g, const float *image_host, int le
         return 1;
     TMB_CUDA(cudaMemcpy(labels_host, g->d_labels, sizeof(int32_t) * (size_t)g->V, cudaMemcpyDeviceToHost));
     TMB_CUDA(cudaMemcpy(extents_host, g->d_extents, sizeof(int32_t) * (size_t)g->V, cudaMemcpyDeviceToHost));
-    if (!g->vmap.empty()) {
-        // the kernel labels a component by its smallest INTERNAL index; canonical = smallest caller index
+    {
+        // the kernel labels a component by the INTERNAL index of its union-find root; the canonical label
+        // is the smallest caller index of the component.  labels_host[] currently holds internal ids.
         std::vector<int32_t> canon((size_t)g->V, INT32_MAX);
         for (int32_t o = 0; o < g->V; ++o)
             if (labels_host[o] >= 0) canon[labels_host[o]] = std::min(canon[labels_host[o]], o);

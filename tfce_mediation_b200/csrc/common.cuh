@@ -70,6 +70,7 @@ struct SweepParams {
     const float *tab_T;
     const float *tab_HH;
     const int32_t *tab_status;
+    int flags;                  // bit 0: union-find pointer loads go through L1 (ld.ca) instead of ld.cg
     unsigned long long *timing; // optional [8] per-phase cycle totals (development aid), or nullptr
     // workspace
     char *workspace;
@@ -82,5 +83,6 @@ int launch_tfce_sweep(const SweepParams &p, int num_slots, cudaStream_t stream);
 int launch_tfce_maxima(const SurfDesc *surfs, int S, const float *stat, int64_t ld, int B, float *max_out,
                        cudaStream_t stream);
 size_t tfce_slot_bytes(int32_t Vmax);
+void tfce_sweep_geometry(int32_t Vmax, int num_sms, int *threads, int *ctas_per_sm, size_t *dyn_smem);
 
 } // namespace tmb

@@ -17,8 +17,8 @@
 //
 // Algorithm (V2).  Vertices are bucketed by activation level (counting sort).  Levels are swept in
 // order; per level only the NEWLY activated vertices do work:
-//   P1   hook new vertices into earlier-activated neighbours (lock-free union-find; larger root
-//        index under smaller, so a root is the smallest index of its component)
+//   P1   hook new vertices into earlier-activated neighbours (lock-free union-find; roots are
+//        totally ordered by (activation level, index) and the later root goes under the earlier)
 //   P2a  sizes + component-tree bookkeeping: every component whose membership changed in this
 //        level gets a new tree node (size, level); warp-aggregated atomics
 //   P2bc links the previous nodes of merged/grown components to the new node and records each new
@@ -33,20 +33,42 @@
 
 namespace tmb {
 
-static constexpr int kSweepThreads = 512;
+static constexpr int kSweepMaxThreads = 1024;
 static constexpr int kMaxSteps = 128;
 static constexpr int kNone = 0x00FFFFFF; // "no parent" in the 24-bit parent field of a node
 static constexpr int kPending = -2;
 
 __device__ __forceinline__ int ld_cg(const int *p) { return __ldcg(p); }
 
-// union-find with path halving.  Reads go to L2 (ld.cg) so they are coherent with the atomicCAS
-// hooks issued by other warps of the CTA.
+// Union-find pointer load.  CACHED uses the default L1-allocating load.  That is safe here:
+//  * only this CTA ever touches its slot, and __syncthreads() orders the block's earlier global
+//    writes AND atomics before later loads of every thread of the block, so the phases that need the
+//    exact forest (P2a, outputs) see it;
+//  * inside P1, a stale pointer is still a pointer to an ancestor (pointers only ever move towards
+//    smaller indices within the same tree), and every hook is decided by an atomicCAS at L2.
+template <bool CACHED>
+__device__ __forceinline__ int ld_uf(const int *p) { return CACHED ? *p : __ldcg(p); }
+
+// union-find with path halving
+template <bool CACHED>
 __device__ __forceinline__ int uf_find(int *parent, int v) {
     int cur = v;
-    int p = ld_cg(parent + cur);
+    int p = ld_uf<CACHED>(parent + cur);
     while (p != cur) {
-        int gp = ld_cg(parent + p);
+        int gp = ld_uf<CACHED>(parent + p);
+        if (gp != p) parent[cur] = gp;
+        cur = p;
+        p = gp;
+    }
+    return cur;
+}
+
+// find continuing from an already loaded parent pointer p == parent[v]
+template <bool CACHED>
+__device__ __forceinline__ int uf_find_from(int *parent, int v, int p) {
+    int cur = v;
+    while (p != cur) {
+        int gp = ld_uf<CACHED>(parent + p);
         if (gp != p) parent[cur] = gp;
         cur = p;
         p = gp;
@@ -125,7 +147,11 @@ __device__ __forceinline__ float walk_path(const int2 *__restrict__ nodes, const
     return acc;
 }
 
-__global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParams P) {
+// LEV_SMEM: the per-vertex activation level/sign bytes live in dynamic shared memory (V bytes) instead
+// of the slot workspace: the neighbour filter of P1, the hottest random read, then never leaves the SM.
+template <bool LEV_SMEM, bool CACHED>
+__global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_sweep_kernel(SweepParams P) {
+    extern __shared__ __align__(16) unsigned char sLevDyn[];
     __shared__ float sT[2][kMaxSteps];
     __shared__ float sHH[2][kMaxSteps];
     __shared__ int sNs[2];
@@ -133,7 +159,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
     __shared__ int sStatus[2];
     __shared__ int sCount[kMaxSteps];   // histogram, then running cursor
     __shared__ int sStart[kMaxSteps + 1];
-    __shared__ float sRed[2][kSweepThreads / 32];
+    __shared__ float sRed[2][kSweepMaxThreads / 32];
     __shared__ int sItem;
     __shared__ int sMcount[2];
     __shared__ int sCcount[2];
@@ -142,6 +168,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
     const int nthr = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5;
     const SlotWs ws = carve(P.workspace + (size_t)blockIdx.x * P.slot_stride, P.Vmax);
+    unsigned char *const lev8 = LEV_SMEM ? sLevDyn : ws.lev8;
     const int total_items = P.B * P.S;
 
     for (;;) {
@@ -246,7 +273,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
                 }
                 if (lo < ns) { code = lo | (sg << 7); atomicAdd(&sCount[lo], 1); }
             }
-            ws.lev8[v] = (unsigned char)code;
+            lev8[v] = (unsigned char)code;
             ws.parent[v] = v;
             ws.size[v] = 0;
             ws.curnode[v] = -1;
@@ -260,7 +287,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
         }
         __syncthreads();
         for (int v = tid; v < V; v += nthr) {
-            const int lev = ws.lev8[v] & 0x7f;
+            const int lev = lev8[v] & 0x7f;
             if (lev > 0) ws.order[atomicAdd(&sCount[lev], 1)] = v;
         }
         __syncthreads();
@@ -287,7 +314,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
                     const int2 e = ws.clist[c];
                     const int r = e.x, old = e.y;
                     const int j = pend_nodebase + c;
-                    const int sg = ws.lev8[r] >> 7;
+                    const int sg = lev8[r] >> 7;
                     ws.nodes[j] = make_int2(ld_cg(ws.size + r), (sg << 31) | (pend_lev << 24) | kNone);
                     if (old >= 0) ws.nodes[old].y = (ws.nodes[old].y & 0xFF000000) | j;
                 }
@@ -307,41 +334,65 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
             int2 *mcur = ws.mlist[buf];
             for (int idx = beg + tid; idx < end; idx += nthr) {
                 const int u = ws.order[idx];
-                const int cu = ws.lev8[u];
+                const int cu = lev8[u];
                 const float xu = directed ? x[u] : 0.f;
                 const int64_t r0 = indptr[u], r1 = indptr[u + 1];
                 int ru = u;
-                for (int64_t k = r0; k < r1; ++k) {
-                    const int a = indices[k];
-                    const int ca = ws.lev8[a];
-                    if (ca == 0 || ((ca ^ cu) & 0x80)) continue; // inactive or other sign
-                    bool earlier;
-                    if (ca != cu) {
-                        earlier = ca < cu; // same sign: smaller level == activated at a higher threshold
-                    } else if (directed) {
-                        const float xa = x[a];
-                        earlier = (cu & 0x80) ? (xa < xu || (xa == xu && a < u)) : (xa > xu || (xa == xu && a < u));
-                    } else {
-                        earlier = a < u;   // symmetric graph: the pair is seen from both ends, join once
-                    }
-                    if (!earlier) continue;
-                    ru = uf_find(ws.parent, ru);
-                    int ra = uf_find(ws.parent, a);
-                    while (ru != ra) {
-                        const int hi = max(ru, ra), lo = min(ru, ra);
-                        const int old = atomicCAS(ws.parent + hi, hi, lo);
-                        if (old == hi) {
-                            if ((ws.lev8[hi] & 0x7f) != lev) { // an older component lost its root
-                                const int m = atomicAdd(&sMcount[buf], 1);
-                                mcur[m] = make_int2(hi, -1);
-                            }
-                            ru = lo;
-                            break;
+                for (int64_t k0 = r0; k0 < r1; k0 += 8) {
+                    // neighbour ids, their level bytes and their first parent pointers are fetched as
+                    // three batches of independent loads (memory-level parallelism per thread)
+                    const int cnt = (int)min((int64_t)8, r1 - k0);
+                    int nb[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) nb[j] = (j < cnt) ? indices[k0 + j] : -1;
+                    unsigned early = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (nb[j] < 0) continue;
+                        const int a = nb[j];
+                        const int ca = lev8[a];
+                        if (ca == 0 || ((ca ^ cu) & 0x80)) continue; // inactive or other sign
+                        bool e;
+                        if (ca != cu) {
+                            e = ca < cu; // same sign: smaller level == activated at a higher threshold
+                        } else if (directed) {
+                            const float xa = x[a];
+                            e = (cu & 0x80) ? (xa < xu || (xa == xu && a < u)) : (xa > xu || (xa == xu && a < u));
+                        } else {
+                            e = a < u;   // symmetric graph: the pair is seen from both ends, join once
                         }
-                        // hi was hooked by someone else meanwhile: climb from its real parent
-                        const int nh = uf_find(ws.parent, old);
-                        if (hi == ru) { ru = nh; ra = uf_find(ws.parent, ra); }
-                        else          { ra = nh; ru = uf_find(ws.parent, ru); }
+                        if (e) early |= 1u << j;
+                    }
+                    int pa[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pa[j] = ((early >> j) & 1u) ? ld_uf<CACHED>(ws.parent + nb[j]) : -1;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (!((early >> j) & 1u)) continue;
+                        const int a = nb[j];
+                        if (pa[j] == ru || a == ru) continue; // a already hangs under u's (possibly former) root
+                        int ra = uf_find_from<CACHED>(ws.parent, a, pa[j]);
+                        ru = uf_find<CACHED>(ws.parent, ru);
+                        while (ru != ra) {
+                            // total order on roots: (activation level, index).  The root that activated at
+                            // the later threshold goes under the earlier one, so a growing component keeps
+                            // its root and new vertices attach directly to it (shallow trees).
+                            const int kru = ((lev8[ru] & 0x7f) << 24) | ru, kra = ((lev8[ra] & 0x7f) << 24) | ra;
+                            const int hi = kru > kra ? ru : ra, lo = kru > kra ? ra : ru;
+                            const int old = atomicCAS(ws.parent + hi, hi, lo);
+                            if (old == hi) {
+                                if ((lev8[hi] & 0x7f) != lev) { // an older component lost its root
+                                    const int m = atomicAdd(&sMcount[buf], 1);
+                                    mcur[m] = make_int2(hi, -1);
+                                }
+                                ru = lo;
+                                break;
+                            }
+                            // hi was hooked by someone else meanwhile: climb from its real parent
+                            const int nh = uf_find<CACHED>(ws.parent, old);
+                            if (hi == ru) { ru = nh; ra = uf_find<CACHED>(ws.parent, ra); }
+                            else          { ra = nh; ru = uf_find<CACHED>(ws.parent, ru); }
+                        }
                     }
                 }
             }
@@ -361,7 +412,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
                     int u = 0;
                     if (valid) {
                         u = ws.order[idx];
-                        r = uf_find(ws.parent, u);
+                        r = uf_find<CACHED>(ws.parent, u);
                         ws.leaf[u] = r;
                     }
                     const unsigned peers = __match_any_sync(0xffffffffu, r);
@@ -383,7 +434,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
                 }
                 for (int m = tid; m < mcount; m += nthr) {
                     const int h = mcur[m].x;
-                    const int r = uf_find(ws.parent, h);
+                    const int r = uf_find<CACHED>(ws.parent, h);
                     mcur[m].y = r;
                     atomicAdd(ws.size + r, ld_cg(ws.size + h));
                 }
@@ -403,13 +454,13 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
             for (int v = tid; v < V; v += nthr) {
                 const int o = vmap ? vmap[v] : v;
                 int lab = -1, ext = 0;
-                const int code = ws.lev8[v];
+                const int code = lev8[v];
                 if (code != 0 && !(code & 0x80) && (code & 0x7f) <= last_level) { // inspection is one-sided (+ map)
-                    const int r = uf_find(ws.parent, v);
+                    const int r = uf_find<CACHED>(ws.parent, v);
                     lab = r;
                     ext = ld_cg(ws.size + r);
                 }
-                P.labels[o] = lab;   // root == smallest INTERNAL index; canonicalised on the host when reordered
+                P.labels[o] = lab;   // internal root id; canonicalised (smallest caller index) on the host
                 P.extents[o] = ext;
             }
             if (tid == 0 && P.threshold_out)
@@ -438,7 +489,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfce_sweep_kernel(SweepParam
             }
             for (int idx = tid; idx < total_active; idx += nthr) {
                 const int u = ws.order[idx];
-                const bool neg = (ws.lev8[u] & 0x80) != 0;
+                const bool neg = (lev8[u] & 0x80) != 0;
                 const size_t o = (size_t)b * P.ld + sd.col_off + (vmap ? vmap[u] : u);
                 float *dst = neg ? P.tfce_neg : P.tfce_pos;
                 float val;
@@ -505,12 +556,37 @@ int launch_tfce_maxima(const SurfDesc *surfs, int S, const float *stat, int64_t 
     return 0;
 }
 
+// Launch geometry: with the level bytes in shared memory one CTA of 1024 threads owns an SM (large
+// surfaces) or two CTAs of 512 share it (V <= ~110k); otherwise two CTAs of 512 with global bytes.
+void tfce_sweep_geometry(int32_t Vmax, int num_sms, int *threads, int *ctas_per_sm, size_t *dyn_smem) {
+    const size_t need = align_up((size_t)Vmax, 16);
+    if (need <= 108 * 1024) { *threads = 512; *ctas_per_sm = 2; *dyn_smem = need; }
+    else if (need <= 220 * 1024) { *threads = 1024; *ctas_per_sm = 1; *dyn_smem = need; }
+    else { *threads = 512; *ctas_per_sm = 2; *dyn_smem = 0; }
+    (void)num_sms;
+}
+
 int launch_tfce_sweep(const SweepParams &p, int num_slots, cudaStream_t stream) {
     const int items = p.B * p.S;
     if (items <= 0) return 0;
+    int threads, per_sm;
+    size_t dyn;
+    tfce_sweep_geometry(p.Vmax, 0, &threads, &per_sm, &dyn);
     int grid = items < num_slots ? items : num_slots;
     TMB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
-    tfce_sweep_kernel<<<grid, kSweepThreads, 0, stream>>>(p);
+    const bool cached = (p.flags & 1) != 0;
+    if (dyn > 0) {
+        if (cached) {
+            TMB_CUDA(cudaFuncSetAttribute(tfce_sweep_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            tfce_sweep_kernel<true, true><<<grid, threads, dyn, stream>>>(p);
+        } else {
+            TMB_CUDA(cudaFuncSetAttribute(tfce_sweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            tfce_sweep_kernel<true, false><<<grid, threads, dyn, stream>>>(p);
+        }
+    } else {
+        if (cached) tfce_sweep_kernel<false, true><<<grid, threads, 0, stream>>>(p);
+        else tfce_sweep_kernel<false, false><<<grid, threads, 0, stream>>>(p);
+    }
     count_launch();
     TMB_CUDA(cudaGetLastError());
     return 0;
