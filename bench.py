@@ -284,11 +284,11 @@ def run_b200(args):
         if world > 1:
             dist.all_gather(gathered, out_max)       # the per-shuffle maxima, tiny (NCCL over NVLink)
 
-    for s in range(args.warmup):
-        device_step(s)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # sampled from the warm-up on, so short timed regions still get samples under load
+    for s in range(args.warmup):
+        device_step(s)
     barrier()
     launches0 = _lib.launch_count()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)

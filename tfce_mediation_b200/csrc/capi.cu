@@ -38,6 +38,8 @@ struct tmb_graph {
     int32_t *d_indices = nullptr;
     double *d_powE = nullptr;
     int32_t *d_vmap = nullptr;          // internal -> caller index (nullptr: identity)
+    int32_t *d_ell = nullptr;           // fixed-width adjacency rows (low-degree graphs)
+    int32_t ell_width = 0;
     std::vector<int32_t> vmap;          // host copy
     bool symmetric = true;
     tmb_plan *self_plan = nullptr; // lazily created single-surface plan for tmb_tfce_run
@@ -60,6 +62,7 @@ struct tmb_plan {
     char *d_workspace = nullptr;
     size_t slot_stride = 0;
     int *d_counter = nullptr;
+    int use_basin = 0;          // every surface symmetric -> V3 basin sweep
     unsigned long long *d_timing = nullptr; // TMB_PHASE_TIMING=1: per-phase cycle totals
 };
 
@@ -211,6 +214,22 @@ extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, co
         return fail("memcpy", e);
     if ((e = cudaMemcpy(g->d_powE, powE.data(), sizeof(double) * ((size_t)V + 1), cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail("memcpy", e);
+    {
+        // fixed-width (ELL) copy of the rows for low-degree graphs: one or two 128-bit loads fetch a whole
+        // row from a single 32-byte sector instead of indptr + one scalar load per neighbour
+        int64_t maxdeg = 0;
+        for (int32_t v = 0; v < V; ++v) maxdeg = std::max<int64_t>(maxdeg, use_indptr[v + 1] - use_indptr[v]);
+        int width = maxdeg <= 8 ? 8 : maxdeg <= 16 ? 16 : maxdeg <= 32 ? 32 : 0;
+        if (width && nnz > 0 && (double)nnz / ((double)V * width) >= 0.4) {
+            std::vector<int32_t> ell((size_t)V * width, -1);
+            for (int32_t v = 0; v < V; ++v)
+                std::copy(use_indices + use_indptr[v], use_indices + use_indptr[v + 1], ell.begin() + (size_t)v * width);
+            if ((e = cudaMalloc(&g->d_ell, sizeof(int32_t) * ell.size())) != cudaSuccess) return fail("malloc", e);
+            if ((e = cudaMemcpy(g->d_ell, ell.data(), sizeof(int32_t) * ell.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+                return fail("memcpy", e);
+            g->ell_width = width;
+        }
+    }
     if (!g->vmap.empty()) {
         if ((e = cudaMalloc(&g->d_vmap, sizeof(int32_t) * (size_t)V)) != cudaSuccess) return fail("malloc", e);
         if ((e = cudaMemcpy(g->d_vmap, g->vmap.data(), sizeof(int32_t) * (size_t)V, cudaMemcpyHostToDevice)) != cudaSuccess)
@@ -224,7 +243,7 @@ extern "C" int tmb_graph_destroy(tmb_graph *g) {
     if (!g) return 0;
     cudaSetDevice(g->device);
     if (g->self_plan) tmb_plan_destroy(g->self_plan);
-    cudaFree(g->d_indptr); cudaFree(g->d_indices); cudaFree(g->d_powE); cudaFree(g->d_vmap);
+    cudaFree(g->d_indptr); cudaFree(g->d_indices); cudaFree(g->d_powE); cudaFree(g->d_vmap); cudaFree(g->d_ell);
     cudaFree(g->d_image); cudaFree(g->d_enhn); cudaFree(g->d_labels); cudaFree(g->d_extents);
     cudaFree(g->d_status); cudaFree(g->d_thr); cudaFree(g->d_tabs);
     delete g;
@@ -261,11 +280,17 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { set_error("tmb_plan_create: %s", cudaGetErrorString(e)); delete p; return 1; }
-    p->slot_stride = tfce_slot_bytes(p->Vmax);
+    {
+        const char *sw = getenv("TMB_SWEEP"); // "v2" forces the vertex-level sweep (A/B measurements)
+        p->use_basin = !(sw && strcmp(sw, "v2") == 0);
+        for (int s = 0; s < S; ++s)
+            if (!graphs[s]->symmetric) p->use_basin = 0; // directed adjacency: reference's directional rule (V2)
+    }
+    p->slot_stride = tfce_slot_bytes_for(p->Vmax, p->use_basin);
     {
         int threads, per_sm;
         size_t dyn;
-        tfce_sweep_geometry(p->Vmax, prop.multiProcessorCount, &threads, &per_sm, &dyn);
+        tfce_sweep_geometry(p->Vmax, p->use_basin, &threads, &per_sm, &dyn);
         p->num_slots = max_slots > 0 ? max_slots : prop.multiProcessorCount * per_sm;
     }
     {   // keep the workspace within a quarter of the free HBM (huge merged graphs get fewer slots)
@@ -291,7 +316,7 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
             if ((e = cudaMemcpy(p->d_weights[s], w.data(), sizeof(float) * (size_t)g->V, cudaMemcpyHostToDevice)) != cudaSuccess)
                 return fail("memcpy", e);
         }
-        descs[s] = SurfDesc{g->d_indptr, g->d_indices, g->d_powE, p->d_weights[s], g->d_vmap, col_offset[s], g->V, g->H,
+        descs[s] = SurfDesc{g->d_indptr, g->d_indices, g->d_ell, g->ell_width, g->d_powE, p->d_weights[s], g->d_vmap, col_offset[s], g->V, g->H,
                             g->symmetric ? 0 : 1};
     }
     if ((e = cudaMalloc(&p->d_surfs, sizeof(SurfDesc) * S)) != cudaSuccess) return fail("malloc", e);
@@ -300,8 +325,8 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
     {
         const char *pt = getenv("TMB_PHASE_TIMING");
         if (pt && pt[0] == '1') {
-            if ((e = cudaMalloc(&p->d_timing, sizeof(unsigned long long) * 8)) != cudaSuccess) return fail("malloc", e);
-            cudaMemset(p->d_timing, 0, sizeof(unsigned long long) * 8);
+            if ((e = cudaMalloc(&p->d_timing, sizeof(unsigned long long) * 12)) != cudaSuccess) return fail("malloc", e);
+            cudaMemset(p->d_timing, 0, sizeof(unsigned long long) * 12);
         }
     }
     if ((e = cudaMalloc(&p->d_workspace, p->slot_stride * (size_t)p->num_slots)) != cudaSuccess) return fail("malloc workspace", e);
@@ -315,13 +340,17 @@ extern "C" int tmb_plan_destroy(tmb_plan *p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     if (p->d_timing) {
-        unsigned long long t[8];
+        unsigned long long t[12];
         if (cudaMemcpy(t, p->d_timing, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess) {
-            static const char *names[7] = {"tables", "levels+sort", "X: P2bc+P1", "Y: P2a", "tail", "node walk", "finalize"};
+            static const char *names_v2[7] = {"tables", "levels+sort", "X: P2bc+P1", "Y: P2a", "tail", "node walk", "finalize"};
+            static const char *names_v3[7] = {"tables", "levels+sort", "ascent+init", "I1: unions", "I2: sizes", "node walk", "finalize"};
+            const char **names = p->use_basin ? names_v3 : names_v2;
             double tot = 0;
             for (int i = 0; i < 7; ++i) tot += (double)t[i];
+            tot += (double)t[8] + (double)t[9];
             fprintf(stderr, "[tmb phase timing] total %.3e cycles, nodes %llu\n", tot, t[7]);
             for (int i = 0; i < 7; ++i) fprintf(stderr, "  %-12s %6.2f%%\n", names[i], tot > 0 ? 100.0 * t[i] / tot : 0.0);
+
         }
         cudaFree(p->d_timing);
     }
@@ -352,7 +381,7 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
     sp.Vmax = p->Vmax; sp.work_counter = p->d_counter; sp.timing = p->d_timing;
     {
         const char *pc = getenv("TMB_PARENT_UNCACHED");
-        sp.flags = (pc && pc[0] == '1') ? 0 : 1; // bit 0: union-find loads may use L1 (see uf_find)
+        sp.flags = ((pc && pc[0] == '1') ? 0 : 1) | (p->use_basin ? 2 : 0); // see SweepParams::flags
     }
     return launch_tfce_sweep(sp, p->num_slots, stream);
 }

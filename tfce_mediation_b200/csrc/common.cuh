@@ -35,6 +35,8 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_or
 struct SurfDesc {
     const int64_t *indptr;  // [V+1]
     const int32_t *indices; // [nnz]
+    const int32_t *ell;     // [V * ell_width] fixed-width rows padded with -1 (32-byte aligned), or nullptr
+    int32_t ell_width;      // 8, 16 or 32 when ell != nullptr
     const double *powE;     // [V+1]  pow((double)n, (double)E) tabulated with the host libm
     const float *weight;    // [V] or nullptr (internal vertex order)
     const int32_t *vmap;    // [V] internal (locality-reordered) index -> caller's index, or nullptr
@@ -70,7 +72,8 @@ struct SweepParams {
     const float *tab_T;
     const float *tab_HH;
     const int32_t *tab_status;
-    int flags;                  // bit 0: union-find pointer loads go through L1 (ld.ca) instead of ld.cg
+    int flags;                  // bit 0: union-find pointer loads go through L1 (ld.ca) instead of ld.cg;
+                                // bit 1: basin sweep (V3, symmetric adjacency only)
     unsigned long long *timing; // optional [8] per-phase cycle totals (development aid), or nullptr
     // workspace
     char *workspace;
@@ -82,7 +85,7 @@ struct SweepParams {
 int launch_tfce_sweep(const SweepParams &p, int num_slots, cudaStream_t stream);
 int launch_tfce_maxima(const SurfDesc *surfs, int S, const float *stat, int64_t ld, int B, float *max_out,
                        cudaStream_t stream);
-size_t tfce_slot_bytes(int32_t Vmax);
-void tfce_sweep_geometry(int32_t Vmax, int num_sms, int *threads, int *ctas_per_sm, size_t *dyn_smem);
+size_t tfce_slot_bytes_for(int32_t Vmax, int use_basin);
+void tfce_sweep_geometry(int32_t Vmax, int use_basin, int *threads, int *ctas_per_sm, size_t *dyn_smem);
 
 } // namespace tmb

@@ -556,26 +556,592 @@ int launch_tfce_maxima(const SurfDesc *surfs, int S, const float *stat, int64_t 
     return 0;
 }
 
-// Launch geometry: with the level bytes in shared memory one CTA of 1024 threads owns an SM (large
-// surfaces) or two CTAs of 512 share it (V <= ~110k); otherwise two CTAs of 512 with global bytes.
-void tfce_sweep_geometry(int32_t Vmax, int num_sms, int *threads, int *ctas_per_sm, size_t *dyn_smem) {
+// =================================================================================================
+// Basin sweep (symmetric adjacency) -- the production kernel.
+//
+// Observation: a vertex is connected, inside the superlevel set of its own activation level, to any
+// neighbour that activated at a strictly earlier level -- and through it, step by step, to a vertex
+// with no earlier neighbour (a "peak").  So every vertex can inherit a BASIN id from one earlier
+// neighbour, and connectivity only has to be tracked between basins, of which there are 10-100x
+// fewer than vertices: the lock-free union-find of the level sweep lives on the basin ids, in
+// SHARED memory when it fits, and a vertex only issues a union when an earlier neighbour carries a
+// different basin id.  The assignment itself needs no pointer chasing because it is done in level
+// order: when level l+1 is assigned, every basin id of levels <= l is final.
+//
+//   P   one pass in vertex order: ascent pointer up[v] = earliest-level neighbour (ELL row + level
+//       bytes in shared memory), peaks get compact basin ids
+//   per level l (two __syncthreads):
+//     I1  unions between the basins of level-l vertices and their earlier neighbours
+//         (+ component-tree links of level l-1, which touch no union-find state)
+//     I2  sizes and changed components of level l  (+ basin assignment of the next level)
+//   then the per-node walk and the outputs exactly as in V2: values are bit-identical.
+//
+// Vertices are bucketed by level with a STABLE counting sort (per-warp chunks, warp-local cursors):
+// bucket entries ascend in vertex id, so with the locality relabelling of the graph a warp's 32
+// vertices and all their neighbours fall into a handful of cache lines (few wavefronts per request).
+struct RowIter {
+    const int32_t *ell;
+    const int32_t *indices;
+    int64_t r0, r1;
+    int nchunks;
+    __device__ __forceinline__ RowIter(const SurfDesc &sd, int u) {
+        if (sd.ell) {
+            ell = sd.ell + (size_t)u * sd.ell_width;
+            indices = nullptr;
+            r0 = r1 = 0;
+            nchunks = sd.ell_width >> 3;
+        } else {
+            ell = nullptr;
+            indices = sd.indices;
+            r0 = sd.indptr[u];
+            r1 = sd.indptr[u + 1];
+            nchunks = (int)((r1 - r0 + 7) >> 3);
+        }
+    }
+    // 8 neighbour ids (-1 = none); ELL rows come in with two 128-bit loads from one 32-byte sector
+    __device__ __forceinline__ void load(int c, int (&nb)[8]) const {
+        if (ell) {
+            const int4 a = __ldg(reinterpret_cast<const int4 *>(ell) + 2 * c);
+            const int4 b2 = __ldg(reinterpret_cast<const int4 *>(ell) + 2 * c + 1);
+            nb[0] = a.x; nb[1] = a.y; nb[2] = a.z; nb[3] = a.w;
+            nb[4] = b2.x; nb[5] = b2.y; nb[6] = b2.z; nb[7] = b2.w;
+        } else {
+            const int64_t k0 = r0 + 8 * (int64_t)c;
+            const int cnt = (int)min((int64_t)8, r1 - k0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nb[j] = (j < cnt) ? indices[k0 + j] : -1;
+        }
+    }
+};
+
+struct BasinWs {
+    int *up;            // ascent pointer (self for a peak)
+    int *basin;         // compact basin id per vertex
+    int *leaf;          // leaf node per SORTED POSITION (same indexing as order[])
+    int *order;         // vertices by (activation level, vertex id)
+    int2 *nodes;
+    int2 *mlist[2];
+    int2 *clist;
+    int *bparent_g, *bsize_g, *bcur_g; // global fallback of the per-basin arrays
+    float *nodeval;
+    unsigned char *blev_g;
+    unsigned char *lev8_g;
+};
+
+size_t tfce_basin_slot_bytes(int32_t Vmax) {
+    const size_t per4 = align_up(sizeof(int) * (size_t)Vmax, 256);
+    const size_t per8 = align_up(sizeof(int2) * (size_t)Vmax, 256);
+    return per4 * 8 + per8 * 4 + 2 * align_up((size_t)Vmax, 256);
+}
+
+__device__ __forceinline__ BasinWs carve_basin(char *base, int32_t Vmax) {
+    const size_t per4 = align_up(sizeof(int) * (size_t)Vmax, 256);
+    const size_t per8 = align_up(sizeof(int2) * (size_t)Vmax, 256);
+    const size_t per1 = align_up((size_t)Vmax, 256);
+    BasinWs w;
+    w.up = reinterpret_cast<int *>(base);
+    w.basin = reinterpret_cast<int *>(base + per4);
+    w.leaf = reinterpret_cast<int *>(base + 2 * per4);
+    w.order = reinterpret_cast<int *>(base + 3 * per4);
+    w.bparent_g = reinterpret_cast<int *>(base + 4 * per4);
+    w.bsize_g = reinterpret_cast<int *>(base + 5 * per4);
+    w.bcur_g = reinterpret_cast<int *>(base + 6 * per4);
+    w.nodeval = reinterpret_cast<float *>(base + 7 * per4);
+    char *b8 = base + 8 * per4;
+    w.nodes = reinterpret_cast<int2 *>(b8);
+    w.mlist[0] = reinterpret_cast<int2 *>(b8 + per8);
+    w.mlist[1] = reinterpret_cast<int2 *>(b8 + 2 * per8);
+    w.clist = reinterpret_cast<int2 *>(b8 + 3 * per8);
+    w.blev_g = reinterpret_cast<unsigned char *>(b8 + 4 * per8);
+    w.lev8_g = w.blev_g + per1;
+    return w;
+}
+
+// find with path halving on a plain (generic: shared or global) pointer array
+__device__ __forceinline__ int bf_find(int *parent, int v) {
+    int cur = v;
+    int p = parent[cur];
+    while (p != cur) {
+        const int gp = parent[p];
+        if (gp != p) parent[cur] = gp;
+        cur = p;
+        p = gp;
+    }
+    return cur;
+}
+
+__global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_basin_kernel(SweepParams P, int smem_budget) {
+    extern __shared__ __align__(16) unsigned char sDyn[];
+    __shared__ float sT[2][kMaxSteps];
+    __shared__ float sHH[2][kMaxSteps];
+    __shared__ int sNs[2];
+    __shared__ float sDelta[2];
+    __shared__ int sStatus[2];
+    __shared__ int sStart[kMaxSteps + 1];
+    __shared__ float sRed[2][kSweepMaxThreads / 32];
+    __shared__ int sItem;
+    __shared__ int sMcount[2];
+    __shared__ int sCcount[2];
+    __shared__ int sNB;
+
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int nwarps = nthr >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const BasinWs ws = carve_basin(P.workspace + (size_t)blockIdx.x * P.slot_stride, P.Vmax);
+    const int total_items = P.B * P.S;
+
+    for (;;) {
+        if (tid == 0) sItem = atomicAdd(P.work_counter, 1);
+        __syncthreads();
+        const int item = sItem;
+        if (item >= total_items) break;
+        const int s = P.surf_order[item / P.B];
+        const int b = item % P.B;
+        const SurfDesc sd = P.surfs[s];
+        const int V = sd.V;
+        const float *__restrict__ x = P.stat + (size_t)b * P.ld + sd.col_off;
+        const int32_t *__restrict__ vmap = sd.vmap;
+        long long tk = P.timing ? clock64() : 0;
+#define TMB_TICK(i)                                                                  \
+        if (P.timing && tid == 0) {                                                  \
+            const long long now = clock64();                                         \
+            atomicAdd(P.timing + (i), (unsigned long long)(now - tk));               \
+            tk = now;                                                                \
+        }
+        // shared-memory layout: [level bytes | scratch: sort histogram, later the per-basin arrays]
+        const int hist_bytes = nwarps * kMaxSteps * (int)sizeof(int);
+        const int lev_bytes = (int)align_up((size_t)V, 16);
+        const bool lev_smem = lev_bytes + hist_bytes <= smem_budget;
+        unsigned char *const lev8 = lev_smem ? sDyn : ws.lev8_g;
+        const int scratch_off = lev_smem ? lev_bytes : 0;
+        int *const sHist = reinterpret_cast<int *>(sDyn + scratch_off); // [nwarps][kMaxSteps]
+
+        for (int i = tid; i < nwarps * kMaxSteps; i += nthr) sHist[i] = 0;
+        if (tid == 0) { sMcount[0] = sMcount[1] = 0; sCcount[0] = sCcount[1] = 0; sNB = 0; }
+        if (P.tab_ns) {
+            const size_t e0 = ((size_t)b * P.S + s) * 2;
+            for (int i = tid; i < 2 * kMaxSteps; i += nthr) {
+                const int sg = i / kMaxSteps, l = i % kMaxSteps;
+                sT[sg][l] = P.tab_T[(e0 + sg) * kMaxSteps + l];
+                sHH[sg][l] = P.tab_HH[(e0 + sg) * kMaxSteps + l];
+            }
+            if (tid < 2) {
+                const bool on = (tid == 0) || P.two_sided;
+                sNs[tid] = on ? P.tab_ns[e0 + tid] : 0;
+                sDelta[tid] = P.tab_delta[e0 + tid];
+                sStatus[tid] = on ? P.tab_status[e0 + tid] : 0;
+            }
+            __syncthreads();
+        } else {
+            float mp = -INFINITY, mn = -INFINITY;
+            for (int v = tid; v < V; v += nthr) {
+                float xv = x[v];
+                mp = fmaxf(mp, xv);
+                mn = fmaxf(mn, -xv);
+            }
+            mp = warp_max(mp);
+            mn = warp_max(mn);
+            if (lane == 0) { sRed[0][wid] = mp; sRed[1][wid] = mn; }
+            __syncthreads();
+            if (tid == 0 || tid == 32) {
+                const int sg = tid ? 1 : 0;
+                float mx = -INFINITY;
+                for (int w = 0; w < nwarps; ++w) mx = fmaxf(mx, sRed[sg][w]);
+                int ns = 0, st = 0;
+                float d = 0.f;
+                if ((sg == 0 || P.two_sided) && mx >= 0.f) {
+                    d = __fdiv_rn(mx, 100.0f);
+                    if (d == 0.f) {
+                        st = 1;
+                    } else {
+                        float T = mx;
+                        while (T >= 0.f) {
+                            if (ns == kMaxSteps) { st = 2; ns = 0; break; }
+                            sT[sg][ns] = T;
+                            sHH[sg][ns] = (sd.H == 2.0f) ? __fmul_rn(T, T) : (float)pow((double)T, (double)sd.H);
+                            ++ns;
+                            T = __fsub_rn(T, d);
+                        }
+                    }
+                }
+                sNs[sg] = ns;
+                sDelta[sg] = d;
+                sStatus[sg] = st;
+            }
+            __syncthreads();
+        }
+        const int ns0 = sNs[0], ns1 = sNs[1];
+        const int nlev = max(ns0, ns1);
+        TMB_TICK(0)
+
+        // ---- activation level per vertex + STABLE counting sort by level ----------------------------
+        // warp w owns the contiguous vertex chunk [w*chunk, (w+1)*chunk) and its own histogram row
+        const int chunk = (int)align_up((size_t)(V + nwarps - 1) / nwarps, 32);
+        const int c_beg = wid * chunk, c_end = min(V, c_beg + chunk);
+        int *const myHist = sHist + wid * kMaxSteps;
+        for (int v0 = c_beg; v0 < c_end; v0 += 32) {
+            const int v = v0 + lane;
+            int code = 0;
+            if (v < c_end) {
+                const float xv = x[vmap ? vmap[v] : v];
+                if (xv > 0.f || xv < 0.f) {
+                    const int sg = xv < 0.f;
+                    const int ns = sg ? ns1 : ns0;
+                    const float ax = fabsf(xv);
+                    const float *T = sT[sg];
+                    int lo = 1, hi = ns;
+                    while (lo < hi) {
+                        int mid = (lo + hi) >> 1;
+                        if (ax > T[mid]) hi = mid; else lo = mid + 1;
+                    }
+                    if (lo < ns) code = lo | (sg << 7);
+                }
+                lev8[v] = (unsigned char)code;
+            }
+            const int lev = code & 0x7f;
+            const unsigned peers = __match_any_sync(0xffffffffu, lev);
+            if (lev > 0 && lane == (__ffs(peers) - 1)) myHist[lev] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        // level starts, then per-(warp, level) cursors = start[level] + counts of the earlier warps
+        if (tid < kMaxSteps) {
+            int tot = 0;
+            for (int w = 0; w < nwarps; ++w) { const int c = sHist[w * kMaxSteps + tid]; sHist[w * kMaxSteps + tid] = tot; tot += c; }
+            sStart[tid] = tot; // per-level totals for now
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int l = 0; l < kMaxSteps; ++l) { const int c = (l == 0) ? 0 : sStart[l]; sStart[l] = run; run += c; }
+            sStart[kMaxSteps] = run;
+        }
+        __syncthreads();
+        for (int v0 = c_beg; v0 < c_end; v0 += 32) {
+            const int v = v0 + lane;
+            const int lev = (v < c_end) ? (lev8[v] & 0x7f) : 0;
+            const unsigned peers = __match_any_sync(0xffffffffu, lev);
+            int base = 0;
+            if (lev > 0) base = myHist[lev] + sStart[lev];
+            __syncwarp();
+            if (lev > 0) {
+                ws.order[base + __popc(peers & lt_mask)] = v;
+                if (lane == (__ffs(peers) - 1)) myHist[lev] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        const int total_active = sStart[kMaxSteps];
+        TMB_TICK(1)
+
+        // ---- P: ascent pointer in vertex order (coalesced ELL rows); peaks get compact basin ids --------
+        for (int v = tid; v < V; v += nthr) {
+            const int cv = lev8[v];
+            if (cv == 0) continue;
+            const int lv = cv & 0x7f;
+            int best = v, bestlev = lv;
+            const RowIter row(sd, v);
+            for (int c = 0; c < row.nchunks; ++c) {
+                int nb[8];
+                row.load(c, nb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (nb[j] < 0) continue;
+                    const int ca = lev8[nb[j]];
+                    if (ca == 0 || ((ca ^ cv) & 0x80)) continue;
+                    const int la = ca & 0x7f;
+                    if (la < bestlev) { best = nb[j]; bestlev = la; }
+                }
+            }
+            ws.up[v] = best;
+            if (best == v) {
+                const int pid = atomicAdd(&sNB, 1);
+                ws.basin[v] = pid;
+                ws.blev_g[pid] = (unsigned char)cv;
+            }
+        }
+        __syncthreads();
+        const int NB = sNB;
+        // per-basin arrays: parent + level byte first, then size, then current node, while they fit
+        int avail = smem_budget - scratch_off;
+        int off = scratch_off;
+        int *bparent = ws.bparent_g, *bsize = ws.bsize_g, *bcur = ws.bcur_g;
+        unsigned char *blev = ws.blev_g;
+        const int nb_al = (int)align_up((size_t)NB, 4);
+        if (avail >= nb_al * 5) {
+            bparent = reinterpret_cast<int *>(sDyn + off); off += nb_al * 4;
+            blev = sDyn + off; off += nb_al; avail -= nb_al * 5;
+            if (avail >= nb_al * 4) { bsize = reinterpret_cast<int *>(sDyn + off); off += nb_al * 4; avail -= nb_al * 4; }
+            if (avail >= nb_al * 4) { bcur = reinterpret_cast<int *>(sDyn + off); off += nb_al * 4; avail -= nb_al * 4; }
+        }
+        for (int i = tid; i < NB; i += nthr) {
+            bparent[i] = i;
+            bsize[i] = 0;
+            bcur[i] = -1;
+            if (blev != ws.blev_g) blev[i] = ws.blev_g[i];
+        }
+        // basin ids of the first non-empty level (its vertices are all peaks or ... have no earlier level)
+        __syncthreads();
+        TMB_TICK(2)
+
+        const int last_level = (P.stop_level >= 0) ? min(P.stop_level, nlev - 1) : nlev - 1;
+        bool pend = false;
+        int pend_beg = 0, pend_end = 0, pend_buf = 0, pend_nodebase = 0, pend_lev = 0;
+        int node_base = 0;
+        int buf = 0;
+        // assignment of the first non-empty level: every vertex there is a peak (no earlier level exists)
+        int assigned_upto = 0; // levels <= assigned_upto carry final basin ids
+        for (int l = 1; l < nlev; ++l)
+            if (sStart[l + 1] > sStart[l]) { assigned_upto = l; break; }
+
+        for (int lev = 1; lev <= last_level + 1; ++lev) {
+            const bool have_level = lev <= last_level;
+            const int beg = have_level ? sStart[lev] : 0;
+            const int end = have_level ? sStart[lev + 1] : 0;
+            if (have_level && end == beg) continue;
+            // ================= I1: tree links of the previous level + unions of this level ==============
+            if (pend) {
+                const int ccount = sCcount[pend_buf];
+                const int mcount = sMcount[pend_buf];
+                for (int c = tid; c < ccount; c += nthr) {
+                    const int2 e = ws.clist[c];
+                    const int r = e.x, old = e.y;
+                    const int j = pend_nodebase + c;
+                    const int sg = blev[r] >> 7;
+                    ws.nodes[j] = make_int2(bsize[r], (sg << 31) | (pend_lev << 24) | kNone);
+                    if (old >= 0) ws.nodes[old].y = (ws.nodes[old].y & 0xFF000000) | j;
+                }
+                const int2 *ml = ws.mlist[pend_buf];
+                for (int m = tid; m < mcount; m += nthr) {
+                    const int2 e = ml[m];
+                    const int o = bcur[e.x];
+                    const int jn = bcur[e.y];
+                    ws.nodes[o].y = (ws.nodes[o].y & 0xFF000000) | jn;
+                }
+                for (int idx = pend_beg + tid; idx < pend_end; idx += nthr)
+                    ws.leaf[idx] = bcur[ws.leaf[idx]];
+            }
+            if (!have_level) break;
+            int2 *mcur = ws.mlist[buf];
+            for (int idx = beg + tid; idx < end; idx += nthr) {
+                const int u = ws.order[idx];
+                const int cu = lev8[u];
+                const int bu = ws.basin[u];
+                const RowIter row(sd, u);
+                int ru = bu;
+                for (int c = 0; c < row.nchunks; ++c) {
+                    int nb[8];
+                    row.load(c, nb);
+                    int ba[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        ba[j] = -1;
+                        if (nb[j] < 0) continue;
+                        const int a = nb[j];
+                        const int ca = lev8[a];
+                        if (ca == 0 || ((ca ^ cu) & 0x80)) continue;
+                        // earlier-activated neighbour (same level: the pair is seen from both ends, join once)
+                        if (ca < cu || (ca == cu && a < u)) ba[j] = ws.basin[a];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (ba[j] < 0 || ba[j] == bu) continue;
+                        int ra = bf_find(bparent, ba[j]);
+                        ru = bf_find(bparent, ru);
+                        while (ru != ra) {
+                            const int kru = ((blev[ru] & 0x7f) << 24) | ru, kra = ((blev[ra] & 0x7f) << 24) | ra;
+                            const int hi = kru > kra ? ru : ra, lo = kru > kra ? ra : ru;
+                            const int old = atomicCAS(bparent + hi, hi, lo);
+                            if (old == hi) {
+                                if ((blev[hi] & 0x7f) != lev) { // an older component lost its root
+                                    const int m = atomicAdd(&sMcount[buf], 1);
+                                    mcur[m] = make_int2(hi, -1);
+                                }
+                                ru = lo;
+                                break;
+                            }
+                            const int nh = bf_find(bparent, old);
+                            if (hi == ru) { ru = nh; ra = bf_find(bparent, ra); }
+                            else          { ra = nh; ru = bf_find(bparent, ru); }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            TMB_TICK(3)
+            // ================= I2: sizes + changed components; basin ids of the next level ==============
+            {
+                const int mcount = sMcount[buf];
+                if (tid == 0) { sMcount[buf ^ 1] = 0; sCcount[buf ^ 1] = 0; }
+                const int span = end - beg;
+                const int iters = (span + nthr - 1) / nthr;
+                for (int it = 0; it < iters; ++it) {
+                    const int idx = beg + it * nthr + tid;
+                    const bool valid = idx < end;
+                    int r = -1 - lane;
+                    if (valid) {
+                        const int u = ws.order[idx];
+                        r = bf_find(bparent, ws.basin[u]);
+                        ws.leaf[idx] = r;
+                    }
+                    const unsigned peers = __match_any_sync(0xffffffffu, r);
+                    if (valid && lane == (__ffs(peers) - 1)) {
+                        atomicAdd(bsize + r, __popc(peers));
+                        int old = bcur[r];
+                        for (;;) {
+                            if (old >= node_base || old == kPending) break;
+                            const int prev = atomicCAS(bcur + r, old, kPending);
+                            if (prev == old) {
+                                const int pos = atomicAdd(&sCcount[buf], 1);
+                                ws.clist[pos] = make_int2(r, old);
+                                atomicExch(bcur + r, node_base + pos);
+                                break;
+                            }
+                            old = prev;
+                        }
+                    }
+                }
+                for (int m = tid; m < mcount; m += nthr) {
+                    const int h = mcur[m].x;
+                    const int r = bf_find(bparent, h);
+                    mcur[m].y = r;
+                    atomicAdd(bsize + r, bsize[h]);
+                }
+                // basin ids of the next non-empty level: inherit from the ascent target (an earlier level,
+                // final by now).  Peaks already carry their own id.
+                int nl = lev + 1;
+                while (nl <= last_level && sStart[nl + 1] == sStart[nl]) ++nl;
+                if (nl <= last_level && nl > assigned_upto) {
+                    const int nbeg = sStart[nl], nend = sStart[nl + 1];
+                    for (int idx = nbeg + tid; idx < nend; idx += nthr) {
+                        const int v = ws.order[idx];
+                        const int t = ws.up[v];
+                        if (t != v) ws.basin[v] = ws.basin[t];
+                    }
+                }
+            }
+            __syncthreads();
+            TMB_TICK(4)
+            pend = true; pend_beg = beg; pend_end = end; pend_buf = buf; pend_nodebase = node_base; pend_lev = lev;
+            node_base += sCcount[buf];
+            buf ^= 1;
+        }
+        __syncthreads();
+        const int num_nodes = node_base;
+
+        // ---- outputs (identical to V2) -------------------------------------------------------------
+        if (P.stop_level >= 0) {
+            for (int v = tid; v < V; v += nthr) {
+                const int o = vmap ? vmap[v] : v;
+                int lab = -1, ext = 0;
+                const int code = lev8[v];
+                if (code != 0 && !(code & 0x80) && (code & 0x7f) <= last_level) {
+                    const int r = bf_find(bparent, ws.basin[v]);
+                    lab = r;
+                    ext = bsize[r];
+                }
+                P.labels[o] = lab;
+                P.extents[o] = ext;
+            }
+            if (tid == 0 && P.threshold_out)
+                *P.threshold_out = (P.stop_level < ns0) ? sT[0][P.stop_level] : NAN;
+        } else {
+            float *nodeval = ws.nodeval;
+            const bool per_vertex_walk = P.accumulate != 0;
+            if (!per_vertex_walk) {
+                for (int j = tid; j < num_nodes; j += nthr)
+                    nodeval[j] = walk_path(ws.nodes, sd.powE, sHH, sNs, j, 0.f);
+                __syncthreads();
+            }
+            TMB_TICK(5)
+            if (P.timing && tid == 0) { atomicAdd(P.timing + 7, (unsigned long long)NB); }
+            float m0 = 0.f, m1 = 0.f;
+            const float d0 = sDelta[0], d1 = sDelta[1];
+            const float *__restrict__ w = sd.weight;
+            const bool want_maps = (P.tfce_pos != nullptr) || (P.tfce_neg != nullptr);
+            if (want_maps && !P.accumulate) {
+                for (int v = tid; v < V; v += nthr) {
+                    const size_t o = (size_t)b * P.ld + sd.col_off + v;
+                    if (P.tfce_pos) P.tfce_pos[o] = 0.f;
+                    if (P.tfce_neg) P.tfce_neg[o] = 0.f;
+                }
+                __syncthreads();
+            }
+            for (int idx = tid; idx < total_active; idx += nthr) {
+                const int u = ws.order[idx];
+                const bool neg = (lev8[u] & 0x80) != 0;
+                float val;
+                if (per_vertex_walk || want_maps) {
+                    const size_t o = (size_t)b * P.ld + sd.col_off + (vmap ? vmap[u] : u);
+                    float *dst = neg ? P.tfce_neg : P.tfce_pos;
+                    if (per_vertex_walk) val = walk_path(ws.nodes, sd.powE, sHH, sNs, ws.leaf[idx], dst ? dst[o] : 0.f);
+                    else val = nodeval[ws.leaf[idx]];
+                    if (dst) dst[o] = val;
+                } else {
+                    val = nodeval[ws.leaf[idx]];
+                }
+                float sc = __fmul_rn(val, neg ? d1 : d0);
+                if (w) sc = __fmul_rn(sc, w[u]);
+                if (neg) m1 = fmaxf(m1, sc); else m0 = fmaxf(m0, sc);
+            }
+            m0 = warp_max(m0);
+            m1 = warp_max(m1);
+            __syncthreads();
+            if (lane == 0) { sRed[0][wid] = m0; sRed[1][wid] = m1; }
+            __syncthreads();
+            if (tid == 0) {
+                float a = 0.f, c = 0.f;
+                for (int w2 = 0; w2 < nwarps; ++w2) { a = fmaxf(a, sRed[0][w2]); c = fmaxf(c, sRed[1][w2]); }
+                const size_t o = ((size_t)b * P.S + s) * 2;
+                if (P.max_out) { P.max_out[o] = a; P.max_out[o + 1] = c; }
+                if (P.status) { P.status[o] = sStatus[0]; P.status[o + 1] = sStatus[1]; }
+            }
+        }
+        __syncthreads();
+        TMB_TICK(6)
+#undef TMB_TICK
+    }
+}
+
+// Launch geometry.  V2 (directed graphs): level bytes in shared memory, 1 CTA x 1024 threads per SM for
+// large surfaces, 2 x 512 for V <= ~110k, global bytes beyond 220k.  V3 (basin sweep): the whole opt-in
+// shared memory of the SM is split between the resident CTAs: 1 x 1024 threads for large surfaces,
+// 2 x 512 below 100k vertices, 4 x 256 below 40k (small surfaces are latency bound: more items in flight).
+void tfce_sweep_geometry(int32_t Vmax, int use_basin, int *threads, int *ctas_per_sm, size_t *dyn_smem) {
     const size_t need = align_up((size_t)Vmax, 16);
+    if (use_basin) {
+        const size_t total = 216 * 1024;
+        if (Vmax <= 40000) { *threads = 256; *ctas_per_sm = 4; }
+        else if (Vmax <= 100000) { *threads = 512; *ctas_per_sm = 2; }
+        else { *threads = 1024; *ctas_per_sm = 1; }
+        *dyn_smem = total / *ctas_per_sm - 6 * 1024;
+        return;
+    }
     if (need <= 108 * 1024) { *threads = 512; *ctas_per_sm = 2; *dyn_smem = need; }
     else if (need <= 220 * 1024) { *threads = 1024; *ctas_per_sm = 1; *dyn_smem = need; }
     else { *threads = 512; *ctas_per_sm = 2; *dyn_smem = 0; }
-    (void)num_sms;
+}
+
+size_t tfce_slot_bytes_for(int32_t Vmax, int use_basin) {
+    return use_basin ? tfce_basin_slot_bytes(Vmax) : tfce_slot_bytes(Vmax);
 }
 
 int launch_tfce_sweep(const SweepParams &p, int num_slots, cudaStream_t stream) {
     const int items = p.B * p.S;
     if (items <= 0) return 0;
+    const int use_basin = (p.flags & 2) != 0;
     int threads, per_sm;
     size_t dyn;
-    tfce_sweep_geometry(p.Vmax, 0, &threads, &per_sm, &dyn);
+    tfce_sweep_geometry(p.Vmax, use_basin, &threads, &per_sm, &dyn);
     int grid = items < num_slots ? items : num_slots;
     TMB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
     const bool cached = (p.flags & 1) != 0;
-    if (dyn > 0) {
+    if (use_basin) {
+        TMB_CUDA(cudaFuncSetAttribute(tfce_basin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        tfce_basin_kernel<<<grid, threads, dyn, stream>>>(p, (int)dyn);
+    } else if (dyn > 0) {
         if (cached) {
             TMB_CUDA(cudaFuncSetAttribute(tfce_sweep_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             tfce_sweep_kernel<true, true><<<grid, threads, dyn, stream>>>(p);
