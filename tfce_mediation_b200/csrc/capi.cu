@@ -325,8 +325,8 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
     {
         const char *pt = getenv("TMB_PHASE_TIMING");
         if (pt && pt[0] == '1') {
-            if ((e = cudaMalloc(&p->d_timing, sizeof(unsigned long long) * 12)) != cudaSuccess) return fail("malloc", e);
-            cudaMemset(p->d_timing, 0, sizeof(unsigned long long) * 12);
+            if ((e = cudaMalloc(&p->d_timing, sizeof(unsigned long long) * 272)) != cudaSuccess) return fail("malloc", e);
+            cudaMemset(p->d_timing, 0, sizeof(unsigned long long) * 272);
         }
     }
     if ((e = cudaMalloc(&p->d_workspace, p->slot_stride * (size_t)p->num_slots)) != cudaSuccess) return fail("malloc workspace", e);
@@ -340,7 +340,7 @@ extern "C" int tmb_plan_destroy(tmb_plan *p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     if (p->d_timing) {
-        unsigned long long t[12];
+        unsigned long long t[272];
         if (cudaMemcpy(t, p->d_timing, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess) {
             static const char *names_v2[7] = {"tables", "levels+sort", "X: P2bc+P1", "Y: P2a", "tail", "node walk", "finalize"};
             static const char *names_v3[7] = {"tables", "levels+sort", "ascent+init", "I1: unions", "I2: sizes", "node walk", "finalize"};
@@ -351,6 +351,14 @@ extern "C" int tmb_plan_destroy(tmb_plan *p) {
             fprintf(stderr, "[tmb phase timing] total %.3e cycles, nodes %llu\n", tot, t[7]);
             for (int i = 0; i < 7; ++i) fprintf(stderr, "  %-12s %6.2f%%\n", names[i], tot > 0 ? 100.0 * t[i] / tot : 0.0);
 
+        }
+        if (p->use_basin) {
+            double tot = 0;
+            for (int i = 0; i < 7; ++i) tot += (double)t[i];
+            fprintf(stderr, "  per-level share of I1 / I2 (levels 1..127, %% of total):\n");
+            for (int l = 1; l < 128; ++l)
+                if (t[16 + l] || t[144 + l])
+                    fprintf(stderr, "   L%-3d %5.2f %5.2f\n", l, 100.0 * t[16 + l] / tot, 100.0 * t[144 + l] / tot);
         }
         cudaFree(p->d_timing);
     }

@@ -30,6 +30,8 @@
 #include "common.cuh"
 
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 
 namespace tmb {
 
@@ -614,12 +616,20 @@ struct RowIter {
     }
 };
 
+// component-tree node of the basin sweep: pow(size, E) is looked up once at creation, so a hop of the
+// final walk is a single 128-bit load
+struct __align__(16) TreeNode {
+    double pw;
+    int pack; // (sign<<31) | (level<<24) | parent
+    int size;
+};
+
 struct BasinWs {
     int *up;            // ascent pointer (self for a peak)
     int *basin;         // compact basin id per vertex
     int *leaf;          // leaf node per SORTED POSITION (same indexing as order[])
     int *order;         // vertices by (activation level, vertex id)
-    int2 *nodes;
+    TreeNode *nodes;    // {pow(size,E), (sign<<31)|(level<<24)|parent}
     int2 *mlist[2];
     int2 *clist;
     int *bparent_g, *bsize_g, *bcur_g; // global fallback of the per-basin arrays
@@ -631,7 +641,7 @@ struct BasinWs {
 size_t tfce_basin_slot_bytes(int32_t Vmax) {
     const size_t per4 = align_up(sizeof(int) * (size_t)Vmax, 256);
     const size_t per8 = align_up(sizeof(int2) * (size_t)Vmax, 256);
-    return per4 * 8 + per8 * 4 + 2 * align_up((size_t)Vmax, 256);
+    return per4 * 8 + per8 * 5 + 2 * align_up((size_t)Vmax, 256);
 }
 
 __device__ __forceinline__ BasinWs carve_basin(char *base, int32_t Vmax) {
@@ -648,11 +658,11 @@ __device__ __forceinline__ BasinWs carve_basin(char *base, int32_t Vmax) {
     w.bcur_g = reinterpret_cast<int *>(base + 6 * per4);
     w.nodeval = reinterpret_cast<float *>(base + 7 * per4);
     char *b8 = base + 8 * per4;
-    w.nodes = reinterpret_cast<int2 *>(b8);
-    w.mlist[0] = reinterpret_cast<int2 *>(b8 + per8);
-    w.mlist[1] = reinterpret_cast<int2 *>(b8 + 2 * per8);
-    w.clist = reinterpret_cast<int2 *>(b8 + 3 * per8);
-    w.blev_g = reinterpret_cast<unsigned char *>(b8 + 4 * per8);
+    w.nodes = reinterpret_cast<TreeNode *>(b8); // 16 bytes per node: two per8 blocks
+    w.mlist[0] = reinterpret_cast<int2 *>(b8 + 2 * per8);
+    w.mlist[1] = reinterpret_cast<int2 *>(b8 + 3 * per8);
+    w.clist = reinterpret_cast<int2 *>(b8 + 4 * per8);
+    w.blev_g = reinterpret_cast<unsigned char *>(b8 + 5 * per8);
     w.lev8_g = w.blev_g + per1;
     return w;
 }
@@ -670,7 +680,40 @@ __device__ __forceinline__ int bf_find(int *parent, int v) {
     return cur;
 }
 
-__global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_basin_kernel(SweepParams P, int smem_budget) {
+// One step of a component-tree walk: consume node `rec` (levels [its level, parent's level)) and move up.
+// Returns false when the root has been consumed.
+__device__ __forceinline__ bool walk_step(const TreeNode *__restrict__ nodes, const float (*sHH)[kMaxSteps],
+                                          const int *sNs, TreeNode &rec, float &acc) {
+    const int pk = rec.pack;
+    const int par = pk & kNone;
+    const int lv = (pk >> 24) & 0x7f;
+    const int sg = (pk >> 31) & 1;
+    TreeNode prec;
+    int endl;
+    if (par == kNone) {
+        endl = sNs[sg];
+    } else {
+        prec = nodes[par];
+        endl = (prec.pack >> 24) & 0x7f;
+    }
+    const double pw = rec.pw;
+    const float *hh = sHH[sg];
+    for (int l = lv; l < endl; ++l) acc = __fadd_rn(acc, __double2float_rn(__dmul_rn(pw, (double)hh[l])));
+    if (par == kNone) return false;
+    rec = prec;
+    return true;
+}
+
+__device__ __forceinline__ float walk_path16(const TreeNode *__restrict__ nodes, const float (*sHH)[kMaxSteps],
+                                             const int *sNs, int j, float acc) {
+    TreeNode rec = nodes[j];
+    while (walk_step(nodes, sHH, sNs, rec, acc)) {
+    }
+    return acc;
+}
+
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepParams P, int smem_budget) {
     extern __shared__ __align__(16) unsigned char sDyn[];
     __shared__ float sT[2][kMaxSteps];
     __shared__ float sHH[2][kMaxSteps];
@@ -869,7 +912,10 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_basin_kernel(SweepPa
         int off = scratch_off;
         int *bparent = ws.bparent_g, *bsize = ws.bsize_g, *bcur = ws.bcur_g;
         unsigned char *blev = ws.blev_g;
+        unsigned *bbits = reinterpret_cast<unsigned *>(ws.nodeval); // "changed in this level" bitset
         const int nb_al = (int)align_up((size_t)NB, 4);
+        const int bits_bytes = (int)align_up((size_t)(NB + 31) / 32 * 4, 16);
+        if (avail >= bits_bytes) { bbits = reinterpret_cast<unsigned *>(sDyn + off); off += bits_bytes; avail -= bits_bytes; }
         if (avail >= nb_al * 5) {
             bparent = reinterpret_cast<int *>(sDyn + off); off += nb_al * 4;
             blev = sDyn + off; off += nb_al; avail -= nb_al * 5;
@@ -882,6 +928,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_basin_kernel(SweepPa
             bcur[i] = -1;
             if (blev != ws.blev_g) blev[i] = ws.blev_g[i];
         }
+        for (int i = tid; i < (NB + 31) / 32; i += nthr) bbits[i] = 0u;
         // basin ids of the first non-empty level (its vertices are all peaks or ... have no earlier level)
         __syncthreads();
         TMB_TICK(2)
@@ -910,15 +957,21 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_basin_kernel(SweepPa
                     const int r = e.x, old = e.y;
                     const int j = pend_nodebase + c;
                     const int sg = blev[r] >> 7;
-                    ws.nodes[j] = make_int2(bsize[r], (sg << 31) | (pend_lev << 24) | kNone);
-                    if (old >= 0) ws.nodes[old].y = (ws.nodes[old].y & 0xFF000000) | j;
+                    const int sz = bsize[r];
+                    TreeNode nd;
+                    nd.pw = sd.powE[sz];
+                    nd.pack = (sg << 31) | (pend_lev << 24) | kNone;
+                    nd.size = sz;
+                    ws.nodes[j] = nd;
+                    if (old >= 0) ws.nodes[old].pack = (ws.nodes[old].pack & 0xFF000000) | j;
+                    atomicAnd(bbits + (r >> 5), ~(1u << (r & 31))); // release this level's claim
                 }
                 const int2 *ml = ws.mlist[pend_buf];
                 for (int m = tid; m < mcount; m += nthr) {
                     const int2 e = ml[m];
                     const int o = bcur[e.x];
                     const int jn = bcur[e.y];
-                    ws.nodes[o].y = (ws.nodes[o].y & 0xFF000000) | jn;
+                    ws.nodes[o].pack = (ws.nodes[o].pack & 0xFF000000) | jn;
                 }
                 for (int idx = pend_beg + tid; idx < pend_end; idx += nthr)
                     ws.leaf[idx] = bcur[ws.leaf[idx]];
@@ -970,6 +1023,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_basin_kernel(SweepPa
                 }
             }
             __syncthreads();
+            if (P.timing && tid == 0) atomicAdd(P.timing + 16 + lev, (unsigned long long)(clock64() - tk));
             TMB_TICK(3)
             // ================= I2: sizes + changed components; basin ids of the next level ==============
             {
@@ -977,29 +1031,33 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_basin_kernel(SweepPa
                 if (tid == 0) { sMcount[buf ^ 1] = 0; sCcount[buf ^ 1] = 0; }
                 const int span = end - beg;
                 const int iters = (span + nthr - 1) / nthr;
-                for (int it = 0; it < iters; ++it) {
-                    const int idx = beg + it * nthr + tid;
-                    const bool valid = idx < end;
-                    int r = -1 - lane;
-                    if (valid) {
-                        const int u = ws.order[idx];
-                        r = bf_find(bparent, ws.basin[u]);
-                        ws.leaf[idx] = r;
+                for (int it = 0; it < iters; it += 4) { // 4 vertices per thread in flight (independent loads)
+                    int idxs[4], rr[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        idxs[q] = beg + (it + q) * nthr + tid;
+                        rr[q] = (it + q < iters && idxs[q] < end) ? ws.order[idxs[q]] : -1;
                     }
-                    const unsigned peers = __match_any_sync(0xffffffffu, r);
-                    if (valid && lane == (__ffs(peers) - 1)) {
-                        atomicAdd(bsize + r, __popc(peers));
-                        int old = bcur[r];
-                        for (;;) {
-                            if (old >= node_base || old == kPending) break;
-                            const int prev = atomicCAS(bcur + r, old, kPending);
-                            if (prev == old) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) rr[q] = (rr[q] >= 0) ? ws.basin[rr[q]] : -1;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (it + q >= iters) break; // warp-uniform
+                        const bool valid = rr[q] >= 0;
+                        int r = -1 - lane; // distinct dummy keys for idle lanes
+                        if (valid) {
+                            r = bf_find(bparent, rr[q]);
+                            ws.leaf[idxs[q]] = r;
+                        }
+                        const unsigned peers = __match_any_sync(0xffffffffu, r);
+                        if (valid && lane == (__ffs(peers) - 1)) {
+                            atomicAdd(bsize + r, __popc(peers));
+                            const unsigned bit = 1u << (r & 31);
+                            if (!(atomicOr(bbits + (r >> 5), bit) & bit)) { // first touch of this component in this level
                                 const int pos = atomicAdd(&sCcount[buf], 1);
-                                ws.clist[pos] = make_int2(r, old);
-                                atomicExch(bcur + r, node_base + pos);
-                                break;
+                                ws.clist[pos] = make_int2(r, bcur[r]);
+                                bcur[r] = node_base + pos;
                             }
-                            old = prev;
                         }
                     }
                 }
@@ -1023,6 +1081,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_basin_kernel(SweepPa
                 }
             }
             __syncthreads();
+            if (P.timing && tid == 0) atomicAdd(P.timing + 16 + 128 + lev, (unsigned long long)(clock64() - tk));
             TMB_TICK(4)
             pend = true; pend_beg = beg; pend_end = end; pend_buf = buf; pend_nodebase = node_base; pend_lev = lev;
             node_base += sCcount[buf];
@@ -1051,8 +1110,30 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_basin_kernel(SweepPa
             float *nodeval = ws.nodeval;
             const bool per_vertex_walk = P.accumulate != 0;
             if (!per_vertex_walk) {
-                for (int j = tid; j < num_nodes; j += nthr)
-                    nodeval[j] = walk_path(ws.nodes, sd.powE, sHH, sNs, j, 0.f);
+                for (int j0 = tid; j0 < num_nodes; j0 += 4 * nthr) { // 4 independent chains per thread
+                    TreeNode rec[4];
+                    float acc[4];
+                    bool live[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = j0 + q * nthr;
+                        live[q] = j < num_nodes;
+                        acc[q] = 0.f;
+                        if (live[q]) rec[q] = ws.nodes[j];
+                    }
+                    bool any = true;
+                    while (any) {
+                        any = false;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (live[q]) { live[q] = walk_step(ws.nodes, sHH, sNs, rec[q], acc[q]); any |= live[q]; }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = j0 + q * nthr;
+                        if (j < num_nodes) nodeval[j] = acc[q];
+                    }
+                }
                 __syncthreads();
             }
             TMB_TICK(5)
@@ -1076,7 +1157,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_basin_kernel(SweepPa
                 if (per_vertex_walk || want_maps) {
                     const size_t o = (size_t)b * P.ld + sd.col_off + (vmap ? vmap[u] : u);
                     float *dst = neg ? P.tfce_neg : P.tfce_pos;
-                    if (per_vertex_walk) val = walk_path(ws.nodes, sd.powE, sHH, sNs, ws.leaf[idx], dst ? dst[o] : 0.f);
+                    if (per_vertex_walk) val = walk_path16(ws.nodes, sHH, sNs, ws.leaf[idx], dst ? dst[o] : 0.f);
                     else val = nodeval[ws.leaf[idx]];
                     if (dst) dst[o] = val;
                 } else {
@@ -1105,23 +1186,29 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_basin_kernel(SweepPa
     }
 }
 
-// Launch geometry.  V2 (directed graphs): level bytes in shared memory, 1 CTA x 1024 threads per SM for
-// large surfaces, 2 x 512 for V <= ~110k, global bytes beyond 220k.  V3 (basin sweep): the whole opt-in
-// shared memory of the SM is split between the resident CTAs: 1 x 1024 threads for large surfaces,
-// 2 x 512 below 100k vertices, 4 x 256 below 40k (small surfaces are latency bound: more items in flight).
+// Launch geometry (measured on B200, profiles/README.md): the sweep is bound by the latency of dependent,
+// data-dependent loads, and a large L1 serves them better than a large shared-memory carve-out -- keeping
+// the 146 KB of level bytes of an fsaverage hemisphere in shared memory was 45% SLOWER than leaving them in
+// global memory behind a ~128 KB L1.  So only the small per-basin union-find arrays (and the sort histogram)
+// live in shared memory: ~100 KB per SM in total, split between the resident CTAs.
+//   basin sweep: 1 CTA x 1024 threads per SM for large surfaces, 2 x 512 below 100k vertices,
+//                4 x 256 below 40k (small surfaces are latency bound: more items in flight)
+//   V2 (directed adjacency): 2 CTAs x 512 threads, no dynamic shared memory.
 void tfce_sweep_geometry(int32_t Vmax, int use_basin, int *threads, int *ctas_per_sm, size_t *dyn_smem) {
-    const size_t need = align_up((size_t)Vmax, 16);
     if (use_basin) {
-        const size_t total = 216 * 1024;
+        size_t total = 100 * 1024;
         if (Vmax <= 40000) { *threads = 256; *ctas_per_sm = 4; }
         else if (Vmax <= 100000) { *threads = 512; *ctas_per_sm = 2; }
         else { *threads = 1024; *ctas_per_sm = 1; }
+        if (const char *g = getenv("TMB_GEOM")) { // "threads,ctas_per_sm" (development aid)
+            int t = 0, c = 0;
+            if (sscanf(g, "%d,%d", &t, &c) == 2 && t >= 64 && t <= 1024 && c >= 1 && c <= 8) { *threads = t; *ctas_per_sm = c; }
+        }
+        if (const char *g = getenv("TMB_SMEM_KB")) { int kb = atoi(g); if (kb >= 16 && kb <= 216) total = (size_t)kb * 1024; }
         *dyn_smem = total / *ctas_per_sm - 6 * 1024;
         return;
     }
-    if (need <= 108 * 1024) { *threads = 512; *ctas_per_sm = 2; *dyn_smem = need; }
-    else if (need <= 220 * 1024) { *threads = 1024; *ctas_per_sm = 1; *dyn_smem = need; }
-    else { *threads = 512; *ctas_per_sm = 2; *dyn_smem = 0; }
+    *threads = 512; *ctas_per_sm = 2; *dyn_smem = 0;
 }
 
 size_t tfce_slot_bytes_for(int32_t Vmax, int use_basin) {
@@ -1139,8 +1226,20 @@ int launch_tfce_sweep(const SweepParams &p, int num_slots, cudaStream_t stream) 
     TMB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
     const bool cached = (p.flags & 1) != 0;
     if (use_basin) {
-        TMB_CUDA(cudaFuncSetAttribute(tfce_basin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        tfce_basin_kernel<<<grid, threads, dyn, stream>>>(p, (int)dyn);
+        // register budget follows the geometry: 1024 threads -> 64 regs, 512 x 1 -> 128, 512 x 2 / 256 x 4 -> 64
+        if (threads > 512) {
+            TMB_CUDA(cudaFuncSetAttribute(tfce_basin_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            tfce_basin_kernel<1024, 1><<<grid, threads, dyn, stream>>>(p, (int)dyn);
+        } else if (threads > 256 && per_sm == 1) {
+            TMB_CUDA(cudaFuncSetAttribute(tfce_basin_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            tfce_basin_kernel<512, 1><<<grid, threads, dyn, stream>>>(p, (int)dyn);
+        } else if (threads > 256) {
+            TMB_CUDA(cudaFuncSetAttribute(tfce_basin_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            tfce_basin_kernel<512, 2><<<grid, threads, dyn, stream>>>(p, (int)dyn);
+        } else {
+            TMB_CUDA(cudaFuncSetAttribute(tfce_basin_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            tfce_basin_kernel<256, 4><<<grid, threads, dyn, stream>>>(p, (int)dyn);
+        }
     } else if (dyn > 0) {
         if (cached) {
             TMB_CUDA(cudaFuncSetAttribute(tfce_sweep_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));

@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""mmr-lr randomisation -- replaces the reference's fan-out of one `tm_multimodal mmr-lr-run` job per
+(100-permutation block, surface) (tm_mmr_rand_low_ram.py:237-260, tm_mmr_rand_low_ram_parallel.py:166-207).
+
+Reads the same tmi_temp/ state the reference's `mmr-lr` front end writes
+({i}_data_temp.npy float32 n x V_i, {i}_mask_temp.npy, {i}_adjacency_temp.npy, {i}_vdensity_temp.npy,
+opts.npy) and appends the same rows to <path>/perm_maxTFCE_surf{i}_tcon{c}.csv ('%f', positive then
+negative per shuffle).  All surfaces of a shuffle are processed together: one fused fit over the
+concatenated data and one TFCE launch over shuffles x contrasts x surfaces with per-surface (H, E).
+The permutation of shuffle p is the reference's deterministic rule np.random.seed(p + seed);
+np.random.permutation(range(n)) (tm_func.py:146-151), so rows are reproducible and row i of every
+surface file belongs to the same shuffle (the reference's apply_mfwer assumes exactly that).
+Under torchrun the range -pr a b is sharded over ranks; rank 0 writes.
+"""
+import argparse as ap
+import os
+from time import time
+
+import numpy as np
+
+from .. import parallel
+from ..tmanalysis import _common as C
+
+DESCRIPTION = "Batched GPU companion of mmr-lr (all surfaces of a permutation block at once)"
+
+
+def getArgumentParser(ap=ap.ArgumentParser(description=DESCRIPTION)):
+    ap.add_argument("-sn", "--surfacenumber", nargs="+", type=int, metavar=('INT'), required=False,
+                    help="Restrict to these surfaces (default: all, as one batch)")
+    ap.add_argument("-pr", "--permutationrange", nargs=2, type=int, metavar=('INT', 'INT'), required=True)
+    ap.add_argument("--path", nargs=1, type=str, metavar=('STR'), required=True)
+    ap.add_argument("--seed", nargs=1, type=int, metavar=('INT'), required=True)
+    ap.add_argument("--tmitemp", default="tmi_temp", help="Directory written by mmr-lr (default tmi_temp)")
+    ap.add_argument("-i", "--input", nargs="+", metavar=('*.csv'),
+                    help="Predictor file(s); default: those recorded in tmi_temp/opts.npy")
+    ap.add_argument("--tfce", nargs="+", type=float, help="H E [H E ...]; default: tmi_temp/opts.npy")
+    ap.add_argument("--assigntfcesettings", nargs="+", type=int, help="TFCE setting index per surface")
+    return ap
+
+
+def load_setup(opts):
+    tmp = opts.tmitemp
+    sopts = None
+    if os.path.exists("%s/opts.npy" % tmp):
+        try:
+            sopts = C.load("%s/opts.npy" % tmp).tolist()
+        except Exception:
+            sopts = None
+    inputs = opts.input or (getattr(sopts, "input", None) if sopts is not None else None)
+    if not inputs:
+        raise SystemExit("no predictor files: pass -i or provide tmi_temp/opts.npy")
+    pred_x = None
+    for f in inputs:
+        col = np.genfromtxt(f, delimiter=',')
+        pred_x = col if pred_x is None else np.column_stack([pred_x, col])
+    tfce = opts.tfce or (getattr(sopts, "tfce", None) if sopts is not None else None) or [2, 0.67]
+    assign = opts.assigntfcesettings or (getattr(sopts, "assigntfcesettings", None) if sopts is not None else None)
+    nsurf = 0
+    while os.path.exists("%s/%d_data_temp.npy" % (tmp, nsurf)):
+        nsurf += 1
+    surfaces = opts.surfacenumber if opts.surfacenumber else list(range(nsurf))
+    return pred_x, [float(t) for t in tfce], assign, surfaces
+
+
+def run(opts):
+    start_time = time()
+    np.seterr(divide="ignore", invalid="ignore")
+    from ..engine import PermutationEngine
+    pred_x, tfce, assign, surfaces = load_setup(opts)
+    tmp = opts.tmitemp
+    datas, surfs, off = [], [], 0
+    for sn in surfaces:
+        data = C.load("%s/%d_data_temp.npy" % (tmp, sn))
+        mask = C.load("%s/%d_mask_temp.npy" % (tmp, sn))
+        adjacency = C.load("%s/%d_adjacency_temp.npy" % (tmp, sn))
+        vdensity = C.load("%s/%d_vdensity_temp.npy" % (tmp, sn))
+        ptr = int(assign[sn] * 2) if assign else 0
+        H, E = tfce[ptr], tfce[ptr + 1]
+        keep = np.asarray(mask == 1)
+        if keep.shape[0] != len(adjacency):        # voxel surfaces store an all-True flattened mask
+            keep = None
+        w = None if vdensity.shape[0] == 1 else vdensity     # --noweight stores [1]
+        s = C.masked_surface(adjacency, H, E, keep, None, off)
+        if w is not None:
+            s.weight = np.ascontiguousarray(w, dtype=np.float32)
+        surfs.append(s)
+        datas.append(np.ascontiguousarray(data, dtype=np.float32))
+        off += data.shape[1]
+    y = np.ascontiguousarray(np.hstack(datas), dtype=np.float32)
+    n = y.shape[0]
+    X = np.column_stack([np.ones(n), pred_x])
+    k = X.shape[1]
+    eng = PermutationEngine(y, surfs, two_sided=True)
+    first, last = int(opts.permutationrange[0]), int(opts.permutationrange[1])
+    seed = int(opts.seed[0])
+    rank, ws, a, b = C.shard(first, last)
+    outdir = str(opts.path[0])
+    if rank == 0:
+        os.makedirs(outdir, exist_ok=True)
+    results = []
+    for p0, p1 in C.chunks(a, b):
+        idx = []
+        for perm_number in range(p0, p1 + 1):
+            np.random.seed(perm_number + seed)                       # tm_func.py:147-148
+            idx.append(np.random.permutation(list(range(n))))
+        results.append(eng.regression_block(X, perm_idx=np.stack(idx)))  # [P, C, S, 2]
+    local = np.concatenate(results, axis=0) if results else np.zeros((0, k - 1, len(surfs), 2), dtype=np.float32)
+    allrows = parallel.gather_rows(local)
+    if rank == 0:
+        for si, sn in enumerate(surfaces):
+            for c in range(k - 1):
+                C.append_rows("%s/perm_maxTFCE_surf%d_tcon%d.csv" % (outdir, sn, c + 1),
+                              allrows[:, c, si, :].reshape(-1), "%f")
+        print("Surfaces %s, permutations %d -> %d took %i seconds." % (surfaces, first, last, int(time() - start_time)))
+
+
+if __name__ == "__main__":
+    parser = getArgumentParser()
+    run(parser.parse_args())
