@@ -1073,10 +1073,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                 while (nl <= last_level && sStart[nl + 1] == sStart[nl]) ++nl;
                 if (nl <= last_level && nl > assigned_upto) {
                     const int nbeg = sStart[nl], nend = sStart[nl + 1];
-                    for (int idx = nbeg + tid; idx < nend; idx += nthr) {
-                        const int v = ws.order[idx];
-                        const int t = ws.up[v];
-                        if (t != v) ws.basin[v] = ws.basin[t];
+                    for (int idx0 = nbeg + tid; idx0 < nend; idx0 += 4 * nthr) { // 4 independent chains in flight
+                        int vv[4], tt[4], bb[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int idx = idx0 + q * nthr;
+                            vv[q] = idx < nend ? ws.order[idx] : -1;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) tt[q] = vv[q] >= 0 ? ws.up[vv[q]] : -1;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) bb[q] = (vv[q] >= 0 && tt[q] != vv[q]) ? ws.basin[tt[q]] : -1;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (vv[q] >= 0 && tt[q] != vv[q]) ws.basin[vv[q]] = bb[q];
                     }
                 }
             }
