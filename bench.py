@@ -12,7 +12,7 @@ vertices), 300 subjects, k=2, H=2, E=0.67, synthetic data
 
 Prints ONE JSON line (see the task contract): value = whole-job shuffles/s with inputs resident in
 HBM, device-timed, max over ranks; `e2e` = the same through PermutationEngine.regression_block with
-host index rows in / host maxima out; `roofline` for the dominant kernel (tfce_sweep_kernel);
+host index rows in / host maxima out; `roofline` for the dominant kernel (tfce_basin_kernel);
 `cpu_baseline` = the reference's own compiled kernels (oracle/_ref) on one host core.
 `--impl reference` times the reference's CPU implementation with all host cores.
 """
@@ -374,7 +374,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": eng.d2h_bytes // args.steps, "ms_per_step": e2e_ms / args.steps,
                     "data_upload_once_bytes": int(w["y"].nbytes), "data_upload_once_ms": data_upload_ms},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "tfce_sweep_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "tfce_basin_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_tfce * P, "kernel_ms_per_launch": tfce_ms,
                          "kernel_share_of_step": tfce_ms / (dev_ms / args.steps)},

@@ -181,6 +181,14 @@ int tmb_sobelz(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, con
 int tmb_voxel_adjacency(int device, const uint8_t *mask_host, int nx, int ny, int nz, int conn, int variant,
                         int32_t *num_voxel, int64_t *nnz, int64_t *indptr_host, int32_t *indices_host);
 
+/* ---------------------------------------------------------------------------------------------
+ * FWER-corrected p lookup == tmanalysis/calculate_fweP_vertex.py:37-42,61-69 (and _voxel.py:23-50):
+ * corrp[i] = max(searchsorted(sorted_max, values[i], "left") - 1, 0) / n for the ASCENDING sorted null
+ * maxima sorted_max_dev (float64 [n], as np.genfromtxt reads the CSV) and TFCE values float32 [m].
+ * ------------------------------------------------------------------------------------------- */
+int tmb_fwe_lookup(const double *sorted_max_dev, int n, const float *values_dev, int64_t m, double *corrp_dev,
+                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

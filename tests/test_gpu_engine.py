@@ -93,3 +93,22 @@ def test_voxel_style_single_surface_nan_to_zero():
         for c in range(k - 1):
             assert np.float32(oracle.perm_max_voxel(t[c + 1], run)) == got[p, c, 0, 0]
             assert np.float32(oracle.perm_max_voxel(t[c + 1] * -1, run)) == got[p, c, 0, 1]
+
+
+def test_observed_statistics_match_step1_writer_math():
+    """Identity permutation with full maps: pyfunc.py:80-91 write_vertStat_img's array math."""
+    from tfce_mediation_b200.engine import PermutationEngine
+    n, k = 40, 3
+    csr, V, y, X, surfs, w = _two_hemi_setup(4, n, k, 30, True)
+    eng = PermutationEngine(y, surfs, two_sided=True)
+    obs = eng.observed_statistics(X)
+    t = oracle.tval_int(X, np.linalg.inv(X.T @ X), y, n, k, 2 * V)[1:].astype(np.float32)
+    assert np.array_equal(obs["t"], t)
+    for c in range(k - 1):
+        for h in range(2):
+            seg = np.ascontiguousarray(t[c, h * V:(h + 1) * V])
+            want_pos = oracle.tfce_run(2, 0.67, csr, seg) * (seg.max() / 100) * w
+            want_neg = oracle.tfce_run(2, 0.67, csr, -seg) * ((-seg).max() / 100) * w
+            assert np.array_equal(obs["tfce_pos"][c, h * V:(h + 1) * V], want_pos)
+            assert np.array_equal(obs["tfce_neg"][c, h * V:(h + 1) * V], want_neg)
+            assert obs["max_pos"][c, h] == want_pos.max() and obs["max_neg"][c, h] == want_neg.max()

@@ -149,3 +149,18 @@ def test_mmr_lowram_rows_identical_to_reference_csv():
     for c, want in ((0, g["rows_tcon1"]), (1, g["rows_tcon2"])):
         rows = ["%f" % mx[p, c, 0, sg] for p in range(len(idx)) for sg in (0, 1)]
         assert rows == list(want)
+
+
+def test_fwe_lookup_vs_reference_outputs():
+    from tfce_mediation_b200.tmanalysis.calculate_fweP import fwe_corrected_p, fwe_image
+    import oracle
+    g = load("fwe.npz")
+    assert np.array_equal(fwe_corrected_p(g["perm_max"], g["values"]), g["corrp"])
+    rs = np.random.RandomState(0)
+    big = (np.abs(rs.standard_normal(50000)) * 100).astype(np.float32)
+    big[::7] = 0
+    pm = np.round(np.abs(rs.standard_normal(2000)) * 90, 4)
+    got = fwe_image(pm, big)
+    want = np.zeros(big.shape)
+    want[big > 0] = oracle.fwe_p(pm, big[big > 0])
+    assert np.array_equal(got, want)

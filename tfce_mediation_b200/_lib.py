@@ -49,6 +49,7 @@ SIGNATURES = {
     "tmb_se_of_slope": (_int, [_vp, _i64, _vp, _int, _vp, _i64, _vp]),
     "tmb_sobelz": (_int, [_vp, _int, _int, _i64, _i64, _vp, _i64, _int, _vp, _vp, _int, _int, _f64, _vp, _vp, _int,
                           _int, _f64, _vp, _vp, _int, _int, _vp, _vp, _i64, _vp]),
+    "tmb_fwe_lookup": (_int, [_vp, _int, _vp, _i64, _vp, _vp]),
     "tmb_voxel_adjacency": (_int, [_int, _vp, _int, _int, _int, _int, _int, _c.POINTER(_i32), _c.POINTER(_i64),
                                    _vp, _vp]),
 }

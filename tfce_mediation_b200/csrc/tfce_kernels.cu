@@ -682,12 +682,22 @@ __device__ __forceinline__ int bf_find(int *parent, int v) {
 
 // One step of a component-tree walk: consume node `rec` (levels [its level, parent's level)) and move up.
 // Returns false when the root has been consumed.
-__device__ __forceinline__ bool walk_step(const TreeNode *__restrict__ nodes, const float (*sHH)[kMaxSteps],
-                                          const int *sNs, TreeNode &rec, float &acc) {
+__device__ __forceinline__ bool walk_step(const TreeNode *__restrict__ nodes, const double (*sHH)[kMaxSteps],
+                                          const int *sNs, const double (*sMainPw)[kMaxSteps], TreeNode &rec,
+                                          float &acc) {
     const int pk = rec.pack;
     const int par = pk & kNone;
     const int lv = (pk >> 24) & 0x7f;
     const int sg = (pk >> 31) & 1;
+    const double *hh = sHH[sg];
+    if (rec.size < 0) {
+        // The node belongs to the component of the sign's first peak, whose root is never hooked: from here
+        // on the path is that component's history, tabulated per level in shared memory -- no more hops.
+        const double *mp = sMainPw[sg];
+        const int endl = sNs[sg];
+        for (int l = lv; l < endl; ++l) acc = __fadd_rn(acc, __double2float_rn(__dmul_rn(mp[l], hh[l])));
+        return false;
+    }
     TreeNode prec;
     int endl;
     if (par == kNone) {
@@ -697,17 +707,16 @@ __device__ __forceinline__ bool walk_step(const TreeNode *__restrict__ nodes, co
         endl = (prec.pack >> 24) & 0x7f;
     }
     const double pw = rec.pw;
-    const float *hh = sHH[sg];
-    for (int l = lv; l < endl; ++l) acc = __fadd_rn(acc, __double2float_rn(__dmul_rn(pw, (double)hh[l])));
+    for (int l = lv; l < endl; ++l) acc = __fadd_rn(acc, __double2float_rn(__dmul_rn(pw, hh[l])));
     if (par == kNone) return false;
     rec = prec;
     return true;
 }
 
-__device__ __forceinline__ float walk_path16(const TreeNode *__restrict__ nodes, const float (*sHH)[kMaxSteps],
-                                             const int *sNs, int j, float acc) {
+__device__ __forceinline__ float walk_path16(const TreeNode *__restrict__ nodes, const double (*sHH)[kMaxSteps],
+                                             const int *sNs, const double (*sMainPw)[kMaxSteps], int j, float acc) {
     TreeNode rec = nodes[j];
-    while (walk_step(nodes, sHH, sNs, rec, acc)) {
+    while (walk_step(nodes, sHH, sNs, sMainPw, rec, acc)) {
     }
     return acc;
 }
@@ -726,6 +735,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
     __shared__ int sMcount[2];
     __shared__ int sCcount[2];
     __shared__ int sNB;
+    __shared__ int sStarKey[2];              // smallest (level, id) key per sign: the never-hooked root
+    __shared__ double sMainPw[2][kMaxSteps]; // pow(size, E) of that root's component per level (0 = unset)
+    __shared__ double sHHd[2][kMaxSteps];    // height terms widened once (the walk multiplies in double)
 
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
@@ -762,7 +774,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
         int *const sHist = reinterpret_cast<int *>(sDyn + scratch_off); // [nwarps][kMaxSteps]
 
         for (int i = tid; i < nwarps * kMaxSteps; i += nthr) sHist[i] = 0;
-        if (tid == 0) { sMcount[0] = sMcount[1] = 0; sCcount[0] = sCcount[1] = 0; sNB = 0; }
+        if (tid == 0) { sMcount[0] = sMcount[1] = 0; sCcount[0] = sCcount[1] = 0; sNB = 0; sStarKey[0] = sStarKey[1] = 0x7fffffff; }
+        for (int i = tid; i < 2 * kMaxSteps; i += nthr) sMainPw[i / kMaxSteps][i % kMaxSteps] = 0.0;
         if (P.tab_ns) {
             const size_t e0 = ((size_t)b * P.S + s) * 2;
             for (int i = tid; i < 2 * kMaxSteps; i += nthr) {
@@ -926,7 +939,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
             bparent[i] = i;
             bsize[i] = 0;
             bcur[i] = -1;
-            if (blev != ws.blev_g) blev[i] = ws.blev_g[i];
+            const int bl = ws.blev_g[i];
+            if (blev != ws.blev_g) blev[i] = (unsigned char)bl;
+            atomicMin(&sStarKey[bl >> 7], ((bl & 0x7f) << 24) | i);
         }
         for (int i = tid; i < (NB + 31) / 32; i += nthr) bbits[i] = 0u;
         // basin ids of the first non-empty level (its vertices are all peaks or ... have no earlier level)
@@ -961,7 +976,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                     TreeNode nd;
                     nd.pw = sd.powE[sz];
                     nd.pack = (sg << 31) | (pend_lev << 24) | kNone;
-                    nd.size = sz;
+                    const bool main_chain = r == (sStarKey[sg] & kNone);
+                    nd.size = main_chain ? (sz | 0x80000000) : sz;
+                    if (main_chain) sMainPw[sg][pend_lev] = nd.pw;
                     ws.nodes[j] = nd;
                     if (old >= 0) ws.nodes[old].pack = (ws.nodes[old].pack & 0xFF000000) | j;
                     atomicAnd(bbits + (r >> 5), ~(1u << (r & 31))); // release this level's claim
@@ -1119,6 +1136,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
         } else {
             float *nodeval = ws.nodeval;
             const bool per_vertex_walk = P.accumulate != 0;
+            for (int i = tid; i < 2 * kMaxSteps; i += nthr) sHHd[i / kMaxSteps][i % kMaxSteps] = (double)sHH[i / kMaxSteps][i % kMaxSteps];
+            if (tid == 0 || tid == 32) { // dense per-level table of the main chain (carry unchanged levels forward)
+                double *mp = sMainPw[tid ? 1 : 0];
+                for (int l = 1; l < kMaxSteps; ++l)
+                    if (mp[l] == 0.0) mp[l] = mp[l - 1];
+            }
+            __syncthreads();
             if (!per_vertex_walk) {
                 for (int j0 = tid; j0 < num_nodes; j0 += 4 * nthr) { // 4 independent chains per thread
                     TreeNode rec[4];
@@ -1136,7 +1160,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                         any = false;
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            if (live[q]) { live[q] = walk_step(ws.nodes, sHH, sNs, rec[q], acc[q]); any |= live[q]; }
+                            if (live[q]) { live[q] = walk_step(ws.nodes, sHHd, sNs, sMainPw, rec[q], acc[q]); any |= live[q]; }
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -1167,7 +1191,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                 if (per_vertex_walk || want_maps) {
                     const size_t o = (size_t)b * P.ld + sd.col_off + (vmap ? vmap[u] : u);
                     float *dst = neg ? P.tfce_neg : P.tfce_pos;
-                    if (per_vertex_walk) val = walk_path16(ws.nodes, sHH, sNs, ws.leaf[idx], dst ? dst[o] : 0.f);
+                    if (per_vertex_walk) val = walk_path16(ws.nodes, sHHd, sNs, sMainPw, ws.leaf[idx], dst ? dst[o] : 0.f);
                     else val = nodeval[ws.leaf[idx]];
                     if (dst) dst[o] = val;
                 } else {

@@ -273,6 +273,34 @@ class PermutationEngine(object):
             return mx, t32, maps
         return self._download(mx) if download else mx
 
+    def observed_statistics(self, X):
+        """Un-permuted statistics with full TFCE maps -- the computation of the reference's step-1 writers
+        (STEP_1_vertex_tfce_multiple_regression.py:354-398 -> pyfunc.py:80-91 write_vertStat_img,
+        pyfunc.py:93-103 write_voxelStat_img; image file I/O is out of scope).  Returns a dict of host arrays:
+        t [C, V] float32, tfce_pos / tfce_neg [C, V] float32 scaled per surface by max(stat)/100 and the
+        vertex-density weights exactly like `vertStat_TFCE * (vertStat.max()/100) * density_corr`, and
+        max_pos / max_neg [C, S] (the values the reference echoes to max_TFCE_contrast_values.csv)."""
+        n = self.Y.n
+        mx, t32, (pos, neg) = self.regression_block(X, perm_idx=np.arange(n)[None, :], want_maps=True)
+        V = self.Y.V
+        t = to_host(t32[0, :, :V])
+        pos = to_host(pos[:, :V])
+        neg = to_host(neg[:, :V]) if neg is not None else None
+        C = t.shape[0]
+        out_pos = np.zeros_like(pos)
+        out_neg = np.zeros_like(pos) if neg is not None else None
+        for s in self.plan.surfaces:
+            a, b = s.col_offset, s.col_offset + s.adjset.num_vertices
+            w = 1 if s.weight is None else s.weight
+            for c in range(C):
+                seg = t[c, a:b]
+                out_pos[c, a:b] = pos[c, a:b] * (seg[np.isfinite(seg)].max() / 100) * w
+                if neg is not None:
+                    nseg = -seg
+                    out_neg[c, a:b] = neg[c, a:b] * (nseg[np.isfinite(nseg)].max() / 100) * w
+        mxh = to_host(mx[0])
+        return dict(t=t, tfce_pos=out_pos, tfce_neg=out_neg, max_pos=mxh[:, :, 0], max_neg=mxh[:, :, 1])
+
     def sobelz(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", want_f64=False):
         """Fused two-fit Sobel-family z for a block of shuffles (pyfunc.py:130-162).
         Returns CUDA float32 [P, ld] (and float64 when want_f64)."""
