@@ -625,14 +625,16 @@ struct __align__(16) TreeNode {
 };
 
 struct BasinWs {
-    int *up;            // ascent pointer (self for a peak)
-    int *basin;         // compact basin id per vertex
+    int *up;            // ascent target per SORTED POSITION (the vertex itself for a peak)
+    int *basin;         // compact basin id per VERTEX (the one array read at random neighbours)
+    int *basinS;        // the same per SORTED POSITION (dense per level)
     int *leaf;          // leaf node per SORTED POSITION (same indexing as order[])
     int *order;         // vertices by (activation level, vertex id)
     TreeNode *nodes;    // {pow(size,E), (sign<<31)|(level<<24)|parent}
     int2 *mlist[2];
     int2 *clist;
     int *bparent_g, *bsize_g, *bcur_g; // global fallback of the per-basin arrays
+    unsigned *emask;    // per SORTED POSITION: which ELL slots hold an earlier-activated same-sign neighbour
     float *nodeval;
     unsigned char *blev_g;
     unsigned char *lev8_g;
@@ -641,7 +643,7 @@ struct BasinWs {
 size_t tfce_basin_slot_bytes(int32_t Vmax) {
     const size_t per4 = align_up(sizeof(int) * (size_t)Vmax, 256);
     const size_t per8 = align_up(sizeof(int2) * (size_t)Vmax, 256);
-    return per4 * 8 + per8 * 5 + 2 * align_up((size_t)Vmax, 256);
+    return per4 * 10 + per8 * 5 + 2 * align_up((size_t)Vmax, 256);
 }
 
 __device__ __forceinline__ BasinWs carve_basin(char *base, int32_t Vmax) {
@@ -657,7 +659,9 @@ __device__ __forceinline__ BasinWs carve_basin(char *base, int32_t Vmax) {
     w.bsize_g = reinterpret_cast<int *>(base + 5 * per4);
     w.bcur_g = reinterpret_cast<int *>(base + 6 * per4);
     w.nodeval = reinterpret_cast<float *>(base + 7 * per4);
-    char *b8 = base + 8 * per4;
+    w.emask = reinterpret_cast<unsigned *>(base + 8 * per4);
+    w.basinS = reinterpret_cast<int *>(base + 9 * per4);
+    char *b8 = base + 10 * per4;
     w.nodes = reinterpret_cast<TreeNode *>(b8); // 16 bytes per node: two per8 blocks
     w.mlist[0] = reinterpret_cast<int2 *>(b8 + 2 * per8);
     w.mlist[1] = reinterpret_cast<int2 *>(b8 + 3 * per8);
@@ -892,12 +896,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
         const int total_active = sStart[kMaxSteps];
         TMB_TICK(1)
 
-        // ---- P: ascent pointer in vertex order (coalesced ELL rows); peaks get compact basin ids --------
-        for (int v = tid; v < V; v += nthr) {
+        // ---- P: ascent pointer per active vertex; peaks get compact basin ids --------------------------
+        const bool use_mask = sd.ell != nullptr && sd.ell_width <= 32;
+        int *const peaklist = reinterpret_cast<int *>(ws.clist); // scratch until the level loop starts
+        // (sorted order: everything a level owns -- ascent target, mask, basin id, leaf -- is then a dense
+        //  segment indexed by sorted position; only basin[] is looked up at random neighbours)
+        for (int idx = tid; idx < total_active; idx += nthr) {
+            const int v = ws.order[idx];
             const int cv = lev8[v];
-            if (cv == 0) continue;
             const int lv = cv & 0x7f;
             int best = v, bestlev = lv;
+            unsigned em = 0; // earlier-activated neighbours: lower level, or same level and smaller index
             const RowIter row(sd, v);
             for (int c = 0; c < row.nchunks; ++c) {
                 int nb[8];
@@ -909,17 +918,31 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                     if (ca == 0 || ((ca ^ cv) & 0x80)) continue;
                     const int la = ca & 0x7f;
                     if (la < bestlev) { best = nb[j]; bestlev = la; }
+                    if (c < 4 && (la < lv || (la == lv && nb[j] < v))) em |= 1u << (c * 8 + j);
                 }
             }
-            ws.up[v] = best;
+            ws.up[idx] = best;
+            if (use_mask) {
+                // a single earlier neighbour that is also the ascent target can never trigger a union
+                if (best != v && __popc(em) == 1) em = 0;
+                ws.emask[idx] = em;
+            }
             if (best == v) {
                 const int pid = atomicAdd(&sNB, 1);
-                ws.basin[v] = pid;
+                peaklist[pid] = v; // basin[] is written once the id width is known
+                ws.basinS[idx] = pid;
                 ws.blev_g[pid] = (unsigned char)cv;
             }
         }
         __syncthreads();
         const int NB = sNB;
+        // basin ids by vertex -- the one array that is looked up at random neighbours -- are stored as 16-bit
+        // values whenever they fit: half the sectors, and the sweeps of 148 items in flight then fit the L2
+        const bool b16 = NB < 65536;
+        unsigned short *const basin16 = reinterpret_cast<unsigned short *>(ws.basin);
+#define RD_BASIN(v) (b16 ? (int)basin16[(v)] : ws.basin[(v)])
+#define WR_BASIN(v, val) do { if (b16) basin16[(v)] = (unsigned short)(val); else ws.basin[(v)] = (val); } while (0)
+        for (int i = tid; i < NB; i += nthr) WR_BASIN(peaklist[i], i);
         // per-basin arrays: parent + level byte first, then size, then current node, while they fit
         int avail = smem_budget - scratch_off;
         int off = scratch_off;
@@ -997,11 +1020,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
             int2 *mcur = ws.mlist[buf];
             for (int idx = beg + tid; idx < end; idx += nthr) {
                 const int u = ws.order[idx];
-                const int cu = lev8[u];
-                const int bu = ws.basin[u];
+                unsigned em = 0xffffffffu;
+                if (use_mask) {
+                    em = ws.emask[idx];
+                    if (em == 0) continue; // no earlier neighbour that could carry another basin
+                }
+                const int cu = use_mask ? 0 : lev8[u];
+                const int bu = ws.basinS[idx];
                 const RowIter row(sd, u);
                 int ru = bu;
                 for (int c = 0; c < row.nchunks; ++c) {
+                    const unsigned cm = use_mask ? ((em >> (c * 8)) & 0xffu) : 0xffu;
+                    if (cm == 0) continue;
                     int nb[8];
                     row.load(c, nb);
                     int ba[8];
@@ -1010,10 +1040,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                         ba[j] = -1;
                         if (nb[j] < 0) continue;
                         const int a = nb[j];
-                        const int ca = lev8[a];
-                        if (ca == 0 || ((ca ^ cu) & 0x80)) continue;
-                        // earlier-activated neighbour (same level: the pair is seen from both ends, join once)
-                        if (ca < cu || (ca == cu && a < u)) ba[j] = ws.basin[a];
+                        if (use_mask) {
+                            if ((cm >> j) & 1u) ba[j] = RD_BASIN(a);
+                        } else {
+                            const int ca = lev8[a];
+                            if (ca == 0 || ((ca ^ cu) & 0x80)) continue;
+                            // earlier-activated neighbour (same level: the pair is seen from both ends, join once)
+                            if (ca < cu || (ca == cu && a < u)) ba[j] = RD_BASIN(a);
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -1053,10 +1087,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         idxs[q] = beg + (it + q) * nthr + tid;
-                        rr[q] = (it + q < iters && idxs[q] < end) ? ws.order[idxs[q]] : -1;
+                        rr[q] = (it + q < iters && idxs[q] < end) ? ws.basinS[idxs[q]] : -1;
                     }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) rr[q] = (rr[q] >= 0) ? ws.basin[rr[q]] : -1;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         if (it + q >= iters) break; // warp-uniform
@@ -1096,14 +1128,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                         for (int q = 0; q < 4; ++q) {
                             const int idx = idx0 + q * nthr;
                             vv[q] = idx < nend ? ws.order[idx] : -1;
+                            tt[q] = idx < nend ? ws.up[idx] : -1;
                         }
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) tt[q] = vv[q] >= 0 ? ws.up[vv[q]] : -1;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) bb[q] = (vv[q] >= 0 && tt[q] != vv[q]) ? ws.basin[tt[q]] : -1;
+                        for (int q = 0; q < 4; ++q) bb[q] = (vv[q] >= 0 && tt[q] != vv[q]) ? RD_BASIN(tt[q]) : -1;
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            if (vv[q] >= 0 && tt[q] != vv[q]) ws.basin[vv[q]] = bb[q];
+                            if (vv[q] >= 0 && tt[q] != vv[q]) {
+                                WR_BASIN(vv[q], bb[q]);
+                                ws.basinS[idx0 + q * nthr] = bb[q];
+                            }
                     }
                 }
             }
@@ -1124,7 +1158,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                 int lab = -1, ext = 0;
                 const int code = lev8[v];
                 if (code != 0 && !(code & 0x80) && (code & 0x7f) <= last_level) {
-                    const int r = bf_find(bparent, ws.basin[v]);
+                    const int r = bf_find(bparent, RD_BASIN(v));
                     lab = r;
                     ext = bsize[r];
                 }
@@ -1217,6 +1251,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
         __syncthreads();
         TMB_TICK(6)
 #undef TMB_TICK
+#undef RD_BASIN
+#undef WR_BASIN
     }
 }
 
