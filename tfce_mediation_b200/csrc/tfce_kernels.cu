@@ -742,6 +742,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
     __shared__ int sStarKey[2];              // smallest (level, id) key per sign: the never-hooked root
     __shared__ double sMainPw[2][kMaxSteps]; // pow(size, E) of that root's component per level (0 = unset)
     __shared__ double sHHd[2][kMaxSteps];    // height terms widened once (the walk multiplies in double)
+    __shared__ float sMainInc[2][kMaxSteps]; // per-level increment of the main chain
 
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
@@ -1177,27 +1178,57 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                     if (mp[l] == 0.0) mp[l] = mp[l - 1];
             }
             __syncthreads();
+            for (int i = tid; i < 2 * kMaxSteps; i += nthr) {
+                const int sg = i / kMaxSteps, l = i % kMaxSteps;
+                sMainInc[sg][l] = __double2float_rn(__dmul_rn(sMainPw[sg][l], sHHd[sg][l]));
+            }
+            __syncthreads();
             if (!per_vertex_walk) {
-                for (int j0 = tid; j0 < num_nodes; j0 += 4 * nthr) { // 4 independent chains per thread
-                    TreeNode rec[4];
-                    float acc[4];
-                    bool live[4];
+                // Level-synchronous walk: node ids ascend with their creation level, so the 32 walkers of a warp
+                // start at (almost) the same level and step through the levels in lock-step -- one fp32 add per
+                // lane per level, hops (parent loads) only where a lane's node ends.  Two walkers per thread.
+                for (int j0 = tid; j0 < num_nodes; j0 += 2 * nthr) {
+                    TreeNode prec[2];
+                    double pw[2];
+                    float acc[2];
+                    int lvl[2], endl[2], sgn[2], nsq[2];
+                    bool mainc[2];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         const int j = j0 + q * nthr;
-                        live[q] = j < num_nodes;
-                        acc[q] = 0.f;
-                        if (live[q]) rec[q] = ws.nodes[j];
+                        acc[q] = 0.f; lvl[q] = 0; endl[q] = 0; sgn[q] = 0; nsq[q] = 0; mainc[q] = true; pw[q] = 0.0;
+                        if (j < num_nodes) {
+                            const TreeNode rec = ws.nodes[j];
+                            const int par = rec.pack & kNone;
+                            sgn[q] = (rec.pack >> 31) & 1;
+                            lvl[q] = (rec.pack >> 24) & 0x7f;
+                            nsq[q] = sNs[sgn[q]];
+                            pw[q] = rec.pw;
+                            mainc[q] = rec.size < 0;
+                            endl[q] = nsq[q];
+                            if (!mainc[q] && par != kNone) { prec[q] = ws.nodes[par]; endl[q] = (prec[q].pack >> 24) & 0x7f; }
+                        }
                     }
-                    bool any = true;
-                    while (any) {
-                        any = false;
+                    while (lvl[0] < nsq[0] || lvl[1] < nsq[1]) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (live[q]) { live[q] = walk_step(ws.nodes, sHHd, sNs, sMainPw, rec[q], acc[q]); any |= live[q]; }
+                        for (int q = 0; q < 2; ++q) {
+                            if (lvl[q] >= nsq[q]) continue;
+                            if (lvl[q] == endl[q]) { // this lane's node ends here: move to its parent
+                                const TreeNode rec = prec[q];
+                                const int par = rec.pack & kNone;
+                                pw[q] = rec.pw;
+                                mainc[q] = rec.size < 0;
+                                endl[q] = nsq[q];
+                                if (!mainc[q] && par != kNone) { prec[q] = ws.nodes[par]; endl[q] = (prec[q].pack >> 24) & 0x7f; }
+                            }
+                            const float inc = mainc[q] ? sMainInc[sgn[q]][lvl[q]]
+                                                       : __double2float_rn(__dmul_rn(pw[q], sHHd[sgn[q]][lvl[q]]));
+                            acc[q] = __fadd_rn(acc[q], inc);
+                            ++lvl[q];
+                        }
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         const int j = j0 + q * nthr;
                         if (j < num_nodes) nodeval[j] = acc[q];
                     }
@@ -1205,7 +1236,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                 __syncthreads();
             }
             TMB_TICK(5)
-            if (P.timing && tid == 0) { atomicAdd(P.timing + 7, (unsigned long long)NB); }
+            if (P.timing && tid == 0) { atomicAdd(P.timing + 7, (unsigned long long)num_nodes); }
             float m0 = 0.f, m1 = 0.f;
             const float d0 = sDelta[0], d1 = sDelta[1];
             const float *__restrict__ w = sd.weight;
