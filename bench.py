@@ -89,9 +89,10 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 6:
-                self.samples.append(parts)
+                self.samples.append((time.time(), parts))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary over the samples that arrived inside [t0, t1] (the timed regions); all samples if none did."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -100,7 +101,10 @@ class ClockSampler(object):
         except Exception:
             self.proc.kill()
         mhz, mx, reasons = [], None, set()
-        for p in self.samples:
+        inside = [p for (ts, p) in self.samples if t0 is None or (t0 <= ts <= t1 + 0.15)]
+        if not inside:
+            inside = [p for (_, p) in self.samples]
+        for p in inside:
             try:
                 mhz.append(float(p[0])); mx = float(p[1])
             except ValueError:
@@ -223,6 +227,9 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs a moment to start: launched first, filtered to the timed regions
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
@@ -284,12 +291,10 @@ def run_b200(args):
         if world > 1:
             dist.all_gather(gathered, out_max)       # the per-shuffle maxima, tiny (NCCL over NVLink)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()          # sampled from the warm-up on, so short timed regions still get samples under load
     for s in range(args.warmup):
         device_step(s)
     barrier()
+    t_load0 = time.time()
     launches0 = _lib.launch_count()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     tfce_events = []
@@ -301,7 +306,6 @@ def run_b200(args):
     dev_ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
     tfce_ms = float(np.mean([a.elapsed_time(b) for a, b in tfce_events]))
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end arm: the public call, host index rows in (pinned staging), host maxima out ----
     for s in range(min(args.warmup, 2)):
@@ -318,6 +322,7 @@ def run_b200(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_load0, time.time()) if rank == 0 else None   # sampled during both timed regions
 
     times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:

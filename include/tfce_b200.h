@@ -59,6 +59,10 @@ int tmb_graph_create(int device, int32_t V, const int64_t *indptr_host, const in
                      float H, float E, tmb_graph **out);
 int tmb_graph_destroy(tmb_graph *g);
 int tmb_graph_num_vertices(const tmb_graph *g, int32_t *V, int64_t *nnz);
+/* The library relabels the vertices of symmetric graphs for memory locality (reverse Cuthill-McKee +
+ * 64-vertex patches); callers never see it unless they opt in: vmap_host[i] (int32 [V]) is the caller's
+ * index of internal vertex i (identity when the graph was not relabelled). */
+int tmb_graph_vmap(const tmb_graph *g, int32_t *vmap_host);
 
 /* == tfce.pyx:44-45  `CreateAdjSet.run(image, enhn)`:  enhn[v] += TFCE(image)[v], fp32, host buffers.
  * map_status (may be NULL) receives TMB_MAP_* bits. */
@@ -87,6 +91,10 @@ int tmb_tfce_components(tmb_graph *g, const float *image_host, int level, int32_
 int tmb_plan_create(int device, int S, tmb_graph *const *graphs, const int64_t *col_offset,
                     const float *const *weight_host, int max_slots, tmb_plan **out);
 int tmb_plan_destroy(tmb_plan *p);
+/* Opt-in fast path of the batched engine: declare that statistic rows (and requested TFCE maps) use the
+ * graphs' INTERNAL vertex order (tmb_graph_vmap), e.g. because the data columns were permuted once at
+ * upload; the per-map gather through vmap is then skipped. */
+int tmb_plan_set_internal_order(tmb_plan *p, int on);
 int tmb_plan_run(tmb_plan *p, const float *stat_dev, int64_t ld, int B, int two_sided, float *max_dev,
                  float *tfce_pos_dev, float *tfce_neg_dev, int32_t *status_dev, void *stream);
 

@@ -66,7 +66,7 @@ def test_engine_tstat_batch_matches_oracle(n, V, k, P):
     idx = np.stack([rs.permutation(n) for _ in range(P)])
     Y = DeviceMatrix(y)
     e = eng.PermutationEngine.__new__(eng.PermutationEngine)      # fit only: no TFCE plan needed
-    e.device, e.Y, e.nan_to_zero, e.h2d_bytes, e.d2h_bytes, e._pinned = Y.t.device, Y, False, 0, 0, {}
+    e.device, e.Y, e.nan_to_zero, e.h2d_bytes, e.d2h_bytes, e._pinned, e.colperm = Y.t.device, Y, False, 0, 0, {}, None
     t32, t64 = e.tstat(eng.row_permuted_stack(X, idx), want_f64=True)
     t32, t64 = t32.cpu().numpy()[:, :, :V], t64.cpu().numpy()[:, :, :V]
     # and through explicit per-shuffle designs (the -v / mediation route)

@@ -32,6 +32,8 @@ SIGNATURES = {
     "tmb_graph_create": (_int, [_int, _i32, _vp, _vp, _f32, _f32, _c.POINTER(_vp)]),
     "tmb_graph_destroy": (_int, [_vp]),
     "tmb_graph_num_vertices": (_int, [_vp, _c.POINTER(_i32), _c.POINTER(_i64)]),
+    "tmb_graph_vmap": (_int, [_vp, _vp]),
+    "tmb_plan_set_internal_order": (_int, [_vp, _int]),
     "tmb_tfce_run": (_int, [_vp, _vp, _vp, _c.POINTER(_int)]),
     "tmb_tfce_components": (_int, [_vp, _vp, _int, _vp, _vp, _c.POINTER(_f32)]),
     "tmb_plan_create": (_int, [_int, _int, _c.POINTER(_vp), _c.POINTER(_i64), _c.POINTER(_vp), _int, _c.POINTER(_vp)]),

@@ -63,6 +63,7 @@ struct tmb_plan {
     size_t slot_stride = 0;
     int *d_counter = nullptr;
     int use_basin = 0;          // every surface symmetric -> V3 basin sweep
+    int internal_order = 0;     // statistic rows already use the graphs' internal vertex order (vmap ignored)
     unsigned long long *d_timing = nullptr; // TMB_PHASE_TIMING=1: per-phase cycle totals
 };
 
@@ -250,6 +251,18 @@ extern "C" int tmb_graph_destroy(tmb_graph *g) {
     return 0;
 }
 
+extern "C" int tmb_graph_vmap(const tmb_graph *g, int32_t *vmap_host) {
+    TMB_REQUIRE(g && vmap_host, "tmb_graph_vmap: null pointer");
+    for (int32_t i = 0; i < g->V; ++i) vmap_host[i] = g->vmap.empty() ? i : g->vmap[i];
+    return 0;
+}
+
+extern "C" int tmb_plan_set_internal_order(tmb_plan *p, int on) {
+    TMB_REQUIRE(p, "tmb_plan_set_internal_order: null plan");
+    p->internal_order = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" int tmb_graph_num_vertices(const tmb_graph *g, int32_t *V, int64_t *nnz) {
     TMB_REQUIRE(g, "tmb_graph_num_vertices: null graph");
     if (V) *V = g->V;
@@ -389,7 +402,7 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
     sp.Vmax = p->Vmax; sp.work_counter = p->d_counter; sp.timing = p->d_timing;
     {
         const char *pc = getenv("TMB_PARENT_UNCACHED");
-        sp.flags = ((pc && pc[0] == '1') ? 0 : 1) | (p->use_basin ? 2 : 0); // see SweepParams::flags
+        sp.flags = ((pc && pc[0] == '1') ? 0 : 1) | (p->use_basin ? 2 : 0) | (p->internal_order ? 4 : 0); // see SweepParams::flags
     }
     return launch_tfce_sweep(sp, p->num_slots, stream);
 }

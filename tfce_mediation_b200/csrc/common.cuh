@@ -73,7 +73,8 @@ struct SweepParams {
     const float *tab_HH;
     const int32_t *tab_status;
     int flags;                  // bit 0: union-find pointer loads go through L1 (ld.ca) instead of ld.cg;
-                                // bit 1: basin sweep (V3, symmetric adjacency only)
+                                // bit 1: basin sweep (symmetric adjacency only)
+                                // bit 2: statistic rows are in the graphs' internal vertex order (ignore vmap)
     unsigned long long *timing; // optional [8] per-phase cycle totals (development aid), or nullptr
     // workspace
     char *workspace;

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_sweep_kernel(SweepPa
         const float *__restrict__ x = P.stat + (size_t)b * P.ld + sd.col_off;
         const int64_t *__restrict__ indptr = sd.indptr;
         const int32_t *__restrict__ indices = sd.indices;
-        const int32_t *__restrict__ vmap = sd.vmap; // internal (reordered) index -> caller's index, or null
+        const int32_t *__restrict__ vmap = (P.flags & 4) ? nullptr : sd.vmap; // internal index -> caller's index, or null
         const bool directed = sd.directed != 0;
 
         if (tid < kMaxSteps) sCount[tid] = 0;
@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
         const SurfDesc sd = P.surfs[s];
         const int V = sd.V;
         const float *__restrict__ x = P.stat + (size_t)b * P.ld + sd.col_off;
-        const int32_t *__restrict__ vmap = sd.vmap;
+        const int32_t *__restrict__ vmap = (P.flags & 4) ? nullptr : sd.vmap;
         long long tk = P.timing ? clock64() : 0;
 #define TMB_TICK(i)                                                                  \
         if (P.timing && tid == 0) {                                                  \

@@ -62,6 +62,7 @@ class TfcePlan(object):
         self.S = S
         self.row_len = max(s.col_offset + s.adjset.num_vertices for s in self.surfaces)
         self._H = np.array([s.adjset.H for s in self.surfaces], dtype=np.float32)
+        self.internal_order = False
         self.exact_pow = True
         self._stage = {}
         self._inflight = None
@@ -71,6 +72,22 @@ class TfcePlan(object):
         if h is not None and _lib._lib is not None:
             _lib._lib.tmb_plan_destroy(h)
             self._handle = None
+
+    def column_permutation(self, row_len):
+        """int64 [row_len]: position j of an internal-order row holds caller column perm[j] (identity outside the
+        surfaces).  Used by the engine to permute the data columns once, so that t-maps come out of the fit in
+        the graphs' internal (locality) order and the sweep reads them coalesced."""
+        perm = np.arange(row_len, dtype=np.int64)
+        for s in self.surfaces:
+            V = s.adjset.num_vertices
+            vm = np.empty(V, dtype=np.int32)
+            _lib.check(_lib.lib().tmb_graph_vmap(s.adjset._handle, _lib.ptr(vm)))
+            perm[s.col_offset:s.col_offset + V] = s.col_offset + vm.astype(np.int64)
+        return perm
+
+    def set_internal_order(self, on=True):
+        _lib.check(_lib.lib().tmb_plan_set_internal_order(self._handle, 1 if on else 0))
+        self.internal_order = bool(on)
 
     def run(self, stat, two_sided=True, want_maps=False, out_max=None, exact_pow=None):
         """stat: CUDA float32 [B, ld].  Returns (max [B, S, 2] CUDA float32, status [B,S,2] int32, maps).
@@ -182,7 +199,8 @@ def pack_At(pinv, rp):
 class PermutationEngine(object):
     """Data resident in HBM + a TFCE plan; runs blocks of shuffles."""
 
-    def __init__(self, data, surfaces, two_sided=True, nan_to_zero=False, device=None, max_slots=0):
+    def __init__(self, data, surfaces, two_sided=True, nan_to_zero=False, device=None, max_slots=0,
+                 permute_columns=True):
         import torch
         _lib.require_device()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -190,11 +208,28 @@ class PermutationEngine(object):
         self.plan = TfcePlan(surfaces, device=self.device, max_slots=max_slots) if surfaces is not None else None
         if self.plan is not None and self.plan.row_len > self.Y.V:
             raise ValueError("surfaces cover %d columns but the data has %d" % (self.plan.row_len, self.Y.V))
+        self.colperm = None
+        if self.plan is not None and permute_columns:
+            perm = self.plan.column_permutation(self.Y.V)
+            if not np.array_equal(perm, np.arange(self.Y.V)):
+                # one-time gather of the data columns into the graphs' internal vertex order
+                self.colperm = torch.from_numpy(perm).to(self.device)
+                self.Y.t[:, :self.Y.V] = self.Y.t[:, :self.Y.V].index_select(1, self.colperm)
+                self.Y._yy = {}
+                self.plan.set_internal_order(True)
         self.two_sided = bool(two_sided)
         self.nan_to_zero = bool(nan_to_zero)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._pinned = {}
+
+    def to_caller_order(self, t):
+        """Undo the one-time column permutation on a [..., ld] device tensor (maps returned to the user)."""
+        if self.colperm is None:
+            return t
+        out = t.clone()
+        out[..., :self.Y.V].index_copy_(t.dim() - 1, self.colperm, t[..., :self.Y.V])
+        return out
 
     # -- staging ---------------------------------------------------------------------------------
     def _upload(self, name, host_array):
@@ -221,7 +256,7 @@ class PermutationEngine(object):
         return to_host(t)
 
     # -- fit -------------------------------------------------------------------------------------
-    def tstat(self, stack, rows=None, want_f64=False):
+    def tstat(self, stack, rows=None, want_f64=False, caller_order=True):
         """Fused fit+t for a design stack (design_stack / row_permuted_stack output).
         Returns CUDA float32 [P, C, ld] (and float64 when want_f64)."""
         import torch
@@ -242,6 +277,9 @@ class PermutationEngine(object):
             _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA,
             _lib.ptr(G_d), _lib.ptr(d_d), P, r, rp, row0, nrows, stack["dof"], _lib.ptr(yy), _lib.ptr(t32),
             _lib.ptr(t64), self.Y.ld, 1 if self.nan_to_zero else 0, _lib.current_stream()))
+        if caller_order and self.colperm is not None:
+            t32 = self.to_caller_order(t32)
+            t64 = self.to_caller_order(t64) if t64 is not None else None
         return (t32, t64) if want_f64 else t32
 
     # -- whole shuffles --------------------------------------------------------------------------
@@ -264,13 +302,14 @@ class PermutationEngine(object):
             if not has_intercept(X):
                 raise ValueError("X must have the intercept in column 0")
             stack = row_permuted_stack(X, perm_idx, center=True)
-        t32 = self.tstat(stack)
+        t32 = self.tstat(stack, caller_order=False)
         P, C, ld = t32.shape
         mx, status, maps = self.plan.run(t32.view(P * C, ld), two_sided=self.two_sided, want_maps=want_maps)
         mx = mx.view(P, C, self.plan.S, 2)
         self.last_status = status
         if want_maps:
-            return mx, t32, maps
+            maps = tuple(self.to_caller_order(m) if m is not None else None for m in maps)
+            return mx, self.to_caller_order(t32), maps
         return self._download(mx) if download else mx
 
     def observed_statistics(self, X):
@@ -301,7 +340,7 @@ class PermutationEngine(object):
         mxh = to_host(mx[0])
         return dict(t=t, tfce_pos=out_pos, tfce_neg=out_neg, max_pos=mxh[:, :, 0], max_neg=mxh[:, :, 1])
 
-    def sobelz(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", want_f64=False):
+    def sobelz(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", want_f64=False, caller_order=True):
         """Fused two-fit Sobel-family z for a block of shuffles (pyfunc.py:130-162).
         Returns CUDA float32 [P, ld] (and float64 when want_f64)."""
         import torch
@@ -356,17 +395,21 @@ class PermutationEngine(object):
             _lib.ptr(GA_d), _lib.ptr(dA_d), rA, 0, sA["dof"] if sA else 1.0, _lib.ptr(GB_d), _lib.ptr(dB_d), rB, 0,
             sB["dof"], _lib.ptr(yy), _lib.ptr(ta_d), P, algc, _lib.ptr(z32), _lib.ptr(z64), self.Y.ld,
             _lib.current_stream()))
+        if caller_order and self.colperm is not None:
+            z32 = self.to_caller_order(z32)
+            z64 = self.to_caller_order(z64) if z64 is not None else None
         return (z32, z64) if want_f64 else z32
 
     def mediation_block(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", want_maps=False, download=True):
         """Sobel-z + one-sided TFCE + scaled max for a block of shuffles
         (vertex_tfce_mediation_randomise.py:80-91, pyfunc.py:130-162).  Returns float32 [P, S]."""
-        z32 = self.sobelz(medtype, pred_x, depend_y, perm_idx, alg)
+        z32 = self.sobelz(medtype, pred_x, depend_y, perm_idx, alg, caller_order=False)
         mx, status, maps = self.plan.run(z32, two_sided=False, want_maps=want_maps)
         self.last_status = status
         mx = mx[:, :, 0]
         if want_maps:
-            return mx, z32, maps
+            maps = tuple(self.to_caller_order(m) if m is not None else None for m in maps)
+            return mx, self.to_caller_order(z32), maps
         return self._download(mx) if download else mx
 
 
