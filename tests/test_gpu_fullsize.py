@@ -103,3 +103,42 @@ def test_fullsize_engine_rows_vs_oracle(ico7):
         for sg, sign in enumerate((1.0, -1.0)):
             want = oracle.perm_max_vertex(t[1] * sign, V, mask, mask, run, run)
             assert "%.4f" % want == "%.4f" % max(got[p, 0, 0, sg], got[p, 0, 1, sg])
+
+
+def test_high_degree_graph_csr_path_bitexact():
+    """Degree > 32 (3-ring neighbourhoods, like the geodesic '3 mm' adjacency sets): no fixed-width rows, the
+    kernels walk CSR rows in chunks of 8."""
+    import torch
+    from tfce_mediation_b200.engine import Surface, TfcePlan
+    from tfce_mediation_b200.tfce import CreateAdjSet
+    _, _, csr = helpers.ico(5)
+    k3 = synth.kring_csr(csr, 3)
+    assert np.diff(k3[0]).max() > 32
+    V = csr[0].shape[0] - 1
+    dens = synth.vertex_density(k3)
+    c = CreateAdjSet(2, 0.67, k3)
+    plan = TfcePlan([Surface(c, 0, dens)])
+    stat = np.stack([helpers.smooth_map(csr, 300 + b, b % 3) for b in range(5)])
+    mx, status, (pos, neg) = plan.run(torch.from_numpy(stat).cuda(), two_sided=True, want_maps=True)
+    pos, neg, mx = pos.cpu().numpy(), neg.cpu().numpy(), mx.cpu().numpy()
+    for b in range(5):
+        assert np.array_equal(pos[b], oracle.tfce_run(2, 0.67, k3, stat[b]))
+        assert np.array_equal(neg[b], oracle.tfce_run(2, 0.67, k3, -stat[b]))
+        want = helpers.oracle_signed_max(2, 0.67, k3, stat[b], dens)
+        assert mx[b, 0, 0] == want[0] and mx[b, 0, 1] == want[1]
+
+
+def test_many_basins_32bit_ids_bitexact():
+    """White noise on a 655,362-vertex sphere: > 65,535 basins, so basin ids take the 32-bit path and the
+    per-basin arrays no longer fit in shared memory (global fallback)."""
+    from tfce_mediation_b200.tfce import CreateAdjSet
+    _, _, csr = helpers.ico(8)
+    V = csr[0].shape[0] - 1
+    img = np.random.RandomState(5).standard_normal(V).astype(np.float32)
+    got = np.zeros_like(img)
+    c = CreateAdjSet(2, 0.67, csr)
+    c.run(img, got)
+    assert np.array_equal(got, oracle.tfce_run(2, 0.67, csr, img))
+    labels, extents, _ = c.components(img, 60)
+    wl, we = oracle.tfce_components(csr, img, 60)
+    assert np.array_equal(labels, wl) and np.array_equal(extents, we)

@@ -64,8 +64,8 @@ class TfcePlan(object):
         self._H = np.array([s.adjset.H for s in self.surfaces], dtype=np.float32)
         self.internal_order = False
         self.exact_pow = True
-        self._stage = {}
-        self._inflight = None
+        self._tickets = {}
+        self._flip = 0
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -115,35 +115,64 @@ class TfcePlan(object):
             _lib.check(L.tmb_plan_run(self._handle, _lib.ptr(stat), ld, B, 1 if two_sided else 0, _lib.ptr(mx),
                                       _lib.ptr(pos), _lib.ptr(neg), _lib.ptr(status), stream))
             return mx, status, (pos, neg)
+        ticket = self.prepare(stat)
+        return self.finish(ticket, stat, two_sided=two_sided, out_max=mx, pos=pos, neg=neg, status=status)
+
+    # -- exact-libm mode in two stages, so callers can overlap the host part with other GPU work ----------
+    def prepare(self, stat):
+        """Stage 1: per-(row, surface, sign) maxima on the device and an asynchronous copy to pinned host
+        memory.  Returns a ticket for finish().  Enqueue further GPU work (e.g. the fit of the next block)
+        before calling finish() and the host table building overlaps it."""
+        import torch
+        B, ld = int(stat.shape[0]), int(stat.stride(0))
         cnt = B * self.S * 2
-        maxima = torch.empty((cnt,), dtype=torch.float32, device=stat.device)
-        _lib.check(L.tmb_plan_maxima(self._handle, _lib.ptr(stat), ld, B, _lib.ptr(maxima), stream))
-        mh = maxima.cpu().numpy()                                    # the one host round trip of the block
-        Hs = np.ascontiguousarray(np.tile(np.repeat(self._H, 2), B), dtype=np.float32)
-        tab = self._table_stage(cnt)
-        _lib.check(L.tmb_threshold_tables(_lib.ptr(mh), _lib.ptr(Hs), cnt, _lib.ptr(tab["ns"]), _lib.ptr(tab["delta"]),
-                                          _lib.ptr(tab["T"]), _lib.ptr(tab["HH"]), _lib.ptr(tab["st"])))
+        slot = self._tickets.setdefault((cnt, self._flip), {})
+        self._flip ^= 1
+        if not slot:
+            slot["dev"] = torch.empty((cnt,), dtype=torch.float32, device=stat.device)
+            slot["host"] = torch.empty((cnt,), dtype=torch.float32).pin_memory()
+            slot["event"] = torch.cuda.Event()
+            slot["tab"] = dict(ns=torch.empty((cnt,), dtype=torch.int32).pin_memory(),
+                               delta=torch.empty((cnt,), dtype=torch.float32).pin_memory(),
+                               T=torch.empty((cnt, 128), dtype=torch.float32).pin_memory(),
+                               HH=torch.empty((cnt, 128), dtype=torch.float32).pin_memory(),
+                               st=torch.empty((cnt,), dtype=torch.int32).pin_memory())
+            slot["tab_event"] = None
+            slot["Hs"] = np.ascontiguousarray(np.tile(np.repeat(self._H, 2), B), dtype=np.float32)
+        _lib.check(_lib.lib().tmb_plan_maxima(self._handle, _lib.ptr(stat), ld, B, _lib.ptr(slot["dev"]),
+                                              _lib.current_stream()))
+        slot["host"].copy_(slot["dev"], non_blocking=True)
+        slot["event"].record()
+        slot["cnt"] = cnt
+        return slot
+
+    def finish(self, ticket, stat, two_sided=True, out_max=None, pos=None, neg=None, status=None):
+        """Stage 2: wait for the maxima, build the threshold tables on the host with libm's powf
+        (tmb_threshold_tables), upload them and launch the sweep."""
+        import torch
+        L = _lib.lib()
+        B, ld = int(stat.shape[0]), int(stat.stride(0))
+        cnt = ticket["cnt"]
+        mx = out_max if out_max is not None else torch.empty((B, self.S, 2), dtype=torch.float32, device=stat.device)
+        if status is None:
+            status = torch.empty((B, self.S, 2), dtype=torch.int32, device=stat.device)
+        ticket["event"].synchronize()
+        if ticket["tab_event"] is not None:
+            ticket["tab_event"].synchronize()     # the previous upload out of this staging buffer is done
+        tab = ticket["tab"]
+        mh = ticket["host"].numpy()
+        _lib.check(L.tmb_threshold_tables(_lib.ptr(mh), _lib.ptr(ticket["Hs"]), cnt, _lib.ptr(tab["ns"]),
+                                          _lib.ptr(tab["delta"]), _lib.ptr(tab["T"]), _lib.ptr(tab["HH"]),
+                                          _lib.ptr(tab["st"])))
         d = {k: v.to(stat.device, non_blocking=True) for k, v in tab.items()}
+        ticket["tab_event"] = torch.cuda.Event()
+        ticket["tab_event"].record()
         _lib.check(L.tmb_plan_run_tables(self._handle, _lib.ptr(stat), ld, B, 1 if two_sided else 0, _lib.ptr(d["ns"]),
                                          _lib.ptr(d["delta"]), _lib.ptr(d["T"]), _lib.ptr(d["HH"]), _lib.ptr(d["st"]),
-                                         _lib.ptr(mx), _lib.ptr(pos), _lib.ptr(neg), _lib.ptr(status), stream))
-        self._inflight = d   # keep the device tables alive until the next call on this stream
+                                         _lib.ptr(mx), _lib.ptr(pos), _lib.ptr(neg), _lib.ptr(status),
+                                         _lib.current_stream()))
+        ticket["inflight"] = d   # keep the device tables alive until this ticket is reused
         return mx, status, (pos, neg)
-
-    def _table_stage(self, cnt):
-        """Pinned host staging for the threshold tables (reused; guarded by an event)."""
-        import torch
-        ent = self._stage.get(cnt)
-        if ent is None:
-            ent = dict(ns=torch.empty((cnt,), dtype=torch.int32).pin_memory(),
-                       delta=torch.empty((cnt,), dtype=torch.float32).pin_memory(),
-                       T=torch.empty((cnt, 128), dtype=torch.float32).pin_memory(),
-                       HH=torch.empty((cnt, 128), dtype=torch.float32).pin_memory(),
-                       st=torch.empty((cnt,), dtype=torch.int32).pin_memory())
-            self._stage[cnt] = ent
-        else:
-            torch.cuda.current_stream().synchronize()   # previous async copies out of the staging are done
-        return ent
 
 
 # ------------------------------------------------------------------------------------------ designs
@@ -311,6 +340,42 @@ class PermutationEngine(object):
             maps = tuple(self.to_caller_order(m) if m is not None else None for m in maps)
             return mx, self.to_caller_order(t32), maps
         return self._download(mx) if download else mx
+
+    def regression_blocks(self, X, perm_idx, block=256):
+        """Many shuffles, `block` at a time, software-pipelined on one stream: while the sweep of block i runs,
+        the fit and the maxima of block i+1 are already queued and the host builds block i+1's threshold
+        tables, so the GPU never waits for the host round trip of the exact-libm mode.
+        perm_idx int [N, n] (whole-row permutations of X).  Returns float32 [N, C, S, 2] on the host."""
+        import torch
+        X = np.asarray(X, dtype=np.float64)
+        if not has_intercept(X):
+            raise ValueError("X must have the intercept in column 0")
+        perm_idx = np.asarray(perm_idx)
+        N = perm_idx.shape[0]
+        chunks = [(a, min(N, a + block)) for a in range(0, N, block)]
+        C = X.shape[1] - 1
+        host = torch.empty((N, C, self.plan.S, 2), dtype=torch.float32).pin_memory()
+
+        def stage1(a, b):
+            t32 = self.tstat(row_permuted_stack(X, perm_idx[a:b], center=True), caller_order=False)
+            flat = t32.view(t32.shape[0] * t32.shape[1], t32.shape[2])
+            tk = self.plan.prepare(flat) if self.plan.exact_pow else None
+            return t32, flat, tk
+
+        nxt = stage1(*chunks[0]) if chunks else None
+        for ci, (a, b) in enumerate(chunks):
+            cur = nxt
+            nxt = stage1(*chunks[ci + 1]) if ci + 1 < len(chunks) else None   # queued before this block's sweep
+            t32, flat, tk = cur
+            if tk is not None:
+                mx, status, _ = self.plan.finish(tk, flat, two_sided=self.two_sided)
+            else:
+                mx, status, _ = self.plan.run(flat, two_sided=self.two_sided, exact_pow=False)
+            host[a:b].copy_(mx.view(b - a, C, self.plan.S, 2), non_blocking=True)   # no per-block host sync
+            self.d2h_bytes += (b - a) * C * self.plan.S * 2 * 4
+        torch.cuda.current_stream().synchronize()
+        self.last_status = None
+        return host.numpy().copy()
 
     def observed_statistics(self, X):
         """Un-permuted statistics with full TFCE maps -- the computation of the reference's step-1 writers

@@ -98,12 +98,12 @@ def run(opts):
     if rank == 0:
         os.makedirs(outdir, exist_ok=True)
     results = []
-    for p0, p1 in C.chunks(a, b):
-        idx = []
-        for perm_number in range(p0, p1 + 1):
-            np.random.seed(perm_number + seed)                       # tm_func.py:147-148
-            idx.append(np.random.permutation(list(range(n))))
-        results.append(eng.regression_block(X, perm_idx=np.stack(idx)))  # [P, C, S, 2]
+    idx = []
+    for perm_number in range(a, b + 1):
+        np.random.seed(perm_number + seed)                           # tm_func.py:147-148
+        idx.append(np.random.permutation(list(range(n))))
+    if idx:
+        results.append(eng.regression_blocks(X, np.stack(idx), block=C.BLOCK))  # [P, C, S, 2]
     local = np.concatenate(results, axis=0) if results else np.zeros((0, k - 1, len(surfs), 2), dtype=np.float32)
     allrows = parallel.gather_rows(local)
     if rank == 0:

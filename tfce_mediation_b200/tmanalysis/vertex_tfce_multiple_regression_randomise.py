@@ -66,23 +66,26 @@ def run(opts):
     k = X.shape[1]
     ncon = (opts.specifyvars[1] + 1 - opts.specifyvars[0]) if opts.specifyvars else k - 1
     results = []
-    for p0, p1 in C.chunks(a, b):
-        idx, designs = [], []
-        for iter_perm in range(p0, p1 + 1):
+    if not opts.specifyvars:
+        # whole-row permutations: draw the index stream with the reference's RNG calls, then run the whole
+        # slice through the pipelined engine
+        idx = []
+        for iter_perm in range(a, b + 1):
             np.random.seed(C.reference_seed(iter_perm, opts.seed))
-            if opts.specifyvars:
+            idx.append(C.draw_block_permutation(block_list, indexer) if opts.exchangeblock
+                       else C.draw_row_permutation(n))
+        if idx:
+            results.append(eng.regression_blocks(X, np.stack(idx), block=C.BLOCK).max(axis=2))
+    else:
+        for p0, p1 in C.chunks(a, b):
+            designs = []
+            for iter_perm in range(p0, p1 + 1):
+                np.random.seed(C.reference_seed(iter_perm, opts.seed))
                 s0, s1 = opts.specifyvars[0], opts.specifyvars[1] + 1
                 X[:, s0:s1] = X[:, s0:s1][C.draw_row_permutation(n)]   # cumulative, like the reference (:93-97)
                 designs.append(X.copy())
-            elif opts.exchangeblock:
-                idx.append(C.draw_block_permutation(block_list, indexer))
-            else:
-                idx.append(C.draw_row_permutation(n))
-        if designs:
             mx = eng.regression_block(None, designs=np.stack(designs))
-        else:
-            mx = eng.regression_block(X, perm_idx=np.stack(idx))
-        results.append(mx.max(axis=2))                 # max over the two hemispheres -> [P, C, 2]
+            results.append(mx.max(axis=2))             # max over the two hemispheres -> [P, C, 2]
     local = np.concatenate(results, axis=0) if results else np.zeros((0, k - 1, 2), dtype=np.float32)
     allrows = parallel.gather_rows(local)
     if rank == 0:
