@@ -124,7 +124,7 @@ int tmb_plan_run_tables(tmb_plan *p, const float *stat_dev, int64_t ld, int B, i
  *        covering V rounded up to 128 (pad columns zero); 16-byte aligned.
  * At_dev: float64 [n, ldA]: column j*rp + i is row i of the j-th design's pseudo-inverse
  *         (X_j'X_j)^-1 X_j' (k-major so one subject's coefficients are contiguous); rp is r padded
- *         to 1, 2, 4 or 8 with zero columns; ldA is a multiple of 64 covering P*rp rounded up.
+ *         to 1, 2, 4 or 8 with zero columns; ldA is a multiple of 128 covering P*rp rounded up.
  * G_dev:  float64 [P, r, r] = X_j'X_j ;  d_dev: float64 [P, r] = diag((X_j'X_j)^-1).
  * yy_dev: float64 [V] = sum_i Y[i,v]^2 (tmb_glm_sumsq; colsum_dev optionally receives sum_i Y[i,v]).
  * SSE = yy - b'Gb ; sigma2 = SSE/dof ; se = (float)sqrt(sigma2 * d)  (the fp32 rounding of
@@ -142,7 +142,7 @@ int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, 
                   double dof, const double *yy_dev, float *t32_dev, double *t64_dev, int64_t ldt,
                   int nan_to_zero, void *stream);
 /* betas only == cynumstats.pyx:28-29 cy_lin_lstsqr_mat: beta64_dev float64 [nrows, ldt] for the nrows
- * pseudo-inverse rows stored as the first nrows columns of At_dev (ldA a multiple of 64). */
+ * pseudo-inverse rows stored as the first nrows columns of At_dev (ldA a multiple of 128). */
 int tmb_glm_beta(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev, int64_t ldA,
                  int nrows, double *beta64_dev, int64_t ldt, void *stream);
 

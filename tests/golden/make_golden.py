@@ -224,6 +224,33 @@ def main():
         p_array[j] = np.true_divide(j, len(srt))
     corr = np.array([fwe.find_nearest(srt, v, p_array) for v in vals])
     np.savez_compressed(os.path.join(HERE, "fwe.npz"), perm_max=perm_max, values=vals, corrp=corr)
+    # ---- 8. mmr study-wide FWER (tm_func.py:403-491 apply_mfwer) ---------------------------------------------
+    sizes = [120, 80, 100]
+    position_array = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    nperm, ncon = 60, 2
+    img = np.abs(rs.standard_normal((sum(sizes), 4))) * 300
+    img[rs.rand(*img.shape) < 0.2] = 0.5          # log <= 0 -> excluded by the reference's mask
+    perm_csv = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            os.mkdir("output_t")
+            for sf in range(3):
+                for c in range(ncon):
+                    vals = np.abs(rs.standard_normal(nperm)) * 200 * (1 + sf) + 1
+                    perm_csv["s%d_c%d" % (sf, c + 1)] = vals
+                    np.savetxt("output_t/perm_maxTFCE_surf%d_tcon%d.csv" % (sf, c + 1), vals, fmt="%f")
+            out = {}
+            for wname, w in (("none", None), ("logmasksize", "logmasksize")):
+                with np.errstate(all="ignore"):
+                    pos, neg = tm_func.apply_mfwer([img.copy()], ncon, list(range(3)), nperm, 3, "t", position_array,
+                                                   pos_range=[0, 1], neg_range=[2, 3], weight=w)
+                out["pos_" + wname] = pos
+                out["neg_" + wname] = neg
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "mfwer.npz"), image=img, position_array=np.array(position_array),
+                        num_perm=nperm, **{"csv_" + k: v for k, v in perm_csv.items()}, **out)
     print("golden fixtures written to", HERE)
 
 

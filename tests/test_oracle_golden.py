@@ -145,3 +145,21 @@ def test_threshold_sequence_properties():
         T = oracle.tfce_thresholds(mx)
         assert T[0] == np.float32(mx) and len(T) in (100, 101, 102)
         assert np.all(np.diff(T) < 0) and T[-1] >= 0
+
+
+def test_apply_mfwer_restatement_vs_reference(tmp_path, monkeypatch):
+    """tm_func.apply_mfwer (host post-processing) against the reference's output."""
+    from tfce_mediation_b200 import tm_func
+    g = load("mfwer.npz")
+    monkeypatch.chdir(tmp_path)
+    os.mkdir("output_t")
+    for sf in range(3):
+        for c in (1, 2):
+            np.savetxt("output_t/perm_maxTFCE_surf%d_tcon%d.csv" % (sf, c), g["csv_s%d_c%d" % (sf, c)], fmt="%f")
+    pa = g["position_array"].tolist()
+    for wname, w in (("none", None), ("logmasksize", "logmasksize")):
+        pos, neg = tm_func.apply_mfwer([g["image"].copy()], 2, [0, 1, 2], int(g["num_perm"]), 3, "t", pa,
+                                       pos_range=[0, 1], neg_range=[2, 3], weight=w)
+        assert np.array_equal(pos, g["pos_" + wname])
+        assert np.array_equal(neg, g["neg_" + wname])
+    assert tm_func.lowest_length(2, [0, 1, 2], "t") == int(g["num_perm"])

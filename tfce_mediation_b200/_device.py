@@ -4,7 +4,7 @@ import numpy as np
 from . import _lib
 
 TILE_V = 128   # vertex tile of the fit kernel: rows of Y are padded to a multiple of this
-TILE_M = 64    # design-row tile
+TILE_M = 128   # design-row tile
 
 
 def round_up(x, m):

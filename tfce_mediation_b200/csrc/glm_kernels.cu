@@ -4,10 +4,10 @@
 // :66-74 (calc_beta_se) and the fit half of pyfunc.py:130-162 (calc_sobelz) for P designs at once.
 //
 // One dense fp64 contraction  B[P*rp, V] = At^T[P*rp, n] . Y[n, V]  with the stacked
-// pseudo-inverses of P permuted designs as the left operand, tiled 64 (design rows) x 128
+// pseudo-inverses of P permuted designs as the left operand, tiled 128 (design rows) x 128
 // (vertices) x 32 (subjects) per CTA.  A dedicated producer warp streams both operands into a
 // 3-stage shared-memory ring with bulk async copies (cp.async.bulk -> UBLKCP, completion on
-// mbarriers); 8 consumer warps run an 8x4 register tile of DFMAs each.  The betas never go to
+// mbarriers); 8 consumer warps run an 8x8 register tile of DFMAs per thread (64 DFMA per 6 LDS.128).  The betas never go to
 // HBM: the epilogue turns them into t (or Sobel z) in registers:
 //     SSE = yy - b'Gb,  sigma2 = SSE/dof,  se = fl32(sqrt(sigma2 * d)),  t = b / (double)se
 // keeping the reference's fp32 rounding of se (cynumstats.pyx:49-51).
@@ -15,7 +15,8 @@
 
 namespace tmb {
 
-static constexpr int BM = 64;       // design rows per tile
+static constexpr int BM = 128;      // design rows per tile
+static constexpr int TN = 8;        // vertices per thread: columns tn*4..+3 and 64+tn*4..+3 of the tile
 static constexpr int BN = 128;      // vertices per tile
 static constexpr int BK = 32;       // subjects per stage
 static constexpr int STAGES = 3;
@@ -77,7 +78,7 @@ struct GlmParams {
 // sum_{a,b in [lo,lo+r)} acc[g*RP+a][c] * G[(a-lo)*r + (b-lo)] * acc[g*RP+b][c]; every loop is fully
 // unrolled with predicates so the accumulator tile stays in registers.
 template <int RP>
-__device__ __forceinline__ double quad_form(const double (&acc)[8][4], int g, int c, const double *__restrict__ G,
+__device__ __forceinline__ double quad_form(const double (&acc)[8][TN], int g, int c, const double *__restrict__ G,
                                             int lo, int r) {
     double q = 0.0;
 #pragma unroll
@@ -94,7 +95,7 @@ __device__ __forceinline__ double quad_form(const double (&acc)[8][4], int g, in
 }
 
 template <int RP>
-__device__ __forceinline__ double pick_row(const double (&acc)[8][4], int g, int c, int idx) {
+__device__ __forceinline__ double pick_row(const double (&acc)[8][TN], int g, int c, int idx) {
     double v = 0.0;
 #pragma unroll
     for (int a = 0; a < RP; ++a)
@@ -109,25 +110,42 @@ __device__ __forceinline__ double t_from(double beta, double sse, double dof, do
     return __ddiv_rn(beta, (double)se);
 }
 
+// one output row of a thread's tile: two 128-bit stores (float) / eight scalar stores (double)
+__device__ __forceinline__ void store_tile_row(float *t32, double *t64, size_t off, int64_t v0, int tn,
+                                               const float (&o32)[8], const double (&o64)[8]) {
+    const size_t c0 = off + v0 + tn * 4;
+    if (t32) {
+        *reinterpret_cast<float4 *>(t32 + c0) = make_float4(o32[0], o32[1], o32[2], o32[3]);
+        *reinterpret_cast<float4 *>(t32 + c0 + 64) = make_float4(o32[4], o32[5], o32[6], o32[7]);
+    }
+    if (t64) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { t64[c0 + c] = o64[c]; t64[c0 + 64 + c] = o64[4 + c]; }
+    }
+}
+
+// column c (0..7) of a thread's tile: two groups of four, 64 vertices apart (conflict-free LDS.128)
+__device__ __forceinline__ int64_t tile_col(int64_t v0, int tn, int c) { return v0 + (c >> 2) * 64 + tn * 4 + (c & 3); }
+
 template <int RP>
-__device__ __forceinline__ void epilogue(const GlmParams &p, const double (&acc)[8][4], int m_base, int64_t v_base) {
-    // thread owns design rows m_base .. m_base+7 and vertices v_base .. v_base+3
+__device__ __forceinline__ void epilogue(const GlmParams &p, const double (&acc)[8][TN], int m_base, int64_t v0, int tn) {
+    // thread owns design rows m_base .. m_base+7 and the vertices tile_col(v0, tn, 0..7)
     if (p.mode == 1) { // betas
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int m = m_base + i;
             if (m < p.P * RP) {
-                double *dst = p.t64 + (size_t)m * p.ldt + v_base;
+                double *dst = p.t64 + (size_t)m * p.ldt;
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (v_base + c < p.V) dst[c] = acc[i][c];
+                for (int c = 0; c < TN; ++c)
+                    if (tile_col(v0, tn, c) < p.V) dst[tile_col(v0, tn, c)] = acc[i][c];
             }
         }
         return;
     }
-    double yy[4];
+    double yy[TN];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) yy[c] = (v_base + c < p.V) ? p.yy[v_base + c] : 0.0;
+    for (int c = 0; c < TN; ++c) yy[c] = (tile_col(v0, tn, c) < p.V) ? p.yy[tile_col(v0, tn, c)] : 0.0;
 
 #pragma unroll
     for (int g = 0; g < 8 / RP; ++g) {
@@ -137,38 +155,34 @@ __device__ __forceinline__ void epilogue(const GlmParams &p, const double (&acc)
             const int r = p.r;
             const double *G = p.G + (size_t)perm * r * r;
             const double *dg = p.d + (size_t)perm * r;
-            double sse[4];
+            double sse[TN];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) sse[c] = yy[c] - quad_form<RP>(acc, g, c, G, 0, r);
+            for (int c = 0; c < TN; ++c) sse[c] = yy[c] - quad_form<RP>(acc, g, c, G, 0, r);
 #pragma unroll
             for (int a = 0; a < RP; ++a) {
                 if (a < p.row0 || a >= p.row0 + p.nrows || a >= r) continue;
                 const double da = dg[a];
-                float o32[4];
-                double o64[4];
+                float o32[TN];
+                double o64[TN];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < TN; ++c) {
                     double t = t_from(acc[g * RP + a][c], sse[c], p.dof, da);
                     if (p.nan_to_zero && t != t) t = 0.0;
-                    if (v_base + c >= p.V) t = 0.0;
+                    if (tile_col(v0, tn, c) >= p.V) t = 0.0;
                     o64[c] = t;
                     o32[c] = __double2float_rn(t);
                 }
-                const size_t off = ((size_t)perm * p.nrows + (a - p.row0)) * p.ldt + v_base;
-                if (p.t32) *reinterpret_cast<float4 *>(p.t32 + off) = make_float4(o32[0], o32[1], o32[2], o32[3]);
-                if (p.t64) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) p.t64[off + c] = o64[c];
-                }
+                const size_t off = ((size_t)perm * p.nrows + (a - p.row0)) * p.ldt;
+                store_tile_row(p.t32, p.t64, off, v0, tn, o32, o64);
             }
         } else { // sobel (pyfunc.py:130-162)
             const int rA = p.rA, rB = p.rB;
             const double *GB = p.GB + (size_t)perm * rB * rB;
             const double dBr = p.dB[(size_t)perm * rB + p.rowB];
-            float o32[4];
-            double o64[4];
+            float o32[TN];
+            double o64[TN];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < TN; ++c) {
                 double ta;
                 if (p.ta_scalar) {
                     ta = p.ta_scalar[perm];
@@ -185,29 +199,25 @@ __device__ __forceinline__ void epilogue(const GlmParams &p, const double (&acc)
                 if (p.alg == 0) s = __dadd_rn(s, cross);
                 else if (p.alg == 2) s = __dsub_rn(s, cross);
                 double z = __ddiv_rn(1.0, __dsqrt_rn(s));
-                if (v_base + c >= p.V) z = 0.0;
+                if (tile_col(v0, tn, c) >= p.V) z = 0.0;
                 o64[c] = z;
                 o32[c] = __double2float_rn(z);
             }
-            const size_t off = (size_t)perm * p.ldt + v_base;
-            if (p.t32) *reinterpret_cast<float4 *>(p.t32 + off) = make_float4(o32[0], o32[1], o32[2], o32[3]);
-            if (p.t64) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) p.t64[off + c] = o64[c];
-            }
+            const size_t off = (size_t)perm * p.ldt;
+            store_tile_row(p.t32, p.t64, off, v0, tn, o32, o64);
         }
     }
 }
 
 template <typename YT>
-__device__ __forceinline__ void load_y4(const YT *p, double (&y)[4]);
+__device__ __forceinline__ void load_y4(const YT *p, double *y);
 template <>
-__device__ __forceinline__ void load_y4<float>(const float *p, double (&y)[4]) {
+__device__ __forceinline__ void load_y4<float>(const float *p, double *y) {
     const float4 f = *reinterpret_cast<const float4 *>(p);
     y[0] = (double)f.x; y[1] = (double)f.y; y[2] = (double)f.z; y[3] = (double)f.w;
 }
 template <>
-__device__ __forceinline__ void load_y4<double>(const double *p, double (&y)[4]) {
+__device__ __forceinline__ void load_y4<double>(const double *p, double *y) {
     const double2 a = *reinterpret_cast<const double2 *>(p);
     const double2 b = *reinterpret_cast<const double2 *>(p + 2);
     y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y;
@@ -258,13 +268,13 @@ __global__ void __launch_bounds__(kGlmThreads, 1) glm_tile_kernel(GlmParams p, i
     }
 
     // ===== consumers =====
-    const int tm = tid >> 5;  // 0..7  -> design rows tm*8 .. +7   (warp-uniform: A reads broadcast)
-    const int tn = tid & 31;  // 0..31 -> vertices tn*4 .. +3
-    double acc[8][4];
+    const int tm = tid >> 4;  // 0..15 -> design rows tm*8 .. +7   (two values per warp: A reads broadcast per half-warp)
+    const int tn = tid & 15;  // 0..15 -> vertices tn*4 .. +3 and 64+tn*4 .. +3
+    double acc[8][TN];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[i][c] = 0.0;
+        for (int c = 0; c < TN; ++c) acc[i][c] = 0.0;
 
     for (int kc = 0; kc < nchunks; ++kc) {
         const int s = kc % STAGES;
@@ -280,17 +290,18 @@ __global__ void __launch_bounds__(kGlmThreads, 1) glm_tile_kernel(GlmParams p, i
             const double2 a45 = *reinterpret_cast<const double2 *>(a_base + kk * BM + 4);
             const double2 a67 = *reinterpret_cast<const double2 *>(a_base + kk * BM + 6);
             const double a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
-            double y[4];
+            double y[TN];
             load_y4<YT>(y_base + kk * BN, y);
+            load_y4<YT>(y_base + kk * BN + 64, y + 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[i][c] = __fma_rn(a[i], y[c], acc[i][c]);
+                for (int c = 0; c < TN; ++c) acc[i][c] = __fma_rn(a[i], y[c], acc[i][c]);
         }
         __syncwarp();
-        if (tn == 0) mbar_arrive(empty + s);
+        if ((tid & 31) == 0) mbar_arrive(empty + s); // one arrival per consumer warp
     }
-    epilogue<RP>(p, acc, m0 + tm * 8, v0 + tn * 4);
+    epilogue<RP>(p, acc, m0 + tm * 8, v0, tn);
 }
 
 // ---------------------------------------------------------------- per-vertex sum of squares

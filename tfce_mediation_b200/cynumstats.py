@@ -80,7 +80,7 @@ def cy_lin_lstsqr_mat(X, y):
     y2, was1d = _as_2d(y)
     Y = DeviceMatrix(y2)
     dev = Y.t.device
-    ldA = (k + 63) // 64 * 64
+    ldA = (k + 127) // 128 * 128
     At = np.zeros((n, ldA), dtype=np.float64)
     At[:, :k] = _pinv(X).T
     Atd = torch.from_numpy(At).to(dev)
