@@ -5,9 +5,8 @@
 //
 // One dense fp64 contraction  B[P*rp, V] = At^T[P*rp, n] . Y[n, V]  with the stacked
 // pseudo-inverses of P permuted designs as the left operand, tiled 128 (design rows) x 128
-// (vertices) x 32 (subjects) per CTA.  A dedicated producer warp streams both operands into a
-// 3-stage shared-memory ring with bulk async copies (cp.async.bulk -> UBLKCP, completion on
-// mbarriers); 8 consumer warps run an 8x8 register tile of DFMAs per thread (64 DFMA per 6 LDS.128).  The betas never go to
+// (vertices) x 32 (subjects) per CTA.  One elected thread streams both operands into a 3-stage
+// shared-memory ring with bulk async copies (cp.async.bulk -> UBLKCP, completion on mbarriers); 8 consumer warps run an 8x8 register tile of DFMAs per thread (64 DFMA per 6 LDS.128).  The betas never go to
 // HBM: the epilogue turns them into t (or Sobel z) in registers:
 //     SSE = yy - b'Gb,  sigma2 = SSE/dof,  se = fl32(sqrt(sigma2 * d)),  t = b / (double)se
 // keeping the reference's fp32 rounding of se (cynumstats.pyx:49-51).
@@ -21,7 +20,8 @@ static constexpr int BN = 128;      // vertices per tile
 static constexpr int BK = 32;       // subjects per stage
 static constexpr int STAGES = 3;
 static constexpr int kConsumers = 256;
-static constexpr int kGlmThreads = kConsumers + 32;
+static constexpr int kGlmThreads = kConsumers; // 8 warps; thread 0 doubles as the copy issuer (a 9th warp would
+                                               // round the CTA up to 12 warps of registers and cap the tile at 168 regs)
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -247,25 +247,22 @@ __global__ void __launch_bounds__(kGlmThreads, 1) glm_tile_kernel(GlmParams p, i
     }
     __syncthreads();
 
-    if (tid >= kConsumers) {
-        // ===== producer warp: one elected lane issues the bulk copies =====
-        if (tid == kConsumers) {
-            for (int kc = 0; kc < nchunks; ++kc) {
-                const int s = kc % STAGES;
-                const int round = kc / STAGES;
-                mbar_wait(empty + s, (round & 1) ^ 1);
-                const int k0 = kc * BK;
-                const int rows = min(BK, p.n - k0);
-                mbar_expect_tx(full + s, (uint32_t)rows * (BM * 8 + BN * (uint32_t)sizeof(YT)));
-                for (int kk = 0; kk < rows; ++kk) {
-                    bulk_g2s(sA + ((size_t)s * BK + kk) * BM, p.At + (size_t)(k0 + kk) * p.ldA + m0, BM * 8, full + s);
-                    bulk_g2s(sY + ((size_t)s * BK + kk) * BN, reinterpret_cast<const YT *>(p.Y) + (size_t)(k0 + kk) * p.ldy + v0,
-                             BN * (uint32_t)sizeof(YT), full + s);
-                }
-            }
+    // issue the bulk copies of chunk kc into its ring slot (thread 0 only)
+    auto issue_chunk = [&](int kc) {
+        const int s = kc % STAGES;
+        const int round = kc / STAGES;
+        mbar_wait(empty + s, (round & 1) ^ 1); // every consumer warp has released the slot
+        const int k0 = kc * BK;
+        const int rows = min(BK, p.n - k0);
+        mbar_expect_tx(full + s, (uint32_t)rows * (BM * 8 + BN * (uint32_t)sizeof(YT)));
+        for (int kk = 0; kk < rows; ++kk) {
+            bulk_g2s(sA + ((size_t)s * BK + kk) * BM, p.At + (size_t)(k0 + kk) * p.ldA + m0, BM * 8, full + s);
+            bulk_g2s(sY + ((size_t)s * BK + kk) * BN, reinterpret_cast<const YT *>(p.Y) + (size_t)(k0 + kk) * p.ldy + v0,
+                     BN * (uint32_t)sizeof(YT), full + s);
         }
-        return;
-    }
+    };
+    if (tid == 0)
+        for (int kc = 0; kc < STAGES - 1 && kc < nchunks; ++kc) issue_chunk(kc); // prologue: fill the ring
 
     // ===== consumers =====
     const int tm = tid >> 4;  // 0..15 -> design rows tm*8 .. +7   (two values per warp: A reads broadcast per half-warp)
@@ -279,6 +276,8 @@ __global__ void __launch_bounds__(kGlmThreads, 1) glm_tile_kernel(GlmParams p, i
     for (int kc = 0; kc < nchunks; ++kc) {
         const int s = kc % STAGES;
         const int round = kc / STAGES;
+        // keep STAGES-1 chunks in flight: the slot released by iteration kc-1 is refilled now
+        if (tid == 0 && kc + STAGES - 1 < nchunks) issue_chunk(kc + STAGES - 1);
         mbar_wait(full + s, round & 1);
         const int rows = min(BK, p.n - kc * BK);
         const double *a_base = sA + (size_t)s * BK * BM + tm * 8;

@@ -880,62 +880,58 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
             sStart[kMaxSteps] = run;
         }
         __syncthreads();
+        // Second pass of the sort, fused with the ascent scan (P): in vertex order the fixed-width rows and the
+        // level bytes of the neighbours are read coalesced / in a narrow window, and the sorted position is known
+        // here, so everything a level owns -- ascent target, earlier-neighbour mask, basin id, later the leaf --
+        // is written as a dense segment indexed by sorted position.  Only basin[] is looked up at random.
+        const bool use_mask = sd.ell != nullptr && sd.ell_width <= 32;
+        int *const peaklist = reinterpret_cast<int *>(ws.clist); // scratch until the level loop starts
         for (int v0 = c_beg; v0 < c_end; v0 += 32) {
             const int v = v0 + lane;
-            const int lev = (v < c_end) ? (lev8[v] & 0x7f) : 0;
+            const int cv = (v < c_end) ? lev8[v] : 0;
+            const int lev = cv & 0x7f;
             const unsigned peers = __match_any_sync(0xffffffffu, lev);
             int base = 0;
             if (lev > 0) base = myHist[lev] + sStart[lev];
             __syncwarp();
             if (lev > 0) {
-                ws.order[base + __popc(peers & lt_mask)] = v;
+                const int pos = base + __popc(peers & lt_mask);
+                ws.order[pos] = v;
                 if (lane == (__ffs(peers) - 1)) myHist[lev] += __popc(peers);
+                int best = v, bestlev = lev;
+                unsigned em = 0; // earlier-activated neighbours: lower level, or same level and smaller index
+                const RowIter row(sd, v);
+                for (int c = 0; c < row.nchunks; ++c) {
+                    int nb[8];
+                    row.load(c, nb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (nb[j] < 0) continue;
+                        const int ca = lev8[nb[j]];
+                        if (ca == 0 || ((ca ^ cv) & 0x80)) continue;
+                        const int la = ca & 0x7f;
+                        if (la < bestlev) { best = nb[j]; bestlev = la; }
+                        if (c < 4 && (la < lev || (la == lev && nb[j] < v))) em |= 1u << (c * 8 + j);
+                    }
+                }
+                ws.up[pos] = best;
+                if (use_mask) {
+                    // a single earlier neighbour that is also the ascent target can never trigger a union
+                    if (best != v && __popc(em) == 1) em = 0;
+                    ws.emask[pos] = em;
+                }
+                if (best == v) { // a peak: new basin
+                    const int pid = atomicAdd(&sNB, 1);
+                    peaklist[pid] = v; // basin[] is written once the id width is known
+                    ws.basinS[pos] = pid;
+                    ws.blev_g[pid] = (unsigned char)cv;
+                }
             }
             __syncwarp();
         }
         __syncthreads();
         const int total_active = sStart[kMaxSteps];
         TMB_TICK(1)
-
-        // ---- P: ascent pointer per active vertex; peaks get compact basin ids --------------------------
-        const bool use_mask = sd.ell != nullptr && sd.ell_width <= 32;
-        int *const peaklist = reinterpret_cast<int *>(ws.clist); // scratch until the level loop starts
-        // (sorted order: everything a level owns -- ascent target, mask, basin id, leaf -- is then a dense
-        //  segment indexed by sorted position; only basin[] is looked up at random neighbours)
-        for (int idx = tid; idx < total_active; idx += nthr) {
-            const int v = ws.order[idx];
-            const int cv = lev8[v];
-            const int lv = cv & 0x7f;
-            int best = v, bestlev = lv;
-            unsigned em = 0; // earlier-activated neighbours: lower level, or same level and smaller index
-            const RowIter row(sd, v);
-            for (int c = 0; c < row.nchunks; ++c) {
-                int nb[8];
-                row.load(c, nb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (nb[j] < 0) continue;
-                    const int ca = lev8[nb[j]];
-                    if (ca == 0 || ((ca ^ cv) & 0x80)) continue;
-                    const int la = ca & 0x7f;
-                    if (la < bestlev) { best = nb[j]; bestlev = la; }
-                    if (c < 4 && (la < lv || (la == lv && nb[j] < v))) em |= 1u << (c * 8 + j);
-                }
-            }
-            ws.up[idx] = best;
-            if (use_mask) {
-                // a single earlier neighbour that is also the ascent target can never trigger a union
-                if (best != v && __popc(em) == 1) em = 0;
-                ws.emask[idx] = em;
-            }
-            if (best == v) {
-                const int pid = atomicAdd(&sNB, 1);
-                peaklist[pid] = v; // basin[] is written once the id width is known
-                ws.basinS[idx] = pid;
-                ws.blev_g[pid] = (unsigned char)cv;
-            }
-        }
-        __syncthreads();
         const int NB = sNB;
         // basin ids by vertex -- the one array that is looked up at random neighbours -- are stored as 16-bit
         // values whenever they fit: half the sectors, and the sweeps of 148 items in flight then fit the L2

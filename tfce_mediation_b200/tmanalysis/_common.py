@@ -7,7 +7,7 @@ import numpy as np
 from .. import parallel
 from .._graph import adjacency_to_csr, induced_subgraph
 
-BLOCK = 256      # shuffles per engine call
+BLOCK = 512      # shuffles per engine call
 
 
 def load(path):
