@@ -12,6 +12,9 @@
 // keeping the reference's fp32 rounding of se (cynumstats.pyx:49-51).
 #include "common.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace tmb {
 
 static constexpr int BM = 128;      // design rows per tile
@@ -303,6 +306,137 @@ __global__ void __launch_bounds__(kGlmThreads, 1) glm_tile_kernel(GlmParams p, i
     epilogue<RP>(p, acc, m0 + tm * 8, v0, tn);
 }
 
+// ---------------------------------------------------------------- fp64 tensor-core (DMMA) variant
+// The same contraction on the fp64 tensor cores: mma.sync.m8n8k4.f64 (SASS DMMA).  On B200 the DFMA
+// version above saturates the fp64 vector pipe (ncu: math-pipe throttle); the tensor path has twice the
+// fp64 throughput.  Used for the headline case r == 1 (one slope per design, k = 2), whose epilogue needs
+// no exchange between threads: every accumulator element is one (design, vertex) pair.
+// CTA tile 64 (designs) x 128 (vertices) x 32 (subjects); 8 warps as 2 (m) x 4 (n), warp tile 32 x 32 =
+// 4 x 4 DMMA tiles (4 + 4 fragment loads and 4 conversions per 16 DMMAs).  Shared-memory rows are pitched (+4 doubles / +8 floats) so that the fragment loads
+// -- A[m = lane/4][k = lane%4], B[k = lane%4][n = lane/4] -- are bank-conflict free.
+static constexpr int DM = 64, DN = 128, DK = 32, DSTAGES = 3;
+static constexpr int DPA = DM + 4;   // pitch of an A row (doubles)
+static constexpr int DPY = DN + 8;   // pitch of a Y row (elements)
+
+__device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <typename YT>
+__global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sA = reinterpret_cast<double *>(smem_raw);                                  // [DSTAGES][DK][DPA]
+    YT *sY = reinterpret_cast<YT *>(smem_raw + sizeof(double) * DSTAGES * DK * DPA);    // [DSTAGES][DK][DPY]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + sizeof(double) * DSTAGES * DK * DPA +
+                                                   sizeof(YT) * DSTAGES * DK * DPY);
+    uint64_t *empty = full + DSTAGES;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int mt = tile % mtiles;
+    const int64_t vt = tile / mtiles;
+    const int m0 = mt * DM;
+    const int64_t v0 = vt * DN;
+    const int nchunks = (p.n + DK - 1) / DK;
+    if (tid == 0) {
+        for (int s = 0; s < DSTAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue_chunk = [&](int kc) {
+        const int s = kc % DSTAGES;
+        const int round = kc / DSTAGES;
+        mbar_wait(empty + s, (round & 1) ^ 1);
+        const int k0 = kc * DK;
+        const int rows = min(DK, p.n - k0);
+        mbar_expect_tx(full + s, (uint32_t)rows * (DM * 8 + DN * (uint32_t)sizeof(YT)));
+        for (int kk = 0; kk < rows; ++kk) {
+            bulk_g2s(sA + ((size_t)s * DK + kk) * DPA, p.At + (size_t)(k0 + kk) * p.ldA + m0, DM * 8, full + s);
+            bulk_g2s(sY + ((size_t)s * DK + kk) * DPY, reinterpret_cast<const YT *>(p.Y) + (size_t)(k0 + kk) * p.ldy + v0,
+                     DN * (uint32_t)sizeof(YT), full + s);
+        }
+    };
+    if (tid == 0)
+        for (int kc = 0; kc < DSTAGES - 1 && kc < nchunks; ++kc) issue_chunk(kc);
+
+    const int wm = warp >> 2, wn = warp & 3;      // warp tile: rows wm*32.., cols wn*32..
+    const int g = lane >> 2, t4 = lane & 3;       // fragment coordinates
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kc = 0; kc < nchunks; ++kc) {
+        const int s = kc % DSTAGES;
+        const int round = kc / DSTAGES;
+        if (tid == 0 && kc + DSTAGES - 1 < nchunks) issue_chunk(kc + DSTAGES - 1);
+        mbar_wait(full + s, round & 1);
+        const int rows = min(DK, p.n - kc * DK);
+        const double *a_st = sA + (size_t)s * DK * DPA + wm * 32 + g;
+        const YT *y_st = sY + (size_t)s * DK * DPY + wn * 32 + g;
+        for (int k4 = 0; k4 < rows; k4 += 4) {
+            const int kr = k4 + t4;
+            const bool ok = kr < rows;   // the last chunk of n may be ragged: pad the k-slice with zeros
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = ok ? a_st[(size_t)kr * DPA + i * 8] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = ok ? (double)y_st[(size_t)kr * DPY + j * 8] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+    // epilogue (r == 1): element (i, j, e) is design m0 + wm*32 + i*8 + g, vertex v0 + wn*32 + j*8 + t4*2 + e
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int perm = m0 + wm * 32 + i * 8 + g;
+        if (perm >= p.P) continue;
+        const double G = p.G[perm], dg = p.d[perm];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t v = v0 + wn * 32 + j * 8 + t4 * 2;
+            float o32[2];
+            double o64[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double beta = acc[i][j][e];
+                const double yyv = (v + e < p.V) ? p.yy[v + e] : 0.0;
+                const double sse = yyv - __dmul_rn(beta, __dmul_rn(G, beta));
+                double t = t_from(beta, sse, p.dof, dg);
+                if (p.nan_to_zero && t != t) t = 0.0;
+                if (v + e >= p.V) t = 0.0;
+                o64[e] = t;
+                o32[e] = __double2float_rn(t);
+            }
+            const size_t off = (size_t)perm * p.ldt + v;
+            if (p.t32) *reinterpret_cast<float2 *>(p.t32 + off) = make_float2(o32[0], o32[1]);
+            if (p.t64) { p.t64[off] = o64[0]; p.t64[off + 1] = o64[1]; }
+        }
+    }
+}
+
+template <typename YT>
+static int launch_dmma(const GlmParams &p, cudaStream_t stream) {
+    const int mtiles = (p.P + DM - 1) / DM;
+    const int64_t vtiles = (p.V + DN - 1) / DN;
+    const int64_t tiles = (int64_t)mtiles * vtiles;
+    TMB_REQUIRE(tiles < (int64_t)INT32_MAX, "glm: too many tiles");
+    const size_t smem = sizeof(double) * DSTAGES * DK * DPA + sizeof(YT) * DSTAGES * DK * DPY + sizeof(uint64_t) * 2 * DSTAGES;
+    TMB_CUDA(cudaFuncSetAttribute(glm_dmma_kernel<YT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    glm_dmma_kernel<YT><<<(unsigned)tiles, 256, smem, stream>>>(p, mtiles);
+    count_launch();
+    TMB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ---------------------------------------------------------------- per-vertex sum of squares
 template <typename YT>
 __global__ void glm_sumsq_kernel(const YT *__restrict__ Y, int n, int64_t V, int64_t ldy, int center,
@@ -439,6 +573,14 @@ int launch_glm(const GlmParams &p, cudaStream_t stream) {
     TMB_REQUIRE((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.At) & 15) == 0,
                 "glm: Y and At must be 16-byte aligned");
     TMB_REQUIRE(!p.t32 || (reinterpret_cast<uintptr_t>(p.t32) & 15) == 0, "glm: t32 must be 16-byte aligned");
+    {
+        // headline case (one slope per design, t-statistic): fp64 tensor cores; TMB_GLM=dfma forces the vector kernel
+        const char *force = getenv("TMB_GLM");
+        const bool dfma = force && strcmp(force, "dfma") == 0;
+        // (float32 data only: with fp64 data the doubled Y stage halves the resident CTAs and DFMA wins, measured)
+        if (!dfma && !p.y_is_f64 && p.mode == 0 && p.r == 1 && p.rp == 1 && p.row0 == 0 && p.nrows == 1)
+            return launch_dmma<float>(p, stream);
+    }
     return p.y_is_f64 ? launch_glm_t<double>(p, stream) : launch_glm_t<float>(p, stream);
 }
 
