@@ -65,6 +65,19 @@ struct tmb_plan {
     int use_basin = 0;          // every surface symmetric -> V3 basin sweep
     int internal_order = 0;     // statistic rows already use the graphs' internal vertex order (vmap ignored)
     unsigned long long *d_timing = nullptr; // TMB_PHASE_TIMING=1: per-phase cycle totals
+    // streaming pipeline (tfce_pipeline.cu): per-item buffers for `pipe_items` work items, grown on demand
+    int pipe_ok = 0;            // basin path and every surface has fixed-width rows of at most 32 slots
+    int pipe_weights = 0;       // some surface carries vertex weights (scaled maxima then need the per-vertex pass)
+    int pipe_items = 0;
+    int64_t pipe_vstride = 0, pipe_tabcap = 0;
+    int pipe_nbcap = 0, pipe_paircap = 0;
+    char *d_pipe = nullptr;     // one allocation: lev8 | up | emask | basin | meta | blev | pairs | table
+    char *d_pipe_slots = nullptr;
+    size_t pipe_slot_stride = 0;
+    int pipe_slots = 0;
+    // device-built threshold tables (exact_pow = False) for `tab_items` work items
+    int tab_items = 0;
+    char *d_tabs = nullptr;     // maxima | ns | status | delta | T | HH
 };
 
 extern "C" const char *tmb_last_error(void) { return g_error.c_str(); }
@@ -345,6 +358,15 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
     if ((e = cudaMalloc(&p->d_workspace, p->slot_stride * (size_t)p->num_slots)) != cudaSuccess) return fail("malloc workspace", e);
     if ((e = cudaMemcpy(p->d_surfs, descs.data(), sizeof(SurfDesc) * S, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("memcpy", e);
     if ((e = cudaMemcpy(p->d_order, order.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("memcpy", e);
+    {
+        const char *tf = getenv("TMB_TFCE"); // "basin" forces the one-kernel sweep (A/B measurements)
+        p->pipe_ok = p->use_basin && !(tf && strcmp(tf, "basin") == 0);
+        for (int s = 0; s < S; ++s) {
+            if (!graphs[s]->d_ell || graphs[s]->ell_width > 32) p->pipe_ok = 0;
+            if (p->d_weights[s]) p->pipe_weights = 1;
+        }
+        p->pipe_slots = 2 * prop.multiProcessorCount; // up to two sweep CTAs per SM
+    }
     *out = p;
     return 0;
 }
@@ -352,12 +374,19 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
 extern "C" int tmb_plan_destroy(tmb_plan *p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
+    cudaFree(p->d_pipe); cudaFree(p->d_pipe_slots); cudaFree(p->d_tabs);
+    p->d_pipe = p->d_pipe_slots = p->d_tabs = nullptr;
     if (p->d_timing) {
         unsigned long long t[272];
         if (cudaMemcpy(t, p->d_timing, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess) {
             static const char *names_v2[7] = {"tables", "levels+sort", "X: P2bc+P1", "Y: P2a", "tail", "node walk", "finalize"};
             static const char *names_v3[7] = {"tables", "levels+sort", "ascent+init", "I1: unions", "I2: sizes", "node walk", "finalize"};
-            const char **names = p->use_basin ? names_v3 : names_v2;
+            static const char *names_pipe[7] = {"S: init+sort", "S: (loop rest)", "S: outputs", "S: F1 unions", "S: F2 sizes", "S: F3 incr", "S: fold"};
+            const char **names = p->pipe_ok ? names_pipe : p->use_basin ? names_v3 : names_v2;
+            if (p->pipe_ok)
+                fprintf(stderr, "[tmb pipeline] maps swept %llu (mean basins %.0f, candidate unions %.0f, classes %.0f), flagged for the sweep kernel %llu\n",
+                        t[13], t[13] ? (double)t[11] / t[13] : 0.0, t[13] ? (double)t[12] / t[13] : 0.0,
+                        t[13] ? (double)t[7] / t[13] : 0.0, t[10]);
             double tot = 0;
             for (int i = 0; i < 7; ++i) tot += (double)t[i];
             tot += (double)t[8] + (double)t[9];
@@ -365,7 +394,7 @@ extern "C" int tmb_plan_destroy(tmb_plan *p) {
             for (int i = 0; i < 7; ++i) fprintf(stderr, "  %-12s %6.2f%%\n", names[i], tot > 0 ? 100.0 * t[i] / tot : 0.0);
 
         }
-        if (p->use_basin) {
+        if (p->use_basin && !p->pipe_ok) {
             double tot = 0;
             for (int i = 0; i < 7; ++i) tot += (double)t[i];
             fprintf(stderr, "  per-level share of I1 / I2 (levels 1..127, %% of total):\n");
@@ -389,22 +418,141 @@ struct TableSet {
     const int32_t *status = nullptr;
 };
 
-static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int two_sided, int accumulate,
-                       float *max_dev, float *tfce_pos, float *tfce_neg, int32_t *status, int stop_level,
-                       int32_t *labels, int32_t *extents, float *thr, cudaStream_t stream,
-                       const TableSet *tabs = nullptr) {
+static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+// per-item bytes of the streaming pipeline's buffers
+static size_t pipe_item_bytes(const tmb_plan *p) {
+    return al256((size_t)p->pipe_vstride) + 3 * al256(sizeof(int) * (size_t)p->pipe_vstride) + 16 + al256((size_t)p->pipe_nbcap) +
+           al256(sizeof(unsigned long long) * (size_t)p->pipe_paircap) + al256(sizeof(unsigned) * (size_t)p->pipe_tabcap);
+}
+
+// (re)allocate the pipeline buffers for at least `items` work items; returns the number of items that fit
+// the memory budget (a third of the free HBM), 0 when not even one does.
+static int pipe_ensure(tmb_plan *p, int items) {
+    if (p->pipe_vstride == 0) {
+        p->pipe_vstride = ((int64_t)p->Vmax + 127) / 128 * 128;
+        p->pipe_nbcap = (int)std::min<int64_t>(p->pipe_vstride, std::max<int64_t>(4096, p->pipe_vstride / 8));
+        p->pipe_paircap = (int)p->pipe_vstride;
+        p->pipe_tabcap = 8 * p->pipe_vstride;
+    }
+    if (!p->d_pipe_slots) {
+        p->pipe_slot_stride = pipe_slot_bytes(p->Vmax, p->pipe_nbcap, p->pipe_paircap);
+        if (cudaMalloc(&p->d_pipe_slots, p->pipe_slot_stride * (size_t)p->pipe_slots) != cudaSuccess) {
+            cudaGetLastError();
+            p->d_pipe_slots = nullptr;
+            return 0;
+        }
+    }
+    if (items <= p->pipe_items) return items;
+    const size_t per = pipe_item_bytes(p);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return p->pipe_items; }
+    const size_t have = (size_t)p->pipe_items * per;
+    const size_t fit = (free_b + have) / 3 / per;
+    int want = (int)std::min<size_t>((size_t)items, fit);
+    if (want <= p->pipe_items) return p->pipe_items;
+    cudaFree(p->d_pipe);
+    p->d_pipe = nullptr;
+    p->pipe_items = 0;
+    if (cudaMalloc(&p->d_pipe, per * (size_t)want + 8192) != cudaSuccess) { cudaGetLastError(); return 0; }
+    p->pipe_items = want;
+    return want;
+}
+
+static int tabs_ensure(tmb_plan *p, int items) {
+    if (items <= p->tab_items) return 0;
+    cudaFree(p->d_tabs);
+    p->d_tabs = nullptr;
+    p->tab_items = 0;
+    const size_t cnt = (size_t)items * 2;
+    TMB_CUDA(cudaMalloc(&p->d_tabs, cnt * (sizeof(float) * 2 + sizeof(int32_t) * 2 + sizeof(float) * 256)));
+    p->tab_items = items;
+    return 0;
+}
+
+static int plan_launch_sweep(tmb_plan *p, const float *stat, int64_t ld, int B, int two_sided, int accumulate,
+                             float *max_dev, float *tfce_pos, float *tfce_neg, int32_t *status, int stop_level,
+                             int32_t *labels, int32_t *extents, float *thr, cudaStream_t stream, const TableSet *tabs,
+                             const int *only_flagged) {
     SweepParams sp{};
     if (tabs) { sp.tab_ns = tabs->ns; sp.tab_delta = tabs->delta; sp.tab_T = tabs->T; sp.tab_HH = tabs->HH; sp.tab_status = tabs->status; }
     sp.surfs = p->d_surfs; sp.surf_order = p->d_order; sp.S = p->S; sp.B = B; sp.two_sided = two_sided;
     sp.accumulate = accumulate; sp.stat = stat; sp.ld = ld; sp.max_out = max_dev; sp.tfce_pos = tfce_pos;
     sp.tfce_neg = tfce_neg; sp.status = status; sp.stop_level = stop_level; sp.labels = labels;
     sp.extents = extents; sp.threshold_out = thr; sp.workspace = p->d_workspace; sp.slot_stride = p->slot_stride;
-    sp.Vmax = p->Vmax; sp.work_counter = p->d_counter; sp.timing = p->d_timing;
+    sp.Vmax = p->Vmax; sp.work_counter = p->d_counter; sp.timing = only_flagged ? nullptr : p->d_timing;
+    sp.only_flagged = only_flagged;
     {
         const char *pc = getenv("TMB_PARENT_UNCACHED");
         sp.flags = ((pc && pc[0] == '1') ? 0 : 1) | (p->use_basin ? 2 : 0) | (p->internal_order ? 4 : 0); // see SweepParams::flags
     }
     return launch_tfce_sweep(sp, p->num_slots, stream);
+}
+
+static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int two_sided, int accumulate,
+                       float *max_dev, float *tfce_pos, float *tfce_neg, int32_t *status, int stop_level,
+                       int32_t *labels, int32_t *extents, float *thr, cudaStream_t stream,
+                       const TableSet *tabs = nullptr) {
+    const bool pipeline = p->pipe_ok && !accumulate && stop_level < 0 && B > 0;
+    int fit = 0;
+    if (pipeline) fit = pipe_ensure(p, B * p->S) / p->S; // statistic rows per pipeline pass
+    if (!pipeline || fit < 1)
+        return plan_launch_sweep(p, stat, ld, B, two_sided, accumulate, max_dev, tfce_pos, tfce_neg, status, stop_level,
+                                 labels, extents, thr, stream, tabs, nullptr);
+    // ---- streaming pipeline, `fit` rows at a time; maps it flags as over capacity are redone by the sweep kernel
+    TableSet dev_tabs;
+    if (!tabs) {
+        // exact_pow = False: correctly rounded tables built on the device (no host round trip)
+        if (tabs_ensure(p, B * p->S)) return 1;
+        const size_t cnt = (size_t)B * p->S * 2;
+        float *mx = reinterpret_cast<float *>(p->d_tabs);
+        float *delta = mx + cnt;
+        int32_t *ns = reinterpret_cast<int32_t *>(delta + cnt);
+        int32_t *st = ns + cnt;
+        float *T = reinterpret_cast<float *>(st + cnt);
+        float *HH = T + cnt * 128;
+        if (launch_tfce_maxima(p->d_surfs, p->S, stat, ld, B, mx, stream)) return 1;
+        if (launch_tfce_tables(p->d_surfs, p->S, (int)cnt, mx, two_sided, ns, delta, T, HH, st, stream)) return 1;
+        dev_tabs.ns = ns; dev_tabs.delta = delta; dev_tabs.T = T; dev_tabs.HH = HH; dev_tabs.status = st;
+        tabs = &dev_tabs;
+    }
+    const size_t vs = (size_t)p->pipe_vstride;
+    for (int b0 = 0; b0 < B; b0 += fit) {
+        const int Bc = std::min(fit, B - b0);
+        const size_t items = (size_t)Bc * p->S;
+        const size_t eoff = (size_t)b0 * p->S * 2;
+        PipeParams pp{};
+        pp.surfs = p->d_surfs; pp.surf_order = p->d_order; pp.S = p->S; pp.B = Bc; pp.two_sided = two_sided;
+        pp.stat = stat + (size_t)b0 * ld; pp.ld = ld;
+        pp.tab_ns = tabs->ns + eoff; pp.tab_delta = tabs->delta + eoff; pp.tab_T = tabs->T + eoff * 128;
+        pp.tab_HH = tabs->HH + eoff * 128; pp.tab_status = tabs->status + eoff;
+        pp.flags = p->internal_order ? 4 : 0;
+        pp.Vmax = p->Vmax; pp.vstride = p->pipe_vstride;
+        char *base = p->d_pipe;
+        pp.lev8 = reinterpret_cast<unsigned char *>(base); base += al256(items * vs);
+        pp.up = reinterpret_cast<int *>(base); base += al256(items * vs * sizeof(int));
+        pp.emask = reinterpret_cast<unsigned *>(base); base += al256(items * vs * sizeof(int));
+        pp.basin = reinterpret_cast<int *>(base); base += al256(items * vs * sizeof(int));
+        pp.meta = reinterpret_cast<int *>(base); base += al256(items * 16);
+        pp.blev = reinterpret_cast<unsigned char *>(base); base += al256(items * (size_t)p->pipe_nbcap);
+        pp.pairs = reinterpret_cast<unsigned long long *>(base); base += al256(items * (size_t)p->pipe_paircap * sizeof(unsigned long long));
+        pp.table = reinterpret_cast<unsigned *>(base);
+        pp.nbcap = p->pipe_nbcap; pp.paircap = p->pipe_paircap; pp.tabcap = p->pipe_tabcap;
+        pp.max_out = max_dev ? max_dev + eoff : nullptr;
+        pp.tfce_pos = tfce_pos ? tfce_pos + (size_t)b0 * ld : nullptr;
+        pp.tfce_neg = tfce_neg ? tfce_neg + (size_t)b0 * ld : nullptr;
+        pp.status = status ? status + eoff : nullptr;
+        pp.want_vertex_pass = (tfce_pos || tfce_neg || p->pipe_weights) ? 1 : 0;
+        pp.slot_ws = p->d_pipe_slots; pp.slot_stride = p->pipe_slot_stride; pp.work_counter = p->d_counter;
+        pp.timing = p->d_timing;
+        if (launch_tfce_pipeline(pp, p->pipe_slots, stream)) return 1;
+        TableSet sub;
+        sub.ns = pp.tab_ns; sub.delta = pp.tab_delta; sub.T = pp.tab_T; sub.HH = pp.tab_HH; sub.status = pp.tab_status;
+        if (plan_launch_sweep(p, pp.stat, ld, Bc, two_sided, 0, pp.max_out, pp.tfce_pos, pp.tfce_neg, pp.status, -1, nullptr,
+                              nullptr, nullptr, stream, &sub, pp.meta))
+            return 1;
+    }
+    return 0;
 }
 
 extern "C" int tmb_plan_run(tmb_plan *p, const float *stat_dev, int64_t ld, int B, int two_sided, float *max_dev,

@@ -81,12 +81,61 @@ struct SweepParams {
     size_t slot_stride;
     int32_t Vmax;
     int *work_counter;
+    const int *only_flagged;    // optional [B*S][4]: process only work items with only_flagged[item*4 + 2] != 0
+                                // (maps the streaming pipeline could not take, see tfce_pipeline.cu)
+};
+
+// per-launch parameters of the streaming TFCE pipeline (tfce_pipeline.cu); work item = (row b, surface s)
+struct PipeParams {
+    const SurfDesc *surfs;
+    const int32_t *surf_order;
+    int S;
+    int B;
+    int two_sided;
+    const float *stat;
+    int64_t ld;
+    // threshold tables, entry e = (b*S + s)*2 + sign (host-built exact-libm tables or pipe_tables_kernel)
+    const int32_t *tab_ns;
+    const float *tab_delta;
+    const float *tab_T;
+    const float *tab_HH;
+    const int32_t *tab_status;
+    int flags;              // bit 2: statistic rows are in the graphs' internal vertex order
+    int32_t Vmax;
+    // per-item buffers
+    int64_t vstride;        // elements per work item in the per-vertex arrays
+    unsigned char *lev8;    // activation level | sign << 7; 0 = never active
+    int *up;                // ascent target; -1 - basin for a peak; INT_MIN when inactive
+    unsigned *emask;        // ELL slots holding an earlier-activated same-sign neighbour (ascent target excluded)
+    int *basin;             // compact basin id, -1 when inactive
+    int *meta;              // [items][4]: basins, candidate unions, over-capacity flag, unused
+    unsigned char *blev;    // [items][nbcap] level | sign of each peak
+    int nbcap;
+    unsigned long long *pairs; // [items][paircap] (level << 48) | (basin << 24) | basin
+    int paircap;
+    unsigned *table;        // [items][tabcap]: [level][basin] vertex counts -> class ids -> TFCE values
+    int64_t tabcap;
+    // outputs
+    float *max_out;
+    float *tfce_pos;
+    float *tfce_neg;
+    int32_t *status;
+    int want_vertex_pass;   // vertex weights or maps requested: values go through the table and K_G
+    // sweep slots
+    char *slot_ws;
+    size_t slot_stride;
+    int *work_counter;
+    unsigned long long *timing;
 };
 
 int launch_tfce_sweep(const SweepParams &p, int num_slots, cudaStream_t stream);
 int launch_tfce_maxima(const SurfDesc *surfs, int S, const float *stat, int64_t ld, int B, float *max_out,
                        cudaStream_t stream);
 size_t tfce_slot_bytes_for(int32_t Vmax, int use_basin);
+int launch_tfce_pipeline(const PipeParams &p, int num_slots, cudaStream_t stream);
+int launch_tfce_tables(const SurfDesc *surfs, int S, int count, const float *maxima, int two_sided, int32_t *ns,
+                       float *delta, float *T, float *HH, int32_t *st, cudaStream_t stream);
+size_t pipe_slot_bytes(int32_t Vmax, int nbcap, int paircap);
 void tfce_sweep_geometry(int32_t Vmax, int use_basin, int *threads, int *ctas_per_sm, size_t *dyn_smem);
 
 } // namespace tmb

@@ -42,6 +42,11 @@ static constexpr int kPending = -2;
 
 __device__ __forceinline__ int ld_cg(const int *p) { return __ldcg(p); }
 
+// software prefetch into L1 (generic address of a global object): the sweep is bound by the latency of
+// dependent loads, and most addresses are known one barrier interval before they are needed
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.L2 [%0];" ::"l"(p)); }
+
 // Union-find pointer load.  CACHED uses the default L1-allocating load.  That is safe here:
 //  * only this CTA ever touches its slot, and __syncthreads() orders the block's earlier global
 //    writes AND atomics before later loads of every thread of the block, so the phases that need the
@@ -757,6 +762,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
         __syncthreads();
         const int item = sItem;
         if (item >= total_items) break;
+        if (P.only_flagged && P.only_flagged[(size_t)item * 4 + 2] == 0) { __syncthreads(); continue; }
         const int s = P.surf_order[item / P.B];
         const int b = item % P.B;
         const SurfDesc sd = P.surfs[s];
@@ -842,29 +848,49 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
         const int chunk = (int)align_up((size_t)(V + nwarps - 1) / nwarps, 32);
         const int c_beg = wid * chunk, c_end = min(V, c_beg + chunk);
         int *const myHist = sHist + wid * kMaxSteps;
-        for (int v0 = c_beg; v0 < c_end; v0 += 32) {
-            const int v = v0 + lane;
-            int code = 0;
-            if (v < c_end) {
-                const float xv = x[vmap ? vmap[v] : v];
+        // activation level = smallest i >= 1 with |x| > T[i]: thresholds are (almost) equally spaced, so the
+        // index is guessed from (T[0] - |x|) / delta and corrected against the exact fp32 table (1-2 probes
+        // instead of a 7-step binary search).  Four 32-vertex groups per iteration: the four statistic loads
+        // (cold: t-maps stream from HBM) are in flight together.
+        const float rdel0 = sDelta[0] > 0.f ? __frcp_rn(sDelta[0]) : 0.f;
+        const float rdel1 = sDelta[1] > 0.f ? __frcp_rn(sDelta[1]) : 0.f;
+        for (int v0 = c_beg; v0 < c_end; v0 += 128) {
+            float xq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int v = v0 + q * 32 + lane;
+                xq[q] = (v < c_end) ? x[vmap ? vmap[v] : v] : 0.f;
+            }
+            int codes[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int v = v0 + q * 32 + lane;
+                const float xv = xq[q];
+                int code = 0;
                 if (xv > 0.f || xv < 0.f) {
                     const int sg = xv < 0.f;
                     const int ns = sg ? ns1 : ns0;
-                    const float ax = fabsf(xv);
-                    const float *T = sT[sg];
-                    int lo = 1, hi = ns;
-                    while (lo < hi) {
-                        int mid = (lo + hi) >> 1;
-                        if (ax > T[mid]) hi = mid; else lo = mid + 1;
+                    if (ns > 1) {
+                        const float ax = fabsf(xv);
+                        const float *T = sT[sg];
+                        int g = __float2int_rz((T[0] - ax) * (sg ? rdel1 : rdel0));
+                        g = max(0, min(g, ns - 1)) + 1;
+                        while (g > 1 && ax > T[g - 1]) --g;
+                        while (g < ns && !(ax > T[g])) ++g;
+                        if (g < ns) code = g | (sg << 7);
                     }
-                    if (lo < ns) code = lo | (sg << 7);
                 }
-                lev8[v] = (unsigned char)code;
+                codes[q] = code;
+                if (v < c_end) lev8[v] = (unsigned char)code;
             }
-            const int lev = code & 0x7f;
-            const unsigned peers = __match_any_sync(0xffffffffu, lev);
-            if (lev > 0 && lane == (__ffs(peers) - 1)) myHist[lev] += __popc(peers);
-            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (v0 + q * 32 >= c_end) break; // warp-uniform
+                const int lev = codes[q] & 0x7f;
+                const unsigned peers = __match_any_sync(0xffffffffu, lev);
+                if (lev > 0 && lane == (__ffs(peers) - 1)) myHist[lev] += __popc(peers);
+                __syncwarp();
+            }
         }
         __syncthreads();
         // level starts, then per-(warp, level) cursors = start[level] + counts of the earlier warps
@@ -888,6 +914,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
         int *const peaklist = reinterpret_cast<int *>(ws.clist); // scratch until the level loop starts
         for (int v0 = c_beg; v0 < c_end; v0 += 32) {
             const int v = v0 + lane;
+            if (sd.ell && v + 64 < c_end) prefetch_l1(sd.ell + (size_t)(v + 64) * sd.ell_width); // rows two groups ahead
             const int cv = (v < c_end) ? lev8[v] : 0;
             const int lev = cv & 0x7f;
             const unsigned peers = __match_any_sync(0xffffffffu, lev);
@@ -1014,6 +1041,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                     ws.leaf[idx] = bcur[ws.leaf[idx]];
             }
             if (!have_level) break;
+            {
+                int nl = lev + 1;
+                while (nl <= last_level && sStart[nl + 1] == sStart[nl]) ++nl;
+                if (nl <= last_level)
+                    for (int idx = sStart[nl] + tid; idx < sStart[nl + 1]; idx += nthr) {
+                        prefetch_l1(ws.order + idx);
+                        prefetch_l1(ws.up + idx);
+                    }
+            }
             int2 *mcur = ws.mlist[buf];
             for (int idx = beg + tid; idx < end; idx += nthr) {
                 const int u = ws.order[idx];
@@ -1126,6 +1162,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                             const int idx = idx0 + q * nthr;
                             vv[q] = idx < nend ? ws.order[idx] : -1;
                             tt[q] = idx < nend ? ws.up[idx] : -1;
+                            if (vv[q] >= 0) { // what I1 of that level reads for this vertex (cold since the scan)
+                                if (use_mask) prefetch_l1(ws.emask + idx);
+                                if (sd.ell) prefetch_l1(sd.ell + (size_t)vv[q] * sd.ell_width);
+                            }
                         }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) bb[q] = (vv[q] >= 0 && tt[q] != vv[q]) ? RD_BASIN(tt[q]) : -1;
@@ -1202,7 +1242,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                             pw[q] = rec.pw;
                             mainc[q] = rec.size < 0;
                             endl[q] = nsq[q];
-                            if (!mainc[q] && par != kNone) { prec[q] = ws.nodes[par]; endl[q] = (prec[q].pack >> 24) & 0x7f; }
+                            if (!mainc[q] && par != kNone) {
+                                prec[q] = ws.nodes[par];
+                                endl[q] = (prec[q].pack >> 24) & 0x7f;
+                                if ((prec[q].pack & kNone) != kNone) prefetch_l1(ws.nodes + (prec[q].pack & kNone));
+                            }
                         }
                     }
                     while (lvl[0] < nsq[0] || lvl[1] < nsq[1]) {
@@ -1215,7 +1259,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                                 pw[q] = rec.pw;
                                 mainc[q] = rec.size < 0;
                                 endl[q] = nsq[q];
-                                if (!mainc[q] && par != kNone) { prec[q] = ws.nodes[par]; endl[q] = (prec[q].pack >> 24) & 0x7f; }
+                                if (!mainc[q] && par != kNone) {
+                                    prec[q] = ws.nodes[par];
+                                    endl[q] = (prec[q].pack >> 24) & 0x7f;
+                                    if ((prec[q].pack & kNone) != kNone) prefetch_l1(ws.nodes + (prec[q].pack & kNone));
+                                }
                             }
                             const float inc = mainc[q] ? sMainInc[sgn[q]][lvl[q]]
                                                        : __double2float_rn(__dmul_rn(pw[q], sHHd[sgn[q]][lvl[q]]));

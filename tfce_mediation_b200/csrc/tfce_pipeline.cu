@@ -1,0 +1,777 @@
+// TFCE pipeline (sm_100a): the level sweep of lib/fast_tfce.hpp:11-95 moved from the VERTICES to the BASINS.
+//
+// tfce_basin_kernel (tfce_kernels.cu) walks every vertex once per barrier interval of a 100-level loop; it
+// is bound by the latency of dependent loads inside those intervals.  Here everything that is per VERTEX
+// is done by flat, barrier-free streaming kernels over all (statistic row, surface, vertex) triples of a
+// block of maps -- full occupancy, coalesced rows, no level loop:
+//
+//   K_A  levels   activation level per vertex (fast_tfce.hpp:39-41: x > T_i, exact fp32 threshold table)
+//   K_B  ascent   per vertex: the neighbour of the earliest level ("up"), the set of earlier neighbours;
+//                 vertices without an earlier neighbour are peaks and get compact basin ids
+//   K_C  basins   basin id per vertex = peak at the end of its ascent chain (read-only pointer chase)
+//   K_D  counts   table[level][basin] += 1;  every (vertex, earlier neighbour) pair that straddles two
+//                 basins becomes a candidate union (level, basin, basin)
+//
+// and the sequential part -- the threshold sweep with its union-find, component sizes and the fp32 sums
+// in the reference's order -- runs on the few thousand basins of a map, entirely in shared memory:
+//
+//   K_S  sweep    one CTA per map: candidate unions bucketed by level; per level: unions, sizes from the
+//                 table row, one accumulator ("class") per component that gains vertices, and every live
+//                 class adds fl32(pow(size, E) * pow(T, H)) of its component (fast_tfce.hpp:70-84)
+//   K_G  output   (only with vertex weights or when the maps are requested) per vertex value lookup
+//
+// Values are bit-identical to the reference: a vertex activated at level l receives, one fp32 add per level
+// l, l+1, ... in descending-threshold order, the increment of the component it belongs to at that level.
+// All vertices of one (level, component) share that sequence, hence one accumulator per such pair.
+// Maps whose basin count / pair count exceed the fixed capacities are flagged and redone by
+// tfce_basin_kernel (launch_tfce_sweep with only_flagged), so the result never depends on a capacity.
+#include "common.cuh"
+
+#include <climits>
+#include <cstdlib>
+
+namespace tmb {
+
+static constexpr int kLevels = 128;
+static constexpr int kInactive = INT_MIN;
+
+namespace {
+
+__device__ __forceinline__ int pf_find(int *parent, int v) {
+    int cur = v;
+    int p = parent[cur];
+    while (p != cur) {
+        const int gp = parent[p];
+        if (gp != p) parent[cur] = gp;
+        cur = p;
+        p = gp;
+    }
+    return cur;
+}
+
+__device__ __forceinline__ void pf_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ float pwarp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ void item_coords(const PipeParams &P, int item, int &s, int &b) {
+    s = P.surf_order[item / P.B];
+    b = item % P.B;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------- tables
+// exact_pow = False: threshold tables on the device from the per-map maxima, same fp32 operations as
+// fast_tfce.hpp:32-39 with a correctly rounded height term (see tfce_basin_kernel).
+__global__ void pipe_tables_kernel(const SurfDesc *__restrict__ surfs, int S, int count, const float *__restrict__ maxima,
+                                   int two_sided, int32_t *__restrict__ ns_out, float *__restrict__ delta_out,
+                                   float *__restrict__ T_out, float *__restrict__ HH_out, int32_t *__restrict__ st_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const int sg = e & 1;
+    const int s = (e >> 1) % S;
+    const float H = surfs[s].H;
+    const float mx = maxima[e];
+    int ns = 0, st = 0;
+    float d = 0.f;
+    if ((sg == 0 || two_sided) && mx >= 0.f) {
+        d = __fdiv_rn(mx, 100.0f);
+        if (d == 0.f) {
+            st = 1;
+        } else {
+            float T = mx;
+            while (T >= 0.f) {
+                if (ns == kLevels) { st = 2; ns = 0; break; }
+                T_out[(size_t)e * kLevels + ns] = T;
+                HH_out[(size_t)e * kLevels + ns] = (H == 2.0f) ? __fmul_rn(T, T) : (float)pow((double)T, (double)H);
+                ++ns;
+                T = __fsub_rn(T, d);
+            }
+        }
+    }
+    ns_out[e] = ns;
+    delta_out[e] = d;
+    st_out[e] = st;
+}
+
+// ------------------------------------------------------------------------------------------- K_A
+static constexpr int kChunkA = 2048; // vertices per CTA (8 per thread)
+
+__global__ void __launch_bounds__(256) pipe_levels_kernel(PipeParams P, int chunks) {
+    __shared__ float sT[2][kLevels];
+    __shared__ int sNs[2];
+    __shared__ float sRd[2];
+    const int tid = threadIdx.x;
+    const int item = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    int s, b;
+    item_coords(P, item, s, b);
+    const SurfDesc sd = P.surfs[s];
+    const int V = sd.V;
+    const int v_beg = chunk * kChunkA;
+    if (v_beg >= V) return;
+    const size_t e0 = ((size_t)b * P.S + s) * 2;
+    sT[tid >> 7][tid & 127] = P.tab_T[(e0 + (tid >> 7)) * kLevels + (tid & 127)];
+    if (tid < 2) {
+        const bool on = (tid == 0) || P.two_sided;
+        sNs[tid] = on ? P.tab_ns[e0 + tid] : 0;
+        const float d = P.tab_delta[e0 + tid];
+        sRd[tid] = d > 0.f ? __frcp_rn(d) : 0.f;
+    }
+    if (chunk == 0 && tid < 4) P.meta[(size_t)item * 4 + tid] = 0; // npeaks, npairs, flag (K_B runs after this kernel)
+    __syncthreads();
+    const float *__restrict__ x = P.stat + (size_t)b * P.ld + sd.col_off;
+    const int32_t *__restrict__ vmap = (P.flags & 4) ? nullptr : sd.vmap;
+    unsigned char *__restrict__ lev8 = P.lev8 + (size_t)item * P.vstride;
+    const int ns0 = sNs[0], ns1 = sNs[1];
+    float xq[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int v = v_beg + q * 256 + tid;
+        xq[q] = (v < V) ? x[vmap ? vmap[v] : v] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int v = v_beg + q * 256 + tid;
+        if (v >= V) break;
+        const float xv = xq[q];
+        int code = 0;
+        if (xv > 0.f || xv < 0.f) {
+            const int sg = xv < 0.f;
+            const int ns = sg ? ns1 : ns0;
+            if (ns > 1) {
+                // smallest i >= 1 with |x| > T[i]: guessed from the (almost) equal spacing, fixed against the exact table
+                const float ax = fabsf(xv);
+                const float *T = sT[sg];
+                int g = __float2int_rz((T[0] - ax) * sRd[sg]);
+                g = max(0, min(g, ns - 1)) + 1;
+                while (g > 1 && ax > T[g - 1]) --g;
+                while (g < ns && !(ax > T[g])) ++g;
+                if (g < ns) code = g | (sg << 7);
+            }
+        }
+        lev8[v] = (unsigned char)code;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- K_B
+__global__ void __launch_bounds__(256) pipe_ascent_kernel(PipeParams P, int chunks) {
+    const int item = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    int s, b;
+    item_coords(P, item, s, b);
+    const SurfDesc sd = P.surfs[s];
+    const int v = chunk * 256 + threadIdx.x;
+    if (v >= sd.V) return;
+    const size_t base = (size_t)item * P.vstride;
+    const unsigned char *__restrict__ lev8 = P.lev8 + base;
+    const int cv = lev8[v];
+    const int lev = cv & 0x7f;
+    if (lev == 0) {
+        P.up[base + v] = kInactive;
+        P.emask[base + v] = 0u;
+        return;
+    }
+    int best = v, bestlev = lev, bestbit = 0;
+    unsigned em = 0; // earlier-activated neighbours: lower level, or same level and smaller index
+    const int4 *__restrict__ row = reinterpret_cast<const int4 *>(sd.ell + (size_t)v * sd.ell_width);
+    const int nch = sd.ell_width >> 3;
+    for (int c = 0; c < nch; ++c) {
+        const int4 r0 = __ldg(row + 2 * c), r1 = __ldg(row + 2 * c + 1);
+        const int nb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        int ca[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ca[j] = nb[j] >= 0 ? (int)lev8[nb[j]] : 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (ca[j] == 0 || ((ca[j] ^ cv) & 0x80)) continue; // absent, inactive or other sign
+            const int la = ca[j] & 0x7f;
+            if (la < bestlev) { best = nb[j]; bestlev = la; bestbit = c * 8 + j; }
+            if (la < lev || (la == lev && nb[j] < v)) em |= 1u << (c * 8 + j);
+        }
+    }
+    if (best != v) {
+        em &= ~(1u << bestbit); // the ascent target lies in the same basin by construction
+        P.up[base + v] = best;
+    } else { // a peak: new basin
+        const int pid = atomicAdd(P.meta + (size_t)item * 4, 1);
+        if (pid < P.nbcap) P.blev[(size_t)item * P.nbcap + pid] = (unsigned char)cv;
+        P.up[base + v] = -1 - pid;
+    }
+    P.emask[base + v] = em;
+}
+
+// ------------------------------------------------------------------------------------------- K_C
+__global__ void __launch_bounds__(256) pipe_basin_kernel(PipeParams P, int chunks) {
+    const int item = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    int s, b;
+    item_coords(P, item, s, b);
+    const int V = P.surfs[s].V;
+    const int v = chunk * 256 + threadIdx.x;
+    if (v >= V) return;
+    const size_t base = (size_t)item * P.vstride;
+    const int *__restrict__ up = P.up + base;
+    int t = up[v];
+    int bas = -1;
+    if (t != kInactive) {
+        while (t >= 0) t = up[t];
+        bas = -1 - t;
+    }
+    P.basin[base + v] = bas;
+    // zero this map's count table (rows 1 .. nlev-1 of NB entries), a slice per thread
+    const size_t e0 = ((size_t)b * P.S + s) * 2;
+    const int NB = P.meta[(size_t)item * 4];
+    const int nlev = max(P.tab_ns[e0], P.two_sided ? P.tab_ns[e0 + 1] : 0);
+    const int64_t n = (int64_t)nlev * NB;
+    if (NB > P.nbcap || n > P.tabcap) {
+        if (v == 0) P.meta[(size_t)item * 4 + 2] = 1; // over capacity: redone by tfce_basin_kernel
+        return;
+    }
+    unsigned *__restrict__ tab = P.table + (size_t)item * P.tabcap;
+    for (int64_t i = v; i < n; i += V) tab[i] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------- K_D
+__global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunks) {
+    const int item = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    int s, b;
+    item_coords(P, item, s, b);
+    const SurfDesc sd = P.surfs[s];
+    const int v = chunk * 256 + threadIdx.x;
+    constexpr int kStage = 1024;
+    __shared__ unsigned long long sPairs[kStage];
+    __shared__ int sCnt, sBase;
+    int *meta = P.meta + (size_t)item * 4;
+    if (chunk * 256 >= sd.V || meta[2]) return; // CTA-uniform
+    if (threadIdx.x == 0) sCnt = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t base = (size_t)item * P.vstride;
+    const int *__restrict__ basin = P.basin + base;
+    const int NB = meta[0];
+    const int bu = (v < sd.V) ? basin[v] : -1;
+    unsigned em = 0;
+    int lev = 0;
+    if (bu >= 0) {
+        lev = P.lev8[base + v] & 0x7f;
+        em = P.emask[base + v];
+    }
+    {
+        // table[level][basin] += 1, one atomic per distinct (level, basin) of the warp: neighbouring vertices
+        // mostly share it, and same-address atomics of one warp serialise in the L2
+        const int key = bu >= 0 ? lev * NB + bu : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (!(P.flags & 256) && bu >= 0 && lane == (__ffs(peers) - 1))
+            atomicAdd(P.table + (size_t)item * P.tabcap + key, (unsigned)__popc(peers));
+    }
+    // candidate unions: earlier neighbours lying in another basin (each distinct basin once per vertex, best
+    // effort).  Staged in shared memory: one returning atomic per CTA reserves the output range.
+    if (em && !(P.flags & 512)) {
+        const int *__restrict__ row = sd.ell + (size_t)v * sd.ell_width;
+        int s0 = -1, s1 = -1, s2 = -1, s3 = -1;
+        unsigned m = em;
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const int ba = basin[row[j]];
+            if (ba == bu || ba == s0 || ba == s1 || ba == s2 || ba == s3) continue;
+            s3 = s2; s2 = s1; s1 = s0; s0 = ba;
+            const unsigned long long pr = ((unsigned long long)lev << 48) | ((unsigned long long)bu << 24) | (unsigned long long)ba;
+            const int pos = atomicAdd(&sCnt, 1);
+            if (pos < kStage) {
+                sPairs[pos] = pr;
+            } else { // staging buffer full (cannot happen on meshes; kept for correctness)
+                const int gp = atomicAdd(meta + 1, 1);
+                if (gp < P.paircap) P.pairs[(size_t)item * P.paircap + gp] = pr;
+            }
+        }
+    }
+    __syncthreads();
+    const int n = min(sCnt, kStage);
+    if (n == 0) return;
+    if (threadIdx.x == 0) sBase = atomicAdd(meta + 1, n);
+    __syncthreads();
+    const int gbase = sBase;
+    if (gbase + n <= P.paircap) { // else: K_S sees npairs > paircap and flags the map
+        unsigned long long *__restrict__ dst = P.pairs + (size_t)item * P.paircap + gbase;
+        for (int i = threadIdx.x; i < n; i += 256) dst[i] = sPairs[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------- K_S
+// Per-slot scratch in global memory.
+static constexpr int kSweepBasinCap = 12288; // (< 65536: the fold packs root ids in 16 bits) // basins whose state fits the sweep's shared memory (18 B each)
+
+struct SweepSlot {
+    unsigned long long *pairs2; // [paircap] candidate unions bucketed by level
+    int2 *cls;                  // [Vmax] class = {root at creation, creation level} -> {root, fp32 value bits}
+    float *incseq;              // [min(nbcap, kSweepBasinCap)][128] increment of root r's component at level l
+};
+
+static inline size_t pipe_al256(size_t x) { return (x + 255) / 256 * 256; }
+
+size_t pipe_slot_bytes(int32_t Vmax, int nbcap, int paircap) {
+    const size_t nb = (size_t)(nbcap < kSweepBasinCap ? nbcap : kSweepBasinCap);
+    return pipe_al256(sizeof(unsigned long long) * (size_t)paircap) + pipe_al256(sizeof(int2) * (size_t)Vmax) +
+           pipe_al256(sizeof(float) * kLevels * nb);
+}
+
+__device__ __forceinline__ SweepSlot carve_slot(char *base, int32_t Vmax, int nbcap, int paircap) {
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    SweepSlot w;
+    w.pairs2 = reinterpret_cast<unsigned long long *>(base);
+    base += al(sizeof(unsigned long long) * (size_t)paircap);
+    w.cls = reinterpret_cast<int2 *>(base);
+    base += al(sizeof(int2) * (size_t)Vmax);
+    w.incseq = reinterpret_cast<float *>(base);
+    return w;
+}
+
+// bytes of dynamic shared memory the sweep needs for NB basins
+__host__ __device__ inline size_t pipe_sweep_smem(int NB, bool max_only) {
+    const size_t nba = ((size_t)NB + 3) / 4 * 4;
+    const size_t bits = (((size_t)NB + 31) / 32 * 4 + 15) / 16 * 16;
+    if (max_only) return nba * (4 + 4 + 4 + 1 + 1) + 16;    // parent, size, leader accumulator, hook level, peak level
+    return nba * (4 + 4 + 4 + 4 + 1 + 1 + 8) + bits + 16;  // + class of the level, hook parent, two fp32 row buffers
+}
+
+// The sweep over the basins of one map.  Per level l (three barrier intervals, shared memory only on the
+// critical path; the table row and the candidate unions of level l+1 are fetched into registers during F3):
+//   F1  unions of the level's candidate pairs (lock-free union-find; roots ordered by (level, id); the hook of
+//       a root is logged: hookpar/hooklev keep the uncompressed merge history)
+//   F2  sizes: table row l (vertices per basin at this level) added to the components' roots, sizes of older
+//       roots hooked in this level carried over; one class {root, level} per component that gained vertices
+//   F3  every live root logs this level's increment fl32(pow(size, E) * pow(T, H)) in incseq[root][l]
+// After the sweep a class is folded on its own: its vertices receive, one fp32 add per level in
+// descending-threshold order (fast_tfce.hpp:70-84), the logged increments of the root their component
+// had at each level -- which follows from the merge history alone.
+//
+// kMaxOnly (no vertex weights, no maps requested): only the per-map maximum leaves the kernel, and that needs
+// ONE accumulator per live root instead of one per class.  All increments are >= 0 and fp32 round-to-nearest
+// addition is monotone, so among the classes of a component the one with the largest sum so far keeps the
+// largest sum for ever (they all add the same increments from here on): the "leader".  A root's leader is its
+// own first class (born with the root, at its peak); when roots merge the leader of the union is the larger of
+// the two.  max_v TFCE(v) is therefore max over the final roots of the leader sums -- bit-identical to the
+// maximum of the full map, with no per-class state at all.
+template <int kThreads, int kMinBlocks, bool kMaxOnly>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_kernel(PipeParams P, int smem_bytes) {
+    extern __shared__ __align__(16) unsigned char sDyn[];
+    __shared__ double sHHd[2][kLevels];
+    __shared__ int sPstart[kLevels + 1];
+    __shared__ int sCursor[kLevels];
+    __shared__ int sNs[2];
+    __shared__ float sDelta[2];
+    __shared__ int sItem;
+    __shared__ int sC;
+    __shared__ float sRed[2][kThreads / 32];
+
+    const int tid = threadIdx.x;
+    constexpr int nthr = kThreads;
+    const int lane = tid & 31, wid = tid >> 5;
+    const SweepSlot ws = carve_slot(P.slot_ws + (size_t)blockIdx.x * P.slot_stride, P.Vmax, P.nbcap, P.paircap);
+    const int total_items = P.B * P.S;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sItem = atomicAdd(P.work_counter, 1);
+        __syncthreads();
+        const int item = sItem;
+        if (item >= total_items) break;
+        int s, b;
+        item_coords(P, item, s, b);
+        const SurfDesc sd = P.surfs[s];
+        int *meta = P.meta + (size_t)item * 4;
+        const int NB = meta[0], NP = meta[1];
+        const size_t e0 = ((size_t)b * P.S + s) * 2;
+        long long tk = P.timing ? clock64() : 0;
+#define PIPE_TICK(i)                                                                 \
+        if (P.timing && tid == 0) {                                                  \
+            const long long now = clock64();                                         \
+            atomicAdd(P.timing + (i), (unsigned long long)(now - tk));               \
+            tk = now;                                                                \
+        }
+        if (meta[2] || NB > P.nbcap || NB > kSweepBasinCap || NP > P.paircap ||
+            pipe_sweep_smem(NB, kMaxOnly) > (size_t)smem_bytes) {
+            if (tid == 0) {
+                meta[2] = 1; // redone by tfce_basin_kernel
+                if (P.timing) atomicAdd(P.timing + 10, 1ull);
+            }
+            continue;
+        }
+        if (P.timing && tid == 0) {
+            atomicAdd(P.timing + 11, (unsigned long long)NB);
+            atomicAdd(P.timing + 12, (unsigned long long)NP);
+            atomicAdd(P.timing + 13, 1ull);
+        }
+        // ---- shared-memory layout of the per-basin state
+        const int nba = (NB + 3) / 4 * 4;
+        const int bits_words = (((NB + 31) / 32 * 4 + 15) / 16 * 16) / 4;
+        int *bparent = reinterpret_cast<int *>(sDyn);
+        int *bsize = bparent + nba;
+        int *bcur = bsize + nba;       // root -> class created for it in this level; kMaxOnly: leader sum (fp32 bits)
+        int *hookpar = kMaxOnly ? bcur : bcur + nba; // merge history: the root this one was hooked under ... (not kMaxOnly)
+        unsigned *bitsC = reinterpret_cast<unsigned *>(hookpar + nba);  // root got a class in this level (not kMaxOnly)
+        unsigned char *hooklev = reinterpret_cast<unsigned char *>(kMaxOnly ? (unsigned *)(bcur + nba) : bitsC + bits_words); // ... and the level (255: never)
+        unsigned char *blev = hooklev + nba;
+        float *rowbuf = reinterpret_cast<float *>(blev + nba); // [2][nba] increments of one level (the fold; not kMaxOnly)
+        int *racc = bcur;
+        for (int i = tid; i < 2 * kLevels; i += nthr)
+            sHHd[i / kLevels][i % kLevels] = (double)P.tab_HH[(e0 + i / kLevels) * kLevels + i % kLevels];
+        if (tid < 2) {
+            const bool on = (tid == 0) || P.two_sided;
+            sNs[tid] = on ? P.tab_ns[e0 + tid] : 0;
+            sDelta[tid] = P.tab_delta[e0 + tid];
+            if (P.status) P.status[e0 + tid] = on ? P.tab_status[e0 + tid] : 0;
+        }
+        if (tid == 0) sC = 0;
+        for (int i = tid; i < kLevels; i += nthr) sCursor[i] = 0;
+        const unsigned char *__restrict__ gblev = P.blev + (size_t)item * P.nbcap;
+        for (int i = tid; i < NB; i += nthr) {
+            bparent[i] = i;
+            bsize[i] = 0;
+            if (kMaxOnly) {
+                racc[i] = 0; // +0.0f
+            } else {
+                bcur[i] = -1;
+                hookpar[i] = i;
+            }
+            hooklev[i] = 255;
+            blev[i] = gblev[i];
+        }
+        if (!kMaxOnly)
+            for (int i = tid; i < bits_words; i += nthr) bitsC[i] = 0u;
+        __syncthreads();
+        const int ns0 = sNs[0], ns1 = sNs[1];
+        const int nlev = max(ns0, ns1);
+        // ---- candidate unions bucketed by level (counting sort; order inside a level is irrelevant)
+        const unsigned long long *__restrict__ pairs = P.pairs + (size_t)item * P.paircap;
+        for (int i = tid; i < NP; i += nthr) atomicAdd(&sCursor[(int)(pairs[i] >> 48)], 1);
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int l = 0; l < kLevels; ++l) { const int c = sCursor[l]; sPstart[l] = run; sCursor[l] = run; run += c; }
+            sPstart[kLevels] = run;
+        }
+        __syncthreads();
+        for (int i = tid; i < NP; i += nthr) {
+            const unsigned long long p = pairs[i];
+            ws.pairs2[atomicAdd(&sCursor[(int)(p >> 48)], 1)] = p;
+        }
+        __syncthreads();
+        PIPE_TICK(0)
+
+        unsigned *__restrict__ tab = P.table + (size_t)item * P.tabcap;
+        const double *__restrict__ powE = sd.powE;
+        // register prefetch of the next level's inputs: up to 8 table entries and 1 candidate union per thread
+        unsigned cq[8];
+        unsigned long long pq = 0ull;
+        auto prefetch_level = [&](int l) {
+            const unsigned *__restrict__ row = tab + (size_t)l * NB;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cq[q] = (tid + q * nthr < NB) ? row[tid + q * nthr] : 0u;
+            const int i = sPstart[l] + tid;
+            pq = (i < sPstart[l + 1]) ? ws.pairs2[i] : 0ull;
+        };
+        if (nlev > 1) prefetch_level(1);
+        int nclass = 0;
+        for (int lev = 1; lev < nlev; ++lev) {
+            // ================= F1: unions of this level =================================================
+            for (int i = sPstart[lev] + tid; i < sPstart[lev + 1]; i += nthr) {
+                const unsigned long long p = (i == sPstart[lev] + tid && !(P.flags & 1024)) ? pq : ws.pairs2[i];
+                int ru = pf_find(bparent, (int)((p >> 24) & 0xFFFFFFu));
+                int ra = pf_find(bparent, (int)(p & 0xFFFFFFu));
+                while (ru != ra) {
+                    // total order on roots: (activation level, id); the later root goes under the earlier one
+                    const int kru = ((blev[ru] & 0x7f) << 24) | ru, kra = ((blev[ra] & 0x7f) << 24) | ra;
+                    const int hi = kru > kra ? ru : ra, lo = kru > kra ? ra : ru;
+                    const int old = atomicCAS(bparent + hi, hi, lo);
+                    if (old == hi) { // this thread hooked hi: log it
+                        if (!kMaxOnly) hookpar[hi] = lo;
+                        hooklev[hi] = (unsigned char)lev;
+                        break;
+                    }
+                    const int nh = pf_find(bparent, old);
+                    if (hi == ru) { ru = nh; ra = pf_find(bparent, ra); }
+                    else          { ra = nh; ru = pf_find(bparent, ru); }
+                }
+            }
+            __syncthreads();
+            PIPE_TICK(3)
+            // ================= F2: sizes; one new class per component that gains vertices ================
+            unsigned *__restrict__ row = tab + (size_t)lev * NB;
+            for (int bb0 = tid; bb0 < NB; bb0 += 8 * nthr) {
+                if (bb0 != tid || (P.flags & 1024)) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) cq[q] = (bb0 + q * nthr < NB) ? row[bb0 + q * nthr] : 0u;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int bb = bb0 + q * nthr;
+                    if (bb >= NB) break;
+                    const unsigned c = cq[q];
+                    if (c != 0u) {
+                        const int r = pf_find(bparent, bb);
+                        atomicAdd(bsize + r, (int)c);
+                        if (!kMaxOnly) {
+                            const unsigned bit = 1u << (r & 31);
+                            if (!(atomicOr(bitsC + (r >> 5), bit) & bit)) {
+                                const int j = atomicAdd(&sC, 1);
+                                ws.cls[j] = make_int2(r, lev);
+                                bcur[r] = j;
+                            }
+                        }
+                    }
+                    // an older root hooked in this level hands its size (and its leader) over; a root of this very
+                    // level has neither yet
+                    if (hooklev[bb] == lev && (blev[bb] & 0x7f) != lev) {
+                        const int r = pf_find(bparent, bb);
+                        atomicAdd(bsize + r, bsize[bb]);
+                        if (kMaxOnly) atomicMax(racc + r, racc[bb]); // sums are >= 0: integer order == float order
+                    }
+                }
+            }
+            __syncthreads();
+            PIPE_TICK(4)
+            // ================= F3: the level's increment of every live root ==============================
+            if (lev + 1 < nlev && !(P.flags & 1024)) prefetch_level(lev + 1);
+            if (lev + 3 < nlev && !(P.flags & 2048)) { // rows come from HBM (written by K_D long ago): pull the row of level l+3 into the L2
+                const unsigned *__restrict__ far = tab + (size_t)(lev + 3) * NB;
+                for (int i = tid * 32; i < NB; i += nthr * 32) pf_prefetch_l2(far + i);
+            }
+            for (int bb0 = tid; bb0 < NB; bb0 += 8 * nthr) { // gather sizes, then 8 independent pow-table loads
+                int szq[8];
+                double pwq[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int bb = bb0 + q * nthr;
+                    szq[q] = -1;
+                    if (bb < NB) {
+                        const int cb = blev[bb];
+                        if (bparent[bb] == bb && (cb & 0x7f) <= lev && lev < ((cb >> 7) ? ns1 : ns0)) szq[q] = bsize[bb];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) pwq[q] = szq[q] >= 0 ? powE[szq[q]] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int bb = bb0 + q * nthr;
+                    if (szq[q] >= 0) {
+                        const float inc = __double2float_rn(__dmul_rn(pwq[q], sHHd[blev[bb] >> 7][lev]));
+                        if (kMaxOnly) racc[bb] = __float_as_int(__fadd_rn(__int_as_float(racc[bb]), inc));
+                        else ws.incseq[(size_t)lev * nba + bb] = inc;
+                    }
+                }
+            }
+            if (!kMaxOnly) {
+                if (P.want_vertex_pass)
+                    for (int bb = tid; bb < NB; bb += nthr)
+                        if (row[bb] != 0u) row[bb] = 0x80000000u | (unsigned)bcur[pf_find(bparent, bb)];
+                for (int i = tid; i < bits_words; i += nthr) bitsC[i] = 0u;
+            }
+            __syncthreads();
+            PIPE_TICK(5)
+        }
+        nclass = kMaxOnly ? 0 : sC;
+        // ---- fold: the value of a class = the increments of its component in level order, following the merge
+        // history.  Level-synchronous with the accumulators in REGISTERS: kFold classes per thread and pass; per
+        // level the increments of all roots (one coalesced row) are staged in shared memory, so a (class, level)
+        // step is two shared-memory loads and one fp32 add.  Class ids ascend with the creation level: the classes
+        // of one pass start at about the same level and earlier levels are skipped.
+        const float d0 = sDelta[0], d1 = sDelta[1];
+        float m0 = 0.f, m1 = 0.f;
+        constexpr int kFold = 16;
+        if (kMaxOnly) {
+            for (int bb = tid; bb < NB; bb += nthr)
+                if (bparent[bb] == bb) { // final roots carry the leaders
+                    const int sg = blev[bb] >> 7;
+                    const float sc = __fmul_rn(__int_as_float(racc[bb]), sg ? d1 : d0);
+                    if (sg) m1 = fmaxf(m1, sc); else m0 = fmaxf(m0, sc);
+                }
+        }
+        for (int cbase = 0; !kMaxOnly && cbase < nclass; cbase += kFold * nthr) {
+            int pk[kFold];    // root (16 bits) | creation level << 16 (7 bits) | last level << 23 (7 bits); -1 = no class
+            float ac[kFold];
+#pragma unroll
+            for (int k = 0; k < kFold; ++k) {
+                const int j = cbase + k * nthr + tid;
+                pk[k] = -1;
+                ac[k] = 0.f;
+                if (j < nclass) {
+                    const int2 rec = ws.cls[j];
+                    const int sg = blev[rec.x] >> 7;
+                    pk[k] = rec.x | (rec.y << 16) | (((sg ? ns1 : ns0) - 1) << 23);
+                }
+            }
+            const int lmin = ws.cls[cbase].y; // creation level of the pass's first (= earliest) class
+            __syncthreads();
+            for (int i = tid; i < NB; i += nthr) rowbuf[(lmin & 1) * nba + i] = ws.incseq[(size_t)lmin * nba + i];
+            __syncthreads();
+            for (int l = lmin; l < nlev; ++l) {
+                float nxt[8];
+                const bool more = l + 1 < nlev;
+                if (more) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) nxt[q] = (tid + q * nthr < NB) ? ws.incseq[(size_t)(l + 1) * nba + tid + q * nthr] : 0.f;
+                }
+                const float *__restrict__ cur = rowbuf + (l & 1) * nba;
+#pragma unroll
+                for (int k = 0; k < kFold; ++k) {
+                    const int w = pk[k];
+                    if (w >= 0 && l >= ((w >> 16) & 0x7f) && l <= ((w >> 23) & 0x7f)) {
+                        int r = w & 0xffff;
+                        while (hooklev[r] <= l) r = hookpar[r];
+                        pk[k] = (w & ~0xffff) | r;
+                        ac[k] = __fadd_rn(ac[k], cur[r]);
+                    }
+                }
+                if (more) {
+                    float *__restrict__ dstb = rowbuf + ((l + 1) & 1) * nba;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (tid + q * nthr < NB) dstb[tid + q * nthr] = nxt[q];
+                    for (int i = tid + 8 * nthr; i < NB; i += nthr) dstb[i] = ws.incseq[(size_t)(l + 1) * nba + i];
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int k = 0; k < kFold; ++k) {
+                const int j = cbase + k * nthr + tid;
+                if (pk[k] >= 0) {
+                    if (P.want_vertex_pass) ws.cls[j].y = __float_as_int(ac[k]);
+                    const int sg = blev[pk[k] & 0xffff] >> 7;
+                    const float sc = __fmul_rn(ac[k], sg ? d1 : d0);
+                    if (sg) m1 = fmaxf(m1, sc); else m0 = fmaxf(m0, sc);
+                }
+            }
+        }
+        PIPE_TICK(6)
+        // ---- outputs
+        if (!kMaxOnly && P.want_vertex_pass) {
+            // class ids -> values in the table; the scaled maxima are taken per vertex by K_G (vertex weights)
+            __syncthreads();
+            const int64_t n = (int64_t)nlev * NB;
+            for (int64_t i = NB + tid; i < n; i += nthr) {
+                const unsigned e = tab[i];
+                if (e & 0x80000000u) tab[i] = (unsigned)ws.cls[e & 0x7fffffffu].y;
+            }
+            if (tid < 2 && P.max_out) P.max_out[e0 + tid] = 0.f;
+        } else {
+            m0 = pwarp_max(m0);
+            m1 = pwarp_max(m1);
+            if (lane == 0) { sRed[0][wid] = m0; sRed[1][wid] = m1; }
+            __syncthreads();
+            if (tid == 0 && P.max_out) {
+                float a = 0.f, c = 0.f;
+                for (int w = 0; w < nthr / 32; ++w) { a = fmaxf(a, sRed[0][w]); c = fmaxf(c, sRed[1][w]); }
+                P.max_out[e0] = a;
+                P.max_out[e0 + 1] = c;
+            }
+        }
+        PIPE_TICK(2)
+        if (P.timing && tid == 0) atomicAdd(P.timing + 7, (unsigned long long)nclass);
+#undef PIPE_TICK
+    }
+}
+
+// ------------------------------------------------------------------------------------------- K_G
+__global__ void __launch_bounds__(256) pipe_output_kernel(PipeParams P, int chunks) {
+    const int item = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    int s, b;
+    item_coords(P, item, s, b);
+    const SurfDesc sd = P.surfs[s];
+    const int *meta = P.meta + (size_t)item * 4;
+    if (chunk * 256 >= sd.V || meta[2]) return; // CTA-uniform
+    const int v = chunk * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const size_t base = (size_t)item * P.vstride;
+    const size_t e0 = ((size_t)b * P.S + s) * 2;
+    float sc0 = 0.f, sc1 = 0.f;
+    if (v < sd.V) {
+        const int bu = P.basin[base + v];
+        float val = 0.f;
+        int neg = 0;
+        if (bu >= 0) {
+            const int cv = P.lev8[base + v];
+            neg = cv >> 7;
+            val = __uint_as_float(P.table[(size_t)item * P.tabcap + (size_t)(cv & 0x7f) * meta[0] + bu]);
+            float sc = __fmul_rn(val, P.tab_delta[e0 + neg]);
+            if (sd.weight) sc = __fmul_rn(sc, sd.weight[v]);
+            if (neg) sc1 = sc; else sc0 = sc;
+        }
+        const int32_t *__restrict__ vmap = (P.flags & 4) ? nullptr : sd.vmap;
+        const size_t o = (size_t)b * P.ld + sd.col_off + (vmap ? vmap[v] : v);
+        if (P.tfce_pos) P.tfce_pos[o] = neg ? 0.f : val;
+        if (P.tfce_neg) P.tfce_neg[o] = neg ? val : 0.f;
+    }
+    sc0 = pwarp_max(sc0);
+    sc1 = pwarp_max(sc1);
+    if (lane == 0 && P.max_out) { // values are >= 0: integer order == float order
+        if (sc0 > 0.f) atomicMax(reinterpret_cast<int *>(P.max_out + e0), __float_as_int(sc0));
+        if (sc1 > 0.f) atomicMax(reinterpret_cast<int *>(P.max_out + e0 + 1), __float_as_int(sc1));
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host
+int pipe_sweep_max_smem() {
+    int v = 220 * 1024;
+    if (const char *g = getenv("TMB_PIPE_SMEM_KB")) { const int kb = atoi(g); if (kb >= 16 && kb <= 224) v = kb * 1024; }
+    return v;
+}
+
+int launch_tfce_tables(const SurfDesc *surfs, int S, int count, const float *maxima, int two_sided, int32_t *ns,
+                       float *delta, float *T, float *HH, int32_t *st, cudaStream_t stream) {
+    if (count <= 0) return 0;
+    pipe_tables_kernel<<<(count + 63) / 64, 64, 0, stream>>>(surfs, S, count, maxima, two_sided, ns, delta, T, HH, st);
+    count_launch();
+    TMB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t stream) {
+    PipeParams p = p_in;
+    if (const char *d = getenv("TMB_PIPE_DEBUG")) p.flags |= atoi(d) & ~7; // timing experiments only (results invalid)
+    const int items = p.B * p.S;
+    if (items <= 0) return 0;
+    const int chunksA = (p.Vmax + kChunkA - 1) / kChunkA;
+    const int chunks = (p.Vmax + 255) / 256;
+    TMB_REQUIRE((int64_t)items * chunks < (int64_t)INT32_MAX, "tfce pipeline: too many work items (%d maps x %d chunks)",
+                items, chunks);
+    pipe_levels_kernel<<<items * chunksA, 256, 0, stream>>>(p, chunksA);
+    pipe_ascent_kernel<<<items * chunks, 256, 0, stream>>>(p, chunks);
+    pipe_basin_kernel<<<items * chunks, 256, 0, stream>>>(p, chunks);
+    pipe_count_kernel<<<items * chunks, 256, 0, stream>>>(p, chunks);
+    TMB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
+    // sweep geometry: max-only maps keep 14 bytes per basin in shared memory -> two 512-thread CTAs per SM hide each
+    // other's barrier intervals; the class path (26 bytes per basin) runs one 1024-thread CTA per SM
+    if (p.want_vertex_pass) {
+        const int smem = pipe_sweep_max_smem();
+        TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_kernel<1024, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int grid = items < num_slots / 2 ? items : num_slots / 2;
+        pipe_sweep_kernel<1024, 1, false><<<grid, 1024, smem, stream>>>(p, smem);
+    } else {
+        int geom = 2;
+        if (const char *g = getenv("TMB_PIPE_GEOM")) geom = atoi(g);
+        if (geom == 1) {
+            const int smem = pipe_sweep_max_smem();
+            TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_kernel<1024, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const int grid = items < num_slots / 2 ? items : num_slots / 2;
+            pipe_sweep_kernel<1024, 1, true><<<grid, 1024, smem, stream>>>(p, smem);
+        } else {
+            const int smem = pipe_sweep_max_smem() / 2 - 4096;
+            TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_kernel<512, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const int grid = items < num_slots ? items : num_slots;
+            pipe_sweep_kernel<512, 2, true><<<grid, 512, smem, stream>>>(p, smem);
+        }
+    }
+    count_launch(5);
+    if (p.want_vertex_pass) {
+        pipe_output_kernel<<<items * chunks, 256, 0, stream>>>(p, chunks);
+        count_launch();
+    }
+    TMB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+} // namespace tmb
