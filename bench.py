@@ -12,7 +12,7 @@ vertices), 300 subjects, k=2, H=2, E=0.67, synthetic data
 
 Prints ONE JSON line (see the task contract): value = whole-job shuffles/s with inputs resident in
 HBM, device-timed, max over ranks; `e2e` = the same through PermutationEngine.regression_block with
-host index rows in / host maxima out; `roofline` for the dominant kernel (tfce_basin_kernel);
+host index rows in / host maxima out; `roofline` for the dominant stage (the TFCE pipeline);
 `cpu_baseline` = the reference's own compiled kernels (oracle/_ref) on one host core.
 `--impl reference` times the reference's CPU implementation with all host cores.
 """
@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "permutations/sec (regression+TFCE+max)"
+TFCE_STAGE = "tfce pipeline (pipe_levels + pipe_ascent + pipe_basin + pipe_count + pipe_sweep_max kernels)"
 UNIT = "permutations/s"
 
 
@@ -279,11 +280,20 @@ def run_b200(args):
 
     t32b = [t32, torch.empty_like(t32)]
 
+    fit_events = []
+
     def fit(s, buf):
         At_d, ldA, G_d, d_d, dof = stacks[s]
+        if fit_events is not None and len(fit_events) < 64:
+            fa = torch.cuda.Event(enable_timing=True); fb = torch.cuda.Event(enable_timing=True)
+            fa.record()
+        else:
+            fa = None
         _lib.check(L.tmb_glm_tstat(_lib.ptr(eng.Y.t), eng.Y.dtype_code, eng.Y.n, eng.Y.V, eng.Y.ld, _lib.ptr(At_d), ldA,
                                    _lib.ptr(G_d), _lib.ptr(d_d), P, 1, 1, 0, 1, dof, _lib.ptr(yy), _lib.ptr(buf), None,
                                    eng.Y.ld, 0, _lib.current_stream()))
+        if fa is not None:
+            fb.record(); fit_events.append((fa, fb))
         return eng.plan.prepare(buf.view(P * C, eng.Y.ld))          # maxima kernel + async copy to the host
 
     def run_steps(first, count, tfce_events=None):
@@ -306,6 +316,7 @@ def run_b200(args):
 
     run_steps(0, args.warmup)
     barrier()
+    fit_events.clear()
     t_load0 = time.time()
     launches0 = _lib.launch_count()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
@@ -317,6 +328,7 @@ def run_b200(args):
     dev_ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
     tfce_ms = float(np.mean([a.elapsed_time(b) for a, b in tfce_events]))
+    fit_ms = float(np.mean([a.elapsed_time(b) for a, b in fit_events])) if fit_events else None
 
     # ---- end-to-end arm: the public call, host index rows in (pinned staging), host maxima out ----
     idx_warm = np.concatenate(idx_all[:min(args.warmup, 2)], axis=0)
@@ -353,7 +365,7 @@ def run_b200(args):
         tpath = os.path.join(ROOT, "profiles", "tfce_sweep_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("workload") == w["name"] and tj.get("block") == P:
+            if tj.get("workload") == w["name"] and tj.get("block") == P and tj.get("kernel") == TFCE_STAGE:
                 traffic = tj.get("dram_bytes_per_launch")
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -388,10 +400,17 @@ def run_b200(args):
                     "d2h_bytes_per_step": eng.d2h_bytes // args.steps, "ms_per_step": e2e_ms / args.steps,
                     "data_upload_once_bytes": int(w["y"].nbytes), "data_upload_once_ms": data_upload_ms},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "tfce_basin_kernel", "achieved": achieved, "peak": peak,
+            # the dominant stage is TFCE + max: since round 1 v7 a pipeline of five kernels launched back to back
+            # (levels, ascent, basins, counts, basin sweep), timed as one unit with CUDA events on their stream
+            "roofline": {"bound": "hbm", "kernel": TFCE_STAGE, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_tfce * P, "kernel_ms_per_launch": tfce_ms,
-                         "kernel_share_of_step": tfce_ms / (dev_ms / args.steps)},
+                         "kernel_share_of_step": tfce_ms / (dev_ms / args.steps),
+                         "fit": None if fit_ms is None else {
+                             "kernel": "glm_dmma_kernel", "bound": "tensor (fp64 DMMA)", "ms_per_launch": fit_ms,
+                             "achieved": 2.0 * P * w["n"] * eng.Y.V / (fit_ms / 1e3) / 1e12, "unit": "TFLOP/s",
+                             "peak": 40.0, "peak_source": "nominal B200 fp64 (no fp64 entry in MEASURED_PEAKS.json)",
+                             "share_of_step": fit_ms / (dev_ms / args.steps)}},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -51,6 +51,20 @@ __device__ __forceinline__ int pf_find(int *parent, int v) {
 
 __device__ __forceinline__ void pf_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// asynchronous 8-byte copy global -> shared (LDGSTS): no register, no scoreboard stall until cp_async_wait_all
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// predicated 8-byte global load: issued without a dependent select, so the thread does not stall until first use
+__device__ __forceinline__ unsigned long long ld_u64_if(const unsigned long long *p, bool pred) {
+    unsigned long long v = 0ull;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u64 %0, [%1];\n\t}" : "+l"(v) : "l"(p), "r"((int)pred) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ float pwarp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -60,6 +74,14 @@ __device__ __forceinline__ float pwarp_max(float v) {
 __device__ __forceinline__ void item_coords(const PipeParams &P, int item, int &s, int &b) {
     s = P.surf_order[item / P.B];
     b = item % P.B;
+}
+
+// streaming kernels run on a 3-D grid (chunk, statistic row, surface slot): no integer divisions per thread
+__device__ __forceinline__ void grid_coords(const PipeParams &P, int &item, int &chunk, int &s, int &b) {
+    chunk = blockIdx.x;
+    b = blockIdx.y;
+    s = P.surf_order[blockIdx.z];
+    item = blockIdx.z * P.B + b;
 }
 
 } // namespace
@@ -106,9 +128,8 @@ __global__ void __launch_bounds__(256) pipe_levels_kernel(PipeParams P, int chun
     __shared__ int sNs[2];
     __shared__ float sRd[2];
     const int tid = threadIdx.x;
-    const int item = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-    int s, b;
-    item_coords(P, item, s, b);
+    int item, chunk, s, b;
+    grid_coords(P, item, chunk, s, b);
     const SurfDesc sd = P.surfs[s];
     const int V = sd.V;
     const int v_beg = chunk * kChunkA;
@@ -158,56 +179,80 @@ __global__ void __launch_bounds__(256) pipe_levels_kernel(PipeParams P, int chun
 }
 
 // ------------------------------------------------------------------------------------------- K_B
-__global__ void __launch_bounds__(256) pipe_ascent_kernel(PipeParams P, int chunks) {
-    const int item = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-    int s, b;
-    item_coords(P, item, s, b);
-    const SurfDesc sd = P.surfs[s];
-    const int v = chunk * 256 + threadIdx.x;
-    if (v >= sd.V) return;
-    const size_t base = (size_t)item * P.vstride;
+// ascent target and earlier-neighbour mask of vertex v; returns the vertex's level code when it is a peak, else -1
+__device__ __forceinline__ int ascent_of_vertex(const PipeParams &P, const SurfDesc &sd, size_t base, int v) {
+    if (v >= sd.V) return -1;
     const unsigned char *__restrict__ lev8 = P.lev8 + base;
     const int cv = lev8[v];
     const int lev = cv & 0x7f;
     if (lev == 0) {
         P.up[base + v] = kInactive;
         P.emask[base + v] = 0u;
-        return;
+        return -1;
     }
-    int best = v, bestlev = lev, bestbit = 0;
-    unsigned em = 0; // earlier-activated neighbours: lower level, or same level and smaller index
+    // per neighbour: la = its level when it is active with v's sign, else 255.  The ascent target is the first
+    // neighbour of the smallest level below v's own (packed key: level << 8 | slot); "earlier" = (level, index)
+    // below (lev, v), one packed unsigned compare.
+    unsigned bestkey = ((unsigned)lev << 8) | 0xffu; // no strictly earlier level found yet
+    unsigned em = 0;
+    const unsigned sign = (unsigned)cv & 0x80u;
+    const unsigned mykey = ((unsigned)lev << 24) | (unsigned)v;
     const int4 *__restrict__ row = reinterpret_cast<const int4 *>(sd.ell + (size_t)v * sd.ell_width);
     const int nch = sd.ell_width >> 3;
     for (int c = 0; c < nch; ++c) {
         const int4 r0 = __ldg(row + 2 * c), r1 = __ldg(row + 2 * c + 1);
         const int nb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-        int ca[8];
+        unsigned ca[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ca[j] = nb[j] >= 0 ? (int)lev8[nb[j]] : 0;
+        for (int j = 0; j < 8; ++j) ca[j] = nb[j] >= 0 ? (unsigned)lev8[nb[j]] : 0u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (ca[j] == 0 || ((ca[j] ^ cv) & 0x80)) continue; // absent, inactive or other sign
-            const int la = ca[j] & 0x7f;
-            if (la < bestlev) { best = nb[j]; bestlev = la; bestbit = c * 8 + j; }
-            if (la < lev || (la == lev && nb[j] < v)) em |= 1u << (c * 8 + j);
+            const unsigned x = ca[j] ^ sign;                 // 1..127: active, same sign
+            const unsigned la = (x - 1u) < 127u ? x : 255u;
+            bestkey = min(bestkey, (la << 8) | (unsigned)(c * 8 + j));
+            if (((la << 24) | (unsigned)nb[j]) < mykey) em |= 1u << (c * 8 + j); // nb < 2^24; la = 255 never passes
         }
     }
-    if (best != v) {
+    const int bestbit = (int)(bestkey & 0xffu);
+    const bool has_up = (int)(bestkey >> 8) < lev;
+    int best = v;
+    if (has_up) {
+        best = sd.ell[(size_t)v * sd.ell_width + bestbit];
         em &= ~(1u << bestbit); // the ascent target lies in the same basin by construction
         P.up[base + v] = best;
-    } else { // a peak: new basin
-        const int pid = atomicAdd(P.meta + (size_t)item * 4, 1);
-        if (pid < P.nbcap) P.blev[(size_t)item * P.nbcap + pid] = (unsigned char)cv;
-        P.up[base + v] = -1 - pid;
     }
     P.emask[base + v] = em;
+    return best == v ? cv : -1;
+}
+
+__global__ void __launch_bounds__(256) pipe_ascent_kernel(PipeParams P, int chunks) {
+    __shared__ int sPeaks, sBase;
+    int item, chunk, s, b;
+    grid_coords(P, item, chunk, s, b);
+    const SurfDesc sd = P.surfs[s];
+    if (chunk * 256 >= sd.V) return; // CTA-uniform
+    if (threadIdx.x == 0) sPeaks = 0;
+    __syncthreads();
+    const int v = chunk * 256 + threadIdx.x;
+    const size_t base = (size_t)item * P.vstride;
+    const int peak_code = ascent_of_vertex(P, sd, base, v);
+    // peaks get compact basin ids: one returning atomic per CTA on the map's counter
+    int local = -1;
+    if (peak_code >= 0) local = atomicAdd(&sPeaks, 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && sPeaks > 0) sBase = atomicAdd(P.meta + (size_t)item * 4, sPeaks);
+    __syncthreads();
+    if (local >= 0) {
+        const int pid = sBase + local;
+        if (pid < P.nbcap) P.blev[(size_t)item * P.nbcap + pid] = (unsigned char)peak_code;
+        P.up[base + v] = -1 - pid;
+    }
 }
 
 // ------------------------------------------------------------------------------------------- K_C
 __global__ void __launch_bounds__(256) pipe_basin_kernel(PipeParams P, int chunks) {
-    const int item = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-    int s, b;
-    item_coords(P, item, s, b);
+    int item, chunk, s, b;
+    grid_coords(P, item, chunk, s, b);
     const int V = P.surfs[s].V;
     const int v = chunk * 256 + threadIdx.x;
     if (v >= V) return;
@@ -225,19 +270,23 @@ __global__ void __launch_bounds__(256) pipe_basin_kernel(PipeParams P, int chunk
     const int NB = P.meta[(size_t)item * 4];
     const int nlev = max(P.tab_ns[e0], P.two_sided ? P.tab_ns[e0 + 1] : 0);
     const int64_t n = (int64_t)nlev * NB;
-    if (NB > P.nbcap || n > P.tabcap) {
+    if (NB > P.nbcap || (P.want_vertex_pass && n > P.tabcap)) {
         if (v == 0) P.meta[(size_t)item * 4 + 2] = 1; // over capacity: redone by tfce_basin_kernel
         return;
     }
+    if (!P.want_vertex_pass) return; // max-only maps use compact entry lists, no dense table
     unsigned *__restrict__ tab = P.table + (size_t)item * P.tabcap;
     for (int64_t i = v; i < n; i += V) tab[i] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------- K_D
+// kDense (class path): table[level][basin] += 1 in global memory.  Otherwise (max-only maps) the (level, basin)
+// counts of the CTA's 256 vertices are aggregated in a shared-memory hash and appended to the map's entry list
+// {level, basin, vertices}; the same key may come from several CTAs -- the sweep simply adds them up.
+template <bool kDense>
 __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunks) {
-    const int item = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-    int s, b;
-    item_coords(P, item, s, b);
+    int item, chunk, s, b;
+    grid_coords(P, item, chunk, s, b);
     const SurfDesc sd = P.surfs[s];
     const int v = chunk * 256 + threadIdx.x;
     constexpr int kStage = 1024;
@@ -245,7 +294,13 @@ __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunk
     __shared__ int sCnt, sBase;
     int *meta = P.meta + (size_t)item * 4;
     if (chunk * 256 >= sd.V || meta[2]) return; // CTA-uniform
-    if (threadIdx.x == 0) sCnt = 0;
+    constexpr int kHash = 512; // >= 2 x the CTA's vertices: the open-addressing table can never fill up
+    __shared__ int sKey[kDense ? 1 : kHash];
+    __shared__ int sVal[kDense ? 1 : kHash];
+    __shared__ int sEn, sEbase;
+    if (threadIdx.x == 0) { sCnt = 0; sEn = 0; }
+    if (!kDense)
+        for (int i = threadIdx.x; i < kHash; i += 256) { sKey[i] = -1; sVal[i] = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const size_t base = (size_t)item * P.vstride;
@@ -258,13 +313,21 @@ __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunk
         lev = P.lev8[base + v] & 0x7f;
         em = P.emask[base + v];
     }
-    {
+    if (kDense) {
         // table[level][basin] += 1, one atomic per distinct (level, basin) of the warp: neighbouring vertices
         // mostly share it, and same-address atomics of one warp serialise in the L2
         const int key = bu >= 0 ? lev * NB + bu : -1 - lane;
         const unsigned peers = __match_any_sync(0xffffffffu, key);
         if (!(P.flags & 256) && bu >= 0 && lane == (__ffs(peers) - 1))
             atomicAdd(P.table + (size_t)item * P.tabcap + key, (unsigned)__popc(peers));
+    } else if (bu >= 0) {
+        const int key = (lev << 24) | bu;
+        unsigned h = ((unsigned)key * 2654435761u) >> 23; // 9 bits
+        for (;;) {
+            const int old = atomicCAS(&sKey[h], -1, key);
+            if (old == -1 || old == key) { atomicAdd(&sVal[h], 1); break; }
+            h = (h + 1) & (kHash - 1);
+        }
     }
     // candidate unions: earlier neighbours lying in another basin (each distinct basin once per vertex, best
     // effort).  Staged in shared memory: one returning atomic per CTA reserves the output range.
@@ -289,23 +352,49 @@ __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunk
         }
     }
     __syncthreads();
-    const int n = min(sCnt, kStage);
-    if (n == 0) return;
-    if (threadIdx.x == 0) sBase = atomicAdd(meta + 1, n);
+    // flush: one returning atomic per CTA and list
+    int mypos = 0, myn = 0;
+    if (!kDense) {
+        for (int q = 0; q < kHash / 256; ++q) myn += sKey[threadIdx.x * (kHash / 256) + q] != -1;
+        if (myn) mypos = atomicAdd(&sEn, myn);
+    }
     __syncthreads();
-    const int gbase = sBase;
-    if (gbase + n <= P.paircap) { // else: K_S sees npairs > paircap and flags the map
-        unsigned long long *__restrict__ dst = P.pairs + (size_t)item * P.paircap + gbase;
-        for (int i = threadIdx.x; i < n; i += 256) dst[i] = sPairs[i];
+    const int n = min(sCnt, kStage);
+    if (threadIdx.x == 0) {
+        if (n) sBase = atomicAdd(meta + 1, n);
+        if (!kDense && sEn) sEbase = atomicAdd(meta + 3, sEn);
+    }
+    __syncthreads();
+    if (n) {
+        const int gbase = sBase;
+        if (gbase + n <= P.paircap) { // else: K_S sees npairs > paircap and flags the map
+            unsigned long long *__restrict__ dst = P.pairs + (size_t)item * P.paircap + gbase;
+            for (int i = threadIdx.x; i < n; i += 256) dst[i] = sPairs[i];
+        }
+    }
+    if (!kDense && myn) {
+        // entries live in the (otherwise unused) table region: (level << 48) | (basin << 24) | vertices
+        unsigned long long *__restrict__ dst = reinterpret_cast<unsigned long long *>(P.table + (size_t)item * P.tabcap);
+        int pos = sEbase + mypos;
+        if (sEbase + sEn <= P.tabcap / 2) // else: K_S sees too many entries and flags the map
+            for (int q = 0; q < kHash / 256; ++q) {
+                const int slot = threadIdx.x * (kHash / 256) + q;
+                const int key = sKey[slot];
+                if (key != -1)
+                    dst[pos++] = ((unsigned long long)(key >> 24) << 48) | ((unsigned long long)(key & 0xFFFFFF) << 24) |
+                                 (unsigned long long)sVal[slot];
+            }
     }
 }
 
 // ------------------------------------------------------------------------------------------- K_S
 // Per-slot scratch in global memory.
+static constexpr int kPowSmem = 2048;
 static constexpr int kSweepBasinCap = 12288; // (< 65536: the fold packs root ids in 16 bits) // basins whose state fits the sweep's shared memory (18 B each)
 
 struct SweepSlot {
     unsigned long long *pairs2; // [paircap] candidate unions bucketed by level
+    uint2 *elist;               // [Vmax] non-empty table entries {basin, vertices} bucketed by level
     int2 *cls;                  // [Vmax] class = {root at creation, creation level} -> {root, fp32 value bits}
     float *incseq;              // [min(nbcap, kSweepBasinCap)][128] increment of root r's component at level l
 };
@@ -314,7 +403,7 @@ static inline size_t pipe_al256(size_t x) { return (x + 255) / 256 * 256; }
 
 size_t pipe_slot_bytes(int32_t Vmax, int nbcap, int paircap) {
     const size_t nb = (size_t)(nbcap < kSweepBasinCap ? nbcap : kSweepBasinCap);
-    return pipe_al256(sizeof(unsigned long long) * (size_t)paircap) + pipe_al256(sizeof(int2) * (size_t)Vmax) +
+    return pipe_al256(sizeof(unsigned long long) * (size_t)paircap) + 2 * pipe_al256(sizeof(int2) * (size_t)Vmax) +
            pipe_al256(sizeof(float) * kLevels * nb);
 }
 
@@ -323,6 +412,8 @@ __device__ __forceinline__ SweepSlot carve_slot(char *base, int32_t Vmax, int nb
     SweepSlot w;
     w.pairs2 = reinterpret_cast<unsigned long long *>(base);
     base += al(sizeof(unsigned long long) * (size_t)paircap);
+    w.elist = reinterpret_cast<uint2 *>(base);
+    base += al(sizeof(int2) * (size_t)Vmax);
     w.cls = reinterpret_cast<int2 *>(base);
     base += al(sizeof(int2) * (size_t)Vmax);
     w.incseq = reinterpret_cast<float *>(base);
@@ -333,8 +424,8 @@ __device__ __forceinline__ SweepSlot carve_slot(char *base, int32_t Vmax, int nb
 __host__ __device__ inline size_t pipe_sweep_smem(int NB, bool max_only) {
     const size_t nba = ((size_t)NB + 3) / 4 * 4;
     const size_t bits = (((size_t)NB + 31) / 32 * 4 + 15) / 16 * 16;
-    if (max_only) return nba * (4 + 4 + 4 + 1 + 1) + 16;    // parent, size, leader accumulator, hook level, peak level
-    return nba * (4 + 4 + 4 + 4 + 1 + 1 + 8) + bits + 16;  // + class of the level, hook parent, two fp32 row buffers
+    if (max_only) return nba * (8 + 4 + 4 + 4 + 1 + 1) + 16;   // pow(size,E), parent, size, leader accumulator, hook level, peak level
+    return nba * (8 + 4 + 4 + 4 + 4 + 1 + 1 + 8) + bits + 16; // + class of the level, hook parent, two fp32 row buffers
 }
 
 // The sweep over the basins of one map.  Per level l (three barrier intervals, shared memory only on the
@@ -361,6 +452,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_kernel(PipePa
     __shared__ double sHHd[2][kLevels];
     __shared__ int sPstart[kLevels + 1];
     __shared__ int sCursor[kLevels];
+    __shared__ int sEstart[kLevels + 1];
+    __shared__ int sEcursor[kLevels];
+    __shared__ double sPow[kPowSmem];     // pow(n, E) for small n: most components are small
     __shared__ int sNs[2];
     __shared__ float sDelta[2];
     __shared__ int sItem;
@@ -408,7 +502,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_kernel(PipePa
         // ---- shared-memory layout of the per-basin state
         const int nba = (NB + 3) / 4 * 4;
         const int bits_words = (((NB + 31) / 32 * 4 + 15) / 16 * 16) / 4;
-        int *bparent = reinterpret_cast<int *>(sDyn);
+        double *bpw = reinterpret_cast<double *>(sDyn); // pow(size, E) of the live roots, fetched asynchronously
+        int *bparent = reinterpret_cast<int *>(bpw + nba);
         int *bsize = bparent + nba;
         int *bcur = bsize + nba;       // root -> class created for it in this level; kMaxOnly: leader sum (fp32 bits)
         int *hookpar = kMaxOnly ? bcur : bcur + nba; // merge history: the root this one was hooked under ... (not kMaxOnly)
@@ -426,7 +521,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_kernel(PipePa
             if (P.status) P.status[e0 + tid] = on ? P.tab_status[e0 + tid] : 0;
         }
         if (tid == 0) sC = 0;
-        for (int i = tid; i < kLevels; i += nthr) sCursor[i] = 0;
+        for (int i = tid; i < kLevels; i += nthr) { sCursor[i] = 0; sEcursor[i] = 0; }
+        for (int i = tid; i < kPowSmem; i += nthr) sPow[i] = (i <= sd.V) ? sd.powE[i] : 0.0;
         const unsigned char *__restrict__ gblev = P.blev + (size_t)item * P.nbcap;
         for (int i = tid; i < NB; i += nthr) {
             bparent[i] = i;
@@ -448,31 +544,82 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_kernel(PipePa
         // ---- candidate unions bucketed by level (counting sort; order inside a level is irrelevant)
         const unsigned long long *__restrict__ pairs = P.pairs + (size_t)item * P.paircap;
         for (int i = tid; i < NP; i += nthr) atomicAdd(&sCursor[(int)(pairs[i] >> 48)], 1);
+        // ---- the count table [level][basin] is ~90% zeros: compact it once into per-level lists {basin, vertices}.
+        //      Column-wise traversal: a warp looks at 32 neighbouring basins of ONE level at a time (coalesced, the
+        //      level is the loop index), eight levels in flight per thread.
+        unsigned *__restrict__ tab = P.table + (size_t)item * P.tabcap;
+        const int ncols = (NB + 31) & ~31; // warp-uniform column loop
+        for (int col = tid; col < ncols; col += nthr) {
+            for (int l0 = 1; l0 < nlev; l0 += 8) {
+                unsigned cc[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) cc[q] = (col < NB && l0 + q < nlev) ? tab[(size_t)(l0 + q) * NB + col] : 0u;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const unsigned nz = __ballot_sync(0xffffffffu, cc[q] != 0u);
+                    if (nz && lane == 0) atomicAdd(&sEcursor[l0 + q], __popc(nz));
+                }
+            }
+        }
         __syncthreads();
         if (tid == 0) {
             int run = 0;
             for (int l = 0; l < kLevels; ++l) { const int c = sCursor[l]; sPstart[l] = run; sCursor[l] = run; run += c; }
             sPstart[kLevels] = run;
         }
+        if (tid == 32) {
+            int run = 0;
+            for (int l = 0; l < kLevels; ++l) { const int c = sEcursor[l]; sEstart[l] = run; sEcursor[l] = run; run += c; }
+            sEstart[kLevels] = run;
+        }
         __syncthreads();
         for (int i = tid; i < NP; i += nthr) {
             const unsigned long long p = pairs[i];
             ws.pairs2[atomicAdd(&sCursor[(int)(p >> 48)], 1)] = p;
         }
+        for (int col = tid; col < ncols; col += nthr) {
+            for (int l0 = 1; l0 < nlev; l0 += 8) {
+                unsigned cc[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) cc[q] = (col < NB && l0 + q < nlev) ? tab[(size_t)(l0 + q) * NB + col] : 0u;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const unsigned nz = __ballot_sync(0xffffffffu, cc[q] != 0u);
+                    if (nz) {
+                        int basepos = 0;
+                        if (lane == 0) basepos = atomicAdd(&sEcursor[l0 + q], __popc(nz));
+                        basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                        if (cc[q] != 0u) ws.elist[basepos + __popc(nz & ((1u << lane) - 1u))] = make_uint2((unsigned)col, cc[q]);
+                    }
+                }
+            }
+        }
         __syncthreads();
         PIPE_TICK(0)
 
-        unsigned *__restrict__ tab = P.table + (size_t)item * P.tabcap;
         const double *__restrict__ powE = sd.powE;
-        // register prefetch of the next level's inputs: up to 8 table entries and 1 candidate union per thread
-        unsigned cq[8];
+        // register prefetch of the next level's inputs: one table entry and one candidate union per thread
+        uint2 eq = make_uint2(0u, 0u);
         unsigned long long pq = 0ull;
         auto prefetch_level = [&](int l) {
-            const unsigned *__restrict__ row = tab + (size_t)l * NB;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) cq[q] = (tid + q * nthr < NB) ? row[tid + q * nthr] : 0u;
+            const int ie = sEstart[l] + tid;
+            eq = (ie < sEstart[l + 1]) ? ws.elist[ie] : make_uint2(0u, 0u);
             const int i = sPstart[l] + tid;
             pq = (i < sPstart[l + 1]) ? ws.pairs2[i] : 0ull;
+        };
+        // increments of level l for the roots that were live at l (derivable from the hook log at any later time);
+        // their pow(size, E) was fetched into bpw by the same thread during F3 of level l
+        auto consume_level = [&](int l) {
+            cp_async_wait_all();
+            for (int bb = tid; bb < NB; bb += nthr) {
+                const int cb = blev[bb];
+                const int sg = cb >> 7;
+                if ((cb & 0x7f) <= l && hooklev[bb] > l && l < (sg ? ns1 : ns0)) {
+                    const float inc = __double2float_rn(__dmul_rn(bpw[bb], sHHd[sg][l]));
+                    if (kMaxOnly) racc[bb] = __float_as_int(__fadd_rn(__int_as_float(racc[bb]), inc));
+                    else ws.incseq[(size_t)l * nba + bb] = inc;
+                }
+            }
         };
         if (nlev > 1) prefetch_level(1);
         int nclass = 0;
@@ -499,22 +646,32 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_kernel(PipePa
             }
             __syncthreads();
             PIPE_TICK(3)
-            // ================= F2: sizes; one new class per component that gains vertices ================
+            // ================= F2a: the previous level's increments (its pow(size, E) fetches have landed) =
+            if (lev > 1) consume_level(lev - 1);
+            if (kMaxOnly) __syncthreads(); // leaders of level lev-1 final before the hand-over below
+            // ================= F2b: sizes; one new class per component that gains vertices ================
             unsigned *__restrict__ row = tab + (size_t)lev * NB;
-            for (int bb0 = tid; bb0 < NB; bb0 += 8 * nthr) {
-                if (bb0 != tid || (P.flags & 1024)) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) cq[q] = (bb0 + q * nthr < NB) ? row[bb0 + q * nthr] : 0u;
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int bb = bb0 + q * nthr;
-                    if (bb >= NB) break;
-                    const unsigned c = cq[q];
-                    if (c != 0u) {
-                        const int r = pf_find(bparent, bb);
-                        atomicAdd(bsize + r, (int)c);
-                        if (!kMaxOnly) {
+            {
+                const int ebeg = sEstart[lev], eend = sEstart[lev + 1];
+                for (int ew = ebeg + (tid & ~31); ew < eend; ew += nthr) { // warp-uniform trip counts (ballots below)
+                    const int ie = ew + lane;
+                    uint2 ent = make_uint2(0u, 0u);
+                    if (ie < eend) ent = (ew == ebeg + (tid & ~31) && !(P.flags & 1024)) ? eq : ws.elist[ie];
+                    const unsigned c = ent.y;
+                    int r = -1;
+                    if (c != 0u) r = pf_find(bparent, (int)ent.x);
+                    // Late levels send most basins to a few giant roots: same-address shared-memory atomics would
+                    // serialise.  The lanes that agree with the first active lane's root are summed by one redux.
+                    const unsigned am = __ballot_sync(0xffffffffu, c != 0u);
+                    if (am) {
+                        const int lead = __ffs(am) - 1;
+                        const int r0 = __shfl_sync(0xffffffffu, r, lead);
+                        const bool same = (c != 0u) && r == r0;
+                        const int sum = __reduce_add_sync(0xffffffffu, same ? (int)c : 0);
+                        const bool own = (c != 0u) && !same; // a different root: on its own
+                        if (lane == lead) atomicAdd(bsize + r0, sum);
+                        if (own) atomicAdd(bsize + r, (int)c);
+                        if (!kMaxOnly && (lane == lead || own)) {
                             const unsigned bit = 1u << (r & 31);
                             if (!(atomicOr(bitsC + (r >> 5), bit) & bit)) {
                                 const int j = atomicAdd(&sC, 1);
@@ -523,56 +680,41 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_kernel(PipePa
                             }
                         }
                     }
-                    // an older root hooked in this level hands its size (and its leader) over; a root of this very
-                    // level has neither yet
-                    if (hooklev[bb] == lev && (blev[bb] & 0x7f) != lev) {
-                        const int r = pf_find(bparent, bb);
-                        atomicAdd(bsize + r, bsize[bb]);
-                        if (kMaxOnly) atomicMax(racc + r, racc[bb]); // sums are >= 0: integer order == float order
-                    }
                 }
+                // older roots hooked in this level hand their size (and their leader) over; a root of this very level
+                // has neither yet
+                for (int bb = tid; bb < NB; bb += nthr)
+                    if (hooklev[bb] == lev && (blev[bb] & 0x7f) != lev) {
+                        const int rr = pf_find(bparent, bb);
+                        atomicAdd(bsize + rr, bsize[bb]);
+                        if (kMaxOnly) atomicMax(racc + rr, racc[bb]); // sums are >= 0: integer order == float order
+                    }
             }
             __syncthreads();
             PIPE_TICK(4)
-            // ================= F3: the level's increment of every live root ==============================
+            // ================= F3: fetch pow(size, E) of every live root (asynchronously) ================
             if (lev + 1 < nlev && !(P.flags & 1024)) prefetch_level(lev + 1);
-            if (lev + 3 < nlev && !(P.flags & 2048)) { // rows come from HBM (written by K_D long ago): pull the row of level l+3 into the L2
-                const unsigned *__restrict__ far = tab + (size_t)(lev + 3) * NB;
-                for (int i = tid * 32; i < NB; i += nthr * 32) pf_prefetch_l2(far + i);
-            }
-            for (int bb0 = tid; bb0 < NB; bb0 += 8 * nthr) { // gather sizes, then 8 independent pow-table loads
-                int szq[8];
-                double pwq[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int bb = bb0 + q * nthr;
-                    szq[q] = -1;
-                    if (bb < NB) {
-                        const int cb = blev[bb];
-                        if (bparent[bb] == bb && (cb & 0x7f) <= lev && lev < ((cb >> 7) ? ns1 : ns0)) szq[q] = bsize[bb];
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) pwq[q] = szq[q] >= 0 ? powE[szq[q]] : 0.0;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int bb = bb0 + q * nthr;
-                    if (szq[q] >= 0) {
-                        const float inc = __double2float_rn(__dmul_rn(pwq[q], sHHd[blev[bb] >> 7][lev]));
-                        if (kMaxOnly) racc[bb] = __float_as_int(__fadd_rn(__int_as_float(racc[bb]), inc));
-                        else ws.incseq[(size_t)lev * nba + bb] = inc;
-                    }
+            for (int bb = tid; bb < NB; bb += nthr) {
+                const int cb = blev[bb];
+                if (bparent[bb] == bb && (cb & 0x7f) <= lev && lev < ((cb >> 7) ? ns1 : ns0)) {
+                    const int sz = bsize[bb];
+                    if (sz < kPowSmem) bpw[bb] = sPow[sz];
+                    else cp_async8(bpw + bb, powE + sz); // the few large components: asynchronous, consumed next level
                 }
             }
             if (!kMaxOnly) {
                 if (P.want_vertex_pass)
-                    for (int bb = tid; bb < NB; bb += nthr)
-                        if (row[bb] != 0u) row[bb] = 0x80000000u | (unsigned)bcur[pf_find(bparent, bb)];
+                    for (int ie = sEstart[lev] + tid; ie < sEstart[lev + 1]; ie += nthr) {
+                        const int bb = (int)ws.elist[ie].x;
+                        row[bb] = 0x80000000u | (unsigned)bcur[pf_find(bparent, bb)];
+                    }
                 for (int i = tid; i < bits_words; i += nthr) bitsC[i] = 0u;
             }
             __syncthreads();
             PIPE_TICK(5)
         }
+        if (nlev > 1) consume_level(nlev - 1);
+        __syncthreads();
         nclass = kMaxOnly ? 0 : sC;
         // ---- fold: the value of a class = the increments of its component in level order, following the merge
         // history.  Level-synchronous with the accumulators in REGISTERS: kFold classes per thread and pass; per
@@ -675,11 +817,323 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_kernel(PipePa
     }
 }
 
+// ------------------------------------------------------------------------------------------- K_S (max-only maps)
+// No vertex weights and no maps requested: only the per-map maximum leaves the kernel, and that needs ONE
+// accumulator per live root instead of one per class.  All increments are >= 0 and fp32 round-to-nearest
+// addition is monotone, so among the classes of a component the one with the largest sum so far keeps the
+// largest sum for ever (they all add the same increments from here on): the "leader".  A root's leader is its
+// own first class (born with the root, at its peak); when roots merge the leader of the union is the larger of
+// the two.  max_v TFCE(v) is therefore the maximum over the final roots of the leader sums -- bit-identical
+// to the maximum of the full map, with no per-class state at all.
+//
+// Per level only LIVE roots are visited: a compact list (double-buffered, rebuilt in passing every level)
+// instead of a dense loop over all basins; roots enter it at the level of their peak (basins bucketed by
+// birth level) and leave it when they are hooked.  pow(size, E) comes from a shared-memory copy of the table
+// for small components; the few large ones are fetched asynchronously (cp.async) and added one barrier later.
+static constexpr int kPend = 512;
+
+__host__ __device__ inline size_t pipe_sweep_max_smem_bytes(int NB) {
+    const size_t nba = ((size_t)NB + 7) / 8 * 8;
+    return nba * (4 + 4 + 4 + 2 + 2 + 2 + 1 + 1) + 16;
+}
+
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(PipeParams P, int smem_bytes) {
+    extern __shared__ __align__(16) unsigned char sDyn[];
+    __shared__ double sHHd[2][kLevels];
+    __shared__ double sPow[kPowSmem];
+    __shared__ double sPendPw[kPend];
+    __shared__ int sPendBb[kPend];
+    __shared__ int sPstart[kLevels + 1], sEstart[kLevels + 1], sBstart[kLevels + 1];
+    __shared__ int sCurP[kLevels], sCurE[kLevels], sCurB[kLevels];
+    __shared__ int sNs[2];
+    __shared__ float sDelta[2];
+    __shared__ int sItem, sNpend, sNalive[2];
+    __shared__ float sRed[2][kThreads / 32];
+
+    const int tid = threadIdx.x;
+    constexpr int nthr = kThreads;
+    const int lane = tid & 31, wid = tid >> 5;
+    const SweepSlot ws = carve_slot(P.slot_ws + (size_t)blockIdx.x * P.slot_stride, P.Vmax, P.nbcap, P.paircap);
+    unsigned long long *const elist = reinterpret_cast<unsigned long long *>(ws.elist);
+    const int total_items = P.B * P.S;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sItem = atomicAdd(P.work_counter, 1);
+        __syncthreads();
+        const int item = sItem;
+        if (item >= total_items) break;
+        int s, b;
+        item_coords(P, item, s, b);
+        const SurfDesc sd = P.surfs[s];
+        int *meta = P.meta + (size_t)item * 4;
+        const int NB = meta[0], NP = meta[1], NE = meta[3];
+        const size_t e0 = ((size_t)b * P.S + s) * 2;
+        long long tk = P.timing ? clock64() : 0;
+#define PIPE_TICK(i)                                                                 \
+        if (P.timing && tid == 0) {                                                  \
+            const long long now = clock64();                                         \
+            atomicAdd(P.timing + (i), (unsigned long long)(now - tk));               \
+            tk = now;                                                                \
+        }
+        if (meta[2] || NB > P.nbcap || NB > 65535 || NP > P.paircap || (int64_t)NE > P.tabcap / 2 || NE > P.Vmax ||
+            pipe_sweep_max_smem_bytes(NB) > (size_t)smem_bytes) {
+            if (tid == 0) {
+                meta[2] = 1; // redone by tfce_basin_kernel
+                if (P.timing) atomicAdd(P.timing + 10, 1ull);
+            }
+            continue;
+        }
+        if (P.timing && tid == 0) {
+            atomicAdd(P.timing + 11, (unsigned long long)NB);
+            atomicAdd(P.timing + 12, (unsigned long long)NP);
+            atomicAdd(P.timing + 13, 1ull);
+            atomicAdd(P.timing + 7, (unsigned long long)NE);
+        }
+        // ---- shared-memory layout of the per-basin state
+        const int nba = (NB + 7) / 8 * 8;
+        int *bparent = reinterpret_cast<int *>(sDyn);
+        int *bsize = bparent + nba;
+        int *racc = bsize + nba;                                                  // leader sum of a root (fp32 bits)
+        unsigned short *alive[2];
+        alive[0] = reinterpret_cast<unsigned short *>(racc + nba);                // live roots (double-buffered)
+        alive[1] = alive[0] + nba;
+        unsigned short *birth = alive[1] + nba;                                   // basins bucketed by the level of their peak
+        unsigned char *hooklev = reinterpret_cast<unsigned char *>(birth + nba);  // level at which a root was hooked (255: never)
+        unsigned char *blev = hooklev + nba;                                      // level | sign << 7 of the peak
+
+        for (int i = tid; i < 2 * kLevels; i += nthr)
+            sHHd[i / kLevels][i % kLevels] = (double)P.tab_HH[(e0 + i / kLevels) * kLevels + i % kLevels];
+        for (int i = tid; i < kPowSmem; i += nthr) sPow[i] = (i <= sd.V) ? sd.powE[i] : 0.0;
+        if (tid < 2) {
+            const bool on = (tid == 0) || P.two_sided;
+            sNs[tid] = on ? P.tab_ns[e0 + tid] : 0;
+            sDelta[tid] = P.tab_delta[e0 + tid];
+            if (P.status) P.status[e0 + tid] = on ? P.tab_status[e0 + tid] : 0;
+            sNalive[tid] = 0;
+        }
+        if (tid == 0) sNpend = 0;
+        for (int i = tid; i < kLevels; i += nthr) { sCurP[i] = 0; sCurE[i] = 0; sCurB[i] = 0; }
+        const unsigned char *__restrict__ gblev = P.blev + (size_t)item * P.nbcap;
+        __syncthreads();
+        for (int i = tid; i < NB; i += nthr) {
+            bparent[i] = i;
+            bsize[i] = 0;
+            racc[i] = 0; // +0.0f
+            hooklev[i] = 255;
+            const int cb = gblev[i];
+            blev[i] = (unsigned char)cb;
+            atomicAdd(&sCurB[cb & 0x7f], 1);
+        }
+        // ---- candidate unions, table entries and basins bucketed by level (counting sorts; order inside a level
+        //      is irrelevant)
+        const unsigned long long *__restrict__ pairs = P.pairs + (size_t)item * P.paircap;
+        const unsigned long long *__restrict__ entries = reinterpret_cast<const unsigned long long *>(P.table + (size_t)item * P.tabcap);
+        // (eight independent loads in flight per thread: the shared-memory atomics in between keep the compiler from
+        //  overlapping them on its own)
+        auto for_each_batched = [&](const unsigned long long *__restrict__ src, int n, auto &&fn) {
+            for (int i0 = tid; i0 < n; i0 += 8 * nthr) {
+                unsigned long long v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = ld_u64_if(src + i0 + q * nthr, i0 + q * nthr < n);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (i0 + q * nthr < n) fn(v[q]);
+            }
+        };
+        for_each_batched(pairs, NP, [&](unsigned long long p) { atomicAdd(&sCurP[(int)(p >> 48)], 1); });
+        for_each_batched(entries, NE, [&](unsigned long long p) { atomicAdd(&sCurE[(int)(p >> 48)], 1); });
+        __syncthreads();
+        if (tid < 3) {
+            int *cur = tid == 0 ? sCurP : tid == 1 ? sCurE : sCurB;
+            int *start = tid == 0 ? sPstart : tid == 1 ? sEstart : sBstart;
+            int run = 0;
+            for (int l = 0; l < kLevels; ++l) { const int c = cur[l]; start[l] = run; cur[l] = run; run += c; }
+            start[kLevels] = run;
+        }
+        __syncthreads();
+        for_each_batched(pairs, NP, [&](unsigned long long p) { ws.pairs2[atomicAdd(&sCurP[(int)(p >> 48)], 1)] = p; });
+        for_each_batched(entries, NE, [&](unsigned long long p) { elist[atomicAdd(&sCurE[(int)(p >> 48)], 1)] = p; });
+        for (int i = tid; i < NB; i += nthr) birth[atomicAdd(&sCurB[blev[i] & 0x7f], 1)] = (unsigned short)i;
+        __syncthreads();
+        const int ns0 = sNs[0], ns1 = sNs[1];
+        const int nlev = max(ns0, ns1);
+        PIPE_TICK(0)
+
+        const double *__restrict__ powE = sd.powE;
+        // register pipeline of the coming levels' inputs, two levels deep: one entry and one candidate union per thread
+        // and level (predicated loads: issued here, first used two levels later)
+        unsigned long long eq[2] = {0ull, 0ull}, pq[2] = {0ull, 0ull};
+        auto prefetch_level = [&](int l, int slot) {
+            if (l >= nlev) return; // block-uniform
+            const int ie = sEstart[l] + tid;
+            const int i = sPstart[l] + tid;
+            const unsigned long long e = ld_u64_if(elist + ie, ie < sEstart[l + 1]);
+            const unsigned long long p = ld_u64_if(ws.pairs2 + i, i < sPstart[l + 1]);
+            if (slot) { eq[1] = e; pq[1] = p; } else { eq[0] = e; pq[0] = p; }
+        };
+        prefetch_level(1, 1);
+        prefetch_level(2, 0);
+        int cur = 0; // which alive list is current
+        for (int lev = 1; lev < nlev; ++lev) {
+            // ================= F1: unions of this level =================================================
+            for (int i = sPstart[lev] + tid; i < sPstart[lev + 1]; i += nthr) {
+                const unsigned long long p = (i == sPstart[lev] + tid) ? ((lev & 1) ? pq[1] : pq[0]) : ws.pairs2[i];
+                int ru = pf_find(bparent, (int)((p >> 24) & 0xFFFFFFu));
+                int ra = pf_find(bparent, (int)(p & 0xFFFFFFu));
+                while (ru != ra) {
+                    // total order on roots: (activation level, id); the later root goes under the earlier one
+                    const int kru = ((blev[ru] & 0x7f) << 24) | ru, kra = ((blev[ra] & 0x7f) << 24) | ra;
+                    const int hi = kru > kra ? ru : ra, lo = kru > kra ? ra : ru;
+                    const int old = atomicCAS(bparent + hi, hi, lo);
+                    if (old == hi) { hooklev[hi] = (unsigned char)lev; break; } // this thread hooked hi
+                    const int nh = pf_find(bparent, old);
+                    if (hi == ru) { ru = nh; ra = pf_find(bparent, ra); }
+                    else          { ra = nh; ru = pf_find(bparent, ru); }
+                }
+            }
+            cp_async_wait_all(); // this thread's pow(size, E) fetches of the previous level
+            __syncthreads();
+            PIPE_TICK(3)
+            // ================= F2a: previous level's increments of the large components ===================
+            const int npend = sNpend;
+            if (npend > 0) { // block-uniform
+                for (int i = tid; i < npend; i += nthr) {
+                    const int bb = sPendBb[i];
+                    const float inc = __double2float_rn(__dmul_rn(sPendPw[i], sHHd[blev[bb] >> 7][lev - 1]));
+                    racc[bb] = __float_as_int(__fadd_rn(__int_as_float(racc[bb]), inc));
+                }
+                __syncthreads();
+                if (tid == 0) sNpend = 0;
+            }
+            // ================= F2b: sizes =================================================================
+            {
+                const int ebeg = sEstart[lev], eend = sEstart[lev + 1];
+                for (int ew = ebeg + (tid & ~31); ew < eend; ew += nthr) { // warp-uniform trip counts (ballots below)
+                    const int ie = ew + lane;
+                    unsigned long long ent = 0ull;
+                    if (ie < eend) ent = (ew == ebeg + (tid & ~31)) ? ((lev & 1) ? eq[1] : eq[0]) : elist[ie];
+                    const int c = (int)(ent & 0xFFFFFFu);
+                    int r = -1;
+                    if (c != 0) r = pf_find(bparent, (int)((ent >> 24) & 0xFFFFFFu));
+                    // Late levels send most basins to a few giant roots: same-address shared-memory atomics would
+                    // serialise.  The lanes that agree with the first active lane's root are summed by one redux.
+                    const unsigned am = __ballot_sync(0xffffffffu, c != 0);
+                    if (am) {
+                        const int lead = __ffs(am) - 1;
+                        const int r0 = __shfl_sync(0xffffffffu, r, lead);
+                        const bool same = (c != 0) && r == r0;
+                        const int sum = __reduce_add_sync(0xffffffffu, same ? c : 0);
+                        if (lane == lead) atomicAdd(bsize + r0, sum);
+                        if (c != 0 && !same) atomicAdd(bsize + r, c);
+                    }
+                }
+                // older roots hooked in this level hand their size and their leader over (a root of this very level has
+                // neither yet); they are still on the live list of the previous level
+                const unsigned short *__restrict__ al = alive[cur];
+                const int na = sNalive[cur];
+                for (int i = tid; i < na; i += nthr) {
+                    const int bb = al[i];
+                    if (hooklev[bb] == lev) {
+                        const int rr = pf_find(bparent, bb);
+                        atomicAdd(bsize + rr, bsize[bb]);
+                        atomicMax(racc + rr, racc[bb]); // sums are >= 0: integer order == float order
+                    }
+                }
+            }
+            __syncthreads();
+            PIPE_TICK(4)
+            // ================= F3: this level's increment of every live root; next live list ==============
+            prefetch_level(lev + 2, lev & 1); // this level's registers are free again
+            {
+                const unsigned short *__restrict__ al = alive[cur];
+                unsigned short *__restrict__ nx = alive[cur ^ 1];
+                const int na = sNalive[cur];
+                const int nb = sBstart[lev + 1] - sBstart[lev];   // roots born at this level
+                const int tot = na + nb;
+                for (int iw = (tid & ~31); iw < tot; iw += nthr) { // warp-uniform trip counts
+                    const int i = iw + lane;
+                    int bb = -1;
+                    if (i < na) bb = al[i];
+                    else if (i < tot) bb = birth[sBstart[lev] + i - na];
+                    const bool live = bb >= 0 && bparent[bb] == bb;
+                    if (live) {
+                        const int cb = blev[bb];
+                        const int sg = cb >> 7;
+                        if (lev < (sg ? ns1 : ns0)) {
+                            const int sz = bsize[bb];
+                            if (sz < kPowSmem) {
+                                const float inc = __double2float_rn(__dmul_rn(sPow[sz], sHHd[sg][lev]));
+                                racc[bb] = __float_as_int(__fadd_rn(__int_as_float(racc[bb]), inc));
+                            } else {
+                                const int slot = atomicAdd(&sNpend, 1);
+                                if (slot < kPend) {
+                                    sPendBb[slot] = bb;
+                                    cp_async8(sPendPw + slot, powE + sz); // added at the next level's F2a
+                                } else { // more large components than slots: fetch synchronously
+                                    atomicSub(&sNpend, 1);
+                                    const float inc = __double2float_rn(__dmul_rn(powE[sz], sHHd[sg][lev]));
+                                    racc[bb] = __float_as_int(__fadd_rn(__int_as_float(racc[bb]), inc));
+                                }
+                            }
+                        }
+                    }
+                    const unsigned lm = __ballot_sync(0xffffffffu, live);
+                    if (lm) {
+                        int basepos = 0;
+                        if (lane == 0) basepos = atomicAdd(&sNalive[cur ^ 1], __popc(lm));
+                        basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                        if (live) nx[basepos + __popc(lm & ((1u << lane) - 1u))] = (unsigned short)bb;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) sNalive[cur] = 0; // becomes the next "next" list (nobody reads it before the barrier of F1)
+            cur ^= 1;
+            PIPE_TICK(5)
+        }
+        // the last level's pending increments
+        cp_async_wait_all();
+        __syncthreads();
+        {
+            const int npend = sNpend;
+            for (int i = tid; i < npend; i += nthr) {
+                const int bb = sPendBb[i];
+                const float inc = __double2float_rn(__dmul_rn(sPendPw[i], sHHd[blev[bb] >> 7][nlev - 1]));
+                racc[bb] = __float_as_int(__fadd_rn(__int_as_float(racc[bb]), inc));
+            }
+        }
+        __syncthreads();
+        if (tid == 0) sNpend = 0;
+        // ---- outputs: the final roots carry the leaders
+        const float d0 = sDelta[0], d1 = sDelta[1];
+        float m0 = 0.f, m1 = 0.f;
+        for (int bb = tid; bb < NB; bb += nthr)
+            if (bparent[bb] == bb) {
+                const int sg = blev[bb] >> 7;
+                const float sc = __fmul_rn(__int_as_float(racc[bb]), sg ? d1 : d0);
+                if (sg) m1 = fmaxf(m1, sc); else m0 = fmaxf(m0, sc);
+            }
+        m0 = pwarp_max(m0);
+        m1 = pwarp_max(m1);
+        if (lane == 0) { sRed[0][wid] = m0; sRed[1][wid] = m1; }
+        __syncthreads();
+        if (tid == 0 && P.max_out) {
+            float a = 0.f, c = 0.f;
+            for (int w = 0; w < nthr / 32; ++w) { a = fmaxf(a, sRed[0][w]); c = fmaxf(c, sRed[1][w]); }
+            P.max_out[e0] = a;
+            P.max_out[e0 + 1] = c;
+        }
+        PIPE_TICK(2)
+#undef PIPE_TICK
+    }
+}
+
 // ------------------------------------------------------------------------------------------- K_G
 __global__ void __launch_bounds__(256) pipe_output_kernel(PipeParams P, int chunks) {
-    const int item = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-    int s, b;
-    item_coords(P, item, s, b);
+    int item, chunk, s, b;
+    grid_coords(P, item, chunk, s, b);
     const SurfDesc sd = P.surfs[s];
     const int *meta = P.meta + (size_t)item * 4;
     if (chunk * 256 >= sd.V || meta[2]) return; // CTA-uniform
@@ -715,7 +1169,7 @@ __global__ void __launch_bounds__(256) pipe_output_kernel(PipeParams P, int chun
 
 // ------------------------------------------------------------------------------------------- host
 int pipe_sweep_max_smem() {
-    int v = 220 * 1024;
+    int v = 200 * 1024;
     if (const char *g = getenv("TMB_PIPE_SMEM_KB")) { const int kb = atoi(g); if (kb >= 16 && kb <= 224) v = kb * 1024; }
     return v;
 }
@@ -736,38 +1190,39 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
     if (items <= 0) return 0;
     const int chunksA = (p.Vmax + kChunkA - 1) / kChunkA;
     const int chunks = (p.Vmax + 255) / 256;
-    TMB_REQUIRE((int64_t)items * chunks < (int64_t)INT32_MAX, "tfce pipeline: too many work items (%d maps x %d chunks)",
-                items, chunks);
-    pipe_levels_kernel<<<items * chunksA, 256, 0, stream>>>(p, chunksA);
-    pipe_ascent_kernel<<<items * chunks, 256, 0, stream>>>(p, chunks);
-    pipe_basin_kernel<<<items * chunks, 256, 0, stream>>>(p, chunks);
-    pipe_count_kernel<<<items * chunks, 256, 0, stream>>>(p, chunks);
+    TMB_REQUIRE(p.B <= 65535 && p.S <= 65535, "tfce pipeline: at most 65535 rows and surfaces per launch (got %d, %d)", p.B, p.S);
+    pipe_levels_kernel<<<dim3(chunksA, p.B, p.S), 256, 0, stream>>>(p, chunksA);
+    pipe_ascent_kernel<<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
+    pipe_basin_kernel<<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
+    if (p.want_vertex_pass) pipe_count_kernel<true><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
+    else pipe_count_kernel<false><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
     TMB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
-    // sweep geometry: max-only maps keep 14 bytes per basin in shared memory -> two 512-thread CTAs per SM hide each
-    // other's barrier intervals; the class path (26 bytes per basin) runs one 1024-thread CTA per SM
     if (p.want_vertex_pass) {
+        // class path (values per vertex): one 1024-thread CTA per SM
         const int smem = pipe_sweep_max_smem();
         TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_kernel<1024, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const int grid = items < num_slots / 2 ? items : num_slots / 2;
         pipe_sweep_kernel<1024, 1, false><<<grid, 1024, smem, stream>>>(p, smem);
     } else {
-        int geom = 2;
+        // max-only path: 20 bytes of shared memory per basin -> two 512-thread CTAs per SM hide each other's barrier
+        // intervals (TMB_PIPE_GEOM=1: one 1024-thread CTA)
+        int geom = 1;
         if (const char *g = getenv("TMB_PIPE_GEOM")) geom = atoi(g);
         if (geom == 1) {
-            const int smem = pipe_sweep_max_smem();
-            TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_kernel<1024, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const int smem = 190 * 1024;
+            TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             const int grid = items < num_slots / 2 ? items : num_slots / 2;
-            pipe_sweep_kernel<1024, 1, true><<<grid, 1024, smem, stream>>>(p, smem);
+            pipe_sweep_max_kernel<1024, 1><<<grid, 1024, smem, stream>>>(p, smem);
         } else {
-            const int smem = pipe_sweep_max_smem() / 2 - 4096;
-            TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_kernel<512, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const int smem = 85 * 1024;
+            TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             const int grid = items < num_slots ? items : num_slots;
-            pipe_sweep_kernel<512, 2, true><<<grid, 512, smem, stream>>>(p, smem);
+            pipe_sweep_max_kernel<512, 2><<<grid, 512, smem, stream>>>(p, smem);
         }
     }
     count_launch(5);
     if (p.want_vertex_pass) {
-        pipe_output_kernel<<<items * chunks, 256, 0, stream>>>(p, chunks);
+        pipe_output_kernel<<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
         count_launch();
     }
     TMB_CUDA(cudaGetLastError());
