@@ -392,6 +392,9 @@ extern "C" int tmb_plan_destroy(tmb_plan *p) {
             tot += (double)t[8] + (double)t[9];
             fprintf(stderr, "[tmb phase timing] total %.3e cycles, nodes %llu\n", tot, t[7]);
             for (int i = 0; i < 7; ++i) fprintf(stderr, "  %-12s %6.2f%%\n", names[i], tot > 0 ? 100.0 * t[i] / tot : 0.0);
+            if (p->pipe_ok)
+                fprintf(stderr, "  init detail (%% of total): setup %.2f, pair hist %.2f, vertex hist %.2f, scans %.2f, pair scatter %.2f (rest of init: births + vertex scatter)\n",
+                        100.0 * t[20] / tot, 100.0 * t[21] / tot, 100.0 * t[22] / tot, 100.0 * t[23] / tot, 100.0 * t[24] / tot);
 
         }
         if (p->use_basin && !p->pipe_ok) {

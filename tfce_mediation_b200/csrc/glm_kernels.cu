@@ -113,6 +113,13 @@ __device__ __forceinline__ double t_from(double beta, double sse, double dof, do
     return __ddiv_rn(beta, (double)se);
 }
 
+// the same with d / dof folded into one factor
+__device__ __forceinline__ double t_from_scaled(double beta, double sse, double d_over_dof) {
+    if (sse < 0.0) sse = 0.0;
+    const float se = __double2float_rn(__dsqrt_rn(__dmul_rn(sse, d_over_dof)));
+    return __ddiv_rn(beta, (double)se);
+}
+
 // one output row of a thread's tile: two 128-bit stores (float) / eight scalar stores (double)
 __device__ __forceinline__ void store_tile_row(float *t32, double *t64, size_t off, int64_t v0, int tn,
                                                const float (&o32)[8], const double (&o64)[8]) {
@@ -399,7 +406,11 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
     for (int i = 0; i < 4; ++i) {
         const int perm = m0 + wm * 32 + i * 8 + g;
         if (perm >= p.P) continue;
-        const double G = p.G[perm], dg = p.d[perm];
+        // sigma2 * d = sse * (d / dof): the quotient is formed once per design, which removes one of the epilogue's two
+        // fp64 divisions per statistic (ncu: the epilogue's divisions and square root keep the fp64 pipe throttled for
+        // ~45% of the kernel's samples).  fp64 rounding differs from (sse / dof) * d by <= 1 ulp before the reference's
+        // own rounding of se to fp32.
+        const double G = p.G[perm], dscale = __ddiv_rn(p.d[perm], p.dof);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int64_t v = v0 + wn * 32 + j * 8 + t4 * 2;
@@ -410,7 +421,7 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
                 const double beta = acc[i][j][e];
                 const double yyv = (v + e < p.V) ? p.yy[v + e] : 0.0;
                 const double sse = yyv - __dmul_rn(beta, __dmul_rn(G, beta));
-                double t = t_from(beta, sse, p.dof, dg);
+                double t = t_from_scaled(beta, sse, dscale);
                 if (p.nan_to_zero && t != t) t = 0.0;
                 if (v + e >= p.V) t = 0.0;
                 o64[e] = t;

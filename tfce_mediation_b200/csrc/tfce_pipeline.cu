@@ -283,107 +283,81 @@ __global__ void __launch_bounds__(256) pipe_basin_kernel(PipeParams P, int chunk
 // kDense (class path): table[level][basin] += 1 in global memory.  Otherwise (max-only maps) the (level, basin)
 // counts of the CTA's 256 vertices are aggregated in a shared-memory hash and appended to the map's entry list
 // {level, basin, vertices}; the same key may come from several CTAs -- the sweep simply adds them up.
+static constexpr int kCountVPT = 1;                 // vertices per thread (4 was slower: longer CTAs, bigger hash)
+static constexpr int kCountChunk = 256 * kCountVPT; // vertices per CTA
+
 template <bool kDense>
 __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunks) {
     int item, chunk, s, b;
     grid_coords(P, item, chunk, s, b);
     const SurfDesc sd = P.surfs[s];
-    const int v = chunk * 256 + threadIdx.x;
-    constexpr int kStage = 1024;
+    constexpr int kStage = 2 * kCountChunk;
     __shared__ unsigned long long sPairs[kStage];
     __shared__ int sCnt, sBase;
     int *meta = P.meta + (size_t)item * 4;
-    if (chunk * 256 >= sd.V || meta[2]) return; // CTA-uniform
-    constexpr int kHash = 512; // >= 2 x the CTA's vertices: the open-addressing table can never fill up
-    __shared__ int sKey[kDense ? 1 : kHash];
-    __shared__ int sVal[kDense ? 1 : kHash];
-    __shared__ int sEn, sEbase;
-    if (threadIdx.x == 0) { sCnt = 0; sEn = 0; }
-    if (!kDense)
-        for (int i = threadIdx.x; i < kHash; i += 256) { sKey[i] = -1; sVal[i] = 0; }
+    const int v_beg = chunk * kCountChunk;
+    if (v_beg >= sd.V || meta[2]) return; // CTA-uniform
+    if (threadIdx.x == 0) sCnt = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const size_t base = (size_t)item * P.vstride;
     const int *__restrict__ basin = P.basin + base;
     const int NB = meta[0];
-    const int bu = (v < sd.V) ? basin[v] : -1;
-    unsigned em = 0;
-    int lev = 0;
-    if (bu >= 0) {
-        lev = P.lev8[base + v] & 0x7f;
-        em = P.emask[base + v];
+    int buq[kCountVPT], levq[kCountVPT];
+    unsigned emq[kCountVPT];
+#pragma unroll
+    for (int q = 0; q < kCountVPT; ++q) {
+        const int v = v_beg + q * 256 + threadIdx.x;
+        buq[q] = (v < sd.V) ? basin[v] : -1;
+        levq[q] = (v < sd.V) ? (int)(P.lev8[base + v] & 0x7f) : 0;
+        emq[q] = (v < sd.V) ? P.emask[base + v] : 0u;
     }
-    if (kDense) {
-        // table[level][basin] += 1, one atomic per distinct (level, basin) of the warp: neighbouring vertices
-        // mostly share it, and same-address atomics of one warp serialise in the L2
-        const int key = bu >= 0 ? lev * NB + bu : -1 - lane;
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        if (!(P.flags & 256) && bu >= 0 && lane == (__ffs(peers) - 1))
-            atomicAdd(P.table + (size_t)item * P.tabcap + key, (unsigned)__popc(peers));
-    } else if (bu >= 0) {
-        const int key = (lev << 24) | bu;
-        unsigned h = ((unsigned)key * 2654435761u) >> 23; // 9 bits
-        for (;;) {
-            const int old = atomicCAS(&sKey[h], -1, key);
-            if (old == -1 || old == key) { atomicAdd(&sVal[h], 1); break; }
-            h = (h + 1) & (kHash - 1);
+#pragma unroll
+    for (int q = 0; q < kCountVPT; ++q) {
+        const int v = v_beg + q * 256 + threadIdx.x;
+        const int bu = buq[q], lev = levq[q];
+        const unsigned em = bu >= 0 ? emq[q] : 0u;
+        if (kDense) {
+            // table[level][basin] += 1, one atomic per distinct (level, basin) of the warp: neighbouring vertices
+            // mostly share it, and same-address atomics of one warp serialise in the L2
+            const int key = bu >= 0 ? lev * NB + bu : -1 - lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (!(P.flags & 256) && bu >= 0 && lane == (__ffs(peers) - 1))
+                atomicAdd(P.table + (size_t)item * P.tabcap + key, (unsigned)__popc(peers));
         }
-    }
-    // candidate unions: earlier neighbours lying in another basin (each distinct basin once per vertex, best
-    // effort).  Staged in shared memory: one returning atomic per CTA reserves the output range.
-    if (em && !(P.flags & 512)) {
-        const int *__restrict__ row = sd.ell + (size_t)v * sd.ell_width;
-        int s0 = -1, s1 = -1, s2 = -1, s3 = -1;
-        unsigned m = em;
-        while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const int ba = basin[row[j]];
-            if (ba == bu || ba == s0 || ba == s1 || ba == s2 || ba == s3) continue;
-            s3 = s2; s2 = s1; s1 = s0; s0 = ba;
-            const unsigned long long pr = ((unsigned long long)lev << 48) | ((unsigned long long)bu << 24) | (unsigned long long)ba;
-            const int pos = atomicAdd(&sCnt, 1);
-            if (pos < kStage) {
-                sPairs[pos] = pr;
-            } else { // staging buffer full (cannot happen on meshes; kept for correctness)
-                const int gp = atomicAdd(meta + 1, 1);
-                if (gp < P.paircap) P.pairs[(size_t)item * P.paircap + gp] = pr;
+        // candidate unions: earlier neighbours lying in another basin (each distinct basin once per vertex, best
+        // effort).  Staged in shared memory: one returning atomic per CTA reserves the output range.
+        if (em && !(P.flags & 512)) {
+            const int *__restrict__ row = sd.ell + (size_t)v * sd.ell_width;
+            int s0 = -1, s1 = -1, s2 = -1, s3 = -1;
+            unsigned m = em;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const int ba = basin[row[j]];
+                if (ba == bu || ba == s0 || ba == s1 || ba == s2 || ba == s3) continue;
+                s3 = s2; s2 = s1; s1 = s0; s0 = ba;
+                const unsigned long long pr = ((unsigned long long)lev << 48) | ((unsigned long long)bu << 24) | (unsigned long long)ba;
+                const int pos = atomicAdd(&sCnt, 1);
+                if (pos < kStage) {
+                    sPairs[pos] = pr;
+                } else { // staging buffer full (cannot happen on meshes; kept for correctness)
+                    const int gp = atomicAdd(meta + 1, 1);
+                    if (gp < P.paircap) P.pairs[(size_t)item * P.paircap + gp] = pr;
+                }
             }
         }
     }
     __syncthreads();
-    // flush: one returning atomic per CTA and list
-    int mypos = 0, myn = 0;
-    if (!kDense) {
-        for (int q = 0; q < kHash / 256; ++q) myn += sKey[threadIdx.x * (kHash / 256) + q] != -1;
-        if (myn) mypos = atomicAdd(&sEn, myn);
-    }
-    __syncthreads();
+    // flush: one returning atomic per CTA
     const int n = min(sCnt, kStage);
-    if (threadIdx.x == 0) {
-        if (n) sBase = atomicAdd(meta + 1, n);
-        if (!kDense && sEn) sEbase = atomicAdd(meta + 3, sEn);
-    }
+    if (n == 0) return;
+    if (threadIdx.x == 0) sBase = atomicAdd(meta + 1, n);
     __syncthreads();
-    if (n) {
-        const int gbase = sBase;
-        if (gbase + n <= P.paircap) { // else: K_S sees npairs > paircap and flags the map
-            unsigned long long *__restrict__ dst = P.pairs + (size_t)item * P.paircap + gbase;
-            for (int i = threadIdx.x; i < n; i += 256) dst[i] = sPairs[i];
-        }
-    }
-    if (!kDense && myn) {
-        // entries live in the (otherwise unused) table region: (level << 48) | (basin << 24) | vertices
-        unsigned long long *__restrict__ dst = reinterpret_cast<unsigned long long *>(P.table + (size_t)item * P.tabcap);
-        int pos = sEbase + mypos;
-        if (sEbase + sEn <= P.tabcap / 2) // else: K_S sees too many entries and flags the map
-            for (int q = 0; q < kHash / 256; ++q) {
-                const int slot = threadIdx.x * (kHash / 256) + q;
-                const int key = sKey[slot];
-                if (key != -1)
-                    dst[pos++] = ((unsigned long long)(key >> 24) << 48) | ((unsigned long long)(key & 0xFFFFFF) << 24) |
-                                 (unsigned long long)sVal[slot];
-            }
+    const int gbase = sBase;
+    if (gbase + n <= P.paircap) { // else: K_S sees npairs > paircap and flags the map
+        unsigned long long *__restrict__ dst = P.pairs + (size_t)item * P.paircap + gbase;
+        for (int i = threadIdx.x; i < n; i += 256) dst[i] = sPairs[i];
     }
 }
 
@@ -836,6 +810,7 @@ __host__ __device__ inline size_t pipe_sweep_max_smem_bytes(int NB) {
     const size_t nba = ((size_t)NB + 7) / 8 * 8;
     return nba * (4 + 4 + 4 + 2 + 2 + 2 + 1 + 1) + 16;
 }
+// + per-warp level histograms of the vertex sort: (threads / 32) * 128 ints, added by the launcher
 
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(PipeParams P, int smem_bytes) {
@@ -855,7 +830,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
     constexpr int nthr = kThreads;
     const int lane = tid & 31, wid = tid >> 5;
     const SweepSlot ws = carve_slot(P.slot_ws + (size_t)blockIdx.x * P.slot_stride, P.Vmax, P.nbcap, P.paircap);
-    unsigned long long *const elist = reinterpret_cast<unsigned long long *>(ws.elist);
+    unsigned short *const elist = reinterpret_cast<unsigned short *>(ws.elist); // basin of every active vertex, bucketed by level
     const int total_items = P.B * P.S;
 
     for (;;) {
@@ -868,7 +843,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         item_coords(P, item, s, b);
         const SurfDesc sd = P.surfs[s];
         int *meta = P.meta + (size_t)item * 4;
-        const int NB = meta[0], NP = meta[1], NE = meta[3];
+        const int NB = meta[0], NP = meta[1];
+        const int V = sd.V;
         const size_t e0 = ((size_t)b * P.S + s) * 2;
         long long tk = P.timing ? clock64() : 0;
 #define PIPE_TICK(i)                                                                 \
@@ -877,8 +853,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             atomicAdd(P.timing + (i), (unsigned long long)(now - tk));               \
             tk = now;                                                                \
         }
-        if (meta[2] || NB > P.nbcap || NB > 65535 || NP > P.paircap || (int64_t)NE > P.tabcap / 2 || NE > P.Vmax ||
-            pipe_sweep_max_smem_bytes(NB) > (size_t)smem_bytes) {
+        if (meta[2] || NB > P.nbcap || NB > 65535 || NP > P.paircap ||
+            pipe_sweep_max_smem_bytes(NB) + (nthr / 32) * kLevels * sizeof(int) > (size_t)smem_bytes) {
             if (tid == 0) {
                 meta[2] = 1; // redone by tfce_basin_kernel
                 if (P.timing) atomicAdd(P.timing + 10, 1ull);
@@ -889,7 +865,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             atomicAdd(P.timing + 11, (unsigned long long)NB);
             atomicAdd(P.timing + 12, (unsigned long long)NP);
             atomicAdd(P.timing + 13, 1ull);
-            atomicAdd(P.timing + 7, (unsigned long long)NE);
         }
         // ---- shared-memory layout of the per-basin state
         const int nba = (NB + 7) / 8 * 8;
@@ -902,6 +877,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         unsigned short *birth = alive[1] + nba;                                   // basins bucketed by the level of their peak
         unsigned char *hooklev = reinterpret_cast<unsigned char *>(birth + nba);  // level at which a root was hooked (255: never)
         unsigned char *blev = hooklev + nba;                                      // level | sign << 7 of the peak
+        int *whist = reinterpret_cast<int *>(blev + nba);                         // [warps][128] private level histograms / cursors
 
         for (int i = tid; i < 2 * kLevels; i += nthr)
             sHHd[i / kLevels][i % kLevels] = (double)P.tab_HH[(e0 + i / kLevels) * kLevels + i % kLevels];
@@ -926,12 +902,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             blev[i] = (unsigned char)cb;
             atomicAdd(&sCurB[cb & 0x7f], 1);
         }
-        // ---- candidate unions, table entries and basins bucketed by level (counting sorts; order inside a level
-        //      is irrelevant)
+        // ---- candidate unions, basins (by the level of their peak) and VERTICES (by their own level) bucketed by
+        //      level: counting sorts, order inside a level is irrelevant.  The vertex sort uses per-warp private
+        //      histograms (no contention between warps); warp w owns the vertex blocks w, w + nwarps, ... in BOTH
+        //      passes, 128 vertices per block (one 4-byte load of level codes per lane).
         const unsigned long long *__restrict__ pairs = P.pairs + (size_t)item * P.paircap;
-        const unsigned long long *__restrict__ entries = reinterpret_cast<const unsigned long long *>(P.table + (size_t)item * P.tabcap);
-        // (eight independent loads in flight per thread: the shared-memory atomics in between keep the compiler from
-        //  overlapping them on its own)
+        const unsigned *__restrict__ lev32 = reinterpret_cast<const unsigned *>(P.lev8 + (size_t)item * P.vstride);
+        const int4 *__restrict__ basin4 = reinterpret_cast<const int4 *>(P.basin + (size_t)item * P.vstride);
+        constexpr int nwarps = nthr / 32;
+        int *const myhist = whist + wid * kLevels;
+        for (int i = tid; i < nwarps * kLevels; i += nthr) whist[i] = 0;
         auto for_each_batched = [&](const unsigned long long *__restrict__ src, int n, auto &&fn) {
             for (int i0 = tid; i0 < n; i0 += 8 * nthr) {
                 unsigned long long v[8];
@@ -942,8 +922,38 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                     if (i0 + q * nthr < n) fn(v[q]);
             }
         };
+        PIPE_TICK(20)
         for_each_batched(pairs, NP, [&](unsigned long long p) { atomicAdd(&sCurP[(int)(p >> 48)], 1); });
-        for_each_batched(entries, NE, [&](unsigned long long p) { atomicAdd(&sCurE[(int)(p >> 48)], 1); });
+        __syncthreads();
+        PIPE_TICK(21)
+        // vertex blocks of 128 (one 4-byte load of level codes per lane); warp w owns blocks w, w + nwarps, ... in both
+        // passes.  (Measured alternatives: warp-aggregation with match.any and a striped lane mapping were both slower;
+        // the second pass, whose 2-byte stores scatter over the level segments, is what costs.)
+        const int nblocks = (V + 127) / 128;
+        for (int blk0 = wid; blk0 < nblocks; blk0 += 4 * nwarps) { // four blocks (loads) in flight per warp
+            unsigned w4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int blk = blk0 + q * nwarps;
+                w4[q] = (blk < nblocks && blk * 128 + lane * 4 < V) ? lev32[blk * 32 + lane] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int v = (blk0 + q * nwarps) * 128 + lane * 4 + e;
+                    const int lv = (w4[q] >> (8 * e)) & 0x7f;
+                    if (lv && v < V) atomicAdd(&myhist[lv], 1);
+                }
+        }
+        __syncthreads();
+        PIPE_TICK(22)
+        // level totals over the warps; per-(warp, level) cursors = level start + counts of the earlier warps
+        if (tid < kLevels) {
+            int tot = 0;
+            for (int w = 0; w < nwarps; ++w) { const int c = whist[w * kLevels + tid]; whist[w * kLevels + tid] = tot; tot += c; }
+            sCurE[tid] = tot;
+        }
         __syncthreads();
         if (tid < 3) {
             int *cur = tid == 0 ? sCurP : tid == 1 ? sCurE : sCurB;
@@ -953,33 +963,55 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             start[kLevels] = run;
         }
         __syncthreads();
+        PIPE_TICK(23)
         for_each_batched(pairs, NP, [&](unsigned long long p) { ws.pairs2[atomicAdd(&sCurP[(int)(p >> 48)], 1)] = p; });
-        for_each_batched(entries, NE, [&](unsigned long long p) { elist[atomicAdd(&sCurE[(int)(p >> 48)], 1)] = p; });
+        __syncthreads();
+        PIPE_TICK(24)
         for (int i = tid; i < NB; i += nthr) birth[atomicAdd(&sCurB[blev[i] & 0x7f], 1)] = (unsigned short)i;
+        for (int blk0 = wid; blk0 < nblocks; blk0 += 2 * nwarps) { // two blocks in flight per warp
+            unsigned w2[2];
+            int4 b2[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int blk = blk0 + q * nwarps;
+                const bool ok = blk < nblocks && blk * 128 + lane * 4 < V;
+                w2[q] = ok ? lev32[blk * 32 + lane] : 0u;
+                b2[q] = ok ? basin4[blk * 32 + lane] : make_int4(-1, -1, -1, -1);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int bs[4] = {b2[q].x, b2[q].y, b2[q].z, b2[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int v = (blk0 + q * nwarps) * 128 + lane * 4 + e;
+                    const int lv = (w2[q] >> (8 * e)) & 0x7f;
+                    if (lv && v < V) elist[sEstart[lv] + atomicAdd(&myhist[lv], 1)] = (unsigned short)bs[e];
+                }
+            }
+        }
         __syncthreads();
         const int ns0 = sNs[0], ns1 = sNs[1];
         const int nlev = max(ns0, ns1);
         PIPE_TICK(0)
 
         const double *__restrict__ powE = sd.powE;
-        // register pipeline of the coming levels' inputs, two levels deep: one entry and one candidate union per thread
-        // and level (predicated loads: issued here, first used two levels later)
-        unsigned long long eq[2] = {0ull, 0ull}, pq[2] = {0ull, 0ull};
-        auto prefetch_level = [&](int l, int slot) {
+        // register pipeline of the coming levels' candidate unions, two levels deep (one per thread and level); the loads
+        // go straight into their destination registers: first use two levels later
+        unsigned long long pq0 = 0ull, pq1 = 0ull;
+        auto prefetch_pairs = [&](int l) {
             if (l >= nlev) return; // block-uniform
-            const int ie = sEstart[l] + tid;
             const int i = sPstart[l] + tid;
-            const unsigned long long e = ld_u64_if(elist + ie, ie < sEstart[l + 1]);
-            const unsigned long long p = ld_u64_if(ws.pairs2 + i, i < sPstart[l + 1]);
-            if (slot) { eq[1] = e; pq[1] = p; } else { eq[0] = e; pq[0] = p; }
+            const bool ok = i < sPstart[l + 1];
+            if (l & 1) asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u64 %0, [%1];\n\t}" : "+l"(pq1) : "l"(ws.pairs2 + i), "r"((int)ok) : "memory");
+            else       asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u64 %0, [%1];\n\t}" : "+l"(pq0) : "l"(ws.pairs2 + i), "r"((int)ok) : "memory");
         };
-        prefetch_level(1, 1);
-        prefetch_level(2, 0);
+        prefetch_pairs(1);
+        prefetch_pairs(2);
         int cur = 0; // which alive list is current
         for (int lev = 1; lev < nlev; ++lev) {
             // ================= F1: unions of this level =================================================
             for (int i = sPstart[lev] + tid; i < sPstart[lev + 1]; i += nthr) {
-                const unsigned long long p = (i == sPstart[lev] + tid) ? ((lev & 1) ? pq[1] : pq[0]) : ws.pairs2[i];
+                const unsigned long long p = (i == sPstart[lev] + tid) ? ((lev & 1) ? pq1 : pq0) : ws.pairs2[i];
                 int ru = pf_find(bparent, (int)((p >> 24) & 0xFFFFFFu));
                 int ra = pf_find(bparent, (int)(p & 0xFFFFFFu));
                 while (ru != ra) {
@@ -1012,22 +1044,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                 const int ebeg = sEstart[lev], eend = sEstart[lev + 1];
                 for (int ew = ebeg + (tid & ~31); ew < eend; ew += nthr) { // warp-uniform trip counts (ballots below)
                     const int ie = ew + lane;
-                    unsigned long long ent = 0ull;
-                    if (ie < eend) ent = (ew == ebeg + (tid & ~31)) ? ((lev & 1) ? eq[1] : eq[0]) : elist[ie];
-                    const int c = (int)(ent & 0xFFFFFFu);
+                    const bool act = ie < eend;
                     int r = -1;
-                    if (c != 0) r = pf_find(bparent, (int)((ent >> 24) & 0xFFFFFFu));
-                    // Late levels send most basins to a few giant roots: same-address shared-memory atomics would
-                    // serialise.  The lanes that agree with the first active lane's root are summed by one redux.
-                    const unsigned am = __ballot_sync(0xffffffffu, c != 0);
-                    if (am) {
-                        const int lead = __ffs(am) - 1;
-                        const int r0 = __shfl_sync(0xffffffffu, r, lead);
-                        const bool same = (c != 0) && r == r0;
-                        const int sum = __reduce_add_sync(0xffffffffu, same ? c : 0);
-                        if (lane == lead) atomicAdd(bsize + r0, sum);
-                        if (c != 0 && !same) atomicAdd(bsize + r, c);
-                    }
+                    if (act) r = pf_find(bparent, (int)elist[ie]);
+                    // Late levels send most vertices to a few giant roots: same-address shared-memory atomics would
+                    // serialise.  The lanes that agree with the first active lane's root are counted by one ballot.
+                    const unsigned am = __ballot_sync(0xffffffffu, act);
+                    const int lead = __ffs(am) - 1;
+                    const int r0 = __shfl_sync(0xffffffffu, r, lead);
+                    const unsigned same = __ballot_sync(0xffffffffu, act && r == r0);
+                    if (lane == lead) atomicAdd(bsize + r0, __popc(same));
+                    if (act && r != r0) atomicAdd(bsize + r, 1);
                 }
                 // older roots hooked in this level hand their size and their leader over (a root of this very level has
                 // neither yet); they are still on the live list of the previous level
@@ -1045,7 +1072,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             __syncthreads();
             PIPE_TICK(4)
             // ================= F3: this level's increment of every live root; next live list ==============
-            prefetch_level(lev + 2, lev & 1); // this level's registers are free again
+            prefetch_pairs(lev + 2); // this level's register is free again
             {
                 const unsigned short *__restrict__ al = alive[cur];
                 unsigned short *__restrict__ nx = alive[cur ^ 1];
@@ -1194,8 +1221,9 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
     pipe_levels_kernel<<<dim3(chunksA, p.B, p.S), 256, 0, stream>>>(p, chunksA);
     pipe_ascent_kernel<<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
     pipe_basin_kernel<<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
-    if (p.want_vertex_pass) pipe_count_kernel<true><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
-    else pipe_count_kernel<false><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
+    const int chunksD = (p.Vmax + kCountChunk - 1) / kCountChunk;
+    if (p.want_vertex_pass) pipe_count_kernel<true><<<dim3(chunksD, p.B, p.S), 256, 0, stream>>>(p, chunksD);
+    else pipe_count_kernel<false><<<dim3(chunksD, p.B, p.S), 256, 0, stream>>>(p, chunksD);
     TMB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
     if (p.want_vertex_pass) {
         // class path (values per vertex): one 1024-thread CTA per SM
@@ -1209,7 +1237,7 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
         int geom = 1;
         if (const char *g = getenv("TMB_PIPE_GEOM")) geom = atoi(g);
         if (geom == 1) {
-            const int smem = 190 * 1024;
+            const int smem = 196 * 1024;
             TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             const int grid = items < num_slots / 2 ? items : num_slots / 2;
             pipe_sweep_max_kernel<1024, 1><<<grid, 1024, smem, stream>>>(p, smem);
