@@ -533,12 +533,21 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_sweep_kernel(SweepPa
 // per (row, surface): max of +x and of -x, NaN ignored -- the inputs of the host threshold tables
 __global__ void tfce_maxima_kernel(const SurfDesc *__restrict__ surfs, int S, const float *__restrict__ stat,
                                    int64_t ld, float *__restrict__ max_out) {
-    __shared__ float sRed[2][8];
+    __shared__ float sRed[2][32];
     const int b = blockIdx.x / S, s = blockIdx.x % S;
     const SurfDesc sd = surfs[s];
     const float *__restrict__ x = stat + (size_t)b * ld + sd.col_off;
     float mp = -INFINITY, mn = -INFINITY;
-    for (int v = threadIdx.x; v < sd.V; v += blockDim.x) {
+    const int V = sd.V, step = blockDim.x;
+    int v = threadIdx.x;
+    for (; v + 7 * step < V; v += 8 * step) { // eight independent loads in flight per thread: the map streams from HBM
+        float xq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xq[q] = x[v + q * step];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { mp = fmaxf(mp, xq[q]); mn = fmaxf(mn, -xq[q]); }
+    }
+    for (; v < V; v += step) {
         const float xv = x[v];
         mp = fmaxf(mp, xv);
         mn = fmaxf(mn, -xv);
@@ -557,7 +566,7 @@ __global__ void tfce_maxima_kernel(const SurfDesc *__restrict__ surfs, int S, co
 int launch_tfce_maxima(const SurfDesc *surfs, int S, const float *stat, int64_t ld, int B, float *max_out,
                        cudaStream_t stream) {
     if (B * S <= 0) return 0;
-    tfce_maxima_kernel<<<B * S, 256, 0, stream>>>(surfs, S, stat, ld, max_out);
+    tfce_maxima_kernel<<<B * S, 512, 0, stream>>>(surfs, S, stat, ld, max_out);
     count_launch();
     TMB_CUDA(cudaGetLastError());
     return 0;

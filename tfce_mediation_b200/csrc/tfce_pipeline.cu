@@ -1005,8 +1005,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             if (l & 1) asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u64 %0, [%1];\n\t}" : "+l"(pq1) : "l"(ws.pairs2 + i), "r"((int)ok) : "memory");
             else       asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u64 %0, [%1];\n\t}" : "+l"(pq0) : "l"(ws.pairs2 + i), "r"((int)ok) : "memory");
         };
+        unsigned eq0 = 0u, eq1 = 0u; // the same for the level's vertex list (basin of vertex sEstart[l] + tid)
+        auto prefetch_entry = [&](int l) {
+            if (l >= nlev) return; // block-uniform
+            const int ie = sEstart[l] + tid;
+            const bool ok = ie < sEstart[l + 1];
+            if (l & 1) asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u16 %0, [%1];\n\t}" : "+r"(eq1) : "l"(elist + ie), "r"((int)ok) : "memory");
+            else       asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u16 %0, [%1];\n\t}" : "+r"(eq0) : "l"(elist + ie), "r"((int)ok) : "memory");
+        };
         prefetch_pairs(1);
         prefetch_pairs(2);
+        prefetch_entry(1);
+        prefetch_entry(2);
         int cur = 0; // which alive list is current
         for (int lev = 1; lev < nlev; ++lev) {
             // ================= F1: unions of this level =================================================
@@ -1046,7 +1056,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                     const int ie = ew + lane;
                     const bool act = ie < eend;
                     int r = -1;
-                    if (act) r = pf_find(bparent, (int)elist[ie]);
+                    if (act) r = pf_find(bparent, (ew == ebeg + (tid & ~31)) ? (int)((lev & 1) ? eq1 : eq0) : (int)elist[ie]);
                     // Late levels send most vertices to a few giant roots: same-address shared-memory atomics would
                     // serialise.  The lanes that agree with the first active lane's root are counted by one ballot.
                     const unsigned am = __ballot_sync(0xffffffffu, act);
@@ -1072,7 +1082,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             __syncthreads();
             PIPE_TICK(4)
             // ================= F3: this level's increment of every live root; next live list ==============
-            prefetch_pairs(lev + 2); // this level's register is free again
+            prefetch_pairs(lev + 2); // this level's registers are free again
+            prefetch_entry(lev + 2);
             {
                 const unsigned short *__restrict__ al = alive[cur];
                 unsigned short *__restrict__ nx = alive[cur ^ 1];
