@@ -437,6 +437,9 @@ static int pipe_ensure(tmb_plan *p, int items) {
         p->pipe_nbcap = (int)std::min<int64_t>(p->pipe_vstride, std::max<int64_t>(4096, p->pipe_vstride / 8));
         p->pipe_paircap = (int)p->pipe_vstride;
         p->pipe_tabcap = 8 * p->pipe_vstride;
+        // capacity overrides (tests: force the over-capacity path, whose maps are redone by tfce_basin_kernel)
+        if (const char *e = getenv("TMB_PIPE_NBCAP")) { const int v = atoi(e); if (v >= 1) p->pipe_nbcap = std::min<int>(v, p->pipe_nbcap); }
+        if (const char *e = getenv("TMB_PIPE_PAIRCAP")) { const int v = atoi(e); if (v >= 1) p->pipe_paircap = std::min<int>(v, p->pipe_paircap); }
     }
     if (!p->d_pipe_slots) {
         p->pipe_slot_stride = pipe_slot_bytes(p->Vmax, p->pipe_nbcap, p->pipe_paircap);
