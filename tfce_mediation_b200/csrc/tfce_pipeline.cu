@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) pipe_basin_kernel(PipeParams P, int chunk
 // kDense (class path): table[level][basin] += 1 in global memory.  Otherwise (max-only maps) the (level, basin)
 // counts of the CTA's 256 vertices are aggregated in a shared-memory hash and appended to the map's entry list
 // {level, basin, vertices}; the same key may come from several CTAs -- the sweep simply adds them up.
-static constexpr int kCountVPT = 1;                 // vertices per thread (4 was slower: longer CTAs, bigger hash)
+static constexpr int kCountVPT = 4;                 // vertices per thread
 static constexpr int kCountChunk = 256 * kCountVPT; // vertices per CTA
 
 template <bool kDense>
@@ -978,15 +978,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                 w2[q] = ok ? lev32[blk * 32 + lane] : 0u;
                 b2[q] = ok ? basin4[blk * 32 + lane] : make_int4(-1, -1, -1, -1);
             }
+            int pos[8]; // eight returning shared-memory atomics in flight, then the eight stores
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int bs[4] = {b2[q].x, b2[q].y, b2[q].z, b2[q].w};
+            for (int q = 0; q < 2; ++q)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int v = (blk0 + q * nwarps) * 128 + lane * 4 + e;
                     const int lv = (w2[q] >> (8 * e)) & 0x7f;
-                    if (lv && v < V) elist[sEstart[lv] + atomicAdd(&myhist[lv], 1)] = (unsigned short)bs[e];
+                    pos[q * 4 + e] = (lv && v < V) ? sEstart[lv] + atomicAdd(&myhist[lv], 1) : -1;
                 }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int bs[4] = {b2[q].x, b2[q].y, b2[q].z, b2[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (pos[q * 4 + e] >= 0) elist[pos[q * 4 + e]] = (unsigned short)bs[e];
             }
         }
         __syncthreads();
@@ -1005,21 +1011,31 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             if (l & 1) asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u64 %0, [%1];\n\t}" : "+l"(pq1) : "l"(ws.pairs2 + i), "r"((int)ok) : "memory");
             else       asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u64 %0, [%1];\n\t}" : "+l"(pq0) : "l"(ws.pairs2 + i), "r"((int)ok) : "memory");
         };
-        unsigned eq0 = 0u, eq1 = 0u; // the same for the level's vertex list (basin of vertex sEstart[l] + tid)
+        // the same for the level's vertex list: four entries per thread (basins of vertices sEstart[l] + q * nthr + tid)
+        unsigned eqA[4] = {0u, 0u, 0u, 0u}, eqB[4] = {0u, 0u, 0u, 0u};
+#define PIPE_LD_U16(dst, ptr, ok) asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u16 %0, [%1];\n\t}" : "+r"(dst) : "l"(ptr), "r"((int)(ok)) : "memory")
         auto prefetch_entry = [&](int l) {
             if (l >= nlev) return; // block-uniform
-            const int ie = sEstart[l] + tid;
-            const bool ok = ie < sEstart[l + 1];
-            if (l & 1) asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u16 %0, [%1];\n\t}" : "+r"(eq1) : "l"(elist + ie), "r"((int)ok) : "memory");
-            else       asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u16 %0, [%1];\n\t}" : "+r"(eq0) : "l"(elist + ie), "r"((int)ok) : "memory");
+            const int ie = sEstart[l] + tid, iend = sEstart[l + 1];
+            if (l & 1) {
+                PIPE_LD_U16(eqB[0], elist + ie, ie < iend);
+                PIPE_LD_U16(eqB[1], elist + ie + nthr, ie + nthr < iend);
+                PIPE_LD_U16(eqB[2], elist + ie + 2 * nthr, ie + 2 * nthr < iend);
+                PIPE_LD_U16(eqB[3], elist + ie + 3 * nthr, ie + 3 * nthr < iend);
+            } else {
+                PIPE_LD_U16(eqA[0], elist + ie, ie < iend);
+                PIPE_LD_U16(eqA[1], elist + ie + nthr, ie + nthr < iend);
+                PIPE_LD_U16(eqA[2], elist + ie + 2 * nthr, ie + 2 * nthr < iend);
+                PIPE_LD_U16(eqA[3], elist + ie + 3 * nthr, ie + 3 * nthr < iend);
+            }
         };
         prefetch_pairs(1);
         prefetch_pairs(2);
         prefetch_entry(1);
         prefetch_entry(2);
         int cur = 0; // which alive list is current
-        for (int lev = 1; lev < nlev; ++lev) {
-            // ================= F1: unions of this level =================================================
+        // ================= F1: unions of a level =========================================================
+        auto do_unions = [&](int lev) {
             for (int i = sPstart[lev] + tid; i < sPstart[lev + 1]; i += nthr) {
                 const unsigned long long p = (i == sPstart[lev] + tid) ? ((lev & 1) ? pq1 : pq0) : ws.pairs2[i];
                 int ru = pf_find(bparent, (int)((p >> 24) & 0xFFFFFFu));
@@ -1035,9 +1051,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                     else          { ra = nh; ru = pf_find(bparent, ru); }
                 }
             }
-            cp_async_wait_all(); // this thread's pow(size, E) fetches of the previous level
-            __syncthreads();
-            PIPE_TICK(3)
+        };
+        // Two barrier intervals per level: [F3 of level l-1 + F1 of level l] | [F2 of level l].  F3 decides "live at
+        // level l-1" from the hook log (hooklev > l-1), which the concurrent unions of level l cannot invalidate.
+        if (nlev > 1) do_unions(1);
+        __syncthreads();
+        PIPE_TICK(3)
+        for (int lev = 1; lev < nlev; ++lev) {
             // ================= F2a: previous level's increments of the large components ===================
             const int npend = sNpend;
             if (npend > 0) { // block-uniform
@@ -1052,11 +1072,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             // ================= F2b: sizes =================================================================
             {
                 const int ebeg = sEstart[lev], eend = sEstart[lev + 1];
-                for (int ew = ebeg + (tid & ~31); ew < eend; ew += nthr) { // warp-uniform trip counts (ballots below)
+                int it = 0;
+                for (int ew = ebeg + (tid & ~31); ew < eend; ew += nthr, ++it) { // warp-uniform trip counts (ballots below)
                     const int ie = ew + lane;
                     const bool act = ie < eend;
                     int r = -1;
-                    if (act) r = pf_find(bparent, (ew == ebeg + (tid & ~31)) ? (int)((lev & 1) ? eq1 : eq0) : (int)elist[ie]);
+                    if (act) {
+                        int bas;
+                        if (it == 0) bas = (int)((lev & 1) ? eqB[0] : eqA[0]);
+                        else if (it == 1) bas = (int)((lev & 1) ? eqB[1] : eqA[1]);
+                        else if (it == 2) bas = (int)((lev & 1) ? eqB[2] : eqA[2]);
+                        else if (it == 3) bas = (int)((lev & 1) ? eqB[3] : eqA[3]);
+                        else bas = (int)elist[ie];
+                        r = pf_find(bparent, bas);
+                    }
                     // Late levels send most vertices to a few giant roots: same-address shared-memory atomics would
                     // serialise.  The lanes that agree with the first active lane's root are counted by one ballot.
                     const unsigned am = __ballot_sync(0xffffffffu, act);
@@ -1095,7 +1124,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                     int bb = -1;
                     if (i < na) bb = al[i];
                     else if (i < tot) bb = birth[sBstart[lev] + i - na];
-                    const bool live = bb >= 0 && bparent[bb] == bb;
+                    const bool live = bb >= 0 && hooklev[bb] > lev; // 255 = never hooked
                     if (live) {
                         const int cb = blev[bb];
                         const int sg = cb >> 7;
@@ -1126,8 +1155,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                     }
                 }
             }
+            if (lev + 1 < nlev) do_unions(lev + 1);
+            cp_async_wait_all(); // this thread's pow(size, E) fetches
             __syncthreads();
-            if (tid == 0) sNalive[cur] = 0; // becomes the next "next" list (nobody reads it before the barrier of F1)
+            if (tid == 0) sNalive[cur] = 0; // becomes the next "next" list (first touched again after the next barrier)
             cur ^= 1;
             PIPE_TICK(5)
         }
