@@ -141,6 +141,14 @@ int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, 
                   const double *G_dev, const double *d_dev, int P, int r, int rp, int row0, int nrows,
                   double dof, const double *yy_dev, float *t32_dev, double *t64_dev, int64_t ldt,
                   int nan_to_zero, void *stream);
+/* Stacked pseudo-inverses of P row-permuted copies of ONE design (the permutation loop of
+ * vertex_tfce_multiple_regression_randomise.py:104-106, `nx = X[np.random.permutation(...)]`): permuting whole rows
+ * permutes the columns of pinv(X), so At[k, p*rp + i] = pinv[i, perm_idx[p, k]] is a gather done on the device.
+ * pinv_dev float64 [r, n] (centred regressors' pseudo-inverse), perm_idx_dev int32 [P, n], At_dev float64 [n, ldA]
+ * (columns beyond P*rp and rows i >= r are zero-filled). */
+int tmb_glm_pack_rowperm(const double *pinv_dev, int r, int n, const int32_t *perm_idx_dev, int P, int rp,
+                         double *At_dev, int64_t ldA, void *stream);
+
 /* betas only == cynumstats.pyx:28-29 cy_lin_lstsqr_mat: beta64_dev float64 [nrows, ldt] for the nrows
  * pseudo-inverse rows stored as the first nrows columns of At_dev (ldA a multiple of 128). */
 int tmb_glm_beta(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev, int64_t ldA,

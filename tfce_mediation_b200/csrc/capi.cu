@@ -9,6 +9,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace tmb {
@@ -602,9 +603,22 @@ extern "C" int tmb_threshold_tables(const float *maxima_host, const float *H_hos
                                     float *delta_host, float *T_host, float *HH_host, int32_t *status_host) {
     TMB_REQUIRE(maxima_host && H_host && ns_host && delta_host && T_host && HH_host && status_host && count >= 0,
                 "tmb_threshold_tables: bad arguments");
-    for (int i = 0; i < count; ++i)
-        host_tables(maxima_host[i], H_host[i], ns_host + i, delta_host + i, T_host + (size_t)i * 128,
-                    HH_host + (size_t)i * 128, status_host + i);
+    // ~100 powf calls per entry: a block of 512 two-sided shuffles on two surfaces has 2,048 entries (~3 ms on one core,
+    // on the critical path of the host that feeds the GPU), so the entries are split over a few threads
+    auto work = [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i)
+            host_tables(maxima_host[i], H_host[i], ns_host + i, delta_host + i, T_host + (size_t)i * 128,
+                        HH_host + (size_t)i * 128, status_host + i);
+    };
+    int nt = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (const char *e = getenv("TMB_TABLE_THREADS")) nt = std::max(1, atoi(e));
+    if (count < 256 || nt == 1) { work(0, count); return 0; }
+    std::vector<std::thread> pool;
+    const int per = (count + nt - 1) / nt;
+    for (int t = 1; t < nt; ++t)
+        if (t * per < count) pool.emplace_back(work, t * per, std::min(count, (t + 1) * per));
+    work(0, std::min(count, per));
+    for (auto &th : pool) th.join();
     return 0;
 }
 

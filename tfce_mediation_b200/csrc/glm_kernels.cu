@@ -448,6 +448,21 @@ static int launch_dmma(const GlmParams &p, cudaStream_t stream) {
     return 0;
 }
 
+// ---------------------------------------------------------------- stacked pseudo-inverses of row-permuted designs
+// Permuting whole rows of a design permutes the columns of its pseudo-inverse (X'X is invariant), so the left operand
+// of the batched fit is a gather: At[k, p*rp + i] = pinv[i, perm_idx[p, k]].  Done here instead of on the host: the
+// host then ships only the index rows (n * 4 bytes per shuffle) and keeps ~3 ms per 512 shuffles off its critical path.
+__global__ void glm_pack_rowperm_kernel(const double *__restrict__ pinv, int r, int n, const int32_t *__restrict__ idx,
+                                        int P, int rp, double *__restrict__ At, int64_t ldA) {
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (col >= ldA) return;
+    const int p = (int)(col / rp), i = (int)(col - (int64_t)p * rp);
+    double v = 0.0;
+    if (p < P && i < r) v = pinv[(size_t)i * n + idx[(size_t)p * n + k]];
+    At[(size_t)k * ldA + col] = v;
+}
+
 // ---------------------------------------------------------------- per-vertex sum of squares
 template <typename YT>
 __global__ void glm_sumsq_kernel(const YT *__restrict__ Y, int n, int64_t V, int64_t ldy, int center,
@@ -639,6 +654,18 @@ extern "C" int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, in
     p.P = P; p.r = r; p.rp = rp; p.row0 = row0; p.nrows = nrows; p.dof = dof; p.yy = yy_dev;
     p.t32 = t32_dev; p.t64 = t64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 0;
     return launch_glm(p, (cudaStream_t)stream);
+}
+
+extern "C" int tmb_glm_pack_rowperm(const double *pinv_dev, int r, int n, const int32_t *perm_idx_dev, int P, int rp,
+                                    double *At_dev, int64_t ldA, void *stream) {
+    TMB_REQUIRE(pinv_dev && perm_idx_dev && At_dev, "tmb_glm_pack_rowperm: null pointer");
+    TMB_REQUIRE(r >= 1 && r <= rp && n > 0 && P > 0 && ldA >= (int64_t)P * rp && n <= 65535,
+                "tmb_glm_pack_rowperm: bad shape (r=%d rp=%d n=%d P=%d ldA=%lld)", r, rp, n, P, (long long)ldA);
+    const dim3 grid((unsigned)((ldA + 255) / 256), (unsigned)n);
+    glm_pack_rowperm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pinv_dev, r, n, perm_idx_dev, P, rp, At_dev, ldA);
+    count_launch();
+    TMB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int tmb_glm_beta(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev,

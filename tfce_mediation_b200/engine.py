@@ -311,6 +311,44 @@ class PermutationEngine(object):
             t64 = self.to_caller_order(t64) if t64 is not None else None
         return (t32, t64) if want_f64 else t32
 
+    def tstat_rowperm(self, X, perm_idx):
+        """Fused fit+t for the designs X[perm_idx[p]] (whole rows permuted): the host sends only the index rows;
+        the stacked pseudo-inverses are gathered on the device (tmb_glm_pack_rowperm).  X float64 [n, k] with the
+        intercept in column 0.  Returns CUDA float32 [P, k-1, ld] in the engine's internal column order."""
+        import torch
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        perm_idx = np.asarray(perm_idx)
+        P, n = perm_idx.shape
+        if n != self.Y.n or X.shape[0] != n:
+            raise ValueError("design has %d subjects, data has %d" % (n, self.Y.n))
+        key = X.tobytes()
+        base = self._rowperm_base.get(key) if hasattr(self, "_rowperm_base") else None
+        if base is None:
+            st = design_stack(X[None], center=True)
+            r = st["r"]
+            base = dict(r=r, rp=_rp_for(r), dof=st["dof"], G=st["G"][0], d=st["d"][0],
+                        pinv=torch.from_numpy(np.ascontiguousarray(st["pinv"][0])).to(self.device), rep={})
+            self._rowperm_base = {key: base}            # one design at a time (the drivers' loop)
+        r, rp = base["r"], base["rp"]
+        rep = base["rep"].get(P)
+        if rep is None:                                  # X'X and diag(inv(X'X)) are invariant: one row, repeated
+            rep = (torch.from_numpy(np.repeat(base["G"][None], P, axis=0)).to(self.device),
+                   torch.from_numpy(np.repeat(base["d"][None], P, axis=0)).to(self.device))
+            base["rep"] = {P: rep}
+        idx_d = self._upload("perm_idx", np.ascontiguousarray(perm_idx, dtype=np.int32))
+        ldA = round_up(P * rp, TILE_M)
+        At_d = torch.empty((n, ldA), dtype=torch.float64, device=self.device)
+        L = _lib.lib()
+        stream = _lib.current_stream()
+        _lib.check(L.tmb_glm_pack_rowperm(_lib.ptr(base["pinv"]), r, n, _lib.ptr(idx_d), P, rp, _lib.ptr(At_d), ldA, stream))
+        yy = self.Y.sumsq(True)
+        t32 = torch.empty((P, r, self.Y.ld), dtype=torch.float32, device=self.device)
+        _lib.check(L.tmb_glm_tstat(
+            _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA,
+            _lib.ptr(rep[0]), _lib.ptr(rep[1]), P, r, rp, 0, r, base["dof"], _lib.ptr(yy), _lib.ptr(t32),
+            None, self.Y.ld, 1 if self.nan_to_zero else 0, stream))
+        return t32
+
     # -- whole shuffles --------------------------------------------------------------------------
     def regression_block(self, X, perm_idx=None, designs=None, want_maps=False, download=True):
         """Regression + TFCE + scaled max for a block of shuffles.
@@ -330,8 +368,8 @@ class PermutationEngine(object):
             X = np.asarray(X, dtype=np.float64)
             if not has_intercept(X):
                 raise ValueError("X must have the intercept in column 0")
-            stack = row_permuted_stack(X, perm_idx, center=True)
-        t32 = self.tstat(stack, caller_order=False)
+            stack = None
+        t32 = self.tstat(stack, caller_order=False) if stack is not None else self.tstat_rowperm(X, perm_idx)
         P, C, ld = t32.shape
         mx, status, maps = self.plan.run(t32.view(P * C, ld), two_sided=self.two_sided, want_maps=want_maps)
         mx = mx.view(P, C, self.plan.S, 2)
@@ -357,7 +395,7 @@ class PermutationEngine(object):
         host = torch.empty((N, C, self.plan.S, 2), dtype=torch.float32).pin_memory()
 
         def stage1(a, b):
-            t32 = self.tstat(row_permuted_stack(X, perm_idx[a:b], center=True), caller_order=False)
+            t32 = self.tstat_rowperm(X, perm_idx[a:b])
             flat = t32.view(t32.shape[0] * t32.shape[1], t32.shape[2])
             tk = self.plan.prepare(flat) if self.plan.exact_pow else None
             return t32, flat, tk
