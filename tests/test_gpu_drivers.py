@@ -153,3 +153,38 @@ def test_mmr_lr_driver_rows_identical_to_reference_csv(tmp_path, monkeypatch):
     for s in (0, 1):
         assert [l.strip() for l in open("out/perm_maxTFCE_surf%d_tcon1.csv" % s)] == list(g["rows_tcon1"])
         assert [l.strip() for l in open("out/perm_maxTFCE_surf%d_tcon2.csv" % s)] == list(g["rows_tcon2"])
+
+
+@pytest.mark.parametrize("medtype", ["M", "Y"])
+def test_mmr_lr_mediation_driver_matches_per_surface_dropin(tmp_path, monkeypatch, medtype):
+    """mmr-lr mediation: the batched driver (all surfaces of a block of shuffles at once) writes the rows the
+    per-surface drop-in low_ram_calculate_mediation_tfce (tm_func.py:269-305) writes shuffle by shuffle."""
+    from tfce_mediation_b200 import tm_func
+    from tfce_mediation_b200.tfce import CreateAdjSet
+    from tfce_mediation_b200.tm_multisurface import mmr_lr_randomise as drv
+    g = np.load(os.path.join(G, "mmr_lowram.npz"))
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("tmi_temp"); os.makedirs("want")
+    indptr, indices = g["indptr"], g["indices"]
+    adj = [indices[indptr[i]:indptr[i + 1]].tolist() for i in range(len(indptr) - 1)]
+    data, mask, vdens = g["data"], g["mask"], g["vdensity"]
+    n = data.shape[0]
+    rs = np.random.RandomState(11)
+    pred = rs.standard_normal(n); dep = 0.4 * pred + rs.standard_normal(n)
+    for s in (0, 1):
+        np.save("tmi_temp/%d_data_temp.npy" % s, data * (1 + s)); np.save("tmi_temp/%d_mask_temp.npy" % s, mask)
+        np.save("tmi_temp/%d_adjacency_temp.npy" % s, _obj(adj), allow_pickle=True)
+        np.save("tmi_temp/%d_vdensity_temp.npy" % s, vdens)
+    np.savetxt("pred.csv", pred, delimiter=","); np.savetxt("dep.csv", dep, delimiter=",")
+    opts = drv.getArgumentParser(argparse.ArgumentParser()).parse_args(
+        ["--path", "out", "-pr", "3", "8", "--seed", "42", "-im", medtype, "pred.csv", "dep.csv", "--tfce", "2", "0.67"])
+    drv.run(opts)
+    calc = CreateAdjSet(2, 0.67, adj)
+    for s in (0, 1):
+        for p in range(3, 9):
+            tm_func.low_ram_calculate_mediation_tfce(medtype, data * (1 + s), mask, pred, dep, calc, vdens, set_surf_count=s,
+                                                     perm_number=p, randomise=True, output_dir="want", perm_seed=42)
+        got = [float(l) for l in open("out/perm_maxTFCE_surf%d_%s_zstat.csv" % (s, medtype))]
+        want = [float(l) for l in open("want/perm_maxTFCE_surf%d_%s_zstat.csv" % (s, medtype))]
+        assert len(got) == len(want) == 6
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)

@@ -133,3 +133,24 @@ def test_synth_shapes():
     k2 = synth.kring_csr(csr, 2)
     assert np.diff(k2[0]).min() > 6
     assert synth.cap_mask(v, 600).sum() == 600
+
+
+def test_step2_wrapper_rounding_and_blocks_follow_the_reference():
+    """STEP_2_tfce_randomise_parallel.py:139-148: round(N/200)*100 shuffles (x2 for mediation), blocks of 100."""
+    import argparse
+    from tfce_mediation_b200.tmanalysis import STEP_2_tfce_randomise_parallel as s2
+    for N, doubled in [(10000, False), (10000, True), (250, False), (300, False), (1000, True), (200, False)]:
+        want = int(np.round(N / 200.0) * 100.0) * (2 if doubled else 1)           # the reference's own expression
+        assert s2.rounded_shuffles(N, doubled) == want
+        blocks = s2.command_blocks(N, doubled)
+        assert blocks == [(i * 100 + 1, i * 100 + 100) for i in range(int(want / 100))]
+        if blocks:
+            assert blocks[0][0] == 1 and blocks[-1][1] == want
+    p = s2.getArgumentParser(argparse.ArgumentParser())
+    mod, argv = s2.driver_call(p.parse_args(["--vertex", "area", "-n", "10000", "-v", "1", "2", "--seed", "7"]))
+    assert mod == "vertex_tfce_multiple_regression_randomise"
+    assert argv == ["-r", "1", "5000", "-s", "area", "-v", "1", "2", "--seed", "7"]
+    mod, argv = s2.driver_call(p.parse_args(["--voxel", "-n", "1000", "-m", "M", "-p", "8"]))
+    assert mod == "voxel_tfce_mediation_randomise" and argv == ["-r", "1", "1000", "-m", "M"]
+    with pytest.raises(NotImplementedError):
+        s2.driver_call(p.parse_args(["--voxel", "-n", "1000", "-glm"]))

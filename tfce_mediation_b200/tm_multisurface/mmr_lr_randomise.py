@@ -33,6 +33,9 @@ def getArgumentParser(ap=ap.ArgumentParser(description=DESCRIPTION)):
     ap.add_argument("--tmitemp", default="tmi_temp", help="Directory written by mmr-lr (default tmi_temp)")
     ap.add_argument("-i", "--input", nargs="+", metavar=('*.csv'),
                     help="Predictor file(s); default: those recorded in tmi_temp/opts.npy")
+    ap.add_argument("-im", "--inputmediation", nargs=3, metavar=('{I|M|Y}', 'pred.csv', 'dep.csv'),
+                    help="Mediation instead of regression (default: tmi_temp/opts.npy): one row per shuffle and surface "
+                         "in perm_maxTFCE_surf{i}_{medtype}_zstat.csv (tm_func.py:269-305)")
     ap.add_argument("--tfce", nargs="+", type=float, help="H E [H E ...]; default: tmi_temp/opts.npy")
     ap.add_argument("--assigntfcesettings", nargs="+", type=int, help="TFCE setting index per surface")
     return ap
@@ -46,13 +49,17 @@ def load_setup(opts):
             sopts = C.load("%s/opts.npy" % tmp).tolist()
         except Exception:
             sopts = None
+    med = opts.inputmediation or (getattr(sopts, "inputmediation", None) if sopts is not None else None)
     inputs = opts.input or (getattr(sopts, "input", None) if sopts is not None else None)
-    if not inputs:
-        raise SystemExit("no predictor files: pass -i or provide tmi_temp/opts.npy")
-    pred_x = None
-    for f in inputs:
-        col = np.genfromtxt(f, delimiter=',')
-        pred_x = col if pred_x is None else np.column_stack([pred_x, col])
+    if med and not opts.input:
+        pred_x = (str(med[0]), np.genfromtxt(med[1], delimiter=','), np.genfromtxt(med[2], delimiter=','))
+    else:
+        if not inputs:
+            raise SystemExit("no predictor files: pass -i / -im or provide tmi_temp/opts.npy")
+        pred_x = None
+        for f in inputs:
+            col = np.genfromtxt(f, delimiter=',')
+            pred_x = col if pred_x is None else np.column_stack([pred_x, col])
     tfce = opts.tfce or (getattr(sopts, "tfce", None) if sopts is not None else None) or [2, 0.67]
     assign = opts.assigntfcesettings or (getattr(sopts, "assigntfcesettings", None) if sopts is not None else None)
     nsurf = 0
@@ -88,6 +95,9 @@ def run(opts):
         off += data.shape[1]
     y = np.ascontiguousarray(np.hstack(datas), dtype=np.float32)
     n = y.shape[0]
+    mediation = isinstance(pred_x, tuple)
+    if mediation:
+        return run_mediation(opts, y, surfs, surfaces, pred_x, start_time)
     X = np.column_stack([np.ones(n), pred_x])
     k = X.shape[1]
     eng = PermutationEngine(y, surfs, two_sided=True)
@@ -111,6 +121,33 @@ def run(opts):
             for c in range(k - 1):
                 C.append_rows("%s/perm_maxTFCE_surf%d_tcon%d.csv" % (outdir, sn, c + 1),
                               allrows[:, c, si, :].reshape(-1), "%f")
+        print("Surfaces %s, permutations %d -> %d took %i seconds." % (surfaces, first, last, int(time() - start_time)))
+
+
+def run_mediation(opts, y, surfs, surfaces, med, start_time):
+    """mmr-lr mediation (tm_mmr_rand_low_ram_parallel.py:190-206 -> tm_func.py:269-305): Sobel z of every shuffle on
+    all surfaces at once, one-sided TFCE, '%f' rows in perm_maxTFCE_surf{i}_{medtype}_zstat.csv."""
+    from ..engine import PermutationEngine
+    medtype, pred_x, depend_y = med
+    n = y.shape[0]
+    eng = PermutationEngine(y, surfs, two_sided=False)
+    first, last = int(opts.permutationrange[0]), int(opts.permutationrange[1])
+    seed = int(opts.seed[0])
+    rank, ws, a, b = C.shard(first, last)
+    outdir = str(opts.path[0])
+    if rank == 0:
+        os.makedirs(outdir, exist_ok=True)
+    idx = []
+    for perm_number in range(a, b + 1):
+        np.random.seed(perm_number + seed)                           # tm_func.py:281-283
+        idx.append(np.random.permutation(list(range(n))))
+    rows = [eng.mediation_block(medtype, pred_x, depend_y, np.stack(idx[i:i + C.BLOCK]))
+            for i in range(0, len(idx), C.BLOCK)]
+    local = np.concatenate(rows, axis=0) if rows else np.zeros((0, len(surfs)), dtype=np.float32)
+    allrows = parallel.gather_rows(local.reshape(local.shape[0], 1, -1))
+    if rank == 0:
+        for si, sn in enumerate(surfaces):
+            C.append_rows("%s/perm_maxTFCE_surf%d_%s_zstat.csv" % (outdir, sn, medtype), allrows[:, 0, si], "%f")
         print("Surfaces %s, permutations %d -> %d took %i seconds." % (surfaces, first, last, int(time() - start_time)))
 
 
