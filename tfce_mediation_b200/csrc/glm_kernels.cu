@@ -23,7 +23,7 @@ static constexpr int BN = 128;      // vertices per tile
 static constexpr int BK = 32;       // subjects per stage
 static constexpr int STAGES = 3;
 static constexpr int kConsumers = 256;
-static constexpr int kGlmThreads = kConsumers; // 8 warps; thread 0 doubles as the copy issuer (a 9th warp would
+static constexpr int kGlmThreads = kConsumers; // 8 warps; lane 0 of each warp doubles as a copy issuer (a 9th warp would
                                                // round the CTA up to 12 warps of registers and cap the tile at 168 regs)
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX
@@ -257,21 +257,26 @@ __global__ void __launch_bounds__(kGlmThreads, 1) glm_tile_kernel(GlmParams p, i
     }
     __syncthreads();
 
-    // issue the bulk copies of chunk kc into its ring slot (thread 0 only)
+    // issue the bulk copies of chunk kc into its ring slot.  Lane 0 of EVERY warp issues the rows warp, warp + 8, ... of
+    // the chunk (8 of the 64 row copies): one thread issuing all 64 took about as long as a warp's share of the chunk's
+    // arithmetic (ncu: half of the stall samples sat on the consumers' wait for the ring), and it skewed warp 0 against
+    // the others.  Warp 0 also posts the expected byte count; the slot's phase cannot complete before it has (the
+    // barrier's one pending arrival), whatever the order in which the copies land.
+    const int lane_i = tid & 31, warp_i = tid >> 5;
     auto issue_chunk = [&](int kc) {
         const int s = kc % STAGES;
         const int round = kc / STAGES;
         mbar_wait(empty + s, (round & 1) ^ 1); // every consumer warp has released the slot
         const int k0 = kc * BK;
         const int rows = min(BK, p.n - k0);
-        mbar_expect_tx(full + s, (uint32_t)rows * (BM * 8 + BN * (uint32_t)sizeof(YT)));
-        for (int kk = 0; kk < rows; ++kk) {
+        if (warp_i == 0) mbar_expect_tx(full + s, (uint32_t)rows * (BM * 8 + BN * (uint32_t)sizeof(YT)));
+        for (int kk = warp_i; kk < rows; kk += kConsumers / 32) {
             bulk_g2s(sA + ((size_t)s * BK + kk) * BM, p.At + (size_t)(k0 + kk) * p.ldA + m0, BM * 8, full + s);
             bulk_g2s(sY + ((size_t)s * BK + kk) * BN, reinterpret_cast<const YT *>(p.Y) + (size_t)(k0 + kk) * p.ldy + v0,
                      BN * (uint32_t)sizeof(YT), full + s);
         }
     };
-    if (tid == 0)
+    if (lane_i == 0)
         for (int kc = 0; kc < STAGES - 1 && kc < nchunks; ++kc) issue_chunk(kc); // prologue: fill the ring
 
     // ===== consumers =====
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(kGlmThreads, 1) glm_tile_kernel(GlmParams p, i
         const int s = kc % STAGES;
         const int round = kc / STAGES;
         // keep STAGES-1 chunks in flight: the slot released by iteration kc-1 is refilled now
-        if (tid == 0 && kc + STAGES - 1 < nchunks) issue_chunk(kc + STAGES - 1);
+        if (lane_i == 0 && kc + STAGES - 1 < nchunks) issue_chunk(kc + STAGES - 1);
         mbar_wait(full + s, round & 1);
         const int rows = min(BK, p.n - kc * BK);
         const double *a_base = sA + (size_t)s * BK * BM + tm * 8;
@@ -359,14 +364,14 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
         mbar_wait(empty + s, (round & 1) ^ 1);
         const int k0 = kc * DK;
         const int rows = min(DK, p.n - k0);
-        mbar_expect_tx(full + s, (uint32_t)rows * (DM * 8 + DN * (uint32_t)sizeof(YT)));
-        for (int kk = 0; kk < rows; ++kk) {
+        if (warp == 0) mbar_expect_tx(full + s, (uint32_t)rows * (DM * 8 + DN * (uint32_t)sizeof(YT)));
+        for (int kk = warp; kk < rows; kk += 8) { // lane 0 of every warp issues an eighth of the row copies (see glm_tile_kernel)
             bulk_g2s(sA + ((size_t)s * DK + kk) * DPA, p.At + (size_t)(k0 + kk) * p.ldA + m0, DM * 8, full + s);
             bulk_g2s(sY + ((size_t)s * DK + kk) * DPY, reinterpret_cast<const YT *>(p.Y) + (size_t)(k0 + kk) * p.ldy + v0,
                      DN * (uint32_t)sizeof(YT), full + s);
         }
     };
-    if (tid == 0)
+    if (lane == 0)
         for (int kc = 0; kc < DSTAGES - 1 && kc < nchunks; ++kc) issue_chunk(kc);
 
     const int wm = warp >> 2, wn = warp & 3;      // warp tile: rows wm*32.., cols wn*32..
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
     for (int kc = 0; kc < nchunks; ++kc) {
         const int s = kc % DSTAGES;
         const int round = kc / DSTAGES;
-        if (tid == 0 && kc + DSTAGES - 1 < nchunks) issue_chunk(kc + DSTAGES - 1);
+        if (lane == 0 && kc + DSTAGES - 1 < nchunks) issue_chunk(kc + DSTAGES - 1);
         mbar_wait(full + s, round & 1);
         const int rows = min(DK, p.n - kc * DK);
         const double *a_st = sA + (size_t)s * DK * DPA + wm * 32 + g;
