@@ -425,7 +425,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config2")
-    ap.add_argument("--block", type=int, default=512, help="shuffles per step per GPU")
+    ap.add_argument("--block", type=int, default=1024, help="shuffles per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -41,6 +41,7 @@ struct tmb_graph {
     int32_t *d_vmap = nullptr;          // internal -> caller index (nullptr: identity)
     int32_t *d_ell = nullptr;           // fixed-width adjacency rows (low-degree graphs)
     int32_t ell_width = 0;
+    int32_t max_degree = 0;
     std::vector<int32_t> vmap;          // host copy
     bool symmetric = true;
     tmb_plan *self_plan = nullptr; // lazily created single-surface plan for tmb_tfce_run
@@ -243,6 +244,7 @@ extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, co
             if ((e = cudaMemcpy(g->d_ell, ell.data(), sizeof(int32_t) * ell.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
                 return fail("memcpy", e);
             g->ell_width = width;
+            g->max_degree = (int32_t)maxdeg;
         }
     }
     if (!g->vmap.empty()) {
@@ -398,10 +400,10 @@ extern "C" int tmb_plan_destroy(tmb_plan *p) {
                         100.0 * t[20] / tot, 100.0 * t[21] / tot, 100.0 * t[22] / tot, 100.0 * t[23] / tot, 100.0 * t[24] / tot);
 
         }
-        if (p->use_basin && !p->pipe_ok) {
+        if (p->use_basin || p->pipe_ok) {
             double tot = 0;
             for (int i = 0; i < 7; ++i) tot += (double)t[i];
-            fprintf(stderr, "  per-level share of I1 / I2 (levels 1..127, %% of total):\n");
+            fprintf(stderr, "  per-level share of I1 / I2 (pipeline: F2 / F3+F1) (levels 1..127, %% of total):\n");
             for (int l = 1; l < 128; ++l)
                 if (t[16 + l] || t[144 + l])
                     fprintf(stderr, "   L%-3d %5.2f %5.2f\n", l, 100.0 * t[16 + l] / tot, 100.0 * t[144 + l] / tot);
@@ -552,6 +554,8 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
         pp.want_vertex_pass = (tfce_pos || tfce_neg || p->pipe_weights) ? 1 : 0;
         pp.slot_ws = p->d_pipe_slots; pp.slot_stride = p->pipe_slot_stride; pp.work_counter = p->d_counter;
         pp.timing = p->d_timing;
+        pp.max_degree = 0;
+        for (int s = 0; s < p->S; ++s) pp.max_degree = std::max(pp.max_degree, (int)p->graphs[s]->max_degree);
         if (launch_tfce_pipeline(pp, p->pipe_slots, stream)) return 1;
         TableSet sub;
         sub.ns = pp.tab_ns; sub.delta = pp.tab_delta; sub.T = pp.tab_T; sub.HH = pp.tab_HH; sub.status = pp.tab_status;

@@ -101,6 +101,7 @@ struct PipeParams {
     const float *tab_HH;
     const int32_t *tab_status;
     int flags;              // bit 2: statistic rows are in the graphs' internal vertex order
+    int max_degree;         // largest vertex degree over the plan's graphs (triangle meshes: 6 -> the ascent kernel skips the two pad slots)
     int32_t Vmax;
     // per-item buffers
     int64_t vstride;        // elements per work item in the per-vertex arrays

@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(256) pipe_levels_kernel(PipeParams P, int chun
 // ascent target and earlier-neighbour mask of vertex v; returns the vertex's level code when it is a peak, else -1
 // (Staging the CTA's own 256 level codes in shared memory -- 81% of the neighbour lookups fall into the vertex's own
 //  block, scripts/probe_window.py -- was measured slower than the L1 gathers: 1.26 vs 1.17 ms.)
+// kSix: every row has at most six neighbours in one 8-slot chunk (triangle meshes): slots 6 and 7 are padding and skipped.
+template <bool kSix>
 __device__ __forceinline__ int ascent_of_vertex(const PipeParams &P, const SurfDesc &sd, size_t base, int v) {
     if (v >= sd.V) return -1;
     const unsigned char *__restrict__ lev8 = P.lev8 + base;
@@ -200,15 +202,16 @@ __device__ __forceinline__ int ascent_of_vertex(const PipeParams &P, const SurfD
     const unsigned sign = (unsigned)cv & 0x80u;
     const unsigned mykey = ((unsigned)lev << 24) | (unsigned)v;
     const int4 *__restrict__ row = reinterpret_cast<const int4 *>(sd.ell + (size_t)v * sd.ell_width);
-    const int nch = sd.ell_width >> 3;
+    const int nch = kSix ? 1 : (sd.ell_width >> 3);
+    constexpr int kSlots = kSix ? 6 : 8;
     for (int c = 0; c < nch; ++c) {
         const int4 r0 = __ldg(row + 2 * c), r1 = __ldg(row + 2 * c + 1);
         const int nb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
         unsigned ca[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ca[j] = nb[j] >= 0 ? (unsigned)lev8[nb[j]] : 0u;
+        for (int j = 0; j < kSlots; ++j) ca[j] = nb[j] >= 0 ? (unsigned)lev8[nb[j]] : 0u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < kSlots; ++j) {
             const unsigned x = ca[j] ^ sign;                 // 1..127: active, same sign
             const unsigned la = (x - 1u) < 127u ? x : 255u;
             bestkey = min(bestkey, (la << 8) | (unsigned)(c * 8 + j));
@@ -227,6 +230,7 @@ __device__ __forceinline__ int ascent_of_vertex(const PipeParams &P, const SurfD
     return best == v ? cv : -1;
 }
 
+template <bool kSix>
 __global__ void __launch_bounds__(256) pipe_ascent_kernel(PipeParams P, int chunks) {
     __shared__ int sPeaks, sBase;
     int item, chunk, s, b;
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(256) pipe_ascent_kernel(PipeParams P, int chun
     __syncthreads();
     const int v = chunk * 256 + threadIdx.x;
     const size_t base = (size_t)item * P.vstride;
-    const int peak_code = ascent_of_vertex(P, sd, base, v);
+    const int peak_code = ascent_of_vertex<kSix>(P, sd, base, v);
     // peaks get compact basin ids: one returning atomic per CTA on the map's counter
     int local = -1;
     if (peak_code >= 0) local = atomicAdd(&sPeaks, 1);
@@ -1115,6 +1119,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                         else if (it == 3) bas = (int)((lev & 1) ? eqB[3] : eqA[3]);
                         else bas = (int)elist[ie];
                         r = pf_find(bparent, bas);
+                        if ((P.flags & 2048) && r != bas) bparent[bas] = r;
                     }
                     // Late levels send most vertices to a few giant roots: same-address shared-memory atomics would
                     // serialise.  The lanes that agree with the first active lane's root are counted by one ballot.
@@ -1133,12 +1138,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                     const int bb = kSmall ? (int)__ldcg(al + i) : (int)al[i];
                     if (hooklev[bb] == lev) {
                         const int rr = pf_find(bparent, bb);
+                        if (P.flags & 2048) bparent[bb] = rr;
                         atomicAdd(bsize + rr, bsize[bb]);
                         atomicMax(racc + rr, racc[bb]); // sums are >= 0: integer order == float order
                     }
                 }
             }
             __syncthreads();
+            if (P.timing && tid == 0) atomicAdd(P.timing + 16 + lev, (unsigned long long)(clock64() - tk));
             PIPE_TICK(4)
             // ================= F3: this level's increment of every live root; next live list ==============
             prefetch_pairs(lev + 2); // this level's registers are free again
@@ -1190,6 +1197,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             __syncthreads();
             if (tid == 0) sNalive[cur] = 0; // becomes the next "next" list (first touched again after the next barrier)
             cur ^= 1;
+            if (P.timing && tid == 0) atomicAdd(P.timing + 144 + lev, (unsigned long long)(clock64() - tk));
             PIPE_TICK(5)
         }
         // the last level's pending increments
@@ -1291,7 +1299,8 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
     const int chunks = (p.Vmax + 255) / 256;
     TMB_REQUIRE(p.B <= 65535 && p.S <= 65535, "tfce pipeline: at most 65535 rows and surfaces per launch (got %d, %d)", p.B, p.S);
     pipe_levels_kernel<<<dim3(chunksA, p.B, p.S), 256, 0, stream>>>(p, chunksA);
-    pipe_ascent_kernel<<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
+    if (p.max_degree > 0 && p.max_degree <= 6) pipe_ascent_kernel<true><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
+    else pipe_ascent_kernel<false><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
     pipe_basin_kernel<<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
     const int chunksD = (p.Vmax + kCountChunk - 1) / kCountChunk;
     if (p.want_vertex_pass) pipe_count_kernel<true><<<dim3(chunksD, p.B, p.S), 256, 0, stream>>>(p, chunksD);
@@ -1304,10 +1313,12 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
         const int grid = items < num_slots / 2 ? items : num_slots / 2;
         pipe_sweep_kernel<1024, 1, false><<<grid, 1024, smem, stream>>>(p, smem);
     } else {
-        // max-only path.  Default: one 1,024-thread CTA per SM (large geometry).  TMB_PIPE_GEOM=2: two 512-thread CTAs
-        // per SM (small geometry) first, then one launch of the large geometry for the maps the small one could not
-        // hold -- measured 8% faster on 512 maps, 1% on 1,024 (its longer maps cost more at the tail of the launch).
-        int geom = 1;
+        // max-only path.  Default (TMB_PIPE_GEOM=2): two 512-thread CTAs per SM (small geometry) that hide each other's
+        // barrier intervals, then one launch of the large geometry (one 1,024-thread CTA per SM) for the maps the small
+        // one could not hold.  TMB_PIPE_GEOM=1: large geometry only.  Measured on config 2 (B200, whole TFCE stage):
+        // 1,024 maps 9.15 -> 9.04 ms, 2,048 maps 18.05 -> 17.20 ms (the small geometry's longer maps cost more at the
+        // tail of a launch, so it pays with more maps per launch).
+        int geom = 2;
         if (const char *g = getenv("TMB_PIPE_GEOM")) geom = atoi(g);
         const int smem_large = 196 * 1024, smem_small = 94 * 1024;
         TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<1024, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_large));
