@@ -141,6 +141,18 @@ int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, 
                   const double *G_dev, const double *d_dev, int P, int r, int rp, int row0, int nrows,
                   double dof, const double *yy_dev, float *t32_dev, double *t64_dev, int64_t ldt,
                   int nan_to_zero, void *stream);
+/* F statistics of pyfunc.py:2282-2401 glm_typeI (the tm-models GLM branch, tmanalysis/tm_models_randomise.py:197-272)
+ * for P designs at once, from ONE fit per design: operands as in tmb_glm_tstat (centred designs, r = k-1 regressors).
+ * Tested variable i covers regressor rows [var_lo[i], var_lo[i] + var_k[i]) (host arrays, nvar <= 8); M_dev float64
+ * [P, sum_i var_k[i]^2] holds, per design, the matrices inv(C[S_i, S_i]) one after the other, C = (X'X)^-1, because
+ * RSS_without_i - RSS = b_S' inv(C_SS) b_S.  Output rows per design (ldt-strided, float32 and/or float64):
+ *   [model F = ((TSS-RSS)/r) / (RSS/dof)  -- only when want_model != 0],  then per variable
+ *   F_i = (RSS_without_i - RSS) / ((RSS/dof) * var_k[i])                  (pyfunc.py:2336-2354). */
+int tmb_glm_fstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev, int64_t ldA,
+                  const double *G_dev, const double *M_dev, int P, int r, int rp, int nvar, const int32_t *var_lo,
+                  const int32_t *var_k, int want_model, double dof, const double *yy_dev, float *f32_dev,
+                  double *f64_dev, int64_t ldt, int nan_to_zero, void *stream);
+
 /* Stacked pseudo-inverses of P row-permuted copies of ONE design (the permutation loop of
  * vertex_tfce_multiple_regression_randomise.py:104-106, `nx = X[np.random.permutation(...)]`): permuting whole rows
  * permutes the columns of pinv(X), so At[k, p*rp + i] = pinv[i, perm_idx[p, k]] is a gather done on the device.

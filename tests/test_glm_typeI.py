@@ -1,0 +1,191 @@
+"""tm-models GLM statistics: pyfunc.py:2282-2401 glm_typeI and the GLM branch of
+tmanalysis/tm_models_randomise.py:197-272.  CPU: the oracle restatement against the golden fixture produced by the real
+reference (tests/golden/make_golden_glm.py) and the host algebra of the one-fit F formulation.  GPU: the fused F/t
+kernels, the batched block and the driver against the oracle pipeline."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from tests import helpers
+from tfce_mediation_b200 import synth
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+F64_TOL = 1e-10        # |delta| <= tol * max(1, |value|) for float64 statistics (BASELINE.json north_star)
+
+
+def _golden():
+    g = np.load(os.path.join(G, "glm_typeI.npz"))
+    return g, [g["exog0"], g["exog1"], g["exog2"]]
+
+
+def _close64(got, want):
+    return np.all(np.abs(got - want) <= F64_TOL * np.maximum(1.0, np.abs(want)))
+
+
+# ------------------------------------------------------------------------------------------- CPU
+def test_oracle_glm_typeI_matches_reference_golden():
+    g, exog = _golden()
+    F, Fvar, T = oracle.glm_typeI(g["data"], exog, g["cov"], output_tvalues=True)
+    assert np.array_equal(F, g["F"]) and np.array_equal(Fvar, g["Fvar"]) and np.array_equal(T, g["T"])
+    F0, Fvar0, T0 = oracle.glm_typeI(g["data"], exog, None, output_tvalues=True)
+    assert np.array_equal(F0, g["F_nocov"]) and np.array_equal(Fvar0, g["Fvar_nocov"]) and np.array_equal(T0, g["T_nocov"])
+    for p, r in enumerate(g["perms"]):
+        assert np.array_equal(oracle.glm_typeI(g["data"], exog, g["cov"], rand_array=r)[1], g["perm_Fvar"][p])
+        assert np.array_equal(oracle.glm_typeI(g["data"], exog, g["cov"], output_fvalues=False, output_tvalues=True,
+                                               rand_array=r), g["perm_T"][p])
+
+
+def test_extra_sum_of_squares_identity_host():
+    """RSS_without_S - RSS == b_S' inv(C_SS) b_S with C = inv(X'X) on centred designs: the algebra tmb_glm_fstat uses."""
+    from tfce_mediation_b200.engine import design_stack, fstat_blocks
+    from tfce_mediation_b200.pyfunc import typeI_design
+    g, exog = _golden()
+    y = g["data"].astype(np.float64)
+    X, kvars = typeI_design(exog, g["cov"], y.shape[0])
+    assert kvars == [1, 2, 1] and X.shape[1] == 7
+    st = design_stack(X[None], center=True)
+    b = st["pinv"][0] @ y                                                  # [r, V] slopes
+    var_lo = [0, 1, 3]
+    M = fstat_blocks(st["G"], var_lo, kvars)[0]
+    off = 0
+    for i, (lo, k) in enumerate(zip(var_lo, kvars)):
+        Mi = M[off:off + k * k].reshape(k, k); off += k * k
+        num = np.einsum("av,ab,bv->v", b[lo:lo + k], Mi, b[lo:lo + k])
+        rss_full = oracle.lstsq_residual(X, y)[1]
+        rss_red = oracle.lstsq_residual(np.delete(X, np.s_[1 + lo:1 + lo + k], 1), y)[1]
+        assert np.allclose(num, rss_red - rss_full, rtol=1e-9, atol=1e-9)
+        F = num / (rss_full / (y.shape[0] - X.shape[1]) * k)
+        assert np.allclose(F, g["Fvar"][i], rtol=1e-9, atol=1e-9)
+
+
+def test_rand_blocks_follows_reference_rng_calls():
+    from tfce_mediation_b200.pyfunc import check_blocks, rand_blocks
+    blocks = np.array(["a", "b", "a", "c", "b", "c", "a", "b", "c"])
+    assert check_blocks(blocks) is True
+    np.random.seed(5)
+    got = rand_blocks(blocks, True)
+    np.random.seed(5)
+    idx = np.arange(9)
+    want = np.concatenate([np.random.permutation(idx[blocks == b]) for b in np.random.permutation(list(np.unique(blocks)))])
+    assert np.array_equal(got, want) and sorted(got.tolist()) == list(range(9))
+    uneq = np.array(["a", "a", "b"])
+    assert check_blocks(uneq) is False
+    r = rand_blocks(uneq, False)
+    assert sorted(r[:2].tolist()) == [0, 1] and r[2] == 2
+
+
+# ------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_glm_typeI_dropin_matches_reference_golden():
+    from tfce_mediation_b200 import pyfunc
+    g, exog = _golden()
+    F, Fvar, T = pyfunc.glm_typeI(g["data"], exog, dmy_covariates=g["cov"], output_tvalues=True, verbose=False)
+    assert _close64(Fvar, g["Fvar"]) and _close64(T, g["T"])
+    # The MODEL F of float32 data carries float32 noise in the reference itself: pyfunc.py:2331 accumulates SS_Total
+    # with numpy float32 arithmetic (mean, squares and pairwise sum of the float32 data), the residual SS in float64.
+    # The GPU forms both in float64, so on float32 data the model F agrees to float32 accuracy (1e-5, the north star's
+    # fp32 tolerance) and on float64 data to 1e-10.  The per-variable F -- the statistic the permutation loop uses
+    # (tm_models_randomise.py:206-210) -- is a difference in which SS_Total cancels, and agrees to 1e-10 either way.
+    assert np.allclose(F, g["F"], rtol=1e-5, atol=0)
+    F64, Fvar64 = pyfunc.glm_typeI(g["data"].astype(np.float64), exog, dmy_covariates=g["cov"], verbose=False)
+    assert _close64(F64, g["F_f64"]) and _close64(Fvar64, g["Fvar_f64"])
+    F0, Fvar0 = pyfunc.glm_typeI(g["data"], exog, verbose=False)
+    assert np.allclose(F0, g["F_nocov"], rtol=1e-5, atol=0) and _close64(Fvar0, g["Fvar_nocov"])
+    for p, r in enumerate(g["perms"][:3]):
+        Fp = pyfunc.glm_typeI(g["data"], exog, dmy_covariates=g["cov"], verbose=False, rand_array=r)[1]
+        assert _close64(Fp, g["perm_Fvar"][p])
+        Tp = pyfunc.glm_typeI(g["data"], exog, dmy_covariates=g["cov"], output_fvalues=False, output_tvalues=True,
+                              verbose=False, rand_array=r)
+        assert _close64(Tp, g["perm_T"][p])
+
+
+def _glm_state(n=40, seed=9):
+    v, f, csr = helpers.ico(3)
+    keep_lh, keep_rh = synth.cap_mask(v, 600), synth.cap_mask(-v, 590)
+    dens = synth.vertex_density(synth.kring_csr(csr, 2))
+    y = np.hstack([synth.subject_data(n, csr, seed, 2)[:, keep_lh], synth.subject_data(n, csr, seed + 1, 2)[:, keep_rh]])
+    rs = np.random.RandomState(seed)
+    grp = rs.randint(0, 3, n)
+    exog = [rs.standard_normal((n, 1)), np.column_stack([(grp == 1) * 1.0, (grp == 2) * 1.0])]
+    cov = rs.standard_normal((n, 2))
+    y = y.astype(np.float32)
+    y[:, :100] += np.float32(0.7) * exog[0].astype(np.float32)
+    return dict(v=v, csr=csr, keep_lh=keep_lh, keep_rh=keep_rh, dens=dens, y=y, exog=exog, cov=cov, n=n)
+
+
+def _oracle_rows(st, perms, stat):
+    run = helpers.oracle_run(2, 0.67, st["csr"])
+    nlh = int(st["keep_lh"].sum())
+    rows_f, rows_t = [], []
+    for r in perms:
+        if stat in ("f", "both"):
+            Fvar = oracle.glm_typeI(st["y"], st["exog"], st["cov"], rand_array=r)[1]
+            rows_f.append([oracle.perm_max_vertex(Fvar[j], nlh, st["keep_lh"], st["keep_rh"], run, run, st["dens"], st["dens"])
+                           for j in range(Fvar.shape[0])])
+        if stat in ("t", "both"):
+            T = oracle.glm_typeI(st["y"], st["exog"], st["cov"], output_fvalues=False, output_tvalues=True, rand_array=r)
+            rows_t.append([[oracle.perm_max_vertex(T[j] * s, nlh, st["keep_lh"], st["keep_rh"], run, run, st["dens"], st["dens"])
+                            for s in (1, -1)] for j in range(1, 4)])
+    return np.array(rows_f), np.array(rows_t)
+
+
+@pytest.mark.gpu
+def test_glm_typeI_block_maxima_match_oracle_pipeline():
+    from tfce_mediation_b200.engine import PermutationEngine
+    from tfce_mediation_b200.pyfunc import typeI_design
+    from tfce_mediation_b200.tmanalysis import _common as C
+    st = _glm_state()
+    adj = synth.csr_to_lists(st["csr"])
+    surfs = [C.masked_surface(adj, 2, 0.67, st["keep_lh"], st["dens"], 0),
+             C.masked_surface(adj, 2, 0.67, st["keep_rh"], st["dens"], int(st["keep_lh"].sum()))]
+    eng = PermutationEngine(st["y"], surfs, two_sided=True)
+    X, kvars = typeI_design(st["exog"], st["cov"], st["n"])
+    perms = np.stack([oracle.permutation_indices(300 + p, st["n"]) for p in range(5)])
+    f, t = eng.glm_typeI_block(X, kvars, perms, stat="both")
+    want_f, want_t = _oracle_rows(st, perms, "both")
+    assert f.shape == (5, 2, 2) and t.shape == (5, 3, 2, 2)
+    assert np.allclose(f.max(axis=2), want_f, rtol=1e-5, atol=0)
+    assert np.allclose(t.max(axis=2), want_t, rtol=1e-5, atol=0)
+
+
+def _obj(lists):
+    a = np.empty(len(lists), dtype=object)
+    for i, l in enumerate(lists):
+        a[i] = list(l)
+    return a
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gstat", ["f", "t", "all"])
+def test_tm_models_randomise_glm_driver_rows(tmp_path, monkeypatch, gstat):
+    from tfce_mediation_b200.tmanalysis import tm_models_randomise as drv
+    st = _glm_state()
+    d = os.path.join(str(tmp_path), "tmtemp_GLM_area")
+    os.makedirs(d)
+    adj = synth.csr_to_lists(st["csr"])
+    np.save(d + "/exog_flat.npy", np.column_stack(st["exog"])); np.save(d + "/exog_shape.npy", np.array([1, 2]))
+    np.save(d + "/varnames.npy", np.array(["age", "group"])); np.save(d + "/gstat.npy", np.array(gstat))
+    np.save(d + "/data.npy", st["y"]); np.save(d + "/optstfce.npy", np.array([2, 0.67]))
+    np.save(d + "/dmy_covariates.npy", st["cov"]); np.save(d + "/num_vertex_lh.npy", int(st["keep_lh"].sum()))
+    np.save(d + "/mask_lh.npy", st["keep_lh"]); np.save(d + "/mask_rh.npy", st["keep_rh"])
+    np.save(d + "/adjac_lh.npy", _obj(adj), allow_pickle=True); np.save(d + "/adjac_rh.npy", _obj(adj), allow_pickle=True)
+    np.save(d + "/vdensity_lh.npy", st["dens"]); np.save(d + "/vdensity_rh.npy", st["dens"])
+    monkeypatch.chdir(tmp_path)
+    opts = drv.getArgumentParser(argparse.ArgumentParser()).parse_args(["-r", "1", "4", "-s", "area", "-glm", "--seed", "3"])
+    drv.run(opts)
+    perms = [oracle.permutation_indices(p * 1000 + 3, st["n"]) for p in range(1, 5)]
+    want_f, want_t = _oracle_rows(st, perms, {"f": "f", "t": "t", "all": "both"}[gstat])
+    out = "output_GLM_area/perm_GLM"
+    if gstat != "t":
+        for j, name in enumerate(["age", "group"]):
+            got = np.array([float(l) for l in open("%s/perm_Fstat_%s_TFCE_maxVertex.csv" % (out, name))])
+            assert np.allclose(got, want_f[:, j], rtol=1e-5, atol=6e-5)
+    else:
+        assert not os.path.exists("%s/perm_Fstat_age_TFCE_maxVertex.csv" % out)
+    if gstat != "f":
+        for j in range(3):
+            got = np.array([float(l) for l in open("%s/perm_Tstat_con%d_TFCE_maxVertex.csv" % (out, j + 1))])
+            assert np.allclose(got, want_t[:, j, :].reshape(-1), rtol=1e-5, atol=6e-5)

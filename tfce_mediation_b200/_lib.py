@@ -45,6 +45,8 @@ SIGNATURES = {
     "tmb_glm_sumsq": (_int, [_vp, _int, _int, _i64, _i64, _int, _vp, _vp, _vp]),
     "tmb_glm_tstat": (_int, [_vp, _int, _int, _i64, _i64, _vp, _i64, _vp, _vp, _int, _int, _int, _int, _int, _f64,
                              _vp, _vp, _vp, _i64, _int, _vp]),
+    "tmb_glm_fstat": (_int, [_vp, _int, _int, _i64, _i64, _vp, _i64, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _int,
+                             _f64, _vp, _vp, _vp, _i64, _int, _vp]),
     "tmb_glm_pack_rowperm": (_int, [_vp, _int, _int, _vp, _int, _int, _vp, _i64, _vp]),
     "tmb_glm_beta": (_int, [_vp, _int, _int, _i64, _i64, _vp, _i64, _int, _vp, _i64, _vp]),
     "tmb_glm_direct": (_int, [_vp, _int, _int, _i64, _i64, _vp, _vp, _int, _vp, _f64, _f64, _vp, _vp, _vp, _i64,

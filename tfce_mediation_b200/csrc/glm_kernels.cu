@@ -72,10 +72,13 @@ struct GlmParams {
     const double *yy;
     float *t32; double *t64; int64_t ldt;
     int nan_to_zero;
-    int mode;                           // 0 t-stat, 1 betas, 2 sobel
+    int mode;                           // 0 t-stat, 1 betas, 2 sobel, 3 F statistics
     // sobel: rows [0, rA) of each design group are path A, rows [rA, rA+rB) path B
     const double *GB; const double *dB; int rA, rB, rowA, rowB; double dofB;
     const double *ta_scalar; int alg;
+    // F statistics (mode 3): per design the inverse blocks M_i = inv((X'X)^-1[S_i, S_i]) of every tested variable,
+    // stored one after the other (k_i x k_i each, msz doubles per design); variable i covers rows [var_lo[i], +var_k[i])
+    const double *M; int msz, nvar; int var_lo[8], var_k[8];
 };
 
 // sum_{a,b in [lo,lo+r)} acc[g*RP+a][c] * G[(a-lo)*r + (b-lo)] * acc[g*RP+b][c]; every loop is fully
@@ -184,6 +187,49 @@ __device__ __forceinline__ void epilogue(const GlmParams &p, const double (&acc)
                 }
                 const size_t off = ((size_t)perm * p.nrows + (a - p.row0)) * p.ldt;
                 store_tile_row(p.t32, p.t64, off, v0, tn, o32, o64);
+            }
+        } else if (p.mode == 3) {
+            // F statistics of pyfunc.py:2282-2401 glm_typeI: model F = ((TSS - RSS)/(k-1)) / (RSS/(n-k)) and per tested
+            // variable i the partial F = ((RSS_without_i - RSS)/k_i) / (RSS/(n-k)).  The extra sum of squares of a set S
+            // of regressors needs no second fit: RSS_without_S - RSS = b_S' inv(C_SS) b_S with C = (X'X)^-1.
+            // Output rows: [model F when row0 == 0], then one row per variable.
+            const int r = p.r;
+            const double *G = p.G + (size_t)perm * r * r;
+            double ssb[TN], ms[TN];
+#pragma unroll
+            for (int c = 0; c < TN; ++c) {
+                ssb[c] = quad_form<RP>(acc, g, c, G, 0, r);
+                ms[c] = __ddiv_rn(yy[c] - ssb[c], p.dof);
+            }
+            const int first = p.row0 == 0 ? 1 : 0;
+            float o32[TN];
+            double o64[TN];
+            if (first) {
+#pragma unroll
+                for (int c = 0; c < TN; ++c) {
+                    double f = __ddiv_rn(__ddiv_rn(ssb[c], (double)r), ms[c]);
+                    if (p.nan_to_zero && f != f) f = 0.0;
+                    if (tile_col(v0, tn, c) >= p.V) f = 0.0;
+                    o64[c] = f;
+                    o32[c] = __double2float_rn(f);
+                }
+                store_tile_row(p.t32, p.t64, (size_t)perm * p.nrows * p.ldt, v0, tn, o32, o64);
+            }
+            const double *M = p.M + (size_t)perm * p.msz;
+#pragma unroll 1
+            for (int i = 0; i < p.nvar; ++i) {
+                const int lo = p.var_lo[i], ki = p.var_k[i];
+#pragma unroll
+                for (int c = 0; c < TN; ++c) {
+                    const double num = quad_form<RP>(acc, g, c, M, lo, ki);
+                    double f = __ddiv_rn(num, __dmul_rn(ms[c], (double)ki));
+                    if (p.nan_to_zero && f != f) f = 0.0;
+                    if (tile_col(v0, tn, c) >= p.V) f = 0.0;
+                    o64[c] = f;
+                    o32[c] = __double2float_rn(f);
+                }
+                store_tile_row(p.t32, p.t64, ((size_t)perm * p.nrows + first + i) * p.ldt, v0, tn, o32, o64);
+                M += ki * ki;
             }
         } else { // sobel (pyfunc.py:130-162)
             const int rA = p.rA, rB = p.rB;
@@ -658,6 +704,28 @@ extern "C" int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, in
     p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.G = G_dev; p.d = d_dev;
     p.P = P; p.r = r; p.rp = rp; p.row0 = row0; p.nrows = nrows; p.dof = dof; p.yy = yy_dev;
     p.t32 = t32_dev; p.t64 = t64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 0;
+    return launch_glm(p, (cudaStream_t)stream);
+}
+
+extern "C" int tmb_glm_fstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev,
+                             int64_t ldA, const double *G_dev, const double *M_dev, int P, int r, int rp, int nvar,
+                             const int32_t *var_lo, const int32_t *var_k, int want_model, double dof,
+                             const double *yy_dev, float *f32_dev, double *f64_dev, int64_t ldt, int nan_to_zero,
+                             void *stream) {
+    TMB_REQUIRE(Y_dev && At_dev && G_dev && yy_dev && (f32_dev || f64_dev), "tmb_glm_fstat: null pointer");
+    TMB_REQUIRE(n > 0 && V > 0 && P > 0 && r >= 1 && r <= rp && nvar >= 0 && nvar <= 8 && (nvar == 0 || (M_dev && var_lo && var_k)) &&
+                    (nvar > 0 || want_model),
+                "tmb_glm_fstat: bad shape (n=%d V=%lld P=%d r=%d rp=%d nvar=%d)", n, (long long)V, P, r, rp, nvar);
+    GlmParams p{};
+    if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
+    p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.G = G_dev; p.M = M_dev;
+    p.P = P; p.r = r; p.rp = rp; p.row0 = want_model ? 0 : 1; p.nrows = nvar + (want_model ? 1 : 0); p.dof = dof; p.yy = yy_dev;
+    p.t32 = f32_dev; p.t64 = f64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 3; p.nvar = nvar;
+    for (int i = 0; i < nvar; ++i) {
+        TMB_REQUIRE(var_lo[i] >= 0 && var_k[i] >= 1 && var_lo[i] + var_k[i] <= r,
+                    "tmb_glm_fstat: variable %d covers rows [%d, %d) of %d", i, var_lo[i], var_lo[i] + var_k[i], r);
+        p.var_lo[i] = var_lo[i]; p.var_k[i] = var_k[i]; p.msz += var_k[i] * var_k[i];
+    }
     return launch_glm(p, (cudaStream_t)stream);
 }
 

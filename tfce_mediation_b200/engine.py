@@ -203,6 +203,20 @@ def design_stack(Xs, center=True):
                 centered=bool(center))
 
 
+def fstat_blocks(G, var_lo, var_k):
+    """Per design the matrices inv(C[S_i, S_i]), C = inv(G), of every tested variable i (regressor rows
+    [var_lo[i], var_lo[i] + var_k[i])), one after the other: float64 [P, sum k_i^2].  With them the extra sum of
+    squares of dropping variable i is b_S' inv(C_SS) b_S (no second fit), which is what pyfunc.py:2346-2351 obtains
+    from the residual SS of the reduced design."""
+    G = np.asarray(G, dtype=np.float64)
+    C = np.linalg.inv(G)
+    parts = []
+    for lo, k in zip(var_lo, var_k):
+        lo, k = int(lo), int(k)
+        parts.append(np.linalg.inv(C[:, lo:lo + k, lo:lo + k]).reshape(G.shape[0], k * k))
+    return np.ascontiguousarray(np.concatenate(parts, axis=1)) if parts else np.zeros((G.shape[0], 0))
+
+
 def row_permuted_stack(X, perm_idx, center=True):
     """Same as design_stack for designs X[perm_idx[p]] (whole rows permuted): X'X is invariant, so
     one pseudo-inverse is formed and its columns are gathered."""
@@ -311,10 +325,10 @@ class PermutationEngine(object):
             t64 = self.to_caller_order(t64) if t64 is not None else None
         return (t32, t64) if want_f64 else t32
 
-    def tstat_rowperm(self, X, perm_idx):
-        """Fused fit+t for the designs X[perm_idx[p]] (whole rows permuted): the host sends only the index rows;
-        the stacked pseudo-inverses are gathered on the device (tmb_glm_pack_rowperm).  X float64 [n, k] with the
-        intercept in column 0.  Returns CUDA float32 [P, k-1, ld] in the engine's internal column order."""
+    def _rowperm_operands(self, X, perm_idx):
+        """Device operands for the designs X[perm_idx[p]] (whole rows permuted): the host sends only the index rows;
+        the stacked pseudo-inverses are gathered on the device (tmb_glm_pack_rowperm).  X'X and its inverse are
+        invariant under row permutations, so G and diag(inv(X'X)) are one row repeated P times."""
         import torch
         X = np.ascontiguousarray(X, dtype=np.float64)
         perm_idx = np.asarray(perm_idx)
@@ -327,27 +341,111 @@ class PermutationEngine(object):
             st = design_stack(X[None], center=True)
             r = st["r"]
             base = dict(r=r, rp=_rp_for(r), dof=st["dof"], G=st["G"][0], d=st["d"][0],
-                        pinv=torch.from_numpy(np.ascontiguousarray(st["pinv"][0])).to(self.device), rep={})
+                        pinv=torch.from_numpy(np.ascontiguousarray(st["pinv"][0])).to(self.device), rep={}, fmat={})
             self._rowperm_base = {key: base}            # one design at a time (the drivers' loop)
         r, rp = base["r"], base["rp"]
         rep = base["rep"].get(P)
-        if rep is None:                                  # X'X and diag(inv(X'X)) are invariant: one row, repeated
+        if rep is None:
             rep = (torch.from_numpy(np.repeat(base["G"][None], P, axis=0)).to(self.device),
                    torch.from_numpy(np.repeat(base["d"][None], P, axis=0)).to(self.device))
             base["rep"] = {P: rep}
+            base["fmat"] = {}
         idx_d = self._upload("perm_idx", np.ascontiguousarray(perm_idx, dtype=np.int32))
         ldA = round_up(P * rp, TILE_M)
         At_d = torch.empty((n, ldA), dtype=torch.float64, device=self.device)
-        L = _lib.lib()
-        stream = _lib.current_stream()
-        _lib.check(L.tmb_glm_pack_rowperm(_lib.ptr(base["pinv"]), r, n, _lib.ptr(idx_d), P, rp, _lib.ptr(At_d), ldA, stream))
+        _lib.check(_lib.lib().tmb_glm_pack_rowperm(_lib.ptr(base["pinv"]), r, n, _lib.ptr(idx_d), P, rp, _lib.ptr(At_d),
+                                                   ldA, _lib.current_stream()))
+        return base, rep, At_d, ldA, P
+
+    def tstat_rowperm(self, X, perm_idx, rows=None):
+        """Fused fit+t for the designs X[perm_idx[p]] (whole rows permuted).  X float64 [n, k] with the intercept in
+        column 0; rows = (first, count) selects regressors (default: all k-1).  Returns CUDA float32 [P, count, ld] in
+        the engine's internal column order."""
+        import torch
+        base, rep, At_d, ldA, P = self._rowperm_operands(X, perm_idx)
+        r, rp = base["r"], base["rp"]
+        row0, nrows = (0, r) if rows is None else (int(rows[0]), int(rows[1]))
         yy = self.Y.sumsq(True)
-        t32 = torch.empty((P, r, self.Y.ld), dtype=torch.float32, device=self.device)
-        _lib.check(L.tmb_glm_tstat(
+        t32 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().tmb_glm_tstat(
             _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA,
-            _lib.ptr(rep[0]), _lib.ptr(rep[1]), P, r, rp, 0, r, base["dof"], _lib.ptr(yy), _lib.ptr(t32),
-            None, self.Y.ld, 1 if self.nan_to_zero else 0, stream))
+            _lib.ptr(rep[0]), _lib.ptr(rep[1]), P, r, rp, row0, nrows, base["dof"], _lib.ptr(yy), _lib.ptr(t32),
+            None, self.Y.ld, 1 if self.nan_to_zero else 0, _lib.current_stream()))
         return t32
+
+    # -- F statistics (tm-models GLM branch) -------------------------------------------------------
+    def fstat(self, stack, var_lo, var_k, want_model=False, want_f64=False, caller_order=True):
+        """Model F and per-variable partial F of pyfunc.py:2282-2401 glm_typeI for a design stack (design_stack
+        output, intercept centred away): variable i covers regressors [var_lo[i], var_lo[i] + var_k[i]).
+        Returns CUDA float32 [P, nvar (+1 with the model F first), ld] (and float64 when want_f64)."""
+        import torch
+        P, r, n = stack["pinv"].shape
+        if n != self.Y.n:
+            raise ValueError("design has %d subjects, data has %d" % (n, self.Y.n))
+        rp = _rp_for(r)
+        At, ldA = pack_At(stack["pinv"], rp)
+        At_d = self._upload("At", At)
+        G_d = self._upload("G", stack["G"])
+        M_d = self._upload("M", fstat_blocks(stack["G"], var_lo, var_k))
+        out = self._fstat_launch(At_d, ldA, G_d, M_d, P, r, rp, var_lo, var_k, want_model, stack["dof"], want_f64)
+        if caller_order and self.colperm is not None:
+            out = tuple(self.to_caller_order(o) if o is not None else None for o in out)
+        return out if want_f64 else out[0]
+
+    def _fstat_launch(self, At_d, ldA, G_d, M_d, P, r, rp, var_lo, var_k, want_model, dof, want_f64=False):
+        import torch
+        nvar = len(var_lo)
+        nrows = nvar + (1 if want_model else 0)
+        lo = np.ascontiguousarray(var_lo, dtype=np.int32)
+        kk = np.ascontiguousarray(var_k, dtype=np.int32)
+        yy = self.Y.sumsq(True)
+        f32 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float32, device=self.device)
+        f64 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
+        _lib.check(_lib.lib().tmb_glm_fstat(
+            _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA, _lib.ptr(G_d),
+            _lib.ptr(M_d), P, r, rp, nvar, lo.ctypes.data, kk.ctypes.data, 1 if want_model else 0, dof, _lib.ptr(yy),
+            _lib.ptr(f32), _lib.ptr(f64), self.Y.ld, 1 if self.nan_to_zero else 0, _lib.current_stream()))
+        return f32, f64
+
+    def fstat_rowperm(self, X, var_lo, var_k, perm_idx, want_model=False):
+        """fstat for the designs X[perm_idx[p]] (glm_typeI's `exog_vars[rand_array]`, pyfunc.py:2317-2321): only the
+        index rows travel; X'X, and with it every variable's inverse block, is the same for all permutations."""
+        import torch
+        base, rep, At_d, ldA, P = self._rowperm_operands(X, perm_idx)
+        key = (tuple(int(a) for a in var_lo), tuple(int(a) for a in var_k), P)
+        M_d = base["fmat"].get(key)
+        if M_d is None:
+            M1 = fstat_blocks(base["G"][None], var_lo, var_k)
+            M_d = torch.from_numpy(np.repeat(M1, P, axis=0)).to(self.device)
+            base["fmat"] = {key: M_d}
+        return self._fstat_launch(At_d, ldA, rep[0], M_d, P, base["r"], base["rp"], var_lo, var_k, want_model,
+                                  base["dof"])[0]
+
+    def glm_typeI_block(self, exog_vars, kvars, perm_idx, stat="f", download=True):
+        """One block of the tm-models GLM permutation loop (tmanalysis/tm_models_randomise.py:197-272): per shuffle the
+        design is exog_vars[perm_idx[p]] (intercept in column 0, then the variables of interest with kvars[i] columns
+        each, then covariates).  stat 'f': per-variable F maps -> one-sided TFCE -> scaled max, float32 [P, nvar, S];
+        't': t of the variables' columns, both signs, float32 [P, sum(kvars), S, 2]; 'both': (F result, t result)."""
+        exog_vars = np.asarray(exog_vars, dtype=np.float64)
+        if not has_intercept(exog_vars):
+            raise ValueError("exog_vars must have the intercept in column 0")
+        kvars = [int(a) for a in kvars]
+        var_lo = np.concatenate([[0], np.cumsum(kvars)[:-1]]).astype(np.int32)   # regressor index = column - 1
+        out_f = out_t = None
+        if stat in ("f", "both"):
+            f32 = self.fstat_rowperm(exog_vars, var_lo, kvars, perm_idx)
+            P, nv, ld = f32.shape
+            mx, status, _ = self.plan.run(f32.view(P * nv, ld), two_sided=False)
+            out_f = mx.view(P, nv, self.plan.S, 2)[..., 0]
+            out_f = self._download(out_f.contiguous()) if download else out_f
+        if stat in ("t", "both"):
+            ncon = int(sum(kvars))
+            t32 = self.tstat_rowperm(exog_vars, perm_idx, rows=(0, ncon))
+            P, C, ld = t32.shape
+            mx, status, _ = self.plan.run(t32.view(P * C, ld), two_sided=True)
+            out_t = mx.view(P, C, self.plan.S, 2)
+            out_t = self._download(out_t) if download else out_t
+        return out_f if stat == "f" else out_t if stat == "t" else (out_f, out_t)
 
     # -- whole shuffles --------------------------------------------------------------------------
     def regression_block(self, X, perm_idx=None, designs=None, want_maps=False, download=True):

@@ -106,3 +106,99 @@ def calc_sobelz(medtype, pred_x, depend_y, merge_y, n, num_vertex, alg="aroian")
     (tmb_sobelz) through a one-shuffle engine call with the identity permutation."""
     from .engine import sobelz_single
     return sobelz_single(medtype, pred_x, depend_y, merge_y, alg)
+
+
+def typeI_design(exog, dmy_covariates, n):
+    """The design of pyfunc.py:2304-2315: [1, exog variables ..., covariates] and the column count of each variable."""
+    kvars = []
+    exog_vars = np.ones((n))
+    for var in exog:
+        var = np.array(var)
+        kvars.append(1 if var.ndim == 1 else var.shape[1])
+        exog_vars = np.column_stack((exog_vars, var))
+    if dmy_covariates is not None:
+        exog_vars = np.column_stack((exog_vars, dmy_covariates))
+    return np.array(exog_vars, dtype=np.float64), kvars
+
+
+def glm_typeI(endog, exog, dmy_covariates=None, output_fvalues=True, output_tvalues=False, output_pvalues=False,
+              verbose=True, rand_array=None, use_reduced_residuals=False, output_reduced_residuals=False,
+              exog_names=None):
+    """pyfunc.py:2282-2401 glm_typeI: model F, per-variable F (Type I extra sum of squares) and t of the design
+    [1, exog..., dmy_covariates] with rows optionally permuted by rand_array; same return tuples as the reference.
+    The F statistics come from ONE fused GPU fit (tmb_glm_fstat: RSS_without_i - RSS = b_S' inv(C_SS) b_S), the t
+    values from the tval_int drop-in; p-values (scipy) stay on the host like in the reference."""
+    from . import cynumstats
+    from .engine import PermutationEngine, design_stack, to_host
+    endog = np.asarray(endog)
+    if endog.ndim == 1:
+        endog = endog[:, None]
+    n = endog.shape[0]
+    exog_vars, kvars = typeI_design(exog, dmy_covariates, n)
+    if rand_array is not None:
+        if use_reduced_residuals:
+            endog = np.asarray(cynumstats.resid_covars(exog_vars, endog.T))
+        exog_vars = exog_vars[rand_array]
+    reduced_data = None
+    if output_reduced_residuals:
+        reduced_data = np.asarray(cynumstats.resid_covars(exog_vars, endog.T))
+    k = exog_vars.shape[1]
+    DF_Between, DF_Within, DF_Total = k - 1, n - k, n - 1
+    V = endog.shape[1]
+    Fvalues = Fvar = Tvalues = None
+    if output_fvalues:
+        eng = PermutationEngine(endog, None)
+        var_lo = np.concatenate([[0], np.cumsum(kvars)[:-1]]).astype(np.int32)
+        _, f64 = eng.fstat(design_stack(exog_vars[None], center=True), var_lo, kvars, want_model=True, want_f64=True)
+        f64 = to_host(f64[0, :, :V])
+        Fvalues, Fvar = f64[0], f64[1:]
+        if verbose:
+            print("Source\t\tDF\tF(Max)")
+            print("Model\t\t(%d,%d)\t%.2f" % (DF_Between, DF_Within, Fvalues.max()))
+            for i, col in enumerate(kvars):
+                print("%s\t\t(%d,%d)\t%.2f" % (exog_names[i] if exog_names is not None else "Exog%d" % (i + 1), col,
+                                                DF_Within, Fvar[i].max()))
+    if output_tvalues:
+        invXX = np.linalg.inv(np.dot(exog_vars.T, exog_vars))
+        Tvalues = cynumstats.tval_int(exog_vars, invXX, endog, n, k, V)
+    if output_pvalues:
+        from scipy.stats import f as f_dist, t as t_dist
+    if output_tvalues and output_fvalues:
+        if output_pvalues:
+            Pvar = np.array([f_dist.sf(Fvar[i], col, DF_Within) for i, col in enumerate(kvars)])
+            return (Fvalues, Fvar, Tvalues, f_dist.sf(Fvalues, DF_Between, DF_Within), Pvar,
+                    t_dist.sf(np.abs(Tvalues), DF_Total) * 2)
+        return (Fvalues, Fvar, Tvalues, reduced_data) if output_reduced_residuals else (Fvalues, Fvar, Tvalues)
+    if output_tvalues:
+        if output_pvalues:
+            return (Tvalues, t_dist.sf(np.abs(Tvalues), DF_Total) * 2)
+        return (Tvalues, reduced_data) if output_reduced_residuals else Tvalues
+    if output_fvalues:
+        if output_pvalues:
+            Pvar = np.array([f_dist.sf(Fvar[i], col, DF_Within) for i, col in enumerate(kvars)])
+            return (Fvalues, Fvar, f_dist.sf(Fvalues, DF_Between, DF_Within), Pvar)
+        return (Fvalues, Fvar, reduced_data) if output_reduced_residuals else (Fvalues, Fvar)
+    print("No output has been selected")
+
+
+def check_blocks(block_list):
+    """pyfunc.py:2711-2731."""
+    unique_blocks = np.unique(block_list)
+    block_sizes = [len(block_list[block_list == block]) for block in unique_blocks]
+    is_equal_sizes = all(x == block_sizes[0] for x in block_sizes)
+    if not is_equal_sizes:
+        print("Warning: blocks are not equal. Swaping with only occur within blocks, but not among blocks.")
+    return is_equal_sizes
+
+
+def rand_blocks(block_list, is_equal_sizes):
+    """pyfunc.py:2733-2757: permutation index from exchangeability blocks (same numpy RNG calls, same order)."""
+    indexer = np.array(range(len(block_list)))
+    randindex = []
+    if is_equal_sizes is True:
+        for block in np.random.permutation(list(np.unique(block_list))):
+            randindex.append(np.random.permutation(indexer[block_list == block]))
+    else:
+        for block in np.unique(block_list):
+            randindex.append(np.random.permutation(indexer[block_list == block]))
+    return np.concatenate(randindex)
