@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(256) pipe_levels_kernel(PipeParams P, int chun
     __shared__ float sT[2][kLevels];
     __shared__ int sNs[2];
     __shared__ float sRd[2];
+    __shared__ int sHist[kLevels]; // vertices of this CTA per activation level -> the map's histogram (lhist, zeroed by the launcher)
     const int tid = threadIdx.x;
     int item, chunk, s, b;
     grid_coords(P, item, chunk, s, b);
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(256) pipe_levels_kernel(PipeParams P, int chun
         sRd[tid] = d > 0.f ? __frcp_rn(d) : 0.f;
     }
     if (chunk == 0 && tid < 4) P.meta[(size_t)item * 4 + tid] = 0; // npeaks, npairs, flag (K_B runs after this kernel)
+    if (tid < kLevels) sHist[tid] = 0;
     __syncthreads();
     const float *__restrict__ x = P.stat + (size_t)b * P.ld + sd.col_off;
     const int32_t *__restrict__ vmap = (P.flags & 4) ? nullptr : sd.vmap;
@@ -175,7 +177,10 @@ __global__ void __launch_bounds__(256) pipe_levels_kernel(PipeParams P, int chun
             }
         }
         lev8[v] = (unsigned char)code;
+        if (code) atomicAdd(&sHist[code & 0x7f], 1);
     }
+    __syncthreads();
+    if (tid < kLevels && sHist[tid]) atomicAdd(P.lhist + (size_t)item * 256 + tid, sHist[tid]);
 }
 
 // ------------------------------------------------------------------------------------------- K_B
@@ -320,7 +325,62 @@ __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunk
         levq[q] = (v < sd.V) ? (int)(P.lev8[base + v] & 0x7f) : 0;
         emq[q] = (v < sd.V) ? P.emask[base + v] : 0u;
     }
+    // Max-only maps: this CTA's vertices go into the map's vertex lists bucketed by activation level (the basin id of
+    // every active vertex, 2 bytes), which the sweep reads level by level.  K_A left the level histogram; a CTA ranks
+    // its vertices per level in shared memory, reserves its range of each level's list with one returning atomic on
+    // the level's cursor, and scatters.  Order inside a level is irrelevant.  (The sweep did this itself until round-1
+    // v9, one CTA per SM: 19% of its time.)  The lists reuse the storage of `up`, dead since K_C.
+    __shared__ int sLcnt[kLevels], sLbase[kLevels], sLloc[kLevels];
+    __shared__ unsigned long long sWtot[kLevels / 32];
+    int rankq[kCountVPT];
+    if (!kDense) {
+        if (threadIdx.x < kLevels) sLcnt[threadIdx.x] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kCountVPT; ++q) rankq[q] = levq[q] ? atomicAdd(&sLcnt[levq[q]], 1) : 0;
+    }
     __syncthreads();
+    if (!kDense) {
+        // thread t < 128 owns level t: one packed warp scan gives the exclusive prefix of the map's level histogram
+        // (low word: where level t's list starts) and of this CTA's counts (high word: where level t starts in the
+        // CTA's staging buffer)
+        const int t = threadIdx.x;
+        const int cl = t < kLevels ? sLcnt[t] : 0;
+        const int hl = t < kLevels ? P.lhist[(size_t)item * 256 + t] : 0;
+        const unsigned long long mine = ((unsigned long long)(unsigned)cl << 32) | (unsigned)hl;
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (t < kLevels && lane == 31) sWtot[t >> 5] = incl;
+        __syncthreads();
+        if (t < kLevels) {
+            unsigned long long excl = incl - mine;
+            for (int w = 0; w < (t >> 5); ++w) excl += sWtot[w];
+            sLloc[t] = (int)(excl >> 32);
+            // reserve this CTA's range of level t's list: one returning atomic on the level's cursor
+            if (cl) sLbase[t] = (int)(unsigned)excl + atomicAdd(P.lhist + (size_t)item * 256 + kLevels + t, cl);
+        }
+        __syncthreads();
+        // staged through shared memory (the candidate-union buffer, not yet in use) so that each level's run leaves as
+        // consecutive 2-byte stores: scattering straight from the registers cost one 32-byte sector per vertex in the L2
+        unsigned short *sStage = reinterpret_cast<unsigned short *>(sPairs);
+        int *sStagePos = reinterpret_cast<int *>(sPairs) + kCountChunk / 2;
+#pragma unroll
+        for (int q = 0; q < kCountVPT; ++q)
+            if (levq[q]) {
+                const int i = sLloc[levq[q]] + rankq[q];
+                sStage[i] = (unsigned short)buq[q];
+                sStagePos[i] = sLbase[levq[q]] + rankq[q];
+            }
+        __syncthreads();
+        const int total = sLloc[kLevels - 1] + sLcnt[kLevels - 1];
+        unsigned short *__restrict__ vlist = reinterpret_cast<unsigned short *>(P.up + base);
+        for (int i = threadIdx.x; i < total; i += 256) vlist[sStagePos[i]] = sStage[i];
+        __syncthreads();
+    }
 #pragma unroll
     for (int q = 0; q < kCountVPT; ++q) {
         const int v = v_beg + q * 256 + threadIdx.x;
@@ -845,7 +905,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
     constexpr int nthr = kThreads;
     const int lane = tid & 31, wid = tid >> 5;
     const SweepSlot ws = carve_slot(P.slot_ws + (size_t)blockIdx.x * P.slot_stride, P.Vmax, P.nbcap, P.paircap);
-    unsigned short *const elist = reinterpret_cast<unsigned short *>(ws.elist); // basin of every active vertex, bucketed by level
     const int total_items = P.B * P.S;
 
     for (;;) {
@@ -873,7 +932,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         const int flag = meta[2];
         if (stage == 2 ? flag != 2 : flag != 0) continue;
         const bool hopeless = NB > P.nbcap || NB > 65535 || NP > P.paircap;
-        const bool too_big = pipe_sweep_max_smem_bytes(NB, kSmall) + (nthr / 32) * kLevels * sizeof(int) > (size_t)smem_bytes;
+        const bool too_big = pipe_sweep_max_smem_bytes(NB, kSmall) > (size_t)smem_bytes;
         if (hopeless || too_big) {
             __syncthreads(); // everybody has read the flag
             if (tid == 0) {
@@ -911,7 +970,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             hooklev = reinterpret_cast<unsigned char *>(birth + nba);
         }
         unsigned char *blev = hooklev + nba;                                      // level | sign << 7 of the peak
-        int *whist = reinterpret_cast<int *>(blev + nba);                         // [warps][128] private level histograms / cursors
+        // basin of every active vertex, bucketed by level: built by K_D in the storage of `up` (see pipe_count_kernel)
+        const unsigned short *__restrict__ elist = reinterpret_cast<const unsigned short *>(P.up + (size_t)item * P.vstride);
 
         for (int i = tid; i < 2 * kLevels; i += nthr)
             sHHd[i / kLevels][i % kLevels] = (double)P.tab_HH[(e0 + i / kLevels) * kLevels + i % kLevels];
@@ -941,11 +1001,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         //      histograms (no contention between warps); warp w owns the vertex blocks w, w + nwarps, ... in BOTH
         //      passes, 128 vertices per block (one 4-byte load of level codes per lane).
         const unsigned long long *__restrict__ pairs = P.pairs + (size_t)item * P.paircap;
-        const unsigned *__restrict__ lev32 = reinterpret_cast<const unsigned *>(P.lev8 + (size_t)item * P.vstride);
-        const int4 *__restrict__ basin4 = reinterpret_cast<const int4 *>(P.basin + (size_t)item * P.vstride);
-        constexpr int nwarps = nthr / 32;
-        int *const myhist = whist + wid * kLevels;
-        for (int i = tid; i < nwarps * kLevels; i += nthr) whist[i] = 0;
         auto for_each_batched = [&](const unsigned long long *__restrict__ src, int n, auto &&fn) {
             for (int i0 = tid; i0 < n; i0 += 8 * nthr) {
                 unsigned long long v[8];
@@ -960,35 +1015,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         for_each_batched(pairs, NP, [&](unsigned long long p) { atomicAdd(&sCurP[(int)(p >> 48)], 1); });
         __syncthreads();
         PIPE_TICK(21)
-        // vertex blocks of 128 (one 4-byte load of level codes per lane); warp w owns blocks w, w + nwarps, ... in both
-        // passes.  (Measured alternatives: warp-aggregation with match.any and a striped lane mapping were both slower;
-        // the second pass, whose 2-byte stores scatter over the level segments, is what costs.)
-        const int nblocks = (V + 127) / 128;
-        for (int blk0 = wid; blk0 < nblocks; blk0 += 4 * nwarps) { // four blocks (loads) in flight per warp
-            unsigned w4[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int blk = blk0 + q * nwarps;
-                w4[q] = (blk < nblocks && blk * 128 + lane * 4 < V) ? lev32[blk * 32 + lane] : 0u;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int v = (blk0 + q * nwarps) * 128 + lane * 4 + e;
-                    const int lv = (w4[q] >> (8 * e)) & 0x7f;
-                    if (lv && v < V) atomicAdd(&myhist[lv], 1);
-                }
-        }
+        // vertices per level: the map's histogram from K_A (the lists themselves were written by K_D)
+        if (tid < kLevels) sCurE[tid] = P.lhist[(size_t)item * 256 + tid];
         __syncthreads();
         PIPE_TICK(22)
-        // level totals over the warps; per-(warp, level) cursors = level start + counts of the earlier warps
-        if (tid < kLevels) {
-            int tot = 0;
-            for (int w = 0; w < nwarps; ++w) { const int c = whist[w * kLevels + tid]; whist[w * kLevels + tid] = tot; tot += c; }
-            sCurE[tid] = tot;
-        }
-        __syncthreads();
         if (tid < 3) {
             int *cur = tid == 0 ? sCurP : tid == 1 ? sCurE : sCurB;
             int *start = tid == 0 ? sPstart : tid == 1 ? sEstart : sBstart;
@@ -1002,33 +1032,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         __syncthreads();
         PIPE_TICK(24)
         for (int i = tid; i < NB; i += nthr) birth[atomicAdd(&sCurB[blev[i] & 0x7f], 1)] = (unsigned short)i;
-        for (int blk0 = wid; blk0 < nblocks; blk0 += 2 * nwarps) { // two blocks in flight per warp
-            unsigned w2[2];
-            int4 b2[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int blk = blk0 + q * nwarps;
-                const bool ok = blk < nblocks && blk * 128 + lane * 4 < V;
-                w2[q] = ok ? lev32[blk * 32 + lane] : 0u;
-                b2[q] = ok ? basin4[blk * 32 + lane] : make_int4(-1, -1, -1, -1);
-            }
-            int pos[8]; // eight returning shared-memory atomics in flight, then the eight stores
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int v = (blk0 + q * nwarps) * 128 + lane * 4 + e;
-                    const int lv = (w2[q] >> (8 * e)) & 0x7f;
-                    pos[q * 4 + e] = (lv && v < V) ? sEstart[lv] + atomicAdd(&myhist[lv], 1) : -1;
-                }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int bs[4] = {b2[q].x, b2[q].y, b2[q].z, b2[q].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (pos[q * 4 + e] >= 0) elist[pos[q * 4 + e]] = (unsigned short)bs[e];
-            }
-        }
         __syncthreads();
         const int ns0 = sNs[0], ns1 = sNs[1];
         const int nlev = max(ns0, ns1);
@@ -1297,6 +1300,7 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
     const int chunksA = (p.Vmax + kChunkA - 1) / kChunkA;
     const int chunks = (p.Vmax + 255) / 256;
     TMB_REQUIRE(p.B <= 65535 && p.S <= 65535, "tfce pipeline: at most 65535 rows and surfaces per launch (got %d, %d)", p.B, p.S);
+    TMB_CUDA(cudaMemsetAsync(p.lhist, 0, sizeof(int) * 256 * (size_t)items, stream));
     pipe_levels_kernel<<<dim3(chunksA, p.B, p.S), 256, 0, stream>>>(p, chunksA);
     if (p.max_degree > 0 && p.max_degree <= 6) pipe_ascent_kernel<true><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
     else pipe_ascent_kernel<false><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);

@@ -10,11 +10,16 @@ drivers generate them with the reference's own numpy RNG calls), so results are 
 """
 import ctypes
 
+import os as _os
+import time as _time
+
 import numpy as np
 
 from . import _lib
 from ._device import DeviceMatrix, TILE_M, round_up, to_host
 from .tfce import CreateAdjSet
+
+_E2E_DEBUG = bool(_os.environ.get("TMB_E2E_DEBUG"))   # per-block host timings of the exact-libm round trip on stderr
 
 
 def _rp_for(r):
@@ -156,15 +161,23 @@ class TfcePlan(object):
         mx = out_max if out_max is not None else torch.empty((B, self.S, 2), dtype=torch.float32, device=stat.device)
         if status is None:
             status = torch.empty((B, self.S, 2), dtype=torch.int32, device=stat.device)
+        dbg = _E2E_DEBUG
+        t0 = _time.perf_counter() if dbg else 0.0
         ticket["event"].synchronize()
         if ticket["tab_event"] is not None:
             ticket["tab_event"].synchronize()     # the previous upload out of this staging buffer is done
+        t1 = _time.perf_counter() if dbg else 0.0
         tab = ticket["tab"]
         mh = ticket["host"].numpy()
         _lib.check(L.tmb_threshold_tables(_lib.ptr(mh), _lib.ptr(ticket["Hs"]), cnt, _lib.ptr(tab["ns"]),
                                           _lib.ptr(tab["delta"]), _lib.ptr(tab["T"]), _lib.ptr(tab["HH"]),
                                           _lib.ptr(tab["st"])))
+        t2 = _time.perf_counter() if dbg else 0.0
         d = {k: v.to(stat.device, non_blocking=True) for k, v in tab.items()}
+        if dbg:
+            import sys
+            sys.stderr.write("[tmb e2e] wait maxima %.2f ms, host tables %.2f ms, table upload issue %.2f ms\n"
+                             % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (_time.perf_counter() - t2) * 1e3))
         ticket["tab_event"] = torch.cuda.Event()
         ticket["tab_event"].record()
         _lib.check(L.tmb_plan_run_tables(self._handle, _lib.ptr(stat), ld, B, 1 if two_sided else 0, _lib.ptr(d["ns"]),
@@ -265,6 +278,7 @@ class PermutationEngine(object):
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._pinned = {}
+        self._rings = {}
 
     def to_caller_order(self, t):
         """Undo the one-time column permutation on a [..., ld] device tensor (maps returned to the user)."""
@@ -293,6 +307,22 @@ class PermutationEngine(object):
         ent[1] = torch.cuda.Event()
         ent[1].record()
         return dev
+
+    def _ring(self, name, shape, dtype, depth=3):
+        """Reused device buffers for the per-block operands and statistic maps (a ring of `depth` per shape): the
+        pipelined block loop keeps two blocks in flight on one stream, so a buffer comes round again only after the
+        kernels that read it.  Without it every block took ~1.2 GB from torch's caching allocator, whose occasional
+        cudaMalloc/cudaFree (synchronous) made one bench run in four 30% slower end to end."""
+        import torch
+        key = (name, tuple(int(x) for x in shape), dtype)
+        ent = self._rings.get(key)
+        if ent is None:
+            if len(self._rings) > 12:                        # shapes changed (another block size): drop the old rings
+                self._rings.clear()
+            ent = [[torch.empty(key[1], dtype=dtype, device=self.device) for _ in range(depth)], 0]
+            self._rings[key] = ent
+        ent[1] = (ent[1] + 1) % depth
+        return ent[0][ent[1]]
 
     def _download(self, t):
         self.d2h_bytes += t.numel() * t.element_size()
@@ -352,7 +382,7 @@ class PermutationEngine(object):
             base["fmat"] = {}
         idx_d = self._upload("perm_idx", np.ascontiguousarray(perm_idx, dtype=np.int32))
         ldA = round_up(P * rp, TILE_M)
-        At_d = torch.empty((n, ldA), dtype=torch.float64, device=self.device)
+        At_d = self._ring("At", (n, ldA), torch.float64)
         _lib.check(_lib.lib().tmb_glm_pack_rowperm(_lib.ptr(base["pinv"]), r, n, _lib.ptr(idx_d), P, rp, _lib.ptr(At_d),
                                                    ldA, _lib.current_stream()))
         return base, rep, At_d, ldA, P
@@ -366,7 +396,7 @@ class PermutationEngine(object):
         r, rp = base["r"], base["rp"]
         row0, nrows = (0, r) if rows is None else (int(rows[0]), int(rows[1]))
         yy = self.Y.sumsq(True)
-        t32 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float32, device=self.device)
+        t32 = self._ring("t32", (P, nrows, self.Y.ld), torch.float32)
         _lib.check(_lib.lib().tmb_glm_tstat(
             _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA,
             _lib.ptr(rep[0]), _lib.ptr(rep[1]), P, r, rp, row0, nrows, base["dof"], _lib.ptr(yy), _lib.ptr(t32),
