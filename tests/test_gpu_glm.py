@@ -81,3 +81,33 @@ def test_engine_tstat_batch_matches_oracle(n, V, k, P):
         bad += int(np.sum(t32[p] != want.astype(np.float32)))
     assert bad <= 2, "float32 t-maps are expected to be bit-identical to the reference (%d differ)" % bad
     assert torch.cuda.is_available()
+
+
+def test_dmma_fast_epilogue_bit_identical_to_exact(monkeypatch):
+    """The headline fit's fp32 t-maps: the cheap epilogue (fp32 MUFU seeds + one fp64 Newton step, exact path whenever the
+    value is within 2^-41 of an fp32 rounding boundary) must reproduce the exact fp64 sqrt/division path bit for bit --
+    including constant columns (sse = 0 -> inf / NaN), tiny and huge scales, and zero slopes."""
+    import torch
+    from tfce_mediation_b200.engine import PermutationEngine
+    n, V, P = 96, 40000, 192
+    rs = np.random.RandomState(5)
+    y = rs.standard_normal((n, V)).astype(np.float32)
+    y[:, :64] = 1.25                                         # constant columns: beta = 0, sse = 0
+    y[:, 64:128] *= np.float32(1e-18)                        # se far below the fp32-normal window of the fast path
+    y[:, 128:192] *= np.float32(1e17)
+    x = rs.standard_normal(n)
+    y[:, 192:256] = (np.outer(x, np.ones(64)) * 3).astype(np.float32)   # exact fit of the unpermuted design: sse ~ 0
+    X = np.column_stack([np.ones(n), x])
+    perm = np.stack([np.arange(n)] + [rs.permutation(n) for _ in range(P - 1)])
+    eng = PermutationEngine(y, None)
+    monkeypatch.setenv("TMB_GLM_EPILOGUE", "exact")
+    want = eng.tstat_rowperm(X, perm).clone()
+    monkeypatch.delenv("TMB_GLM_EPILOGUE")
+    got = eng.tstat_rowperm(X, perm).clone()
+    torch.cuda.synchronize()
+    a, b = want.view(torch.int32), got.view(torch.int32)
+    assert int((a != b).sum()) == 0
+    # and the exact path is the oracle's (spot check on the regular columns)
+    nx = X[perm[3]]
+    ref = oracle.tval_int(nx, np.linalg.inv(nx.T @ nx), y[:, 256:2256], n, 2, 2000)[1].astype(np.float32)
+    assert np.mean(got[3, 0, 256:2256].cpu().numpy() != ref) < 1e-3

@@ -79,6 +79,7 @@ struct GlmParams {
     // F statistics (mode 3): per design the inverse blocks M_i = inv((X'X)^-1[S_i, S_i]) of every tested variable,
     // stored one after the other (k_i x k_i each, msz doubles per design); variable i covers rows [var_lo[i], +var_k[i])
     const double *M; int msz, nvar; int var_lo[8], var_k[8];
+    int exact_epilogue;                 // DMMA kernel: always take the fp64 square root / division (TMB_GLM_EPILOGUE=exact)
 };
 
 // sum_{a,b in [lo,lo+r)} acc[g*RP+a][c] * G[(a-lo)*r + (b-lo)] * acc[g*RP+b][c]; every loop is fully
@@ -121,6 +122,49 @@ __device__ __forceinline__ double t_from_scaled(double beta, double sse, double 
     if (sse < 0.0) sse = 0.0;
     const float se = __double2float_rn(__dsqrt_rn(__dmul_rn(sse, d_over_dof)));
     return __ddiv_rn(beta, (double)se);
+}
+
+// exact widening of a positive normal float (integer pipe instead of the conversion unit)
+__device__ __forceinline__ double widen_pos_normal(float f) {
+    const unsigned u = __float_as_uint(f);
+    return __hiloint2double((int)((u >> 3) + 0x38000000u), (int)(u << 29));
+}
+
+// fl32(t) of t_from_scaled with ~8 fp64-pipe instructions instead of ~35.  The epilogue's dependent fp64 chain (square
+// root, division) queues behind the other CTA's DMMAs on the one fp64 pipe and held the warps for most of their
+// lifetime (ncu: 40% of the stall samples on these two lines).  Both results are only needed to fp32 accuracy:
+//   se = fl32(RN64(sqrt(s))),   t32 = fl32(RN64(beta / se))
+// so a 2^-43-accurate square root and a 2^-45-accurate quotient (fp32 MUFU seed + one fp64 Newton step each) round
+// to the same fp32 value as the correctly rounded fp64 results UNLESS they fall within 2^-41 (relative) of an fp32
+// rounding boundary -- then, and for zero / out-of-range / non-finite operands, `slow` is set and the caller takes the
+// exact path (probability ~3e-5 per value).  Bit-identical to the exact path by construction.
+__device__ __forceinline__ float t32_fast(double beta, double sse, double d_over_dof, bool &slow) {
+    if (sse < 0.0) sse = 0.0;
+    const double s = __dmul_rn(sse, d_over_dof);
+    const float sf = __double2float_rn(s);
+    slow = !(sf > 1e-30f && sf < 1e30f);                    // also catches 0, NaN, inf
+    float y32;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y32) : "f"(slow ? 1.0f : sf));   // rel. error < 2^-22
+    const double y = widen_pos_normal(y32);
+    const double g = __dmul_rn(s, y);                        // ~ sqrt(s) (1 + e0)
+    const double h = __dmul_rn(0.5, y);
+    const double e = __fma_rn(-h, g, 0.5);                   // ~ -e0
+    const double g1 = __fma_rn(g, e, g);                     // sqrt(s) (1 - 1.5 e0^2): rel. error < 2^-43
+    const unsigned lowg = (unsigned)__double2loint(g1) & 0x1FFFFFFFu;   // the 29 bits below fp32 precision
+    slow |= (lowg - (0x10000000u - 4096u)) < 8192u;          // within 2^12 ulp64 of a rounding boundary
+    const float se = __double2float_rn(g1);
+    float r32;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r32) : "f"(slow ? 1.0f : se));     // rel. error < 2^-22.9
+    const double sed = widen_pos_normal(slow ? 1.0f : se);
+    const double r = widen_pos_normal(r32);
+    const double e2 = __fma_rn(-sed, r, 1.0);
+    const double r1 = __fma_rn(r, e2, r);                    // 1/se: rel. error < 2^-45
+    const double q = __dmul_rn(beta, r1);
+    const unsigned lowq = (unsigned)__double2loint(q) & 0x1FFFFFFFu;
+    slow |= (lowq - (0x10000000u - 4096u)) < 8192u;
+    const unsigned ex = ((unsigned)__double2hiint(q) >> 20) & 0x7ffu;  // fp32-normal quotient (or exactly zero) only
+    slow |= !((ex - (1023u - 120u)) <= 240u || q == 0.0);
+    return __double2float_rn(q);
 }
 
 // one output row of a thread's tile: two 128-bit stores (float) / eight scalar stores (double)
@@ -453,6 +497,7 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
         if (lane == 0) mbar_arrive(empty + s);
     }
     // epilogue (r == 1): element (i, j, e) is design m0 + wm*32 + i*8 + g, vertex v0 + wn*32 + j*8 + t4*2 + e
+    const bool fast = p.t64 == nullptr && !p.exact_epilogue; // fp32 output only
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int perm = m0 + wm * 32 + i * 8 + g;
@@ -472,11 +517,18 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
                 const double beta = acc[i][j][e];
                 const double yyv = (v + e < p.V) ? p.yy[v + e] : 0.0;
                 const double sse = yyv - __dmul_rn(beta, __dmul_rn(G, beta));
-                double t = t_from_scaled(beta, sse, dscale);
-                if (p.nan_to_zero && t != t) t = 0.0;
-                if (v + e >= p.V) t = 0.0;
+                bool slow = true;
+                float tf = 0.f;
+                if (fast) tf = t32_fast(beta, sse, dscale, slow);
+                double t = 0.0;
+                if (slow) { // exact path: fp64 outputs requested, or the fast value is too close to an fp32 rounding boundary
+                    t = t_from_scaled(beta, sse, dscale);
+                    if (p.nan_to_zero && t != t) t = 0.0;
+                    tf = __double2float_rn(t);
+                }
+                if (v + e >= p.V) { t = 0.0; tf = 0.f; }
                 o64[e] = t;
-                o32[e] = __double2float_rn(t);
+                o32[e] = tf;
             }
             const size_t off = (size_t)perm * p.ldt + v;
             if (p.t32) *reinterpret_cast<float2 *>(p.t32 + off) = make_float2(o32[0], o32[1]);
@@ -655,8 +707,12 @@ int launch_glm(const GlmParams &p, cudaStream_t stream) {
         const char *force = getenv("TMB_GLM");
         const bool dfma = force && strcmp(force, "dfma") == 0;
         // (float32 data only: with fp64 data the doubled Y stage halves the resident CTAs and DFMA wins, measured)
-        if (!dfma && !p.y_is_f64 && p.mode == 0 && p.r == 1 && p.rp == 1 && p.row0 == 0 && p.nrows == 1)
-            return launch_dmma<float>(p, stream);
+        if (!dfma && !p.y_is_f64 && p.mode == 0 && p.r == 1 && p.rp == 1 && p.row0 == 0 && p.nrows == 1) {
+            const char *ep = getenv("TMB_GLM_EPILOGUE");
+            GlmParams q = p;
+            q.exact_epilogue = ep && strcmp(ep, "exact") == 0;
+            return launch_dmma<float>(q, stream);
+        }
     }
     return p.y_is_f64 ? launch_glm_t<double>(p, stream) : launch_glm_t<float>(p, stream);
 }
