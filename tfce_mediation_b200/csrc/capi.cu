@@ -428,7 +428,8 @@ static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
 // per-item bytes of the streaming pipeline's buffers
 static size_t pipe_item_bytes(const tmb_plan *p) {
-    return al256((size_t)p->pipe_vstride) + 3 * al256(sizeof(int) * (size_t)p->pipe_vstride) + 16 + 1024 + al256((size_t)p->pipe_nbcap) +
+    return al256((size_t)p->pipe_vstride) + 3 * al256(sizeof(int) * (size_t)p->pipe_vstride) + 16 + 1024 + al256(2 * (size_t)p->pipe_vstride) +
+           al256((size_t)p->pipe_nbcap) +
            al256(sizeof(unsigned long long) * (size_t)p->pipe_paircap) + al256(sizeof(unsigned) * (size_t)p->pipe_tabcap);
 }
 
@@ -544,6 +545,7 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
         pp.basin = reinterpret_cast<int *>(base); base += al256(items * vs * sizeof(int));
         pp.meta = reinterpret_cast<int *>(base); base += al256(items * 16);
         pp.lhist = reinterpret_cast<int *>(base); base += al256(items * 1024);
+        pp.vlist = reinterpret_cast<unsigned short *>(base); base += al256(items * vs * 2);
         pp.blev = reinterpret_cast<unsigned char *>(base); base += al256(items * (size_t)p->pipe_nbcap);
         pp.pairs = reinterpret_cast<unsigned long long *>(base); base += al256(items * (size_t)p->pipe_paircap * sizeof(unsigned long long));
         pp.table = reinterpret_cast<unsigned *>(base);

@@ -111,7 +111,8 @@ struct PipeParams {
     int *basin;             // compact basin id, -1 when inactive
     int *meta;              // [items][4]: basins, candidate unions, over-capacity flag, unused
     int *lhist;             // [items][256]: [0,128) vertices per activation level (K_A), [128,256) the cursors with which
-                            // K_D reserves each CTA's range of a level's vertex list (max-only maps)
+                            // K_C reserves each CTA's range of a level's vertex list (max-only maps)
+    unsigned short *vlist;  // [items][vstride] basin of every active vertex, bucketed by activation level (K_C -> sweep)
     unsigned char *blev;    // [items][nbcap] level | sign of each peak
     int nbcap;
     unsigned long long *pairs; // [items][paircap] (level << 48) | (basin << 24) | basin

@@ -261,33 +261,110 @@ __global__ void __launch_bounds__(256) pipe_ascent_kernel(PipeParams P, int chun
 }
 
 // ------------------------------------------------------------------------------------------- K_C
+// Basin of every vertex (read-only pointer chase along `up`, four independent chains per thread), and -- for max-only
+// maps -- the map's VERTEX LISTS bucketed by activation level: the basin id (2 bytes) of every active vertex, which the
+// sweep reads level by level.  K_A left the level histogram; a CTA ranks its 1,024 vertices per level in shared memory,
+// reserves its range of each level's list with one returning atomic on the level's cursor, and writes the runs from a
+// shared-memory staging buffer (consecutive 2-byte stores instead of one 32-byte L2 sector per vertex).  Order inside a
+// level is irrelevant.  The kernel waits on dependent loads most of the time (the chase), so the ranking rides along
+// almost for free; the sweep did it itself until round-1 v9 (one CTA per SM: 19% of its time), the count kernel in v10
+// (+1.1 ms: it is bound by its instruction count).
+static constexpr int kBasinVPT = 4;                 // vertices per thread
+static constexpr int kBasinChunk = 256 * kBasinVPT; // vertices per CTA
+
 __global__ void __launch_bounds__(256) pipe_basin_kernel(PipeParams P, int chunks) {
     int item, chunk, s, b;
     grid_coords(P, item, chunk, s, b);
     const int V = P.surfs[s].V;
-    const int v = chunk * 256 + threadIdx.x;
-    if (v >= V) return;
+    const int v_beg = chunk * kBasinChunk;
+    if (v_beg >= V) return; // CTA-uniform
+    const int tid = threadIdx.x, lane = tid & 31;
     const size_t base = (size_t)item * P.vstride;
     const int *__restrict__ up = P.up + base;
-    int t = up[v];
-    int bas = -1;
-    if (t != kInactive) {
-        while (t >= 0) t = up[t];
-        bas = -1 - t;
+    int t[kBasinVPT], levq[kBasinVPT];
+#pragma unroll
+    for (int q = 0; q < kBasinVPT; ++q) {
+        const int v = v_beg + q * 256 + tid;
+        t[q] = v < V ? up[v] : kInactive;
+        levq[q] = v < V ? (int)(P.lev8[base + v] & 0x7f) : 0;
     }
-    P.basin[base + v] = bas;
-    // zero this map's count table (rows 1 .. nlev-1 of NB entries), a slice per thread
+    for (;;) { // kInactive and the peaks' -1 - basin are negative: a chain ends at the first negative entry
+        bool more = false;
+#pragma unroll
+        for (int q = 0; q < kBasinVPT; ++q)
+            if (t[q] >= 0) { t[q] = up[t[q]]; more |= t[q] >= 0; }
+        if (!more) break;
+    }
+    int bas[kBasinVPT];
+#pragma unroll
+    for (int q = 0; q < kBasinVPT; ++q) {
+        const int v = v_beg + q * 256 + tid;
+        bas[q] = t[q] == kInactive ? -1 : -1 - t[q];
+        if (v < V) P.basin[base + v] = bas[q];
+    }
     const size_t e0 = ((size_t)b * P.S + s) * 2;
     const int NB = P.meta[(size_t)item * 4];
     const int nlev = max(P.tab_ns[e0], P.two_sided ? P.tab_ns[e0 + 1] : 0);
     const int64_t n = (int64_t)nlev * NB;
-    if (NB > P.nbcap || (P.want_vertex_pass && n > P.tabcap)) {
-        if (v == 0) P.meta[(size_t)item * 4 + 2] = 1; // over capacity: redone by tfce_basin_kernel
+    if (NB > P.nbcap || (P.want_vertex_pass && n > P.tabcap)) { // CTA-uniform
+        if (chunk == 0 && tid == 0) P.meta[(size_t)item * 4 + 2] = 1; // over capacity: redone by tfce_basin_kernel
         return;
     }
-    if (!P.want_vertex_pass) return; // max-only maps use compact entry lists, no dense table
-    unsigned *__restrict__ tab = P.table + (size_t)item * P.tabcap;
-    for (int64_t i = v; i < n; i += V) tab[i] = 0u;
+    if (P.want_vertex_pass) {
+        // class path: zero this map's count table (rows 1 .. nlev-1 of NB entries), a slice per vertex slot
+        unsigned *__restrict__ tab = P.table + (size_t)item * P.tabcap;
+#pragma unroll
+        for (int q = 0; q < kBasinVPT; ++q) {
+            const int v = v_beg + q * 256 + tid;
+            if (v < V)
+                for (int64_t i = v; i < n; i += V) tab[i] = 0u;
+        }
+        return;
+    }
+    // ---- max-only maps: vertex lists by level
+    __shared__ int sLcnt[kLevels], sLbase[kLevels], sLloc[kLevels];
+    __shared__ unsigned long long sWtot[kLevels / 32];
+    __shared__ unsigned short sStage[kBasinChunk];
+    __shared__ int sStagePos[kBasinChunk];
+    if (tid < kLevels) sLcnt[tid] = 0;
+    __syncthreads();
+    int rankq[kBasinVPT];
+#pragma unroll
+    for (int q = 0; q < kBasinVPT; ++q) rankq[q] = levq[q] ? atomicAdd(&sLcnt[levq[q]], 1) : 0;
+    __syncthreads();
+    {
+        // thread t < 128 owns level t: one packed warp scan gives the exclusive prefix of the map's level histogram (low
+        // word: where level t's list starts) and of this CTA's counts (high word: where level t starts in the staging buffer)
+        const int cl = tid < kLevels ? sLcnt[tid] : 0;
+        const int hl = tid < kLevels ? P.lhist[(size_t)item * 256 + tid] : 0;
+        const unsigned long long mine = ((unsigned long long)(unsigned)cl << 32) | (unsigned)hl;
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (tid < kLevels && lane == 31) sWtot[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < kLevels) {
+            unsigned long long excl = incl - mine;
+            for (int w = 0; w < (tid >> 5); ++w) excl += sWtot[w];
+            sLloc[tid] = (int)(excl >> 32);
+            if (cl) sLbase[tid] = (int)(unsigned)excl + atomicAdd(P.lhist + (size_t)item * 256 + kLevels + tid, cl);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kBasinVPT; ++q)
+        if (levq[q]) {
+            const int i = sLloc[levq[q]] + rankq[q];
+            sStage[i] = (unsigned short)bas[q];
+            sStagePos[i] = sLbase[levq[q]] + rankq[q];
+        }
+    __syncthreads();
+    const int total = sLloc[kLevels - 1] + sLcnt[kLevels - 1];
+    unsigned short *__restrict__ vlist = P.vlist + base;
+    for (int i = tid; i < total; i += 256) vlist[sStagePos[i]] = sStage[i];
 }
 
 // ------------------------------------------------------------------------------------------- K_D
@@ -325,62 +402,7 @@ __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunk
         levq[q] = (v < sd.V) ? (int)(P.lev8[base + v] & 0x7f) : 0;
         emq[q] = (v < sd.V) ? P.emask[base + v] : 0u;
     }
-    // Max-only maps: this CTA's vertices go into the map's vertex lists bucketed by activation level (the basin id of
-    // every active vertex, 2 bytes), which the sweep reads level by level.  K_A left the level histogram; a CTA ranks
-    // its vertices per level in shared memory, reserves its range of each level's list with one returning atomic on
-    // the level's cursor, and scatters.  Order inside a level is irrelevant.  (The sweep did this itself until round-1
-    // v9, one CTA per SM: 19% of its time.)  The lists reuse the storage of `up`, dead since K_C.
-    __shared__ int sLcnt[kLevels], sLbase[kLevels], sLloc[kLevels];
-    __shared__ unsigned long long sWtot[kLevels / 32];
-    int rankq[kCountVPT];
-    if (!kDense) {
-        if (threadIdx.x < kLevels) sLcnt[threadIdx.x] = 0;
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < kCountVPT; ++q) rankq[q] = levq[q] ? atomicAdd(&sLcnt[levq[q]], 1) : 0;
-    }
     __syncthreads();
-    if (!kDense) {
-        // thread t < 128 owns level t: one packed warp scan gives the exclusive prefix of the map's level histogram
-        // (low word: where level t's list starts) and of this CTA's counts (high word: where level t starts in the
-        // CTA's staging buffer)
-        const int t = threadIdx.x;
-        const int cl = t < kLevels ? sLcnt[t] : 0;
-        const int hl = t < kLevels ? P.lhist[(size_t)item * 256 + t] : 0;
-        const unsigned long long mine = ((unsigned long long)(unsigned)cl << 32) | (unsigned)hl;
-        unsigned long long incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long nb = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += nb;
-        }
-        if (t < kLevels && lane == 31) sWtot[t >> 5] = incl;
-        __syncthreads();
-        if (t < kLevels) {
-            unsigned long long excl = incl - mine;
-            for (int w = 0; w < (t >> 5); ++w) excl += sWtot[w];
-            sLloc[t] = (int)(excl >> 32);
-            // reserve this CTA's range of level t's list: one returning atomic on the level's cursor
-            if (cl) sLbase[t] = (int)(unsigned)excl + atomicAdd(P.lhist + (size_t)item * 256 + kLevels + t, cl);
-        }
-        __syncthreads();
-        // staged through shared memory (the candidate-union buffer, not yet in use) so that each level's run leaves as
-        // consecutive 2-byte stores: scattering straight from the registers cost one 32-byte sector per vertex in the L2
-        unsigned short *sStage = reinterpret_cast<unsigned short *>(sPairs);
-        int *sStagePos = reinterpret_cast<int *>(sPairs) + kCountChunk / 2;
-#pragma unroll
-        for (int q = 0; q < kCountVPT; ++q)
-            if (levq[q]) {
-                const int i = sLloc[levq[q]] + rankq[q];
-                sStage[i] = (unsigned short)buq[q];
-                sStagePos[i] = sLbase[levq[q]] + rankq[q];
-            }
-        __syncthreads();
-        const int total = sLloc[kLevels - 1] + sLcnt[kLevels - 1];
-        unsigned short *__restrict__ vlist = reinterpret_cast<unsigned short *>(P.up + base);
-        for (int i = threadIdx.x; i < total; i += 256) vlist[sStagePos[i]] = sStage[i];
-        __syncthreads();
-    }
 #pragma unroll
     for (int q = 0; q < kCountVPT; ++q) {
         const int v = v_beg + q * 256 + threadIdx.x;
@@ -970,8 +992,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             hooklev = reinterpret_cast<unsigned char *>(birth + nba);
         }
         unsigned char *blev = hooklev + nba;                                      // level | sign << 7 of the peak
-        // basin of every active vertex, bucketed by level: built by K_D in the storage of `up` (see pipe_count_kernel)
-        const unsigned short *__restrict__ elist = reinterpret_cast<const unsigned short *>(P.up + (size_t)item * P.vstride);
+        // basin of every active vertex, bucketed by level: built by K_C (see pipe_basin_kernel)
+        const unsigned short *__restrict__ elist = P.vlist + (size_t)item * P.vstride;
 
         for (int i = tid; i < 2 * kLevels; i += nthr)
             sHHd[i / kLevels][i % kLevels] = (double)P.tab_HH[(e0 + i / kLevels) * kLevels + i % kLevels];
@@ -1015,7 +1037,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         for_each_batched(pairs, NP, [&](unsigned long long p) { atomicAdd(&sCurP[(int)(p >> 48)], 1); });
         __syncthreads();
         PIPE_TICK(21)
-        // vertices per level: the map's histogram from K_A (the lists themselves were written by K_D)
+        // vertices per level: the map's histogram from K_A (the lists themselves were written by K_C)
         if (tid < kLevels) sCurE[tid] = P.lhist[(size_t)item * 256 + tid];
         __syncthreads();
         PIPE_TICK(22)
@@ -1304,7 +1326,8 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
     pipe_levels_kernel<<<dim3(chunksA, p.B, p.S), 256, 0, stream>>>(p, chunksA);
     if (p.max_degree > 0 && p.max_degree <= 6) pipe_ascent_kernel<true><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
     else pipe_ascent_kernel<false><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
-    pipe_basin_kernel<<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
+    const int chunksC = (p.Vmax + kBasinChunk - 1) / kBasinChunk;
+    pipe_basin_kernel<<<dim3(chunksC, p.B, p.S), 256, 0, stream>>>(p, chunksC);
     const int chunksD = (p.Vmax + kCountChunk - 1) / kCountChunk;
     if (p.want_vertex_pass) pipe_count_kernel<true><<<dim3(chunksD, p.B, p.S), 256, 0, stream>>>(p, chunksD);
     else pipe_count_kernel<false><<<dim3(chunksD, p.B, p.S), 256, 0, stream>>>(p, chunksD);
