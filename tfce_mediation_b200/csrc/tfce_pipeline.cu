@@ -1130,6 +1130,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             }
             // ================= F2b: sizes =================================================================
             {
+                // the small geometry keeps the live lists in global memory (L2): the first entry of the hooked-roots pass
+                // below is requested now, so that its latency passes behind the vertex loop
+                const int na2 = sNalive[cur];
+                int bbpre = -1;
+                if (kSmall && tid < na2) bbpre = (int)__ldcg(alive[cur] + tid);
                 const int ebeg = sEstart[lev], eend = sEstart[lev + 1];
                 int it = 0;
                 for (int ew = ebeg + (tid & ~31); ew < eend; ew += nthr, ++it) { // warp-uniform trip counts (ballots below)
@@ -1158,9 +1163,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                 // older roots hooked in this level hand their size and their leader over (a root of this very level has
                 // neither yet); they are still on the live list of the previous level
                 const unsigned short *__restrict__ al = alive[cur];
-                const int na = sNalive[cur];
+                const int na = na2;
                 for (int i = tid; i < na; i += nthr) {
-                    const int bb = kSmall ? (int)__ldcg(al + i) : (int)al[i];
+                    const int bb = kSmall ? (i == tid ? bbpre : (int)__ldcg(al + i)) : (int)al[i];
                     if (hooklev[bb] == lev) {
                         const int rr = pf_find(bparent, bb);
                         atomicAdd(bsize + rr, bsize[bb]);
@@ -1180,10 +1185,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                 const int na = sNalive[cur];
                 const int nb = sBstart[lev + 1] - sBstart[lev];   // roots born at this level
                 const int tot = na + nb;
+                // small geometry: request this thread's first list entry (L2), run the next level's unions while it is in
+                // flight.  The order inside the interval is free: the unions of level lev+1 touch neither the sizes nor
+                // the leader sums, and the hooks they log carry level lev+1 > lev.
+                int bbfirst = -1;
+                if (kSmall) {
+                    if (tid < na) bbfirst = (int)__ldcg(al + tid);
+                    else if (tid < tot) bbfirst = (int)__ldcg(birth + sBstart[lev] + tid - na);
+                    if (lev + 1 < nlev) do_unions(lev + 1);
+                }
                 for (int iw = (tid & ~31); iw < tot; iw += nthr) { // warp-uniform trip counts
                     const int i = iw + lane;
                     int bb = -1;
-                    if (i < na) bb = kSmall ? (int)__ldcg(al + i) : (int)al[i];
+                    if (kSmall && iw == (tid & ~31)) bb = bbfirst;
+                    else if (i < na) bb = kSmall ? (int)__ldcg(al + i) : (int)al[i];
                     else if (i < tot) bb = kSmall ? (int)__ldcg(birth + sBstart[lev] + i - na) : (int)birth[sBstart[lev] + i - na];
                     const bool live = bb >= 0 && hooklev[bb] > lev; // 255 = never hooked
                     if (live) {
@@ -1216,7 +1231,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                     }
                 }
             }
-            if (lev + 1 < nlev) do_unions(lev + 1);
+            if (!kSmall && lev + 1 < nlev) do_unions(lev + 1);
             cp_async_wait_all(); // this thread's pow(size, E) fetches
             __syncthreads();
             if (tid == 0) sNalive[cur] = 0; // becomes the next "next" list (first touched again after the next barrier)
