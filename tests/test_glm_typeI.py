@@ -190,3 +190,34 @@ def test_tm_models_randomise_glm_driver_rows(tmp_path, monkeypatch, gstat):
         for j in range(3):
             got = np.array([float(l) for l in open("%s/perm_Tstat_con%d_TFCE_maxVertex.csv" % (out, j + 1))])
             assert np.allclose(got, want_t[:, j, :].reshape(-1), rtol=1e-5, atol=6e-5)
+
+
+@pytest.mark.gpu
+def test_tm_models_randomise_glm_driver_volume_rows(tmp_path, monkeypatch):
+    """-v (volume) input of the GLM branch: one voxel graph, no density weights, '%.4f' rows of maxVoxel files."""
+    from tfce_mediation_b200.tmanalysis import tm_models_randomise as drv
+    mask = synth.skeleton_mask(shape=(24, 28, 24), frac=0.35, seed=5, sigma=2.0, margin=3)
+    csr = oracle.adjacency_to_csr(oracle.voxel_adjacency(mask, 26))
+    V = int(mask.sum())
+    n = 32
+    rs = np.random.RandomState(12)
+    y = rs.standard_normal((n, V)).astype(np.float32)
+    exog = [rs.standard_normal((n, 1)), rs.standard_normal((n, 2))]
+    d = os.path.join(str(tmp_path), "tmtemp_GLM_volume")
+    os.makedirs(d)
+    np.save(d + "/exog_flat.npy", np.column_stack(exog)); np.save(d + "/exog_shape.npy", np.array([1, 2]))
+    np.save(d + "/varnames.npy", np.array(["x", "pair"])); np.save(d + "/gstat.npy", np.array("f"))
+    np.save(d + "/data.npy", y); np.save(d + "/optstfce.npy", np.array([2, 0.5]))
+    np.save(d + "/dmy_covariates.npy", np.array(None, dtype=object), allow_pickle=True)
+    np.save(d + "/adjac.npy", _obj(synth.csr_to_lists(csr)), allow_pickle=True)
+    monkeypatch.chdir(tmp_path)
+    opts = drv.getArgumentParser(argparse.ArgumentParser()).parse_args(["-r", "1", "3", "-v", "-glm", "--seed", "8"])
+    drv.run(opts)
+    run = helpers.oracle_run(2, 0.5, csr)
+    for j, name in enumerate(["x", "pair"]):
+        got = np.array([float(l) for l in open("output_GLM_volume/perm_GLM/perm_Fstat_%s_TFCE_maxVoxel.csv" % name)])
+        want = []
+        for p in range(1, 4):
+            Fvar = oracle.glm_typeI(y, exog, None, rand_array=oracle.permutation_indices(p * 1000 + 8, n))[1]
+            want.append(oracle.perm_max_voxel(Fvar[j], run))
+        assert np.allclose(got, np.array(want), rtol=1e-5, atol=6e-5)

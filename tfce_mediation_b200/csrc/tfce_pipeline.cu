@@ -5,19 +5,22 @@
 // is done by flat, barrier-free streaming kernels over all (statistic row, surface, vertex) triples of a
 // block of maps -- full occupancy, coalesced rows, no level loop:
 //
-//   K_A  levels   activation level per vertex (fast_tfce.hpp:39-41: x > T_i, exact fp32 threshold table)
+//   K_A  levels   activation level per vertex (fast_tfce.hpp:39-41: x > T_i, exact fp32 threshold table) and the
+//                 map's histogram of the levels
 //   K_B  ascent   per vertex: the neighbour of the earliest level ("up"), the set of earlier neighbours;
 //                 vertices without an earlier neighbour are peaks and get compact basin ids
-//   K_C  basins   basin id per vertex = peak at the end of its ascent chain (read-only pointer chase)
-//   K_D  counts   table[level][basin] += 1;  every (vertex, earlier neighbour) pair that straddles two
-//                 basins becomes a candidate union (level, basin, basin)
+//   K_C  basins   basin id per vertex = peak at the end of its ascent chain (read-only pointer chase); max-only
+//                 maps: the basin ids of the active vertices bucketed by activation level (the sweep's input)
+//   K_D  counts   every (vertex, earlier neighbour) pair that straddles two basins becomes a candidate union
+//                 (level, basin, basin); class path only: table[level][basin] += 1
 //
 // and the sequential part -- the threshold sweep with its union-find, component sizes and the fp32 sums
 // in the reference's order -- runs on the few thousand basins of a map, entirely in shared memory:
 //
-//   K_S  sweep    one CTA per map: candidate unions bucketed by level; per level: unions, sizes from the
-//                 table row, one accumulator ("class") per component that gains vertices, and every live
-//                 class adds fl32(pow(size, E) * pow(T, H)) of its component (fast_tfce.hpp:70-84)
+//   K_S  sweep    one CTA per map: candidate unions bucketed by level; per level: unions, sizes from the level's
+//                 vertex list (max-only maps: one leader accumulator per live root, pipe_sweep_max_kernel) or from
+//                 the table row (class path: one accumulator per component that gains vertices), and every live
+//                 root / class adds fl32(pow(size, E) * pow(T, H)) of its component (fast_tfce.hpp:70-84)
 //   K_G  output   (only with vertex weights or when the maps are requested) per vertex value lookup
 //
 // Values are bit-identical to the reference: a vertex activated at level l receives, one fp32 add per level

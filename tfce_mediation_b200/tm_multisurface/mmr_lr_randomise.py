@@ -36,9 +36,70 @@ def getArgumentParser(ap=ap.ArgumentParser(description=DESCRIPTION)):
     ap.add_argument("-im", "--inputmediation", nargs=3, metavar=('{I|M|Y}', 'pred.csv', 'dep.csv'),
                     help="Mediation instead of regression (default: tmi_temp/opts.npy): one row per shuffle and surface "
                          "in perm_maxTFCE_surf{i}_{medtype}_zstat.csv (tm_func.py:269-305)")
+    ap.add_argument("--tmifile", nargs=1, metavar=('*.tmi'),
+                    help="Build the tmi_temp/ state from this TMI container first (what the reference's `mmr-lr` front end "
+                         "does, tm_mmr_rand_low_ram.py:138-199) when it does not exist yet")
+    ap.add_argument("-c", "--covariates", nargs=1, metavar=('*.csv'), help="With --tmifile: covariates of no interest")
+    ap.add_argument("--subset", nargs=1, metavar=('*.csv'), help="With --tmifile: keep the subjects whose entry is finite")
+    ap.add_argument("--noweight", action="store_true", help="With --tmifile: no vertex-density weighting")
+    ap.add_argument("-sa", "--setadjacencyobjs", nargs="+", type=int, metavar=('INT'),
+                    help="With --tmifile: adjacency object of every mask")
     ap.add_argument("--tfce", nargs="+", type=float, help="H E [H E ...]; default: tmi_temp/opts.npy")
     ap.add_argument("--assigntfcesettings", nargs="+", type=int, help="TFCE setting index per surface")
     return ap
+
+
+def setup_from_tmi(tmifile, tmitemp="tmi_temp", covariates=None, subset=None, noweight=False, setadjacencyobjs=None):
+    """The memory-mapping step of the reference's mmr-lr front end (tm_mmr_rand_low_ram.py:138-199): split a TMI
+    container into per-surface {i}_data_temp.npy (float32, subjects x vertices; residualised on the covariates when
+    given), {i}_mask_temp.npy, {i}_adjacency_temp.npy and {i}_vdensity_temp.npy (neighbour-count density weights,
+    1 - d/max(d) + mean(d)/max(d), or [1] with noweight).  Returns the number of surfaces."""
+    from ..tm_func import create_position_array
+    from ..tm_io import read_tm_filetype
+    _, image_array, masking_array, _, _, _, _, _, adjacency_array, _, _ = read_tm_filetype(tmifile, verbose=False)
+    position_array = create_position_array(masking_array)
+    if setadjacencyobjs:
+        if len(setadjacencyobjs) != len(masking_array):
+            raise SystemExit("Error: # of masking arrays (%d) must and list of matching adjacency (%d) must be equal."
+                             % (len(masking_array), len(setadjacencyobjs)))
+        adjacent_range = [int(a) for a in setadjacencyobjs]
+    else:
+        adjacent_range = list(range(len(adjacency_array)))
+    os.makedirs(tmitemp, exist_ok=True)
+    for i in range(len(masking_array)):
+        if not noweight:
+            adj = adjacency_array[adjacent_range[i]]
+            temp_vdensity = np.array([len(adj[j]) for j in range(adj.shape[0])], dtype=np.float64)
+            if masking_array[i].shape[2] == 1:
+                temp_vdensity = temp_vdensity[masking_array[i][:, 0, 0] == True]  # noqa: E712
+        else:
+            temp_vdensity = np.array([1])
+        vdensity = np.array((1 - (temp_vdensity / temp_vdensity.max()) + (temp_vdensity.mean() / temp_vdensity.max())),
+                            dtype=np.float32)
+        np.save("%s/%s_vdensity_temp.npy" % (tmitemp, i), vdensity)
+        if masking_array[i].shape[2] == 1:          # vertex image: mask of shape [V, 1, 1]
+            outmask = masking_array[i][:, 0, 0]
+        else:
+            outmask = masking_array[i][masking_array[i] == True]  # noqa: E712
+        np.save("%s/%s_mask_temp.npy" % (tmitemp, i), outmask)
+    for num, j in enumerate(adjacent_range):
+        np.save("%s/%s_adjacency_temp.npy" % (tmitemp, num), np.copy(adjacency_array[j]), allow_pickle=True)
+    x_covars = None
+    if covariates is not None:
+        covars = np.genfromtxt(covariates, delimiter=',')
+        x_covars = np.column_stack([np.ones(len(covars)), covars])
+    keep = np.isfinite(np.genfromtxt(str(subset), delimiter=',')) if subset is not None else None
+    for data_count in range(len(masking_array)):
+        data_array = image_array[0][position_array[data_count]:position_array[data_count + 1], :]
+        if keep is not None:
+            data_array = data_array[:, keep]
+        if x_covars is not None:
+            from ..cynumstats import resid_covars
+            merge_y = np.asarray(resid_covars(x_covars, data_array))
+        else:
+            merge_y = data_array.T
+        np.save("%s/%s_data_temp.npy" % (tmitemp, data_count), merge_y.astype(np.float32, order="C"))
+    return len(masking_array)
 
 
 def load_setup(opts):
@@ -73,8 +134,16 @@ def run(opts):
     start_time = time()
     np.seterr(divide="ignore", invalid="ignore")
     from ..engine import PermutationEngine
-    pred_x, tfce, assign, surfaces = load_setup(opts)
     tmp = opts.tmitemp
+    if opts.tmifile and not os.path.exists("%s/0_data_temp.npy" % tmp):
+        if parallel.world()[0] == 0:
+            setup_from_tmi(opts.tmifile[0], tmp, opts.covariates[0] if opts.covariates else None,
+                           opts.subset[0] if opts.subset else None, opts.noweight, opts.setadjacencyobjs)
+        if parallel.world()[1] > 1:
+            parallel.init_process_group()
+            import torch.distributed as dist
+            dist.barrier()
+    pred_x, tfce, assign, surfaces = load_setup(opts)
     datas, surfs, off = [], [], 0
     for sn in surfaces:
         data = C.load("%s/%d_data_temp.npy" % (tmp, sn))
