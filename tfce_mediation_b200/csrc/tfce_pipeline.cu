@@ -1139,40 +1139,56 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                 int bbpre = -1;
                 if (kSmall && tid < na2) bbpre = (int)__ldcg(alive[cur] + tid);
                 const int ebeg = sEstart[lev], eend = sEstart[lev + 1];
-                int it = 0;
-                for (int ew = ebeg + (tid & ~31); ew < eend; ew += nthr, ++it) { // warp-uniform trip counts (ballots below)
-                    const int ie = ew + lane;
-                    const bool act = ie < eend;
-                    int r = -1;
-                    if (act) {
-                        int bas;
-                        if (it == 0) bas = (int)((lev & 1) ? eqB[0] : eqA[0]);
-                        else if (it == 1) bas = (int)((lev & 1) ? eqB[1] : eqA[1]);
-                        else if (it == 2) bas = (int)((lev & 1) ? eqB[2] : eqA[2]);
-                        else if (it == 3) bas = (int)((lev & 1) ? eqB[3] : eqA[3]);
-                        else bas = (int)elist[ie];
-                        r = pf_find(bparent, bas);
+                // Passes of nthr entries, four at a time: the first four entries of a thread were prefetched two levels ago,
+                // later groups are loaded together (four independent L2 loads in flight instead of one exposed load per
+                // pass -- the dense late levels have ten and more passes).
+                for (int eg = ebeg + (tid & ~31), grp = 0; eg < eend; eg += 4 * nthr, ++grp) { // warp-uniform trip counts
+                    unsigned e4[4];
+                    if (grp == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) e4[q] = (lev & 1) ? eqB[q] : eqA[q];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { e4[q] = 0u; PIPE_LD_U16(e4[q], elist + eg + q * nthr + lane, eg + q * nthr + lane < eend); }
                     }
-                    // Late levels send most vertices to a few giant roots: same-address shared-memory atomics would
-                    // serialise.  The lanes that agree with the first active lane's root are counted by one ballot.
-                    // (A second round for the other sign's giant root was measured slower: 8.07 vs 7.87 ms per 1,024 maps.)
-                    const unsigned am = __ballot_sync(0xffffffffu, act);
-                    const int lead = __ffs(am) - 1;
-                    const int r0 = __shfl_sync(0xffffffffu, r, lead);
-                    const unsigned same = __ballot_sync(0xffffffffu, act && r == r0);
-                    if (lane == lead) atomicAdd(bsize + r0, __popc(same));
-                    if (act && r != r0) atomicAdd(bsize + r, 1);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int ew = eg + q * nthr;
+                        if (ew >= eend) break; // warp-uniform
+                        const bool act = ew + lane < eend;
+                        int r = -1;
+                        if (act) r = pf_find(bparent, (int)e4[q]);
+                        // Late levels send most vertices to a few giant roots: same-address shared-memory atomics would
+                        // serialise.  The lanes that agree with the first active lane's root are counted by one ballot.
+                        // (A second round for the other sign's giant root was measured slower: 8.07 vs 7.87 ms per 1,024 maps.)
+                        const unsigned am = __ballot_sync(0xffffffffu, act);
+                        const int lead = __ffs(am) - 1;
+                        const int r0 = __shfl_sync(0xffffffffu, r, lead);
+                        const unsigned same = __ballot_sync(0xffffffffu, act && r == r0);
+                        if (lane == lead) atomicAdd(bsize + r0, __popc(same));
+                        if (act && r != r0) atomicAdd(bsize + r, 1);
+                    }
                 }
                 // older roots hooked in this level hand their size and their leader over (a root of this very level has
                 // neither yet); they are still on the live list of the previous level
                 const unsigned short *__restrict__ al = alive[cur];
                 const int na = na2;
-                for (int i = tid; i < na; i += nthr) {
-                    const int bb = kSmall ? (i == tid ? bbpre : (int)__ldcg(al + i)) : (int)al[i];
-                    if (hooklev[bb] == lev) {
-                        const int rr = pf_find(bparent, bb);
-                        atomicAdd(bsize + rr, bsize[bb]);
-                        atomicMax(racc + rr, racc[bb]); // sums are >= 0: integer order == float order
+                for (int i0 = tid; i0 < na; i0 += 4 * nthr) { // four list entries in flight per thread
+                    int b4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = i0 + q * nthr;
+                        b4[q] = -1;
+                        if (i < na) b4[q] = kSmall ? ((q == 0 && i0 == tid) ? bbpre : (int)__ldcg(al + i)) : (int)al[i];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int bb = b4[q];
+                        if (bb >= 0 && hooklev[bb] == lev) {
+                            const int rr = pf_find(bparent, bb);
+                            atomicAdd(bsize + rr, bsize[bb]);
+                            atomicMax(racc + rr, racc[bb]); // sums are >= 0: integer order == float order
+                        }
                     }
                 }
             }
@@ -1197,12 +1213,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                     else if (tid < tot) bbfirst = (int)__ldcg(birth + sBstart[lev] + tid - na);
                     if (lev + 1 < nlev) do_unions(lev + 1);
                 }
-                for (int iw = (tid & ~31); iw < tot; iw += nthr) { // warp-uniform trip counts
-                    const int i = iw + lane;
-                    int bb = -1;
-                    if (kSmall && iw == (tid & ~31)) bb = bbfirst;
-                    else if (i < na) bb = kSmall ? (int)__ldcg(al + i) : (int)al[i];
-                    else if (i < tot) bb = kSmall ? (int)__ldcg(birth + sBstart[lev] + i - na) : (int)birth[sBstart[lev] + i - na];
+                for (int ig = (tid & ~31); ig < tot; ig += 4 * nthr) { // warp-uniform trip counts; four entries in flight
+                  int b4[4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                      const int i = ig + q * nthr + lane;
+                      b4[q] = -1;
+                      if (kSmall && q == 0 && ig == (tid & ~31)) b4[q] = bbfirst;
+                      else if (i < na) b4[q] = kSmall ? (int)__ldcg(al + i) : (int)al[i];
+                      else if (i < tot) b4[q] = kSmall ? (int)__ldcg(birth + sBstart[lev] + i - na) : (int)birth[sBstart[lev] + i - na];
+                  }
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    if (ig + q * nthr >= tot) break; // warp-uniform
+                    const int bb = b4[q];
                     const bool live = bb >= 0 && hooklev[bb] > lev; // 255 = never hooked
                     if (live) {
                         const int cb = blev[bb];
@@ -1232,6 +1256,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                         basepos = __shfl_sync(0xffffffffu, basepos, 0);
                         if (live) nx[basepos + __popc(lm & ((1u << lane) - 1u))] = (unsigned short)bb;
                     }
+                  }
                 }
             }
             if (!kSmall && lev + 1 < nlev) do_unions(lev + 1);
