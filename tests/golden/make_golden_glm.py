@@ -38,6 +38,25 @@ def main():
                                  for r in perms])
     out["perm_T"] = np.stack([pyfunc.glm_typeI(data, exog, dmy_covariates=cov, output_fvalues=False,
                                                output_tvalues=True, verbose=False, rand_array=r) for r in perms])
+    # tm-models mediation statistic (tm_models_randomise.py:435-503): reference glm_typeI t-values + calc_indirect
+    left = rs.standard_normal((n, 1))
+    right = 0.6 * left + rs.standard_normal((n, 1))
+    for medtype in ("I", "M", "Y"):
+        zs = []
+        for r in perms[:3]:
+            lv = left[r]
+            rv = right[r] if medtype == "Y" else right
+            tv = lambda endog, ex: pyfunc.glm_typeI(endog, ex, dmy_covariates=cov, output_fvalues=False,  # noqa: E731
+                                                    output_tvalues=True, verbose=False)[1]
+            if medtype == "I":
+                ta, tb = tv(data, [lv]), tv(data, [lv, rv])
+            elif medtype == "M":
+                ta, tb = tv(data, [lv]), tv(data, [rv, lv])
+            else:
+                ta, tb = tv(rv, [lv]), tv(data, [rv, lv])
+            zs.append(pyfunc.calc_indirect(ta, tb, alg="aroian"))
+        out["med_%s" % medtype] = np.stack(zs)
+    out["med_left"], out["med_right"] = left, right
     np.savez_compressed(os.path.join(HERE, "glm_typeI.npz"), data=data, exog0=exog[0], exog1=exog[1], exog2=exog[2],
                         cov=cov, perms=perms, **out)
     print("glm_typeI.npz written:", {k: np.shape(v) for k, v in out.items()})

@@ -221,3 +221,73 @@ def test_tm_models_randomise_glm_driver_volume_rows(tmp_path, monkeypatch):
             Fvar = oracle.glm_typeI(y, exog, None, rand_array=oracle.permutation_indices(p * 1000 + 8, n))[1]
             want.append(oracle.perm_max_voxel(Fvar[j], run))
         assert np.allclose(got, np.array(want), rtol=1e-5, atol=6e-5)
+
+
+# ------------------------------------------------------------------------------------------- tm-models mediation
+def test_oracle_tm_models_sobelz_matches_reference_golden():
+    g, _ = _golden()
+    for m in "IMY":
+        for i, r in enumerate(g["perms"][:3]):
+            lv = g["med_left"][r]
+            rv = g["med_right"][r] if m == "Y" else g["med_right"]
+            assert np.array_equal(oracle.tm_models_sobelz(m, g["data"], lv, rv, g["cov"]), g["med_%s" % m][i])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("medtype", ["I", "M", "Y"])
+def test_sobelz_designs_matches_reference_golden(medtype):
+    """glm_typeI t-values + calc_indirect of the reference (golden) against the fused two-fit kernel on general designs."""
+    from tfce_mediation_b200.engine import PermutationEngine
+    g, _ = _golden()
+    data, cov, left, right = g["data"], g["cov"], g["med_left"], g["med_right"]
+    n = data.shape[0]
+    eng = PermutationEngine(data, None)
+    perms = g["perms"][:3]
+    ones = np.ones((3, n, 1))
+    lv = left[perms]
+    rv = right[perms] if medtype == "Y" else np.broadcast_to(right, (3,) + right.shape)
+    cv = np.broadcast_to(cov, (3,) + cov.shape)
+    XA = np.concatenate([ones, lv, cv], axis=2)
+    XB = np.concatenate([ones, lv, rv, cv], axis=2) if medtype == "I" else np.concatenate([ones, rv, lv, cv], axis=2)
+    ta = None
+    if medtype == "Y":
+        ta = np.array([oracle.glm_typeI(rv[p], [lv[p]], cov, output_fvalues=False, output_tvalues=True)[1][0] for p in range(3)])
+        XA = None
+    _, z64 = eng.sobelz_designs(XA, XB, ta, "aroian", want_f64=True)
+    z = z64[:, :data.shape[1]].cpu().numpy()
+    assert np.all(np.abs(z - g["med_%s" % medtype]) <= 1e-9 * np.maximum(1.0, np.abs(g["med_%s" % medtype])))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("medtype", ["M", "Y"])
+def test_tm_models_randomise_mediation_driver_rows(tmp_path, monkeypatch, medtype):
+    from tfce_mediation_b200.tmanalysis import tm_models_randomise as drv
+    st = _glm_state()
+    n = st["n"]
+    rs = np.random.RandomState(21)
+    left = rs.standard_normal((n, 1))
+    right = 0.5 * left + rs.standard_normal((n, 1))
+    d = os.path.join(str(tmp_path), "tmtemp_mediation_area")
+    os.makedirs(d)
+    adj = synth.csr_to_lists(st["csr"])
+    np.save(d + "/dmy_leftvar.npy", left); np.save(d + "/dmy_rightvar.npy", right); np.save(d + "/medtype.npy", np.array(medtype))
+    np.save(d + "/data.npy", st["y"]); np.save(d + "/optstfce.npy", np.array([2, 0.67]))
+    np.save(d + "/dmy_covariates.npy", st["cov"]); np.save(d + "/num_vertex_lh.npy", int(st["keep_lh"].sum()))
+    np.save(d + "/mask_lh.npy", st["keep_lh"]); np.save(d + "/mask_rh.npy", st["keep_rh"])
+    np.save(d + "/adjac_lh.npy", _obj(adj), allow_pickle=True); np.save(d + "/adjac_rh.npy", _obj(adj), allow_pickle=True)
+    np.save(d + "/vdensity_lh.npy", st["dens"]); np.save(d + "/vdensity_rh.npy", st["dens"])
+    monkeypatch.chdir(tmp_path)
+    opts = drv.getArgumentParser(argparse.ArgumentParser()).parse_args(["-r", "1", "4", "-s", "area", "-med", "--seed", "6"])
+    drv.run(opts)
+    run = helpers.oracle_run(2, 0.67, st["csr"])
+    nlh = int(st["keep_lh"].sum())
+    want, lv, rv = [], left, right
+    for p in range(1, 5):                                   # the reference permutes its variables in place (:436,:459,:480-481)
+        r = oracle.permutation_indices(p * 1000 + 6, n)
+        lv = lv[r]
+        if medtype == "Y":
+            rv = rv[r]
+        z = oracle.tm_models_sobelz(medtype, st["y"], lv, rv, st["cov"])
+        want.append(oracle.perm_max_vertex(z, nlh, st["keep_lh"], st["keep_rh"], run, run, st["dens"], st["dens"]))
+    got = np.array([float(l) for l in open("output_mediation_area/perm_mediation/perm_Zstat_%s_TFCE_maxVertex.csv" % medtype)])
+    assert np.allclose(got, np.array(want), rtol=1e-5, atol=6e-5)

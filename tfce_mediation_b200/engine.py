@@ -598,6 +598,16 @@ class PermutationEngine(object):
             XB = np.stack([ones, dep, xp], axis=2)
         else:
             raise ValueError("Invalid mediation type")
+        return self.sobelz_designs(XA, XB, ta_scalar, alg, want_f64, caller_order)
+
+    def sobelz_designs(self, XA, XB, ta_scalar=None, alg="aroian", want_f64=False, caller_order=True):
+        """Sobel-family z from two stacks of per-shuffle designs (intercept in column 0): path A = t of XA's first
+        regressor (or the per-shuffle scalars ta_scalar when XA is None), path B = t of XB's first regressor.
+        XA float64 [P, n, kA], XB [P, n, kB], (kA - 1) + (kB - 1) <= 8.  Serves calc_sobelz (pyfunc.py:130-162) and the
+        tm-models mediation branch (tm_models_randomise.py:430-503: glm_typeI t-values + calc_indirect)."""
+        import torch
+        n = self.Y.n
+        P = XB.shape[0]
         sB = design_stack(XB, center=True)
         if XA is not None:
             sA = design_stack(XA, center=True)
@@ -630,6 +640,49 @@ class PermutationEngine(object):
             z32 = self.to_caller_order(z32)
             z64 = self.to_caller_order(z64) if z64 is not None else None
         return (z32, z64) if want_f64 else z32
+
+    def tm_models_mediation_block(self, medtype, leftvar, rightvar, dmy_covariates, perm_idx, alg="aroian", download=True):
+        """One block of the tm-models mediation loop (tmanalysis/tm_models_randomise.py:430-520): shuffle p uses
+        leftvar[perm_idx[p]] (and rightvar[perm_idx[p]] for medtype 'Y'); path A / path B are glm_typeI t-values of the
+        designs [1, left, cov] and [1, left, right, cov] ('I') or [1, right, left, cov] ('M', 'Y'); 'Y' takes path A from
+        the regression of rightvar on [1, left, cov] (one scalar per shuffle).  Sobel z (calc_indirect, Aroian by
+        default) -> one-sided TFCE -> scaled max: float32 [P, S]."""
+        n = self.Y.n
+        left = np.asarray(leftvar, dtype=np.float64).reshape(n, -1)
+        right = np.asarray(rightvar, dtype=np.float64).reshape(n, -1)
+        cov = None if dmy_covariates is None else np.asarray(dmy_covariates, dtype=np.float64).reshape(n, -1)
+        perm_idx = np.asarray(perm_idx)
+        P = perm_idx.shape[0]
+        ones = np.ones((P, n, 1))
+        lv = left[perm_idx]                                                  # [P, n, kL]
+        rv = right[perm_idx] if medtype == "Y" else np.broadcast_to(right, (P,) + right.shape)
+        tail = [np.broadcast_to(cov, (P,) + cov.shape)] if cov is not None else []
+        XA = np.concatenate([ones, lv] + tail, axis=2)
+        if medtype == "I":
+            XB = np.concatenate([ones, lv, rv] + tail, axis=2)
+        elif medtype in ("M", "Y"):
+            XB = np.concatenate([ones, rv, lv] + tail, axis=2)
+        else:
+            raise ValueError("Invalid mediation type")
+        ta_scalar = None
+        if medtype == "Y":
+            if right.shape[1] != 1:
+                raise ValueError("medtype 'Y' needs a single-column dependent variable")
+            k = XA.shape[2]
+            ta_scalar = np.empty(P, dtype=np.float64)
+            for p in range(P):                       # n x 1 regressions on the host (tval_int's arithmetic, cynumstats.pyx:59-64)
+                X = XA[p]
+                invXX = np.linalg.inv(X.T @ X)
+                a = (invXX @ X.T) @ rv[p]
+                sigma2 = np.sum((rv[p] - X @ a) ** 2, axis=0) / (n - k)
+                se = np.float32(np.sqrt(sigma2[0] * invXX[1, 1]))
+                ta_scalar[p] = a[1, 0] / se
+            XA = None
+        z32 = self.sobelz_designs(XA, XB, ta_scalar, alg, caller_order=False)
+        mx, status, _ = self.plan.run(z32, two_sided=False)
+        self.last_status = status
+        mx = mx[:, :, 0]
+        return self._download(mx.contiguous()) if download else mx
 
     def mediation_block(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", want_maps=False, download=True):
         """Sobel-z + one-sided TFCE + scaled max for a block of shuffles

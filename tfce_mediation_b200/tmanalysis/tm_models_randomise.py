@@ -6,7 +6,8 @@ output_GLM_*/perm_GLM/perm_{Tstat_con<j>,Fstat_<name>}_TFCE_max{Vertex,Voxel}.cs
 of shuffles run through the batched GPU engine (one fused fit per block: partial F of every variable from the extra
 sum of squares, t of the variables' columns), then TFCE and the scaled maximum.  Under torchrun the permutation range
 is sharded across ranks and rank 0 writes the rows in order.  The other model families of the reference script
-(mediation, cosinor, repeated-measures ANCOVA: tm_models_randomise.py:274-677) are not built yet and exit loudly."""
+(cosinor, repeated-measures ANCOVA: tm_models_randomise.py:274-427,522-677) are not built yet and exit loudly; the
+mediation branch (-med, :430-520) is run_mediation below."""
 import argparse as ap
 import os
 from time import time
@@ -45,8 +46,11 @@ def run(opts):
     start_time = time()
     np.seterr(divide="ignore", invalid="ignore")
     from ..engine import PermutationEngine
+    if opts.mediation:
+        return run_mediation(opts, start_time)
     if not opts.generalizedlinearmodel:
-        raise NotImplementedError("tm_models_randomise: only the GLM branch (-glm) is built on the B200 path")
+        raise NotImplementedError("tm_models_randomise: only the GLM (-glm) and mediation (-med) branches are built on the "
+                                  "B200 path")
     if opts.tmi:
         raise NotImplementedError("tm_models_randomise: TMI input (-t) is not built on the B200 path")
     first, last = int(opts.range[0]), int(opts.range[1])
@@ -117,6 +121,67 @@ def run(opts):
         if all_f is not None:
             for j in range(nvar):                       # :258-272
                 C.append_rows("%s/perm_Fstat_%s_TFCE_%s.csv" % (outdir, varnames[j], suffix), all_f[:, j], "%.4f")
+        print("Finished. Randomization took %.1f seconds" % (time() - start_time))
+
+
+def _surfaces(opts, tempdir, H, E):
+    if opts.surface:
+        num_vertex_lh = int(C.load("%s/num_vertex_lh.npy" % tempdir))
+        return [C.masked_surface(C.load("%s/adjac_lh.npy" % tempdir), H, E, C.load("%s/mask_lh.npy" % tempdir),
+                                 C.load("%s/vdensity_lh.npy" % tempdir), 0),
+                C.masked_surface(C.load("%s/adjac_rh.npy" % tempdir), H, E, C.load("%s/mask_rh.npy" % tempdir),
+                                 C.load("%s/vdensity_rh.npy" % tempdir), num_vertex_lh)], "maxVertex"
+    return [C.masked_surface(C.load("%s/adjac.npy" % tempdir), H, E)], "maxVoxel"
+
+
+def run_mediation(opts, start_time):
+    """The mediation branch (-med), tm_models_randomise.py:92-100,430-520: perm_Zstat_<medtype>_TFCE_max{Vertex,Voxel}.csv,
+    one '%.4f' row per shuffle.  The reference permutes `dmy_leftvar = dmy_leftvar[rand_array]` IN PLACE, so shuffle i
+    sees the composition of all draws since the start of the range; the same composition is built here (every rank
+    replays the draws from the first permutation of the range)."""
+    from ..engine import PermutationEngine
+    if opts.tmi:
+        raise NotImplementedError("tm_models_randomise: TMI input (-t) is not built on the B200 path")
+    first, last = int(opts.range[0]), int(opts.range[1])
+    if opts.surface:
+        surface = str(opts.surface[0])
+        tempdir, outdir = "tmtemp_mediation_%s" % surface, "output_mediation_%s/perm_mediation" % surface
+    else:
+        tempdir, outdir = "tmtemp_mediation_volume", "output_mediation_volume/perm_mediation"
+    dmy_leftvar = C.load("%s/dmy_leftvar.npy" % tempdir)
+    dmy_rightvar = C.load("%s/dmy_rightvar.npy" % tempdir)
+    medtype = str(np.asarray(C.load("%s/medtype.npy" % tempdir)).reshape(-1)[0])
+    data = C.load("%s/data.npy" % tempdir)
+    optstfce = C.load("%s/optstfce.npy" % tempdir)
+    dmy_covariates = C.load("%s/dmy_covariates.npy" % tempdir)
+    if np.all(dmy_covariates) is None or dmy_covariates.ndim == 0:
+        dmy_covariates = None
+    surfs, suffix = _surfaces(opts, tempdir, float(optstfce[0]), float(optstfce[1]))
+    if opts.exchangeblock:
+        block_list = np.genfromtxt(opts.exchangeblock[0], dtype=str)
+        is_equal_sizes = check_blocks(block_list)
+    n = data.shape[0]
+    eng = PermutationEngine(data, surfs, two_sided=False)
+    rank, ws, a, b = C.shard(first, last)
+    if rank == 0:
+        os.makedirs(outdir, exist_ok=True)
+    composed = np.arange(n)
+    idx = []
+    for iter_perm in range(first, b + 1):
+        if opts.seed is not None:
+            np.random.seed(int(iter_perm * 1000 + opts.seed))
+        rand_array = rand_blocks(block_list, is_equal_sizes) if opts.exchangeblock else C.draw_row_permutation(n)
+        composed = composed[rand_array]              # x[r1][r2] == x[r1[r2]]
+        if iter_perm >= a:
+            idx.append(composed)
+    res = []
+    for c0 in range(0, len(idx), C.BLOCK):
+        res.append(eng.tm_models_mediation_block(medtype, dmy_leftvar, dmy_rightvar, dmy_covariates,
+                                                 np.stack(idx[c0:c0 + C.BLOCK])).max(axis=1))
+    local = np.concatenate(res, axis=0) if res else np.zeros((0,), dtype=np.float32)
+    allrows = parallel.gather_rows(local)
+    if rank == 0:
+        C.append_rows("%s/perm_Zstat_%s_TFCE_%s.csv" % (outdir, medtype, suffix), allrows, "%.4f")
         print("Finished. Randomization took %.1f seconds" % (time() - start_time))
 
 
