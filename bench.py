@@ -205,7 +205,7 @@ def run_reference(args):
                                    % (cores * per_worker, cores, per_worker)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------- B200 arm
@@ -413,12 +413,27 @@ def run_b200(args):
                              "share_of_step": fit_ms / (dev_ms / args.steps)}},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else printed to fd 1 during the run (e.g. NCCL's
+    version banner under torchrun) was redirected to stderr in main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)            # library chatter on stdout -> stderr; only emit() writes to the real stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
