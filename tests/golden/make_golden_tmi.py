@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Golden fixture for the TMI container reader: writes tests/golden/sample.tmi with the test-side writer
-(tests/helpers.write_tmi_binary, header grammar of tm_io.py:158-228) and stores what the REAL reference reader
+"""Golden fixture for the TMI container reader and writer: writes tests/golden/sample.tmi with the product writer
+(tfce_mediation_b200.tm_io.write_tm_filetype, header grammar of tm_io.py:158-228), checks that the REAL reference reader
+returns the inputs for it, and stores what the reference reader
 (/root/reference/tfce_mediation/tm_io.py:284-444 read_tm_filetype) returns for it in tests/golden/tmi_reader.npz.
 Build container only (needs /root/reference); import shims as in make_golden.py.
 
@@ -17,7 +18,6 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 sys.path.insert(0, ROOT)
 from make_golden import load_reference  # noqa: E402
-from tests import helpers  # noqa: E402
 from tfce_mediation_b200 import synth  # noqa: E402
 
 
@@ -47,9 +47,19 @@ def sample_inputs():
 def main():
     load_reference()
     tm_io = importlib.import_module("tfce_mediation.tm_io")
+    from tfce_mediation_b200.tm_io import write_tm_filetype
     path = os.path.join(HERE, "sample.tmi")
-    helpers.write_tmi_binary(path, **sample_inputs())
+    inp = sample_inputs()
+    # the file is written by the PRODUCT writer (deterministic: fixed history line) and read back by the REFERENCE reader
+    write_tm_filetype(path, columnids=inp["column_ids"], checkname=False, image_array=inp["data"], masking_array=inp["masks"],
+                      maskname=inp["masknames"], affine_array=inp["affines"], vertex_array=inp["vertices"],
+                      face_array=inp["faces"], surfname=inp["surfnames"], adjacency_array=inp["adjacency"],
+                      tmi_history=["history mode_add 20261017000000 1 2 1 1 2"], append_history=False)
     el, img, masks, masknames, aff, vert, face, surfnames, adj, hist, cols = tm_io.read_tm_filetype(path, verbose=False)
+    assert np.array_equal(img[0], inp["data"]) and all(np.array_equal(a, b) for a, b in zip(masks, inp["masks"]))
+    assert np.array_equal(vert[0], inp["vertices"][0].astype(np.float32)) and np.array_equal(face[0], inp["faces"][0])
+    assert np.array_equal(cols[0], inp["column_ids"]) and np.array_equal(aff[0], inp["affines"][0].astype(np.float32))
+    assert all(list(x) == list(y) for a, b in zip(adj, inp["adjacency"]) for x, y in zip(a, b))
     out = dict(elements=np.array(el), image=img[0], masknames=np.array(masknames), surfnames=np.array(surfnames),
                history=np.array(hist), affine0=aff[0], vertex0=vert[0], face0=face[0], columns=cols[0])
     for i, m in enumerate(masks):

@@ -103,3 +103,30 @@ def test_mmr_lr_from_tmi_rows_match_oracle(tmp_path, monkeypatch):
             rows = oracle.low_ram_max(data, mask, pred, run, vdensity, p, 40)
             want += [rows[0][0], rows[0][1]]
         assert np.allclose(got, np.array(want, dtype=np.float64), rtol=1e-5, atol=2e-6)
+
+
+def test_writer_reproduces_golden_container(tmp_path):
+    """write_tm_filetype (tm_io.py:72-282): the file the REFERENCE reader was verified to read back to the inputs
+    (tests/golden/make_golden_tmi.py) is reproduced byte for byte; an existing name is never overwritten silently."""
+    import sys
+    from tfce_mediation_b200.tm_io import read_tm_filetype, write_tm_filetype
+    sys.path.insert(0, G)
+    try:
+        from make_golden_tmi import sample_inputs
+    finally:
+        sys.path.remove(G)
+    inp = sample_inputs()
+    kw = dict(columnids=inp["column_ids"], image_array=inp["data"], masking_array=inp["masks"], maskname=inp["masknames"],
+              affine_array=inp["affines"], vertex_array=inp["vertices"], face_array=inp["faces"], surfname=inp["surfnames"],
+              adjacency_array=inp["adjacency"])
+    name = write_tm_filetype(str(tmp_path / "out"), tmi_history=["history mode_add 20261017000000 1 2 1 1 2"],
+                             append_history=False, **kw)
+    assert name.endswith("out.tmi")
+    assert open(name, "rb").read() == open(os.path.join(G, "sample.tmi"), "rb").read()
+    # appended history: counts net of what the passed history already records; existing file -> new_<name>
+    name2 = write_tm_filetype(name, tmi_history=["history mode_add 20261017000000 1 1 1 1 1"], **kw)
+    assert os.path.basename(name2) == "new_out.tmi"
+    hist = read_tm_filetype(name2, verbose=False)[9]
+    assert len(hist) == 2 and hist[1].split()[1] == "mode_add" and hist[1].split()[3:] == ["1", "1", "0", "0", "1"]
+    with pytest.raises(NotImplementedError):
+        write_tm_filetype(str(tmp_path / "a"), output_binary=False, **kw)

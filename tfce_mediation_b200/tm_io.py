@@ -132,3 +132,114 @@ def read_tm_filetype(tm_file, verbose=True):
         else:
             raise ValueError("Error unknown filetype: %s" % fmt)
     return (elements, o_img, o_mask, masknames, o_affine, o_vertex, o_face, surfnames, o_adj, history, o_cols)
+
+
+# ------------------------------------------------------------------------------------------------------------ writer
+def tm_filetype_version():
+    """tm_io.py:34-36."""
+    return "0.1"
+
+
+def check_outname(outname):
+    """pyfunc.py:315-326: never overwrite silently -- an existing name becomes new_<name> (which IS overwritten)."""
+    if os.path.exists(outname):
+        outpath, name = os.path.split(outname)
+        outname = ("new_%s" % name) if not outpath else ("%s/new_%s" % (outpath, name))
+        print("Output file aleady exists. Renaming output file to %s" % outname)
+        if os.path.exists(outname):
+            print("%s also exists. Overwriting the file." % outname)
+            os.remove(outname)
+    return outname
+
+
+def _as_list(x, single_ndim):
+    """The reference accepts one array or a list / object array of arrays (tm_io.py:106-139)."""
+    if x is None:
+        return []
+    if isinstance(x, np.ndarray) and x.dtype != object and x.ndim == single_ndim:
+        return [x]
+    return [np.asarray(a) if not isinstance(a, np.ndarray) else a for a in x]
+
+
+def _history_counts(tmi_history):
+    """Net (masks, affines, objects, adjacencies) already recorded by the history lines (tm_io.py:87-104)."""
+    tot = [0, 0, 0, 0]
+    for line in tmi_history:
+        w = line.split(" ")
+        if w[1] in ("mode_add", "mode_sub"):
+            sign = 1 if w[1] == "mode_add" else -1
+            for i in range(4):
+                tot[i] += sign * int(w[4 + i])
+        elif w[1] not in ("mode_replace", "mode_reorder"):
+            print("Error reading history. Mode %s is not understood. Count is reflect number of element in current file" % w[1])
+    return tot
+
+
+def write_tm_filetype(outname, columnids=[], imgtype=[], checkname=True, output_binary=True, image_array=[],
+                      masking_array=[], maskname=[], affine_array=[], vertex_array=[], face_array=[], surfname=[],
+                      adjacency_array=[], tmi_history=[], append_history=True):
+    """tm_io.py:72-282 write_tm_filetype, binary container: same header grammar, element order, dtypes (float32 data /
+    affines / vertices, uint8 masks, uint32 faces, pickled adjacency objects), transposed payloads and history line.
+    Two deliberate differences: (1) the reference cannot run under numpy >= 2 (`image_array == []` on arrays,
+    ragged `np.array(masks)`), this one can; (2) the reference stores the column ids BEFORE the adjacency objects while
+    its header -- and therefore its own reader, which consumes payloads in header order (tm_io.py:364-398) -- lists
+    them AFTER; here payloads follow the header order, so files with both are readable by either reader.
+    The ascii variant is not built.  Returns the file name written."""
+    from time import gmtime, strftime
+    if not output_binary:
+        raise NotImplementedError("write_tm_filetype: only the binary container is built")
+    image = None if (isinstance(image_array, list) and len(image_array) == 0) else np.asarray(image_array)
+    masks = _as_list(masking_array, 3)
+    affines = _as_list(affine_array, 2)
+    vertices = _as_list(vertex_array, 2)
+    faces = _as_list(face_array, 2)
+    adjacency = list(adjacency_array)      # a list (or object array) of adjacency objects, one per surface (tm_io.py:131-139)
+    cols = None if (isinstance(columnids, list) and len(columnids) == 0) else np.asarray(columnids)
+    tmi_history = list(tmi_history)
+    h_mask, h_affine, h_object, h_adj = _history_counts(tmi_history)
+    if not outname.endswith("tmi"):
+        outname += ".tmi"
+    if checkname:
+        outname = check_outname(outname)
+    head = ["tmi", "format binary_little_endian %s" % tm_filetype_version(), "comment made with TFCE_mediation"]
+    payloads = []
+    num_data = 0
+    if image is not None:
+        num_data = 1
+        nvert, nsub = (len(image), 1) if image.ndim == 1 else image.shape
+        d32 = image.astype("float32")
+        head += ["element data_array", "dtype float32", "nbytes %d" % d32.nbytes, "datashape %d %d" % (nvert, nsub)]
+        payloads.append(np.array(d32.T, dtype="float32").tobytes())
+    for i, m in enumerate(masks):
+        m = np.asarray(m)
+        head += ["element masking_array", "dtype uint8", "nbytes %d" % m.astype(np.uint8).nbytes,
+                 "nmasked %d" % int((m == True).sum()), "maskshape %d %d %d" % m.shape,  # noqa: E712
+                 "maskname %s" % (maskname[i] if len(maskname) > i else "unknown")]
+        payloads.append(np.array((m * 1).T, dtype=np.uint8).tobytes())
+    for a in affines:
+        a = np.asarray(a)
+        head += ["element affine", "dtype float32", "nbytes %d" % a.astype("float32").nbytes, "affineshape %d %d" % a.shape]
+        payloads.append(np.array(a.T, dtype="float32").tobytes())
+    for i, (v, f) in enumerate(zip(vertices, faces)):
+        v, f = np.asarray(v), np.asarray(f)
+        head += ["surfname %s" % (surfname[i] if len(surfname) > i else "unknown"),
+                 "element vertex", "dtype float32", "nbytes %d" % v.astype("float32").nbytes, "vertexshape %d %d" % v.shape,
+                 "element face", "dtype uint32", "nbytes %d" % f.astype("uint32").nbytes, "faceshape %d %d" % f.shape]
+        payloads += [np.array(v.T, dtype="float32").tobytes(), np.array(f.T, dtype="uint32").tobytes()]
+    for adj in adjacency:
+        blob = pickle.dumps(adj, protocol=pickle.HIGHEST_PROTOCOL)
+        head += ["element adjacency_object", "dtype python_object", "nbytes %d" % len(blob), "adjlength %d" % len(adj)]
+        payloads.append(blob)
+    if cols is not None:
+        head += ["element column_id", "dtype %s" % cols.dtype, "nbytes %d" % cols.nbytes, "listlength %d" % len(cols)]
+        payloads.append(cols.tobytes())
+    if append_history:
+        tmi_history.append("history mode_add %d %d %d %d %d %d" % (
+            int(strftime("%Y%m%d%H%M%S", gmtime())), num_data, len(masks) - h_mask, len(affines) - h_affine,
+            len(vertices) - h_object, len(adjacency) - h_adj))
+    head += tmi_history + ["end_header"]
+    with open(outname, "wb") as o:
+        o.write(("\n".join(head) + "\n").encode("UTF-8"))
+        for p in payloads:
+            o.write(p)
+    return outname
