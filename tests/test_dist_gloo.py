@@ -56,3 +56,38 @@ def test_shard_range_partitions_exactly():
         assert seen == list(range(first, last + 1))
     assert parallel.world() == (int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)),
                                 int(os.environ.get("LOCAL_RANK", 0)))
+
+
+def _worker_1d(rank, world, port, first, last, out_dir):
+    """1-D rows (one value per shuffle: the mediation drivers) and the composed permutation stream of the tm-models
+    mediation branch, replayed on every rank from the first permutation of the range (tm_models_randomise.py:430-436)."""
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from tfce_mediation_b200 import parallel
+    parallel.init_process_group("gloo")
+    a, b = parallel.shard_range(first, last, rank, world)
+    n = 11
+    composed, local = np.arange(n), []
+    for it in range(first, b + 1):
+        np.random.seed(it * 1000 + 3)
+        composed = composed[np.random.permutation(list(range(n)))]
+        if it >= a:
+            local.append(float(np.dot(composed, np.arange(n))))       # stand-in statistic of the composed order
+    allrows = parallel.gather_rows(np.asarray(local, dtype=np.float32))
+    np.save(os.path.join(out_dir, "rank%d.npy" % rank), allrows)
+    import torch.distributed as dist
+    dist.destroy_process_group()
+
+
+def test_composed_permutation_stream_world2(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    first, last, n = 1, 9, 11
+    mp.spawn(_worker_1d, args=(2, port, first, last, str(tmp_path)), nprocs=2, join=True)
+    x, want = np.arange(n), []
+    for it in range(first, last + 1):              # the reference's in-place permutation, one process
+        np.random.seed(it * 1000 + 3)
+        x = x[np.random.permutation(list(range(n)))]
+        want.append(float(np.dot(x, np.arange(n))))
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / ("rank%d.npy" % r)), np.asarray(want, dtype=np.float32))
