@@ -154,3 +154,22 @@ def test_step2_wrapper_rounding_and_blocks_follow_the_reference():
     assert mod == "voxel_tfce_mediation_randomise" and argv == ["-r", "1", "1000", "-m", "M"]
     with pytest.raises(NotImplementedError):
         s2.driver_call(p.parse_args(["--voxel", "-n", "1000", "-glm"]))
+
+
+def test_bench_reads_measured_hbm_peak_tolerantly(tmp_path, monkeypatch):
+    """bench.py's roofline denominator: MEASURED_PEAKS.json is driver-written, its key names are not ours."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.measured_hbm_peak()[0] == 6650.0
+    for doc, want in (({"hbm_gbs": 6555.5}, 6555.5), ({"hbm": {"burst_gbs": 7000, "sustained_gbs": 6500}}, 6500.0),
+                      ({"HBM_TBps": 6.6, "bf16_tflops": 1800}, 6600.0), ({"bf16_tflops": 1800}, 6650.0)):
+        (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps(doc))
+        assert abs(bench.measured_hbm_peak()[0] - want) < 1e-6
+    (tmp_path / "MEASURED_PEAKS.json").write_text("not json")
+    val, src = bench.measured_hbm_peak()
+    assert val == 6650.0 and "unreadable" in src
