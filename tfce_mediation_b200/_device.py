@@ -55,6 +55,16 @@ class DeviceMatrix(object):
         self.h2d_bytes = self.n * self.V * src.element_size() if not src.is_cuda else 0
         self._yy = {}
 
+    def permuted_copy(self, colperm):
+        """A second DeviceMatrix whose column j holds this one's column colperm[j] (padding untouched)."""
+        import torch
+        out = object.__new__(DeviceMatrix)
+        out.n, out.V, out.ld, out.dtype_code, out.h2d_bytes = self.n, self.V, self.ld, self.dtype_code, 0
+        out.t = torch.zeros_like(self.t)
+        out.t[:, :self.V] = self.t[:, :self.V].index_select(1, colperm)
+        out._yy = {}
+        return out
+
     def sumsq(self, center):
         """float64 [V] (centred) sum of squares per vertex, cached."""
         import torch

@@ -151,7 +151,7 @@ extern "C" int tmb_voxel_adjacency(int device, const uint8_t *mask_host, int nx,
     TMB_REQUIRE(nx > 0 && ny > 0 && nz > 0, "tmb_voxel_adjacency: bad volume shape");
     TMB_REQUIRE(conn == 26 || conn == 6, "tmb_voxel_adjacency: conn must be 26 or 6");
     TMB_REQUIRE(variant == 0 || variant == 1, "tmb_voxel_adjacency: variant must be 0 (pyfunc) or 1 (tools)");
-    TMB_CUDA(cudaSetDevice(device));
+    TMB_ON_DEVICE(device);
     const int64_t nvol = (int64_t)nx * ny * nz;
     const int nblocks = (int)((nvol + kScanTile - 1) / kScanTile);
     uint8_t *d_mask = nullptr;

@@ -42,6 +42,12 @@ struct tmb_graph {
     int32_t *d_ell = nullptr;           // fixed-width adjacency rows (low-degree graphs)
     int32_t ell_width = 0;
     int32_t max_degree = 0;
+    // sliced rows (SELL-32-4, see SurfDesc): built on the host at creation for every symmetric graph of degree <= 256,
+    // uploaded by the first plan that runs the wide pipeline kernels
+    std::vector<int32_t> sell_host, sell_off_host;
+    int32_t sell_words = 0;             // ceil(max_degree / 32); 0: no sliced rows
+    int4 *d_sell = nullptr;
+    int32_t *d_sell_off = nullptr;
     std::vector<int32_t> vmap;          // host copy
     bool symmetric = true;
     tmb_plan *self_plan = nullptr; // lazily created single-surface plan for tmb_tfce_run
@@ -70,6 +76,7 @@ struct tmb_plan {
     // streaming pipeline (tfce_pipeline.cu): per-item buffers for `pipe_items` work items, grown on demand
     int pipe_ok = 0;            // basin path and every surface has fixed-width rows of at most 32 slots
     int pipe_weights = 0;       // some surface carries vertex weights (scaled maxima then need the per-vertex pass)
+    int pipe_words = 0;         // 0: fixed-width rows; W > 0: sliced rows, W mask words per vertex (wide pipeline kernels)
     int pipe_items = 0;
     int64_t pipe_vstride = 0, pipe_tabcap = 0;
     int pipe_nbcap = 0, pipe_paircap = 0;
@@ -180,7 +187,7 @@ extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, co
     for (int64_t e = 0; e < nnz; ++e)
         TMB_REQUIRE(indices[e] >= 0 && indices[e] < V, "tmb_graph_create: neighbour index %d out of range [0,%d)",
                     indices[e], V);
-    TMB_CUDA(cudaSetDevice(device));
+    TMB_ON_DEVICE(device);
     tmb_graph *g = new tmb_graph();
     g->device = device; g->V = V; g->nnz = nnz; g->H = H; g->E = E;
     g->symmetric = csr_is_symmetric(V, indptr, indices);
@@ -235,6 +242,7 @@ extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, co
         // row from a single 32-byte sector instead of indptr + one scalar load per neighbour
         int64_t maxdeg = 0;
         for (int32_t v = 0; v < V; ++v) maxdeg = std::max<int64_t>(maxdeg, use_indptr[v + 1] - use_indptr[v]);
+        g->max_degree = (int32_t)std::min<int64_t>(maxdeg, INT32_MAX);
         int width = maxdeg <= 8 ? 8 : maxdeg <= 16 ? 16 : maxdeg <= 32 ? 32 : 0;
         if (width && nnz > 0 && (double)nnz / ((double)V * width) >= 0.4) {
             std::vector<int32_t> ell((size_t)V * width, -1);
@@ -244,7 +252,32 @@ extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, co
             if ((e = cudaMemcpy(g->d_ell, ell.data(), sizeof(int32_t) * ell.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
                 return fail("memcpy", e);
             g->ell_width = width;
-            g->max_degree = (int32_t)maxdeg;
+        }
+        // sliced rows (SELL-32-4) for everything else -- the reference's default geodesic adjacency sets have ~60
+        // neighbours per vertex (STEP_1_vertex_tfce_multiple_regression.py:71-76,155-158) -- kept on the host until
+        // a plan needs them.  Per slice of 32 vertices: width = largest degree rounded up to 4.
+        if (g->symmetric && nnz > 0 && maxdeg <= 256) {
+            const int32_t nsl = (V + 31) / 32;
+            g->sell_off_host.assign((size_t)nsl + 1, 0);
+            int64_t run = 0;
+            for (int32_t sl = 0; sl < nsl; ++sl) {
+                int64_t w = 0;
+                for (int32_t v = sl * 32; v < std::min(V, sl * 32 + 32); ++v) w = std::max<int64_t>(w, use_indptr[v + 1] - use_indptr[v]);
+                run += (w + 3) / 4 * 32;
+                g->sell_off_host[(size_t)sl + 1] = (int32_t)run;
+            }
+            if (run < (int64_t)INT32_MAX / 2) {
+                g->sell_host.assign((size_t)run * 4, -1);
+                for (int32_t v = 0; v < V; ++v) {
+                    const int64_t o0 = g->sell_off_host[v >> 5];
+                    int j = 0;
+                    for (int64_t e2 = use_indptr[v]; e2 < use_indptr[v + 1]; ++e2, ++j)
+                        g->sell_host[(size_t)(o0 + (j >> 2) * 32 + (v & 31)) * 4 + (j & 3)] = use_indices[e2];
+                }
+                g->sell_words = (int32_t)std::max<int64_t>(1, (maxdeg + 31) / 32);
+            } else {
+                g->sell_off_host.clear();
+            }
         }
     }
     if (!g->vmap.empty()) {
@@ -258,9 +291,9 @@ extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, co
 
 extern "C" int tmb_graph_destroy(tmb_graph *g) {
     if (!g) return 0;
-    cudaSetDevice(g->device);
+    DeviceGuard guard(g->device);
     if (g->self_plan) tmb_plan_destroy(g->self_plan);
-    cudaFree(g->d_indptr); cudaFree(g->d_indices); cudaFree(g->d_powE); cudaFree(g->d_vmap); cudaFree(g->d_ell);
+    cudaFree(g->d_indptr); cudaFree(g->d_indices); cudaFree(g->d_powE); cudaFree(g->d_vmap); cudaFree(g->d_ell); cudaFree(g->d_sell); cudaFree(g->d_sell_off);
     cudaFree(g->d_image); cudaFree(g->d_enhn); cudaFree(g->d_labels); cudaFree(g->d_extents);
     cudaFree(g->d_status); cudaFree(g->d_thr); cudaFree(g->d_tabs);
     delete g;
@@ -295,7 +328,7 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
                     graphs[s]->device, device);
         TMB_REQUIRE(col_offset[s] >= 0, "tmb_plan_create: negative column offset");
     }
-    TMB_CUDA(cudaSetDevice(device));
+    TMB_ON_DEVICE(device);
     tmb_plan *p = new tmb_plan();
     p->device = device; p->S = S;
     p->graphs.assign(graphs, graphs + S);
@@ -335,6 +368,36 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
         tmb_plan_destroy(p);
         return 1;
     };
+    {
+        // which row format the streaming pipeline uses: fixed-width rows when every surface has them (degree <= 32,
+        // round-1 kernels), else sliced rows for all surfaces (wide kernels); neither: the one-kernel sweep
+        const char *tf = getenv("TMB_TFCE");        // "basin" forces the one-kernel sweep (A/B measurements)
+        const char *fs = getenv("TMB_PIPE_ROWS");   // "sell" forces sliced rows (tests, A/B measurements)
+        p->pipe_ok = p->use_basin && !(tf && strcmp(tf, "basin") == 0);
+        bool all_ell = true, all_sell = true;
+        int words = 1;
+        for (int s = 0; s < S; ++s) {
+            if (!graphs[s]->d_ell || graphs[s]->ell_width > 32) all_ell = false;
+            if (graphs[s]->sell_words == 0) all_sell = false;
+            words = std::max(words, (int)graphs[s]->sell_words);
+        }
+        if (fs && strcmp(fs, "sell") == 0 && all_sell) all_ell = false;
+        if (all_ell) p->pipe_words = 0;
+        else if (all_sell) p->pipe_words = words <= 1 ? 1 : words <= 2 ? 2 : words <= 4 ? 4 : 8;
+        else p->pipe_ok = 0;
+        if (p->pipe_ok && p->pipe_words)
+            for (int s = 0; s < S; ++s) {
+                tmb_graph *g = graphs[s];
+                if (g->d_sell) continue;
+                if ((e = cudaMalloc(&g->d_sell, sizeof(int32_t) * std::max<size_t>(g->sell_host.size(), 4))) != cudaSuccess) return fail("malloc", e);
+                if ((e = cudaMalloc(&g->d_sell_off, sizeof(int32_t) * g->sell_off_host.size())) != cudaSuccess) return fail("malloc", e);
+                if ((e = cudaMemcpy(g->d_sell, g->sell_host.data(), sizeof(int32_t) * g->sell_host.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+                    return fail("memcpy", e);
+                if ((e = cudaMemcpy(g->d_sell_off, g->sell_off_host.data(), sizeof(int32_t) * g->sell_off_host.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+                    return fail("memcpy", e);
+            }
+        p->pipe_slots = 2 * prop.multiProcessorCount; // up to two sweep CTAs per SM
+    }
     for (int s = 0; s < S; ++s) {
         const tmb_graph *g = graphs[s];
         if (weight_host && weight_host[s]) {
@@ -344,9 +407,14 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
             if ((e = cudaMalloc(&p->d_weights[s], sizeof(float) * (size_t)g->V)) != cudaSuccess) return fail("malloc", e);
             if ((e = cudaMemcpy(p->d_weights[s], w.data(), sizeof(float) * (size_t)g->V, cudaMemcpyHostToDevice)) != cudaSuccess)
                 return fail("memcpy", e);
+            p->pipe_weights = 1;
         }
-        descs[s] = SurfDesc{g->d_indptr, g->d_indices, g->d_ell, g->ell_width, g->d_powE, p->d_weights[s], g->d_vmap, col_offset[s], g->V, g->H,
-                            g->symmetric ? 0 : 1};
+        SurfDesc d{};
+        d.indptr = g->d_indptr; d.indices = g->d_indices; d.ell = g->d_ell; d.ell_width = g->ell_width;
+        d.sell = p->pipe_words ? g->d_sell : nullptr; d.sell_off = p->pipe_words ? g->d_sell_off : nullptr;
+        d.powE = g->d_powE; d.weight = p->d_weights[s]; d.vmap = g->d_vmap; d.col_off = col_offset[s]; d.V = g->V; d.H = g->H;
+        d.directed = g->symmetric ? 0 : 1;
+        descs[s] = d;
     }
     if ((e = cudaMalloc(&p->d_surfs, sizeof(SurfDesc) * S)) != cudaSuccess) return fail("malloc", e);
     if ((e = cudaMalloc(&p->d_order, sizeof(int32_t) * S)) != cudaSuccess) return fail("malloc", e);
@@ -361,22 +429,13 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
     if ((e = cudaMalloc(&p->d_workspace, p->slot_stride * (size_t)p->num_slots)) != cudaSuccess) return fail("malloc workspace", e);
     if ((e = cudaMemcpy(p->d_surfs, descs.data(), sizeof(SurfDesc) * S, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("memcpy", e);
     if ((e = cudaMemcpy(p->d_order, order.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("memcpy", e);
-    {
-        const char *tf = getenv("TMB_TFCE"); // "basin" forces the one-kernel sweep (A/B measurements)
-        p->pipe_ok = p->use_basin && !(tf && strcmp(tf, "basin") == 0);
-        for (int s = 0; s < S; ++s) {
-            if (!graphs[s]->d_ell || graphs[s]->ell_width > 32) p->pipe_ok = 0;
-            if (p->d_weights[s]) p->pipe_weights = 1;
-        }
-        p->pipe_slots = 2 * prop.multiProcessorCount; // up to two sweep CTAs per SM
-    }
     *out = p;
     return 0;
 }
 
 extern "C" int tmb_plan_destroy(tmb_plan *p) {
     if (!p) return 0;
-    cudaSetDevice(p->device);
+    DeviceGuard guard(p->device);
     cudaFree(p->d_pipe); cudaFree(p->d_pipe_slots); cudaFree(p->d_tabs);
     p->d_pipe = p->d_pipe_slots = p->d_tabs = nullptr;
     if (p->d_timing) {
@@ -428,7 +487,8 @@ static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
 // per-item bytes of the streaming pipeline's buffers
 static size_t pipe_item_bytes(const tmb_plan *p) {
-    return al256((size_t)p->pipe_vstride) + 3 * al256(sizeof(int) * (size_t)p->pipe_vstride) + 16 + 1024 + al256(2 * (size_t)p->pipe_vstride) +
+    const size_t words = (size_t)std::max(1, p->pipe_words);
+    return al256((size_t)p->pipe_vstride) + (2 + words) * al256(sizeof(int) * (size_t)p->pipe_vstride) + 16 + 1024 + al256(2 * (size_t)p->pipe_vstride) +
            al256((size_t)p->pipe_nbcap) +
            al256(sizeof(unsigned long long) * (size_t)p->pipe_paircap) + al256(sizeof(unsigned) * (size_t)p->pipe_tabcap);
 }
@@ -541,7 +601,7 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
         char *base = p->d_pipe;
         pp.lev8 = reinterpret_cast<unsigned char *>(base); base += al256(items * vs);
         pp.up = reinterpret_cast<int *>(base); base += al256(items * vs * sizeof(int));
-        pp.emask = reinterpret_cast<unsigned *>(base); base += al256(items * vs * sizeof(int));
+        pp.emask = reinterpret_cast<unsigned *>(base); base += al256(items * vs * sizeof(int) * (size_t)std::max(1, p->pipe_words));
         pp.basin = reinterpret_cast<int *>(base); base += al256(items * vs * sizeof(int));
         pp.meta = reinterpret_cast<int *>(base); base += al256(items * 16);
         pp.lhist = reinterpret_cast<int *>(base); base += al256(items * 1024);
@@ -558,6 +618,7 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
         pp.slot_ws = p->d_pipe_slots; pp.slot_stride = p->pipe_slot_stride; pp.work_counter = p->d_counter;
         pp.timing = p->d_timing;
         pp.max_degree = 0;
+        pp.sell_words = p->pipe_words;
         for (int s = 0; s < p->S; ++s) pp.max_degree = std::max(pp.max_degree, (int)p->graphs[s]->max_degree);
         if (launch_tfce_pipeline(pp, p->pipe_slots, stream)) return 1;
         TableSet sub;
@@ -576,7 +637,7 @@ extern "C" int tmb_plan_run(tmb_plan *p, const float *stat_dev, int64_t ld, int 
     for (int s = 0; s < p->S; ++s)
         TMB_REQUIRE(p->col_offset[s] + p->graphs[s]->V <= ld, "tmb_plan_run: surface %d exceeds row length %lld", s,
                     (long long)ld);
-    TMB_CUDA(cudaSetDevice(p->device));
+    TMB_ON_DEVICE(p->device);
     return plan_launch(p, stat_dev, ld, B, two_sided, 0, max_dev, tfce_pos_dev, tfce_neg_dev, status_dev, -1, nullptr,
                        nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -631,7 +692,7 @@ extern "C" int tmb_threshold_tables(const float *maxima_host, const float *H_hos
 
 extern "C" int tmb_plan_maxima(tmb_plan *p, const float *stat_dev, int64_t ld, int B, float *max_dev, void *stream) {
     TMB_REQUIRE(p && stat_dev && max_dev && B >= 0, "tmb_plan_maxima: bad arguments");
-    TMB_CUDA(cudaSetDevice(p->device));
+    TMB_ON_DEVICE(p->device);
     return launch_tfce_maxima(p->d_surfs, p->S, stat_dev, ld, B, max_dev, (cudaStream_t)stream);
 }
 
@@ -645,7 +706,7 @@ extern "C" int tmb_plan_run_tables(tmb_plan *p, const float *stat_dev, int64_t l
     for (int s = 0; s < p->S; ++s)
         TMB_REQUIRE(p->col_offset[s] + p->graphs[s]->V <= ld, "tmb_plan_run_tables: surface %d exceeds row length %lld",
                     s, (long long)ld);
-    TMB_CUDA(cudaSetDevice(p->device));
+    TMB_ON_DEVICE(p->device);
     TableSet t; t.ns = ns_dev; t.delta = delta_dev; t.T = T_dev; t.HH = HH_dev; t.status = tstatus_dev;
     return plan_launch(p, stat_dev, ld, B, two_sided, 0, max_dev, tfce_pos_dev, tfce_neg_dev, status_dev, -1, nullptr,
                        nullptr, nullptr, (cudaStream_t)stream, &t);
@@ -653,7 +714,6 @@ extern "C" int tmb_plan_run_tables(tmb_plan *p, const float *stat_dev, int64_t l
 
 static int ensure_self_plan(tmb_graph *g) {
     if (g->self_plan) return 0;
-    TMB_CUDA(cudaSetDevice(g->device));
     const int64_t off = 0;
     tmb_graph *gs[1] = {g};
     if (tmb_plan_create(g->device, 1, gs, &off, nullptr, 1, &g->self_plan)) return 1;
@@ -686,6 +746,7 @@ static int upload_single_tables(tmb_graph *g, const float *image_host, TableSet 
 
 extern "C" int tmb_tfce_run(tmb_graph *g, const float *image_host, float *enhn_host, int *map_status) {
     TMB_REQUIRE(g && image_host && enhn_host, "tmb_tfce_run: null pointer");
+    TMB_ON_DEVICE(g->device);
     if (ensure_self_plan(g)) return 1;
     const size_t bytes = sizeof(float) * (size_t)g->V;
     TMB_CUDA(cudaMemcpy(g->d_image, image_host, bytes, cudaMemcpyHostToDevice));
@@ -710,6 +771,7 @@ extern "C" int tmb_tfce_run(tmb_graph *g, const float *image_host, float *enhn_h
 extern "C" int tmb_tfce_components(tmb_graph *g, const float *image_host, int level, int32_t *labels_host,
                                    int32_t *extents_host, float *threshold_out) {
     TMB_REQUIRE(g && image_host && labels_host && extents_host && level >= 0, "tmb_tfce_components: bad arguments");
+    TMB_ON_DEVICE(g->device);
     if (ensure_self_plan(g)) return 1;
     const size_t bytes = sizeof(float) * (size_t)g->V;
     TMB_CUDA(cudaMemcpy(g->d_image, image_host, bytes, cudaMemcpyHostToDevice));

@@ -31,12 +31,50 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_or
         }                                                                                           \
     } while (0)
 
+// Scoped current-device switch: every entry point runs on the device that owns its handle / buffers and leaves the
+// calling thread's current device as it found it (the caller is a PyTorch process with its own notion of it).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define TMB_ON_DEVICE(dev)                                                                          \
+    ::tmb::DeviceGuard guard__(dev);                                                                \
+    TMB_REQUIRE(guard__.ok, "cannot switch to CUDA device %d", (int)(dev))
+
+// device that owns a device pointer (-1: not a device pointer)
+inline int device_of(const void *ptr) {
+    cudaPointerAttributes a;
+    if (!ptr || cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+
+#define TMB_DEVICE_OF(ptr, who)                                                                     \
+    const int dev__ = ::tmb::device_of(ptr);                                                        \
+    TMB_REQUIRE(dev__ >= 0, "%s: %s is not a device pointer", who, #ptr);                           \
+    TMB_ON_DEVICE(dev__)
+
 // ---- per-surface descriptor consumed by the TFCE kernels (device-resident array) -------------
 struct SurfDesc {
     const int64_t *indptr;  // [V+1]
     const int32_t *indices; // [nnz]
     const int32_t *ell;     // [V * ell_width] fixed-width rows padded with -1 (32-byte aligned), or nullptr
     int32_t ell_width;      // 8, 16 or 32 when ell != nullptr
+    // sliced rows (SELL-32-4) for graphs wider than 32 neighbours or with very uneven degrees: the 32 vertices of a
+    // slice share a width (their largest degree rounded up to 4); slot group j4 of the slice is 32 consecutive int4
+    // (one per vertex), so a warp that owns the slice reads 512 contiguous bytes per group.  Pad = -1.
+    const int4 *sell;       // [sell_off[nslices]] or nullptr (uploaded only for plans that use the wide kernels)
+    const int32_t *sell_off; // [nslices + 1] first int4 of every slice
     const double *powE;     // [V+1]  pow((double)n, (double)E) tabulated with the host libm
     const float *weight;    // [V] or nullptr (internal vertex order)
     const int32_t *vmap;    // [V] internal (locality-reordered) index -> caller's index, or nullptr
@@ -102,12 +140,14 @@ struct PipeParams {
     const int32_t *tab_status;
     int flags;              // bit 2: statistic rows are in the graphs' internal vertex order
     int max_degree;         // largest vertex degree over the plan's graphs (triangle meshes: 6 -> the ascent kernel skips the two pad slots)
+    int sell_words;         // 0: fixed-width rows (ell); W > 0: sliced rows (sell) with W 32-bit words of earlier-neighbour mask per vertex
     int32_t Vmax;
     // per-item buffers
     int64_t vstride;        // elements per work item in the per-vertex arrays
     unsigned char *lev8;    // activation level | sign << 7; 0 = never active
     int *up;                // ascent target; -1 - basin for a peak; INT_MIN when inactive
-    unsigned *emask;        // ELL slots holding an earlier-activated same-sign neighbour (ascent target excluded)
+    unsigned *emask;        // row slots holding an earlier-activated same-sign neighbour (ascent target excluded);
+                            // sliced rows: sell_words words per vertex, word w of item i at ((i * sell_words + w) * vstride + v)
     int *basin;             // compact basin id, -1 when inactive
     int *meta;              // [items][4]: basins, candidate unions, over-capacity flag, unused
     int *lhist;             // [items][256]: [0,128) vertices per activation level (K_A), [128,256) the cursors with which

@@ -30,6 +30,7 @@ extern "C" int tmb_fwe_lookup(const double *sorted_max_dev, int n, const float *
                               double *corrp_dev, void *stream) {
     TMB_REQUIRE(sorted_max_dev && values_dev && corrp_dev && n > 0 && m >= 0, "tmb_fwe_lookup: bad arguments");
     if (m == 0) return 0;
+    TMB_DEVICE_OF(sorted_max_dev, "tmb_fwe_lookup");
     const int threads = 256;
     fwe_lookup_kernel<<<(unsigned)((m + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
         sorted_max_dev, n, values_dev, m, corrp_dev);

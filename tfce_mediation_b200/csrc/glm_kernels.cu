@@ -732,6 +732,7 @@ static int dtype_is_f64(int ydtype, int *out) {
 extern "C" int tmb_glm_sumsq(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, int center,
                              double *yy_dev, double *colsum_dev, void *stream) {
     TMB_REQUIRE(Y_dev && (yy_dev || colsum_dev) && n > 0 && V > 0, "tmb_glm_sumsq: bad arguments");
+    TMB_DEVICE_OF(Y_dev, "tmb_glm_sumsq");
     int f64;
     if (dtype_is_f64(ydtype, &f64)) return 1;
     const int threads = 256;
@@ -755,6 +756,7 @@ extern "C" int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, in
     TMB_REQUIRE(n > 0 && V > 0 && P > 0 && r >= 1 && r <= rp && row0 >= 0 && nrows >= 1 && row0 + nrows <= r,
                 "tmb_glm_tstat: bad shape (n=%d V=%lld P=%d r=%d rp=%d row0=%d nrows=%d)", n, (long long)V, P, r, rp,
                 row0, nrows);
+    TMB_DEVICE_OF(Y_dev, "tmb_glm_tstat");
     GlmParams p{};
     if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
     p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.G = G_dev; p.d = d_dev;
@@ -772,6 +774,7 @@ extern "C" int tmb_glm_fstat(const void *Y_dev, int ydtype, int n, int64_t V, in
     TMB_REQUIRE(n > 0 && V > 0 && P > 0 && r >= 1 && r <= rp && nvar >= 0 && nvar <= 8 && (nvar == 0 || (M_dev && var_lo && var_k)) &&
                     (nvar > 0 || want_model),
                 "tmb_glm_fstat: bad shape (n=%d V=%lld P=%d r=%d rp=%d nvar=%d)", n, (long long)V, P, r, rp, nvar);
+    TMB_DEVICE_OF(Y_dev, "tmb_glm_fstat");
     GlmParams p{};
     if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
     p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.G = G_dev; p.M = M_dev;
@@ -790,6 +793,7 @@ extern "C" int tmb_glm_pack_rowperm(const double *pinv_dev, int r, int n, const 
     TMB_REQUIRE(pinv_dev && perm_idx_dev && At_dev, "tmb_glm_pack_rowperm: null pointer");
     TMB_REQUIRE(r >= 1 && r <= rp && n > 0 && P > 0 && ldA >= (int64_t)P * rp && n <= 65535,
                 "tmb_glm_pack_rowperm: bad shape (r=%d rp=%d n=%d P=%d ldA=%lld)", r, rp, n, P, (long long)ldA);
+    TMB_DEVICE_OF(pinv_dev, "tmb_glm_pack_rowperm");
     const dim3 grid((unsigned)((ldA + 255) / 256), (unsigned)n);
     glm_pack_rowperm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pinv_dev, r, n, perm_idx_dev, P, rp, At_dev, ldA);
     count_launch();
@@ -800,6 +804,7 @@ extern "C" int tmb_glm_pack_rowperm(const double *pinv_dev, int r, int n, const 
 extern "C" int tmb_glm_beta(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev,
                             int64_t ldA, int nrows, double *beta64_dev, int64_t ldt, void *stream) {
     TMB_REQUIRE(Y_dev && At_dev && beta64_dev && n > 0 && V > 0 && nrows > 0, "tmb_glm_beta: bad arguments");
+    TMB_DEVICE_OF(Y_dev, "tmb_glm_beta");
     GlmParams p{};
     if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
     p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.P = nrows; p.r = 1; p.rp = 1;
@@ -814,6 +819,7 @@ extern "C" int tmb_glm_direct(const void *Y_dev, int ydtype, int n, int64_t V, i
     TMB_REQUIRE(Y_dev && X_dev && pinv_dev && n > 0 && V > 0, "tmb_glm_direct: bad arguments");
     TMB_REQUIRE(k >= 1 && k <= kMaxK, "tmb_glm_direct: k must be in 1..%d (got %d)", kMaxK, k);
     TMB_REQUIRE(!(t64_dev || se32_dev) || d_dev, "tmb_glm_direct: t/se requested without diag(inv(X'X))");
+    TMB_DEVICE_OF(Y_dev, "tmb_glm_direct");
     DirectParams p{};
     if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
     p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.X = X_dev; p.pinv = pinv_dev; p.k = k; p.d = d_dev; p.dof = dof;
@@ -831,6 +837,7 @@ extern "C" int tmb_glm_direct(const void *Y_dev, int ydtype, int n, int64_t V, i
 extern "C" int tmb_se_of_slope(const double *sigma2_dev, int64_t V, const double *d_dev, int k, float *se32_dev,
                                int64_t ld, void *stream) {
     TMB_REQUIRE(sigma2_dev && d_dev && se32_dev && V > 0 && k > 0, "tmb_se_of_slope: bad arguments");
+    TMB_DEVICE_OF(sigma2_dev, "tmb_se_of_slope");
     const int threads = 256;
     se_of_slope_kernel<<<(unsigned)((V + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
         sigma2_dev, V, d_dev, k, se32_dev, ld);
@@ -849,6 +856,7 @@ extern "C" int tmb_sobelz(const void *Y_dev, int ydtype, int n, int64_t V, int64
                     (ta_scalar_dev || (rA >= 1 && rowA >= 0 && rowA < rA && GA_dev && dA_dev)),
                 "tmb_sobelz: bad shape");
     TMB_REQUIRE(alg >= 0 && alg <= 2, "tmb_sobelz: alg must be 0 (aroian), 1 (sobel) or 2 (goodman)");
+    TMB_DEVICE_OF(Y_dev, "tmb_sobelz");
     GlmParams p{};
     if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
     p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.G = GA_dev; p.d = dA_dev;

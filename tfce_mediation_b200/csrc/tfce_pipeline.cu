@@ -263,6 +263,90 @@ __global__ void __launch_bounds__(256) pipe_ascent_kernel(PipeParams P, int chun
     }
 }
 
+
+// ---- K_B, sliced rows (SELL-32-4): graphs with more than 32 neighbours per vertex (the reference's default geodesic
+// adjacency sets, ~60 per vertex) or very uneven degrees.  One thread per vertex as above; the 32 lanes of a warp own
+// the 32 vertices of one slice, so slot group j4 of the slice is ONE coalesced 512-byte load for the warp and the trip
+// count is warp-uniform.  kWords 32-bit words of earlier-neighbour mask per vertex (slot j -> bit j & 31 of word j >> 5).
+template <int kWords>
+__global__ void __launch_bounds__(256) pipe_ascent_wide_kernel(PipeParams P, int chunks) {
+    __shared__ int sPeaks, sBase;
+    int item, chunk, s, b;
+    grid_coords(P, item, chunk, s, b);
+    const SurfDesc sd = P.surfs[s];
+    if (chunk * 256 >= sd.V) return; // CTA-uniform
+    if (threadIdx.x == 0) sPeaks = 0;
+    __syncthreads();
+    const int v = chunk * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const size_t base = (size_t)item * P.vstride;
+    int peak_code = -1;
+    if (v < sd.V) {
+        const unsigned char *__restrict__ lev8 = P.lev8 + base;
+        const int cv = lev8[v];
+        const int lev = cv & 0x7f;
+        if (lev == 0) {
+            P.up[base + v] = kInactive; // the mask words of an inactive vertex are never read
+        } else {
+            const int o0 = sd.sell_off[v >> 5];
+            const int n4 = (sd.sell_off[(v >> 5) + 1] - o0) >> 5; // slot groups of this slice (warp-uniform)
+            const int4 *__restrict__ rows = sd.sell + o0 + lane;
+            unsigned bestkey = ((unsigned)lev << 8) | 0xffu; // level << 8 | slot of the ascent target so far
+            const unsigned sign = (unsigned)cv & 0x80u;
+            const unsigned mykey = ((unsigned)lev << 24) | (unsigned)v;
+            unsigned em[kWords];
+#pragma unroll
+            for (int w = 0; w < kWords; ++w) {
+                unsigned e = 0u;
+                if (w * 8 < n4) {
+#pragma unroll 2
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int j4 = w * 8 + jj;
+                        if (j4 >= n4) break;
+                        const int4 r = __ldg(rows + j4 * 32);
+                        const int nb[4] = {r.x, r.y, r.z, r.w};
+                        unsigned ca[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) ca[q] = nb[q] >= 0 ? (unsigned)lev8[nb[q]] : 0u;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const unsigned x = ca[q] ^ sign;                 // 1..127: active, same sign
+                            const unsigned la = (x - 1u) < 127u ? x : 255u;
+                            bestkey = min(bestkey, (la << 8) | (unsigned)(j4 * 4 + q));
+                            if (((la << 24) | (unsigned)nb[q]) < mykey) e |= 1u << (jj * 4 + q);
+                        }
+                    }
+                }
+                em[w] = e;
+            }
+            const int bestbit = (int)(bestkey & 0xffu);
+            const bool has_up = (int)(bestkey >> 8) < lev;
+            if (has_up) {
+                const int best = reinterpret_cast<const int *>(sd.sell + o0 + (bestbit >> 2) * 32 + lane)[bestbit & 3];
+#pragma unroll
+                for (int w = 0; w < kWords; ++w)
+                    if (w == (bestbit >> 5)) em[w] &= ~(1u << (bestbit & 31)); // the ascent target lies in the same basin
+                P.up[base + v] = best;
+            } else {
+                peak_code = cv;
+            }
+#pragma unroll
+            for (int w = 0; w < kWords; ++w) P.emask[((size_t)item * kWords + w) * P.vstride + v] = em[w];
+        }
+    }
+    // peaks get compact basin ids: one returning atomic per CTA on the map's counter
+    int local = -1;
+    if (peak_code >= 0) local = atomicAdd(&sPeaks, 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && sPeaks > 0) sBase = atomicAdd(P.meta + (size_t)item * 4, sPeaks);
+    __syncthreads();
+    if (local >= 0) {
+        const int pid = sBase + local;
+        if (pid < P.nbcap) P.blev[(size_t)item * P.nbcap + pid] = (unsigned char)peak_code;
+        P.up[base + v] = -1 - pid;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- K_C
 // Basin of every vertex (read-only pointer chase along `up`, four independent chains per thread), and -- for max-only
 // maps -- the map's VERTEX LISTS bucketed by activation level: the basin id (2 bytes) of every active vertex, which the
@@ -454,6 +538,124 @@ __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunk
     if (gbase + n <= P.paircap) { // else: K_S sees npairs > paircap and flags the map
         unsigned long long *__restrict__ dst = P.pairs + (size_t)item * P.paircap + gbase;
         for (int i = threadIdx.x; i < n; i += 256) dst[i] = sPairs[i];
+    }
+}
+
+
+// ---- K_D, sliced rows.  With ~60 neighbours most vertices lie within reach of another basin, and one map would emit
+// more candidate unions than it has vertices.  Only the EARLIEST union of two basins matters (later ones find them in
+// one component already), so the CTA keeps one entry per unordered basin pair in a shared-memory hash -- key = the two
+// basin ids, value = the smallest level seen (one 64-bit atomicMin: the level sits in the low bits) -- and flushes the
+// few dozen distinct pairs of its 1,024 vertices with one returning atomic.  A full probe sequence falls back to a
+// direct append (duplicates are harmless).
+static constexpr int kPairHashBits = 11;
+static constexpr int kPairHash = 1 << kPairHashBits;
+
+template <bool kDense, int kWords>
+__global__ void __launch_bounds__(256) pipe_count_wide_kernel(PipeParams P, int chunks) {
+    int item, chunk, s, b;
+    grid_coords(P, item, chunk, s, b);
+    const SurfDesc sd = P.surfs[s];
+    __shared__ unsigned long long sHash[kPairHash];
+    __shared__ int sBasin[kCountChunk]; // basins of the CTA's own vertices: most neighbour lookups land here
+    __shared__ int sWarpTot[8], sBase;
+    int *meta = P.meta + (size_t)item * 4;
+    const int v_beg = chunk * kCountChunk;
+    if (v_beg >= sd.V || meta[2]) return; // CTA-uniform
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < kPairHash; i += 256) sHash[i] = ~0ull;
+    const size_t base = (size_t)item * P.vstride;
+    const int *__restrict__ basin = P.basin + base;
+    const int NB = meta[0];
+    int buq[kCountVPT], levq[kCountVPT];
+#pragma unroll
+    for (int q = 0; q < kCountVPT; ++q) {
+        const int v = v_beg + q * 256 + tid;
+        buq[q] = (v < sd.V) ? basin[v] : -1;
+        sBasin[q * 256 + tid] = buq[q];
+        levq[q] = (v < sd.V) ? (int)(P.lev8[base + v] & 0x7f) : 0;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int q = 0; q < kCountVPT; ++q) {
+        const int v = v_beg + q * 256 + tid;
+        const int bu = buq[q], lev = levq[q];
+        if (kDense) {
+            const int key = bu >= 0 ? lev * NB + bu : -1 - lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (bu >= 0 && lane == (__ffs(peers) - 1))
+                atomicAdd(P.table + (size_t)item * P.tabcap + key, (unsigned)__popc(peers));
+        }
+        if (bu < 0) continue;
+        const int o0 = sd.sell_off[v >> 5];
+        const int *__restrict__ row = reinterpret_cast<const int *>(sd.sell + o0 + lane);
+        int s0 = -1, s1 = -1, s2 = -1, s3 = -1;
+#pragma unroll
+        for (int w = 0; w < kWords; ++w) {
+            unsigned m = P.emask[((size_t)item * kWords + w) * P.vstride + v];
+            while (m) {
+                const int j = w * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                const int a = row[(j >> 2) * 128 + (j & 3)];
+                const unsigned off = (unsigned)(a - v_beg);
+                const int ba = off < (unsigned)kCountChunk ? sBasin[off] : basin[a];
+                if (ba == bu || ba == s0 || ba == s1 || ba == s2 || ba == s3) continue;
+                s3 = s2; s2 = s1; s1 = s0; s0 = ba;
+                const unsigned lo = (unsigned)min(bu, ba), hi = (unsigned)max(bu, ba);
+                const unsigned long long val = ((unsigned long long)lo << 32) | ((unsigned long long)hi << 8) | (unsigned long long)lev;
+                unsigned h = ((lo * 0x9E3779B1u) ^ (hi * 0x85EBCA6Bu)) >> (32 - kPairHashBits);
+                bool placed = false;
+                for (int probe = 0; probe < 16; ++probe) {
+                    const unsigned long long old = atomicCAS(&sHash[h], ~0ull, val);
+                    if (old == ~0ull) { placed = true; break; }
+                    if ((old >> 8) == (val >> 8)) { atomicMin(&sHash[h], val); placed = true; break; }
+                    h = (h + 1) & (kPairHash - 1);
+                }
+                if (!placed) { // table crowded: append directly
+                    const int gp = atomicAdd(meta + 1, 1);
+                    if (gp < P.paircap)
+                        P.pairs[(size_t)item * P.paircap + gp] = ((unsigned long long)lev << 48) | ((unsigned long long)lo << 24) | (unsigned long long)hi;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // flush the distinct pairs: thread t owns slots [t * 8, t * 8 + 8)
+    constexpr int kPer = kPairHash / 256;
+    unsigned long long mine[kPer];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+        mine[i] = sHash[tid * kPer + i];
+        cnt += mine[i] != ~0ull;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nbv = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nbv;
+    }
+    if (lane == 31) sWarpTot[wid] = incl;
+    __syncthreads();
+    int before = incl - cnt, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        if (w < wid) before += sWarpTot[w];
+        total += sWarpTot[w];
+    }
+    if (total == 0) return;
+    if (tid == 0) sBase = atomicAdd(meta + 1, total);
+    __syncthreads();
+    const int gbase = sBase;
+    if (gbase + total <= P.paircap) { // else: K_S sees npairs > paircap and flags the map
+        unsigned long long *__restrict__ dst = P.pairs + (size_t)item * P.paircap + gbase + before;
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i)
+            if (mine[i] != ~0ull) {
+                const unsigned long long lev = mine[i] & 0xffull, lo = mine[i] >> 32, hi = (mine[i] >> 8) & 0xFFFFFFull;
+                dst[k++] = (lev << 48) | (lo << 24) | hi;
+            }
     }
 }
 
@@ -1367,13 +1569,36 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
     TMB_REQUIRE(p.B <= 65535 && p.S <= 65535, "tfce pipeline: at most 65535 rows and surfaces per launch (got %d, %d)", p.B, p.S);
     TMB_CUDA(cudaMemsetAsync(p.lhist, 0, sizeof(int) * 256 * (size_t)items, stream));
     pipe_levels_kernel<<<dim3(chunksA, p.B, p.S), 256, 0, stream>>>(p, chunksA);
-    if (p.max_degree > 0 && p.max_degree <= 6) pipe_ascent_kernel<true><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
-    else pipe_ascent_kernel<false><<<dim3(chunks, p.B, p.S), 256, 0, stream>>>(p, chunks);
+    const dim3 gridB(chunks, p.B, p.S);
+    switch (p.sell_words) {
+    case 0:
+        if (p.max_degree > 0 && p.max_degree <= 6) pipe_ascent_kernel<true><<<gridB, 256, 0, stream>>>(p, chunks);
+        else pipe_ascent_kernel<false><<<gridB, 256, 0, stream>>>(p, chunks);
+        break;
+    case 1: pipe_ascent_wide_kernel<1><<<gridB, 256, 0, stream>>>(p, chunks); break;
+    case 2: pipe_ascent_wide_kernel<2><<<gridB, 256, 0, stream>>>(p, chunks); break;
+    case 4: pipe_ascent_wide_kernel<4><<<gridB, 256, 0, stream>>>(p, chunks); break;
+    case 8: pipe_ascent_wide_kernel<8><<<gridB, 256, 0, stream>>>(p, chunks); break;
+    default: set_error("tfce pipeline: sell_words must be 0, 1, 2, 4 or 8 (got %d)", p.sell_words); return 1;
+    }
     const int chunksC = (p.Vmax + kBasinChunk - 1) / kBasinChunk;
     pipe_basin_kernel<<<dim3(chunksC, p.B, p.S), 256, 0, stream>>>(p, chunksC);
     const int chunksD = (p.Vmax + kCountChunk - 1) / kCountChunk;
-    if (p.want_vertex_pass) pipe_count_kernel<true><<<dim3(chunksD, p.B, p.S), 256, 0, stream>>>(p, chunksD);
-    else pipe_count_kernel<false><<<dim3(chunksD, p.B, p.S), 256, 0, stream>>>(p, chunksD);
+    const dim3 gridD(chunksD, p.B, p.S);
+#define TMB_COUNT_WIDE(W)                                                                                  \
+    if (p.want_vertex_pass) pipe_count_wide_kernel<true, W><<<gridD, 256, 0, stream>>>(p, chunksD);        \
+    else pipe_count_wide_kernel<false, W><<<gridD, 256, 0, stream>>>(p, chunksD)
+    switch (p.sell_words) {
+    case 0:
+        if (p.want_vertex_pass) pipe_count_kernel<true><<<gridD, 256, 0, stream>>>(p, chunksD);
+        else pipe_count_kernel<false><<<gridD, 256, 0, stream>>>(p, chunksD);
+        break;
+    case 1: TMB_COUNT_WIDE(1); break;
+    case 2: TMB_COUNT_WIDE(2); break;
+    case 4: TMB_COUNT_WIDE(4); break;
+    default: TMB_COUNT_WIDE(8); break;
+    }
+#undef TMB_COUNT_WIDE
     TMB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
     if (p.want_vertex_pass) {
         // class path (values per vertex): one 1024-thread CTA per SM

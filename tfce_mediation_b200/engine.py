@@ -15,7 +15,7 @@ import time as _time
 
 import numpy as np
 
-from . import _lib
+from . import _lib, parallel
 from ._device import DeviceMatrix, TILE_M, round_up, to_host
 from .tfce import CreateAdjSet
 
@@ -57,6 +57,7 @@ class TfcePlan(object):
         if S == 0:
             raise ValueError("no surfaces")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        parallel.check_device(self.device.index)
         graphs = (ctypes.c_void_p * S)(*[s.adjset._handle for s in self.surfaces])
         offs = (ctypes.c_int64 * S)(*[s.col_offset for s in self.surfaces])
         wts = (ctypes.c_void_p * S)(*[(s.weight.ctypes.data if s.weight is not None else None) for s in self.surfaces])
@@ -260,7 +261,9 @@ class PermutationEngine(object):
         import torch
         _lib.require_device()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.Y = data if isinstance(data, DeviceMatrix) else DeviceMatrix(data, device=self.device)
+        parallel.check_device(self.device.index)
+        owned = not isinstance(data, DeviceMatrix)
+        self.Y = DeviceMatrix(data, device=self.device) if owned else data
         self.plan = TfcePlan(surfaces, device=self.device, max_slots=max_slots) if surfaces is not None else None
         if self.plan is not None and self.plan.row_len > self.Y.V:
             raise ValueError("surfaces cover %d columns but the data has %d" % (self.plan.row_len, self.Y.V))
@@ -270,8 +273,13 @@ class PermutationEngine(object):
             if not np.array_equal(perm, np.arange(self.Y.V)):
                 # one-time gather of the data columns into the graphs' internal vertex order
                 self.colperm = torch.from_numpy(perm).to(self.device)
-                self.Y.t[:, :self.Y.V] = self.Y.t[:, :self.Y.V].index_select(1, self.colperm)
-                self.Y._yy = {}
+                if not owned:
+                    # a caller-supplied DeviceMatrix stays in the caller's column order (it may feed another engine
+                    # or be read afterwards): the engine works on its own permuted copy
+                    self.Y = self.Y.permuted_copy(self.colperm)
+                else:
+                    self.Y.t[:, :self.Y.V] = self.Y.t[:, :self.Y.V].index_select(1, self.colperm)
+                    self.Y._yy = {}
                 self.plan.set_internal_order(True)
         self.two_sided = bool(two_sided)
         self.nan_to_zero = bool(nan_to_zero)

@@ -29,6 +29,31 @@ def shard_range(first, last, rank, world_size):
     return a, b
 
 
+def bind_device():
+    """One process per GPU: make cuda:LOCAL_RANK the current device of this process.  Must run before any graph, plan
+    or engine is created (they live on the current device); every driver calls it first through setup()."""
+    import torch
+    _, ws, local = world()
+    if torch.cuda.is_available() and ws > 1:
+        torch.cuda.set_device(local)
+
+
+def setup(backend=None):
+    """First call of every driver's run(): bind the GPU, join the process group.  Returns (rank, world_size)."""
+    bind_device()
+    init_process_group(backend)
+    rank, ws, _ = world()
+    return rank, ws
+
+
+def check_device(device_index):
+    """Refuse to build device state on another rank's GPU (all ranks piling onto cuda:0 was the round-1 driver bug)."""
+    _, ws, local = world()
+    if ws > 1 and device_index is not None and int(device_index) != local:
+        raise RuntimeError("rank with LOCAL_RANK=%d is about to allocate on cuda:%d: call parallel.setup() "
+                           "(or torch.cuda.set_device(LOCAL_RANK)) before creating graphs or engines" % (local, device_index))
+
+
 def init_process_group(backend=None):
     import torch
     import torch.distributed as dist

@@ -45,6 +45,8 @@ class CreateAdjSet(object):
             import torch
             device = torch.cuda.current_device()
         self.device = int(device)
+        from . import parallel
+        parallel.check_device(self.device)
         h = ctypes.c_void_p()
         _lib.check(_lib.lib().tmb_graph_create(self.device, self.num_vertices, _lib.ptr(self.indptr),
                                                _lib.ptr(self.indices), self.H, self.E, ctypes.byref(h)))

@@ -132,6 +132,7 @@ def load_setup(opts):
 
 def run(opts):
     start_time = time()
+    C.setup()            # bind cuda:LOCAL_RANK and join the process group before any device state exists
     np.seterr(divide="ignore", invalid="ignore")
     from ..engine import PermutationEngine
     tmp = opts.tmitemp

@@ -57,10 +57,15 @@ def masked_surface(adjacency, H, E, keep=None, weight=None, col_offset=0):
     return Surface(CreateAdjSet(H, E, (indptr, indices)), col_offset, w)
 
 
+def setup():
+    """Bind this rank's GPU and join the process group -- before ANY device state exists."""
+    return parallel.setup()
+
+
 def shard(first, last):
     rank, ws, _ = parallel.world()
     if ws > 1:
-        parallel.init_process_group()
+        parallel.setup()
     a, b = parallel.shard_range(first, last, rank, ws)
     return rank, ws, a, b
 

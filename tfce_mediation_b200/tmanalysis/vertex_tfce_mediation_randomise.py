@@ -27,6 +27,7 @@ def getArgumentParser(ap=ap.ArgumentParser(description=DESCRIPTION)):
 
 def run(opts):
     start_time = time()
+    C.setup()            # bind cuda:LOCAL_RANK and join the process group before any device state exists
     np.seterr(divide="ignore", invalid="ignore")
     from ..engine import PermutationEngine
     first, last = int(opts.range[0]), int(opts.range[1])
