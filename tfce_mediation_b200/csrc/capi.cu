@@ -67,6 +67,9 @@ struct tmb_plan {
     SurfDesc *d_surfs = nullptr;
     int32_t *d_order = nullptr;
     std::vector<float *> d_weights;
+    std::vector<unsigned short *> d_wrank;  // weight ranks per surface (leader sweep with weights), or nullptr
+    std::vector<float *> d_wtab;            // distinct weight values per surface, ascending
+    int pipe_wfast = 0;                     // every weighted surface has ranks: max-only maps need no per-vertex pass
     char *d_workspace = nullptr;
     size_t slot_stride = 0;
     int *d_counter = nullptr;
@@ -267,12 +270,16 @@ extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, co
                 g->sell_off_host[(size_t)sl + 1] = (int32_t)run;
             }
             if (run < (int64_t)INT32_MAX / 2) {
-                g->sell_host.assign((size_t)run * 4, -1);
+                // pad slots hold the vertex ITSELF: a self-reference is never "earlier" and never an ascent target, so
+                // the kernels need no pad test in front of their gathers
+                g->sell_host.assign((size_t)run * 4, 0);
                 for (int32_t v = 0; v < V; ++v) {
                     const int64_t o0 = g->sell_off_host[v >> 5];
+                    const int64_t w4 = (g->sell_off_host[(v >> 5) + 1] - o0) / 32;
                     int j = 0;
                     for (int64_t e2 = use_indptr[v]; e2 < use_indptr[v + 1]; ++e2, ++j)
                         g->sell_host[(size_t)(o0 + (j >> 2) * 32 + (v & 31)) * 4 + (j & 3)] = use_indices[e2];
+                    for (; j < w4 * 4; ++j) g->sell_host[(size_t)(o0 + (j >> 2) * 32 + (v & 31)) * 4 + (j & 3)] = v;
                 }
                 g->sell_words = (int32_t)std::max<int64_t>(1, (maxdeg + 31) / 32);
             } else {
@@ -334,6 +341,8 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
     p->graphs.assign(graphs, graphs + S);
     p->col_offset.assign(col_offset, col_offset + S);
     p->d_weights.assign(S, nullptr);
+    p->d_wrank.assign(S, nullptr);
+    p->d_wtab.assign(S, nullptr);
     std::vector<SurfDesc> descs(S);
     std::vector<int32_t> order(S);
     std::iota(order.begin(), order.end(), 0);
@@ -398,6 +407,7 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
             }
         p->pipe_slots = 2 * prop.multiProcessorCount; // up to two sweep CTAs per SM
     }
+    bool wfast_ok = true;
     for (int s = 0; s < S; ++s) {
         const tmb_graph *g = graphs[s];
         if (weight_host && weight_host[s]) {
@@ -408,13 +418,38 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
             if ((e = cudaMemcpy(p->d_weights[s], w.data(), sizeof(float) * (size_t)g->V, cudaMemcpyHostToDevice)) != cudaSuccess)
                 return fail("memcpy", e);
             p->pipe_weights = 1;
+            // weight ranks for the leader sweep: finite, non-negative weights with at most 65,535 distinct values
+            // (density weights are a function of the neighbour count: a few dozen values)
+            bool ok = true;
+            for (float x : w) ok = ok && std::isfinite(x) && x >= 0.0f;
+            std::vector<float> vals(w);
+            std::sort(vals.begin(), vals.end());
+            vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+            if (ok && vals.size() <= 65535) {
+                std::vector<unsigned short> rk((size_t)g->V);
+                for (int32_t i = 0; i < g->V; ++i)
+                    rk[i] = (unsigned short)(std::lower_bound(vals.begin(), vals.end(), w[i]) - vals.begin());
+                if ((e = cudaMalloc(&p->d_wrank[s], sizeof(unsigned short) * (size_t)g->V)) != cudaSuccess) return fail("malloc", e);
+                if ((e = cudaMalloc(&p->d_wtab[s], sizeof(float) * vals.size())) != cudaSuccess) return fail("malloc", e);
+                if ((e = cudaMemcpy(p->d_wrank[s], rk.data(), sizeof(unsigned short) * (size_t)g->V, cudaMemcpyHostToDevice)) != cudaSuccess)
+                    return fail("memcpy", e);
+                if ((e = cudaMemcpy(p->d_wtab[s], vals.data(), sizeof(float) * vals.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+                    return fail("memcpy", e);
+            } else {
+                wfast_ok = false;
+            }
         }
         SurfDesc d{};
         d.indptr = g->d_indptr; d.indices = g->d_indices; d.ell = g->d_ell; d.ell_width = g->ell_width;
         d.sell = p->pipe_words ? g->d_sell : nullptr; d.sell_off = p->pipe_words ? g->d_sell_off : nullptr;
+        d.wrank = p->d_wrank[s]; d.wtab = p->d_wtab[s];
         d.powE = g->d_powE; d.weight = p->d_weights[s]; d.vmap = g->d_vmap; d.col_off = col_offset[s]; d.V = g->V; d.H = g->H;
         d.directed = g->symmetric ? 0 : 1;
         descs[s] = d;
+    }
+    {
+        const char *wm = getenv("TMB_PIPE_WEIGHTS"); // "class" forces the per-vertex class path (A/B measurements, tests)
+        p->pipe_wfast = p->pipe_weights && wfast_ok && !(wm && strcmp(wm, "class") == 0);
     }
     if ((e = cudaMalloc(&p->d_surfs, sizeof(SurfDesc) * S)) != cudaSuccess) return fail("malloc", e);
     if ((e = cudaMalloc(&p->d_order, sizeof(int32_t) * S)) != cudaSuccess) return fail("malloc", e);
@@ -470,6 +505,8 @@ extern "C" int tmb_plan_destroy(tmb_plan *p) {
         cudaFree(p->d_timing);
     }
     for (float *w : p->d_weights) cudaFree(w);
+    for (unsigned short *w : p->d_wrank) cudaFree(w);
+    for (float *w : p->d_wtab) cudaFree(w);
     cudaFree(p->d_surfs); cudaFree(p->d_order); cudaFree(p->d_counter); cudaFree(p->d_workspace);
     delete p;
     return 0;
@@ -488,7 +525,7 @@ static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 // per-item bytes of the streaming pipeline's buffers
 static size_t pipe_item_bytes(const tmb_plan *p) {
     const size_t words = (size_t)std::max(1, p->pipe_words);
-    return al256((size_t)p->pipe_vstride) + (2 + words) * al256(sizeof(int) * (size_t)p->pipe_vstride) + 16 + 1024 + al256(2 * (size_t)p->pipe_vstride) +
+    return al256((size_t)p->pipe_vstride) + (2 + words) * al256(sizeof(int) * (size_t)p->pipe_vstride) + 16 + 1024 + al256((p->pipe_wfast ? 4 : 2) * (size_t)p->pipe_vstride) +
            al256((size_t)p->pipe_nbcap) +
            al256(sizeof(unsigned long long) * (size_t)p->pipe_paircap) + al256(sizeof(unsigned) * (size_t)p->pipe_tabcap);
 }
@@ -605,7 +642,7 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
         pp.basin = reinterpret_cast<int *>(base); base += al256(items * vs * sizeof(int));
         pp.meta = reinterpret_cast<int *>(base); base += al256(items * 16);
         pp.lhist = reinterpret_cast<int *>(base); base += al256(items * 1024);
-        pp.vlist = reinterpret_cast<unsigned short *>(base); base += al256(items * vs * 2);
+        pp.vlist = reinterpret_cast<unsigned short *>(base); base += al256(items * vs * (p->pipe_wfast ? 4 : 2));
         pp.blev = reinterpret_cast<unsigned char *>(base); base += al256(items * (size_t)p->pipe_nbcap);
         pp.pairs = reinterpret_cast<unsigned long long *>(base); base += al256(items * (size_t)p->pipe_paircap * sizeof(unsigned long long));
         pp.table = reinterpret_cast<unsigned *>(base);
@@ -614,7 +651,8 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
         pp.tfce_pos = tfce_pos ? tfce_pos + (size_t)b0 * ld : nullptr;
         pp.tfce_neg = tfce_neg ? tfce_neg + (size_t)b0 * ld : nullptr;
         pp.status = status ? status + eoff : nullptr;
-        pp.want_vertex_pass = (tfce_pos || tfce_neg || p->pipe_weights) ? 1 : 0;
+        pp.want_vertex_pass = (tfce_pos || tfce_neg || (p->pipe_weights && !p->pipe_wfast)) ? 1 : 0;
+        pp.weighted = (p->pipe_wfast && !pp.want_vertex_pass) ? 1 : 0;
         pp.slot_ws = p->d_pipe_slots; pp.slot_stride = p->pipe_slot_stride; pp.work_counter = p->d_counter;
         pp.timing = p->d_timing;
         pp.max_degree = 0;

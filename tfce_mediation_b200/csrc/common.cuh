@@ -72,11 +72,15 @@ struct SurfDesc {
     int32_t ell_width;      // 8, 16 or 32 when ell != nullptr
     // sliced rows (SELL-32-4) for graphs wider than 32 neighbours or with very uneven degrees: the 32 vertices of a
     // slice share a width (their largest degree rounded up to 4); slot group j4 of the slice is 32 consecutive int4
-    // (one per vertex), so a warp that owns the slice reads 512 contiguous bytes per group.  Pad = -1.
+    // (one per vertex), so a warp that owns the slice reads 512 contiguous bytes per group.  Pad = the vertex itself.
     const int4 *sell;       // [sell_off[nslices]] or nullptr (uploaded only for plans that use the wide kernels)
     const int32_t *sell_off; // [nslices + 1] first int4 of every slice
     const double *powE;     // [V+1]  pow((double)n, (double)E) tabulated with the host libm
     const float *weight;    // [V] or nullptr (internal vertex order)
+    // weighted maxima without the per-vertex pass (weights finite and >= 0, at most 65,535 distinct values): the
+    // weight of a vertex as the RANK of its value among the surface's distinct weights, and the values by rank
+    const unsigned short *wrank; // [V] or nullptr
+    const float *wtab;           // [distinct weights] or nullptr
     const int32_t *vmap;    // [V] internal (locality-reordered) index -> caller's index, or nullptr
     int64_t col_off;        // first column of this surface in a statistic row
     int32_t V;
@@ -152,7 +156,8 @@ struct PipeParams {
     int *meta;              // [items][4]: basins, candidate unions, over-capacity flag, unused
     int *lhist;             // [items][256]: [0,128) vertices per activation level (K_A), [128,256) the cursors with which
                             // K_C reserves each CTA's range of a level's vertex list (max-only maps)
-    unsigned short *vlist;  // [items][vstride] basin of every active vertex, bucketed by activation level (K_C -> sweep)
+    unsigned short *vlist;  // [items][vstride] basin of every active vertex, bucketed by activation level (K_C -> sweep);
+                            // weighted: 32-bit entries basin | weight rank << 16
     unsigned char *blev;    // [items][nbcap] level | sign of each peak
     int nbcap;
     unsigned long long *pairs; // [items][paircap] (level << 48) | (basin << 24) | basin
@@ -164,7 +169,10 @@ struct PipeParams {
     float *tfce_pos;
     float *tfce_neg;
     int32_t *status;
-    int want_vertex_pass;   // vertex weights or maps requested: values go through the table and K_G
+    int want_vertex_pass;   // maps requested (or weights the leader sweep cannot take): values go through the table and K_G
+    int front_cap;          // weighted sweep: entries a root's front may hold (<= 16; TMB_PIPE_FRONT lowers it in tests)
+    int weighted;           // max-only maps with vertex weights: vertex lists carry {basin, weight rank} (4 bytes), the sweep
+                            // keeps a Pareto front of (sum, weight) leaders per live root (pipe_sweep_max_kernel<.., true>)
     // sweep slots
     char *slot_ws;
     size_t slot_stride;

@@ -32,6 +32,7 @@
 
 #include <climits>
 #include <cstdlib>
+#include <type_traits>
 
 namespace tmb {
 
@@ -52,7 +53,14 @@ __device__ __forceinline__ int pf_find(int *parent, int v) {
     return cur;
 }
 
-__device__ __forceinline__ void pf_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// A base pointer the compiler must keep in registers.  Without it nvcc re-derives `P.array + item * vstride + index` --
+// a 64-bit multiply-add plus two constant-bank loads -- in front of EVERY predicated gather of the flat kernels (seen in
+// the SASS of round 1: seven instructions per neighbour byte instead of three).
+template <typename T>
+__device__ __forceinline__ T *pin_ptr(T *p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
 
 // asynchronous 8-byte copy global -> shared (LDGSTS): no register, no scoreboard stall until cp_async_wait_all
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(256) pipe_levels_kernel(PipeParams P, int chun
 template <bool kSix>
 __device__ __forceinline__ int ascent_of_vertex(const PipeParams &P, const SurfDesc &sd, size_t base, int v) {
     if (v >= sd.V) return -1;
-    const unsigned char *__restrict__ lev8 = P.lev8 + base;
+    const unsigned char *__restrict__ lev8 = pin_ptr(P.lev8 + base);
     const int cv = lev8[v];
     const int lev = cv & 0x7f;
     if (lev == 0) {
@@ -209,7 +217,7 @@ __device__ __forceinline__ int ascent_of_vertex(const PipeParams &P, const SurfD
     unsigned em = 0;
     const unsigned sign = (unsigned)cv & 0x80u;
     const unsigned mykey = ((unsigned)lev << 24) | (unsigned)v;
-    const int4 *__restrict__ row = reinterpret_cast<const int4 *>(sd.ell + (size_t)v * sd.ell_width);
+    const int4 *__restrict__ row = pin_ptr(reinterpret_cast<const int4 *>(sd.ell + (size_t)v * sd.ell_width));
     const int nch = kSix ? 1 : (sd.ell_width >> 3);
     constexpr int kSlots = kSix ? 6 : 8;
     for (int c = 0; c < nch; ++c) {
@@ -217,10 +225,10 @@ __device__ __forceinline__ int ascent_of_vertex(const PipeParams &P, const SurfD
         const int nb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
         unsigned ca[8];
 #pragma unroll
-        for (int j = 0; j < kSlots; ++j) ca[j] = nb[j] >= 0 ? (unsigned)lev8[nb[j]] : 0u;
+        for (int j = 0; j < kSlots; ++j) ca[j] = (unsigned)__ldg(lev8 + (unsigned)max(nb[j], 0)); // pad slots (-1): vertex 0, masked below
 #pragma unroll
         for (int j = 0; j < kSlots; ++j) {
-            const unsigned x = ca[j] ^ sign;                 // 1..127: active, same sign
+            const unsigned x = nb[j] >= 0 ? (ca[j] ^ sign) : 0u; // 1..127: active, same sign
             const unsigned la = (x - 1u) < 127u ? x : 255u;
             bestkey = min(bestkey, (la << 8) | (unsigned)(c * 8 + j));
             if (((la << 24) | (unsigned)nb[j]) < mykey) em |= 1u << (c * 8 + j); // nb < 2^24; la = 255 never passes
@@ -230,7 +238,7 @@ __device__ __forceinline__ int ascent_of_vertex(const PipeParams &P, const SurfD
     const bool has_up = (int)(bestkey >> 8) < lev;
     int best = v;
     if (has_up) {
-        best = sd.ell[(size_t)v * sd.ell_width + bestbit];
+        best = reinterpret_cast<const int *>(row)[bestbit];
         em &= ~(1u << bestbit); // the ascent target lies in the same basin by construction
         P.up[base + v] = best;
     }
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(256) pipe_ascent_wide_kernel(PipeParams P, int
     const size_t base = (size_t)item * P.vstride;
     int peak_code = -1;
     if (v < sd.V) {
-        const unsigned char *__restrict__ lev8 = P.lev8 + base;
+        const unsigned char *__restrict__ lev8 = pin_ptr(P.lev8 + base);
         const int cv = lev8[v];
         const int lev = cv & 0x7f;
         if (lev == 0) {
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(256) pipe_ascent_wide_kernel(PipeParams P, int
         } else {
             const int o0 = sd.sell_off[v >> 5];
             const int n4 = (sd.sell_off[(v >> 5) + 1] - o0) >> 5; // slot groups of this slice (warp-uniform)
-            const int4 *__restrict__ rows = sd.sell + o0 + lane;
+            const int4 *__restrict__ rows = pin_ptr(sd.sell + o0 + lane);
             unsigned bestkey = ((unsigned)lev << 8) | 0xffu; // level << 8 | slot of the ascent target so far
             const unsigned sign = (unsigned)cv & 0x80u;
             const unsigned mykey = ((unsigned)lev << 24) | (unsigned)v;
@@ -307,7 +315,7 @@ __global__ void __launch_bounds__(256) pipe_ascent_wide_kernel(PipeParams P, int
                         const int nb[4] = {r.x, r.y, r.z, r.w};
                         unsigned ca[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) ca[q] = nb[q] >= 0 ? (unsigned)lev8[nb[q]] : 0u;
+                        for (int q = 0; q < 4; ++q) ca[q] = (unsigned)__ldg(lev8 + (unsigned)nb[q]); // pad slots hold the vertex itself
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const unsigned x = ca[q] ^ sign;                 // 1..127: active, same sign
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(256) pipe_ascent_wide_kernel(PipeParams P, int
             const int bestbit = (int)(bestkey & 0xffu);
             const bool has_up = (int)(bestkey >> 8) < lev;
             if (has_up) {
-                const int best = reinterpret_cast<const int *>(sd.sell + o0 + (bestbit >> 2) * 32 + lane)[bestbit & 3];
+                const int best = reinterpret_cast<const int *>(rows + (bestbit >> 2) * 32)[bestbit & 3];
 #pragma unroll
                 for (int w = 0; w < kWords; ++w)
                     if (w == (bestbit >> 5)) em[w] &= ~(1u << (bestbit & 31)); // the ascent target lies in the same basin
@@ -359,15 +367,18 @@ __global__ void __launch_bounds__(256) pipe_ascent_wide_kernel(PipeParams P, int
 static constexpr int kBasinVPT = 4;                 // vertices per thread
 static constexpr int kBasinChunk = 256 * kBasinVPT; // vertices per CTA
 
+template <bool kWeighted>
 __global__ void __launch_bounds__(256) pipe_basin_kernel(PipeParams P, int chunks) {
+    using StageT = typename std::conditional<kWeighted, unsigned, unsigned short>::type;
     int item, chunk, s, b;
     grid_coords(P, item, chunk, s, b);
     const int V = P.surfs[s].V;
+    const unsigned short *__restrict__ wrank = P.surfs[s].wrank;
     const int v_beg = chunk * kBasinChunk;
     if (v_beg >= V) return; // CTA-uniform
     const int tid = threadIdx.x, lane = tid & 31;
     const size_t base = (size_t)item * P.vstride;
-    const int *__restrict__ up = P.up + base;
+    const int *__restrict__ up = pin_ptr(P.up + base);
     int t[kBasinVPT], levq[kBasinVPT];
 #pragma unroll
     for (int q = 0; q < kBasinVPT; ++q) {
@@ -379,7 +390,7 @@ __global__ void __launch_bounds__(256) pipe_basin_kernel(PipeParams P, int chunk
         bool more = false;
 #pragma unroll
         for (int q = 0; q < kBasinVPT; ++q)
-            if (t[q] >= 0) { t[q] = up[t[q]]; more |= t[q] >= 0; }
+            if (t[q] >= 0) { t[q] = __ldg(up + (unsigned)t[q]); more |= t[q] >= 0; }
         if (!more) break;
     }
     int bas[kBasinVPT];
@@ -411,7 +422,7 @@ __global__ void __launch_bounds__(256) pipe_basin_kernel(PipeParams P, int chunk
     // ---- max-only maps: vertex lists by level
     __shared__ int sLcnt[kLevels], sLbase[kLevels], sLloc[kLevels];
     __shared__ unsigned long long sWtot[kLevels / 32];
-    __shared__ unsigned short sStage[kBasinChunk];
+    __shared__ StageT sStage[kBasinChunk];
     __shared__ int sStagePos[kBasinChunk];
     if (tid < kLevels) sLcnt[tid] = 0;
     __syncthreads();
@@ -445,12 +456,17 @@ __global__ void __launch_bounds__(256) pipe_basin_kernel(PipeParams P, int chunk
     for (int q = 0; q < kBasinVPT; ++q)
         if (levq[q]) {
             const int i = sLloc[levq[q]] + rankq[q];
-            sStage[i] = (unsigned short)bas[q];
+            if (kWeighted) {
+                const int v = v_beg + q * 256 + tid;
+                sStage[i] = (StageT)((unsigned)bas[q] | ((unsigned)(wrank ? wrank[v] : 0) << 16));
+            } else {
+                sStage[i] = (StageT)bas[q];
+            }
             sStagePos[i] = sLbase[levq[q]] + rankq[q];
         }
     __syncthreads();
     const int total = sLloc[kLevels - 1] + sLcnt[kLevels - 1];
-    unsigned short *__restrict__ vlist = P.vlist + base;
+    StageT *__restrict__ vlist = reinterpret_cast<StageT *>(P.vlist) + base;
     for (int i = tid; i < total; i += 256) vlist[sStagePos[i]] = sStage[i];
 }
 
@@ -476,7 +492,7 @@ __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunk
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const size_t base = (size_t)item * P.vstride;
-    const int *__restrict__ basin = P.basin + base;
+    const int *__restrict__ basin = pin_ptr(P.basin + base);
     const int NB = meta[0];
     __shared__ int sBasin[kCountChunk]; // basins of the CTA's own vertices: most neighbour lookups land here
     int buq[kCountVPT], levq[kCountVPT];
@@ -506,15 +522,15 @@ __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunk
         // candidate unions: earlier neighbours lying in another basin (each distinct basin once per vertex, best
         // effort).  Staged in shared memory: one returning atomic per CTA reserves the output range.
         if (em && !(P.flags & 512)) {
-            const int *__restrict__ row = sd.ell + (size_t)v * sd.ell_width;
+            const int *__restrict__ row = pin_ptr(sd.ell + (size_t)v * sd.ell_width);
             int s0 = -1, s1 = -1, s2 = -1, s3 = -1;
             unsigned m = em;
             while (m) {
                 const int j = __ffs(m) - 1;
                 m &= m - 1;
-                const int a = row[j];
+                const int a = __ldg(row + j);
                 const unsigned off = (unsigned)(a - v_beg);
-                const int ba = off < (unsigned)kCountChunk ? sBasin[off] : basin[a];
+                const int ba = off < (unsigned)kCountChunk ? sBasin[off] : __ldg(basin + (unsigned)a);
                 if (ba == bu || ba == s0 || ba == s1 || ba == s2 || ba == s3) continue;
                 s3 = s2; s2 = s1; s1 = s0; s0 = ba;
                 const unsigned long long pr = ((unsigned long long)lev << 48) | ((unsigned long long)bu << 24) | (unsigned long long)ba;
@@ -565,8 +581,11 @@ __global__ void __launch_bounds__(256) pipe_count_wide_kernel(PipeParams P, int 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < kPairHash; i += 256) sHash[i] = ~0ull;
     const size_t base = (size_t)item * P.vstride;
-    const int *__restrict__ basin = P.basin + base;
+    const int *__restrict__ basin = pin_ptr(P.basin + base);
     const int NB = meta[0];
+    const unsigned *emw[kWords];
+#pragma unroll
+    for (int w = 0; w < kWords; ++w) emw[w] = pin_ptr(P.emask + ((size_t)item * kWords + w) * P.vstride);
     int buq[kCountVPT], levq[kCountVPT];
 #pragma unroll
     for (int q = 0; q < kCountVPT; ++q) {
@@ -588,17 +607,17 @@ __global__ void __launch_bounds__(256) pipe_count_wide_kernel(PipeParams P, int 
         }
         if (bu < 0) continue;
         const int o0 = sd.sell_off[v >> 5];
-        const int *__restrict__ row = reinterpret_cast<const int *>(sd.sell + o0 + lane);
+        const int *__restrict__ row = pin_ptr(reinterpret_cast<const int *>(sd.sell + o0 + lane));
         int s0 = -1, s1 = -1, s2 = -1, s3 = -1;
 #pragma unroll
         for (int w = 0; w < kWords; ++w) {
-            unsigned m = P.emask[((size_t)item * kWords + w) * P.vstride + v];
+            unsigned m = __ldg(emw[w] + v);
             while (m) {
                 const int j = w * 32 + __ffs(m) - 1;
                 m &= m - 1;
-                const int a = row[(j >> 2) * 128 + (j & 3)];
+                const int a = __ldg(row + (j >> 2) * 128 + (j & 3));
                 const unsigned off = (unsigned)(a - v_beg);
-                const int ba = off < (unsigned)kCountChunk ? sBasin[off] : basin[a];
+                const int ba = off < (unsigned)kCountChunk ? sBasin[off] : __ldg(basin + (unsigned)a);
                 if (ba == bu || ba == s0 || ba == s1 || ba == s2 || ba == s3) continue;
                 s3 = s2; s2 = s1; s1 = s0; s0 = ba;
                 const unsigned lo = (unsigned)min(bu, ba), hi = (unsigned)max(bu, ba);
@@ -606,9 +625,15 @@ __global__ void __launch_bounds__(256) pipe_count_wide_kernel(PipeParams P, int 
                 unsigned h = ((lo * 0x9E3779B1u) ^ (hi * 0x85EBCA6Bu)) >> (32 - kPairHashBits);
                 bool placed = false;
                 for (int probe = 0; probe < 16; ++probe) {
-                    const unsigned long long old = atomicCAS(&sHash[h], ~0ull, val);
+                    // plain look first: neighbouring vertices mostly find their pair already there with an earlier level
+                    unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(&sHash[h]);
+                    if (old == ~0ull) old = atomicCAS(&sHash[h], ~0ull, val);
                     if (old == ~0ull) { placed = true; break; }
-                    if ((old >> 8) == (val >> 8)) { atomicMin(&sHash[h], val); placed = true; break; }
+                    if ((old >> 8) == (val >> 8)) {
+                        if (val < old) atomicMin(&sHash[h], val);
+                        placed = true;
+                        break;
+                    }
                     h = (h + 1) & (kPairHash - 1);
                 }
                 if (!placed) { // table crowded: append directly
@@ -1106,13 +1131,32 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_kernel(PipePa
 // SM that hide each other's barrier intervals -- then the root lists live in global memory (L2) and the pow table and
 // the pending slots are halved, so that 14 bytes per basin fit twice into an SM.  Maps too large for the small
 // geometry are marked (meta[2] = 2) and taken by a second launch of the large one.
-__host__ __device__ inline size_t pipe_sweep_max_smem_bytes(int NB, bool small) {
+__host__ __device__ inline size_t pipe_sweep_max_smem_bytes(int NB, bool small, bool weighted) {
     const size_t nba = ((size_t)NB + 7) / 8 * 8;
-    return nba * (4 + 4 + 4 + 1 + 1 + (small ? 0 : 6)) + 16;
+    return nba * (4 + 4 + 4 + 1 + 1 + (small ? 0 : 6) + (weighted ? 13 : 0)) + 16;
+}
+
+// Weighted maxima (kW).  The scaled maximum of pyfunc.py:116-117 / tm_func.py:173-174 is max_v fl32(fl32(tfce_v * delta) * w_v).
+// All vertices of one class (component, activation level) share tfce_v, so only the class's largest weight matters; and
+// among the classes of one component, class a can be dropped for ever once another class b has sum_b >= sum_a AND
+// w_b >= w_a: both receive the same fp32 increments from now on (round-to-nearest addition is monotone) and the product
+// is monotone in the sum and in the weight (weights >= 0).  Each live root therefore carries the Pareto front of its
+// classes' (sum, weight rank) pairs -- a handful of entries: a late class of a big component sees thousands of new
+// vertices, hence nearly the largest weight, and dominates everything younger.  Entry 0 lives in shared memory, further
+// entries in the slot's global scratch.  The front of a root is only ever written by the thread that owns the root in
+// F3 (merging the fronts of the roots hooked under it this level, then the new class, then the increment), so no locks.
+static constexpr int kFront = 16;           // entries per root; a fuller front flags the map for the one-kernel sweep
+
+template <bool kW>
+__device__ __forceinline__ void ld_ent_if(unsigned &dst, const void *base, int idx, bool ok) {
+    if (kW)
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u32 %0, [%1];\n\t}" : "+r"(dst) : "l"(reinterpret_cast<const unsigned *>(base) + idx), "r"((int)ok) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u16 %0, [%1];\n\t}" : "+r"(dst) : "l"(reinterpret_cast<const unsigned short *>(base) + idx), "r"((int)ok) : "memory");
 }
 // + per-warp level histograms of the vertex sort: (threads / 32) * 128 ints, added by the launcher
 
-template <int kThreads, int kMinBlocks, bool kSmall>
+template <int kThreads, int kMinBlocks, bool kSmall, bool kW>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(PipeParams P, int smem_bytes, int stage) {
     constexpr int kPowN = kSmall ? 1024 : 2048; // pow(n, E) entries kept in shared memory
     constexpr int kPend = kSmall ? 256 : 512;   // asynchronous pow fetches in flight per level
@@ -1125,7 +1169,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
     __shared__ int sCurP[kLevels], sCurE[kLevels], sCurB[kLevels];
     __shared__ int sNs[2];
     __shared__ float sDelta[2];
-    __shared__ int sItem, sNpend, sNalive[2];
+    __shared__ int sItem, sNpend, sNalive[2], sOverflow;
     __shared__ float sRed[2][kThreads / 32];
 
     const int tid = threadIdx.x;
@@ -1136,7 +1180,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) sItem = atomicAdd(P.work_counter, 1);
+        if (tid == 0) { sItem = atomicAdd(P.work_counter, 1); sOverflow = 0; }
         __syncthreads();
         const int item = sItem;
         if (item >= total_items) break;
@@ -1158,8 +1202,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         // geometry takes the maps marked 2.  meta[2] == 1 always means "redo with tfce_basin_kernel".
         const int flag = meta[2];
         if (stage == 2 ? flag != 2 : flag != 0) continue;
-        const bool hopeless = NB > P.nbcap || NB > 65535 || NP > P.paircap;
-        const bool too_big = pipe_sweep_max_smem_bytes(NB, kSmall) > (size_t)smem_bytes;
+        const bool hopeless = NB > P.nbcap || NB > 65534 || NP > P.paircap || (kW && NB > kSweepBasinCap);
+        const bool too_big = pipe_sweep_max_smem_bytes(NB, kSmall, kW) > (size_t)smem_bytes;
         if (hopeless || too_big) {
             __syncthreads(); // everybody has read the flag
             if (tid == 0) {
@@ -1197,8 +1241,50 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             hooklev = reinterpret_cast<unsigned char *>(birth + nba);
         }
         unsigned char *blev = hooklev + nba;                                      // level | sign << 7 of the peak
+        // weighted: Pareto front of (sum, weight rank) per root -- entry 0 in racc / w0, entries 1.. in global scratch
+        int *wnew = reinterpret_cast<int *>(blev + nba);                          // largest weight rank + 1 among the vertices a root gains this level
+        int *phead = wnew + nba;                                                  // roots hooked under this one whose fronts must be merged (list head)
+        unsigned short *w0 = reinterpret_cast<unsigned short *>(phead + nba);
+        unsigned short *pnext = w0 + nba;
+        unsigned char *fcnt = reinterpret_cast<unsigned char *>(pnext + nba);     // entries in the root's front
+        uint2 *fr = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(ws.incseq) + (kSmall ? ((size_t)6 * nba + 15) / 16 * 16 : 0));
+        auto fget = [&](int r, int k) -> uint2 {
+            return k == 0 ? make_uint2((unsigned)racc[r], (unsigned)w0[r]) : fr[(size_t)r * kFront + k];
+        };
+        auto fset = [&](int r, int k, uint2 e) {
+            if (k == 0) { racc[r] = (int)e.x; w0[r] = (unsigned short)e.y; }
+            else fr[(size_t)r * kFront + k] = e;
+        };
+        // add class (sum bits s, weight rank w) to the front of root r (sums are >= 0: integer order == float order)
+        auto finsert = [&](int r, unsigned s_, unsigned w_) {
+            int c = fcnt[r];
+            for (int k = 0; k < c; ++k) {
+                const uint2 e = fget(r, k);
+                if (e.x >= s_ && e.y >= w_) return;      // dominated by an existing class
+            }
+            for (int k = 0; k < c;) {                    // drop the classes it dominates
+                const uint2 e = fget(r, k);
+                if (e.x <= s_ && e.y <= w_) { --c; if (k < c) fset(r, k, fget(r, c)); }
+                else ++k;
+            }
+            if (c >= P.front_cap) { sOverflow = 1; fcnt[r] = (unsigned char)c; return; }
+            fset(r, c, make_uint2(s_, w_));
+            fcnt[r] = (unsigned char)(c + 1);
+        };
+        auto fadd_all = [&](int r, float inc) {         // one level's increment to every class of the front
+            racc[r] = __float_as_int(__fadd_rn(__int_as_float(racc[r]), inc));
+            if (kW) {
+                const int c = fcnt[r];
+                for (int k = 1; k < c; ++k) {
+                    uint2 e = fr[(size_t)r * kFront + k];
+                    e.x = __float_as_uint(__fadd_rn(__uint_as_float(e.x), inc));
+                    fr[(size_t)r * kFront + k] = e;
+                }
+            }
+        };
         // basin of every active vertex, bucketed by level: built by K_C (see pipe_basin_kernel)
-        const unsigned short *__restrict__ elist = P.vlist + (size_t)item * P.vstride;
+        const void *__restrict__ elist = kW ? static_cast<const void *>(reinterpret_cast<const unsigned *>(P.vlist) + (size_t)item * P.vstride)
+                                            : static_cast<const void *>(P.vlist + (size_t)item * P.vstride);
 
         for (int i = tid; i < 2 * kLevels; i += nthr)
             sHHd[i / kLevels][i % kLevels] = (double)P.tab_HH[(e0 + i / kLevels) * kLevels + i % kLevels];
@@ -1219,6 +1305,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             bsize[i] = 0;
             racc[i] = 0; // +0.0f
             hooklev[i] = 255;
+            if (kW) { wnew[i] = 0; phead[i] = -1; fcnt[i] = 0; }
             const int cb = gblev[i];
             blev[i] = (unsigned char)cb;
             atomicAdd(&sCurB[cb & 0x7f], 1);
@@ -1277,20 +1364,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         };
         // the same for the level's vertex list: four entries per thread (basins of vertices sEstart[l] + q * nthr + tid)
         unsigned eqA[4] = {0u, 0u, 0u, 0u}, eqB[4] = {0u, 0u, 0u, 0u};
-#define PIPE_LD_U16(dst, ptr, ok) asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.u16 %0, [%1];\n\t}" : "+r"(dst) : "l"(ptr), "r"((int)(ok)) : "memory")
         auto prefetch_entry = [&](int l) {
             if (l >= nlev) return; // block-uniform
             const int ie = sEstart[l] + tid, iend = sEstart[l + 1];
             if (l & 1) {
-                PIPE_LD_U16(eqB[0], elist + ie, ie < iend);
-                PIPE_LD_U16(eqB[1], elist + ie + nthr, ie + nthr < iend);
-                PIPE_LD_U16(eqB[2], elist + ie + 2 * nthr, ie + 2 * nthr < iend);
-                PIPE_LD_U16(eqB[3], elist + ie + 3 * nthr, ie + 3 * nthr < iend);
+                ld_ent_if<kW>(eqB[0], elist, ie, ie < iend);
+                ld_ent_if<kW>(eqB[1], elist, ie + nthr, ie + nthr < iend);
+                ld_ent_if<kW>(eqB[2], elist, ie + 2 * nthr, ie + 2 * nthr < iend);
+                ld_ent_if<kW>(eqB[3], elist, ie + 3 * nthr, ie + 3 * nthr < iend);
             } else {
-                PIPE_LD_U16(eqA[0], elist + ie, ie < iend);
-                PIPE_LD_U16(eqA[1], elist + ie + nthr, ie + nthr < iend);
-                PIPE_LD_U16(eqA[2], elist + ie + 2 * nthr, ie + 2 * nthr < iend);
-                PIPE_LD_U16(eqA[3], elist + ie + 3 * nthr, ie + 3 * nthr < iend);
+                ld_ent_if<kW>(eqA[0], elist, ie, ie < iend);
+                ld_ent_if<kW>(eqA[1], elist, ie + nthr, ie + nthr < iend);
+                ld_ent_if<kW>(eqA[2], elist, ie + 2 * nthr, ie + 2 * nthr < iend);
+                ld_ent_if<kW>(eqA[3], elist, ie + 3 * nthr, ie + 3 * nthr < iend);
             }
         };
         prefetch_pairs(1);
@@ -1328,7 +1414,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                 for (int i = tid; i < npend; i += nthr) {
                     const int bb = sPendBb[i];
                     const float inc = __double2float_rn(__dmul_rn(sPendPw[i], sHHd[blev[bb] >> 7][lev - 1]));
-                    racc[bb] = __float_as_int(__fadd_rn(__int_as_float(racc[bb]), inc));
+                    fadd_all(bb, inc);
                 }
                 __syncthreads();
                 if (tid == 0) sNpend = 0;
@@ -1351,7 +1437,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                         for (int q = 0; q < 4; ++q) e4[q] = (lev & 1) ? eqB[q] : eqA[q];
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) { e4[q] = 0u; PIPE_LD_U16(e4[q], elist + eg + q * nthr + lane, eg + q * nthr + lane < eend); }
+                        for (int q = 0; q < 4; ++q) { e4[q] = 0u; ld_ent_if<kW>(e4[q], elist, eg + q * nthr + lane, eg + q * nthr + lane < eend); }
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -1359,7 +1445,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                         if (ew >= eend) break; // warp-uniform
                         const bool act = ew + lane < eend;
                         int r = -1;
-                        if (act) r = pf_find(bparent, (int)e4[q]);
+                        if (act) r = pf_find(bparent, kW ? (int)(e4[q] & 0xffffu) : (int)e4[q]);
                         // Late levels send most vertices to a few giant roots: same-address shared-memory atomics would
                         // serialise.  The lanes that agree with the first active lane's root are counted by one ballot.
                         // (A second round for the other sign's giant root was measured slower: 8.07 vs 7.87 ms per 1,024 maps.)
@@ -1369,6 +1455,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                         const unsigned same = __ballot_sync(0xffffffffu, act && r == r0);
                         if (lane == lead) atomicAdd(bsize + r0, __popc(same));
                         if (act && r != r0) atomicAdd(bsize + r, 1);
+                        if (kW) { // largest weight among the vertices every root gains at this level
+                            const int wr1 = act ? (int)(e4[q] >> 16) + 1 : 0;
+                            const int mw = __reduce_max_sync(0xffffffffu, (act && r == r0) ? wr1 : 0);
+                            if (lane == lead) atomicMax(wnew + r0, mw);
+                            if (act && r != r0) atomicMax(wnew + r, wr1);
+                        }
                     }
                 }
                 // older roots hooked in this level hand their size and their leader over (a root of this very level has
@@ -1389,7 +1481,24 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                         if (bb >= 0 && hooklev[bb] == lev) {
                             const int rr = pf_find(bparent, bb);
                             atomicAdd(bsize + rr, bsize[bb]);
-                            atomicMax(racc + rr, racc[bb]); // sums are >= 0: integer order == float order
+                            if (!kW) {
+                                atomicMax(racc + rr, racc[bb]); // sums are >= 0: integer order == float order
+                            } else {
+                                // does any class of bb survive against rr's front as it stands?  (read-only here; the owner
+                                // of rr merges the survivors' roots in F3 and checks again)
+                                const int cb2 = fcnt[bb], cr = fcnt[rr];
+                                bool push = false;
+                                for (int k = 0; k < cb2 && !push; ++k) {
+                                    const uint2 e = fget(bb, k);
+                                    bool dom = false;
+                                    for (int j = 0; j < cr && !dom; ++j) {
+                                        const uint2 f = fget(rr, j);
+                                        dom = f.x >= e.x && f.y >= e.y;
+                                    }
+                                    push = !dom;
+                                }
+                                if (push) pnext[bb] = (unsigned short)atomicExch(phead + rr, bb); // -1 -> 0xffff ends the list
+                            }
                         }
                     }
                 }
@@ -1433,11 +1542,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                     if (live) {
                         const int cb = blev[bb];
                         const int sg = cb >> 7;
+                        if (kW) {
+                            // the fronts of the roots hooked under bb at this level, then the class of the vertices gained
+                            // at this level (sum 0 so far); all sums are those after level lev - 1
+                            int hb = phead[bb];
+                            if (hb >= 0) {
+                                phead[bb] = -1;
+                                while (hb != 0xffff && hb >= 0) {
+                                    const int c2 = fcnt[hb];
+                                    for (int k = 0; k < c2; ++k) { const uint2 e = fget(hb, k); finsert(bb, e.x, e.y); }
+                                    hb = (int)pnext[hb];
+                                }
+                            }
+                            const int wn = wnew[bb];
+                            if (wn > 0) { wnew[bb] = 0; finsert(bb, 0u, (unsigned)(wn - 1)); }
+                        }
                         if (lev < (sg ? ns1 : ns0)) {
                             const int sz = bsize[bb];
                             if (sz < kPowN) {
                                 const float inc = __double2float_rn(__dmul_rn(sPow[sz], sHHd[sg][lev]));
-                                racc[bb] = __float_as_int(__fadd_rn(__int_as_float(racc[bb]), inc));
+                                fadd_all(bb, inc);
                             } else {
                                 const int slot = atomicAdd(&sNpend, 1);
                                 if (slot < kPend) {
@@ -1446,7 +1570,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                                 } else { // more large components than slots: fetch synchronously
                                     atomicSub(&sNpend, 1);
                                     const float inc = __double2float_rn(__dmul_rn(powE[sz], sHHd[sg][lev]));
-                                    racc[bb] = __float_as_int(__fadd_rn(__int_as_float(racc[bb]), inc));
+                                    fadd_all(bb, inc);
                                 }
                             }
                         }
@@ -1477,7 +1601,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             for (int i = tid; i < npend; i += nthr) {
                 const int bb = sPendBb[i];
                 const float inc = __double2float_rn(__dmul_rn(sPendPw[i], sHHd[blev[bb] >> 7][nlev - 1]));
-                racc[bb] = __float_as_int(__fadd_rn(__int_as_float(racc[bb]), inc));
+                fadd_all(bb, inc);
             }
         }
         __syncthreads();
@@ -1488,8 +1612,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         for (int bb = tid; bb < NB; bb += nthr)
             if (bparent[bb] == bb) {
                 const int sg = blev[bb] >> 7;
-                const float sc = __fmul_rn(__int_as_float(racc[bb]), sg ? d1 : d0);
-                if (sg) m1 = fmaxf(m1, sc); else m0 = fmaxf(m0, sc);
+                if (!kW) {
+                    const float sc = __fmul_rn(__int_as_float(racc[bb]), sg ? d1 : d0);
+                    if (sg) m1 = fmaxf(m1, sc); else m0 = fmaxf(m0, sc);
+                } else {
+                    const int c = fcnt[bb];
+                    for (int k = 0; k < c; ++k) { // fl32(fl32(tfce * delta) * w), the reference's order (pyfunc.py:116-117)
+                        const uint2 e = fget(bb, k);
+                        float sc = __fmul_rn(__uint_as_float(e.x), sg ? d1 : d0);
+                        if (sd.wtab) sc = __fmul_rn(sc, sd.wtab[e.y]);
+                        if (sg) m1 = fmaxf(m1, sc); else m0 = fmaxf(m0, sc);
+                    }
+                }
             }
         m0 = pwarp_max(m0);
         m1 = pwarp_max(m1);
@@ -1501,6 +1635,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             P.max_out[e0] = a;
             P.max_out[e0 + 1] = c;
         }
+        if (kW && tid == 0 && sOverflow) meta[2] = 1; // a front outgrew kFront entries: redone by tfce_basin_kernel
         PIPE_TICK(2)
 #undef PIPE_TICK
     }
@@ -1564,6 +1699,8 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
     if (const char *d = getenv("TMB_PIPE_DEBUG")) p.flags |= atoi(d) & ~7; // timing experiments only (results invalid)
     const int items = p.B * p.S;
     if (items <= 0) return 0;
+    p.front_cap = kFront;
+    if (const char *fc = getenv("TMB_PIPE_FRONT")) { const int v = atoi(fc); if (v >= 1 && v < kFront) p.front_cap = v; }
     const int chunksA = (p.Vmax + kChunkA - 1) / kChunkA;
     const int chunks = (p.Vmax + 255) / 256;
     TMB_REQUIRE(p.B <= 65535 && p.S <= 65535, "tfce pipeline: at most 65535 rows and surfaces per launch (got %d, %d)", p.B, p.S);
@@ -1582,7 +1719,8 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
     default: set_error("tfce pipeline: sell_words must be 0, 1, 2, 4 or 8 (got %d)", p.sell_words); return 1;
     }
     const int chunksC = (p.Vmax + kBasinChunk - 1) / kBasinChunk;
-    pipe_basin_kernel<<<dim3(chunksC, p.B, p.S), 256, 0, stream>>>(p, chunksC);
+    if (p.weighted) pipe_basin_kernel<true><<<dim3(chunksC, p.B, p.S), 256, 0, stream>>>(p, chunksC);
+    else pipe_basin_kernel<false><<<dim3(chunksC, p.B, p.S), 256, 0, stream>>>(p, chunksC);
     const int chunksD = (p.Vmax + kCountChunk - 1) / kCountChunk;
     const dim3 gridD(chunksD, p.B, p.S);
 #define TMB_COUNT_WIDE(W)                                                                                  \
@@ -1615,18 +1753,21 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
         int geom = 2;
         if (const char *g = getenv("TMB_PIPE_GEOM")) geom = atoi(g);
         const int smem_large = 196 * 1024, smem_small = 94 * 1024;
-        TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<1024, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_large));
         const int grid_large = items < num_slots / 2 ? items : num_slots / 2;
-        if (geom == 1) {
-            pipe_sweep_max_kernel<1024, 1, false><<<grid_large, 1024, smem_large, stream>>>(p, smem_large, 0);
-        } else {
-            TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<512, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_small));
-            const int grid = items < num_slots ? items : num_slots;
-            pipe_sweep_max_kernel<512, 2, true><<<grid, 512, smem_small, stream>>>(p, smem_small, 1);
-            TMB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
-            pipe_sweep_max_kernel<1024, 1, false><<<grid_large, 1024, smem_large, stream>>>(p, smem_large, 2);
-            count_launch();
+        const int grid_small = items < num_slots ? items : num_slots;
+#define TMB_SWEEP_MAX(W)                                                                                                   \
+        TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<1024, 1, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_large)); \
+        if (geom == 1) {                                                                                                   \
+            pipe_sweep_max_kernel<1024, 1, false, W><<<grid_large, 1024, smem_large, stream>>>(p, smem_large, 0);          \
+        } else {                                                                                                           \
+            TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<512, 2, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_small)); \
+            pipe_sweep_max_kernel<512, 2, true, W><<<grid_small, 512, smem_small, stream>>>(p, smem_small, 1);             \
+            TMB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));                                             \
+            pipe_sweep_max_kernel<1024, 1, false, W><<<grid_large, 1024, smem_large, stream>>>(p, smem_large, 2);          \
+            count_launch();                                                                                                \
         }
+        if (p.weighted) { TMB_SWEEP_MAX(true) } else { TMB_SWEEP_MAX(false) }
+#undef TMB_SWEEP_MAX
     }
     count_launch(5);
     if (p.want_vertex_pass) {
