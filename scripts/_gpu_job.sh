@@ -1,3 +1,4 @@
-(time python -m pytest tests/test_gpu_weighted.py tests/test_gpu_wide.py tests/test_gpu_pipeline.py tests/test_gpu_tfce.py tests/test_gpu_fullsize.py -x -q) > gpurun_out/r2g_pytest.log 2>&1; tail -4 gpurun_out/r2g_pytest.log
-python scripts/probe_wide.py 7 4 300 256 ring1,pipe,pipe_w > gpurun_out/r2g_probe.log 2>&1; tail -3 gpurun_out/r2g_probe.log
-TMB_PIPE_ROWS=sell python scripts/probe_wide.py 7 4 300 256 ring1 > gpurun_out/r2g_probe_sell.log 2>&1; tail -1 gpurun_out/r2g_probe_sell.log
+set -x
+python bench.py --workload tiny --steps 3 > gpurun_out/r2h_tiny.json 2> gpurun_out/r2h_tiny.err; tail -3 gpurun_out/r2h_tiny.err; cat gpurun_out/r2h_tiny.json
+python bench.py --workload tiny --job 400 --job-check 40 > gpurun_out/r2h_tinyjob.json 2> gpurun_out/r2h_tinyjob.err; tail -3 gpurun_out/r2h_tinyjob.err; cat gpurun_out/r2h_tinyjob.json
+python bench.py --workload config2_3mm --steps 6 > gpurun_out/r2h_3mm.json 2> gpurun_out/r2h_3mm.err; tail -3 gpurun_out/r2h_3mm.err; cat gpurun_out/r2h_3mm.json

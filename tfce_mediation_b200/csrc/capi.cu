@@ -81,6 +81,7 @@ struct tmb_plan {
     int pipe_weights = 0;       // some surface carries vertex weights (scaled maxima then need the per-vertex pass)
     int pipe_words = 0;         // 0: fixed-width rows; W > 0: sliced rows, W mask words per vertex (wide pipeline kernels)
     int pipe_items = 0;
+    int pipe_has_table = 0;     // the per-item buffers include the class path's [level][basin] table (32 B per vertex)
     int64_t pipe_vstride = 0, pipe_tabcap = 0;
     int pipe_nbcap = 0, pipe_paircap = 0;
     char *d_pipe = nullptr;     // one allocation: lev8 | up | emask | basin | meta | blev | pairs | table
@@ -523,16 +524,17 @@ struct TableSet {
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
 // per-item bytes of the streaming pipeline's buffers
-static size_t pipe_item_bytes(const tmb_plan *p) {
+static size_t pipe_item_bytes(const tmb_plan *p, bool with_table) {
     const size_t words = (size_t)std::max(1, p->pipe_words);
     return al256((size_t)p->pipe_vstride) + (2 + words) * al256(sizeof(int) * (size_t)p->pipe_vstride) + 16 + 1024 + al256((p->pipe_wfast ? 4 : 2) * (size_t)p->pipe_vstride) +
            al256((size_t)p->pipe_nbcap) +
-           al256(sizeof(unsigned long long) * (size_t)p->pipe_paircap) + al256(sizeof(unsigned) * (size_t)p->pipe_tabcap);
+           al256(sizeof(unsigned long long) * (size_t)p->pipe_paircap) +
+           (with_table ? al256(sizeof(unsigned) * (size_t)p->pipe_tabcap) : 0);
 }
 
 // (re)allocate the pipeline buffers for at least `items` work items; returns the number of items that fit
 // the memory budget (a third of the free HBM), 0 when not even one does.
-static int pipe_ensure(tmb_plan *p, int items) {
+static int pipe_ensure(tmb_plan *p, int items, bool need_table) {
     if (p->pipe_vstride == 0) {
         p->pipe_vstride = ((int64_t)p->Vmax + 127) / 128 * 128;
         p->pipe_nbcap = (int)std::min<int64_t>(p->pipe_vstride, std::max<int64_t>(4096, p->pipe_vstride / 8));
@@ -550,20 +552,24 @@ static int pipe_ensure(tmb_plan *p, int items) {
             return 0;
         }
     }
-    if (items <= p->pipe_items) return items;
-    const size_t per = pipe_item_bytes(p);
+    const bool table = need_table || p->pipe_has_table;
+    if (items <= p->pipe_items && (!need_table || p->pipe_has_table)) return items;
+    const size_t per = pipe_item_bytes(p, table);
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return p->pipe_items; }
-    const size_t have = (size_t)p->pipe_items * per;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return p->pipe_has_table || !need_table ? p->pipe_items : 0; }
+    const size_t have = (size_t)p->pipe_items * pipe_item_bytes(p, p->pipe_has_table != 0);
     const size_t fit = (free_b + have) / 3 / per;
-    int want = (int)std::min<size_t>((size_t)items, fit);
-    if (want <= p->pipe_items) return p->pipe_items;
+    int want = (int)std::min<size_t>((size_t)std::max(items, p->pipe_items), fit);
+    if (want <= p->pipe_items && (!need_table || p->pipe_has_table)) return p->pipe_items;
     cudaFree(p->d_pipe);
     p->d_pipe = nullptr;
     p->pipe_items = 0;
+    p->pipe_has_table = 0;
+    if (want < 1) return 0;
     if (cudaMalloc(&p->d_pipe, per * (size_t)want + 8192) != cudaSuccess) { cudaGetLastError(); return 0; }
     p->pipe_items = want;
-    return want;
+    p->pipe_has_table = table ? 1 : 0;
+    return std::min(want, items);
 }
 
 static int tabs_ensure(tmb_plan *p, int items) {
@@ -602,7 +608,8 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
                        const TableSet *tabs = nullptr) {
     const bool pipeline = p->pipe_ok && !accumulate && stop_level < 0 && B > 0;
     int fit = 0;
-    if (pipeline) fit = pipe_ensure(p, B * p->S) / p->S; // statistic rows per pipeline pass
+    const bool class_path = tfce_pos || tfce_neg || (p->pipe_weights && !p->pipe_wfast);
+    if (pipeline) fit = pipe_ensure(p, B * p->S, class_path) / p->S; // statistic rows per pipeline pass
     if (!pipeline || fit < 1)
         return plan_launch_sweep(p, stat, ld, B, two_sided, accumulate, max_dev, tfce_pos, tfce_neg, status, stop_level,
                                  labels, extents, thr, stream, tabs, nullptr);

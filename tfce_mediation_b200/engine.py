@@ -582,7 +582,12 @@ class PermutationEngine(object):
     def sobelz(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", want_f64=False, caller_order=True):
         """Fused two-fit Sobel-family z for a block of shuffles (pyfunc.py:130-162).
         Returns CUDA float32 [P, ld] (and float64 when want_f64)."""
-        import torch
+        XA, XB, ta_scalar = self.mediation_designs(medtype, pred_x, depend_y, perm_idx)
+        return self.sobelz_designs(XA, XB, ta_scalar, alg, want_f64, caller_order)
+
+    def mediation_designs(self, medtype, pred_x, depend_y, perm_idx):
+        """Per-shuffle designs of calc_sobelz (pyfunc.py:130-162) under the drivers' permutation rule
+        (vertex_tfce_mediation_randomise.py:82-90): (XA [P, n, 2] or None, XB [P, n, 3], ta scalars or None)."""
         n = self.Y.n
         pred_x = np.asarray(pred_x, dtype=np.float64).reshape(n)
         depend_y = np.asarray(depend_y, dtype=np.float64).reshape(n)
@@ -606,15 +611,24 @@ class PermutationEngine(object):
             XB = np.stack([ones, dep, xp], axis=2)
         else:
             raise ValueError("Invalid mediation type")
-        return self.sobelz_designs(XA, XB, ta_scalar, alg, want_f64, caller_order)
+        return XA, XB, ta_scalar
 
     def sobelz_designs(self, XA, XB, ta_scalar=None, alg="aroian", want_f64=False, caller_order=True):
         """Sobel-family z from two stacks of per-shuffle designs (intercept in column 0): path A = t of XA's first
         regressor (or the per-shuffle scalars ta_scalar when XA is None), path B = t of XB's first regressor.
-        XA float64 [P, n, kA], XB [P, n, kB], (kA - 1) + (kB - 1) <= 8.  Serves calc_sobelz (pyfunc.py:130-162) and the
-        tm-models mediation branch (tm_models_randomise.py:430-503: glm_typeI t-values + calc_indirect)."""
+        XA float64 [P, n, kA], XB [P, n, kB].  Serves calc_sobelz (pyfunc.py:130-162) and the tm-models mediation
+        branch (tm_models_randomise.py:430-503: glm_typeI t-values + calc_indirect)."""
+        ops = self.sobelz_operands(XA, XB, ta_scalar, alg)
+        z32, z64 = self.sobelz_launch(ops, want_f64=want_f64)
+        if caller_order and self.colperm is not None:
+            z32 = self.to_caller_order(z32)
+            z64 = self.to_caller_order(z64) if z64 is not None else None
+        return (z32, z64) if want_f64 else z32
+
+    def sobelz_operands(self, XA, XB, ta_scalar=None, alg="aroian", resident=False):
+        """Host algebra (k x k per design) + upload of the two-path operands; `resident` keeps private device copies
+        (bench: operands prepared before the timed region) instead of the reused pinned staging buffers."""
         import torch
-        n = self.Y.n
         P = XB.shape[0]
         sB = design_stack(XB, center=True)
         if XA is not None:
@@ -627,27 +641,32 @@ class PermutationEngine(object):
         rB = sB["r"]
         rp = _rp_for(rA + rB)
         At, ldA = pack_At(pinv, rp)
-        At_d = self._upload("med_At", At)
-        GA_d = self._upload("med_GA", sA["G"]) if sA else None
-        dA_d = self._upload("med_dA", sA["d"]) if sA else None
-        GB_d = self._upload("med_GB", sB["G"])
-        dB_d = self._upload("med_dB", sB["d"])
-        ta_d = self._upload("med_ta", ta_scalar) if ta_scalar is not None else None
-        yy = self.Y.sumsq(True)
-        z32 = torch.empty((P, self.Y.ld), dtype=torch.float32, device=self.device)
-        z64 = torch.empty((P, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
         algc = {"aroian": 0, "sobel": 1, "goodman": 2}.get(alg)
         if algc is None:
             raise ValueError("Unknown indirect test algorithm")
+        if resident:
+            up = lambda name, a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)   # noqa: E731
+        else:
+            up = self._upload
+        return dict(P=P, rp=rp, ldA=ldA, rA=rA, rB=rB, alg=algc,
+                    At=up("med_At", At), GA=up("med_GA", sA["G"]) if sA else None,
+                    dA=up("med_dA", sA["d"]) if sA else None, GB=up("med_GB", sB["G"]), dB=up("med_dB", sB["d"]),
+                    ta=up("med_ta", ta_scalar) if ta_scalar is not None else None,
+                    dofA=sA["dof"] if sA else 1.0, dofB=sB["dof"])
+
+    def sobelz_launch(self, ops, want_f64=False, out=None):
+        """The fused two-fit kernel (tmb_sobelz) on prepared operands: CUDA float32 [P, ld] (internal column order)."""
+        import torch
+        P = ops["P"]
+        yy = self.Y.sumsq(True)
+        z32 = out if out is not None else torch.empty((P, self.Y.ld), dtype=torch.float32, device=self.device)
+        z64 = torch.empty((P, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
         _lib.check(_lib.lib().tmb_sobelz(
-            _lib.ptr(self.Y.t), self.Y.dtype_code, n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA, rp,
-            _lib.ptr(GA_d), _lib.ptr(dA_d), rA, 0, sA["dof"] if sA else 1.0, _lib.ptr(GB_d), _lib.ptr(dB_d), rB, 0,
-            sB["dof"], _lib.ptr(yy), _lib.ptr(ta_d), P, algc, _lib.ptr(z32), _lib.ptr(z64), self.Y.ld,
-            _lib.current_stream()))
-        if caller_order and self.colperm is not None:
-            z32 = self.to_caller_order(z32)
-            z64 = self.to_caller_order(z64) if z64 is not None else None
-        return (z32, z64) if want_f64 else z32
+            _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(ops["At"]), ops["ldA"],
+            ops["rp"], _lib.ptr(ops["GA"]), _lib.ptr(ops["dA"]), ops["rA"], 0, ops["dofA"], _lib.ptr(ops["GB"]),
+            _lib.ptr(ops["dB"]), ops["rB"], 0, ops["dofB"], _lib.ptr(yy), _lib.ptr(ops["ta"]), P, ops["alg"],
+            _lib.ptr(z32), _lib.ptr(z64), self.Y.ld, _lib.current_stream()))
+        return z32, z64
 
     def tm_models_mediation_block(self, medtype, leftvar, rightvar, dmy_covariates, perm_idx, alg="aroian", download=True):
         """One block of the tm-models mediation loop (tmanalysis/tm_models_randomise.py:430-520): shuffle p uses

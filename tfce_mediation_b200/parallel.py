@@ -69,6 +69,13 @@ def init_process_group(backend=None):
         dist.init_process_group(backend)
 
 
+def finalize():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def gather_rows(local_rows, counts=None):
     """All-gather per-shuffle result rows.  local_rows: float array [P_local, ...]; every rank may hold a
     different P_local (shard_range).  Returns the concatenation in rank order on every rank."""

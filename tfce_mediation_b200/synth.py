@@ -122,3 +122,35 @@ def vertex_density(csr):
     indptr, _ = csr
     d = np.diff(indptr).astype(np.float64)
     return np.array(1 - (d / d.max()) + (d.mean() / d.max()), dtype=np.float32)
+
+
+def voxel_csr(mask, dirtype=26):
+    """26-connectivity adjacency of a 3-D mask as CSR with the semantics of pyfunc.create_adjac_voxel
+    (pyfunc.py:48-76): voxels labelled in np.where (C) order, sorted neighbour lists without self, voxel 0
+    isolated in both directions.  Vectorised host builder for the synthetic workloads (the product builds it
+    on the GPU: tmb_voxel_adjacency)."""
+    if int(dirtype) != 26:
+        raise ValueError("only 26-connectivity here")
+    mask = np.asarray(mask).astype(bool)
+    lab = -np.ones(mask.shape, dtype=np.int64)
+    V = int(mask.sum())
+    lab[mask] = np.arange(V)
+    pad = -np.ones(tuple(d + 2 for d in mask.shape), dtype=np.int64)
+    pad[1:-1, 1:-1, 1:-1] = lab
+    src, dst = [], []
+    c = pad[1:-1, 1:-1, 1:-1]
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                if dx == 0 and dy == 0 and dz == 0:
+                    continue
+                nb = pad[1 + dx:pad.shape[0] - 1 + dx, 1 + dy:pad.shape[1] - 1 + dy, 1 + dz:pad.shape[2] - 1 + dz]
+                ok = (c > 0) & (nb > 0)          # label 0 neither lists nor is listed (the reference's `> 0` test)
+                src.append(c[ok]); dst.append(nb[ok])
+    src = np.concatenate(src); dst = np.concatenate(dst)
+    order = np.lexsort((dst, src))
+    src, dst = src[order], dst[order]
+    indptr = np.zeros(V + 1, dtype=np.int64)
+    np.add.at(indptr, src + 1, 1)
+    np.cumsum(indptr, out=indptr)
+    return indptr, dst.astype(np.int32)

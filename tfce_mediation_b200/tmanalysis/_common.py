@@ -9,6 +9,20 @@ from .._graph import adjacency_to_csr, induced_subgraph
 
 BLOCK = 512      # shuffles per engine call
 
+# wall-clock marks of the last driver run: [(label, seconds since the previous mark)], read by tmanalysis/job.py
+TIMINGS = []
+_last_tick = [None]
+
+
+def tick(label=None):
+    """Start (label None) or extend the phase log of a driver run."""
+    now = time()
+    if label is None:
+        del TIMINGS[:]
+    elif _last_tick[0] is not None:
+        TIMINGS.append((label, now - _last_tick[0]))
+    _last_tick[0] = now
+
 
 def load(path):
     return np.load(path, allow_pickle=True)

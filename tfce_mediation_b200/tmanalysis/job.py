@@ -1,0 +1,140 @@
+"""Whole-job run of the north-star configuration through the drop-in drivers, with a wall-clock breakdown.
+
+BASELINE.json's target: 10,000 permutations of the vertex-wise regression + TFCE on fsaverage lh+rh (300 subjects)
+in under a minute on 8 x B200 with FWER p-maps identical to the reference's.  The chain timed here is the reference's
+own (STEP_2_tfce_randomise_parallel.py:139-157 -> vertex_tfce_multiple_regression_randomise.py:56-118 ->
+perm_tstat_con1_TFCE_maxVertex.csv -> calculate_fweP_vertex.py:45-79) with this package's modules in place of
+every step; one process per GPU (torchrun), every rank its slice of the permutation range, one all-gather.
+
+Not timed: synthesising the python_temp_<surface>/ state (it is the output of the reference's step 1,
+STEP_1_vertex_tfce_multiple_regression.py:251-266) and the parity check afterwards, in which the compiled reference
+(oracle/_ref, all host cores) redoes the first `check` permutations and both the CSV rows and the p-map built from
+them must be identical.  The checker is passed in by bench.py (`checker(workdir, shuffles, seed) -> rows`): this package
+never imports oracle/."""
+import os
+import shutil
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+from .. import parallel, synth
+from . import _common as C
+
+SEED = 7
+
+
+def write_state(workdir, workload):
+    """python_temp_area/ exactly as the reference's step 1 leaves it (on-disk contract)."""
+    level, n, rounds, keep = (7, 300, 6, (149955, 149926)) if workload != "tiny" else (4, 40, 2, (2400, 2300))
+    v, f = synth.icosphere(level)
+    csr1 = synth.faces_to_csr(v.shape[0], f)
+    masks = [synth.cap_mask(v, keep[0]), synth.cap_mask(-v, keep[1])]
+    csr = csr1
+    dens = [1, 1]
+    if workload == "config2_3mm":
+        csr = synth.kring_csr(csr1, 4)
+        d = synth.vertex_density(csr)
+        dens = [d, d]
+    ys = [synth.subject_data(n, csr1, 1 + h, rounds)[:, masks[h]] for h in range(2)]
+    y = np.ascontiguousarray(np.hstack(ys), dtype=np.float32)
+    pred_x = np.random.RandomState(1).standard_normal((n, 1))
+    tmp = os.path.join(workdir, "python_temp_area")
+    os.makedirs(tmp, exist_ok=True)
+    adj = np.empty(v.shape[0], dtype=object)
+    lists = synth.csr_to_lists(csr)
+    for i in range(v.shape[0]):
+        adj[i] = lists[i]
+    np.save(os.path.join(tmp, "merge_y.npy"), y)
+    np.save(os.path.join(tmp, "pred_x.npy"), pred_x)
+    np.save(os.path.join(tmp, "num_subjects.npy"), n)
+    np.save(os.path.join(tmp, "num_vertex.npy"), y.shape[1])
+    np.save(os.path.join(tmp, "num_vertex_lh.npy"), int(masks[0].sum()))
+    np.save(os.path.join(tmp, "all_vertex.npy"), v.shape[0])
+    np.save(os.path.join(tmp, "bin_mask_lh.npy"), masks[0])
+    np.save(os.path.join(tmp, "bin_mask_rh.npy"), masks[1])
+    np.save(os.path.join(tmp, "adjac_lh.npy"), adj, allow_pickle=True)
+    np.save(os.path.join(tmp, "adjac_rh.npy"), adj, allow_pickle=True)
+    np.save(os.path.join(tmp, "optstfce.npy"), np.array([2.0, 0.67]))
+    np.save(os.path.join(tmp, "vdensity_lh.npy"), dens[0])
+    np.save(os.path.join(tmp, "vdensity_rh.npy"), dens[1])
+
+
+# ---- the job -------------------------------------------------------------------------------------------------------
+def run_job(numperm, workload="config2", gpus=1, t_process_start=None, check=200, keep=None, checker=None):
+    import argparse
+    from . import STEP_2_tfce_randomise_parallel as step2
+    from .calculate_fweP import fwe_image
+    rank, ws, local = parallel.world()
+    if ws != gpus and not (ws == 1 and gpus == 1):
+        raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % gpus)
+    t_entry = time.time()
+    tag = os.environ.get("MASTER_PORT", "p%d" % os.getpid())
+    workdir = keep or os.path.join(tempfile.gettempdir(), "tmb_job_%s" % tag)
+    marker = os.path.join(workdir, ".state_ready")
+    # ---- untimed: the reference's step-1 state on disk
+    if rank == 0:
+        if os.path.exists(workdir) and not keep:
+            shutil.rmtree(workdir)
+        os.makedirs(workdir, exist_ok=True)
+        if not os.path.exists(marker):
+            write_state(workdir, workload)
+            open(marker, "w").close()
+    else:
+        while not os.path.exists(marker):
+            time.sleep(0.2)
+    t_state = time.time()
+    # ---- timed from here (plus interpreter start-up before run_job, reported separately)
+    os.chdir(workdir)
+    opts = step2.getArgumentParser(argparse.ArgumentParser()).parse_args(
+        ["--vertex", "area", "-n", str(numperm), "--seed", str(SEED)])
+    shuffles = step2.rounded_shuffles(numperm, False)
+    import importlib
+    mod, argv = step2.driver_call(opts)
+    drv = importlib.import_module("tfce_mediation_b200.tmanalysis." + mod)
+    eng = drv.run(drv.getArgumentParser(argparse.ArgumentParser()).parse_args(argv))
+    phases = list(C.TIMINGS)
+    t_rand = time.time()
+    line = None
+    if rank == 0:
+        import torch
+        csv = "output_area/perm_Tstat_area/perm_tstat_con1_TFCE_maxVertex.csv"
+        perm_max = np.genfromtxt(csv)
+        X = np.column_stack([np.ones(eng.Y.n), np.load("python_temp_area/pred_x.npy")])
+        obs = eng.observed_statistics(X)                           # step-1 statistic with full TFCE maps
+        pmap_pos = fwe_image(perm_max, obs["tfce_pos"][0])
+        pmap_neg = fwe_image(perm_max, obs["tfce_neg"][0])
+        torch.cuda.synchronize()
+        t_done = time.time()
+        startup = (t_entry - t_process_start) if t_process_start else 0.0
+        wall = startup + (t_done - t_state)
+        # ---- untimed parity check against the compiled reference on the first `check` permutations
+        chk = None
+        if check > 0 and checker is not None:
+            k = min(shuffles, max(1, check // 2))
+            ref = checker(workdir, k, SEED)
+            mine = perm_max[:2 * k]
+            rows_equal = all("%.4f" % a == "%.4f" % b for a, b in zip(ref, mine))
+            ref_sorted = np.array([float("%.4f" % r) for r in ref])
+            same_p = bool(np.array_equal(fwe_image(ref_sorted, obs["tfce_pos"][0]), fwe_image(mine, obs["tfce_pos"][0])) and
+                          np.array_equal(fwe_image(ref_sorted, obs["tfce_neg"][0]), fwe_image(mine, obs["tfce_neg"][0])))
+            chk = {"permutations_checked": 2 * k, "csv_rows_identical": bool(rows_equal),
+                   "fwer_pmaps_identical_on_subset": same_p}
+        line = {
+            "metric": "wall-clock seconds, %d-permutation vertex-wise regression + TFCE + FWER p-map (%s)" % (numperm, workload),
+            "value": wall, "unit": "s", "n_gpus": ws, "higher_is_better": False, "target_s": 60.0,
+            "data": "synthetic", "config": {"workload": workload, "permutations": numperm, "shuffles": shuffles,
+                                            "driver_block": C.BLOCK, "seed": SEED},
+            "breakdown_s": dict([("process start -> job entry (interpreter, imports)", startup)] +
+                                [(k, v) for k, v in phases] +
+                                [("observed statistic + FWER p-maps (rank 0)", t_done - t_rand)]),
+            "excluded": {"synthesising python_temp_area (reference step-1 output)": t_state - t_entry},
+            "significant_vertices_p>0.95": {"pos": int((pmap_pos > 0.95).sum()), "neg": int((pmap_neg > 0.95).sum())},
+            "shuffles_per_s_whole_job": shuffles / wall,
+            "parity": chk,
+        }
+    parallel.finalize()
+    if rank == 0 and not keep:
+        shutil.rmtree(workdir, ignore_errors=True)
+    return line

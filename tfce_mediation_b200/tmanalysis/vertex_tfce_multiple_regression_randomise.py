@@ -31,7 +31,9 @@ def getArgumentParser(ap=ap.ArgumentParser(description=DESCRIPTION)):
 
 def run(opts):
     start_time = time()
+    C.tick()
     C.setup()            # bind cuda:LOCAL_RANK and join the process group before any device state exists
+    C.tick("init (torch, CUDA context, process group)")
     np.seterr(divide="ignore", invalid="ignore")
     from ..engine import PermutationEngine
     first, last = int(opts.range[0]), int(opts.range[1])
@@ -53,10 +55,13 @@ def run(opts):
     vdensity_lh = C.load("%s/vdensity_lh.npy" % tmp)
     vdensity_rh = C.load("%s/vdensity_rh.npy" % tmp)
     H, E = float(optstfce[0]), float(optstfce[1])
+    C.tick("load python_temp state")
 
     surfs = [C.masked_surface(adjac_lh, H, E, bin_mask_lh, vdensity_lh, 0),
              C.masked_surface(adjac_rh, H, E, bin_mask_rh, vdensity_rh, num_vertex_lh)]
+    C.tick("graphs (CSR, locality order, upload)")
     eng = PermutationEngine(ny, surfs, two_sided=True)
+    C.tick("engine (data upload, column order)")
 
     outdir = "output_%s/perm_Tstat_%s" % (surface, surface)
     rank, ws, a, b = C.shard(first, last)
@@ -75,8 +80,10 @@ def run(opts):
             np.random.seed(C.reference_seed(iter_perm, opts.seed))
             idx.append(C.draw_block_permutation(block_list, indexer) if opts.exchangeblock
                        else C.draw_row_permutation(n))
+        C.tick("permutation index stream (numpy RNG)")
         if idx:
             results.append(eng.regression_blocks(X, np.stack(idx), block=C.BLOCK).max(axis=2))
+        C.tick("shuffles (fit + TFCE + max)")
     else:
         for p0, p1 in C.chunks(a, b):
             designs = []
@@ -89,11 +96,14 @@ def run(opts):
             results.append(mx.max(axis=2))             # max over the two hemispheres -> [P, C, 2]
     local = np.concatenate(results, axis=0) if results else np.zeros((0, k - 1, 2), dtype=np.float32)
     allrows = parallel.gather_rows(local)
+    C.tick("all-gather of the maxima")
     if rank == 0:
         for j in range(ncon):                          # the reference writes contrasts 1..ncon (:108-117)
             rows = allrows[:, j, :].reshape(-1)        # +t then -t per shuffle
             C.append_rows("%s/perm_tstat_con%d_TFCE_maxVertex.csv" % (outdir, j + 1), rows, "%.4f")
+        C.tick("CSV rows")
         print("Finished. Randomization took %.1f seconds" % (time() - start_time))
+    return eng
 
 
 if __name__ == "__main__":
