@@ -545,7 +545,7 @@ def run_b200(args):
             At, ldA = E.pack_At(st["pinv"], 1)
             stacks.append((torch.from_numpy(At).to(dev), ldA, torch.from_numpy(st["G"]).to(dev),
                            torch.from_numpy(st["d"]).to(dev), st["dof"]))
-    fit_rows = 3 if w["kind"] == "mediation" else 1             # stacked pseudo-inverse rows per shuffle
+    fit_rows = 3 if w["kind"] == "mediation" else 1             # pseudo-inverse rows per shuffle (path A: 1, path B: 2)
     t32b = [torch.empty((P, C, ld), dtype=torch.float32, device=dev) for _ in range(2)]
     out_max = torch.empty((P * C, S, 2), dtype=torch.float32, device=dev)
     gathered = [torch.empty_like(out_max) for _ in range(world)] if world > 1 else None
@@ -562,7 +562,7 @@ def run_b200(args):
             At_d, ldA, G_d, d_d, dof = stacks[s]
             _lib.check(L.tmb_glm_tstat(_lib.ptr(eng.Y.t), eng.Y.dtype_code, eng.Y.n, eng.Y.V, ld, _lib.ptr(At_d), ldA,
                                        _lib.ptr(G_d), _lib.ptr(d_d), P, 1, 1, 0, 1, dof, _lib.ptr(yy), _lib.ptr(buf), None,
-                                       ld, 1 if w["nan_to_zero"] else 0, _lib.current_stream()))
+                                       ld, 1 if w["nan_to_zero"] else 0, 0, _lib.current_stream()))
         if fa is not None:
             fb.record(); fit_events.append((fa, fb))
         return eng.plan.prepare(buf.view(P * C, ld))          # maxima kernel + async copy to the host
@@ -606,8 +606,7 @@ def run_b200(args):
     # ---- end-to-end arm: the public call, host index rows in (pinned staging), host maxima out ----
     def e2e_call(idx):
         if w["kind"] == "mediation":
-            return np.concatenate([eng.mediation_block(w["medtype"], w["pred_x"], w["depend_y"], idx[a:a + P])
-                                   for a in range(0, idx.shape[0], P)], axis=0)
+            return eng.mediation_blocks(w["medtype"], w["pred_x"], w["depend_y"], idx, block=P)
         return eng.regression_blocks(X, idx, block=P)
 
     e2e_call(np.concatenate(idx_all[:min(args.warmup, 2)], axis=0))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TMB_ABI_VERSION 1
+#define TMB_ABI_VERSION 2
 #define TMB_F32 0
 #define TMB_F64 1
 
@@ -122,9 +122,13 @@ int tmb_plan_run_tables(tmb_plan *p, const float *stat_dev, int64_t ld, int B, i
  * Y_dev: float32 (ydtype TMB_F32) or float64 (TMB_F64) [n, ldy] row-major subject-by-vertex data
  *        (== merge_y; the reference feeds float64 in step 1 and float32 in the randomise step); ldy is a multiple of 128
  *        covering V rounded up to 128 (pad columns zero); 16-byte aligned.
- * At_dev: float64 [n, ldA]: column j*rp + i is row i of the j-th design's pseudo-inverse
- *         (X_j'X_j)^-1 X_j' (k-major so one subject's coefficients are contiguous); rp is r padded
- *         to 1, 2, 4 or 8 with zero columns; ldA is a multiple of 128 covering P*rp rounded up.
+ * At_dev: float64 [n, ldA]: row i of the j-th design's pseudo-inverse (X_j'X_j)^-1 X_j' as one column
+ *         (k-major so one subject's coefficients are contiguous); rp is r padded to 1, 2, 4 or 8 with
+ *         zero columns.  Column order `layout` (ask tmb_glm_layout(ydtype, rp), which knows the kernel that will run):
+ *           0: column j*rp + i                               (fp64 vector kernel), ldA >= P*rp
+ *           1: "tile8", column (j/8)*8*rp + i*8 + j%8        (fp64 tensor-core kernels: one 8-row DMMA tile
+ *              holds one regressor of 8 designs),            ldA >= ceil(P/8)*8*rp
+ *         ldA is a multiple of 128 covering those columns; columns beyond them are zero.
  * G_dev:  float64 [P, r, r] = X_j'X_j ;  d_dev: float64 [P, r] = diag((X_j'X_j)^-1).
  * yy_dev: float64 [V] = sum_i Y[i,v]^2 (tmb_glm_sumsq; colsum_dev optionally receives sum_i Y[i,v]).
  * SSE = yy - b'Gb ; sigma2 = SSE/dof ; se = (float)sqrt(sigma2 * d)  (the fp32 rounding of
@@ -140,7 +144,13 @@ int tmb_glm_sumsq(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, 
 int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev, int64_t ldA,
                   const double *G_dev, const double *d_dev, int P, int r, int rp, int row0, int nrows,
                   double dof, const double *yy_dev, float *t32_dev, double *t64_dev, int64_t ldt,
-                  int nan_to_zero, void *stream);
+                  int nan_to_zero, int layout, void *stream);
+/* What the fit kernels expect for this data type: the column order of At_dev (see above), the padded regressor count rp
+ * for r regressors (0: r is outside 1..8 -- use the *_beta entry points below), and the columns of At_dev they read
+ * for P designs (a multiple of 128; allocate At_dev with ldA >= this, zero-filled beyond the packed columns). */
+int tmb_glm_layout(int ydtype, int rp);
+int tmb_glm_rp(int ydtype, int r);
+int64_t tmb_glm_packed_columns(int ydtype, int P, int rp);
 /* F statistics of pyfunc.py:2282-2401 glm_typeI (the tm-models GLM branch, tmanalysis/tm_models_randomise.py:197-272)
  * for P designs at once, from ONE fit per design: operands as in tmb_glm_tstat (centred designs, r = k-1 regressors).
  * Tested variable i covers regressor rows [var_lo[i], var_lo[i] + var_k[i]) (host arrays, nvar <= 8); M_dev float64
@@ -151,15 +161,31 @@ int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, 
 int tmb_glm_fstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev, int64_t ldA,
                   const double *G_dev, const double *M_dev, int P, int r, int rp, int nvar, const int32_t *var_lo,
                   const int32_t *var_k, int want_model, double dof, const double *yy_dev, float *f32_dev,
-                  double *f64_dev, int64_t ldt, int nan_to_zero, void *stream);
+                  double *f64_dev, int64_t ldt, int nan_to_zero, int layout, void *stream);
 
 /* Stacked pseudo-inverses of P row-permuted copies of ONE design (the permutation loop of
  * vertex_tfce_multiple_regression_randomise.py:104-106, `nx = X[np.random.permutation(...)]`): permuting whole rows
- * permutes the columns of pinv(X), so At[k, p*rp + i] = pinv[i, perm_idx[p, k]] is a gather done on the device.
+ * permutes the columns of pinv(X), so At[k, col(p, i)] = pinv[i, perm_idx[p, k]] is a gather done on the device
+ * (col as in tmb_glm_tstat's `layout`).
  * pinv_dev float64 [r, n] (centred regressors' pseudo-inverse), perm_idx_dev int32 [P, n], At_dev float64 [n, ldA]
- * (columns beyond P*rp and rows i >= r are zero-filled). */
+ * (unused columns and rows i >= r are zero-filled). */
 int tmb_glm_pack_rowperm(const double *pinv_dev, int r, int n, const int32_t *perm_idx_dev, int P, int rp,
-                         double *At_dev, int64_t ldA, void *stream);
+                         double *At_dev, int64_t ldA, int layout, void *stream);
+
+/* Designs with MORE than 8 non-intercept regressors (the reference accepts any k: cynumstats.pyx:28-29,59-64 -- e.g.
+ * dummy-coded sites plus covariates): the betas are formed first by tmb_glm_beta (every pseudo-inverse row of every
+ * design is one column of At_dev and one output row, design-major: row p*r + i), then these evaluate the same statistics
+ * as tmb_glm_tstat / tmb_glm_fstat / tmb_sobelz per (design, vertex) from beta_dev float64 [P*r, ldb].  r <= 64. */
+int tmb_glm_tstat_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *G_dev, const double *d_dev, int P,
+                       int r, int row0, int nrows, double dof, const double *yy_dev, float *t32_dev, double *t64_dev,
+                       int64_t ldt, int nan_to_zero, void *stream);
+int tmb_glm_fstat_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *G_dev, const double *M_dev, int P,
+                       int r, int nvar, const int32_t *var_lo, const int32_t *var_k, int want_model, double dof,
+                       const double *yy_dev, float *f32_dev, double *f64_dev, int64_t ldt, int nan_to_zero, void *stream);
+int tmb_sobelz_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *GA_dev, const double *dA_dev, int rA,
+                    int rowA, double dofA, const double *GB_dev, const double *dB_dev, int rB, int rowB, double dofB,
+                    const double *yy_dev, const double *ta_scalar_dev, int P, int alg, float *z32_dev, double *z64_dev,
+                    int64_t ldt, void *stream);
 
 /* betas only == cynumstats.pyx:28-29 cy_lin_lstsqr_mat: beta64_dev float64 [nrows, ldt] for the nrows
  * pseudo-inverse rows stored as the first nrows columns of At_dev (ldA a multiple of 128). */
@@ -186,8 +212,8 @@ int tmb_se_of_slope(const double *sigma2_dev, int64_t V, const double *d_dev, in
 /* ---------------------------------------------------------------------------------------------
  * Sobel / Aroian / Goodman mediation z == pyfunc.py:130-162 calc_sobelz for P permutations.
  * Path A and path B are two fits of the same data; their pseudo-inverse rows are stacked in one
- * operand laid out like tmb_glm_tstat's At_dev with group width rp (1,2,4,8): columns
- * j*rp + [0,rA) are path A's rows of permutation j, columns j*rp + rA + [0,rB) path B's.
+ * operand laid out like tmb_glm_tstat's At_dev with group width rp (1,2,4,8) and the same `layout`: regressors
+ * [0,rA) of permutation j are path A's rows, regressors rA + [0,rB) path B's.
  * GA/dA [P,rA,rA]/[P,rA] and GB/dB [P,rB,rB]/[P,rB] as in tmb_glm_tstat; rowA/rowB select the
  * coefficient whose t enters (calc_beta_se's a[1] / se[1], cynumstats.pyx:66-74).
  * ta_scalar_dev (may be NULL): float64 [P] path-A t as a per-permutation scalar (medtype 'Y',
@@ -198,7 +224,7 @@ int tmb_sobelz(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, con
                const double *GA_dev, const double *dA_dev, int rA, int rowA, double dofA, const double *GB_dev,
                const double *dB_dev, int rB, int rowB, double dofB, const double *yy_dev,
                const double *ta_scalar_dev, int P, int alg, float *z32_dev, double *z64_dev, int64_t ldt,
-               void *stream);
+               int layout, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Voxel adjacency == pyfunc.py:48-76 create_adjac_voxel (variant 0) and

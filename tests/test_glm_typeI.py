@@ -291,3 +291,23 @@ def test_tm_models_randomise_mediation_driver_rows(tmp_path, monkeypatch, medtyp
         want.append(oracle.perm_max_vertex(z, nlh, st["keep_lh"], st["keep_rh"], run, run, st["dens"], st["dens"]))
     got = np.array([float(l) for l in open("output_mediation_area/perm_mediation/perm_Zstat_%s_TFCE_maxVertex.csv" % medtype)])
     assert np.allclose(got, np.array(want), rtol=1e-5, atol=6e-5)
+
+
+@pytest.mark.gpu
+def test_glm_typeI_with_many_covariates_matches_oracle():
+    """tm-models GLM with dummy-coded covariates beyond 8 regressors (pyfunc.py:2282-2401 has no limit): the partial F
+    and t maps of the stored-beta path agree with the oracle's restatement to 1e-9."""
+    from tfce_mediation_b200 import pyfunc
+    n, V = 90, 400
+    rs = np.random.RandomState(4)
+    data = rs.standard_normal((n, V)).astype(np.float64)
+    site = np.eye(8)[rs.randint(0, 8, n)][:, 1:]
+    exog = [rs.standard_normal((n, 1)), rs.standard_normal((n, 2))]
+    cov = np.column_stack([site, rs.standard_normal((n, 4))])           # 3 + 11 = 14 regressors
+    perm = rs.permutation(n)
+    for r in (None, perm):
+        F, Fvar, T = pyfunc.glm_typeI(data, exog, dmy_covariates=cov, output_tvalues=True, verbose=False, rand_array=r)
+        wF, wFvar = oracle.glm_typeI(data, exog, cov, rand_array=r)
+        wT = oracle.glm_typeI(data, exog, cov, output_fvalues=False, output_tvalues=True, rand_array=r)
+        tol = lambda a, b: np.all(np.abs(a - b) <= 1e-9 * np.maximum(1, np.abs(b)))   # noqa: E731
+        assert tol(F, wF) and tol(Fvar, wFvar) and tol(T, wT)

@@ -111,3 +111,88 @@ def test_dmma_fast_epilogue_bit_identical_to_exact(monkeypatch):
     nx = X[perm[3]]
     ref = oracle.tval_int(nx, np.linalg.inv(nx.T @ nx), y[:, 256:2256], n, 2, 2000)[1].astype(np.float32)
     assert np.mean(got[3, 0, 256:2256].cpu().numpy() != ref) < 1e-3
+
+
+def _fit_engine(y):
+    from tfce_mediation_b200 import engine as eng
+    from tfce_mediation_b200._device import DeviceMatrix
+    Y = DeviceMatrix(y)
+    e = eng.PermutationEngine.__new__(eng.PermutationEngine)      # fit only: no TFCE plan needed
+    e.device, e.Y, e.nan_to_zero, e.h2d_bytes, e.d2h_bytes, e._pinned, e.colperm = Y.t.device, Y, False, 0, 0, {}, None
+    e._rings = {}
+    return e
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_every_regressor_count_on_both_fit_kernels(k, dtype):
+    """r = k - 1 = 1..8 regressors: float32 data runs on the tensor-core kernels (tile8 column order, one CTA shape per
+    r, no padded rows), float64 data on the fp64 vector kernel (r padded to 1/2/4/8).  Ragged P (not a multiple of 8)
+    and a ragged last subject chunk (n % 32 != 0).  cynumstats.pyx:59-64 via the oracle."""
+    from tfce_mediation_b200 import engine as eng
+    n, V, P = 45, 1300, 21
+    X, y = _data(n, V, k, 11 + k, 0.5, dtype)
+    rs = np.random.RandomState(k)
+    idx = np.stack([rs.permutation(n) for _ in range(P)])
+    e = _fit_engine(y)
+    t32, t64 = e.tstat(eng.row_permuted_stack(X, idx), want_f64=True)
+    t32r = e.tstat_rowperm(X, idx)                                  # device-side gather of the pseudo-inverse columns
+    t32, t64, t32r = t32.cpu().numpy()[:, :, :V], t64.cpu().numpy()[:, :, :V], t32r.cpu().numpy()[:, :, :V]
+    assert np.array_equal(t32, t32r)
+    bad = 0
+    for p in range(P):
+        nx = X[idx[p]]
+        want = oracle.tval_int(nx, np.linalg.inv(nx.T @ nx), y, n, k, V)[1:]
+        assert _close64(t64[p], want)
+        bad += int(np.sum(t32[p] != want.astype(np.float32)))
+    assert bad <= 2, bad
+    # a sub-range of rows, as the drivers request it for `-v first last`
+    if k >= 4:
+        sub = e.tstat(eng.row_permuted_stack(X, idx), rows=(1, 2)).cpu().numpy()[:, :, :V]
+        assert np.array_equal(sub, t32[:, 1:3])
+
+
+@pytest.mark.parametrize("k", [10, 21, 40])
+def test_many_regressors_stored_beta_path(k):
+    """More than 8 non-intercept regressors (site dummies + covariates): the reference has no limit
+    (cynumstats.pyx:28-29,59-64); here the betas make one round trip through HBM (tmb_glm_beta + tmb_glm_tstat_beta)."""
+    from tfce_mediation_b200 import engine as eng
+    n, V, P = 90, 700, 5
+    X, y = _data(n, V, k, 50 + k, 1.0)
+    rs = np.random.RandomState(k)
+    idx = np.stack([rs.permutation(n) for _ in range(P)])
+    e = _fit_engine(y)
+    t32, t64 = e.tstat(eng.row_permuted_stack(X, idx), want_f64=True)
+    t32r = e.tstat_rowperm(X, idx, rows=(0, 3)).cpu().numpy()[:, :, :V]
+    t32, t64 = t32.cpu().numpy()[:, :, :V], t64.cpu().numpy()[:, :, :V]
+    assert np.array_equal(t32[:, :3], t32r)
+    for p in range(P):
+        nx = X[idx[p]]
+        want = oracle.tval_int(nx, np.linalg.inv(nx.T @ nx), y, n, k, V)[1:]
+        assert _close64(t64[p], want, 1e-9)
+        np.testing.assert_allclose(t32[p], want.astype(np.float32), rtol=1e-5, atol=1e-7)
+
+
+def test_regression_block_with_twenty_regressors_end_to_end():
+    """A 20-column design through the whole engine (fit -> TFCE -> max): rows equal the oracle pipeline's."""
+    from tests import helpers
+    from tfce_mediation_b200.engine import PermutationEngine, Surface
+    from tfce_mediation_b200.tfce import CreateAdjSet
+    from tfce_mediation_b200 import synth
+    _, _, csr = helpers.ico(4)
+    V = csr[0].shape[0] - 1
+    n, k, P = 80, 20, 3
+    y = synth.subject_data(n, csr, 5, 2)
+    rs = np.random.RandomState(9)
+    site = np.eye(6)[rs.randint(0, 6, n)][:, 1:]                      # dummy-coded site
+    X = np.column_stack([np.ones(n), rs.standard_normal((n, k - 1 - site.shape[1])), site])
+    eng = PermutationEngine(y, [Surface(CreateAdjSet(2, 0.67, csr), 0)])
+    idx = np.stack([oracle.permutation_indices(77 + p, n) for p in range(P)])
+    got = eng.regression_block(X, perm_idx=idx)
+    assert got.shape == (P, k - 1, 1, 2)
+    for p in range(P):
+        nx = X[idx[p]]
+        t = oracle.tval_int(nx, np.linalg.inv(nx.T @ nx), y, n, k, V)
+        for c in (0, 7, k - 2):
+            want = helpers.oracle_signed_max(2, 0.67, csr, t[c + 1].astype(np.float32))
+            assert "%.4f" % got[p, c, 0, 0] == "%.4f" % want[0] and "%.4f" % got[p, c, 0, 1] == "%.4f" % want[1]

@@ -80,6 +80,8 @@ struct GlmParams {
     // stored one after the other (k_i x k_i each, msz doubles per design); variable i covers rows [var_lo[i], +var_k[i])
     const double *M; int msz, nvar; int var_lo[8], var_k[8];
     int exact_epilogue;                 // DMMA kernel: always take the fp64 square root / division (TMB_GLM_EPILOGUE=exact)
+    int layout;                         // column order of At: 0 = p * rp + i (DFMA tile kernel); 1 = "tile8": 8 designs x rp
+                                        // regressors per block, column (p / 8) * 8 * rp + i * 8 + p % 8 (DMMA kernels)
 };
 
 // sum_{a,b in [lo,lo+r)} acc[g*RP+a][c] * G[(a-lo)*r + (b-lo)] * acc[g*RP+b][c]; every loop is fully
@@ -551,16 +553,245 @@ static int launch_dmma(const GlmParams &p, cudaStream_t stream) {
     return 0;
 }
 
+
+// ---------------------------------------------------------------- DMMA, several regressors per design (rp = 2, 4, 8)
+// Same contraction and operand ring as glm_dmma_kernel.  The columns of At come in the "tile8" order -- blocks of 8
+// designs, inside a block first regressor 0 of the 8 designs, then regressor 1, ... -- so that one 8-row DMMA tile holds
+// ONE regressor of 8 designs and a thread's accumulators of RP consecutive row tiles hold ALL the betas of one
+// (design, vertex) pair: the fused epilogue (t, partial F, Sobel z) needs no exchange between threads.
+//   RP <= 4: 8 warps as 2 (m) x 4 (n), warp tile 32 x 32 (4 x 4 DMMA tiles, 4 / RP design groups per warp)
+//   RP == 8: 8 warps as 1 (m) x 8 (n), warp tile 64 x 16 (8 x 2 DMMA tiles, one design group)
+//   RP = 3     : CTA tile 48 rows, 2 x 4 warps, warp tile 24 x 32 (no padded regressor row: k = 4 regression, Sobel 'M'/'I')
+//   RP = 5,6,7 : CTA tile 8 * RP rows, 1 x 8 warps, warp tile (8 * RP) x 16
+template <int RP>
+struct DmmaShape {
+    static constexpr int WM = RP <= 4 ? 2 : 1;                        // warps along m
+    static constexpr int MT = RP <= 2 ? 4 : RP;                       // DMMA row tiles per warp (a multiple of RP)
+    static constexpr int NT = RP <= 4 ? 4 : 2;                        // DMMA column tiles per warp
+    static constexpr int ROWS = WM * MT * 8;                          // CTA tile rows: 64, 64, 48, 64, 40, 48, 56, 64
+    static constexpr int PITCH = ROWS + 4;                            // doubles per staged A row (pitch mod 16 = 4 or 12:
+                                                                      // fragment loads take the minimum two wavefronts)
+};
+
+// b'Gb over regressors [lo, lo + r) of one (design, vertex); G row-major r x r in global memory (L1-resident: 8 designs per warp)
+template <int RP>
+__device__ __forceinline__ double dq_form(const double (&b)[RP], const double *__restrict__ G, int lo, int r) {
+    double q = 0.0;
+#pragma unroll
+    for (int a = 0; a < RP; ++a) {
+        if (a >= lo && a < lo + r) {
+            double inner = 0.0;
+#pragma unroll
+            for (int c = 0; c < RP; ++c)
+                if (c >= lo && c < lo + r) inner = __fma_rn(__ldg(G + (a - lo) * r + (c - lo)), b[c], inner);
+            q = __fma_rn(b[a], inner, q);
+        }
+    }
+    return q;
+}
+
+template <int RP>
+__device__ __forceinline__ double dpick(const double (&b)[RP], int idx) {
+    double v = 0.0;
+#pragma unroll
+    for (int a = 0; a < RP; ++a)
+        if (a == idx) v = b[a];
+    return v;
+}
+
+// all statistics of one (design, vertex) from its RP betas; same arithmetic as epilogue<RP> of the DFMA kernel
+template <int RP>
+__device__ __forceinline__ void dmma_vertex_stats(const GlmParams &p, int perm, const double (&b)[RP], double yyv, int64_t v) {
+    const bool inside = v < p.V;
+    if (p.mode == 0) {
+        const int r = p.r;
+        const double sse = yyv - dq_form<RP>(b, p.G + (size_t)perm * r * r, 0, r);
+        const double *dg = p.d + (size_t)perm * r;
+#pragma unroll
+        for (int a = 0; a < RP; ++a) {
+            if (a < p.row0 || a >= p.row0 + p.nrows || a >= r) continue;
+            double t = t_from(b[a], sse, p.dof, __ldg(dg + a));
+            if (p.nan_to_zero && t != t) t = 0.0;
+            if (!inside) t = 0.0;
+            const size_t off = ((size_t)perm * p.nrows + (a - p.row0)) * p.ldt + v;
+            if (p.t32) p.t32[off] = __double2float_rn(t);
+            if (p.t64) p.t64[off] = t;
+        }
+    } else if (p.mode == 3) {
+        const int r = p.r;
+        const double ssb = dq_form<RP>(b, p.G + (size_t)perm * r * r, 0, r);
+        const double ms = __ddiv_rn(yyv - ssb, p.dof);
+        const int first = p.row0 == 0 ? 1 : 0;
+        if (first) {
+            double f = __ddiv_rn(__ddiv_rn(ssb, (double)r), ms);
+            if (p.nan_to_zero && f != f) f = 0.0;
+            if (!inside) f = 0.0;
+            const size_t off = (size_t)perm * p.nrows * p.ldt + v;
+            if (p.t32) p.t32[off] = __double2float_rn(f);
+            if (p.t64) p.t64[off] = f;
+        }
+        const double *M = p.M + (size_t)perm * p.msz;
+#pragma unroll 1
+        for (int i = 0; i < p.nvar; ++i) {
+            const int lo = p.var_lo[i], ki = p.var_k[i];
+            double f = __ddiv_rn(dq_form<RP>(b, M, lo, ki), __dmul_rn(ms, (double)ki));
+            if (p.nan_to_zero && f != f) f = 0.0;
+            if (!inside) f = 0.0;
+            const size_t off = ((size_t)perm * p.nrows + first + i) * p.ldt + v;
+            if (p.t32) p.t32[off] = __double2float_rn(f);
+            if (p.t64) p.t64[off] = f;
+            M += ki * ki;
+        }
+    } else { // sobel (pyfunc.py:130-162)
+        const int rA = p.rA, rB = p.rB;
+        double ta;
+        if (p.ta_scalar) {
+            ta = p.ta_scalar[perm];
+        } else {
+            const double sseA = yyv - dq_form<RP>(b, p.G + (size_t)perm * rA * rA, 0, rA);
+            ta = t_from(dpick<RP>(b, p.rowA), sseA, p.dof, p.d[(size_t)perm * rA + p.rowA]);
+        }
+        const double sseB = yyv - dq_form<RP>(b, p.GB + (size_t)perm * rB * rB, rA, rB);
+        const double tb = t_from(dpick<RP>(b, rA + p.rowB), sseB, p.dofB, p.dB[(size_t)perm * rB + p.rowB]);
+        const double ta2 = __dmul_rn(ta, ta), tb2 = __dmul_rn(tb, tb);
+        double s = __dadd_rn(__ddiv_rn(1.0, tb2), __ddiv_rn(1.0, ta2));
+        const double cross = __ddiv_rn(1.0, __dmul_rn(ta2, tb2));
+        if (p.alg == 0) s = __dadd_rn(s, cross);
+        else if (p.alg == 2) s = __dsub_rn(s, cross);
+        double z = __ddiv_rn(1.0, __dsqrt_rn(s));
+        if (!inside) z = 0.0;
+        const size_t off = (size_t)perm * p.ldt + v;
+        if (p.t32) p.t32[off] = __double2float_rn(z);
+        if (p.t64) p.t64[off] = z;
+    }
+}
+
+template <int RP, typename YT>
+__global__ void __launch_bounds__(256, 2) glm_dmma_multi_kernel(GlmParams p, int mtiles) {
+    constexpr int MT = DmmaShape<RP>::MT, NT = DmmaShape<RP>::NT, WM = DmmaShape<RP>::WM;
+    constexpr int DM = DmmaShape<RP>::ROWS, DPA = DmmaShape<RP>::PITCH;   // shadow the r == 1 kernel's constants
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sA = reinterpret_cast<double *>(smem_raw);                                  // [DSTAGES][DK][DPA]
+    YT *sY = reinterpret_cast<YT *>(smem_raw + sizeof(double) * DSTAGES * DK * DPA);    // [DSTAGES][DK][DPY]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + sizeof(double) * DSTAGES * DK * DPA +
+                                                   sizeof(YT) * DSTAGES * DK * DPY);
+    uint64_t *empty = full + DSTAGES;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int mt = tile % mtiles;
+    const int64_t vt = tile / mtiles;
+    const int m0 = mt * DM;
+    const int64_t v0 = vt * DN;
+    const int nchunks = (p.n + DK - 1) / DK;
+    if (tid == 0) {
+        for (int s = 0; s < DSTAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue_chunk = [&](int kc) {
+        const int s = kc % DSTAGES;
+        const int round = kc / DSTAGES;
+        mbar_wait(empty + s, (round & 1) ^ 1);
+        const int k0 = kc * DK;
+        const int rows = min(DK, p.n - k0);
+        if (warp == 0) mbar_expect_tx(full + s, (uint32_t)rows * (DM * 8 + DN * (uint32_t)sizeof(YT)));
+        for (int kk = warp; kk < rows; kk += 8) {
+            bulk_g2s(sA + ((size_t)s * DK + kk) * DPA, p.At + (size_t)(k0 + kk) * p.ldA + m0, DM * 8, full + s);
+            bulk_g2s(sY + ((size_t)s * DK + kk) * DPY, reinterpret_cast<const YT *>(p.Y) + (size_t)(k0 + kk) * p.ldy + v0,
+                     DN * (uint32_t)sizeof(YT), full + s);
+        }
+    };
+    if (lane == 0)
+        for (int kc = 0; kc < DSTAGES - 1 && kc < nchunks; ++kc) issue_chunk(kc);
+
+    const int wm = WM == 1 ? 0 : (warp >> 2), wn = WM == 1 ? warp : (warp & 3);
+    const int g = lane >> 2, t4 = lane & 3;
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kc = 0; kc < nchunks; ++kc) {
+        const int s = kc % DSTAGES;
+        const int round = kc / DSTAGES;
+        if (lane == 0 && kc + DSTAGES - 1 < nchunks) issue_chunk(kc + DSTAGES - 1);
+        mbar_wait(full + s, round & 1);
+        const int rows = min(DK, p.n - kc * DK);
+        const double *a_st = sA + (size_t)s * DK * DPA + wm * (MT * 8) + g;
+        const YT *y_st = sY + (size_t)s * DK * DPY + wn * (NT * 8) + g;
+        for (int k4 = 0; k4 < rows; k4 += 4) {
+            const int kr = k4 + t4;
+            const bool ok = kr < rows;
+            double a[MT], b[NT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) a[i] = ok ? a_st[(size_t)kr * DPA + i * 8] : 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) b[j] = ok ? (double)y_st[(size_t)kr * DPY + j * 8] : 0.0;
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+    // epilogue: row tile i of the warp is regressor i % RP of the designs ((m0 / 8 + wm * MT + i) / RP) * 8 + 0..7
+#pragma unroll
+    for (int gi = 0; gi < MT / RP; ++gi) {
+        const int perm = ((m0 / 8 + wm * MT) / RP + gi) * 8 + g;
+        if (perm >= p.P) continue;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t v = v0 + wn * (NT * 8) + j * 8 + t4 * 2 + e;
+                double b[RP];
+#pragma unroll
+                for (int i = 0; i < RP; ++i) b[i] = acc[gi * RP + i][j][e];
+                const double yyv = (v < p.V) ? p.yy[v] : 0.0;
+                if (v < p.ldt) dmma_vertex_stats<RP>(p, perm, b, yyv, v);
+            }
+        }
+    }
+}
+
+template <int RP, typename YT>
+static int launch_dmma_multi(const GlmParams &p, cudaStream_t stream) {
+    constexpr int DM = DmmaShape<RP>::ROWS, DPA = DmmaShape<RP>::PITCH;
+    const int64_t rows = ((int64_t)p.P + 7) / 8 * 8 * RP;
+    const int mtiles = (int)((rows + DM - 1) / DM);
+    const int64_t vtiles = (p.V + DN - 1) / DN;
+    const int64_t tiles = (int64_t)mtiles * vtiles;
+    TMB_REQUIRE(tiles < (int64_t)INT32_MAX, "glm: too many tiles");
+    TMB_REQUIRE(p.ldA >= (int64_t)mtiles * DM, "glm: ldA must cover %lld columns", (long long)mtiles * DM);
+    const size_t smem = sizeof(double) * DSTAGES * DK * DPA + sizeof(YT) * DSTAGES * DK * DPY + sizeof(uint64_t) * 2 * DSTAGES;
+    TMB_CUDA(cudaFuncSetAttribute(glm_dmma_multi_kernel<RP, YT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    glm_dmma_multi_kernel<RP, YT><<<(unsigned)tiles, 256, smem, stream>>>(p, mtiles);
+    count_launch();
+    TMB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ---------------------------------------------------------------- stacked pseudo-inverses of row-permuted designs
 // Permuting whole rows of a design permutes the columns of its pseudo-inverse (X'X is invariant), so the left operand
 // of the batched fit is a gather: At[k, p*rp + i] = pinv[i, perm_idx[p, k]].  Done here instead of on the host: the
 // host then ships only the index rows (n * 4 bytes per shuffle) and keeps ~3 ms per 512 shuffles off its critical path.
 __global__ void glm_pack_rowperm_kernel(const double *__restrict__ pinv, int r, int n, const int32_t *__restrict__ idx,
-                                        int P, int rp, double *__restrict__ At, int64_t ldA) {
+                                        int P, int rp, double *__restrict__ At, int64_t ldA, int layout) {
     const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (col >= ldA) return;
-    const int p = (int)(col / rp), i = (int)(col - (int64_t)p * rp);
+    int p, i;
+    if (layout == 0) {
+        p = (int)(col / rp); i = (int)(col - (int64_t)p * rp);
+    } else { // tile8: blocks of 8 designs x rp regressors, regressor-major inside a block
+        const int64_t blk = col / (8 * rp);
+        const int rem = (int)(col - blk * 8 * rp);
+        i = rem >> 3; p = (int)(blk * 8 + (rem & 7));
+    }
     double v = 0.0;
     if (p < P && i < r) v = pinv[(size_t)i * n + idx[(size_t)p * n + k]];
     At[(size_t)k * ldA + col] = v;
@@ -693,26 +924,169 @@ static int launch_glm_t(const GlmParams &p, cudaStream_t stream) {
     }
 }
 
+
+// ---------------------------------------------------------------- any number of regressors: statistics from stored betas
+// Designs with more than 8 non-intercept regressors (dummy-coded sites plus covariates; the reference accepts any k,
+// cynumstats.pyx:28-29,59-64) do not fit the register-resident epilogues above.  Their betas are written to HBM by the
+// plain contraction (tmb_glm_beta: every pseudo-inverse row is its own output row) and this kernel evaluates the same
+// statistics per (design, vertex) with run-time loops.  Slower (the betas make one round trip, the quadratic form is
+// O(r^2) per value) but exact and without a limit below kMaxGenericR.
+static constexpr int kMaxGenericR = 64;
+
+__device__ __forceinline__ double rq_form(const double *b, const double *__restrict__ G, int lo, int r) {
+    double q = 0.0;
+    for (int a = 0; a < r; ++a) {
+        double inner = 0.0;
+        for (int c = 0; c < r; ++c) inner = __fma_rn(__ldg(G + a * r + c), b[lo + c], inner);
+        q = __fma_rn(b[lo + a], inner, q);
+    }
+    return q;
+}
+
+__global__ void __launch_bounds__(128) glm_stats_from_beta_kernel(GlmParams p, const double *__restrict__ beta, int64_t ldb) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int perm = blockIdx.y;
+    if (v >= p.ldt) return;
+    const bool inside = v < p.V;
+    const int rt = p.mode == 2 ? p.rA + p.rB : p.r;
+    double b[kMaxGenericR];
+    for (int i = 0; i < rt; ++i) b[i] = inside ? beta[((size_t)perm * rt + i) * ldb + v] : 0.0;
+    const double yyv = inside ? p.yy[v] : 0.0;
+    if (p.mode == 0) {
+        const int r = p.r;
+        const double sse = yyv - rq_form(b, p.G + (size_t)perm * r * r, 0, r);
+        for (int a = p.row0; a < p.row0 + p.nrows; ++a) {
+            double t = t_from(b[a], sse, p.dof, p.d[(size_t)perm * r + a]);
+            if (p.nan_to_zero && t != t) t = 0.0;
+            if (!inside) t = 0.0;
+            const size_t off = ((size_t)perm * p.nrows + (a - p.row0)) * p.ldt + v;
+            if (p.t32) p.t32[off] = __double2float_rn(t);
+            if (p.t64) p.t64[off] = t;
+        }
+    } else if (p.mode == 3) {
+        const int r = p.r;
+        const double ssb = rq_form(b, p.G + (size_t)perm * r * r, 0, r);
+        const double ms = __ddiv_rn(yyv - ssb, p.dof);
+        const int first = p.row0 == 0 ? 1 : 0;
+        if (first) {
+            double f = __ddiv_rn(__ddiv_rn(ssb, (double)r), ms);
+            if (p.nan_to_zero && f != f) f = 0.0;
+            if (!inside) f = 0.0;
+            const size_t off = (size_t)perm * p.nrows * p.ldt + v;
+            if (p.t32) p.t32[off] = __double2float_rn(f);
+            if (p.t64) p.t64[off] = f;
+        }
+        const double *M = p.M + (size_t)perm * p.msz;
+        for (int i = 0; i < p.nvar; ++i) {
+            const int lo = p.var_lo[i], ki = p.var_k[i];
+            double f = __ddiv_rn(rq_form(b, M, lo, ki), __dmul_rn(ms, (double)ki));
+            if (p.nan_to_zero && f != f) f = 0.0;
+            if (!inside) f = 0.0;
+            const size_t off = ((size_t)perm * p.nrows + first + i) * p.ldt + v;
+            if (p.t32) p.t32[off] = __double2float_rn(f);
+            if (p.t64) p.t64[off] = f;
+            M += ki * ki;
+        }
+    } else {
+        const int rA = p.rA, rB = p.rB;
+        double ta;
+        if (p.ta_scalar) {
+            ta = p.ta_scalar[perm];
+        } else {
+            const double sseA = yyv - rq_form(b, p.G + (size_t)perm * rA * rA, 0, rA);
+            ta = t_from(b[p.rowA], sseA, p.dof, p.d[(size_t)perm * rA + p.rowA]);
+        }
+        const double sseB = yyv - rq_form(b, p.GB + (size_t)perm * rB * rB, rA, rB);
+        const double tb = t_from(b[rA + p.rowB], sseB, p.dofB, p.dB[(size_t)perm * rB + p.rowB]);
+        const double ta2 = __dmul_rn(ta, ta), tb2 = __dmul_rn(tb, tb);
+        double s = __dadd_rn(__ddiv_rn(1.0, tb2), __ddiv_rn(1.0, ta2));
+        const double cross = __ddiv_rn(1.0, __dmul_rn(ta2, tb2));
+        if (p.alg == 0) s = __dadd_rn(s, cross);
+        else if (p.alg == 2) s = __dsub_rn(s, cross);
+        double z = __ddiv_rn(1.0, __dsqrt_rn(s));
+        if (!inside) z = 0.0;
+        const size_t off = (size_t)perm * p.ldt + v;
+        if (p.t32) p.t32[off] = __double2float_rn(z);
+        if (p.t64) p.t64[off] = z;
+    }
+}
+
+static int launch_stats_from_beta(const GlmParams &p, const double *beta, int64_t ldb, cudaStream_t stream) {
+    const int rt = p.mode == 2 ? p.rA + p.rB : p.r;
+    TMB_REQUIRE(rt >= 1 && rt <= kMaxGenericR, "glm: at most %d non-intercept regressors per design (got %d)", kMaxGenericR, rt);
+    TMB_REQUIRE(p.P >= 1 && p.P <= 65535, "glm (stored betas): 1..65535 designs per call (got %d)", p.P);
+    const dim3 grid((unsigned)((p.ldt + 127) / 128), (unsigned)p.P);
+    glm_stats_from_beta_kernel<<<grid, 128, 0, stream>>>(p, beta, ldb);
+    count_launch();
+    TMB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// which column order of At the kernels behind launch_glm expect for (data type, padded regressors per design)
+static bool glm_uses_dmma(int y_is_f64, int rp) {
+    const char *force = getenv("TMB_GLM");
+    const bool dfma = force && strcmp(force, "dfma") == 0;
+    return !dfma && !y_is_f64 && rp >= 1 && rp <= 8;
+}
+
+// regressors per design after padding: the tensor-core kernels take any 1..8, the vector kernel 1, 2, 4 or 8
+static int glm_padded_regressors(int y_is_f64, int r) {
+    if (r < 1 || r > 8) return 0;
+    if (glm_uses_dmma(y_is_f64, r)) return r;
+    return r <= 1 ? 1 : r <= 2 ? 2 : r <= 4 ? 4 : 8;
+}
+
+// columns of At the kernels will read for P designs (a multiple of 128)
+static int64_t glm_packed_columns(int y_is_f64, int P, int rp) {
+    int64_t cols;
+    if (glm_uses_dmma(y_is_f64, rp)) {
+        const int dm = rp <= 2 ? 64 : rp <= 4 ? (rp == 3 ? 48 : 64) : 8 * rp;
+        const int64_t rows = ((int64_t)P + 7) / 8 * 8 * rp;
+        cols = (rows + dm - 1) / dm * dm;
+    } else {
+        cols = (int64_t)P * rp;
+    }
+    return (cols + BM - 1) / BM * BM;
+}
+
 int launch_glm(const GlmParams &p, cudaStream_t stream) {
     TMB_REQUIRE(p.ldy % BN == 0 && p.ldy >= (p.V + BN - 1) / BN * BN,
                 "glm: ldy must be a multiple of %d covering V rounded up", BN);
-    TMB_REQUIRE(p.ldA % BM == 0 && p.ldA >= ((int64_t)p.P * p.rp + BM - 1) / BM * BM,
-                "glm: ldA must be a multiple of %d covering P*rp rounded up", BM);
+    TMB_REQUIRE(p.ldA % BM == 0, "glm: ldA must be a multiple of %d", BM);
+    TMB_REQUIRE(p.mode == 1 || p.ldA >= glm_packed_columns(p.y_is_f64, p.P, p.rp),
+                "glm: ldA must be at least tmb_glm_packed_columns()");
     TMB_REQUIRE(p.ldt % 4 == 0 && p.ldt >= (p.V + 3) / 4 * 4, "glm: ldt must be a multiple of 4 covering V");
     TMB_REQUIRE((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.At) & 15) == 0,
                 "glm: Y and At must be 16-byte aligned");
     TMB_REQUIRE(!p.t32 || (reinterpret_cast<uintptr_t>(p.t32) & 15) == 0, "glm: t32 must be 16-byte aligned");
     {
-        // headline case (one slope per design, t-statistic): fp64 tensor cores; TMB_GLM=dfma forces the vector kernel
-        const char *force = getenv("TMB_GLM");
-        const bool dfma = force && strcmp(force, "dfma") == 0;
-        // (float32 data only: with fp64 data the doubled Y stage halves the resident CTAs and DFMA wins, measured)
-        if (!dfma && !p.y_is_f64 && p.mode == 0 && p.r == 1 && p.rp == 1 && p.row0 == 0 && p.nrows == 1) {
-            const char *ep = getenv("TMB_GLM_EPILOGUE");
-            GlmParams q = p;
-            q.exact_epilogue = ep && strcmp(ep, "exact") == 0;
-            return launch_dmma<float>(q, stream);
+        // float32 data: fp64 tensor cores (TMB_GLM=dfma forces the vector kernel).  One slope per design and the
+        // t-statistic (the headline case) has its own kernel with the cheap fp32-seeded epilogue; everything else --
+        // several regressors, partial F, Sobel z -- runs on glm_dmma_multi_kernel.
+        // (float64 data: the doubled Y stage halves the resident CTAs and DFMA wins, measured in round 1.)
+        if (glm_uses_dmma(p.y_is_f64, p.rp) && p.mode != 1) {
+            TMB_REQUIRE(p.layout == 1 || p.rp == 1, "glm: the DMMA kernels need the tile8 column order of At (tmb_glm_layout)");
+            TMB_REQUIRE(p.ldA >= glm_packed_columns(p.y_is_f64, p.P, p.rp), "glm: ldA must be at least tmb_glm_packed_columns() = %lld",
+                        (long long)glm_packed_columns(p.y_is_f64, p.P, p.rp));
+            if (p.mode == 0 && p.r == 1 && p.rp == 1 && p.row0 == 0 && p.nrows == 1) {
+                const char *ep = getenv("TMB_GLM_EPILOGUE");
+                GlmParams q = p;
+                q.exact_epilogue = ep && strcmp(ep, "exact") == 0;
+                return launch_dmma<float>(q, stream);
+            }
+            switch (p.rp) {
+            case 1: return launch_dmma_multi<1, float>(p, stream);
+            case 2: return launch_dmma_multi<2, float>(p, stream);
+            case 3: return launch_dmma_multi<3, float>(p, stream);
+            case 4: return launch_dmma_multi<4, float>(p, stream);
+            case 5: return launch_dmma_multi<5, float>(p, stream);
+            case 6: return launch_dmma_multi<6, float>(p, stream);
+            case 7: return launch_dmma_multi<7, float>(p, stream);
+            case 8: return launch_dmma_multi<8, float>(p, stream);
+            default: break;
+            }
         }
+        TMB_REQUIRE(p.layout == 0 || p.rp == 1, "glm: the DFMA tile kernel needs the plain column order of At (tmb_glm_layout)");
     }
     return p.y_is_f64 ? launch_glm_t<double>(p, stream) : launch_glm_t<float>(p, stream);
 }
@@ -751,7 +1125,7 @@ extern "C" int tmb_glm_sumsq(const void *Y_dev, int ydtype, int n, int64_t V, in
 extern "C" int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev,
                              int64_t ldA, const double *G_dev, const double *d_dev, int P, int r, int rp, int row0,
                              int nrows, double dof, const double *yy_dev, float *t32_dev, double *t64_dev,
-                             int64_t ldt, int nan_to_zero, void *stream) {
+                             int64_t ldt, int nan_to_zero, int layout, void *stream) {
     TMB_REQUIRE(Y_dev && At_dev && G_dev && d_dev && yy_dev && (t32_dev || t64_dev), "tmb_glm_tstat: null pointer");
     TMB_REQUIRE(n > 0 && V > 0 && P > 0 && r >= 1 && r <= rp && row0 >= 0 && nrows >= 1 && row0 + nrows <= r,
                 "tmb_glm_tstat: bad shape (n=%d V=%lld P=%d r=%d rp=%d row0=%d nrows=%d)", n, (long long)V, P, r, rp,
@@ -761,7 +1135,7 @@ extern "C" int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, in
     if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
     p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.G = G_dev; p.d = d_dev;
     p.P = P; p.r = r; p.rp = rp; p.row0 = row0; p.nrows = nrows; p.dof = dof; p.yy = yy_dev;
-    p.t32 = t32_dev; p.t64 = t64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 0;
+    p.t32 = t32_dev; p.t64 = t64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 0; p.layout = layout;
     return launch_glm(p, (cudaStream_t)stream);
 }
 
@@ -769,7 +1143,7 @@ extern "C" int tmb_glm_fstat(const void *Y_dev, int ydtype, int n, int64_t V, in
                              int64_t ldA, const double *G_dev, const double *M_dev, int P, int r, int rp, int nvar,
                              const int32_t *var_lo, const int32_t *var_k, int want_model, double dof,
                              const double *yy_dev, float *f32_dev, double *f64_dev, int64_t ldt, int nan_to_zero,
-                             void *stream) {
+                             int layout, void *stream) {
     TMB_REQUIRE(Y_dev && At_dev && G_dev && yy_dev && (f32_dev || f64_dev), "tmb_glm_fstat: null pointer");
     TMB_REQUIRE(n > 0 && V > 0 && P > 0 && r >= 1 && r <= rp && nvar >= 0 && nvar <= 8 && (nvar == 0 || (M_dev && var_lo && var_k)) &&
                     (nvar > 0 || want_model),
@@ -779,7 +1153,7 @@ extern "C" int tmb_glm_fstat(const void *Y_dev, int ydtype, int n, int64_t V, in
     if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
     p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.G = G_dev; p.M = M_dev;
     p.P = P; p.r = r; p.rp = rp; p.row0 = want_model ? 0 : 1; p.nrows = nvar + (want_model ? 1 : 0); p.dof = dof; p.yy = yy_dev;
-    p.t32 = f32_dev; p.t64 = f64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 3; p.nvar = nvar;
+    p.t32 = f32_dev; p.t64 = f64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 3; p.nvar = nvar; p.layout = layout;
     for (int i = 0; i < nvar; ++i) {
         TMB_REQUIRE(var_lo[i] >= 0 && var_k[i] >= 1 && var_lo[i] + var_k[i] <= r,
                     "tmb_glm_fstat: variable %d covers rows [%d, %d) of %d", i, var_lo[i], var_lo[i] + var_k[i], r);
@@ -788,14 +1162,25 @@ extern "C" int tmb_glm_fstat(const void *Y_dev, int ydtype, int n, int64_t V, in
     return launch_glm(p, (cudaStream_t)stream);
 }
 
+extern "C" int tmb_glm_layout(int ydtype, int rp) {
+    return glm_uses_dmma(ydtype == TMB_F64, rp) ? 1 : 0;
+}
+
+extern "C" int tmb_glm_rp(int ydtype, int r) { return glm_padded_regressors(ydtype == TMB_F64, r); }
+
+extern "C" int64_t tmb_glm_packed_columns(int ydtype, int P, int rp) {
+    return glm_packed_columns(ydtype == TMB_F64, P, rp);
+}
+
 extern "C" int tmb_glm_pack_rowperm(const double *pinv_dev, int r, int n, const int32_t *perm_idx_dev, int P, int rp,
-                                    double *At_dev, int64_t ldA, void *stream) {
+                                    double *At_dev, int64_t ldA, int layout, void *stream) {
     TMB_REQUIRE(pinv_dev && perm_idx_dev && At_dev, "tmb_glm_pack_rowperm: null pointer");
-    TMB_REQUIRE(r >= 1 && r <= rp && n > 0 && P > 0 && ldA >= (int64_t)P * rp && n <= 65535,
+    TMB_REQUIRE(r >= 1 && r <= rp && rp <= 8 && n > 0 && P > 0 && n <= 65535 && (layout == 0 || layout == 1) &&
+                    ldA >= (layout ? ((int64_t)P + 7) / 8 * 8 * rp : (int64_t)P * rp),
                 "tmb_glm_pack_rowperm: bad shape (r=%d rp=%d n=%d P=%d ldA=%lld)", r, rp, n, P, (long long)ldA);
     TMB_DEVICE_OF(pinv_dev, "tmb_glm_pack_rowperm");
     const dim3 grid((unsigned)((ldA + 255) / 256), (unsigned)n);
-    glm_pack_rowperm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pinv_dev, r, n, perm_idx_dev, P, rp, At_dev, ldA);
+    glm_pack_rowperm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pinv_dev, r, n, perm_idx_dev, P, rp, At_dev, ldA, layout);
     count_launch();
     TMB_CUDA(cudaGetLastError());
     return 0;
@@ -850,7 +1235,7 @@ extern "C" int tmb_sobelz(const void *Y_dev, int ydtype, int n, int64_t V, int64
                           int64_t ldA, int rp, const double *GA_dev, const double *dA_dev, int rA, int rowA,
                           double dofA, const double *GB_dev, const double *dB_dev, int rB, int rowB, double dofB,
                           const double *yy_dev, const double *ta_scalar_dev, int P, int alg, float *z32_dev,
-                          double *z64_dev, int64_t ldt, void *stream) {
+                          double *z64_dev, int64_t ldt, int layout, void *stream) {
     TMB_REQUIRE(Y_dev && At_dev && GB_dev && dB_dev && yy_dev && (z32_dev || z64_dev), "tmb_sobelz: null pointer");
     TMB_REQUIRE(rA >= 0 && rB >= 1 && rA + rB <= rp && rowB >= 0 && rowB < rB &&
                     (ta_scalar_dev || (rA >= 1 && rowA >= 0 && rowA < rA && GA_dev && dA_dev)),
@@ -862,6 +1247,55 @@ extern "C" int tmb_sobelz(const void *Y_dev, int ydtype, int n, int64_t V, int64
     p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.G = GA_dev; p.d = dA_dev;
     p.P = P; p.r = rA + rB; p.rp = rp; p.dof = dofA; p.yy = yy_dev; p.t32 = z32_dev; p.t64 = z64_dev; p.ldt = ldt;
     p.mode = 2; p.GB = GB_dev; p.dB = dB_dev; p.rA = rA; p.rB = rB; p.rowA = rowA; p.rowB = rowB; p.dofB = dofB;
-    p.ta_scalar = ta_scalar_dev; p.alg = alg;
+    p.ta_scalar = ta_scalar_dev; p.alg = alg; p.layout = layout;
     return launch_glm(p, (cudaStream_t)stream);
+}
+
+// ---- statistics from stored betas (designs with more than 8 regressors; see glm_stats_from_beta_kernel) ----------
+extern "C" int tmb_glm_tstat_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *G_dev, const double *d_dev,
+                                  int P, int r, int row0, int nrows, double dof, const double *yy_dev, float *t32_dev,
+                                  double *t64_dev, int64_t ldt, int nan_to_zero, void *stream) {
+    TMB_REQUIRE(beta_dev && G_dev && d_dev && yy_dev && (t32_dev || t64_dev), "tmb_glm_tstat_beta: null pointer");
+    TMB_REQUIRE(V > 0 && P > 0 && r >= 1 && row0 >= 0 && nrows >= 1 && row0 + nrows <= r && ldb >= V && ldt >= V,
+                "tmb_glm_tstat_beta: bad shape");
+    TMB_DEVICE_OF(beta_dev, "tmb_glm_tstat_beta");
+    GlmParams p{};
+    p.V = V; p.G = G_dev; p.d = d_dev; p.P = P; p.r = r; p.row0 = row0; p.nrows = nrows; p.dof = dof; p.yy = yy_dev;
+    p.t32 = t32_dev; p.t64 = t64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 0;
+    return launch_stats_from_beta(p, beta_dev, ldb, (cudaStream_t)stream);
+}
+
+extern "C" int tmb_glm_fstat_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *G_dev, const double *M_dev,
+                                  int P, int r, int nvar, const int32_t *var_lo, const int32_t *var_k, int want_model,
+                                  double dof, const double *yy_dev, float *f32_dev, double *f64_dev, int64_t ldt,
+                                  int nan_to_zero, void *stream) {
+    TMB_REQUIRE(beta_dev && G_dev && yy_dev && (f32_dev || f64_dev), "tmb_glm_fstat_beta: null pointer");
+    TMB_REQUIRE(V > 0 && P > 0 && r >= 1 && nvar >= 0 && nvar <= 8 && (nvar == 0 || (M_dev && var_lo && var_k)) &&
+                    (nvar > 0 || want_model) && ldb >= V && ldt >= V, "tmb_glm_fstat_beta: bad shape");
+    TMB_DEVICE_OF(beta_dev, "tmb_glm_fstat_beta");
+    GlmParams p{};
+    p.V = V; p.G = G_dev; p.M = M_dev; p.P = P; p.r = r; p.row0 = want_model ? 0 : 1; p.nrows = nvar + (want_model ? 1 : 0);
+    p.dof = dof; p.yy = yy_dev; p.t32 = f32_dev; p.t64 = f64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 3; p.nvar = nvar;
+    for (int i = 0; i < nvar; ++i) {
+        TMB_REQUIRE(var_lo[i] >= 0 && var_k[i] >= 1 && var_lo[i] + var_k[i] <= r,
+                    "tmb_glm_fstat_beta: variable %d covers rows [%d, %d) of %d", i, var_lo[i], var_lo[i] + var_k[i], r);
+        p.var_lo[i] = var_lo[i]; p.var_k[i] = var_k[i]; p.msz += var_k[i] * var_k[i];
+    }
+    return launch_stats_from_beta(p, beta_dev, ldb, (cudaStream_t)stream);
+}
+
+extern "C" int tmb_sobelz_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *GA_dev, const double *dA_dev,
+                               int rA, int rowA, double dofA, const double *GB_dev, const double *dB_dev, int rB, int rowB,
+                               double dofB, const double *yy_dev, const double *ta_scalar_dev, int P, int alg,
+                               float *z32_dev, double *z64_dev, int64_t ldt, void *stream) {
+    TMB_REQUIRE(beta_dev && GB_dev && dB_dev && yy_dev && (z32_dev || z64_dev), "tmb_sobelz_beta: null pointer");
+    TMB_REQUIRE(rA >= 0 && rB >= 1 && rowB >= 0 && rowB < rB && ldb >= V && ldt >= V &&
+                    (ta_scalar_dev || (rA >= 1 && rowA >= 0 && rowA < rA && GA_dev && dA_dev)), "tmb_sobelz_beta: bad shape");
+    TMB_REQUIRE(alg >= 0 && alg <= 2, "tmb_sobelz_beta: alg must be 0 (aroian), 1 (sobel) or 2 (goodman)");
+    TMB_DEVICE_OF(beta_dev, "tmb_sobelz_beta");
+    GlmParams p{};
+    p.V = V; p.G = GA_dev; p.d = dA_dev; p.P = P; p.r = rA + rB; p.dof = dofA; p.yy = yy_dev; p.t32 = z32_dev; p.t64 = z64_dev;
+    p.ldt = ldt; p.mode = 2; p.GB = GB_dev; p.dB = dB_dev; p.rA = rA; p.rB = rB; p.rowA = rowA; p.rowB = rowB; p.dofB = dofB;
+    p.ta_scalar = ta_scalar_dev; p.alg = alg;
+    return launch_stats_from_beta(p, beta_dev, ldb, (cudaStream_t)stream);
 }

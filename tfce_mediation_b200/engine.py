@@ -22,11 +22,7 @@ from .tfce import CreateAdjSet
 _E2E_DEBUG = bool(_os.environ.get("TMB_E2E_DEBUG"))   # per-block host timings of the exact-libm round trip on stderr
 
 
-def _rp_for(r):
-    for rp in (1, 2, 4, 8):
-        if r <= rp:
-            return rp
-    raise ValueError("the batched fit supports at most 8 non-intercept regressors per design (got %d)" % r)
+MAX_REGRESSORS = 64       # non-intercept regressors per design (more than 8 take the stored-beta path, tmb_glm_*_beta)
 
 
 class Surface(object):
@@ -244,17 +240,62 @@ def row_permuted_stack(X, perm_idx, center=True):
                 d=np.repeat(base["d"], P, axis=0), r=r, dof=base["dof"], centered=bool(center))
 
 
-def pack_At(pinv, rp):
-    """[P, r, n] pseudo-inverse rows -> At float64 [n, ldA] with column p*rp + i = row i of design p."""
+def pack_At(pinv, rp, layout=0, ldA=None):
+    """[P, r, n] pseudo-inverse rows -> At float64 [n, ldA]; row i of design p goes to column p*rp + i (layout 0, the
+    fp64 vector kernel) or (p // 8)*8*rp + i*8 + p % 8 (layout 1, "tile8", the tensor-core kernels: include/tfce_b200.h).
+    ldA: columns the kernel will read (tmb_glm_packed_columns); default: the packed columns rounded up to 128."""
     P, r, n = pinv.shape
-    ldA = round_up(P * rp, TILE_M)
+    if ldA is None:
+        ldA = round_up(P * rp if layout == 0 else (P + 7) // 8 * 8 * rp, TILE_M)
     At = np.zeros((n, ldA), dtype=np.float64)
-    At[:, :P * rp].reshape(n, P, rp)[:, :, :r] = pinv.transpose(2, 0, 1)
+    if layout == 0:
+        At[:, :P * rp].reshape(n, P, rp)[:, :, :r] = pinv.transpose(2, 0, 1)
+    else:
+        P8 = (P + 7) // 8 * 8
+        blk = np.zeros((n, P8, rp), dtype=np.float64)
+        blk[:, :P, :r] = pinv.transpose(2, 0, 1)
+        # [n, P8/8, 8 (q), rp (i)] -> [n, P8/8, rp (i), 8 (q)]
+        At[:, :P8 * rp] = blk.reshape(n, P8 // 8, 8, rp).transpose(0, 1, 3, 2).reshape(n, P8 * rp)
     return At, ldA
 
 
 class PermutationEngine(object):
     """Data resident in HBM + a TFCE plan; runs blocks of shuffles."""
+
+    def _layout(self, rp):
+        """Column order of the stacked pseudo-inverses the fit kernels expect for this data type (tmb_glm_layout)."""
+        return int(_lib.lib().tmb_glm_layout(self.Y.dtype_code, int(rp)))
+
+    def _rp(self, r):
+        """Padded regressors per design for the fused kernels (tmb_glm_rp); 0: more than 8 -> stored-beta path."""
+        if r > MAX_REGRESSORS:
+            raise ValueError("at most %d non-intercept regressors per design (got %d)" % (MAX_REGRESSORS, r))
+        return int(_lib.lib().tmb_glm_rp(self.Y.dtype_code, int(r)))
+
+    def _pack(self, pinv, rp):
+        """(At device tensor, ldA, layout) for a stack of pseudo-inverse rows [P, r, n]."""
+        layout = self._layout(rp)
+        ldA = int(_lib.lib().tmb_glm_packed_columns(self.Y.dtype_code, int(pinv.shape[0]), int(rp)))
+        At, ldA = pack_At(pinv, rp, layout, ldA)
+        return At, ldA, layout
+
+    def _betas_chunks(self, pinv, budget=1.5e9):
+        """Stored-beta path (r > 8): yields (first design, designs, beta64 [designs * r, ld]) chunk by chunk; every
+        pseudo-inverse row is one column of the left operand and one output row of the plain contraction."""
+        import torch
+        P, r, n = pinv.shape
+        per = max(1, int(budget // (r * self.Y.ld * 8)))
+        for a in range(0, P, per):
+            b = min(P, a + per)
+            rows = (b - a) * r
+            ldA = round_up(rows, TILE_M)
+            At = np.zeros((n, ldA), dtype=np.float64)
+            At[:, :rows] = pinv[a:b].reshape(rows, n).T
+            At_d = self._upload("beta_At", At)
+            beta = torch.empty((rows, self.Y.ld), dtype=torch.float64, device=self.device)
+            _lib.check(_lib.lib().tmb_glm_beta(_lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld,
+                                               _lib.ptr(At_d), ldA, rows, _lib.ptr(beta), self.Y.ld, _lib.current_stream()))
+            yield a, b - a, beta
 
     def __init__(self, data, surfaces, two_sided=True, nan_to_zero=False, device=None, max_slots=0,
                  permute_columns=True):
@@ -344,20 +385,28 @@ class PermutationEngine(object):
         P, r, n = stack["pinv"].shape
         if n != self.Y.n:
             raise ValueError("design has %d subjects, data has %d" % (n, self.Y.n))
-        rp = _rp_for(r)
+        rp = self._rp(r)
         row0, nrows = (0, r) if rows is None else (int(rows[0]), int(rows[1]))
-        At, ldA = pack_At(stack["pinv"], rp)
-        At_d = self._upload("At", At)
         G_d = self._upload("G", stack["G"])
         d_d = self._upload("d", stack["d"])
         centered = stack.get("centered", True)
         yy = self.Y.sumsq(centered)
         t32 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float32, device=self.device)
         t64 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
-        _lib.check(_lib.lib().tmb_glm_tstat(
-            _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA,
-            _lib.ptr(G_d), _lib.ptr(d_d), P, r, rp, row0, nrows, stack["dof"], _lib.ptr(yy), _lib.ptr(t32),
-            _lib.ptr(t64), self.Y.ld, 1 if self.nan_to_zero else 0, _lib.current_stream()))
+        if rp == 0:
+            for a, cnt, beta in self._betas_chunks(stack["pinv"]):
+                _lib.check(_lib.lib().tmb_glm_tstat_beta(
+                    _lib.ptr(beta), self.Y.ld, self.Y.V, _lib.ptr(G_d[a:a + cnt]), _lib.ptr(d_d[a:a + cnt]), cnt, r, row0,
+                    nrows, stack["dof"], _lib.ptr(yy), _lib.ptr(t32[a:a + cnt]),
+                    _lib.ptr(t64[a:a + cnt]) if t64 is not None else None, self.Y.ld, 1 if self.nan_to_zero else 0,
+                    _lib.current_stream()))
+        else:
+            At, ldA, layout = self._pack(stack["pinv"], rp)
+            At_d = self._upload("At", At)
+            _lib.check(_lib.lib().tmb_glm_tstat(
+                _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA,
+                _lib.ptr(G_d), _lib.ptr(d_d), P, r, rp, row0, nrows, stack["dof"], _lib.ptr(yy), _lib.ptr(t32),
+                _lib.ptr(t64), self.Y.ld, 1 if self.nan_to_zero else 0, layout, _lib.current_stream()))
         if caller_order and self.colperm is not None:
             t32 = self.to_caller_order(t32)
             t64 = self.to_caller_order(t64) if t64 is not None else None
@@ -378,7 +427,7 @@ class PermutationEngine(object):
         if base is None:
             st = design_stack(X[None], center=True)
             r = st["r"]
-            base = dict(r=r, rp=_rp_for(r), dof=st["dof"], G=st["G"][0], d=st["d"][0],
+            base = dict(r=r, rp=self._rp(r), dof=st["dof"], G=st["G"][0], d=st["d"][0],
                         pinv=torch.from_numpy(np.ascontiguousarray(st["pinv"][0])).to(self.device), rep={}, fmat={})
             self._rowperm_base = {key: base}            # one design at a time (the drivers' loop)
         r, rp = base["r"], base["rp"]
@@ -389,10 +438,11 @@ class PermutationEngine(object):
             base["rep"] = {P: rep}
             base["fmat"] = {}
         idx_d = self._upload("perm_idx", np.ascontiguousarray(perm_idx, dtype=np.int32))
-        ldA = round_up(P * rp, TILE_M)
+        layout = base["layout"] = self._layout(rp)
+        ldA = int(_lib.lib().tmb_glm_packed_columns(self.Y.dtype_code, P, rp))
         At_d = self._ring("At", (n, ldA), torch.float64)
         _lib.check(_lib.lib().tmb_glm_pack_rowperm(_lib.ptr(base["pinv"]), r, n, _lib.ptr(idx_d), P, rp, _lib.ptr(At_d),
-                                                   ldA, _lib.current_stream()))
+                                                   ldA, layout, _lib.current_stream()))
         return base, rep, At_d, ldA, P
 
     def tstat_rowperm(self, X, perm_idx, rows=None):
@@ -400,6 +450,8 @@ class PermutationEngine(object):
         column 0; rows = (first, count) selects regressors (default: all k-1).  Returns CUDA float32 [P, count, ld] in
         the engine's internal column order."""
         import torch
+        if np.asarray(X).shape[1] - 1 > 8:       # stored-beta path: host-built stack (k x k algebra only)
+            return self.tstat(row_permuted_stack(X, perm_idx), rows=rows, caller_order=False)
         base, rep, At_d, ldA, P = self._rowperm_operands(X, perm_idx)
         r, rp = base["r"], base["rp"]
         row0, nrows = (0, r) if rows is None else (int(rows[0]), int(rows[1]))
@@ -408,7 +460,7 @@ class PermutationEngine(object):
         _lib.check(_lib.lib().tmb_glm_tstat(
             _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA,
             _lib.ptr(rep[0]), _lib.ptr(rep[1]), P, r, rp, row0, nrows, base["dof"], _lib.ptr(yy), _lib.ptr(t32),
-            None, self.Y.ld, 1 if self.nan_to_zero else 0, _lib.current_stream()))
+            None, self.Y.ld, 1 if self.nan_to_zero else 0, base["layout"], _lib.current_stream()))
         return t32
 
     # -- F statistics (tm-models GLM branch) -------------------------------------------------------
@@ -420,17 +472,34 @@ class PermutationEngine(object):
         P, r, n = stack["pinv"].shape
         if n != self.Y.n:
             raise ValueError("design has %d subjects, data has %d" % (n, self.Y.n))
-        rp = _rp_for(r)
-        At, ldA = pack_At(stack["pinv"], rp)
-        At_d = self._upload("At", At)
+        rp = self._rp(r)
         G_d = self._upload("G", stack["G"])
         M_d = self._upload("M", fstat_blocks(stack["G"], var_lo, var_k))
-        out = self._fstat_launch(At_d, ldA, G_d, M_d, P, r, rp, var_lo, var_k, want_model, stack["dof"], want_f64)
+        if rp == 0:
+            nvar = len(var_lo)
+            nrows = nvar + (1 if want_model else 0)
+            lo = np.ascontiguousarray(var_lo, dtype=np.int32)
+            kk = np.ascontiguousarray(var_k, dtype=np.int32)
+            yy = self.Y.sumsq(True)
+            f32 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float32, device=self.device)
+            f64 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
+            for a, cnt, beta in self._betas_chunks(stack["pinv"]):
+                _lib.check(_lib.lib().tmb_glm_fstat_beta(
+                    _lib.ptr(beta), self.Y.ld, self.Y.V, _lib.ptr(G_d[a:a + cnt]), _lib.ptr(M_d[a:a + cnt]), cnt, r, nvar,
+                    lo.ctypes.data, kk.ctypes.data, 1 if want_model else 0, stack["dof"], _lib.ptr(yy),
+                    _lib.ptr(f32[a:a + cnt]), _lib.ptr(f64[a:a + cnt]) if f64 is not None else None, self.Y.ld,
+                    1 if self.nan_to_zero else 0, _lib.current_stream()))
+            out = (f32, f64)
+        else:
+            At, ldA, layout = self._pack(stack["pinv"], rp)
+            At_d = self._upload("At", At)
+            out = self._fstat_launch(At_d, ldA, G_d, M_d, P, r, rp, var_lo, var_k, want_model, stack["dof"], want_f64,
+                                     layout=layout)
         if caller_order and self.colperm is not None:
             out = tuple(self.to_caller_order(o) if o is not None else None for o in out)
         return out if want_f64 else out[0]
 
-    def _fstat_launch(self, At_d, ldA, G_d, M_d, P, r, rp, var_lo, var_k, want_model, dof, want_f64=False):
+    def _fstat_launch(self, At_d, ldA, G_d, M_d, P, r, rp, var_lo, var_k, want_model, dof, want_f64=False, layout=0):
         import torch
         nvar = len(var_lo)
         nrows = nvar + (1 if want_model else 0)
@@ -442,13 +511,15 @@ class PermutationEngine(object):
         _lib.check(_lib.lib().tmb_glm_fstat(
             _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA, _lib.ptr(G_d),
             _lib.ptr(M_d), P, r, rp, nvar, lo.ctypes.data, kk.ctypes.data, 1 if want_model else 0, dof, _lib.ptr(yy),
-            _lib.ptr(f32), _lib.ptr(f64), self.Y.ld, 1 if self.nan_to_zero else 0, _lib.current_stream()))
+            _lib.ptr(f32), _lib.ptr(f64), self.Y.ld, 1 if self.nan_to_zero else 0, layout, _lib.current_stream()))
         return f32, f64
 
     def fstat_rowperm(self, X, var_lo, var_k, perm_idx, want_model=False):
         """fstat for the designs X[perm_idx[p]] (glm_typeI's `exog_vars[rand_array]`, pyfunc.py:2317-2321): only the
         index rows travel; X'X, and with it every variable's inverse block, is the same for all permutations."""
         import torch
+        if np.asarray(X).shape[1] - 1 > 8:       # stored-beta path
+            return self.fstat(row_permuted_stack(X, perm_idx), var_lo, var_k, want_model=want_model, caller_order=False)
         base, rep, At_d, ldA, P = self._rowperm_operands(X, perm_idx)
         key = (tuple(int(a) for a in var_lo), tuple(int(a) for a in var_k), P)
         M_d = base["fmat"].get(key)
@@ -457,7 +528,7 @@ class PermutationEngine(object):
             M_d = torch.from_numpy(np.repeat(M1, P, axis=0)).to(self.device)
             base["fmat"] = {key: M_d}
         return self._fstat_launch(At_d, ldA, rep[0], M_d, P, base["r"], base["rp"], var_lo, var_k, want_model,
-                                  base["dof"])[0]
+                                  base["dof"], layout=base["layout"])[0]
 
     def glm_typeI_block(self, exog_vars, kvars, perm_idx, stat="f", download=True):
         """One block of the tm-models GLM permutation loop (tmanalysis/tm_models_randomise.py:197-272): per shuffle the
@@ -639,8 +710,11 @@ class PermutationEngine(object):
             sA, rA = None, 0
             pinv = sB["pinv"]
         rB = sB["r"]
-        rp = _rp_for(rA + rB)
-        At, ldA = pack_At(pinv, rp)
+        rp = self._rp(rA + rB)
+        if rp == 0:
+            At, ldA, layout = None, 0, 0
+        else:
+            At, ldA, layout = self._pack(pinv, rp)
         algc = {"aroian": 0, "sobel": 1, "goodman": 2}.get(alg)
         if algc is None:
             raise ValueError("Unknown indirect test algorithm")
@@ -648,8 +722,8 @@ class PermutationEngine(object):
             up = lambda name, a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)   # noqa: E731
         else:
             up = self._upload
-        return dict(P=P, rp=rp, ldA=ldA, rA=rA, rB=rB, alg=algc,
-                    At=up("med_At", At), GA=up("med_GA", sA["G"]) if sA else None,
+        return dict(P=P, rp=rp, ldA=ldA, rA=rA, rB=rB, alg=algc, layout=layout, pinv=pinv if rp == 0 else None,
+                    At=up("med_At", At) if At is not None else None, GA=up("med_GA", sA["G"]) if sA else None,
                     dA=up("med_dA", sA["d"]) if sA else None, GB=up("med_GB", sB["G"]), dB=up("med_dB", sB["d"]),
                     ta=up("med_ta", ta_scalar) if ta_scalar is not None else None,
                     dofA=sA["dof"] if sA else 1.0, dofB=sB["dof"])
@@ -661,11 +735,20 @@ class PermutationEngine(object):
         yy = self.Y.sumsq(True)
         z32 = out if out is not None else torch.empty((P, self.Y.ld), dtype=torch.float32, device=self.device)
         z64 = torch.empty((P, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
+        if ops["rp"] == 0:                      # more than 8 regressors over both paths: stored-beta path
+            sl = lambda t, a, c: _lib.ptr(t[a:a + c]) if t is not None else None   # noqa: E731
+            for a, cnt, beta in self._betas_chunks(ops["pinv"]):
+                _lib.check(_lib.lib().tmb_sobelz_beta(
+                    _lib.ptr(beta), self.Y.ld, self.Y.V, sl(ops["GA"], a, cnt), sl(ops["dA"], a, cnt), ops["rA"], 0,
+                    ops["dofA"], sl(ops["GB"], a, cnt), sl(ops["dB"], a, cnt), ops["rB"], 0, ops["dofB"], _lib.ptr(yy),
+                    sl(ops["ta"], a, cnt), cnt, ops["alg"], _lib.ptr(z32[a:a + cnt]), sl(z64, a, cnt), self.Y.ld,
+                    _lib.current_stream()))
+            return z32, z64
         _lib.check(_lib.lib().tmb_sobelz(
             _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(ops["At"]), ops["ldA"],
             ops["rp"], _lib.ptr(ops["GA"]), _lib.ptr(ops["dA"]), ops["rA"], 0, ops["dofA"], _lib.ptr(ops["GB"]),
             _lib.ptr(ops["dB"]), ops["rB"], 0, ops["dofB"], _lib.ptr(yy), _lib.ptr(ops["ta"]), P, ops["alg"],
-            _lib.ptr(z32), _lib.ptr(z64), self.Y.ld, _lib.current_stream()))
+            _lib.ptr(z32), _lib.ptr(z64), self.Y.ld, ops["layout"], _lib.current_stream()))
         return z32, z64
 
     def tm_models_mediation_block(self, medtype, leftvar, rightvar, dmy_covariates, perm_idx, alg="aroian", download=True):
@@ -710,6 +793,38 @@ class PermutationEngine(object):
         self.last_status = status
         mx = mx[:, :, 0]
         return self._download(mx.contiguous()) if download else mx
+
+    def mediation_blocks(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", block=256):
+        """Many mediation shuffles, `block` at a time, software-pipelined like regression_blocks: while block i is swept
+        the host builds block i+1's designs (k x k algebra per shuffle: only pred_x is permuted, so X'X changes) and its
+        fit is already queued.  Returns float32 [N, S] on the host."""
+        import torch
+        perm_idx = np.asarray(perm_idx)
+        N = perm_idx.shape[0]
+        chunks = [(a, min(N, a + block)) for a in range(0, N, block)]
+        host = torch.empty((N, self.plan.S, 2), dtype=torch.float32).pin_memory()
+
+        def stage1(a, b):
+            XA, XB, ta = self.mediation_designs(medtype, pred_x, depend_y, perm_idx[a:b])
+            ops = self.sobelz_operands(XA, XB, ta, alg)
+            z32 = self._ring("z32", (b - a, self.Y.ld), torch.float32)
+            self.sobelz_launch(ops, out=z32)
+            return z32, (self.plan.prepare(z32) if self.plan.exact_pow else None), ops
+
+        nxt = stage1(*chunks[0]) if chunks else None
+        for ci, (a, b) in enumerate(chunks):
+            cur = nxt
+            nxt = stage1(*chunks[ci + 1]) if ci + 1 < len(chunks) else None
+            z32, tk, _ = cur
+            if tk is not None:
+                mx, status, _ = self.plan.finish(tk, z32, two_sided=False)
+            else:
+                mx, status, _ = self.plan.run(z32, two_sided=False, exact_pow=False)
+            host[a:b].copy_(mx, non_blocking=True)
+            self.d2h_bytes += (b - a) * self.plan.S * 2 * 4
+        torch.cuda.current_stream().synchronize()
+        self.last_status = None
+        return host.numpy()[:, :, 0].copy()
 
     def mediation_block(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", want_maps=False, download=True):
         """Sobel-z + one-sided TFCE + scaled max for a block of shuffles
