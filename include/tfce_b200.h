@@ -78,7 +78,10 @@ int tmb_tfce_components(tmb_graph *g, const float *image_host, int level, int32_
  * Plan: S graphs ("surfaces": lh/rh hemispheres, a voxel skeleton, mmr surfaces) laid along one
  * statistic row; surface s covers columns [col_offset[s], col_offset[s] + V_s).
  * weight_host[s] is NULL (weight 1) or V_s floats (vertex-density correction, vdensity_?h of
- * STEP_1_vertex_tfce_multiple_regression.py:161-173).  max_slots bounds how many maps are in
+ * STEP_1_vertex_tfce_multiple_regression.py:161-173; float32 there and in mmr-lr, tm_mmr_rand_low_ram.py:165).
+ * weight64_host (may be NULL) / weight64_host[s]: V_s DOUBLES instead -- the non-low-RAM mmr path builds its density
+ * weights in float64 (tm_multimodality_multisurface_regression.py:451-459) and the reference then multiplies in
+ * double: fl32(double(fl32(tfce * scale)) * w), tm_func.py:83-91.  max_slots bounds how many maps are in
  * flight at once (workspace is max_slots * O(V_max)); 0 = library default.
  *
  * tmb_plan_run == the body of pyfunc.py:107-126 write_perm_maxTFCE_vertex / _voxel and of
@@ -89,7 +92,8 @@ int tmb_tfce_components(tmb_graph *g, const float *image_host, int level, int32_
  * TFCE maps, rows of leading dimension ld like stat_dev.  status_dev (may be NULL): int32 [B*S*2].
  * ------------------------------------------------------------------------------------------- */
 int tmb_plan_create(int device, int S, tmb_graph *const *graphs, const int64_t *col_offset,
-                    const float *const *weight_host, int max_slots, tmb_plan **out);
+                    const float *const *weight_host, const double *const *weight64_host, int max_slots,
+                    tmb_plan **out);
 int tmb_plan_destroy(tmb_plan *p);
 /* Opt-in fast path of the batched engine: declare that statistic rows (and requested TFCE maps) use the
  * graphs' INTERNAL vertex order (tmb_graph_vmap), e.g. because the data columns were permuted once at
@@ -106,14 +110,19 @@ int tmb_plan_run(tmb_plan *p, const float *stat_dev, int64_t ld, int B, int two_
  *                          (T_0 = max, T_{i+1} = T_i - max/100 while T_i >= 0, fast_tfce.hpp:32-39) and
  *                          HH_i = powf(T_i, H) into rows of 128 floats, plus step count, delta and TMB_MAP_* status
  *   tmb_plan_run_tables:   tmb_plan_run consuming those tables (device copies) instead of computing
- *                          correctly rounded ones on the device.
+ *                          correctly rounded ones on the device.  scale_dev (may be NULL): float32 [B*S*2], the factor of
+ *                          the scaled maximum per entry when it is not the threshold step delta -- the non-low-RAM mmr
+ *                          path thresholds ONE merged graph, i.e. delta = (maximum over all surfaces) / 100
+ *                          (fast_tfce.hpp:32-36 on tm_func.py:77-78's merged image), but rescales every surface with
+ *                          its own max/100 (tm_func.py:83-91): tables from the group maximum, scale from the surface's.
  * tmb_tfce_run and tmb_tfce_components always use host tables (they have the host image anyway). */
 int tmb_plan_maxima(tmb_plan *p, const float *stat_dev, int64_t ld, int B, float *max_dev, void *stream);
 int tmb_threshold_tables(const float *maxima_host, const float *H_host, int count, int32_t *ns_host,
                          float *delta_host, float *T_host, float *HH_host, int32_t *status_host);
 int tmb_plan_run_tables(tmb_plan *p, const float *stat_dev, int64_t ld, int B, int two_sided, const int32_t *ns_dev,
                         const float *delta_dev, const float *T_dev, const float *HH_dev, const int32_t *tstatus_dev,
-                        float *max_dev, float *tfce_pos_dev, float *tfce_neg_dev, int32_t *status_dev, void *stream);
+                        const float *scale_dev, float *max_dev, float *tfce_pos_dev, float *tfce_neg_dev,
+                        int32_t *status_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Permuted-design fit + t.  Replaces cynumstats.pyx:28-29 cy_lin_lstsqr_mat, :47-52 se_of_slope,

@@ -36,12 +36,13 @@ SIGNATURES = {
     "tmb_plan_set_internal_order": (_int, [_vp, _int]),
     "tmb_tfce_run": (_int, [_vp, _vp, _vp, _c.POINTER(_int)]),
     "tmb_tfce_components": (_int, [_vp, _vp, _int, _vp, _vp, _c.POINTER(_f32)]),
-    "tmb_plan_create": (_int, [_int, _int, _c.POINTER(_vp), _c.POINTER(_i64), _c.POINTER(_vp), _int, _c.POINTER(_vp)]),
+    "tmb_plan_create": (_int, [_int, _int, _c.POINTER(_vp), _c.POINTER(_i64), _c.POINTER(_vp), _c.POINTER(_vp), _int,
+                               _c.POINTER(_vp)]),
     "tmb_plan_destroy": (_int, [_vp]),
     "tmb_plan_run": (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "tmb_plan_maxima": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "tmb_threshold_tables": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
-    "tmb_plan_run_tables": (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tmb_plan_run_tables": (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tmb_glm_sumsq": (_int, [_vp, _int, _int, _i64, _i64, _int, _vp, _vp, _vp]),
     "tmb_glm_tstat": (_int, [_vp, _int, _int, _i64, _i64, _vp, _i64, _vp, _vp, _int, _int, _int, _int, _int, _f64,
                              _vp, _vp, _vp, _i64, _int, _int, _vp]),

@@ -69,6 +69,8 @@ struct tmb_plan {
     std::vector<float *> d_weights;
     std::vector<unsigned short *> d_wrank;  // weight ranks per surface (leader sweep with weights), or nullptr
     std::vector<float *> d_wtab;            // distinct weight values per surface, ascending
+    std::vector<double *> d_weights64;      // float64 weights per surface (non-low-RAM mmr), or nullptr
+    std::vector<double *> d_wtab64;
     int pipe_wfast = 0;                     // every weighted surface has ranks: max-only maps need no per-vertex pass
     char *d_workspace = nullptr;
     size_t slot_stride = 0;
@@ -328,7 +330,8 @@ extern "C" int tmb_graph_num_vertices(const tmb_graph *g, int32_t *V, int64_t *n
 }
 
 extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, const int64_t *col_offset,
-                               const float *const *weight_host, int max_slots, tmb_plan **out) {
+                               const float *const *weight_host, const double *const *weight64_host, int max_slots,
+                               tmb_plan **out) {
     TMB_REQUIRE(out && graphs && col_offset && S > 0, "tmb_plan_create: bad arguments");
     for (int s = 0; s < S; ++s) {
         TMB_REQUIRE(graphs[s], "tmb_plan_create: graph %d is null", s);
@@ -344,6 +347,8 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
     p->d_weights.assign(S, nullptr);
     p->d_wrank.assign(S, nullptr);
     p->d_wtab.assign(S, nullptr);
+    p->d_weights64.assign(S, nullptr);
+    p->d_wtab64.assign(S, nullptr);
     std::vector<SurfDesc> descs(S);
     std::vector<int32_t> order(S);
     std::iota(order.begin(), order.end(), 0);
@@ -411,7 +416,34 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
     bool wfast_ok = true;
     for (int s = 0; s < S; ++s) {
         const tmb_graph *g = graphs[s];
-        if (weight_host && weight_host[s]) {
+        if (weight64_host && weight64_host[s]) {
+            // float64 weights: same ranks, the product is formed in double (scaled_vertex_value)
+            std::vector<double> w(weight64_host[s], weight64_host[s] + g->V);
+            if (!g->vmap.empty())
+                for (int32_t i = 0; i < g->V; ++i) w[i] = weight64_host[s][g->vmap[i]];
+            if ((e = cudaMalloc(&p->d_weights64[s], sizeof(double) * (size_t)g->V)) != cudaSuccess) return fail("malloc", e);
+            if ((e = cudaMemcpy(p->d_weights64[s], w.data(), sizeof(double) * (size_t)g->V, cudaMemcpyHostToDevice)) != cudaSuccess)
+                return fail("memcpy", e);
+            p->pipe_weights = 1;
+            bool ok = true;
+            for (double x : w) ok = ok && std::isfinite(x) && x >= 0.0;
+            std::vector<double> vals(w);
+            std::sort(vals.begin(), vals.end());
+            vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+            if (ok && vals.size() <= 65535) {
+                std::vector<unsigned short> rk((size_t)g->V);
+                for (int32_t i = 0; i < g->V; ++i)
+                    rk[i] = (unsigned short)(std::lower_bound(vals.begin(), vals.end(), w[i]) - vals.begin());
+                if ((e = cudaMalloc(&p->d_wrank[s], sizeof(unsigned short) * (size_t)g->V)) != cudaSuccess) return fail("malloc", e);
+                if ((e = cudaMalloc(&p->d_wtab64[s], sizeof(double) * vals.size())) != cudaSuccess) return fail("malloc", e);
+                if ((e = cudaMemcpy(p->d_wrank[s], rk.data(), sizeof(unsigned short) * (size_t)g->V, cudaMemcpyHostToDevice)) != cudaSuccess)
+                    return fail("memcpy", e);
+                if ((e = cudaMemcpy(p->d_wtab64[s], vals.data(), sizeof(double) * vals.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+                    return fail("memcpy", e);
+            } else {
+                wfast_ok = false;
+            }
+        } else if (weight_host && weight_host[s]) {
             std::vector<float> w(weight_host[s], weight_host[s] + g->V);
             if (!g->vmap.empty())
                 for (int32_t i = 0; i < g->V; ++i) w[i] = weight_host[s][g->vmap[i]];
@@ -443,7 +475,7 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
         SurfDesc d{};
         d.indptr = g->d_indptr; d.indices = g->d_indices; d.ell = g->d_ell; d.ell_width = g->ell_width;
         d.sell = p->pipe_words ? g->d_sell : nullptr; d.sell_off = p->pipe_words ? g->d_sell_off : nullptr;
-        d.wrank = p->d_wrank[s]; d.wtab = p->d_wtab[s];
+        d.wrank = p->d_wrank[s]; d.wtab = p->d_wtab[s]; d.weight64 = p->d_weights64[s]; d.wtab64 = p->d_wtab64[s];
         d.powE = g->d_powE; d.weight = p->d_weights[s]; d.vmap = g->d_vmap; d.col_off = col_offset[s]; d.V = g->V; d.H = g->H;
         d.directed = g->symmetric ? 0 : 1;
         descs[s] = d;
@@ -508,6 +540,8 @@ extern "C" int tmb_plan_destroy(tmb_plan *p) {
     for (float *w : p->d_weights) cudaFree(w);
     for (unsigned short *w : p->d_wrank) cudaFree(w);
     for (float *w : p->d_wtab) cudaFree(w);
+    for (double *w : p->d_weights64) cudaFree(w);
+    for (double *w : p->d_wtab64) cudaFree(w);
     cudaFree(p->d_surfs); cudaFree(p->d_order); cudaFree(p->d_counter); cudaFree(p->d_workspace);
     delete p;
     return 0;
@@ -519,6 +553,7 @@ struct TableSet {
     const float *T = nullptr;
     const float *HH = nullptr;
     const int32_t *status = nullptr;
+    const float *scale = nullptr;   // optional factor of the scaled maxima (default: delta)
 };
 
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
@@ -588,7 +623,7 @@ static int plan_launch_sweep(tmb_plan *p, const float *stat, int64_t ld, int B, 
                              int32_t *labels, int32_t *extents, float *thr, cudaStream_t stream, const TableSet *tabs,
                              const int *only_flagged) {
     SweepParams sp{};
-    if (tabs) { sp.tab_ns = tabs->ns; sp.tab_delta = tabs->delta; sp.tab_T = tabs->T; sp.tab_HH = tabs->HH; sp.tab_status = tabs->status; }
+    if (tabs) { sp.tab_ns = tabs->ns; sp.tab_delta = tabs->delta; sp.tab_T = tabs->T; sp.tab_HH = tabs->HH; sp.tab_status = tabs->status; sp.tab_scale = tabs->scale; }
     sp.surfs = p->d_surfs; sp.surf_order = p->d_order; sp.S = p->S; sp.B = B; sp.two_sided = two_sided;
     sp.accumulate = accumulate; sp.stat = stat; sp.ld = ld; sp.max_out = max_dev; sp.tfce_pos = tfce_pos;
     sp.tfce_neg = tfce_neg; sp.status = status; sp.stop_level = stop_level; sp.labels = labels;
@@ -640,6 +675,7 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
         pp.stat = stat + (size_t)b0 * ld; pp.ld = ld;
         pp.tab_ns = tabs->ns + eoff; pp.tab_delta = tabs->delta + eoff; pp.tab_T = tabs->T + eoff * 128;
         pp.tab_HH = tabs->HH + eoff * 128; pp.tab_status = tabs->status + eoff;
+        pp.tab_scale = tabs->scale ? tabs->scale + eoff : nullptr;
         pp.flags = p->internal_order ? 4 : 0;
         pp.Vmax = p->Vmax; pp.vstride = p->pipe_vstride;
         char *base = p->d_pipe;
@@ -668,6 +704,7 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
         if (launch_tfce_pipeline(pp, p->pipe_slots, stream)) return 1;
         TableSet sub;
         sub.ns = pp.tab_ns; sub.delta = pp.tab_delta; sub.T = pp.tab_T; sub.HH = pp.tab_HH; sub.status = pp.tab_status;
+        sub.scale = pp.tab_scale;
         if (plan_launch_sweep(p, pp.stat, ld, Bc, two_sided, 0, pp.max_out, pp.tfce_pos, pp.tfce_neg, pp.status, -1, nullptr,
                               nullptr, nullptr, stream, &sub, pp.meta))
             return 1;
@@ -743,7 +780,7 @@ extern "C" int tmb_plan_maxima(tmb_plan *p, const float *stat_dev, int64_t ld, i
 
 extern "C" int tmb_plan_run_tables(tmb_plan *p, const float *stat_dev, int64_t ld, int B, int two_sided,
                                    const int32_t *ns_dev, const float *delta_dev, const float *T_dev,
-                                   const float *HH_dev, const int32_t *tstatus_dev, float *max_dev,
+                                   const float *HH_dev, const int32_t *tstatus_dev, const float *scale_dev, float *max_dev,
                                    float *tfce_pos_dev, float *tfce_neg_dev, int32_t *status_dev, void *stream) {
     TMB_REQUIRE(p && stat_dev && B >= 0 && ns_dev && delta_dev && T_dev && HH_dev && tstatus_dev,
                 "tmb_plan_run_tables: bad arguments");
@@ -752,7 +789,7 @@ extern "C" int tmb_plan_run_tables(tmb_plan *p, const float *stat_dev, int64_t l
         TMB_REQUIRE(p->col_offset[s] + p->graphs[s]->V <= ld, "tmb_plan_run_tables: surface %d exceeds row length %lld",
                     s, (long long)ld);
     TMB_ON_DEVICE(p->device);
-    TableSet t; t.ns = ns_dev; t.delta = delta_dev; t.T = T_dev; t.HH = HH_dev; t.status = tstatus_dev;
+    TableSet t; t.ns = ns_dev; t.delta = delta_dev; t.T = T_dev; t.HH = HH_dev; t.status = tstatus_dev; t.scale = scale_dev;
     return plan_launch(p, stat_dev, ld, B, two_sided, 0, max_dev, tfce_pos_dev, tfce_neg_dev, status_dev, -1, nullptr,
                        nullptr, nullptr, (cudaStream_t)stream, &t);
 }
@@ -761,7 +798,7 @@ static int ensure_self_plan(tmb_graph *g) {
     if (g->self_plan) return 0;
     const int64_t off = 0;
     tmb_graph *gs[1] = {g};
-    if (tmb_plan_create(g->device, 1, gs, &off, nullptr, 1, &g->self_plan)) return 1;
+    if (tmb_plan_create(g->device, 1, gs, &off, nullptr, nullptr, 1, &g->self_plan)) return 1;
     TMB_CUDA(cudaMalloc(&g->d_image, sizeof(float) * (size_t)g->V));
     TMB_CUDA(cudaMalloc(&g->d_enhn, sizeof(float) * (size_t)g->V));
     TMB_CUDA(cudaMalloc(&g->d_labels, sizeof(int32_t) * (size_t)g->V));

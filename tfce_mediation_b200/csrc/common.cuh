@@ -77,16 +77,28 @@ struct SurfDesc {
     const int32_t *sell_off; // [nslices + 1] first int4 of every slice
     const double *powE;     // [V+1]  pow((double)n, (double)E) tabulated with the host libm
     const float *weight;    // [V] or nullptr (internal vertex order)
+    const double *weight64; // [V] or nullptr: float64 weights (non-low-RAM mmr builds its density weights with np.hstack
+                            // from [], i.e. float64: the product is then fl32(double(fl32(tfce * delta)) * w), tm_func.py:83-91)
     // weighted maxima without the per-vertex pass (weights finite and >= 0, at most 65,535 distinct values): the
     // weight of a vertex as the RANK of its value among the surface's distinct weights, and the values by rank
     const unsigned short *wrank; // [V] or nullptr
     const float *wtab;           // [distinct weights] or nullptr
+    const double *wtab64;        // the same for float64 weights
     const int32_t *vmap;    // [V] internal (locality-reordered) index -> caller's index, or nullptr
     int64_t col_off;        // first column of this surface in a statistic row
     int32_t V;
     float H;
     int32_t directed;       // adjacency is not symmetric: honour the reference's directional join rule
 };
+
+// fl32(fl32(tfce * scale) * w): the reference's order of operations (pyfunc.py:116-117, tm_func.py:173-174), with the
+// float64 variant of the non-low-RAM mmr path (tm_func.py:83-91)
+__device__ __forceinline__ float scaled_vertex_value(float val, float scale, const SurfDesc &sd, int v) {
+    float sc = __fmul_rn(val, scale);
+    if (sd.weight64) sc = __double2float_rn(__dmul_rn((double)sc, sd.weight64[v]));
+    else if (sd.weight) sc = __fmul_rn(sc, sd.weight[v]);
+    return sc;
+}
 
 // per-launch parameters of the sweep kernel
 struct SweepParams {
@@ -114,6 +126,8 @@ struct SweepParams {
     const float *tab_T;
     const float *tab_HH;
     const int32_t *tab_status;
+    const float *tab_scale;     // optional: factor of the scaled maximum per entry when it is NOT the threshold step
+                                // (non-low-RAM mmr: thresholds from the maximum over ALL surfaces, scale from the surface's own)
     int flags;                  // bit 0: union-find pointer loads go through L1 (ld.ca) instead of ld.cg;
                                 // bit 1: basin sweep (symmetric adjacency only)
                                 // bit 2: statistic rows are in the graphs' internal vertex order (ignore vmap)
@@ -142,6 +156,7 @@ struct PipeParams {
     const float *tab_T;
     const float *tab_HH;
     const int32_t *tab_status;
+    const float *tab_scale; // optional, see SweepParams
     int flags;              // bit 2: statistic rows are in the graphs' internal vertex order
     int max_degree;         // largest vertex degree over the plan's graphs (triangle meshes: 6 -> the ascent kernel skips the two pad slots)
     int sell_words;         // 0: fixed-width rows (ell); W > 0: sliced rows (sell) with W 32-bit words of earlier-neighbour mask per vertex

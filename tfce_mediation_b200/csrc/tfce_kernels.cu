@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_sweep_kernel(SweepPa
     __shared__ float sHH[2][kMaxSteps];
     __shared__ int sNs[2];
     __shared__ float sDelta[2];
+    __shared__ float sScale[2];   // factor of the scaled maximum (the threshold step unless the caller supplies another)
     __shared__ int sStatus[2];
     __shared__ int sCount[kMaxSteps];   // histogram, then running cursor
     __shared__ int sStart[kMaxSteps + 1];
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_sweep_kernel(SweepPa
                 const bool on = (tid == 0) || P.two_sided;
                 sNs[tid] = on ? P.tab_ns[e0 + tid] : 0;
                 sDelta[tid] = P.tab_delta[e0 + tid];
+                sScale[tid] = P.tab_scale ? P.tab_scale[e0 + tid] : P.tab_delta[e0 + tid];
                 sStatus[tid] = on ? P.tab_status[e0 + tid] : 0;
             }
             __syncthreads();
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_sweep_kernel(SweepPa
                 }
                 sNs[sg] = ns;
                 sDelta[sg] = d;
+                sScale[sg] = d;
                 sStatus[sg] = st;
             }
             __syncthreads();
@@ -483,8 +486,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_sweep_kernel(SweepPa
                 if (P.timing && tid == 0) { atomicAdd(P.timing + 7, (unsigned long long)num_nodes); }
             }
             float m0 = 0.f, m1 = 0.f;
-            const float d0 = sDelta[0], d1 = sDelta[1];
-            const float *__restrict__ w = sd.weight;
+            const float d0 = sScale[0], d1 = sScale[1];
             const bool want_maps = (P.tfce_pos != nullptr) || (P.tfce_neg != nullptr);
             if (want_maps && !P.accumulate) {
                 for (int v = tid; v < V; v += nthr) {
@@ -507,8 +509,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, 1) tfce_sweep_kernel(SweepPa
                     val = nodeval[ws.leaf[u]];
                 }
                 if (dst) dst[o] = val;
-                float sc = __fmul_rn(val, neg ? d1 : d0);
-                if (w) sc = __fmul_rn(sc, w[u]);
+                const float sc = scaled_vertex_value(val, neg ? d1 : d0, sd, u);
                 if (neg) m1 = fmaxf(m1, sc); else m0 = fmaxf(m0, sc);
             }
             m0 = warp_max(m0);
@@ -746,6 +747,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
     __shared__ float sHH[2][kMaxSteps];
     __shared__ int sNs[2];
     __shared__ float sDelta[2];
+    __shared__ float sScale[2];   // factor of the scaled maximum (the threshold step unless the caller supplies another)
     __shared__ int sStatus[2];
     __shared__ int sStart[kMaxSteps + 1];
     __shared__ float sRed[2][kSweepMaxThreads / 32];
@@ -807,6 +809,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                 const bool on = (tid == 0) || P.two_sided;
                 sNs[tid] = on ? P.tab_ns[e0 + tid] : 0;
                 sDelta[tid] = P.tab_delta[e0 + tid];
+                sScale[tid] = P.tab_scale ? P.tab_scale[e0 + tid] : P.tab_delta[e0 + tid];
                 sStatus[tid] = on ? P.tab_status[e0 + tid] : 0;
             }
             __syncthreads();
@@ -844,6 +847,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                 }
                 sNs[sg] = ns;
                 sDelta[sg] = d;
+                sScale[sg] = d;
                 sStatus[sg] = st;
             }
             __syncthreads();
@@ -1291,8 +1295,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
             TMB_TICK(5)
             if (P.timing && tid == 0) { atomicAdd(P.timing + 7, (unsigned long long)num_nodes); }
             float m0 = 0.f, m1 = 0.f;
-            const float d0 = sDelta[0], d1 = sDelta[1];
-            const float *__restrict__ w = sd.weight;
+            const float d0 = sScale[0], d1 = sScale[1];
             const bool want_maps = (P.tfce_pos != nullptr) || (P.tfce_neg != nullptr);
             if (want_maps && !P.accumulate) {
                 for (int v = tid; v < V; v += nthr) {
@@ -1315,8 +1318,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tfce_basin_kernel(SweepP
                 } else {
                     val = nodeval[ws.leaf[idx]];
                 }
-                float sc = __fmul_rn(val, neg ? d1 : d0);
-                if (w) sc = __fmul_rn(sc, w[u]);
+                const float sc = scaled_vertex_value(val, neg ? d1 : d0, sd, u);
                 if (neg) m1 = fmaxf(m1, sc); else m0 = fmaxf(m0, sc);
             }
             m0 = warp_max(m0);

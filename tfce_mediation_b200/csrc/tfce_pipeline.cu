@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_kernel(PipePa
         if (tid < 2) {
             const bool on = (tid == 0) || P.two_sided;
             sNs[tid] = on ? P.tab_ns[e0 + tid] : 0;
-            sDelta[tid] = P.tab_delta[e0 + tid];
+            sDelta[tid] = P.tab_scale ? P.tab_scale[e0 + tid] : P.tab_delta[e0 + tid]; // factor of the scaled maximum
             if (P.status) P.status[e0 + tid] = on ? P.tab_status[e0 + tid] : 0;
         }
         if (tid == 0) sC = 0;
@@ -1292,7 +1292,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         if (tid < 2) {
             const bool on = (tid == 0) || P.two_sided;
             sNs[tid] = on ? P.tab_ns[e0 + tid] : 0;
-            sDelta[tid] = P.tab_delta[e0 + tid];
+            sDelta[tid] = P.tab_scale ? P.tab_scale[e0 + tid] : P.tab_delta[e0 + tid]; // factor of the scaled maximum
             if (P.status) P.status[e0 + tid] = on ? P.tab_status[e0 + tid] : 0;
             sNalive[tid] = 0;
         }
@@ -1620,7 +1620,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                     for (int k = 0; k < c; ++k) { // fl32(fl32(tfce * delta) * w), the reference's order (pyfunc.py:116-117)
                         const uint2 e = fget(bb, k);
                         float sc = __fmul_rn(__uint_as_float(e.x), sg ? d1 : d0);
-                        if (sd.wtab) sc = __fmul_rn(sc, sd.wtab[e.y]);
+                        if (sd.wtab64) sc = __double2float_rn(__dmul_rn((double)sc, sd.wtab64[e.y]));
+                        else if (sd.wtab) sc = __fmul_rn(sc, sd.wtab[e.y]);
                         if (sg) m1 = fmaxf(m1, sc); else m0 = fmaxf(m0, sc);
                     }
                 }
@@ -1661,8 +1662,7 @@ __global__ void __launch_bounds__(256) pipe_output_kernel(PipeParams P, int chun
             const int cv = P.lev8[base + v];
             neg = cv >> 7;
             val = __uint_as_float(P.table[(size_t)item * P.tabcap + (size_t)(cv & 0x7f) * meta[0] + bu]);
-            float sc = __fmul_rn(val, P.tab_delta[e0 + neg]);
-            if (sd.weight) sc = __fmul_rn(sc, sd.weight[v]);
+            const float sc = scaled_vertex_value(val, P.tab_scale ? P.tab_scale[e0 + neg] : P.tab_delta[e0 + neg], sd, v);
             if (neg) sc1 = sc; else sc0 = sc;
         }
         const int32_t *__restrict__ vmap = (P.flags & 4) ? nullptr : sd.vmap;

@@ -25,6 +25,11 @@ _E2E_DEBUG = bool(_os.environ.get("TMB_E2E_DEBUG"))   # per-block host timings o
 MAX_REGRESSORS = 64       # non-intercept regressors per design (more than 8 take the stored-beta path, tmb_glm_*_beta)
 
 
+def _row_stride(stat):
+    """Leading dimension of a [B, ld] statistic tensor; a one-row tensor may report any stride for its first axis."""
+    return int(stat.stride(0)) if stat.shape[0] > 1 else max(int(stat.stride(0)), int(stat.shape[1]))
+
+
 class Surface(object):
     """One TFCE graph laid on columns [col_offset, col_offset + V) of a statistic row."""
 
@@ -35,30 +40,50 @@ class Surface(object):
         self.col_offset = int(col_offset)
         if weight is not None and np.ndim(weight) == 0:
             weight = None if float(weight) == 1.0 else np.full(adjset.num_vertices, weight, dtype=np.float32)
+        self.weight64 = None
         if weight is not None:
-            weight = np.ascontiguousarray(weight, dtype=np.float32)
-            if weight.shape != (adjset.num_vertices,):
+            w = np.asarray(weight)
+            if w.shape != (adjset.num_vertices,):
                 raise ValueError("weight must have one entry per vertex")
+            if w.dtype == np.float64 and not np.array_equal(w.astype(np.float32).astype(np.float64), w):
+                # float64 weights that float32 cannot hold: the reference then multiplies in double
+                # (non-low-RAM mmr, tm_func.py:83-91); exactly representable ones give the same product either way
+                self.weight64 = np.ascontiguousarray(w, dtype=np.float64)
+            weight = np.ascontiguousarray(w, dtype=np.float32)
         self.weight = weight
 
 
 class TfcePlan(object):
     """tmb_plan handle: S surfaces along one statistic row."""
 
-    def __init__(self, surfaces, device=None, max_slots=0):
+    def __init__(self, surfaces, device=None, max_slots=0, threshold_groups=None):
+        """threshold_groups: optional list of surface-index lists whose members share ONE threshold sequence, built from
+        the largest statistic over the whole group -- the non-low-RAM mmr path runs a single TFCE over the merged graph of
+        all surfaces (tm_func.py:77-78, so fast_tfce.hpp:32-36 sees the global maximum) and then rescales every surface
+        with its own max/100 (tm_func.py:83-91)."""
         import torch
         _lib.require_device()
         self.surfaces = list(surfaces)
         S = len(self.surfaces)
         if S == 0:
             raise ValueError("no surfaces")
+        self.groups = None
+        if threshold_groups is not None:
+            gid = -np.ones(S, dtype=np.int64)
+            for gi, members in enumerate(threshold_groups):
+                gid[np.asarray(list(members), dtype=np.int64)] = gi
+            if (gid < 0).any():
+                raise ValueError("threshold_groups must cover every surface")
+            self.groups = gid
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         parallel.check_device(self.device.index)
         graphs = (ctypes.c_void_p * S)(*[s.adjset._handle for s in self.surfaces])
         offs = (ctypes.c_int64 * S)(*[s.col_offset for s in self.surfaces])
         wts = (ctypes.c_void_p * S)(*[(s.weight.ctypes.data if s.weight is not None else None) for s in self.surfaces])
+        w64 = (ctypes.c_void_p * S)(*[(s.weight64.ctypes.data if getattr(s, "weight64", None) is not None else None)
+                                      for s in self.surfaces])
         h = ctypes.c_void_p()
-        _lib.check(_lib.lib().tmb_plan_create(self.device.index or 0, S, graphs, offs, wts, int(max_slots),
+        _lib.check(_lib.lib().tmb_plan_create(self.device.index or 0, S, graphs, offs, wts, w64, int(max_slots),
                                               ctypes.byref(h)))
         self._handle = h
         self.S = S
@@ -104,7 +129,9 @@ class TfcePlan(object):
             raise ValueError("stat must be a CUDA float32 [B, ld] tensor with unit column stride")
         if exact_pow is None:
             exact_pow = self.exact_pow
-        B, ld = int(stat.shape[0]), int(stat.stride(0))
+        if self.groups is not None:
+            exact_pow = True              # group thresholds are built on the host
+        B, ld = int(stat.shape[0]), _row_stride(stat)
         mx = out_max if out_max is not None else torch.empty((B, self.S, 2), dtype=torch.float32, device=stat.device)
         status = torch.empty((B, self.S, 2), dtype=torch.int32, device=stat.device)
         pos = neg = None
@@ -126,7 +153,7 @@ class TfcePlan(object):
         memory.  Returns a ticket for finish().  Enqueue further GPU work (e.g. the fit of the next block)
         before calling finish() and the host table building overlaps it."""
         import torch
-        B, ld = int(stat.shape[0]), int(stat.stride(0))
+        B, ld = int(stat.shape[0]), _row_stride(stat)
         cnt = B * self.S * 2
         slot = self._tickets.setdefault((cnt, self._flip), {})
         self._flip ^= 1
@@ -134,6 +161,7 @@ class TfcePlan(object):
             slot["dev"] = torch.empty((cnt,), dtype=torch.float32, device=stat.device)
             slot["host"] = torch.empty((cnt,), dtype=torch.float32).pin_memory()
             slot["event"] = torch.cuda.Event()
+            slot["scale"] = torch.empty((cnt,), dtype=torch.float32).pin_memory()
             slot["tab"] = dict(ns=torch.empty((cnt,), dtype=torch.int32).pin_memory(),
                                delta=torch.empty((cnt,), dtype=torch.float32).pin_memory(),
                                T=torch.empty((cnt, 128), dtype=torch.float32).pin_memory(),
@@ -153,7 +181,7 @@ class TfcePlan(object):
         (tmb_threshold_tables), upload them and launch the sweep."""
         import torch
         L = _lib.lib()
-        B, ld = int(stat.shape[0]), int(stat.stride(0))
+        B, ld = int(stat.shape[0]), _row_stride(stat)
         cnt = ticket["cnt"]
         mx = out_max if out_max is not None else torch.empty((B, self.S, 2), dtype=torch.float32, device=stat.device)
         if status is None:
@@ -166,6 +194,19 @@ class TfcePlan(object):
         t1 = _time.perf_counter() if dbg else 0.0
         tab = ticket["tab"]
         mh = ticket["host"].numpy()
+        scale_d = None
+        if self.groups is not None:
+            # thresholds from the group's maximum, scale factor from the surface's own: fl32(max / 100) as numpy forms
+            # `tval_temp[start:end].max() / 100` on float32 (tm_func.py:87-91)
+            m3 = mh.reshape(B, self.S, 2)
+            with np.errstate(invalid="ignore"):
+                ticket["scale"].numpy()[...] = (m3 / np.float32(100)).reshape(-1)
+            gm = np.empty_like(m3)
+            for gi in np.unique(self.groups):
+                sel = self.groups == gi
+                gm[:, sel, :] = np.fmax.reduce(m3[:, sel, :], axis=1, keepdims=True)
+            mh = np.ascontiguousarray(gm.reshape(-1))
+            scale_d = ticket["scale"].to(stat.device, non_blocking=True)
         _lib.check(L.tmb_threshold_tables(_lib.ptr(mh), _lib.ptr(ticket["Hs"]), cnt, _lib.ptr(tab["ns"]),
                                           _lib.ptr(tab["delta"]), _lib.ptr(tab["T"]), _lib.ptr(tab["HH"]),
                                           _lib.ptr(tab["st"])))
@@ -179,9 +220,9 @@ class TfcePlan(object):
         ticket["tab_event"].record()
         _lib.check(L.tmb_plan_run_tables(self._handle, _lib.ptr(stat), ld, B, 1 if two_sided else 0, _lib.ptr(d["ns"]),
                                          _lib.ptr(d["delta"]), _lib.ptr(d["T"]), _lib.ptr(d["HH"]), _lib.ptr(d["st"]),
-                                         _lib.ptr(mx), _lib.ptr(pos), _lib.ptr(neg), _lib.ptr(status),
+                                         _lib.ptr(scale_d), _lib.ptr(mx), _lib.ptr(pos), _lib.ptr(neg), _lib.ptr(status),
                                          _lib.current_stream()))
-        ticket["inflight"] = d   # keep the device tables alive until this ticket is reused
+        ticket["inflight"] = (d, scale_d)   # keep the device tables alive until this ticket is reused
         return mx, status, (pos, neg)
 
 
@@ -298,14 +339,15 @@ class PermutationEngine(object):
             yield a, b - a, beta
 
     def __init__(self, data, surfaces, two_sided=True, nan_to_zero=False, device=None, max_slots=0,
-                 permute_columns=True):
+                 permute_columns=True, threshold_groups=None):
         import torch
         _lib.require_device()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         parallel.check_device(self.device.index)
         owned = not isinstance(data, DeviceMatrix)
         self.Y = DeviceMatrix(data, device=self.device) if owned else data
-        self.plan = TfcePlan(surfaces, device=self.device, max_slots=max_slots) if surfaces is not None else None
+        self.plan = (TfcePlan(surfaces, device=self.device, max_slots=max_slots, threshold_groups=threshold_groups)
+                     if surfaces is not None else None)
         if self.plan is not None and self.plan.row_len > self.Y.V:
             raise ValueError("surfaces cover %d columns but the data has %d" % (self.plan.row_len, self.Y.V))
         self.colperm = None

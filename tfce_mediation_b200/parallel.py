@@ -29,13 +29,26 @@ def shard_range(first, last, rank, world_size):
     return a, b
 
 
+def _shared_gpu():
+    """TMB_ALLOW_SHARED_GPU=1 (tests on a one-GPU box): ranks beyond the GPU count share devices, collectives use gloo."""
+    import torch
+    _, ws, _ = world()
+    return bool(os.environ.get("TMB_ALLOW_SHARED_GPU")) and torch.cuda.is_available() and torch.cuda.device_count() < ws
+
+
+def local_device_index():
+    import torch
+    _, _, local = world()
+    return local % max(1, torch.cuda.device_count()) if _shared_gpu() else local
+
+
 def bind_device():
     """One process per GPU: make cuda:LOCAL_RANK the current device of this process.  Must run before any graph, plan
     or engine is created (they live on the current device); every driver calls it first through setup()."""
     import torch
     _, ws, local = world()
     if torch.cuda.is_available() and ws > 1:
-        torch.cuda.set_device(local)
+        torch.cuda.set_device(local_device_index())
 
 
 def setup(backend=None):
@@ -49,6 +62,8 @@ def setup(backend=None):
 def check_device(device_index):
     """Refuse to build device state on another rank's GPU (all ranks piling onto cuda:0 was the round-1 driver bug)."""
     _, ws, local = world()
+    if ws > 1:
+        local = local_device_index()
     if ws > 1 and device_index is not None and int(device_index) != local:
         raise RuntimeError("rank with LOCAL_RANK=%d is about to allocate on cuda:%d: call parallel.setup() "
                            "(or torch.cuda.set_device(LOCAL_RANK)) before creating graphs or engines" % (local, device_index))
@@ -61,7 +76,7 @@ def init_process_group(backend=None):
     if ws == 1 or dist.is_initialized():
         return
     if backend is None:
-        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        backend = "nccl" if torch.cuda.is_available() and not _shared_gpu() else "gloo"
     if backend == "nccl":
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

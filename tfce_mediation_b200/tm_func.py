@@ -9,24 +9,22 @@
     low_ram_calculate_mediation_tfce(...)                tm_func.py:269-305
     calc_mixed_tfce(...)                                 tm_func.py:327-378
 
-Same names, arguments, return values and CSV side effects ('%f' rows, positive then negative) as the
-reference.  The per-vertex arithmetic runs on the GPU (cynumstats.tval_int -> tmb_glm_direct,
-CreateAdjSet.run -> tmb_tfce_run, calc_sobelz -> tmb_sobelz); these single-shuffle forms exist for
-API parity.  Whole permutation runs go through tm_multisurface.mmr_lr_randomise, which batches
-shuffles x surfaces through engine.PermutationEngine and writes the same rows.
+Same names, arguments, return values and CSV side effects ('%f' rows, positive then negative) as the reference, but every
+function is an ADAPTER over the batched engine (engine.PermutationEngine): the surfaces of the merged graph behind
+`calcTFCE` become the surfaces of one TFCE plan whose threshold sequence is shared by the whole group (the reference runs
+ONE TFCE over the merged image, so its threshold step is the maximum over all surfaces / 100, fast_tfce.hpp:32-36) while
+every surface is rescaled with its own maximum (tm_func.py:83-91).  A single call is a block of one shuffle; the engine --
+data resident in HBM, graphs, plan -- is built on the first call and reused for as long as the same data and CreateAdjSet
+objects are passed, which is how the reference's permutation loops call these functions
+(tm_multimodality_multisurface_regression.py:540-572).  Whole permutation ranges go through
+tm_multisurface.mmr_randomise / mmr_lr_randomise, which batch shuffles x surfaces and write the same rows.
 """
-import os
+import weakref
 from time import time
 
 import numpy as np
 
-from .cynumstats import tval_int
-from .pyfunc import calc_sobelz
-
-
-def _append(path, value):
-    with open(path, "a") as f:
-        f.write("%f\n" % value)
+from ._graph import induced_subgraph
 
 
 def _time_seed(perm_number):
@@ -34,233 +32,274 @@ def _time_seed(perm_number):
     return perm_number + int(float(str(time())[-6:]) * 100)
 
 
+def _mask_piece(m):
+    """Flat mask of one surface as create_full_mask sees it: a vertex image's [V, 1, 1] column, or the True voxels."""
+    m = np.asarray(m)
+    return m[:, 0, 0] if m.shape[2] == 1 else m[m == True]  # noqa: E712
+
+
 def create_full_mask(masking_array):
-    """Concatenated flat mask of all surfaces (tm_func.py:502-510)."""
-    full_mask = None
-    for i in range(len(masking_array)):
-        piece = masking_array[i][:, 0, 0] if masking_array[i].shape[2] == 1 else masking_array[i][masking_array[i] == True]  # noqa: E712
-        full_mask = piece if full_mask is None else np.hstack((full_mask, piece))
-    return full_mask
-
-
-def merge_adjacency_array(adjacent_range, adjacency_array):
-    """Block-diagonal merge of per-surface adjacency lists (tm_func.py:521-540); like the reference it
-    always starts from adjacency_array[0] and offsets every later surface by the running vertex count."""
-    v_count = 0
-    if len(adjacent_range) == 1:
-        adjacency = np.copy(adjacency_array[0])
-    else:
-        for e in adjacent_range:
-            if v_count == 0:
-                adjacency = np.copy(adjacency_array[0])
-                v_count += len(adjacency_array[0])
-            else:
-                temp_adjacency = np.copy(adjacency_array[e])
-                for i in range(len(adjacency_array[e])):
-                    temp_adjacency[i] = np.add(list(temp_adjacency[i]), v_count).tolist()
-                adjacency = np.hstack((adjacency, temp_adjacency))
-                v_count += len(adjacency_array[e])
-    return adjacency
+    """Concatenated flat mask of all surfaces (tm_func.py:502-510); float64 like the reference's hstack from []."""
+    return np.concatenate([np.zeros(0)] + [np.asarray(_mask_piece(m), dtype=np.float64) for m in masking_array])
 
 
 def create_position_array(masking_array):
-    """Start offsets of every surface in the concatenated data (tm_func.py:556-562)."""
-    pointer = 0
-    position_array = [0]
-    for i in range(len(masking_array)):
-        pointer += len(masking_array[i][masking_array[i] == True])  # noqa: E712
-        position_array.append(pointer)
-    return position_array
+    """Start offset of every surface in the concatenated data (tm_func.py:556-562)."""
+    sizes = [int(np.count_nonzero(np.asarray(m) == True)) for m in masking_array]  # noqa: E712
+    return [0] + np.cumsum(sizes).tolist()
+
+
+def merge_adjacency_array(adjacent_range, adjacency_array):
+    """Block-diagonal merge of per-surface adjacency lists (tm_func.py:521-540).  Like the reference, the first block is
+    always adjacency_array[0] (whatever adjacent_range[0] is) while the running offset advances by len(adjacency_array[e]);
+    a single-entry range returns adjacency_array[0] alone."""
+    blocks, offset = [], 0
+    for pos, e in enumerate(adjacent_range):
+        src = adjacency_array[0] if pos == 0 else adjacency_array[e]
+        blk = np.empty(len(src), dtype=object)
+        for i, nb in enumerate(src):
+            blk[i] = (np.asarray(list(nb), dtype=np.int64) + offset).tolist() if len(nb) else []
+        blocks.append(blk)
+        offset += len(adjacency_array[e])
+        if len(adjacent_range) == 1:
+            break
+    return np.concatenate(blocks) if len(blocks) > 1 else blocks[0]
+
+
+# ---------------------------------------------------------------------------------------------- engines
+_ENGINES = []       # [(weakref(data), weakref(calcTFCE), key, engine)], most recent last
+_MAX_ENGINES = 4
+
+
+def _cached_engine(data, calcTFCE, key, build):
+    for ent in _ENGINES:
+        if ent[0]() is data and ent[1]() is calcTFCE and ent[2] == key:
+            return ent[3]
+    eng = build()
+    _ENGINES.append((weakref.ref(data), weakref.ref(calcTFCE), key, eng))
+    del _ENGINES[:-_MAX_ENGINES]
+    return eng
+
+
+def _split_merged_graph(calcTFCE, pieces):
+    """Per-surface CSR of the kept vertices out of the merged (block-diagonal) graph of a CreateAdjSet."""
+    indptr, indices = calcTFCE.indptr, calcTFCE.indices
+    if sum(len(p) for p in pieces) != calcTFCE.num_vertices:
+        raise ValueError("the masks cover %d vertices, the adjacency %d" % (sum(len(p) for p in pieces), calcTFCE.num_vertices))
+    out, lo = [], 0
+    for piece in pieces:
+        hi = lo + len(piece)
+        ip = indptr[lo:hi + 1] - indptr[lo]
+        ix = indices[indptr[lo]:indptr[hi]].astype(np.int64) - lo
+        if ix.size and (ix.min() < 0 or ix.max() >= hi - lo):
+            raise ValueError("the adjacency of one surface points into another: not a merge_adjacency_array graph")
+        out.append(induced_subgraph(ip.astype(np.int64), ix.astype(np.int32), np.asarray(piece) == 1))
+        lo = hi
+    return out
+
+
+def _density_slices(vdensity, position_array, nsurf):
+    if np.ndim(vdensity) == 0:
+        return [None if float(vdensity) == 1.0 else float(vdensity)] * nsurf
+    v = np.asarray(vdensity)
+    return [v[position_array[i]:position_array[i + 1]] for i in range(nsurf)]
+
+
+def _mmr_engine(merge_y, masking_array, calcTFCE, vdensity, position_array, two_sided):
+    """The engine behind calculate_tfce / calculate_mediation_tfce: one surface per mask, one threshold group."""
+    from .engine import PermutationEngine, Surface
+    from .tfce import CreateAdjSet
+    dens_key = None if np.ndim(vdensity) == 0 else id(vdensity)
+
+    def build():
+        graphs = _split_merged_graph(calcTFCE, [_mask_piece(m) for m in masking_array])
+        dens = _density_slices(vdensity, position_array, len(masking_array))
+        surfs = [Surface(CreateAdjSet(calcTFCE.H, calcTFCE.E, g), position_array[i], dens[i]) for i, g in enumerate(graphs)]
+        return PermutationEngine(merge_y, surfs, two_sided=two_sided, threshold_groups=[list(range(len(surfs)))])
+
+    return _cached_engine(merge_y, calcTFCE, ("mmr", two_sided, dens_key, len(masking_array)), build)
+
+
+def _lowram_engine(data, mask, calcTFCE, vdensity, two_sided):
+    from .engine import PermutationEngine, Surface
+    from .tfce import CreateAdjSet
+    dens_key = None if np.ndim(vdensity) == 0 else id(vdensity)
+
+    def build():
+        g = induced_subgraph(calcTFCE.indptr, calcTFCE.indices, np.asarray(mask) == 1)
+        w = None if (np.ndim(vdensity) == 0 or np.size(vdensity) == 1) and float(np.ravel(vdensity)[0]) == 1.0 else vdensity
+        if w is not None and np.size(w) == 1:
+            w = float(np.ravel(w)[0])
+        return PermutationEngine(data, [Surface(CreateAdjSet(calcTFCE.H, calcTFCE.E, g), 0, w)], two_sided=two_sided)
+
+    return _cached_engine(data, calcTFCE, ("lr", two_sided, dens_key), build)
+
+
+def _append(path, values):
+    with open(path, "a") as f:
+        for v in values:
+            f.write("%f\n" % v)
+
+
+def _scaled_maps(eng, stat, maps):
+    """tfce * (max(stat over the surface) / 100) * density per surface, as float32 (tm_func.py:83-91,173-174)."""
+    out = np.zeros_like(stat, dtype=np.float32)
+    for s in eng.plan.surfaces:
+        a, b = s.col_offset, s.col_offset + s.adjset.num_vertices
+        w = 1 if s.weight is None else (s.weight64 if s.weight64 is not None else s.weight)
+        for c in range(stat.shape[0]):
+            out[c, a:b] = maps[c, a:b] * (stat[c, a:b].max() / 100) * w
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- regression
+def _regression(eng, pred_x, n, seed, randomise, no_intercept):
+    """(X as fitted, maxima [C, S, 2] or observed (t, pos, neg))."""
+    X = np.column_stack([np.ones(n), pred_x])
+    perm = np.arange(n)
+    if randomise:
+        np.random.seed(seed)
+        perm = np.random.permutation(list(range(n)))
+    if randomise:
+        return eng.regression_block(X, perm_idx=perm[None, :])[0]
+    mx, t32, (pos, neg) = eng.regression_block(X, perm_idx=perm[None, :], want_maps=True)
+    V = eng.Y.V
+    t = t32[0, :, :V].cpu().numpy()
+    return t, _scaled_maps(eng, t, pos[:, :V].cpu().numpy()), _scaled_maps(eng, -t, neg[:, :V].cpu().numpy())
 
 
 def calculate_tfce(merge_y, masking_array, pred_x, calcTFCE, vdensity, position_array, fullmask, perm_number=None,
                    randomise=False, verbose=False, no_intercept=True, set_surf_count=None, print_interation=False):
-    """Non-low-RAM mmr (tm_func.py:54-123): ONE TFCE over the merged graph (so the threshold step is the
-    global maximum / 100) followed by a per-surface rescale and per-surface nanmax rows."""
-    X = np.column_stack([np.ones(merge_y.shape[0]), pred_x])
+    """Non-low-RAM mmr (tm_func.py:54-123): ONE TFCE over the merged graph -- threshold step = global maximum / 100 --
+    then a per-surface rescale and per-surface nanmax rows in perm_maxTFCE_surf{s}_tcon{c}.csv."""
+    if not no_intercept:
+        raise NotImplementedError("no_intercept=False: the reference's callers never pass it (the intercept row is dropped)")
+    eng = _mmr_engine(merge_y, masking_array, calcTFCE, vdensity, position_array, True)
+    res = _regression(eng, pred_x, merge_y.shape[0], _time_seed(perm_number) if randomise else None, randomise, no_intercept)
+    labels = [int(np.ravel(s)[0]) for s in set_surf_count] if set_surf_count is not None else list(range(len(masking_array)))
     if randomise:
-        np.random.seed(_time_seed(perm_number))
-        X = X[np.random.permutation(list(range(merge_y.shape[0])))]
-    k = len(X.T)
-    invXX = np.linalg.inv(np.dot(X.T, X))
-    tvals = tval_int(X, invXX, merge_y, merge_y.shape[0], k, merge_y.shape[1])
-    if no_intercept:
-        tvals = tvals[1:, :]
-    tvals = tvals.astype(np.float32, order="C")
-    tfce_tvals = np.zeros_like(tvals).astype(np.float32, order="C")
-    neg_tfce_tvals = np.zeros_like(tvals).astype(np.float32, order="C")
-    for tstat_counter in range(tvals.shape[0]):
-        tval_temp = np.zeros_like((fullmask)).astype(np.float32, order="C")
-        tval_temp[fullmask == 1] = tvals[0] if tvals.shape[0] == 1 else tvals[tstat_counter]
-        tval_temp = tval_temp.astype(np.float32, order="C")
-        tfce_temp = np.zeros_like(tval_temp).astype(np.float32, order="C")
-        neg_tfce_temp = np.zeros_like(tval_temp).astype(np.float32, order="C")
-        calcTFCE.run(tval_temp, tfce_temp)
-        calcTFCE.run((tval_temp * -1), neg_tfce_temp)
-        tval_temp = tval_temp[fullmask == 1]
-        tfce_temp = tfce_temp[fullmask == 1]
-        neg_tfce_temp = neg_tfce_temp[fullmask == 1]
-        for surf_count in range(len(masking_array)):
-            start = position_array[surf_count]
-            end = position_array[surf_count + 1]
-            dens = vdensity if isinstance(vdensity, int) else vdensity[start:end]
-            tfce_tvals[tstat_counter, start:end] = (tfce_temp[start:end] * (tval_temp[start:end].max() / 100) * dens)
-            neg_tfce_tvals[tstat_counter, start:end] = (neg_tfce_temp[start:end] * ((tval_temp * -1)[start:end].max() / 100) * dens)
-            label = int(set_surf_count[surf_count]) if set_surf_count is not None else surf_count
-            pmax = np.nanmax(tfce_tvals[tstat_counter, start:end])
-            nmax = np.nanmax(neg_tfce_tvals[tstat_counter, start:end])
-            if randomise:
-                _append("perm_maxTFCE_surf%d_tcon%d.csv" % (label, tstat_counter + 1), pmax)
-                _append("perm_maxTFCE_surf%d_tcon%d.csv" % (label, tstat_counter + 1), nmax)
-            else:
-                print("Maximum (untransformed) postive tfce value for surface %s, tcon %d: %f" % (label, tstat_counter + 1, pmax))
-                print("Maximum (untransformed) negative tfce value for surface %s, tcon %d: %f" % (label, tstat_counter + 1, nmax))
-        if verbose:
-            print("T-contrast: %d" % tstat_counter)
-            print("Max tfce from all surfaces = %f" % tfce_tvals[tstat_counter].max())
-            print("Max negative tfce from all surfaces = %f" % neg_tfce_tvals[tstat_counter].max())
-    if randomise:
+        for c in range(res.shape[0]):
+            for s, label in enumerate(labels):
+                _append("perm_maxTFCE_surf%d_tcon%d.csv" % (label, c + 1), (res[c, s, 0], res[c, s, 1]))
         if print_interation:
             print("Interation number: %d" % perm_number)
         return None
-    return (tvals.astype(np.float32, order="C"), tfce_tvals.astype(np.float32, order="C"),
-            neg_tfce_tvals.astype(np.float32, order="C"))
+    tvals, tfce_tvals, neg_tfce_tvals = res
+    for c in range(tvals.shape[0]):
+        for s, label in enumerate(labels):
+            a, b = position_array[s], position_array[s + 1]
+            print("Maximum (untransformed) postive tfce value for surface %s, tcon %d: %f" % (label, c + 1, np.nanmax(tfce_tvals[c, a:b])))
+            print("Maximum (untransformed) negative tfce value for surface %s, tcon %d: %f" % (label, c + 1, np.nanmax(neg_tfce_tvals[c, a:b])))
+        if verbose:
+            print("T-contrast: %d" % c)
+            print("Max tfce from all surfaces = %f" % tfce_tvals[c].max())
+            print("Max negative tfce from all surfaces = %f" % neg_tfce_tvals[c].max())
+    return tvals, tfce_tvals, neg_tfce_tvals
 
 
 def low_ram_calculate_tfce(data, mask, pred_x, calcTFCE, vdensity, set_surf_count=0, perm_number=None, randomise=False,
                            no_intercept=True, output_dir=None, perm_seed=None):
     """mmr-lr, one surface (tm_func.py:144-185); deterministic when perm_seed is given."""
-    X = np.column_stack([np.ones(data.shape[0]), pred_x])
+    if not no_intercept:
+        raise NotImplementedError("no_intercept=False: the reference's callers never pass it")
+    eng = _lowram_engine(data, mask, calcTFCE, vdensity, True)
+    seed = None
     if randomise:
-        np.random.seed(perm_number + perm_seed if perm_seed is not None else _time_seed(perm_number))
-        X = X[np.random.permutation(list(range(data.shape[0])))]
-    k = len(X.T)
-    invXX = np.linalg.inv(np.dot(X.T, X))
-    tvals = tval_int(X, invXX, data, data.shape[0], k, data.shape[1])
-    if no_intercept:
-        tvals = tvals[1:, :]
-    tvals = tvals.astype(np.float32, order="C")
-    tfce_tvals = np.zeros_like(tvals).astype(np.float32, order="C")
-    neg_tfce_tvals = np.zeros_like(tvals).astype(np.float32, order="C")
-    for tstat_counter in range(tvals.shape[0]):
-        tval_temp = np.zeros_like((mask)).astype(np.float32, order="C")
-        tval_temp[mask == 1] = tvals[0] if tvals.shape[0] == 1 else tvals[tstat_counter]
-        tval_temp = tval_temp.astype(np.float32, order="C")
-        tfce_temp = np.zeros_like(tval_temp).astype(np.float32, order="C")
-        neg_tfce_temp = np.zeros_like(tval_temp).astype(np.float32, order="C")
-        calcTFCE.run(tval_temp, tfce_temp)
-        calcTFCE.run(-tval_temp, neg_tfce_temp)
-        tfce_tvals[tstat_counter, :] = (tfce_temp[mask == 1] * (tval_temp.max() / 100) * vdensity)
-        neg_tfce_tvals[tstat_counter, :] = (neg_tfce_temp[mask == 1] * ((tval_temp * -1).max() / 100) * vdensity)
-        if randomise:
-            name = "perm_maxTFCE_surf%d_tcon%d.csv" % (int(set_surf_count), tstat_counter + 1)
-            permfile = "%s/%s" % (output_dir, name) if output_dir is not None else name
-            _append(permfile, np.nanmax(tfce_tvals[tstat_counter, :]))
-            _append(permfile, np.nanmax(neg_tfce_tvals[tstat_counter, :]))
+        seed = perm_number + perm_seed if perm_seed is not None else _time_seed(perm_number)
+    res = _regression(eng, pred_x, data.shape[0], seed, randomise, no_intercept)
     if not randomise:
-        return (tvals.astype(np.float32, order="C"), tfce_tvals.astype(np.float32, order="C"),
-                neg_tfce_tvals.astype(np.float32, order="C"))
+        return res
+    for c in range(res.shape[0]):
+        name = "perm_maxTFCE_surf%d_tcon%d.csv" % (int(set_surf_count), c + 1)
+        _append("%s/%s" % (output_dir, name) if output_dir is not None else name, (res[c, 0, 0], res[c, 0, 1]))
 
 
-def _permute_mediation(medtype, pred_x, depend_y, n, perm_number, perm_seed):
-    np.random.seed(perm_number + perm_seed if perm_seed is not None else _time_seed(perm_number))
-    indices_perm = np.random.permutation(list(range(n)))
-    if medtype in ("M", "I"):
-        return pred_x[indices_perm], depend_y
-    return pred_x[indices_perm], depend_y[indices_perm]
+# ---------------------------------------------------------------------------------------------- mediation
+def _mediation(eng, medtype, pred_x, depend_y, n, seed, randomise):
+    perm = np.arange(n)
+    if randomise:
+        np.random.seed(seed)
+        perm = np.random.permutation(list(range(n)))
+    if randomise:
+        return eng.mediation_block(medtype, pred_x, depend_y, perm[None, :])[0]
+    mx, z32, (pos, _) = eng.mediation_block(medtype, pred_x, depend_y, perm[None, :], want_maps=True)
+    V = eng.Y.V
+    z = z32[:, :V].cpu().numpy()
+    return z[0], _scaled_maps(eng, z, pos[:, :V].cpu().numpy())[0]
 
 
 def calculate_mediation_tfce(medtype, merge_y, masking_array, pred_x, depend_y, calcTFCE, vdensity, position_array,
                              fullmask, perm_number=None, randomise=False, verbose=False, no_intercept=True,
                              print_interation=False):
-    """Non-low-RAM mmr mediation (tm_func.py:207-249)."""
+    """Non-low-RAM mmr mediation (tm_func.py:207-249): Sobel z, one-sided TFCE over the merged graph."""
+    eng = _mmr_engine(merge_y, masking_array, calcTFCE, vdensity, position_array, False)
+    res = _mediation(eng, medtype, pred_x, depend_y, merge_y.shape[0], _time_seed(perm_number) if randomise else None, randomise)
     if randomise:
-        pred_x, depend_y = _permute_mediation(medtype, pred_x, depend_y, merge_y.shape[0], perm_number, None)
-    SobelZ = calc_sobelz(medtype, pred_x, depend_y, merge_y, merge_y.shape[0], merge_y.shape[1])
-    SobelZ = SobelZ.astype(np.float32, order="C")
-    tfce_SobelZ = np.zeros_like(SobelZ).astype(np.float32, order="C")
-    zval_temp = np.zeros_like((fullmask)).astype(np.float32, order="C")
-    zval_temp[fullmask == 1] = SobelZ
-    zval_temp = zval_temp.astype(np.float32, order="C")
-    tfce_temp = np.zeros_like(zval_temp).astype(np.float32, order="C")
-    calcTFCE.run(zval_temp, tfce_temp)
-    zval_temp = zval_temp[fullmask == 1]
-    tfce_temp = tfce_temp[fullmask == 1]
-    for surf_count in range(len(masking_array)):
-        start = position_array[surf_count]
-        end = position_array[surf_count + 1]
-        dens = vdensity if isinstance(vdensity, int) else vdensity[start:end]
-        tfce_SobelZ[start:end] = (tfce_temp[start:end] * (zval_temp[start:end].max() / 100) * dens)
-        if randomise:
-            _append("perm_maxTFCE_surf%d_%s_zstat.csv" % (surf_count, medtype), np.nanmax(tfce_SobelZ[start:end]))
-        else:
-            print("Max Sobel Z tfce value for surface %s:\t %1.5f" % (surf_count, np.nanmax(tfce_SobelZ[start:end])))
-    if verbose:
-        print("Max Zstat tfce from all surfaces = %f" % tfce_SobelZ.max())
-    if randomise:
+        for s in range(len(masking_array)):
+            _append("perm_maxTFCE_surf%d_%s_zstat.csv" % (s, medtype), (res[s],))
         print("Interation number: %d" % perm_number)
         return None
-    return (SobelZ.astype(np.float32, order="C"), tfce_SobelZ.astype(np.float32, order="C"))
+    SobelZ, tfce_SobelZ = res
+    for s in range(len(masking_array)):
+        a, b = position_array[s], position_array[s + 1]
+        print("Max Sobel Z tfce value for surface %s:\t %1.5f" % (s, np.nanmax(tfce_SobelZ[a:b])))
+    if verbose:
+        print("Max Zstat tfce from all surfaces = %f" % tfce_SobelZ.max())
+    return SobelZ, tfce_SobelZ
 
 
 def low_ram_calculate_mediation_tfce(medtype, data, mask, pred_x, depend_y, calcTFCE, vdensity, set_surf_count=0,
                                      perm_number=None, randomise=False, no_intercept=True, output_dir=None,
                                      perm_seed=None):
     """mmr-lr mediation, one surface (tm_func.py:269-305)."""
+    eng = _lowram_engine(data, mask, calcTFCE, vdensity, False)
+    seed = None
     if randomise:
-        pred_x, depend_y = _permute_mediation(medtype, pred_x, depend_y, data.shape[0], perm_number, perm_seed)
-    SobelZ = calc_sobelz(medtype, pred_x, depend_y, data, data.shape[0], data.shape[1])
-    SobelZ = SobelZ.astype(np.float32, order="C")
-    zval = np.zeros_like((mask)).astype(np.float32, order="C")
-    zval[mask == 1] = SobelZ
-    zval = zval.astype(np.float32, order="C")
-    tfce_zval = np.zeros_like(zval).astype(np.float32, order="C")
-    calcTFCE.run(zval, tfce_zval)
-    zval = zval[mask == 1]
-    tfce_zval = tfce_zval[mask == 1]
-    tfce_zval = (tfce_zval * (zval.max() / 100) * vdensity)
-    if randomise:
-        name = "perm_maxTFCE_surf%d_%s_zstat.csv" % (set_surf_count, medtype)
-        permfile = "%s/%s" % (output_dir, name) if output_dir is not None else name
-        _append(permfile, np.nanmax(tfce_zval))
-    else:
-        return (zval.astype(np.float32, order="C"), tfce_zval.astype(np.float32, order="C"))
+        seed = perm_number + perm_seed if perm_seed is not None else _time_seed(perm_number)
+    res = _mediation(eng, medtype, pred_x, depend_y, data.shape[0], seed, randomise)
+    if not randomise:
+        return res
+    name = "perm_maxTFCE_surf%d_%s_zstat.csv" % (set_surf_count, medtype)
+    _append("%s/%s" % (output_dir, name) if output_dir is not None else name, (res[0],))
 
 
+# ---------------------------------------------------------------------------------------------- mixed settings
 def calc_mixed_tfce(assigntfcesettings, merge_y, masking_array, position_array, vdensity, pred_x, calcTFCE,
                     perm_number=None, randomise=False, medtype=None, depend_y=None):
-    """One calculate_tfce per (H, E) group (tm_func.py:327-378).  NB: the reference
-    compares a Python list with an int here, so callers must pass an ndarray for it to select anything;
-    the same requirement holds here."""
-    assigntfcesettings = np.asarray(assigntfcesettings)
-    tvals = tfce_tvals = neg_tfce_tvals = None
-    for i in np.unique(assigntfcesettings):
-        data_mask = np.zeros(merge_y.shape[1], dtype=bool)
-        extract_range = np.argwhere(assigntfcesettings == i)
-        for surface in extract_range:
-            data_mask[position_array[int(surface)]:position_array[int(surface) + 1]] = True
-        subset_merge_y = merge_y[:, data_mask]
-        try:
-            temp_vdensity = vdensity[data_mask]
-        except Exception:
-            temp_vdensity = 1
-        sub_masks = [m for m, a in zip(masking_array, assigntfcesettings) if a == i]
-        args = (subset_merge_y, sub_masks, pred_x, calcTFCE[i], temp_vdensity, create_position_array(sub_masks),
+    """One calculate_tfce per (H, E) group (tm_func.py:327-378): the surfaces of a group form their own merged graph
+    (calcTFCE[i]) and hence their own threshold group.  Two notes on the reference: it compares `assigntfcesettings == i`,
+    which selects nothing for a Python list -- lists are accepted here; and its three return values
+    are one aliased array (`tvals = tfce_tvals = neg_tfce_tvals = np.zeros(...)`, :368), so it really returns the
+    negative TFCE values three times -- here the three arrays are what their names say."""
+    assign = np.asarray(assigntfcesettings)
+    tvals = pos = neg = None
+    for i in np.unique(assign):
+        members = np.flatnonzero(assign == i)
+        cols = np.concatenate([np.arange(position_array[s], position_array[s + 1]) for s in members])
+        key = ("mixed", int(i), id(merge_y))
+        sub = _SUBSETS.get(key)
+        if sub is None or sub[0]() is not merge_y:
+            arr = np.ascontiguousarray(merge_y[:, cols])
+            dens = vdensity if np.ndim(vdensity) == 0 else np.ascontiguousarray(np.asarray(vdensity)[cols])
+            sub = (weakref.ref(merge_y), arr, dens)
+            _SUBSETS[key] = sub
+        sub_masks = [masking_array[s] for s in members]
+        args = (sub[1], sub_masks, pred_x, calcTFCE[int(i)], sub[2], create_position_array(sub_masks),
                 create_full_mask(sub_masks))
         if randomise:
-            calculate_tfce(*args, set_surf_count=extract_range, perm_number=perm_number, randomise=True,
+            calculate_tfce(*args, set_surf_count=members, perm_number=perm_number, randomise=True,
                            print_interation=(i == 0))
         else:
-            t, p, q = calculate_tfce(*args, set_surf_count=extract_range)
+            t, p, q = calculate_tfce(*args, set_surf_count=members)
             if tvals is None:
                 tvals = np.zeros((t.shape[0], merge_y.shape[1]))
-                tfce_tvals = np.zeros_like(tvals)
-                neg_tfce_tvals = np.zeros_like(tvals)
-            tvals[:, data_mask] = t
-            tfce_tvals[:, data_mask] = p
-            neg_tfce_tvals[:, data_mask] = q
+                pos, neg = np.zeros_like(tvals), np.zeros_like(tvals)
+            tvals[:, cols], pos[:, cols], neg[:, cols] = t, p, q
     if not randomise:
-        return tvals, tfce_tvals, neg_tfce_tvals
+        return tvals, pos, neg
+
+
+_SUBSETS = {}       # column subsets of calc_mixed_tfce, kept so that the engine cache recognises them on the next call
 
 
 def find_nearest(array, value, p_array):

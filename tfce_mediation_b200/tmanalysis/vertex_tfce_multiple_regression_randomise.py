@@ -85,6 +85,13 @@ def run(opts):
             results.append(eng.regression_blocks(X, np.stack(idx), block=C.BLOCK).max(axis=2))
         C.tick("shuffles (fit + TFCE + max)")
     else:
+        # the reference permutes the chosen columns of X IN PLACE, so shuffle i sees the composition of all draws since
+        # the start of the range (:93-97); a rank whose slice starts later replays the draws it skipped (RNG calls and
+        # an index gather only), so the rows are the same for any number of ranks
+        s0, s1 = opts.specifyvars[0], opts.specifyvars[1] + 1
+        for iter_perm in range(first, a):
+            np.random.seed(C.reference_seed(iter_perm, opts.seed))
+            X[:, s0:s1] = X[:, s0:s1][C.draw_row_permutation(n)]
         for p0, p1 in C.chunks(a, b):
             designs = []
             for iter_perm in range(p0, p1 + 1):
