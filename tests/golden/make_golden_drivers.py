@@ -264,6 +264,53 @@ def main():
             os.chdir(cwd)
     tm_func.np = np
     np.savez_compressed(os.path.join(HERE, "mmr_full.npz"), **mm)
+
+    # ================= the `mmr -p a b` flow on a TMI container (tm_multimodality_multisurface_regression.py:409-572) ====
+    # The driver itself needs nibabel/matplotlib objects at import; its randomise branch is a straight sequence of
+    # reference functions, called here in its order: read_tm_filetype -> create_position_array -> merge_adjacency_array
+    # -> CreateAdjSet -> create_full_mask -> density weights (:449-459) -> calculate_tfce / calculate_mediation_tfce.
+    tm_io = importlib.import_module("tfce_mediation.tm_io")
+    tmi = os.path.join(HERE, "sample.tmi")
+    _, image_array, masking_array, _, _, _, _, _, adjacency_array, _, _ = tm_io.read_tm_filetype(tmi, verbose=False)
+    position_array = tm_func.create_position_array(masking_array)
+    adjacent_range = list(range(len(adjacency_array)))
+    calc = ref_tfce.CreateAdjSet(2.0, 0.67, tm_func.merge_adjacency_array(adjacent_range, adjacency_array))
+    fullmask = tm_func.create_full_mask(masking_array)
+    vdensity = []
+    for i in range(len(masking_array)):
+        temp_vdensity = np.zeros((adjacency_array[adjacent_range[i]].shape[0]))
+        for j in range(adjacency_array[adjacent_range[i]].shape[0]):
+            temp_vdensity[j] = len(adjacency_array[adjacent_range[i]][j])
+        if masking_array[i].shape[2] == 1:
+            temp_vdensity = temp_vdensity[masking_array[i][:, 0, 0] == True]   # noqa: E712
+        vdensity = np.hstack((vdensity, np.array((1 - (temp_vdensity / temp_vdensity.max()) + (temp_vdensity.mean() / temp_vdensity.max())), dtype=np.float32)))
+    nsub = image_array[0].shape[1]
+    dpred = rs.standard_normal(nsub)
+    ddep = 0.5 * dpred + rs.standard_normal(nsub)
+    mapped_y = image_array[0].T.astype(np.float32, order="C")
+    md = dict(pred=dpred, dep=ddep, time_offset=25)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            for pn in range(1, 5):
+                tm_func.calculate_tfce(mapped_y, masking_array, dpred, calc, vdensity, position_array, fullmask,
+                                       perm_number=pn, randomise=True)
+            for sf in range(len(masking_array)):
+                md["rows_surf%d_tcon1" % sf] = read_rows("perm_maxTFCE_surf%d_tcon1.csv" % sf)
+        finally:
+            os.chdir(cwd)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            for pn in range(1, 5):
+                with np.errstate(all="ignore"):
+                    tm_func.calculate_mediation_tfce("M", mapped_y, masking_array, dpred, ddep, calc, vdensity, position_array,
+                                                     fullmask, perm_number=pn, randomise=True)
+            for sf in range(len(masking_array)):
+                md["med_rows_surf%d" % sf] = read_rows("perm_maxTFCE_surf%d_M_zstat.csv" % sf)
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "mmr_driver.npz"), **md)
     print("driver / mmr goldens written to", HERE)
 
 
