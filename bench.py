@@ -548,7 +548,10 @@ def run_b200(args):
     fit_rows = 3 if w["kind"] == "mediation" else 1             # pseudo-inverse rows per shuffle (path A: 1, path B: 2)
     t32b = [torch.empty((P, C, ld), dtype=torch.float32, device=dev) for _ in range(2)]
     out_max = torch.empty((P * C, S, 2), dtype=torch.float32, device=dev)
-    gathered = [torch.empty_like(out_max) for _ in range(world)] if world > 1 else None
+    comm = None
+    if world > 1:
+        from tfce_mediation_b200 import parallel
+        comm = parallel.MaxComm.get()          # tmb_allgather_max behind the C ABI (NCCL over NVLink)
     fit_events = []
 
     def fit(s, buf):
@@ -582,10 +585,10 @@ def run_b200(args):
             if tfce_events is not None:
                 b.record(); tfce_events.append((a, b))
             if world > 1 and args.gather == "step":
-                dist.all_gather(gathered, out_max)   # the per-shuffle maxima, tiny (NCCL over NVLink)
+                comm.allgather(out_max)              # the per-shuffle maxima, tiny (NCCL over NVLink)
             tk = nxt
         if world > 1 and args.gather != "step":
-            dist.all_gather(gathered, out_max)       # one collective per job
+            comm.allgather(out_max)                  # one collective per job
 
     run_steps(0, args.warmup)
     barrier()
@@ -617,8 +620,7 @@ def run_b200(args):
     e0.record()
     res = e2e_call(idx_timed)                                        # numpy on the host
     if world > 1:
-        last = torch.from_numpy(np.ascontiguousarray(res[-P:])).to(dev)
-        dist.all_gather([torch.empty_like(last) for _ in range(world)], last)
+        comm.allgather(torch.from_numpy(np.ascontiguousarray(res, dtype=np.float32)).to(dev))   # the job's maxima, once
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -702,7 +704,8 @@ def run_b200(args):
                        "ref_permutations_per_shuffle": signs,
                        "l2": "inputs larger than L2 (Y %.0f MB, statistic maps %.0f MB per step)"
                              % (eng.Y.t.numel() * eng.Y.t.element_size() / 1e6, t32b[0].numel() * 4 / 1e6),
-                       "parallelism": "perm-shard x%d" % world, "gather": args.gather},
+                       "parallelism": "perm-shard x%d" % world,
+                       "gather": "tmb_allgather_max (NCCL behind the C ABI), once per %s" % ("step" if args.gather == "step" else "timed region")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes // args.steps,
                     "d2h_bytes_per_step": eng.d2h_bytes // args.steps, "ms_per_step": e2e_ms / args.steps,
@@ -726,6 +729,7 @@ def run_b200(args):
         }
         emit(line)
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
 
 

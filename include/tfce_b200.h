@@ -252,6 +252,22 @@ int tmb_voxel_adjacency(int device, const uint8_t *mask_host, int nx, int ny, in
 int tmb_fwe_lookup(const double *sorted_max_dev, int n, const float *values_dev, int64_t m, double *corrp_dev,
                    void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU collection of the per-shuffle maxima (replaces the reference's `echo ... >> perm_*.csv` from N worker
+ * processes, STEP_2_tfce_randomise_parallel.py:139-157 + pyfunc.py:119).  One process per GPU; every rank owns a
+ * contiguous slice of the permutation range; ONE all-gather per job over NCCL / NVLink.
+ *   tmb_comm_unique_id: rank 0 obtains the 128-byte NCCL id and ships it to the other ranks by any host channel
+ *   tmb_comm_create:    collective over all ranks
+ *   tmb_allgather_max:  global_dev[r*count + i] = rank r's local_dev[i]  (count floats per rank; short slices are
+ *                       zero-padded by the caller, whose shard rule tells it every rank's real count)
+ * NCCL is bound at run time (dlopen libnccl.so.2); processes that never call these never load it.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct tmb_comm tmb_comm;
+int tmb_comm_unique_id(void *id_out128);
+int tmb_comm_create(const void *id128, int rank, int world, int device, tmb_comm **out);
+int tmb_comm_destroy(tmb_comm *c);
+int tmb_allgather_max(tmb_comm *c, const float *local_dev, int64_t count, float *global_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

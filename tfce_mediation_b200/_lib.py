@@ -64,6 +64,10 @@ SIGNATURES = {
     "tmb_sobelz": (_int, [_vp, _int, _int, _i64, _i64, _vp, _i64, _int, _vp, _vp, _int, _int, _f64, _vp, _vp, _int,
                           _int, _f64, _vp, _vp, _int, _int, _vp, _vp, _i64, _int, _vp]),
     "tmb_fwe_lookup": (_int, [_vp, _int, _vp, _i64, _vp, _vp]),
+    "tmb_comm_unique_id": (_int, [_vp]),
+    "tmb_comm_create": (_int, [_vp, _int, _int, _int, _c.POINTER(_vp)]),
+    "tmb_comm_destroy": (_int, [_vp]),
+    "tmb_allgather_max": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "tmb_voxel_adjacency": (_int, [_int, _vp, _int, _int, _int, _int, _int, _c.POINTER(_i32), _c.POINTER(_i64),
                                    _vp, _vp]),
 }

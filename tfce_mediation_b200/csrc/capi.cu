@@ -429,7 +429,7 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
             for (double x : w) ok = ok && std::isfinite(x) && x >= 0.0;
             std::vector<double> vals(w);
             std::sort(vals.begin(), vals.end());
-            vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+            vals.resize((size_t)(std::unique(vals.begin(), vals.end()) - vals.begin()));
             if (ok && vals.size() <= 65535) {
                 std::vector<unsigned short> rk((size_t)g->V);
                 for (int32_t i = 0; i < g->V; ++i)
@@ -457,7 +457,7 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
             for (float x : w) ok = ok && std::isfinite(x) && x >= 0.0f;
             std::vector<float> vals(w);
             std::sort(vals.begin(), vals.end());
-            vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+            vals.resize((size_t)(std::unique(vals.begin(), vals.end()) - vals.begin()));
             if (ok && vals.size() <= 65535) {
                 std::vector<unsigned short> rk((size_t)g->V);
                 for (int32_t i = 0; i < g->V; ++i)

@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
                 if (fast) tf = t32_fast(beta, sse, dscale, slow);
                 double t = 0.0;
                 if (slow) { // exact path: fp64 outputs requested, or the fast value is too close to an fp32 rounding boundary
-                    t = t_from_scaled(beta, sse, dscale);
+                    t = p.exact_epilogue == 2 ? t_from(beta, sse, p.dof, p.d[perm]) : t_from_scaled(beta, sse, dscale);
                     if (p.nan_to_zero && t != t) t = 0.0;
                     tf = __double2float_rn(t);
                 }
@@ -1071,7 +1071,7 @@ int launch_glm(const GlmParams &p, cudaStream_t stream) {
             if (p.mode == 0 && p.r == 1 && p.rp == 1 && p.row0 == 0 && p.nrows == 1) {
                 const char *ep = getenv("TMB_GLM_EPILOGUE");
                 GlmParams q = p;
-                q.exact_epilogue = ep && strcmp(ep, "exact") == 0;
+                q.exact_epilogue = !ep ? 0 : strcmp(ep, "exact") == 0 ? 1 : strcmp(ep, "reforder") == 0 ? 2 : 0; // reforder: (sse / dof) * d
                 return launch_dmma<float>(q, stream);
             }
             switch (p.rp) {

@@ -185,7 +185,7 @@ def run(opts):
     if idx:
         results.append(eng.regression_blocks(X, np.stack(idx), block=C.BLOCK))  # [P, C, S, 2]
     local = np.concatenate(results, axis=0) if results else np.zeros((0, k - 1, len(surfs), 2), dtype=np.float32)
-    allrows = parallel.gather_rows(local)
+    allrows = C.gather(local)
     if rank == 0:
         for si, sn in enumerate(surfaces):
             for c in range(k - 1):
@@ -214,7 +214,7 @@ def run_mediation(opts, y, surfs, surfaces, med, start_time):
     rows = [eng.mediation_block(medtype, pred_x, depend_y, np.stack(idx[i:i + C.BLOCK]))
             for i in range(0, len(idx), C.BLOCK)]
     local = np.concatenate(rows, axis=0) if rows else np.zeros((0, len(surfs)), dtype=np.float32)
-    allrows = parallel.gather_rows(local.reshape(local.shape[0], 1, -1))
+    allrows = C.gather(local.reshape(local.shape[0], 1, -1))
     if rank == 0:
         for si, sn in enumerate(surfaces):
             C.append_rows("%s/perm_maxTFCE_surf%d_%s_zstat.csv" % (outdir, sn, medtype), allrows[:, 0, si], "%f")

@@ -182,7 +182,7 @@ def run(opts):
         if opts.inputmediation:
             local = (eng.mediation_blocks(medtype, pred_x, depend_y, idx, block=C.BLOCK) if len(idx)
                      else np.zeros((0, len(members)), dtype=np.float32))
-            allrows = parallel.gather_rows(local.reshape(local.shape[0], 1, -1))
+            allrows = C.gather(local.reshape(local.shape[0], 1, -1))
             if rank == 0:
                 for si, s in enumerate(members):
                     C.append_rows("%s/perm_maxTFCE_surf%d_%s_zstat.csv" % (outdir, s, medtype), allrows[:, 0, si], "%f")
@@ -190,7 +190,7 @@ def run(opts):
             X = np.column_stack([np.ones(n), pred_x])
             local = (eng.regression_blocks(X, idx, block=C.BLOCK) if len(idx)
                      else np.zeros((0, X.shape[1] - 1, len(members), 2), dtype=np.float32))
-            allrows = parallel.gather_rows(local)
+            allrows = C.gather(local)
             if rank == 0:
                 for si, s in enumerate(members):
                     for c in range(X.shape[1] - 1):

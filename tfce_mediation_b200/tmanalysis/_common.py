@@ -76,12 +76,22 @@ def setup():
     return parallel.setup()
 
 
+_SHARD_COUNTS = [None]
+
+
 def shard(first, last):
     rank, ws, _ = parallel.world()
     if ws > 1:
         parallel.setup()
     a, b = parallel.shard_range(first, last, rank, ws)
+    _SHARD_COUNTS[0] = parallel.shard_counts(first, last, ws)      # every rank's row count, known without communication
     return rank, ws, a, b
+
+
+def gather(local_rows):
+    """All-gather of the per-shuffle rows of the last shard(): ONE collective per job (tmb_allgather_max behind the C ABI
+    on NCCL; torch.distributed on gloo)."""
+    return parallel.gather_rows(np.ascontiguousarray(local_rows, dtype=np.float32), counts=_SHARD_COUNTS[0])
 
 
 def chunks(a, b, size=BLOCK):

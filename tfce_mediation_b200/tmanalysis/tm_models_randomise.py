@@ -111,9 +111,9 @@ def run(opts):
         if t is not None:
             res_t.append(t.max(axis=2))                 # [P, ncon, 2]
     nvar, ncon = len(kvars), int(sum(kvars))
-    all_f = parallel.gather_rows(np.concatenate(res_f, axis=0) if res_f else np.zeros((0, nvar), dtype=np.float32)) \
+    all_f = C.gather(np.concatenate(res_f, axis=0) if res_f else np.zeros((0, nvar), dtype=np.float32)) \
         if stat != "t" else None
-    all_t = parallel.gather_rows(np.concatenate(res_t, axis=0) if res_t else np.zeros((0, ncon, 2), dtype=np.float32)) \
+    all_t = C.gather(np.concatenate(res_t, axis=0) if res_t else np.zeros((0, ncon, 2), dtype=np.float32)) \
         if stat != "f" else None
     if rank == 0:
         if all_t is not None:
@@ -180,7 +180,7 @@ def run_mediation(opts, start_time):
         res.append(eng.tm_models_mediation_block(medtype, dmy_leftvar, dmy_rightvar, dmy_covariates,
                                                  np.stack(idx[c0:c0 + C.BLOCK])).max(axis=1))
     local = np.concatenate(res, axis=0) if res else np.zeros((0,), dtype=np.float32)
-    allrows = parallel.gather_rows(local)
+    allrows = C.gather(local)
     if rank == 0:
         C.append_rows("%s/perm_Zstat_%s_TFCE_%s.csv" % (outdir, medtype, suffix), allrows, "%.4f")
         print("Finished. Randomization took %.1f seconds" % (time() - start_time))

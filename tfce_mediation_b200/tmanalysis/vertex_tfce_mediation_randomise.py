@@ -63,7 +63,7 @@ def run(opts):
         mx = eng.mediation_block(medtype, pred_x, depend_y, np.stack(idx))     # [P, S]
         results.append(mx.max(axis=1))
     local = np.concatenate(results) if results else np.zeros((0,), dtype=np.float32)
-    allrows = parallel.gather_rows(local.reshape(-1, 1))
+    allrows = C.gather(local.reshape(-1, 1))
     if rank == 0:
         C.append_rows("%s/perm_Zstat_%s_TFCE_maxVertex.csv" % (outdir, medtype), allrows.reshape(-1), "%.4f")
         print("Finished. Randomization took %.1f seconds" % (time() - start_time))

@@ -102,7 +102,7 @@ def run(opts):
             mx = eng.regression_block(None, designs=np.stack(designs))
             results.append(mx.max(axis=2))             # max over the two hemispheres -> [P, C, 2]
     local = np.concatenate(results, axis=0) if results else np.zeros((0, k - 1, 2), dtype=np.float32)
-    allrows = parallel.gather_rows(local)
+    allrows = C.gather(local)
     C.tick("all-gather of the maxima")
     if rank == 0:
         for j in range(ncon):                          # the reference writes contrasts 1..ncon (:108-117)

@@ -51,7 +51,7 @@ def run(opts):
             idx.append(C.draw_row_permutation(n))
         results.append(eng.mediation_block(medtype, pred_x, depend_y, np.stack(idx))[:, 0])
     local = np.concatenate(results) if results else np.zeros((0,), dtype=np.float32)
-    allrows = parallel.gather_rows(local.reshape(-1, 1))
+    allrows = C.gather(local.reshape(-1, 1))
     if rank == 0:
         C.append_rows("%s/perm_Zstat_%s_TFCE_maxVoxel.csv" % (outdir, medtype), allrows.reshape(-1), "%1.4f")
         print("Finished. Randomization took %.1f seconds" % (time() - start_time))

@@ -69,7 +69,7 @@ def run(opts):
             stat = torch.from_numpy(np.sqrt(f).astype(np.float32)[None, :]).cuda()
             mx, _, _ = plan.run(stat, two_sided=False)
             rows.append(mx[0, 0, 0].item())
-        allrows = parallel.gather_rows(np.asarray(rows, dtype=np.float32).reshape(-1, 1))
+        allrows = C.gather(np.asarray(rows, dtype=np.float32).reshape(-1, 1))
         if rank == 0:
             C.append_rows("%s/perm_fstat_TFCE_maxVoxel.csv" % outdir, allrows.reshape(-1), "%1.4f")
             print("Finished. Randomization took %.1f seconds" % (time() - start_time))
@@ -107,7 +107,7 @@ def run(opts):
                 designs.append(X.copy())
             results.append(eng.regression_block(None, designs=np.stack(designs))[:, :, 0, :])   # [P, C, 2]
     local = np.concatenate(results, axis=0) if results else np.zeros((0, k - 1, 2), dtype=np.float32)
-    allrows = parallel.gather_rows(local)
+    allrows = C.gather(local)
     if rank == 0:
         for j in range(ncon):
             C.append_rows("%s/perm_tstat_con%d_TFCE_maxVoxel.csv" % (outdir, j + 1), allrows[:, j, :].reshape(-1),
