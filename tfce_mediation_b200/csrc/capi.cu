@@ -761,6 +761,10 @@ extern "C" int tmb_threshold_tables(const float *maxima_host, const float *H_hos
                         HH_host + (size_t)i * 128, status_host + i);
     };
     int nt = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) {   // one process per GPU (torchrun): share the host cores between the ranks
+        const int ranks = std::max(1, atoi(lw));
+        nt = std::max(1, std::min(nt, (int)std::thread::hardware_concurrency() / (2 * ranks)));
+    }
     if (const char *e = getenv("TMB_TABLE_THREADS")) nt = std::max(1, atoi(e));
     if (count < 256 || nt == 1) { work(0, count); return 0; }
     std::vector<std::thread> pool;

@@ -12,6 +12,7 @@
 // keeping the reference's fp32 rounding of se (cynumstats.pyx:49-51).
 #include "common.cuh"
 
+#include <cuda.h>   // CUtensorMap and the cuTensorMapEncodeTiled prototype only: the entry point is fetched at run time
 #include <cstdlib>
 #include <cstring>
 
@@ -63,6 +64,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
+// 2-D tiled TMA load (cp.async.bulk.tensor -> UTMALDG): one instruction brings a [rows x box] tile of a row-major matrix
+// into shared memory and completes `bytes` on the mbarrier.  The box is four (A, fp64) / eight (Y, fp32) elements WIDER
+// than the tile the CTA uses: TMA packs box rows densely, so the box width IS the shared-memory row pitch, and the
+// extra columns give exactly the padded pitch whose fragment loads take the minimum number of wavefronts.
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *tmap, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+
 struct GlmParams {
     const void *Y; int y_is_f64; int n; int64_t V; int64_t ldy;
     const double *At; int64_t ldA;
@@ -80,6 +93,7 @@ struct GlmParams {
     // stored one after the other (k_i x k_i each, msz doubles per design); variable i covers rows [var_lo[i], +var_k[i])
     const double *M; int msz, nvar; int var_lo[8], var_k[8];
     int exact_epilogue;                 // DMMA kernel: always take the fp64 square root / division (TMB_GLM_EPILOGUE=exact)
+    int use_tma;                        // DMMA kernels: operands arrive by 2-D tensor-map loads (else one bulk copy per row)
     int layout;                         // column order of At: 0 = p * rp + i (DFMA tile kernel); 1 = "tile8": 8 designs x rp
                                         // regressors per block, column (p / 8) * 8 * rp + i * 8 + p % 8 (DMMA kernels)
 };
@@ -429,7 +443,8 @@ __device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, doubl
 }
 
 template <typename YT>
-__global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtiles) {
+__global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtiles, const __grid_constant__ CUtensorMap tmA,
+                                                          const __grid_constant__ CUtensorMap tmY) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sA = reinterpret_cast<double *>(smem_raw);                                  // [DSTAGES][DK][DPA]
     YT *sY = reinterpret_cast<YT *>(smem_raw + sizeof(double) * DSTAGES * DK * DPA);    // [DSTAGES][DK][DPY]
@@ -456,6 +471,15 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
         mbar_wait(empty + s, (round & 1) ^ 1);
         const int k0 = kc * DK;
         const int rows = min(DK, p.n - k0);
+        if (p.use_tma) {
+            // two tensor-map loads per chunk, issued by warp 0 alone; rows beyond n arrive as zeros (out-of-bounds fill)
+            if (warp == 0) {
+                mbar_expect_tx(full + s, (uint32_t)DK * (DPA * 8 + DPY * (uint32_t)sizeof(YT)));
+                tma_load_2d(sA + (size_t)s * DK * DPA, &tmA, m0, k0, full + s);
+                tma_load_2d(sY + (size_t)s * DK * DPY, &tmY, (int)v0, k0, full + s);
+            }
+            return;
+        }
         if (warp == 0) mbar_expect_tx(full + s, (uint32_t)rows * (DM * 8 + DN * (uint32_t)sizeof(YT)));
         for (int kk = warp; kk < rows; kk += 8) { // lane 0 of every warp issues an eighth of the row copies (see glm_tile_kernel)
             bulk_g2s(sA + ((size_t)s * DK + kk) * DPA, p.At + (size_t)(k0 + kk) * p.ldA + m0, DM * 8, full + s);
@@ -463,7 +487,8 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
                      DN * (uint32_t)sizeof(YT), full + s);
         }
     };
-    if (lane == 0)
+    const bool issuer = lane == 0 && (warp == 0 || !p.use_tma);   // tensor-map loads: warp 0 alone feeds the ring
+    if (issuer)
         for (int kc = 0; kc < DSTAGES - 1 && kc < nchunks; ++kc) issue_chunk(kc);
 
     const int wm = warp >> 2, wn = warp & 3;      // warp tile: rows wm*32.., cols wn*32..
@@ -477,7 +502,7 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
     for (int kc = 0; kc < nchunks; ++kc) {
         const int s = kc % DSTAGES;
         const int round = kc / DSTAGES;
-        if (lane == 0 && kc + DSTAGES - 1 < nchunks) issue_chunk(kc + DSTAGES - 1);
+        if (issuer && kc + DSTAGES - 1 < nchunks) issue_chunk(kc + DSTAGES - 1);
         mbar_wait(full + s, round & 1);
         const int rows = min(DK, p.n - kc * DK);
         const double *a_st = sA + (size_t)s * DK * DPA + wm * 32 + g;
@@ -539,6 +564,44 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
     }
 }
 
+
+// ---------------------------------------------------------------- tensor maps for the DMMA kernels' operands
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char *off = getenv("TMB_GLM_TMA");     // "0": one bulk copy per operand row instead (A/B measurements)
+        if (!(off && off[0] == '0')) {
+            void *sym = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+                q == cudaDriverEntryPointSuccess)
+                fn = reinterpret_cast<EncodeTiledFn>(sym);
+            else
+                cudaGetLastError();
+        }
+    }
+    return fn;
+}
+
+// row-major [rows, ld] matrix of fp64 / fp32 elements, box = box_cols x box_rows (inner dimension first)
+static bool make_tmap(CUtensorMap *m, const void *base, bool f64, int64_t ld, int64_t rows, int box_cols, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * (f64 ? 8u : 4u)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims,
+              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename YT>
 static int launch_dmma(const GlmParams &p, cudaStream_t stream) {
     const int mtiles = (p.P + DM - 1) / DM;
@@ -547,7 +610,11 @@ static int launch_dmma(const GlmParams &p, cudaStream_t stream) {
     TMB_REQUIRE(tiles < (int64_t)INT32_MAX, "glm: too many tiles");
     const size_t smem = sizeof(double) * DSTAGES * DK * DPA + sizeof(YT) * DSTAGES * DK * DPY + sizeof(uint64_t) * 2 * DSTAGES;
     TMB_CUDA(cudaFuncSetAttribute(glm_dmma_kernel<YT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    glm_dmma_kernel<YT><<<(unsigned)tiles, 256, smem, stream>>>(p, mtiles);
+    GlmParams q = p;
+    CUtensorMap tmA, tmY;
+    memset(&tmA, 0, sizeof(tmA)); memset(&tmY, 0, sizeof(tmY));
+    q.use_tma = make_tmap(&tmA, p.At, true, p.ldA, p.n, DPA, DK) && make_tmap(&tmY, p.Y, sizeof(YT) == 8, p.ldy, p.n, DPY, DK);
+    glm_dmma_kernel<YT><<<(unsigned)tiles, 256, smem, stream>>>(q, mtiles, tmA, tmY);
     count_launch();
     TMB_CUDA(cudaGetLastError());
     return 0;
@@ -667,7 +734,8 @@ __device__ __forceinline__ void dmma_vertex_stats(const GlmParams &p, int perm, 
 }
 
 template <int RP, typename YT>
-__global__ void __launch_bounds__(256, 2) glm_dmma_multi_kernel(GlmParams p, int mtiles) {
+__global__ void __launch_bounds__(256, 2) glm_dmma_multi_kernel(GlmParams p, int mtiles, const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmY) {
     constexpr int MT = DmmaShape<RP>::MT, NT = DmmaShape<RP>::NT, WM = DmmaShape<RP>::WM;
     constexpr int DM = DmmaShape<RP>::ROWS, DPA = DmmaShape<RP>::PITCH;   // shadow the r == 1 kernel's constants
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -696,6 +764,14 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_multi_kernel(GlmParams p, int
         mbar_wait(empty + s, (round & 1) ^ 1);
         const int k0 = kc * DK;
         const int rows = min(DK, p.n - k0);
+        if (p.use_tma) {
+            if (warp == 0) {
+                mbar_expect_tx(full + s, (uint32_t)DK * (DPA * 8 + DPY * (uint32_t)sizeof(YT)));
+                tma_load_2d(sA + (size_t)s * DK * DPA, &tmA, m0, k0, full + s);
+                tma_load_2d(sY + (size_t)s * DK * DPY, &tmY, (int)v0, k0, full + s);
+            }
+            return;
+        }
         if (warp == 0) mbar_expect_tx(full + s, (uint32_t)rows * (DM * 8 + DN * (uint32_t)sizeof(YT)));
         for (int kk = warp; kk < rows; kk += 8) {
             bulk_g2s(sA + ((size_t)s * DK + kk) * DPA, p.At + (size_t)(k0 + kk) * p.ldA + m0, DM * 8, full + s);
@@ -703,7 +779,8 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_multi_kernel(GlmParams p, int
                      DN * (uint32_t)sizeof(YT), full + s);
         }
     };
-    if (lane == 0)
+    const bool issuer = lane == 0 && (warp == 0 || !p.use_tma);   // tensor-map loads: warp 0 alone feeds the ring
+    if (issuer)
         for (int kc = 0; kc < DSTAGES - 1 && kc < nchunks; ++kc) issue_chunk(kc);
 
     const int wm = WM == 1 ? 0 : (warp >> 2), wn = WM == 1 ? warp : (warp & 3);
@@ -717,7 +794,7 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_multi_kernel(GlmParams p, int
     for (int kc = 0; kc < nchunks; ++kc) {
         const int s = kc % DSTAGES;
         const int round = kc / DSTAGES;
-        if (lane == 0 && kc + DSTAGES - 1 < nchunks) issue_chunk(kc + DSTAGES - 1);
+        if (issuer && kc + DSTAGES - 1 < nchunks) issue_chunk(kc + DSTAGES - 1);
         mbar_wait(full + s, round & 1);
         const int rows = min(DK, p.n - kc * DK);
         const double *a_st = sA + (size_t)s * DK * DPA + wm * (MT * 8) + g;
@@ -769,7 +846,11 @@ static int launch_dmma_multi(const GlmParams &p, cudaStream_t stream) {
     TMB_REQUIRE(p.ldA >= (int64_t)mtiles * DM, "glm: ldA must cover %lld columns", (long long)mtiles * DM);
     const size_t smem = sizeof(double) * DSTAGES * DK * DPA + sizeof(YT) * DSTAGES * DK * DPY + sizeof(uint64_t) * 2 * DSTAGES;
     TMB_CUDA(cudaFuncSetAttribute(glm_dmma_multi_kernel<RP, YT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    glm_dmma_multi_kernel<RP, YT><<<(unsigned)tiles, 256, smem, stream>>>(p, mtiles);
+    GlmParams q = p;
+    CUtensorMap tmA, tmY;
+    memset(&tmA, 0, sizeof(tmA)); memset(&tmY, 0, sizeof(tmY));
+    q.use_tma = make_tmap(&tmA, p.At, true, p.ldA, p.n, DPA, DK) && make_tmap(&tmY, p.Y, sizeof(YT) == 8, p.ldy, p.n, DPY, DK);
+    glm_dmma_multi_kernel<RP, YT><<<(unsigned)tiles, 256, smem, stream>>>(q, mtiles, tmA, tmY);
     count_launch();
     TMB_CUDA(cudaGetLastError());
     return 0;
