@@ -1,5 +1,3 @@
-(python -m pytest tests/test_gpu_glm.py tests/test_glm_typeI.py tests/test_gpu_golden.py -x -q -m gpu) 2>&1 | tail -3
-for t in 1 0; do TMB_GLM_TMA=$t python bench.py --steps 10 --no-cpu 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('TMA=$t config2', round(d['value']), 'fit', round(d['roofline']['fit']['ms_per_launch'],3), round(d['roofline']['fit']['achieved'],2))"; done
-for t in 1 0; do TMB_GLM_TMA=$t python bench.py --workload config4 --steps 6 --no-cpu 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('TMA=$t config4', round(d['value']), 'fit', round(d['roofline']['fit']['ms_per_launch'],3), round(d['roofline']['fit']['achieved'],2))"; done
+(python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_wide.py tests/test_gpu_weighted.py tests/test_gpu_tfce.py tests/test_gpu_fullsize.py tests/test_gpu_engine.py -x -q -m gpu) 2>&1 | tail -3
+python bench.py --steps 20 2>/dev/null > gpurun_out/r2v_config2.json; python -c "
+import json; d=json.load(open('gpurun_out/r2v_config2.json')); print('config2', round(d['value']), round(d['e2e']['value']), 'tfce', round(d['roofline']['kernel_ms_per_launch'],3), 'frac', round(d['roofline']['frac'],3), 'fit', round(d['roofline']['fit']['ms_per_launch'],3), d['cpu_baseline'])"

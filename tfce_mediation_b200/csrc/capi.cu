@@ -40,6 +40,7 @@ struct tmb_graph {
     double *d_powE = nullptr;
     int32_t *d_vmap = nullptr;          // internal -> caller index (nullptr: identity)
     int32_t *d_ell = nullptr;           // fixed-width adjacency rows (low-degree graphs)
+    int32_t *d_ell_self = nullptr;      // the same rows for width 8 with pad = the vertex itself (pipeline ascent kernel)
     int32_t ell_width = 0;
     int32_t max_degree = 0;
     // sliced rows (SELL-32-4, see SurfDesc): built on the host at creation for every symmetric graph of degree <= 256,
@@ -258,6 +259,13 @@ extern "C" int tmb_graph_create(int device, int32_t V, const int64_t *indptr, co
             if ((e = cudaMemcpy(g->d_ell, ell.data(), sizeof(int32_t) * ell.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
                 return fail("memcpy", e);
             g->ell_width = width;
+            if (width == 8) {
+                for (int32_t v = 0; v < V; ++v)
+                    for (int j = (int)(use_indptr[v + 1] - use_indptr[v]); j < 8; ++j) ell[(size_t)v * 8 + j] = v;
+                if ((e = cudaMalloc(&g->d_ell_self, sizeof(int32_t) * ell.size())) != cudaSuccess) return fail("malloc", e);
+                if ((e = cudaMemcpy(g->d_ell_self, ell.data(), sizeof(int32_t) * ell.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+                    return fail("memcpy", e);
+            }
         }
         // sliced rows (SELL-32-4) for everything else -- the reference's default geodesic adjacency sets have ~60
         // neighbours per vertex (STEP_1_vertex_tfce_multiple_regression.py:71-76,155-158) -- kept on the host until
@@ -303,7 +311,7 @@ extern "C" int tmb_graph_destroy(tmb_graph *g) {
     if (!g) return 0;
     DeviceGuard guard(g->device);
     if (g->self_plan) tmb_plan_destroy(g->self_plan);
-    cudaFree(g->d_indptr); cudaFree(g->d_indices); cudaFree(g->d_powE); cudaFree(g->d_vmap); cudaFree(g->d_ell); cudaFree(g->d_sell); cudaFree(g->d_sell_off);
+    cudaFree(g->d_indptr); cudaFree(g->d_indices); cudaFree(g->d_powE); cudaFree(g->d_vmap); cudaFree(g->d_ell); cudaFree(g->d_ell_self); cudaFree(g->d_sell); cudaFree(g->d_sell_off);
     cudaFree(g->d_image); cudaFree(g->d_enhn); cudaFree(g->d_labels); cudaFree(g->d_extents);
     cudaFree(g->d_status); cudaFree(g->d_thr); cudaFree(g->d_tabs);
     delete g;
@@ -473,7 +481,7 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
             }
         }
         SurfDesc d{};
-        d.indptr = g->d_indptr; d.indices = g->d_indices; d.ell = g->d_ell; d.ell_width = g->ell_width;
+        d.indptr = g->d_indptr; d.indices = g->d_indices; d.ell = g->d_ell; d.ell_width = g->ell_width; d.ell_self = g->d_ell_self;
         d.sell = p->pipe_words ? g->d_sell : nullptr; d.sell_off = p->pipe_words ? g->d_sell_off : nullptr;
         d.wrank = p->d_wrank[s]; d.wtab = p->d_wtab[s]; d.weight64 = p->d_weights64[s]; d.wtab64 = p->d_wtab64[s];
         d.powE = g->d_powE; d.weight = p->d_weights[s]; d.vmap = g->d_vmap; d.col_off = col_offset[s]; d.V = g->V; d.H = g->H;
@@ -645,6 +653,8 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
     int fit = 0;
     const bool class_path = tfce_pos || tfce_neg || (p->pipe_weights && !p->pipe_wfast);
     if (pipeline) fit = pipe_ensure(p, B * p->S, class_path) / p->S; // statistic rows per pipeline pass
+    if (pipeline && fit >= 1)
+        if (const char *wv = getenv("TMB_PIPE_WAVE")) { const int v = atoi(wv); if (v >= 1) fit = std::min(fit, v); } // experiments
     if (!pipeline || fit < 1)
         return plan_launch_sweep(p, stat, ld, B, two_sided, accumulate, max_dev, tfce_pos, tfce_neg, status, stop_level,
                                  labels, extents, thr, stream, tabs, nullptr);
@@ -700,6 +710,8 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
         pp.timing = p->d_timing;
         pp.max_degree = 0;
         pp.sell_words = p->pipe_words;
+        pp.ell_self = 1;
+        for (int s = 0; s < p->S; ++s) if (!p->graphs[s]->d_ell_self) pp.ell_self = 0;
         for (int s = 0; s < p->S; ++s) pp.max_degree = std::max(pp.max_degree, (int)p->graphs[s]->max_degree);
         if (launch_tfce_pipeline(pp, p->pipe_slots, stream)) return 1;
         TableSet sub;

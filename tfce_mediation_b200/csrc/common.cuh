@@ -70,6 +70,7 @@ struct SurfDesc {
     const int32_t *indices; // [nnz]
     const int32_t *ell;     // [V * ell_width] fixed-width rows padded with -1 (32-byte aligned), or nullptr
     int32_t ell_width;      // 8, 16 or 32 when ell != nullptr
+    const int32_t *ell_self; // width-8 rows padded with the vertex ITSELF instead of -1 (pipeline ascent: no pad test), or nullptr
     // sliced rows (SELL-32-4) for graphs wider than 32 neighbours or with very uneven degrees: the 32 vertices of a
     // slice share a width (their largest degree rounded up to 4); slot group j4 of the slice is 32 consecutive int4
     // (one per vertex), so a warp that owns the slice reads 512 contiguous bytes per group.  Pad = the vertex itself.
@@ -159,6 +160,7 @@ struct PipeParams {
     const float *tab_scale; // optional, see SweepParams
     int flags;              // bit 2: statistic rows are in the graphs' internal vertex order
     int max_degree;         // largest vertex degree over the plan's graphs (triangle meshes: 6 -> the ascent kernel skips the two pad slots)
+    int ell_self;           // every surface has self-padded width-8 rows (SurfDesc::ell_self)
     int sell_words;         // 0: fixed-width rows (ell); W > 0: sliced rows (sell) with W 32-bit words of earlier-neighbour mask per vertex
     int32_t Vmax;
     // per-item buffers

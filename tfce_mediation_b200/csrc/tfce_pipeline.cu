@@ -199,7 +199,10 @@ __global__ void __launch_bounds__(256) pipe_levels_kernel(PipeParams P, int chun
 // (Staging the CTA's own 256 level codes in shared memory -- 81% of the neighbour lookups fall into the vertex's own
 //  block, scripts/probe_window.py -- was measured slower than the L1 gathers: 1.26 vs 1.17 ms.)
 // kSix: every row has at most six neighbours in one 8-slot chunk (triangle meshes): slots 6 and 7 are padding and skipped.
-template <bool kSix>
+// kSelf: the rows are padded with the vertex itself (SurfDesc::ell_self, width 8): a self-reference is never "earlier"
+// and never an ascent target, so the gathers need no pad test.  Levels are compared as y = (level - 1) & 255 for a
+// same-sign active neighbour (0..126) and >= 127 for everything else, which needs no select.
+template <bool kSix, bool kSelf>
 __device__ __forceinline__ int ascent_of_vertex(const PipeParams &P, const SurfDesc &sd, size_t base, int v) {
     if (v >= sd.V) return -1;
     const unsigned char *__restrict__ lev8 = pin_ptr(P.lev8 + base);
@@ -210,32 +213,33 @@ __device__ __forceinline__ int ascent_of_vertex(const PipeParams &P, const SurfD
         P.emask[base + v] = 0u;
         return -1;
     }
-    // per neighbour: la = its level when it is active with v's sign, else 255.  The ascent target is the first
-    // neighbour of the smallest level below v's own (packed key: level << 8 | slot); "earlier" = (level, index)
-    // below (lev, v), one packed unsigned compare.
-    unsigned bestkey = ((unsigned)lev << 8) | 0xffu; // no strictly earlier level found yet
+    // per neighbour: y = its level - 1 when it is active with v's sign (0..126), else 127..255.  The ascent target is the
+    // first neighbour of the smallest level below v's own (packed key: y << 8 | slot); "earlier" = (level, index) below
+    // (lev, v), one packed unsigned compare.
+    unsigned bestkey = ((unsigned)(lev - 1) << 8) | 0xffu; // no strictly earlier level found yet
     unsigned em = 0;
     const unsigned sign = (unsigned)cv & 0x80u;
-    const unsigned mykey = ((unsigned)lev << 24) | (unsigned)v;
-    const int4 *__restrict__ row = pin_ptr(reinterpret_cast<const int4 *>(sd.ell + (size_t)v * sd.ell_width));
-    const int nch = kSix ? 1 : (sd.ell_width >> 3);
+    const unsigned mykey = ((unsigned)(lev - 1) << 24) | (unsigned)v;
+    const int width = kSelf ? 8 : sd.ell_width;
+    const int4 *__restrict__ row = pin_ptr(reinterpret_cast<const int4 *>((kSelf ? sd.ell_self : sd.ell) + (size_t)v * width));
+    const int nch = (kSix || kSelf) ? 1 : (width >> 3);
     constexpr int kSlots = kSix ? 6 : 8;
     for (int c = 0; c < nch; ++c) {
         const int4 r0 = __ldg(row + 2 * c), r1 = __ldg(row + 2 * c + 1);
         const int nb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
         unsigned ca[8];
 #pragma unroll
-        for (int j = 0; j < kSlots; ++j) ca[j] = (unsigned)__ldg(lev8 + (unsigned)max(nb[j], 0)); // pad slots (-1): vertex 0, masked below
+        for (int j = 0; j < kSlots; ++j) ca[j] = (unsigned)__ldg(lev8 + (unsigned)(kSelf ? nb[j] : max(nb[j], 0)));
 #pragma unroll
         for (int j = 0; j < kSlots; ++j) {
-            const unsigned x = nb[j] >= 0 ? (ca[j] ^ sign) : 0u; // 1..127: active, same sign
-            const unsigned la = (x - 1u) < 127u ? x : 255u;
-            bestkey = min(bestkey, (la << 8) | (unsigned)(c * 8 + j));
-            if (((la << 24) | (unsigned)nb[j]) < mykey) em |= 1u << (c * 8 + j); // nb < 2^24; la = 255 never passes
+            unsigned y = ((ca[j] ^ sign) + 255u) & 255u;       // 0..126: active, same sign
+            if (!kSelf && nb[j] < 0) y = 255u;                 // pad slot (-1)
+            bestkey = min(bestkey, (y << 8) | (unsigned)(c * 8 + j));
+            if (((y << 24) | (unsigned)nb[j]) < mykey) em |= 1u << (c * 8 + j); // nb < 2^24; y >= 127 never passes
         }
     }
     const int bestbit = (int)(bestkey & 0xffu);
-    const bool has_up = (int)(bestkey >> 8) < lev;
+    const bool has_up = (int)(bestkey >> 8) < lev - 1;
     int best = v;
     if (has_up) {
         best = reinterpret_cast<const int *>(row)[bestbit];
@@ -246,7 +250,7 @@ __device__ __forceinline__ int ascent_of_vertex(const PipeParams &P, const SurfD
     return best == v ? cv : -1;
 }
 
-template <bool kSix>
+template <bool kSix, bool kSelf>
 __global__ void __launch_bounds__(256) pipe_ascent_kernel(PipeParams P, int chunks) {
     __shared__ int sPeaks, sBase;
     int item, chunk, s, b;
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(256) pipe_ascent_kernel(PipeParams P, int chun
     __syncthreads();
     const int v = chunk * 256 + threadIdx.x;
     const size_t base = (size_t)item * P.vstride;
-    const int peak_code = ascent_of_vertex<kSix>(P, sd, base, v);
+    const int peak_code = ascent_of_vertex<kSix, kSelf>(P, sd, base, v);
     // peaks get compact basin ids: one returning atomic per CTA on the map's counter
     int local = -1;
     if (peak_code >= 0) local = atomicAdd(&sPeaks, 1);
@@ -492,7 +496,7 @@ __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunk
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const size_t base = (size_t)item * P.vstride;
-    const int *__restrict__ basin = pin_ptr(P.basin + base);
+    const int *__restrict__ basin = P.basin + base;   // (pinned base pointer + ld.global.nc measured SLOWER here: 3.21 vs 2.68 ms)
     const int NB = meta[0];
     __shared__ int sBasin[kCountChunk]; // basins of the CTA's own vertices: most neighbour lookups land here
     int buq[kCountVPT], levq[kCountVPT];
@@ -522,15 +526,15 @@ __global__ void __launch_bounds__(256) pipe_count_kernel(PipeParams P, int chunk
         // candidate unions: earlier neighbours lying in another basin (each distinct basin once per vertex, best
         // effort).  Staged in shared memory: one returning atomic per CTA reserves the output range.
         if (em && !(P.flags & 512)) {
-            const int *__restrict__ row = pin_ptr(sd.ell + (size_t)v * sd.ell_width);
+            const int *__restrict__ row = sd.ell + (size_t)v * sd.ell_width;
             int s0 = -1, s1 = -1, s2 = -1, s3 = -1;
             unsigned m = em;
             while (m) {
                 const int j = __ffs(m) - 1;
                 m &= m - 1;
-                const int a = __ldg(row + j);
+                const int a = row[j];
                 const unsigned off = (unsigned)(a - v_beg);
-                const int ba = off < (unsigned)kCountChunk ? sBasin[off] : __ldg(basin + (unsigned)a);
+                const int ba = off < (unsigned)kCountChunk ? sBasin[off] : basin[a];
                 if (ba == bu || ba == s0 || ba == s1 || ba == s2 || ba == s3) continue;
                 s3 = s2; s2 = s1; s1 = s0; s0 = ba;
                 const unsigned long long pr = ((unsigned long long)lev << 48) | ((unsigned long long)bu << 24) | (unsigned long long)ba;
@@ -1709,8 +1713,10 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
     const dim3 gridB(chunks, p.B, p.S);
     switch (p.sell_words) {
     case 0:
-        if (p.max_degree > 0 && p.max_degree <= 6) pipe_ascent_kernel<true><<<gridB, 256, 0, stream>>>(p, chunks);
-        else pipe_ascent_kernel<false><<<gridB, 256, 0, stream>>>(p, chunks);
+        if (p.max_degree > 0 && p.max_degree <= 6 && p.ell_self) pipe_ascent_kernel<true, true><<<gridB, 256, 0, stream>>>(p, chunks);
+        else if (p.max_degree > 0 && p.max_degree <= 6) pipe_ascent_kernel<true, false><<<gridB, 256, 0, stream>>>(p, chunks);
+        else if (p.ell_self) pipe_ascent_kernel<false, true><<<gridB, 256, 0, stream>>>(p, chunks);
+        else pipe_ascent_kernel<false, false><<<gridB, 256, 0, stream>>>(p, chunks);
         break;
     case 1: pipe_ascent_wide_kernel<1><<<gridB, 256, 0, stream>>>(p, chunks); break;
     case 2: pipe_ascent_wide_kernel<2><<<gridB, 256, 0, stream>>>(p, chunks); break;
