@@ -112,3 +112,36 @@ def test_observed_statistics_match_step1_writer_math():
             assert np.array_equal(obs["tfce_pos"][c, h * V:(h + 1) * V], want_pos)
             assert np.array_equal(obs["tfce_neg"][c, h * V:(h + 1) * V], want_neg)
             assert obs["max_pos"][c, h] == want_pos.max() and obs["max_neg"][c, h] == want_neg.max()
+
+
+def test_mediation_blocks_pipelined_equals_block_by_block():
+    """engine.mediation_blocks (software-pipelined: host design algebra of block i+1 behind the sweep of block i) returns
+    the rows of mediation_block, and those are the oracle pipeline's (pyfunc.py:130-162 -> :107-119)."""
+    import oracle
+    from tests import helpers
+    from tfce_mediation_b200 import synth
+    from tfce_mediation_b200.engine import PermutationEngine, Surface
+    from tfce_mediation_b200.tfce import CreateAdjSet
+    _, _, csr = helpers.ico(4)
+    V = csr[0].shape[0] - 1
+    n, N = 36, 11
+    rs = np.random.RandomState(12)
+    px = rs.standard_normal(n)
+    dep = 0.5 * px + rs.standard_normal(n)
+    y = (synth.subject_data(n, csr, 3, 2) + np.float32(0.3) * px[:, None].astype(np.float32)
+         + np.float32(0.3) * dep[:, None].astype(np.float32)).astype(np.float32)
+    eng = PermutationEngine(y, [Surface(CreateAdjSet(2, 0.67, csr), 0)], two_sided=False)
+    idx = np.stack([oracle.permutation_indices(500 + p, n) for p in range(N)])
+    for med in ("M", "I", "Y"):
+        whole = eng.mediation_blocks(med, px, dep, idx, block=4)
+        parts = np.concatenate([eng.mediation_block(med, px, dep, idx[a:a + 4]) for a in range(0, N, 4)])
+        assert whole.shape == (N, 1) and np.array_equal(whole, parts)
+    run = helpers.oracle_run(2, 0.67, csr)
+    mask = np.ones(V, dtype=bool)
+    whole = eng.mediation_blocks("M", px, dep, idx, block=4)
+    for p in (0, 5, 10):
+        z = oracle.sobelz("M", px[idx[p]], dep, y, n, V).astype(np.float32)
+        tf = np.zeros(V, dtype=np.float32)
+        run(np.ascontiguousarray(z), tf)
+        want = np.float32((tf * (z.max() / 100)).max())
+        assert "%.4f" % whole[p, 0] == "%.4f" % want

@@ -163,3 +163,20 @@ def test_apply_mfwer_restatement_vs_reference(tmp_path, monkeypatch):
         assert np.array_equal(pos, g["pos_" + wname])
         assert np.array_equal(neg, g["neg_" + wname])
     assert tm_func.lowest_length(2, [0, 1, 2], "t") == int(g["num_perm"])
+
+
+def test_host_libm_powf_matches_the_fixtures_libm():
+    """Bit-identity of TFCE values rests on libm's powf (fast_tfce.hpp:70 compiles to it, and it is NOT correctly rounded:
+    for H = 2 a few thresholds in 10^4 differ from T*T by one ulp).  The golden fixtures were generated with the build
+    container's glibc; this pins that the library on THIS machine returns the same bits on a 4,007-point grid for the
+    exponents the reference uses, so a fixture mismatch elsewhere cannot be a silent libm difference."""
+    import ctypes
+    import ctypes.util
+    g = np.load(os.path.join(G, "libm_powf.npz"))
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.powf.restype = ctypes.c_float
+    libm.powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    got = np.array([[libm.powf(float(t), float(h)) for t in g["T"]] for h in g["H"]], dtype=np.float32)
+    assert np.array_equal(got.view(np.int32), g["powf"].view(np.int32)), \
+        "this machine's libm powf differs from the one the golden fixtures were generated with"
+    assert int((g["powf"][0] != (g["T"] * g["T"]).astype(np.float32)).sum()) > 0      # the non-trivial case is covered
