@@ -1137,7 +1137,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_kernel(PipePa
 // geometry are marked (meta[2] = 2) and taken by a second launch of the large one.
 __host__ __device__ inline size_t pipe_sweep_max_smem_bytes(int NB, bool small, bool weighted) {
     const size_t nba = ((size_t)NB + 7) / 8 * 8;
-    return nba * (4 + 4 + 4 + 1 + 1 + (small ? 0 : 6) + (weighted ? 13 : 0)) + 16;
+    // weighted: + wnew (4), w0 (2), fcnt (1); its live-root lists always sit in the slot's global scratch
+    return nba * (4 + 4 + 4 + 1 + 1 + ((small || weighted) ? 0 : 6) + (weighted ? 7 : 0)) + 16;
 }
 
 // Weighted maxima (kW).  The scaled maximum of pyfunc.py:116-117 / tm_func.py:173-174 is max_v fl32(fl32(tfce_v * delta) * w_v).
@@ -1174,6 +1175,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
     __shared__ int sNs[2];
     __shared__ float sDelta[2];
     __shared__ int sItem, sNpend, sNalive[2], sOverflow;
+    constexpr int kMergeCap = kW ? 256 : 1;   // weighted: (hooked root | new root << 16) pairs whose fronts the new root must
+    __shared__ unsigned sMerge[2][kMergeCap]; // merge this level; double-buffered by level parity, rarely more than a few
+    __shared__ int sMergeN[2];
     __shared__ float sRed[2][kThreads / 32];
 
     const int tid = threadIdx.x;
@@ -1233,7 +1237,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         unsigned short *alive[2];                                                 // live roots (double-buffered) ...
         unsigned short *birth;                                                    // ... and basins bucketed by the level of their peak
         unsigned char *hooklev;                                                   // level at which a root was hooked (255: never)
-        if (kSmall) { // lists in the slot's global scratch (the class path's increment log, unused here)
+        constexpr bool kListsGlobal = kSmall || kW;
+        if (kListsGlobal) { // lists in the slot's global scratch (the class path's increment log, unused here)
             alive[0] = reinterpret_cast<unsigned short *>(ws.incseq);
             alive[1] = alive[0] + nba;
             birth = alive[1] + nba;
@@ -1247,11 +1252,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         unsigned char *blev = hooklev + nba;                                      // level | sign << 7 of the peak
         // weighted: Pareto front of (sum, weight rank) per root -- entry 0 in racc / w0, entries 1.. in global scratch
         int *wnew = reinterpret_cast<int *>(blev + nba);                          // largest weight rank + 1 among the vertices a root gains this level
-        int *phead = wnew + nba;                                                  // roots hooked under this one whose fronts must be merged (list head)
-        unsigned short *w0 = reinterpret_cast<unsigned short *>(phead + nba);
-        unsigned short *pnext = w0 + nba;
-        unsigned char *fcnt = reinterpret_cast<unsigned char *>(pnext + nba);     // entries in the root's front
-        uint2 *fr = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(ws.incseq) + (kSmall ? ((size_t)6 * nba + 15) / 16 * 16 : 0));
+        unsigned short *w0 = reinterpret_cast<unsigned short *>(wnew + nba);
+        unsigned char *fcnt = reinterpret_cast<unsigned char *>(w0 + nba);        // entries in the root's front
+        uint2 *fr = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(ws.incseq) + (kListsGlobal ? ((size_t)6 * nba + 15) / 16 * 16 : 0));
         auto fget = [&](int r, int k) -> uint2 {
             return k == 0 ? make_uint2((unsigned)racc[r], (unsigned)w0[r]) : fr[(size_t)r * kFront + k];
         };
@@ -1300,7 +1303,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             if (P.status) P.status[e0 + tid] = on ? P.tab_status[e0 + tid] : 0;
             sNalive[tid] = 0;
         }
-        if (tid == 0) sNpend = 0;
+        if (tid == 0) { sNpend = 0; sMergeN[0] = 0; sMergeN[1] = 0; }
         for (int i = tid; i < kLevels; i += nthr) { sCurP[i] = 0; sCurE[i] = 0; sCurB[i] = 0; }
         const unsigned char *__restrict__ gblev = P.blev + (size_t)item * P.nbcap;
         __syncthreads();
@@ -1309,7 +1312,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
             bsize[i] = 0;
             racc[i] = 0; // +0.0f
             hooklev[i] = 255;
-            if (kW) { wnew[i] = 0; phead[i] = -1; fcnt[i] = 0; }
+            if (kW) { wnew[i] = 0; fcnt[i] = 0; }
             const int cb = gblev[i];
             blev[i] = (unsigned char)cb;
             atomicAdd(&sCurB[cb & 0x7f], 1);
@@ -1477,7 +1480,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                     for (int q = 0; q < 4; ++q) {
                         const int i = i0 + q * nthr;
                         b4[q] = -1;
-                        if (i < na) b4[q] = kSmall ? ((q == 0 && i0 == tid) ? bbpre : (int)__ldcg(al + i)) : (int)al[i];
+                        if (i < na) b4[q] = kSmall ? ((q == 0 && i0 == tid) ? bbpre : (int)__ldcg(al + i)) : (kListsGlobal ? (int)__ldcg(al + i) : (int)al[i]);
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -1501,7 +1504,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                                     }
                                     push = !dom;
                                 }
-                                if (push) pnext[bb] = (unsigned short)atomicExch(phead + rr, bb); // -1 -> 0xffff ends the list
+                                if (push) {
+                                    const int slot = atomicAdd(&sMergeN[lev & 1], 1);
+                                    if (slot < kMergeCap) sMerge[lev & 1][slot] = (unsigned)bb | ((unsigned)rr << 16);
+                                    else sOverflow = 1;
+                                }
                             }
                         }
                     }
@@ -1519,6 +1526,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                 const int na = sNalive[cur];
                 const int nb = sBstart[lev + 1] - sBstart[lev];   // roots born at this level
                 const int tot = na + nb;
+                const int nmerge = kW ? min(sMergeN[lev & 1], kMergeCap) : 0;
+                if (kW && tid == 0) sMergeN[(lev + 1) & 1] = 0;   // the other buffer was last read one barrier ago
                 // small geometry: request this thread's first list entry (L2), run the next level's unions while it is in
                 // flight.  The order inside the interval is free: the unions of level lev+1 touch neither the sizes nor
                 // the leader sums, and the hooks they log carry level lev+1 > lev.
@@ -1535,8 +1544,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                       const int i = ig + q * nthr + lane;
                       b4[q] = -1;
                       if (kSmall && q == 0 && ig == (tid & ~31)) b4[q] = bbfirst;
-                      else if (i < na) b4[q] = kSmall ? (int)__ldcg(al + i) : (int)al[i];
-                      else if (i < tot) b4[q] = kSmall ? (int)__ldcg(birth + sBstart[lev] + i - na) : (int)birth[sBstart[lev] + i - na];
+                      else if (i < na) b4[q] = kListsGlobal ? (int)__ldcg(al + i) : (int)al[i];
+                      else if (i < tot) b4[q] = kListsGlobal ? (int)__ldcg(birth + sBstart[lev] + i - na) : (int)birth[sBstart[lev] + i - na];
                   }
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
@@ -1549,14 +1558,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
                         if (kW) {
                             // the fronts of the roots hooked under bb at this level, then the class of the vertices gained
                             // at this level (sum 0 so far); all sums are those after level lev - 1
-                            int hb = phead[bb];
-                            if (hb >= 0) {
-                                phead[bb] = -1;
-                                while (hb != 0xffff && hb >= 0) {
-                                    const int c2 = fcnt[hb];
-                                    for (int k = 0; k < c2; ++k) { const uint2 e = fget(hb, k); finsert(bb, e.x, e.y); }
-                                    hb = (int)pnext[hb];
-                                }
+                            for (int i = 0; i < nmerge; ++i) {
+                                const unsigned e2 = sMerge[lev & 1][i];
+                                if ((int)(e2 >> 16) != bb) continue;
+                                const int hb = (int)(e2 & 0xffffu), c2 = fcnt[hb];
+                                for (int k = 0; k < c2; ++k) { const uint2 e = fget(hb, k); finsert(bb, e.x, e.y); }
                             }
                             const int wn = wnew[bb];
                             if (wn > 0) { wnew[bb] = 0; finsert(bb, 0u, (unsigned)(wn - 1)); }
