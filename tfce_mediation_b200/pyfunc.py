@@ -75,30 +75,60 @@ def create_adjac_voxel_tools(data_index, dirtype=26):
     return [set(indices[indptr[i]:indptr[i + 1]].tolist()) for i in range(indptr.shape[0] - 1)]
 
 
+_PLANS = []        # [(weakref to every CreateAdjSet, key, plan)]: the single-map writers reuse one TFCE plan per graph set
+
+
+def _plan_for(adjsets, masks, weights):
+    """A TfcePlan over the kept vertices of the given CreateAdjSet objects (cached while the same objects are passed):
+    masked-out vertices carry statistic 0 in the reference (pyfunc.py:108-113) and can never activate, so the plan runs
+    on the induced sub-graphs, one surface per hemisphere, laid side by side along one statistic row."""
+    import weakref
+    from ._graph import induced_subgraph
+    from .engine import Surface, TfcePlan
+    from .tfce import CreateAdjSet
+    key = tuple(id(w) if np.ndim(w) else float(w) for w in weights)
+    for refs, k, plan in _PLANS:
+        if k == key and len(refs) == len(adjsets) and all(r() is a for r, a in zip(refs, adjsets)):
+            return plan
+    surfs, off = [], 0
+    for adj, mask, w in zip(adjsets, masks, weights):
+        keep = None if mask is None else np.asarray(mask, dtype=bool)
+        graph = (adj.indptr, adj.indices) if keep is None else induced_subgraph(adj.indptr, adj.indices, keep)
+        if np.ndim(w):
+            w = np.asarray(w)[keep] if keep is not None and np.shape(w)[0] == keep.shape[0] else np.asarray(w)
+        surfs.append(Surface(CreateAdjSet(adj.H, adj.E, graph), off, w))
+        off += graph[0].shape[0] - 1
+    plan = TfcePlan(surfs)
+    _PLANS.append(([weakref.ref(a) for a in adjsets], key, plan))
+    del _PLANS[:-4]
+    return plan
+
+
+def _single_map_max(plan, stat):
+    """Scaled TFCE maxima [S] of ONE one-sided statistic row (a block of one map through the batched pipeline)."""
+    import torch
+    row = torch.zeros((1, (plan.row_len + 3) // 4 * 4), dtype=torch.float32, device=plan.device)
+    row[0, :stat.shape[0]] = torch.from_numpy(np.ascontiguousarray(stat, dtype=np.float32)).to(plan.device)
+    mx, _, _ = plan.run(row, two_sided=False)
+    return mx[0, :, 0].cpu().numpy()
+
+
 def write_perm_maxTFCE_vertex(statname, vertStat, num_vertex, bin_mask_lh, bin_mask_rh, calcTFCE_lh, calcTFCE_rh,
                               density_corr_lh=1, density_corr_rh=1):
-    """pyfunc.py:107-119: scatter into full-length hemispheres, TFCE each, scaled max, append '%.4f'."""
-    vertStat_out_lh = np.zeros(bin_mask_lh.shape[0]).astype(np.float32, order="C")
-    vertStat_out_rh = np.zeros(bin_mask_rh.shape[0]).astype(np.float32, order="C")
-    vertStat_TFCE_lh = np.zeros_like(vertStat_out_lh).astype(np.float32, order="C")
-    vertStat_TFCE_rh = np.zeros_like(vertStat_out_rh).astype(np.float32, order="C")
-    vertStat_out_lh[bin_mask_lh] = vertStat[:num_vertex]
-    vertStat_out_rh[bin_mask_rh] = vertStat[num_vertex:]
-    calcTFCE_lh.run(vertStat_out_lh, vertStat_TFCE_lh)
-    calcTFCE_rh.run(vertStat_out_rh, vertStat_TFCE_rh)
-    max_lh = vertStat_TFCE_lh[np.isfinite(vertStat_TFCE_lh)] * (vertStat_out_lh[np.isfinite(vertStat_out_lh)].max() / 100) * density_corr_lh
-    max_rh = vertStat_TFCE_rh[np.isfinite(vertStat_TFCE_rh)] * (vertStat_out_rh[np.isfinite(vertStat_out_rh)].max() / 100) * density_corr_rh
-    maxTFCE = np.array([max_lh.max(), max_rh.max()]).max()
-    _append_line("perm_%s_TFCE_maxVertex.csv" % statname, "%.4f" % maxTFCE)
+    """pyfunc.py:107-119: TFCE of the statistic on both hemispheres, max over both of tfce * (max(stat)/100) * density,
+    one '%.4f' row appended to perm_<statname>_TFCE_maxVertex.csv.  vertStat holds the kept vertices of lh (the first
+    num_vertex entries) and rh; the two hemispheres run as the two surfaces of one cached plan."""
+    plan = _plan_for((calcTFCE_lh, calcTFCE_rh), (bin_mask_lh, bin_mask_rh), (density_corr_lh, density_corr_rh))
+    stat = np.asarray(vertStat, dtype=np.float32)
+    stat = np.where(np.isfinite(stat), stat, np.float32(0))          # the reference drops non-finite entries (:116-117)
+    _append_line("perm_%s_TFCE_maxVertex.csv" % statname, "%.4f" % _single_map_max(plan, stat).max())
 
 
 def write_perm_maxTFCE_voxel(statname, voxelStat, TFCEfunc):
-    """pyfunc.py:121-126."""
-    voxelStat_out = voxelStat.astype(np.float32, order="C")
-    voxelStat_TFCE = np.zeros_like(voxelStat_out).astype(np.float32, order="C")
-    TFCEfunc.run(voxelStat_out, voxelStat_TFCE)
-    maxval = voxelStat_TFCE.max() * (voxelStat_out.max() / 100)
-    _append_line("perm_%s_TFCE_maxVoxel.csv" % statname, "%1.4f" % maxval)
+    """pyfunc.py:121-126: TFCE of the voxel statistic, tfce.max() * (stat.max()/100), one '%1.4f' row."""
+    plan = _plan_for((TFCEfunc,), (None,), (1,))
+    _append_line("perm_%s_TFCE_maxVoxel.csv" % statname,
+                 "%1.4f" % _single_map_max(plan, np.asarray(voxelStat, dtype=np.float32))[0])
 
 
 def calc_sobelz(medtype, pred_x, depend_y, merge_y, n, num_vertex, alg="aroian"):
@@ -110,15 +140,11 @@ def calc_sobelz(medtype, pred_x, depend_y, merge_y, n, num_vertex, alg="aroian")
 
 def typeI_design(exog, dmy_covariates, n):
     """The design of pyfunc.py:2304-2315: [1, exog variables ..., covariates] and the column count of each variable."""
-    kvars = []
-    exog_vars = np.ones((n))
-    for var in exog:
-        var = np.array(var)
-        kvars.append(1 if var.ndim == 1 else var.shape[1])
-        exog_vars = np.column_stack((exog_vars, var))
+    blocks = [np.asarray(v, dtype=np.float64).reshape(n, -1) for v in exog]
+    cols = [np.ones((n, 1))] + blocks
     if dmy_covariates is not None:
-        exog_vars = np.column_stack((exog_vars, dmy_covariates))
-    return np.array(exog_vars, dtype=np.float64), kvars
+        cols.append(np.asarray(dmy_covariates, dtype=np.float64).reshape(n, -1))
+    return np.hstack(cols), [blk.shape[1] for blk in blocks]
 
 
 def glm_typeI(endog, exog, dmy_covariates=None, output_fvalues=True, output_tvalues=False, output_pvalues=False,
@@ -192,13 +218,10 @@ def check_blocks(block_list):
 
 
 def rand_blocks(block_list, is_equal_sizes):
-    """pyfunc.py:2733-2757: permutation index from exchangeability blocks (same numpy RNG calls, same order)."""
-    indexer = np.array(range(len(block_list)))
-    randindex = []
-    if is_equal_sizes is True:
-        for block in np.random.permutation(list(np.unique(block_list))):
-            randindex.append(np.random.permutation(indexer[block_list == block]))
-    else:
-        for block in np.unique(block_list):
-            randindex.append(np.random.permutation(indexer[block_list == block]))
-    return np.concatenate(randindex)
+    """pyfunc.py:2733-2757: permutation index from exchangeability blocks -- the same numpy RNG calls in the same order:
+    with equal block sizes the block ORDER is drawn first, then (always) one permutation inside every block."""
+    block_list = np.asarray(block_list)
+    where = np.arange(len(block_list))
+    labels = np.unique(block_list)
+    order = np.random.permutation(list(labels)) if is_equal_sizes is True else labels
+    return np.concatenate([np.random.permutation(where[block_list == lab]) for lab in order])

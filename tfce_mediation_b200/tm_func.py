@@ -315,72 +315,64 @@ def find_nearest(array, value, p_array):
     return np.where(at_end, p_array[n - 1], np.where(lower, p_array[idc - 1], p_array[idc]))
 
 
+def _perm_file(tminame, surface, contrast, medtype):
+    if medtype is not None:
+        return 'output_%s/perm_maxTFCE_surf%d_%s_zstat.csv' % (tminame, surface, str(medtype))
+    return 'output_%s/perm_maxTFCE_surf%d_tcon%d.csv' % (tminame, surface, contrast + 1)
+
+
 def lowest_length(num_contrasts, surface_range, tmifilename, medtype=None):
     """Shortest permutation file over all surfaces/contrasts (tm_func.py:544-552)."""
-    lengths = []
-    for contrast in range(num_contrasts):
-        for surface in surface_range:
-            if medtype is not None:
-                f = 'output_%s/perm_maxTFCE_surf%d_%s_zstat.csv' % (tmifilename, surface, medtype)
-            else:
-                f = 'output_%s/perm_maxTFCE_surf%d_tcon%d.csv' % (tmifilename, surface, contrast + 1)
-            lengths.append(np.genfromtxt(f).shape[0])
-    return np.array(lengths).min()
+    return min(np.genfromtxt(_perm_file(tmifilename, sf, c, medtype)).shape[0]
+               for c in range(num_contrasts) for sf in surface_range)
 
 
 def apply_mfwer(image_array, num_contrasts, surface_range, num_perm, num_surf, tminame, position_array, pos_range,
                 neg_range=None, method='scale', weight=None, mediation=False, medtype=None):
-    """Study-wide (multi-surface) FWER correction, tm_func.py:403-491: per surface the null maxima are
-    log-transformed and z-standardised (+10), the per-permutation maximum is taken across surfaces (optionally
-    choosing the surface by log-mask-size weights), sorted, and every vertex's equally transformed TFCE value is
-    looked up with the reference's nearest-value rule.  Host numpy: a post-processing step on
-    num_perm x num_surf numbers plus one vectorised lookup per image column."""
-    maxvalue_array = np.zeros((num_perm, num_contrasts))
-    temp_max = np.zeros((num_perm, num_surf))
-    positive_data = np.zeros((image_array[0].shape[0], num_contrasts))
-    negative_data = None if mediation else np.zeros((image_array[0].shape[0], num_contrasts))
+    """Study-wide (multi-surface) FWER correction, tm_func.py:403-491.  Per contrast and surface the null maxima are
+    log-transformed and z-standardised (+10); row i of every surface file is taken as the SAME permutation and the
+    per-permutation maximum across surfaces -- with weight='logmasksize' the value of the surface that wins after its
+    z-scores were scaled by the normalised log mask size -- forms the null distribution; every vertex's TFCE value gets
+    the same transform with ITS surface's null mean / s.d. and is looked up with the reference's nearest-value rule
+    (find_nearest).  Host numpy: num_perm x num_surf numbers plus one vectorised lookup per image column."""
+    img = image_array[0]
+    nvert = img.shape[0]
+    columns = [(pos_range, np.zeros((nvert, num_contrasts)))]
+    if not mediation:
+        columns.append((neg_range, np.zeros((nvert, num_contrasts))))
+    by_size = None
     if weight == 'logmasksize':
-        x = [position_array[i + 1] - position_array[i] for i in range(len(position_array) - 1)]
-        weights = (np.log(x) / np.log(x).sum()) / np.mean(np.log(x) / np.log(x).sum())
-        w_temp_max = np.zeros((num_perm, num_surf))
-    for contrast in range(num_contrasts):
-        for surface in surface_range:
-            if not mediation:
-                f = 'output_%s/perm_maxTFCE_surf%d_tcon%d.csv' % (tminame, surface, contrast + 1)
-            else:
-                f = 'output_%s/perm_maxTFCE_surf%d_%s_zstat.csv' % (tminame, surface, str(medtype))
+        logsize = np.log(np.diff(np.asarray(position_array)))
+        share = logsize / logsize.sum()
+        by_size = share / share.mean()
+    null_sorted = np.zeros((num_perm, num_contrasts))
+    for c in range(num_contrasts):
+        z10 = np.zeros((num_perm, num_surf))
+        z10_weighted = np.zeros((num_perm, num_surf))
+        for sf in surface_range:
             with np.errstate(divide="ignore"):
-                log_perm_results = np.log(np.genfromtxt(f)[:num_perm])
-            log_perm_results[np.isinf(log_perm_results)] = 0
-            start, end = position_array[surface], position_array[surface + 1]
-            for data, rng in ((positive_data, pos_range),) + (() if mediation else ((negative_data, neg_range),)):
-                col = image_array[0][start:end, rng[contrast]]
+                lognull = np.log(np.genfromtxt(_perm_file(tminame, sf, c, medtype if mediation else None))[:num_perm])
+            lognull[np.isinf(lognull)] = 0
+            mu, sd = lognull.mean(), lognull.std()
+            lo, hi = position_array[sf], position_array[sf + 1]
+            for rng, out in columns:
+                vals = img[lo:hi, rng[c]]
                 with np.errstate(divide="ignore", invalid="ignore"):
-                    posvmask = np.log(col) > 0
-                    temp_lt = np.log(col[posvmask])
-                temp_lt -= log_perm_results.mean()
-                temp_lt /= log_perm_results.std()
-                temp_lt += 10
-                data[start:end, contrast][posvmask] = temp_lt
-            log_perm_results -= log_perm_results.mean()
-            log_perm_results /= log_perm_results.std()
-            if weight == 'logmasksize':
-                w_temp_max[:, surface] = log_perm_results * weights[surface] + 10
-            log_perm_results += 10
-            temp_max[:, surface] = log_perm_results
+                    logv = np.log(vals)
+                keep = logv > 0
+                out[lo:hi, c][keep] = (logv[keep] - mu) / sd + 10
+            z = (lognull - mu) / sd
+            if by_size is not None:
+                z10_weighted[:, sf] = z * by_size[sf] + 10
+            z10[:, sf] = z + 10
         if weight is not None:
-            w_temp_max[np.isnan(w_temp_max)] = 0
-            max_index = np.argmax(w_temp_max, axis=1)
-            max_value_list = temp_max[np.arange(len(temp_max)), max_index].astype(np.float32)
-            maxvalue_array[:, contrast] = np.sort(max_value_list)
+            z10_weighted[np.isnan(z10_weighted)] = 0
+            winner = np.argmax(z10_weighted, axis=1)
+            null_sorted[:, c] = np.sort(z10[np.arange(num_perm), winner].astype(np.float32))
         else:
-            maxvalue_array[:, contrast] = np.sort(temp_max.max(axis=1))
+            null_sorted[:, c] = np.sort(z10.max(axis=1))
     p_array = np.arange(num_perm) / float(num_perm)
-    for contrast in range(num_contrasts):
-        srt = maxvalue_array[:, contrast]
-        positive_data[:, contrast] = find_nearest(srt, positive_data[:, contrast], p_array)
-        if not mediation:
-            negative_data[:, contrast] = find_nearest(srt, negative_data[:, contrast], p_array)
-    if mediation:
-        return positive_data
-    return positive_data, negative_data
+    for c in range(num_contrasts):
+        for _, out in columns:
+            out[:, c] = find_nearest(null_sorted[:, c], out[:, c], p_array)
+    return columns[0][1] if mediation else (columns[0][1], columns[1][1])
