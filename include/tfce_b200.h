@@ -196,6 +196,16 @@ int tmb_sobelz_beta(const double *beta_dev, int64_t ldb, int64_t V, const double
                     const double *yy_dev, const double *ta_scalar_dev, int P, int alg, float *z32_dev, double *z64_dev,
                     int64_t ldt, void *stream);
 
+/* Cosinor statistics (pyfunc.py:2406-2563 glm_cosinor, the permutation branch used by tm_models_randomise.py:274-381)
+ * from stored betas of the centred design [cos_0, sin_0, ..., cos_{nper-1}, sin_{nper-1}, nexog tested columns,
+ * covariates] (r regressors, r <= 64).  G_dev, C_dev float64 [P, r, r]: the centred Gram matrix and its inverse.
+ * mediation == 0: rows per design [model F, (|t amplitude_i|, |t acrophase_i|) per period, t of each tested column]
+ * (1 + 2*nper + nexog rows).  mediation != 0 (tm_models_randomise.py:383-412): the single row
+ * calc_indirect(ta, t of tested column 0) with `ta` the un-permuted path-A amplitude t (alg as in tmb_sobelz). */
+int tmb_glm_cosinor_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *G_dev, const double *C_dev, int P,
+                         int r, int nper, int nexog, double dof, const double *yy_dev, int mediation, double ta, int alg,
+                         float *s32_dev, double *s64_dev, int64_t ldt, int nan_to_zero, void *stream);
+
 /* betas only == cynumstats.pyx:28-29 cy_lin_lstsqr_mat: beta64_dev float64 [nrows, ldt] for the nrows
  * pseudo-inverse rows stored as the first nrows columns of At_dev (ldA a multiple of 128). */
 int tmb_glm_beta(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev, int64_t ldA,

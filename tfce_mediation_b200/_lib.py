@@ -54,6 +54,8 @@ SIGNATURES = {
                                   _int, _vp]),
     "tmb_sobelz_beta": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _int, _f64, _vp, _vp, _int, _int, _f64, _vp, _vp, _int,
                                _int, _vp, _vp, _i64, _vp]),
+    "tmb_glm_cosinor_beta": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _int, _int, _int, _f64, _vp, _int, _f64, _int, _vp, _vp,
+                                    _i64, _int, _vp]),
     "tmb_glm_fstat": (_int, [_vp, _int, _int, _i64, _i64, _vp, _i64, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _int,
                              _f64, _vp, _vp, _vp, _i64, _int, _int, _vp]),
     "tmb_glm_pack_rowperm": (_int, [_vp, _int, _int, _vp, _int, _int, _vp, _i64, _int, _vp]),

@@ -85,10 +85,11 @@ struct GlmParams {
     const double *yy;
     float *t32; double *t64; int64_t ldt;
     int nan_to_zero;
-    int mode;                           // 0 t-stat, 1 betas, 2 sobel, 3 F statistics
+    int mode;                           // 0 t-stat, 1 betas, 2 sobel, 3 F statistics, 4 cosinor (stored betas only)
     // sobel: rows [0, rA) of each design group are path A, rows [rA, rA+rB) path B
     const double *GB; const double *dB; int rA, rB, rowA, rowB; double dofB;
     const double *ta_scalar; int alg;
+    int cos_nexog, cos_mediation; double cos_ta;                 // mode 4 (cosinor): tested columns, mediation row, path-A t
     // F statistics (mode 3): per design the inverse blocks M_i = inv((X'X)^-1[S_i, S_i]) of every tested variable,
     // stored one after the other (k_i x k_i each, msz doubles per design); variable i covers rows [var_lo[i], +var_k[i])
     const double *M; int msz, nvar; int var_lo[8], var_k[8];
@@ -1068,6 +1069,61 @@ __global__ void __launch_bounds__(128) glm_stats_from_beta_kernel(GlmParams p, c
             if (p.t64) p.t64[off] = f;
             M += ki * ki;
         }
+    } else if (p.mode == 4) {
+        // Cosinor statistics of pyfunc.py:2406-2563 glm_cosinor (permutation branch): regressors 2i, 2i+1 are the
+        // cos / sin pair of period i, then nexog tested columns, then covariates.  C = inv(G) (= the slope block of
+        // inv(X'X), intercept included).  Output rows: [model F, (|t amplitude|, |t acrophase|) per period, t of every
+        // tested column] -- or, for the cosinor mediation (tm_models_randomise.py:383-412), the single row
+        // calc_indirect(ta, t of tested column 0) with the un-permuted path-A amplitude t handed in by the host.
+        const int r = p.r, nper = p.nvar, nexog = p.cos_nexog;
+        const double *C = p.M + (size_t)perm * r * r;
+        const double ssb = rq_form(b, p.G + (size_t)perm * r * r, 0, r);
+        double sse = yyv - ssb;
+        if (sse < 0.0) sse = 0.0;
+        const double ms = __ddiv_rn(sse, p.dof);
+        const double sigma = __dsqrt_rn(ms);
+        const size_t base = (size_t)perm * p.nrows * p.ldt + v;
+        auto put = [&](int row, double x) {
+            if (p.nan_to_zero && x != x) x = 0.0;
+            if (!inside) x = 0.0;
+            if (p.t32) p.t32[base + (size_t)row * p.ldt] = __double2float_rn(x);
+            if (p.t64) p.t64[base + (size_t)row * p.ldt] = x;
+        };
+        const double s2 = __dmul_rn(sigma, sigma);                          // the reference re-squares sigma (:2507)
+        auto t_exog = [&](int j) {
+            const int col = 2 * nper + j;
+            const float se = __double2float_rn(__dsqrt_rn(__dmul_rn(s2, __ldg(C + col * r + col))));
+            return __ddiv_rn(b[col], (double)se);
+        };
+        if (p.cos_mediation) {                                               // mediation: one row
+            const double ta = p.cos_ta, tb = t_exog(0);
+            const double ta2 = __dmul_rn(ta, ta), tb2 = __dmul_rn(tb, tb);
+            double s = __dadd_rn(__ddiv_rn(1.0, tb2), __ddiv_rn(1.0, ta2));
+            const double cross = __ddiv_rn(1.0, __dmul_rn(ta2, tb2));
+            if (p.alg == 0) s = __dadd_rn(s, cross);
+            else if (p.alg == 2) s = __dsub_rn(s, cross);
+            put(0, __ddiv_rn(1.0, __dsqrt_rn(s)));
+        } else {
+            put(0, __ddiv_rn(__ddiv_rn(ssb, (double)r), ms));
+            for (int i = 0; i < nper; ++i) {
+                const double be = b[2 * i], ga = b[2 * i + 1];
+                const double amp = __dsqrt_rn(__dadd_rn(__dmul_rn(be, be), __dmul_rn(ga, ga)));
+                const double acr = atan(fabs(__ddiv_rn(-ga, be)));
+                double sn, cs;
+                sincos(acr, &sn, &cs);
+                const double c11 = __ldg(C + (2 * i) * r + 2 * i), c12 = __ldg(C + (2 * i) * r + 2 * i + 1),
+                             c22 = __ldg(C + (2 * i + 1) * r + 2 * i + 1);
+                const double sn2 = __dmul_rn(sn, sn), cs2 = __dmul_rn(cs, cs);
+                const double mix = __dmul_rn(__dmul_rn(__dmul_rn(2.0, c12), sn), cs);
+                const double va = __dadd_rn(__dadd_rn(__dmul_rn(c11, sn2), mix), __dmul_rn(c22, cs2));   // acrophase
+                const double vm = __dadd_rn(__dsub_rn(__dmul_rn(c11, cs2), mix), __dmul_rn(c22, sn2));   // amplitude
+                const double se_acr = __ddiv_rn(__dmul_rn(sigma, __dsqrt_rn(va)), amp);
+                const double se_amp = __dmul_rn(sigma, __dsqrt_rn(vm));
+                put(1 + 2 * i, fabs(__ddiv_rn(amp, se_amp)));
+                put(2 + 2 * i, fabs(__ddiv_rn(1.0, se_acr)));
+            }
+            for (int j = 0; j < nexog; ++j) put(1 + 2 * nper + j, t_exog(j));
+        }
     } else {
         const int rA = p.rA, rB = p.rB;
         double ta;
@@ -1362,6 +1418,22 @@ extern "C" int tmb_glm_fstat_beta(const double *beta_dev, int64_t ldb, int64_t V
                     "tmb_glm_fstat_beta: variable %d covers rows [%d, %d) of %d", i, var_lo[i], var_lo[i] + var_k[i], r);
         p.var_lo[i] = var_lo[i]; p.var_k[i] = var_k[i]; p.msz += var_k[i] * var_k[i];
     }
+    return launch_stats_from_beta(p, beta_dev, ldb, (cudaStream_t)stream);
+}
+
+extern "C" int tmb_glm_cosinor_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *G_dev, const double *C_dev,
+                                    int P, int r, int nper, int nexog, double dof, const double *yy_dev, int mediation,
+                                    double ta, int alg, float *s32_dev, double *s64_dev, int64_t ldt, int nan_to_zero,
+                                    void *stream) {
+    TMB_REQUIRE(beta_dev && G_dev && C_dev && yy_dev && (s32_dev || s64_dev), "tmb_glm_cosinor_beta: null pointer");
+    TMB_REQUIRE(V > 0 && P > 0 && nper >= 1 && nexog >= 0 && 2 * nper + nexog <= r && ldb >= V && ldt >= V &&
+                    (!mediation || nexog >= 1) && alg >= 0 && alg <= 2,
+                "tmb_glm_cosinor_beta: bad shape (P=%d r=%d periods=%d tested columns=%d)", P, r, nper, nexog);
+    TMB_DEVICE_OF(beta_dev, "tmb_glm_cosinor_beta");
+    GlmParams p{};
+    p.V = V; p.G = G_dev; p.M = C_dev; p.P = P; p.r = r; p.nvar = nper; p.cos_nexog = nexog; p.dof = dof; p.yy = yy_dev;
+    p.cos_mediation = mediation ? 1 : 0; p.cos_ta = ta; p.alg = alg; p.nrows = mediation ? 1 : 1 + 2 * nper + nexog;
+    p.t32 = s32_dev; p.t64 = s64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 4;
     return launch_stats_from_beta(p, beta_dev, ldb, (cudaStream_t)stream);
 }
 

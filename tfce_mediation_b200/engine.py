@@ -281,6 +281,45 @@ def row_permuted_stack(X, perm_idx, center=True):
                 d=np.repeat(base["d"], P, axis=0), r=r, dof=base["dof"], centered=bool(center))
 
 
+def cosinor_design(time_var, period, exog=None, dmy_covariates=None):
+    """The cosinor design of pyfunc.py:2432-2461: [1, cos(2 pi t / T_i), sin(2 pi t / T_i) per period, tested
+    variables..., covariates].  Returns (float64 [n, k], number of periods, number of tested columns)."""
+    time_var = np.asarray(time_var, dtype=np.float64).reshape(-1)
+    n = time_var.shape[0]
+    cols = [np.ones(n)]
+    for T in period:
+        angle = np.divide(2.0 * np.pi * time_var, T)
+        cols += [np.cos(angle), np.sin(angle)]
+    nexog = 0
+    for var in (exog if exog is not None else []):
+        var = np.asarray(var, dtype=np.float64).reshape(n, -1)
+        nexog += var.shape[1]
+        cols.append(var)
+    if dmy_covariates is not None:
+        cols.append(np.asarray(dmy_covariates, dtype=np.float64).reshape(n, -1))
+    return np.column_stack(cols), len(period), nexog
+
+
+def cosinor_amplitude_t(y, time_var, period):
+    """|t| of the amplitude(s) of ONE variable y [n] under the plain cosinor model (no tested variables, no covariates):
+    the un-permuted path A of the cosinor mediation (tm_models_randomise.py:398-403; pyfunc.py:2530-2551).  Host
+    algebra, k x k."""
+    X, nper, _ = cosinor_design(time_var, period)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    n, k = X.shape
+    invXX = np.linalg.inv(X.T @ X)
+    a = (invXX @ X.T) @ y
+    sigma = np.sqrt(np.sum((y - X @ a) ** 2) / (n - k))
+    out = np.empty(nper)
+    for i in range(nper):
+        c, s = 1 + 2 * i, 2 + 2 * i
+        amp = np.sqrt(a[c] ** 2 + a[s] ** 2)
+        acr = np.arctan(np.abs(-a[s] / a[c]))
+        var = invXX[c, c] * np.cos(acr) ** 2 - 2 * invXX[c, s] * np.sin(acr) * np.cos(acr) + invXX[s, s] * np.sin(acr) ** 2
+        out[i] = np.abs(amp / (sigma * np.sqrt(var)))
+    return out
+
+
 def pack_At(pinv, rp, layout=0, ldA=None):
     """[P, r, n] pseudo-inverse rows -> At float64 [n, ldA]; row i of design p goes to column p*rp + i (layout 0, the
     fp64 vector kernel) or (p // 8)*8*rp + i*8 + p % 8 (layout 1, "tile8", the tensor-core kernels: include/tfce_b200.h).
@@ -832,6 +871,72 @@ class PermutationEngine(object):
             XA = None
         z32 = self.sobelz_designs(XA, XB, ta_scalar, alg, caller_order=False)
         mx, status, _ = self.plan.run(z32, two_sided=False)
+        self.last_status = status
+        mx = mx[:, :, 0]
+        return self._download(mx.contiguous()) if download else mx
+
+    # -- tm-models cosinor ------------------------------------------------------------------------
+    def cosinor_stats(self, X, nper, nexog, perm_idx, mediation_ta=None, alg="aroian", want_f64=False, caller_order=True):
+        """Cosinor statistics (pyfunc.py:2406-2563) of the designs X[perm_idx[p]] (cosinor_design's column order): CUDA
+        float32 [P, 1 + 2*nper + nexog, ld] with rows [model F, (|t amplitude|, |t acrophase|) per period, t of every
+        tested column]; with mediation_ta (path A's amplitude t) the single row calc_indirect(ta, t of tested column
+        0), shape [P, 1, ld].  One plain contraction for the betas, then tmb_glm_cosinor_beta per (design, vertex)."""
+        import torch
+        X = np.asarray(X, dtype=np.float64)
+        if not has_intercept(X):
+            raise ValueError("X must have the intercept in column 0")
+        stack = row_permuted_stack(X, perm_idx)
+        P, r, n = stack["pinv"].shape
+        if n != self.Y.n:
+            raise ValueError("design has %d subjects, data has %d" % (n, self.Y.n))
+        if r > MAX_REGRESSORS:
+            raise ValueError("at most %d non-intercept regressors per design (got %d)" % (MAX_REGRESSORS, r))
+        nrows = 1 if mediation_ta is not None else 1 + 2 * nper + nexog
+        G_d = self._upload("G", stack["G"])
+        C_d = self._upload("cosC", np.ascontiguousarray(np.linalg.inv(stack["G"])))
+        yy = self.Y.sumsq(True)
+        s32 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float32, device=self.device)
+        s64 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
+        for a, cnt, beta in self._betas_chunks(stack["pinv"]):
+            _lib.check(_lib.lib().tmb_glm_cosinor_beta(
+                _lib.ptr(beta), self.Y.ld, self.Y.V, _lib.ptr(G_d[a:a + cnt]), _lib.ptr(C_d[a:a + cnt]), cnt, r, nper, nexog,
+                stack["dof"], _lib.ptr(yy), 0 if mediation_ta is None else 1,
+                0.0 if mediation_ta is None else float(mediation_ta), {"aroian": 0, "sobel": 1, "goodman": 2}[alg], _lib.ptr(s32[a:a + cnt]),
+                _lib.ptr(s64[a:a + cnt]) if s64 is not None else None, self.Y.ld, 1 if self.nan_to_zero else 0,
+                _lib.current_stream()))
+        if caller_order and self.colperm is not None:
+            s32 = self.to_caller_order(s32)
+            s64 = self.to_caller_order(s64) if s64 is not None else None
+        return (s32, s64) if want_f64 else s32
+
+    def cosinor_block(self, time_var, period, exog, dmy_covariates, perm_idx, download=True):
+        """One block of the tm-models cosinor loop (tmanalysis/tm_models_randomise.py:274-381): model F, per period
+        |t amplitude| and |t acrophase| -> one-sided TFCE -> scaled max, float32 [P, 1 + 2*nper, S]; t of every tested
+        column with both signs, float32 [P, nexog, S, 2] (None without tested variables)."""
+        X, nper, nexog = cosinor_design(time_var, period, exog, dmy_covariates)
+        s32 = self.cosinor_stats(X, nper, nexog, perm_idx, caller_order=False)
+        P, nrows, ld = s32.shape
+        npos = 1 + 2 * nper
+        mx, status, _ = self.plan.run(s32[:, :npos].contiguous().view(P * npos, ld), two_sided=False)
+        pos = mx.view(P, npos, self.plan.S, 2)[..., 0].contiguous()
+        tex = None
+        if nexog:
+            mx, status, _ = self.plan.run(s32[:, npos:].contiguous().view(P * nexog, ld), two_sided=True)
+            tex = mx.view(P, nexog, self.plan.S, 2)
+        self.last_status = status
+        if download:
+            return self._download(pos), (self._download(tex) if tex is not None else None)
+        return pos, tex
+
+    def cosinor_mediation_block(self, time_var, period, mediator, perm_idx, alg="aroian", download=True):
+        """One block of the cosinor mediation loop (tm_models_randomise.py:383-426): path A = |t amplitude| of the
+        un-permuted mediator's own cosinor fit (first period), path B = t of the mediator as the one tested column of
+        the data's row-permuted cosinor design; calc_indirect -> one-sided TFCE -> scaled max, float32 [P, S]."""
+        ta = cosinor_amplitude_t(mediator, time_var, period)[0]
+        X, nper, nexog = cosinor_design(time_var, period, [np.asarray(mediator, dtype=np.float64).reshape(-1)])
+        z32 = self.cosinor_stats(X, nper, nexog, perm_idx, mediation_ta=ta, alg=alg, caller_order=False)
+        P, _, ld = z32.shape
+        mx, status, _ = self.plan.run(z32.view(P, ld), two_sided=False)
         self.last_status = status
         mx = mx[:, :, 0]
         return self._download(mx.contiguous()) if download else mx

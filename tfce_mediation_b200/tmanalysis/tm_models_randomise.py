@@ -1,13 +1,13 @@
 #!/usr/bin/env python
-"""Permutation testing for tm-models -- drop-in for the GLM branch (-glm) of the reference's
-tmanalysis/tm_models_randomise.py:70-272: same options, same tmtemp_GLM_<surface|volume>/ inputs, same
-output_GLM_*/perm_GLM/perm_{Tstat_con<j>,Fstat_<name>}_TFCE_max{Vertex,Voxel}.csv rows ('%.4f'; for t statistics +t then
--t per shuffle).  Every shuffle permutes whole rows of the design [1, exog..., covariates] (pyfunc.py:2317-2321); blocks
+"""Permutation testing for tm-models -- drop-in for the GLM (-glm), mediation (-med), cosinor (-cos) and cosinor
+mediation (-mcos) branches of the reference's tmanalysis/tm_models_randomise.py:70-520: same options, same
+tmtemp_<model>_<surface|volume>/ inputs, same output_<model>_*/perm_*/perm_<stat>_TFCE_max{Vertex,Voxel}.csv rows
+('%.4f'; for t statistics +t then -t per shuffle).  Every shuffle permutes whole rows of the design [1, exog..., covariates] (pyfunc.py:2317-2321); blocks
 of shuffles run through the batched GPU engine (one fused fit per block: partial F of every variable from the extra
 sum of squares, t of the variables' columns), then TFCE and the scaled maximum.  Under torchrun the permutation range
-is sharded across ranks and rank 0 writes the rows in order.  The other model families of the reference script
-(cosinor, repeated-measures ANCOVA: tm_models_randomise.py:274-427,522-677) are not built yet and exit loudly; the
-mediation branch (-med, :430-520) is run_mediation below."""
+is sharded across ranks and rank 0 writes the rows in order.  The repeated-measures ANCOVA families of the reference script (-ofa / -tfa,
+tm_models_randomise.py:522-677) are not built and exit loudly; -med is run_mediation, -cos run_cosinor and -mcos
+run_cosinor_mediation below."""
 import argparse as ap
 import os
 from time import time
@@ -18,7 +18,7 @@ from . import _common as C
 from .. import parallel
 from ..pyfunc import check_blocks, rand_blocks, typeI_design
 
-DESCRIPTION = "Permutation testing for tm-models (GLM)"
+DESCRIPTION = "Permutation testing for tm-models (GLM, mediation, cosinor)"
 
 
 def getArgumentParser(ap=ap.ArgumentParser(description=DESCRIPTION)):
@@ -49,9 +49,13 @@ def run(opts):
     from ..engine import PermutationEngine
     if opts.mediation:
         return run_mediation(opts, start_time)
+    if opts.cosinor:
+        return run_cosinor(opts, start_time)
+    if opts.cosinormediation:
+        return run_cosinor_mediation(opts, start_time)
     if not opts.generalizedlinearmodel:
-        raise NotImplementedError("tm_models_randomise: only the GLM (-glm) and mediation (-med) branches are built on the "
-                                  "B200 path")
+        raise NotImplementedError("tm_models_randomise: the repeated-measures ANCOVA branches (-ofa, -tfa) are not built "
+                                  "on the B200 path (GLM, mediation, cosinor and cosinor mediation are)")
     if opts.tmi:
         raise NotImplementedError("tm_models_randomise: TMI input (-t) is not built on the B200 path")
     first, last = int(opts.range[0]), int(opts.range[1])
@@ -181,6 +185,104 @@ def run_mediation(opts, start_time):
                                                  np.stack(idx[c0:c0 + C.BLOCK])).max(axis=1))
     local = np.concatenate(res, axis=0) if res else np.zeros((0,), dtype=np.float32)
     allrows = C.gather(local)
+    if rank == 0:
+        C.append_rows("%s/perm_Zstat_%s_TFCE_%s.csv" % (outdir, medtype, suffix), allrows, "%.4f")
+        print("Finished. Randomization took %.1f seconds" % (time() - start_time))
+
+
+def _common_inputs(opts, model, permdir):
+    """tempdir / outdir names and the inputs every branch loads (tm_models_randomise.py:101-190)."""
+    if opts.tmi:
+        raise NotImplementedError("tm_models_randomise: TMI input (-t) is not built on the B200 path")
+    where = str(opts.surface[0]) if opts.surface else "volume"
+    tempdir, outdir = "tmtemp_%s_%s" % (model, where), "output_%s_%s/%s" % (model, where, permdir)
+    data = C.load("%s/data.npy" % tempdir)
+    optstfce = C.load("%s/optstfce.npy" % tempdir)
+    dmy_covariates = C.load("%s/dmy_covariates.npy" % tempdir)
+    if np.all(dmy_covariates) is None or dmy_covariates.ndim == 0:
+        dmy_covariates = None
+    surfs, suffix = _surfaces(opts, tempdir, float(optstfce[0]), float(optstfce[1]))
+    blocks = None
+    if opts.exchangeblock:
+        block_list = np.genfromtxt(opts.exchangeblock[0], dtype=str)
+        blocks = (block_list, check_blocks(block_list))
+    return tempdir, outdir, data, dmy_covariates, surfs, suffix, blocks
+
+
+def _draws(opts, a, b, n, blocks):
+    """One whole-row permutation per shuffle of [a, b], drawn as the reference does (:276-279)."""
+    idx = []
+    for iter_perm in range(a, b + 1):
+        if opts.seed is not None:
+            np.random.seed(int(iter_perm * 1000 + opts.seed))
+        idx.append(rand_blocks(*blocks) if blocks is not None else C.draw_row_permutation(n))
+    return np.stack(idx)
+
+
+def run_cosinor(opts, start_time):
+    """The cosinor branch (-cos), tm_models_randomise.py:103-123,274-381: per shuffle one row each in
+    perm_Fstat_model_*, perm_Tstat_amplitude_<period>_*, perm_Tstat_acrophase_<period>_*, and +t then -t in
+    perm_Tstat_<name | con<j>>_* for every tested column."""
+    from ..engine import PermutationEngine
+    tempdir, outdir, data, dmy_covariates, surfs, suffix, blocks = _common_inputs(opts, "cosinor", "perm_cosinor")
+    first, last = int(opts.range[0]), int(opts.range[1])
+    time_var = C.load("%s/time_var.npy" % tempdir)
+    period = [float(x) for x in np.asarray(C.load("%s/period.npy" % tempdir)).reshape(-1)]
+    exog_flat = C.load("%s/exog_flat.npy" % tempdir)
+    exog, varnames = None, []
+    if not (exog_flat.ndim == 0 or np.all(exog_flat) is None):
+        exog, count = [], 0
+        for nc in C.load("%s/exog_shape.npy" % tempdir):
+            exog.append(exog_flat[:, count:(count + nc)])
+            count += nc
+        varnames = C.load("%s/varnames.npy" % tempdir)
+    n = data.shape[0]
+    eng = PermutationEngine(data, surfs, two_sided=True)
+    rank, ws, a, b = C.shard(first, last)
+    if rank == 0:
+        os.makedirs(outdir, exist_ok=True)
+    nper = len(period)
+    numcon = int(np.concatenate(exog, 1).shape[1]) if exog is not None else 0
+    res_pos, res_t = [], []
+    for p0, p1 in C.chunks(a, b):
+        pos, tex = eng.cosinor_block(time_var, period, exog, dmy_covariates, _draws(opts, p0, p1, n, blocks))
+        res_pos.append(pos.max(axis=2))                  # max over the surfaces -> [P, 1 + 2*nper]
+        if tex is not None:
+            res_t.append(tex.max(axis=2))                # [P, numcon, 2]
+    all_pos = C.gather(np.concatenate(res_pos, axis=0) if res_pos else np.zeros((0, 1 + 2 * nper), dtype=np.float32))
+    all_t = C.gather(np.concatenate(res_t, axis=0) if res_t else np.zeros((0, numcon, 2), dtype=np.float32)) \
+        if numcon else None
+    if rank == 0:
+        C.append_rows("%s/perm_Fstat_model_TFCE_%s.csv" % (outdir, suffix), all_pos[:, 0], "%.4f")
+        for i, per in enumerate(period):
+            C.append_rows("%s/perm_Tstat_amplitude_%2.2f_TFCE_%s.csv" % (outdir, per, suffix), all_pos[:, 1 + 2 * i], "%.4f")
+            C.append_rows("%s/perm_Tstat_acrophase_%2.2f_TFCE_%s.csv" % (outdir, per, suffix), all_pos[:, 2 + 2 * i], "%.4f")
+        for j in range(numcon):                          # :325-350: names when there is one per column, else con<j>
+            name = "Tstat_%s" % varnames[j] if len(varnames) == numcon else "Tstat_con%d" % (j + 1)
+            C.append_rows("%s/perm_%s_TFCE_%s.csv" % (outdir, name, suffix), all_t[:, j, :].reshape(-1), "%.4f")
+        print("Finished. Randomization took %.1f seconds" % (time() - start_time))
+
+
+def run_cosinor_mediation(opts, start_time):
+    """The cosinor mediation branch (-mcos), tm_models_randomise.py:124-134,383-426: perm_Zstat_<medtype>_TFCE_*.csv, one
+    row per shuffle.  (Without -e the reference draws np.random.permutation(range(dmy_leftvar.shape[0])) with
+    dmy_leftvar never loaded in this branch and stops with a NameError; the number of subjects is used here.)"""
+    from ..engine import PermutationEngine
+    tempdir, outdir, data, _, surfs, suffix, blocks = _common_inputs(opts, "medcosinor", "perm_cosinor")
+    first, last = int(opts.range[0]), int(opts.range[1])
+    time_var = C.load("%s/time_var.npy" % tempdir)
+    period = [float(x) for x in np.asarray(C.load("%s/period.npy" % tempdir)).reshape(-1)]
+    dmy_mediator = C.load("%s/dmy_mediator.npy" % tempdir)
+    medtype = str(np.asarray(C.load("%s/medtype.npy" % tempdir)).reshape(-1)[0])
+    n = data.shape[0]
+    eng = PermutationEngine(data, surfs, two_sided=False)
+    rank, ws, a, b = C.shard(first, last)
+    if rank == 0:
+        os.makedirs(outdir, exist_ok=True)
+    res = []
+    for p0, p1 in C.chunks(a, b):
+        res.append(eng.cosinor_mediation_block(time_var, period, dmy_mediator, _draws(opts, p0, p1, n, blocks)).max(axis=1))
+    allrows = C.gather(np.concatenate(res, axis=0) if res else np.zeros((0,), dtype=np.float32))
     if rank == 0:
         C.append_rows("%s/perm_Zstat_%s_TFCE_%s.csv" % (outdir, medtype, suffix), allrows, "%.4f")
         print("Finished. Randomization took %.1f seconds" % (time() - start_time))
