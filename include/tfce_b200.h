@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TMB_ABI_VERSION 2
+#define TMB_ABI_VERSION 3
 #define TMB_F32 0
 #define TMB_F64 1
 
@@ -166,11 +166,13 @@ int64_t tmb_glm_packed_columns(int ydtype, int P, int rp);
  * [P, sum_i var_k[i]^2] holds, per design, the matrices inv(C[S_i, S_i]) one after the other, C = (X'X)^-1, because
  * RSS_without_i - RSS = b_S' inv(C_SS) b_S.  Output rows per design (ldt-strided, float32 and/or float64):
  *   [model F = ((TSS-RSS)/r) / (RSS/dof)  -- only when want_model != 0],  then per variable
- *   F_i = (RSS_without_i - RSS) / ((RSS/dof) * var_k[i])                  (pyfunc.py:2336-2354). */
+ *   F_i = (RSS_without_i - RSS) / ((RSS/dof) * var_k[i])                  (pyfunc.py:2336-2354).
+ * sstotal_dev float64 [V] or NULL: the TSS of the model F as the reference accumulates it (pyfunc.py:2331: in float32
+ * for float32 data; tmb_rm_totals with order_dev = NULL); NULL uses the float64 explained sum of squares. */
 int tmb_glm_fstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev, int64_t ldA,
                   const double *G_dev, const double *M_dev, int P, int r, int rp, int nvar, const int32_t *var_lo,
-                  const int32_t *var_k, int want_model, double dof, const double *yy_dev, float *f32_dev,
-                  double *f64_dev, int64_t ldt, int nan_to_zero, int layout, void *stream);
+                  const int32_t *var_k, int want_model, double dof, const double *yy_dev, const double *sstotal_dev,
+                  float *f32_dev, double *f64_dev, int64_t ldt, int nan_to_zero, int layout, void *stream);
 
 /* Stacked pseudo-inverses of P row-permuted copies of ONE design (the permutation loop of
  * vertex_tfce_multiple_regression_randomise.py:104-106, `nx = X[np.random.permutation(...)]`): permuting whole rows
@@ -190,7 +192,8 @@ int tmb_glm_tstat_beta(const double *beta_dev, int64_t ldb, int64_t V, const dou
                        int64_t ldt, int nan_to_zero, void *stream);
 int tmb_glm_fstat_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *G_dev, const double *M_dev, int P,
                        int r, int nvar, const int32_t *var_lo, const int32_t *var_k, int want_model, double dof,
-                       const double *yy_dev, float *f32_dev, double *f64_dev, int64_t ldt, int nan_to_zero, void *stream);
+                       const double *yy_dev, const double *sstotal_dev, float *f32_dev, double *f64_dev, int64_t ldt,
+                       int nan_to_zero, void *stream);
 int tmb_sobelz_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *GA_dev, const double *dA_dev, int rA,
                     int rowA, double dofA, const double *GB_dev, const double *dB_dev, int rB, int rowB, double dofB,
                     const double *yy_dev, const double *ta_scalar_dev, int P, int alg, float *z32_dev, double *z64_dev,
@@ -199,12 +202,37 @@ int tmb_sobelz_beta(const double *beta_dev, int64_t ldb, int64_t V, const double
 /* Cosinor statistics (pyfunc.py:2406-2563 glm_cosinor, the permutation branch used by tm_models_randomise.py:274-381)
  * from stored betas of the centred design [cos_0, sin_0, ..., cos_{nper-1}, sin_{nper-1}, nexog tested columns,
  * covariates] (r regressors, r <= 64).  G_dev, C_dev float64 [P, r, r]: the centred Gram matrix and its inverse.
+ * sstotal_dev float64 [V] or NULL: SS_Total as the reference accumulates it (tmb_rm_totals; float32 arithmetic for
+ * float32 data) for the model F's numerator SS_Total - SS_Residuals; NULL uses the float64 explained sum of squares.
  * mediation == 0: rows per design [model F, (|t amplitude_i|, |t acrophase_i|) per period, t of each tested column]
  * (1 + 2*nper + nexog rows).  mediation != 0 (tm_models_randomise.py:383-412): the single row
  * calc_indirect(ta, t of tested column 0) with `ta` the un-permuted path-A amplitude t (alg as in tmb_sobelz). */
 int tmb_glm_cosinor_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *G_dev, const double *C_dev, int P,
-                         int r, int nper, int nexog, double dof, const double *yy_dev, int mediation, double ta, int alg,
-                         float *s32_dev, double *s64_dev, int64_t ldt, int nan_to_zero, void *stream);
+                         int r, int nper, int nexog, double dof, const double *yy_dev, const double *sstotal_dev,
+                         int mediation, double ta, int alg, float *s32_dev, double *s64_dev, int64_t ldt, int nan_to_zero,
+                         void *stream);
+
+/* Repeated-measures ANCOVA (pyfunc.py:1712-2280 reg_rm_ancova_{one,two}_bs_factor in the permutation loop of
+ * tm_models_randomise.py:522-677).  The reference shuffles the rows of the long-format data [N = intervals*subjects, V]
+ * and regresses them on a chain of designs; here the data stay in place and every design is a whole-row permutation
+ * of a fixed base design.  Per shuffle: (1) tmb_glm_beta with the centred, row-permuted union of all design columns
+ * gives the cross-products c = Z'Y [rU, V]; (2) tmb_rm_totals gives SS_Total accumulated in the data's own precision in
+ * the shuffled row order (as numpy reduces axis 0; order_dev int32 [P, N]: shuffled row i = original row order[i]) and
+ * the residual of the subject-dummy regression (grp_rows_dev int32 [P, N]: the original rows subject by subject,
+ * grp_size_dev int32 [ngroups] rows each; order_dev NULL = the rows as stored, grp_rows_dev = sswithin_dev = NULL = SS_Total
+ * only -- that form also gives glm_cosinor's SS_Total, pyfunc.py:2492); (3) tmb_rm_ancova_stats forms the residual SS of every design,
+ * yy - c_S' inv(G_SS) c_S, and runs the host-written program that combines them as the reference does.
+ * meta (int32, the same array on the host and on the device): [0] designs D, [1] operations, [2] output rows, [3] rU,
+ * [8 + 66*d ..] = k_d, offset of inv(G_SS) (k_d x k_d, row-major) in mats_dev, k_d column indices; then 4 ints per
+ * operation (op, dst, a, b) and the output registers.  Registers: 0 SS_Total, 1 subject residual, 2+d residual SS of
+ * design d, the rest temporaries (< 96).  op 0: dst = a - b; 1: a + b; 2: a / consts_dev[b]; 3: a / b; 4: 0. */
+int tmb_rm_totals(const void *Y_dev, int ydtype, int N, int64_t V, int64_t ldy, const int32_t *order_dev,
+                  const int32_t *grp_rows_dev, const int32_t *grp_size_dev, int ngroups, int P, double *sstotal_dev,
+                  double *sswithin_dev, int64_t ldo, void *stream);
+int tmb_rm_ancova_stats(const double *cross_dev, int64_t ldb, int64_t V, int P, const int32_t *meta_dev,
+                        const int32_t *meta_host, const double *mats_dev, const double *consts_dev, const double *yy_dev,
+                        const double *sstotal_dev, const double *sswithin_dev, int64_t ldo, float *f32_dev,
+                        double *f64_dev, int64_t ldt, int nan_to_zero, void *stream);
 
 /* betas only == cynumstats.pyx:28-29 cy_lin_lstsqr_mat: beta64_dev float64 [nrows, ldt] for the nrows
  * pseudo-inverse rows stored as the first nrows columns of At_dev (ldA a multiple of 128). */

@@ -84,17 +84,14 @@ def test_glm_typeI_dropin_matches_reference_golden():
     g, exog = _golden()
     F, Fvar, T = pyfunc.glm_typeI(g["data"], exog, dmy_covariates=g["cov"], output_tvalues=True, verbose=False)
     assert _close64(Fvar, g["Fvar"]) and _close64(T, g["T"])
-    # The MODEL F of float32 data carries float32 noise in the reference itself: pyfunc.py:2331 accumulates SS_Total
-    # with numpy float32 arithmetic (mean, squares and pairwise sum of the float32 data), the residual SS in float64.
-    # The GPU forms both in float64, so on float32 data the model F agrees to float32 accuracy -- 1e-5 relative (the north
-    # star's fp32 tolerance) plus the reference's own absolute noise, eps32 * SS_Total / (DF * MS) ~ 1e-5 -- and on
-    # float64 data to 1e-10.  The per-variable F -- the statistic the permutation loop uses
-    # (tm_models_randomise.py:206-210) -- is a difference in which SS_Total cancels, and agrees to 1e-10 either way.
-    assert np.allclose(F, g["F"], rtol=1e-5, atol=2e-5)
+    # The MODEL F of float32 data: pyfunc.py:2331 accumulates SS_Total with numpy float32 arithmetic (mean, squares and sum
+    # of the float32 data, row after row) and the residual SS in float64.  tmb_rm_totals restates that accumulation
+    # (Device matrix sstotal_reference), so the model F agrees to float64 accuracy as well.
+    assert _close64(F, g["F"])
     F64, Fvar64 = pyfunc.glm_typeI(g["data"].astype(np.float64), exog, dmy_covariates=g["cov"], verbose=False)
     assert _close64(F64, g["F_f64"]) and _close64(Fvar64, g["Fvar_f64"])
     F0, Fvar0 = pyfunc.glm_typeI(g["data"], exog, verbose=False)
-    assert np.allclose(F0, g["F_nocov"], rtol=1e-5, atol=2e-5) and _close64(Fvar0, g["Fvar_nocov"])
+    assert _close64(F0, g["F_nocov"]) and _close64(Fvar0, g["Fvar_nocov"])
     for p, r in enumerate(g["perms"][:3]):
         Fp = pyfunc.glm_typeI(g["data"], exog, dmy_covariates=g["cov"], verbose=False, rand_array=r)[1]
         assert _close64(Fp, g["perm_Fvar"][p])

@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.tmb_abi_version() == _lib.ABI_VERSION == 2
+    assert L.tmb_abi_version() == _lib.ABI_VERSION == 3
     assert isinstance(L.tmb_device_count(), int)
     assert L.tmb_last_error() is not None
 

@@ -75,3 +75,15 @@ class DeviceMatrix(object):
                                                 1 if center else 0, _lib.ptr(yy), None, _lib.current_stream()))
             self._yy[key] = yy
         return self._yy[key]
+
+    def sstotal_reference(self):
+        """float64 [ld]: SS_Total as the reference forms it, np.sum((endog - np.mean(endog, 0))**2, 0) (pyfunc.py:2331,
+        :2492): numpy reduces axis 0 row after row in the data's own type, so float32 data give a float32-accumulated
+        value (widened).  The model F statistics subtract the float64 residual SS from THIS number.  Cached."""
+        import torch
+        if "ref" not in self._yy:
+            tot = torch.empty((self.ld,), dtype=torch.float64, device=self.t.device)
+            _lib.check(_lib.lib().tmb_rm_totals(_lib.ptr(self.t), self.dtype_code, self.n, self.V, self.ld, None, None, None,
+                                                0, 1, _lib.ptr(tot), None, self.ld, _lib.current_stream()))
+            self._yy["ref"] = tot
+        return self._yy["ref"]

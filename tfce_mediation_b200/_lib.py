@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libtfce_b200.so")
 F32, F64 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class TmbError(RuntimeError):
@@ -50,14 +50,16 @@ SIGNATURES = {
     "tmb_glm_rp": (_int, [_int, _int]),
     "tmb_glm_packed_columns": (_i64, [_int, _int, _int]),
     "tmb_glm_tstat_beta": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _int, _int, _int, _f64, _vp, _vp, _vp, _i64, _int, _vp]),
-    "tmb_glm_fstat_beta": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _int, _int, _vp, _vp, _int, _f64, _vp, _vp, _vp, _i64,
-                                  _int, _vp]),
+    "tmb_glm_fstat_beta": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _int, _int, _vp, _vp, _int, _f64, _vp, _vp, _vp, _vp,
+                                  _i64, _int, _vp]),
     "tmb_sobelz_beta": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _int, _f64, _vp, _vp, _int, _int, _f64, _vp, _vp, _int,
                                _int, _vp, _vp, _i64, _vp]),
-    "tmb_glm_cosinor_beta": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _int, _int, _int, _f64, _vp, _int, _f64, _int, _vp, _vp,
+    "tmb_glm_cosinor_beta": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _int, _int, _int, _f64, _vp, _vp, _int, _f64, _int, _vp, _vp,
                                     _i64, _int, _vp]),
+    "tmb_rm_totals": (_int, [_vp, _int, _int, _i64, _i64, _vp, _vp, _vp, _int, _int, _vp, _vp, _i64, _vp]),
+    "tmb_rm_ancova_stats": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _vp]),
     "tmb_glm_fstat": (_int, [_vp, _int, _int, _i64, _i64, _vp, _i64, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _int,
-                             _f64, _vp, _vp, _vp, _i64, _int, _int, _vp]),
+                             _f64, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
     "tmb_glm_pack_rowperm": (_int, [_vp, _int, _int, _vp, _int, _int, _vp, _i64, _int, _vp]),
     "tmb_glm_beta": (_int, [_vp, _int, _int, _i64, _i64, _vp, _i64, _int, _vp, _i64, _vp]),
     "tmb_glm_direct": (_int, [_vp, _int, _int, _i64, _i64, _vp, _vp, _int, _vp, _f64, _f64, _vp, _vp, _vp, _i64,

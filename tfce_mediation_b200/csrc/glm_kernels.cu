@@ -89,6 +89,7 @@ struct GlmParams {
     // sobel: rows [0, rA) of each design group are path A, rows [rA, rA+rB) path B
     const double *GB; const double *dB; int rA, rB, rowA, rowB; double dofB;
     const double *ta_scalar; int alg;
+    const double *sstot;                                         // the reference's own SS_Total (model F numerator) or null
     int cos_nexog, cos_mediation; double cos_ta;                 // mode 4 (cosinor): tested columns, mediation row, path-A t
     // F statistics (mode 3): per design the inverse blocks M_i = inv((X'X)^-1[S_i, S_i]) of every tested variable,
     // stored one after the other (k_i x k_i each, msz doubles per design); variable i covers rows [var_lo[i], +var_k[i])
@@ -268,9 +269,12 @@ __device__ __forceinline__ void epilogue(const GlmParams &p, const double (&acc)
             if (first) {
 #pragma unroll
                 for (int c = 0; c < TN; ++c) {
-                    double f = __ddiv_rn(__ddiv_rn(ssb[c], (double)r), ms[c]);
+                    // model F = ((SS_Total - SS_Residuals) / (k-1)) / MS_Residuals with the reference's own SS_Total
+                    const int64_t vc = tile_col(v0, tn, c);
+                    const double between = (p.sstot && vc < p.V) ? __dsub_rn(p.sstot[vc], yy[c] - ssb[c]) : ssb[c];
+                    double f = __ddiv_rn(__ddiv_rn(between, (double)r), ms[c]);
                     if (p.nan_to_zero && f != f) f = 0.0;
-                    if (tile_col(v0, tn, c) >= p.V) f = 0.0;
+                    if (vc >= p.V) f = 0.0;
                     o64[c] = f;
                     o32[c] = __double2float_rn(f);
                 }
@@ -691,7 +695,8 @@ __device__ __forceinline__ void dmma_vertex_stats(const GlmParams &p, int perm, 
         const double ms = __ddiv_rn(yyv - ssb, p.dof);
         const int first = p.row0 == 0 ? 1 : 0;
         if (first) {
-            double f = __ddiv_rn(__ddiv_rn(ssb, (double)r), ms);
+            const double between = (p.sstot && inside) ? __dsub_rn(p.sstot[v], yyv - ssb) : ssb;
+            double f = __ddiv_rn(__ddiv_rn(between, (double)r), ms);
             if (p.nan_to_zero && f != f) f = 0.0;
             if (!inside) f = 0.0;
             const size_t off = (size_t)perm * p.nrows * p.ldt + v;
@@ -1051,7 +1056,8 @@ __global__ void __launch_bounds__(128) glm_stats_from_beta_kernel(GlmParams p, c
         const double ms = __ddiv_rn(yyv - ssb, p.dof);
         const int first = p.row0 == 0 ? 1 : 0;
         if (first) {
-            double f = __ddiv_rn(__ddiv_rn(ssb, (double)r), ms);
+            const double between = (p.sstot && inside) ? __dsub_rn(p.sstot[v], yyv - ssb) : ssb;
+            double f = __ddiv_rn(__ddiv_rn(between, (double)r), ms);
             if (p.nan_to_zero && f != f) f = 0.0;
             if (!inside) f = 0.0;
             const size_t off = (size_t)perm * p.nrows * p.ldt + v;
@@ -1104,7 +1110,9 @@ __global__ void __launch_bounds__(128) glm_stats_from_beta_kernel(GlmParams p, c
             else if (p.alg == 2) s = __dsub_rn(s, cross);
             put(0, __ddiv_rn(1.0, __dsqrt_rn(s)));
         } else {
-            put(0, __ddiv_rn(__ddiv_rn(ssb, (double)r), ms));
+            // Fmodel = ((SS_Total - SS_Residuals) / DF_Between) / MS_Residuals (:2492-2495)
+            const double between = p.sstot ? __dsub_rn(inside ? p.sstot[v] : 0.0, sse) : ssb;
+            put(0, __ddiv_rn(__ddiv_rn(between, (double)r), ms));
             for (int i = 0; i < nper; ++i) {
                 const double be = b[2 * i], ga = b[2 * i + 1];
                 const double amp = __dsqrt_rn(__dadd_rn(__dmul_rn(be, be), __dmul_rn(ga, ga)));
@@ -1279,8 +1287,8 @@ extern "C" int tmb_glm_tstat(const void *Y_dev, int ydtype, int n, int64_t V, in
 extern "C" int tmb_glm_fstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev,
                              int64_t ldA, const double *G_dev, const double *M_dev, int P, int r, int rp, int nvar,
                              const int32_t *var_lo, const int32_t *var_k, int want_model, double dof,
-                             const double *yy_dev, float *f32_dev, double *f64_dev, int64_t ldt, int nan_to_zero,
-                             int layout, void *stream) {
+                             const double *yy_dev, const double *sstotal_dev, float *f32_dev, double *f64_dev,
+                             int64_t ldt, int nan_to_zero, int layout, void *stream) {
     TMB_REQUIRE(Y_dev && At_dev && G_dev && yy_dev && (f32_dev || f64_dev), "tmb_glm_fstat: null pointer");
     TMB_REQUIRE(n > 0 && V > 0 && P > 0 && r >= 1 && r <= rp && nvar >= 0 && nvar <= 8 && (nvar == 0 || (M_dev && var_lo && var_k)) &&
                     (nvar > 0 || want_model),
@@ -1291,6 +1299,7 @@ extern "C" int tmb_glm_fstat(const void *Y_dev, int ydtype, int n, int64_t V, in
     p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.G = G_dev; p.M = M_dev;
     p.P = P; p.r = r; p.rp = rp; p.row0 = want_model ? 0 : 1; p.nrows = nvar + (want_model ? 1 : 0); p.dof = dof; p.yy = yy_dev;
     p.t32 = f32_dev; p.t64 = f64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 3; p.nvar = nvar; p.layout = layout;
+    p.sstot = sstotal_dev;
     for (int i = 0; i < nvar; ++i) {
         TMB_REQUIRE(var_lo[i] >= 0 && var_k[i] >= 1 && var_lo[i] + var_k[i] <= r,
                     "tmb_glm_fstat: variable %d covers rows [%d, %d) of %d", i, var_lo[i], var_lo[i] + var_k[i], r);
@@ -1404,8 +1413,8 @@ extern "C" int tmb_glm_tstat_beta(const double *beta_dev, int64_t ldb, int64_t V
 
 extern "C" int tmb_glm_fstat_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *G_dev, const double *M_dev,
                                   int P, int r, int nvar, const int32_t *var_lo, const int32_t *var_k, int want_model,
-                                  double dof, const double *yy_dev, float *f32_dev, double *f64_dev, int64_t ldt,
-                                  int nan_to_zero, void *stream) {
+                                  double dof, const double *yy_dev, const double *sstotal_dev, float *f32_dev,
+                                  double *f64_dev, int64_t ldt, int nan_to_zero, void *stream) {
     TMB_REQUIRE(beta_dev && G_dev && yy_dev && (f32_dev || f64_dev), "tmb_glm_fstat_beta: null pointer");
     TMB_REQUIRE(V > 0 && P > 0 && r >= 1 && nvar >= 0 && nvar <= 8 && (nvar == 0 || (M_dev && var_lo && var_k)) &&
                     (nvar > 0 || want_model) && ldb >= V && ldt >= V, "tmb_glm_fstat_beta: bad shape");
@@ -1413,6 +1422,7 @@ extern "C" int tmb_glm_fstat_beta(const double *beta_dev, int64_t ldb, int64_t V
     GlmParams p{};
     p.V = V; p.G = G_dev; p.M = M_dev; p.P = P; p.r = r; p.row0 = want_model ? 0 : 1; p.nrows = nvar + (want_model ? 1 : 0);
     p.dof = dof; p.yy = yy_dev; p.t32 = f32_dev; p.t64 = f64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 3; p.nvar = nvar;
+    p.sstot = sstotal_dev;
     for (int i = 0; i < nvar; ++i) {
         TMB_REQUIRE(var_lo[i] >= 0 && var_k[i] >= 1 && var_lo[i] + var_k[i] <= r,
                     "tmb_glm_fstat_beta: variable %d covers rows [%d, %d) of %d", i, var_lo[i], var_lo[i] + var_k[i], r);
@@ -1422,9 +1432,9 @@ extern "C" int tmb_glm_fstat_beta(const double *beta_dev, int64_t ldb, int64_t V
 }
 
 extern "C" int tmb_glm_cosinor_beta(const double *beta_dev, int64_t ldb, int64_t V, const double *G_dev, const double *C_dev,
-                                    int P, int r, int nper, int nexog, double dof, const double *yy_dev, int mediation,
-                                    double ta, int alg, float *s32_dev, double *s64_dev, int64_t ldt, int nan_to_zero,
-                                    void *stream) {
+                                    int P, int r, int nper, int nexog, double dof, const double *yy_dev,
+                                    const double *sstotal_dev, int mediation, double ta, int alg, float *s32_dev,
+                                    double *s64_dev, int64_t ldt, int nan_to_zero, void *stream) {
     TMB_REQUIRE(beta_dev && G_dev && C_dev && yy_dev && (s32_dev || s64_dev), "tmb_glm_cosinor_beta: null pointer");
     TMB_REQUIRE(V > 0 && P > 0 && nper >= 1 && nexog >= 0 && 2 * nper + nexog <= r && ldb >= V && ldt >= V &&
                     (!mediation || nexog >= 1) && alg >= 0 && alg <= 2,
@@ -1432,7 +1442,7 @@ extern "C" int tmb_glm_cosinor_beta(const double *beta_dev, int64_t ldb, int64_t
     TMB_DEVICE_OF(beta_dev, "tmb_glm_cosinor_beta");
     GlmParams p{};
     p.V = V; p.G = G_dev; p.M = C_dev; p.P = P; p.r = r; p.nvar = nper; p.cos_nexog = nexog; p.dof = dof; p.yy = yy_dev;
-    p.cos_mediation = mediation ? 1 : 0; p.cos_ta = ta; p.alg = alg; p.nrows = mediation ? 1 : 1 + 2 * nper + nexog;
+    p.cos_mediation = mediation ? 1 : 0; p.cos_ta = ta; p.alg = alg; p.sstot = sstotal_dev; p.nrows = mediation ? 1 : 1 + 2 * nper + nexog;
     p.t32 = s32_dev; p.t64 = s64_dev; p.ldt = ldt; p.nan_to_zero = nan_to_zero; p.mode = 4;
     return launch_stats_from_beta(p, beta_dev, ldb, (cudaStream_t)stream);
 }

@@ -568,7 +568,7 @@ class PermutationEngine(object):
                 _lib.check(_lib.lib().tmb_glm_fstat_beta(
                     _lib.ptr(beta), self.Y.ld, self.Y.V, _lib.ptr(G_d[a:a + cnt]), _lib.ptr(M_d[a:a + cnt]), cnt, r, nvar,
                     lo.ctypes.data, kk.ctypes.data, 1 if want_model else 0, stack["dof"], _lib.ptr(yy),
-                    _lib.ptr(f32[a:a + cnt]), _lib.ptr(f64[a:a + cnt]) if f64 is not None else None, self.Y.ld,
+                    _lib.ptr(self.Y.sstotal_reference()) if want_model else None, _lib.ptr(f32[a:a + cnt]), _lib.ptr(f64[a:a + cnt]) if f64 is not None else None, self.Y.ld,
                     1 if self.nan_to_zero else 0, _lib.current_stream()))
             out = (f32, f64)
         else:
@@ -592,7 +592,7 @@ class PermutationEngine(object):
         _lib.check(_lib.lib().tmb_glm_fstat(
             _lib.ptr(self.Y.t), self.Y.dtype_code, self.Y.n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA, _lib.ptr(G_d),
             _lib.ptr(M_d), P, r, rp, nvar, lo.ctypes.data, kk.ctypes.data, 1 if want_model else 0, dof, _lib.ptr(yy),
-            _lib.ptr(f32), _lib.ptr(f64), self.Y.ld, 1 if self.nan_to_zero else 0, layout, _lib.current_stream()))
+            _lib.ptr(self.Y.sstotal_reference()) if want_model else None, _lib.ptr(f32), _lib.ptr(f64), self.Y.ld, 1 if self.nan_to_zero else 0, layout, _lib.current_stream()))
         return f32, f64
 
     def fstat_rowperm(self, X, var_lo, var_k, perm_idx, want_model=False):
@@ -895,12 +895,13 @@ class PermutationEngine(object):
         G_d = self._upload("G", stack["G"])
         C_d = self._upload("cosC", np.ascontiguousarray(np.linalg.inv(stack["G"])))
         yy = self.Y.sumsq(True)
+        sstot = self.Y.sstotal_reference()
         s32 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float32, device=self.device)
         s64 = torch.empty((P, nrows, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
         for a, cnt, beta in self._betas_chunks(stack["pinv"]):
             _lib.check(_lib.lib().tmb_glm_cosinor_beta(
                 _lib.ptr(beta), self.Y.ld, self.Y.V, _lib.ptr(G_d[a:a + cnt]), _lib.ptr(C_d[a:a + cnt]), cnt, r, nper, nexog,
-                stack["dof"], _lib.ptr(yy), 0 if mediation_ta is None else 1,
+                stack["dof"], _lib.ptr(yy), _lib.ptr(sstot), 0 if mediation_ta is None else 1,
                 0.0 if mediation_ta is None else float(mediation_ta), {"aroian": 0, "sobel": 1, "goodman": 2}[alg], _lib.ptr(s32[a:a + cnt]),
                 _lib.ptr(s64[a:a + cnt]) if s64 is not None else None, self.Y.ld, 1 if self.nan_to_zero else 0,
                 _lib.current_stream()))
@@ -940,6 +941,66 @@ class PermutationEngine(object):
         self.last_status = status
         mx = mx[:, :, 0]
         return self._download(mx.contiguous()) if download else mx
+
+    # -- tm-models repeated-measures ANCOVA ----------------------------------------------------------
+    def rm_ancova_stats(self, model, shuffles, rand_arrays, want_f64=False, caller_order=True, budget=1.5e9):
+        """F statistics of pyfunc.py:1712-2280 reg_rm_ancova_{one,two}_bs_factor for P shuffles of the long-format data
+        this engine holds ([intervals*subjects, V]); model: rmancova.RmAncovaModel; shuffles / rand_arrays as in
+        RmAncovaModel.operands.  CUDA float32 [P, model.nout, ld] (and float64 when want_f64).  Per chunk of shuffles:
+        one plain contraction for the cross-products of the union design (tmb_glm_beta), the order-dependent totals
+        (tmb_rm_totals) and the statistics program (tmb_rm_ancova_stats)."""
+        import torch
+        if model.N != self.Y.n:
+            raise ValueError("model has %d long-format rows, data has %d" % (model.N, self.Y.n))
+        P = len(shuffles) if shuffles is not None else len(rand_arrays)
+        rU, N, ld = model.rU, model.N, self.Y.ld
+        dev = getattr(model, "_device_state", None)
+        if dev is None or dev[0] != self.device:
+            dev = (self.device, torch.from_numpy(model.meta).to(self.device), torch.from_numpy(model.mats).to(self.device),
+                   torch.from_numpy(model.consts).to(self.device), torch.from_numpy(model.group_sizes).to(self.device))
+            model._device_state = dev
+        _, meta_d, mats_d, consts_d, sizes_d = dev
+        yy = self.Y.sumsq(True)
+        f32 = torch.empty((P, model.nout, ld), dtype=torch.float32, device=self.device)
+        f64 = torch.empty((P, model.nout, ld), dtype=torch.float64, device=self.device) if want_f64 else None
+        per = max(1, int(budget // (rU * ld * 8)))
+        for a in range(0, P, per):
+            b = min(P, a + per)
+            cnt = b - a
+            A, order, grp_rows = model.operands(None if shuffles is None else shuffles[a:b],
+                                                None if rand_arrays is None else rand_arrays[a:b])
+            rows = cnt * rU
+            ldA = round_up(rows, TILE_M)
+            At = np.zeros((N, ldA), dtype=np.float64)
+            At[:, :rows] = A
+            At_d = self._upload("rm_At", At)
+            order_d, grp_d = self._upload("rm_order", order), self._upload("rm_grp", grp_rows)
+            cross = torch.empty((rows, ld), dtype=torch.float64, device=self.device)
+            lib, st = _lib.lib(), _lib.current_stream()
+            _lib.check(lib.tmb_glm_beta(_lib.ptr(self.Y.t), self.Y.dtype_code, N, self.Y.V, ld, _lib.ptr(At_d), ldA, rows,
+                                        _lib.ptr(cross), ld, st))
+            tot = torch.empty((2, cnt, ld), dtype=torch.float64, device=self.device)
+            _lib.check(lib.tmb_rm_totals(_lib.ptr(self.Y.t), self.Y.dtype_code, N, self.Y.V, ld, _lib.ptr(order_d),
+                                         _lib.ptr(grp_d), _lib.ptr(sizes_d), int(model.group_sizes.shape[0]), cnt,
+                                         _lib.ptr(tot[0]), _lib.ptr(tot[1]), ld, st))
+            _lib.check(lib.tmb_rm_ancova_stats(
+                _lib.ptr(cross), ld, self.Y.V, cnt, _lib.ptr(meta_d), _lib.ptr(model.meta), _lib.ptr(mats_d),
+                _lib.ptr(consts_d), _lib.ptr(yy), _lib.ptr(tot[0]), _lib.ptr(tot[1]), ld, _lib.ptr(f32[a:b]),
+                _lib.ptr(f64[a:b]) if f64 is not None else None, ld, 1 if self.nan_to_zero else 0, st))
+        if caller_order and self.colperm is not None:
+            f32 = self.to_caller_order(f32)
+            f64 = self.to_caller_order(f64) if f64 is not None else None
+        return (f32, f64) if want_f64 else f32
+
+    def rm_ancova_block(self, model, shuffles, rand_arrays, download=True):
+        """One block of the repeated-measures ANCOVA permutation loop (tm_models_randomise.py:522-677): every F map ->
+        one-sided TFCE -> scaled max, float32 [P, model.nout, S] (rows in the reference's return order, model.names)."""
+        f32 = self.rm_ancova_stats(model, shuffles, rand_arrays, caller_order=False)
+        P, nout, ld = f32.shape
+        mx, status, _ = self.plan.run(f32.view(P * nout, ld), two_sided=False)
+        self.last_status = status
+        mx = mx.view(P, nout, self.plan.S, 2)[..., 0].contiguous()
+        return self._download(mx) if download else mx
 
     def mediation_blocks(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", block=256):
         """Many mediation shuffles, `block` at a time, software-pipelined like regression_blocks: while block i is swept

@@ -1,13 +1,13 @@
 #!/usr/bin/env python
-"""Permutation testing for tm-models -- drop-in for the GLM (-glm), mediation (-med), cosinor (-cos) and cosinor
-mediation (-mcos) branches of the reference's tmanalysis/tm_models_randomise.py:70-520: same options, same
+"""Permutation testing for tm-models -- drop-in for the reference's tmanalysis/tm_models_randomise.py:70-677, all six
+model families: GLM (-glm), mediation (-med), cosinor (-cos), cosinor mediation (-mcos) and the repeated-measures ANCOVA
+with one or two between-subject factors (-ofa, -tfa): same options, same
 tmtemp_<model>_<surface|volume>/ inputs, same output_<model>_*/perm_*/perm_<stat>_TFCE_max{Vertex,Voxel}.csv rows
 ('%.4f'; for t statistics +t then -t per shuffle).  Every shuffle permutes whole rows of the design [1, exog..., covariates] (pyfunc.py:2317-2321); blocks
 of shuffles run through the batched GPU engine (one fused fit per block: partial F of every variable from the extra
 sum of squares, t of the variables' columns), then TFCE and the scaled maximum.  Under torchrun the permutation range
-is sharded across ranks and rank 0 writes the rows in order.  The repeated-measures ANCOVA families of the reference script (-ofa / -tfa,
-tm_models_randomise.py:522-677) are not built and exit loudly; -med is run_mediation, -cos run_cosinor and -mcos
-run_cosinor_mediation below."""
+is sharded across ranks and rank 0 writes the rows in order.  -med is run_mediation, -cos run_cosinor, -mcos run_cosinor_mediation and -ofa / -tfa
+run_rm_ancova below."""
 import argparse as ap
 import os
 from time import time
@@ -18,7 +18,7 @@ from . import _common as C
 from .. import parallel
 from ..pyfunc import check_blocks, rand_blocks, typeI_design
 
-DESCRIPTION = "Permutation testing for tm-models (GLM, mediation, cosinor)"
+DESCRIPTION = "Permutation testing for tm-models"
 
 
 def getArgumentParser(ap=ap.ArgumentParser(description=DESCRIPTION)):
@@ -53,9 +53,10 @@ def run(opts):
         return run_cosinor(opts, start_time)
     if opts.cosinormediation:
         return run_cosinor_mediation(opts, start_time)
+    if opts.onebetweenssubjectfactor or opts.twobetweenssubjectfactor:
+        return run_rm_ancova(opts, start_time)
     if not opts.generalizedlinearmodel:
-        raise NotImplementedError("tm_models_randomise: the repeated-measures ANCOVA branches (-ofa, -tfa) are not built "
-                                  "on the B200 path (GLM, mediation, cosinor and cosinor mediation are)")
+        raise SystemExit("tm_models_randomise: choose one of -glm, -med, -cos, -mcos, -ofa, -tfa")
     if opts.tmi:
         raise NotImplementedError("tm_models_randomise: TMI input (-t) is not built on the B200 path")
     first, last = int(opts.range[0]), int(opts.range[1])
@@ -285,6 +286,66 @@ def run_cosinor_mediation(opts, start_time):
     allrows = C.gather(np.concatenate(res, axis=0) if res else np.zeros((0,), dtype=np.float32))
     if rank == 0:
         C.append_rows("%s/perm_Zstat_%s_TFCE_%s.csv" % (outdir, medtype, suffix), allrows, "%.4f")
+        print("Finished. Randomization took %.1f seconds" % (time() - start_time))
+
+
+def run_rm_ancova(opts, start_time):
+    """The repeated-measures ANCOVA branches (-ofa / -tfa), tm_models_randomise.py:135-158,522-677: per shuffle one row in
+    perm_Fstat_<factor>_*, perm_Fstat_time_*, perm_Fstat_<factor>.X.time_* (and for two factors the second factor, the
+    factors' interaction and their interactions with time).  The reference shuffles the rows of the long-format data IN
+    PLACE every iteration (pyfunc.py:1826,2148), so shuffle i sees the composition of all shuffles since the start of the
+    range; the same composition of row orders is replayed here (every rank from the first permutation of the range)
+    while the data stay put in HBM.  ('long' data: the reference computes the number of intervals as a float and stops
+    at range(s-1) under Python 3; the integer is used here.)"""
+    from ..engine import PermutationEngine
+    from ..rmancova import RmAncovaModel
+    two = bool(opts.twobetweenssubjectfactor)
+    model_name = "rmANCOVA2BS" if two else "rmANCOVA1BS"
+    tempdir, outdir, data, dmy_covariates, surfs, suffix, blocks = _common_inputs(opts, model_name, "perm_" + model_name)
+    first, last = int(opts.range[0]), int(opts.range[1])
+    dmy_factor1 = C.load("%s/dmy_factor1.npy" % tempdir)
+    dmy_factor2 = C.load("%s/dmy_factor2.npy" % tempdir) if two else None
+    factors = [str(f) for f in np.asarray(C.load("%s/factors.npy" % tempdir)).reshape(-1)]
+    dmy_subjects = C.load("%s/dmy_subjects.npy" % tempdir)
+    dformat = str(np.asarray(C.load("%s/dformat.npy" % tempdir)).reshape(-1)[0])
+    n = len(dmy_factor1)
+    if dformat == "short":
+        if data.ndim == 2:
+            data = data[:, :, np.newaxis]
+        s = data.shape[0]
+        data = data.reshape(s * n, data.shape[2])
+    elif dformat == "long":
+        s = int(len(data) // n)
+    else:
+        raise ValueError("data format must be short or long")
+    N = s * n
+    model = RmAncovaModel(n, s, [dmy_factor1, dmy_factor2] if two else [dmy_factor1], dmy_subjects, dmy_covariates)
+    eng = PermutationEngine(data, surfs, two_sided=False)
+    rank, ws, a, b = C.shard(first, last)
+    if rank == 0:
+        os.makedirs(outdir, exist_ok=True)
+    pi = np.arange(N)
+    shuffles, rands = [], []
+    for iter_perm in range(first, b + 1):
+        if opts.seed is not None:
+            np.random.seed(int(iter_perm * 1000 + opts.seed))
+        rand_array = rand_blocks(*blocks) if blocks is not None else C.draw_row_permutation(n)
+        np.random.shuffle(pi)                        # the draws of shuffling the data rows themselves
+        if iter_perm >= a:
+            shuffles.append(pi.copy())
+            rands.append(rand_array)
+    res = []
+    for c0 in range(0, len(shuffles), C.BLOCK):
+        res.append(eng.rm_ancova_block(model, shuffles[c0:c0 + C.BLOCK], rands[c0:c0 + C.BLOCK]).max(axis=2))
+    allrows = C.gather(np.concatenate(res, axis=0) if res else np.zeros((0, model.nout), dtype=np.float32))
+    if rank == 0:
+        if two:          # :604-677, the reference's return order F_a, F_b, F_ab, F_s, F_sa, F_sb, F_sab; factors.npy holds
+            f1, f2 = factors[0], factors[2]          # [name1, type1, name2, type2]
+            names = [f1, f2, "%s.X.%s" % (f1, f2), "time", "%s.X.time" % f1, "%s.X.time" % f2, "%s.X.%s.X.time" % (f1, f2)]
+        else:            # :537-574
+            names = [factors[0], "time", "%s.X.time" % factors[0]]
+        for j, name in enumerate(names):
+            C.append_rows("%s/perm_Fstat_%s_TFCE_%s.csv" % (outdir, name, suffix), allrows[:, j], "%.4f")
         print("Finished. Randomization took %.1f seconds" % (time() - start_time))
 
 
