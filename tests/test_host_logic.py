@@ -152,8 +152,14 @@ def test_step2_wrapper_rounding_and_blocks_follow_the_reference():
     assert argv == ["-r", "1", "5000", "-s", "area", "-v", "1", "2", "--seed", "7"]
     mod, argv = s2.driver_call(p.parse_args(["--voxel", "-n", "1000", "-m", "M", "-p", "8"]))
     assert mod == "voxel_tfce_mediation_randomise" and argv == ["-r", "1", "1000", "-m", "M"]
-    with pytest.raises(NotImplementedError):
-        s2.driver_call(p.parse_args(["--voxel", "-n", "1000", "-glm"]))
+    # tm-models families (:104-133): the reference's flags; the count doubles for -ofa/-tfa/-cos/-mcos only (:142)
+    assert s2.driver_call(p.parse_args(["--voxel", "-n", "1000", "-glm"])) == \
+        ("tm_models_randomise", ["-r", "1", "500", "-v", "-glm"])
+    assert s2.driver_call(p.parse_args(["--vertex", "area", "-n", "1000", "-med", "-e", "blocks.csv"])) == \
+        ("tm_models_randomise", ["-r", "1", "500", "-s", "area", "-med", "-e", "blocks.csv"])
+    for flag in ("-ofa", "-tfa", "-cos", "-mcos"):
+        assert s2.driver_call(p.parse_args(["--vertex", "area", "-n", "1000", flag, "--seed", "3"])) == \
+            ("tm_models_randomise", ["-r", "1", "1000", "-s", "area", flag, "--seed", "3"])
 
 
 def test_bench_reads_measured_hbm_peak_tolerantly(tmp_path, monkeypatch):

@@ -9,7 +9,9 @@ this package instead: the whole range 1..roundperm is ONE call of the driver's r
 blocks like the reference's) and rank 0 writes the rows in permutation order.  `command_blocks`
 returns the reference's own (start, stop) list, so that the two decompositions can be compared.
 The scheduler options (-p/-c/-f) are accepted and ignored; the tm-models statistics
-(-glm/-ofa/-tfa/-cos/-med/-mcos) are outside this package's scope."""
+(-glm/-ofa/-tfa/-cos/-med/-mcos) go to tm_models_randomise with the reference's flags (:104-133).  (The families whose
+shuffles compose in place -- tm-models mediation and repeated-measures ANCOVA -- compose over the whole range here,
+where the reference's fan-out restarts the composition in every block of 100.)"""
 import argparse as ap
 
 import numpy as np
@@ -54,9 +56,18 @@ def command_blocks(numperm, doubled):
 
 def driver_call(opts):
     """(driver module name, argv) equivalent to the reference's `whichScript -r 1 roundperm`."""
-    if any(getattr(opts, k) for k in ("generalizedlinearmodel", "onebetweenssubjectfactor", "twobetweenssubjectfactor",
-                                      "cosinor", "modelmediation", "cosinormediation")):
-        raise NotImplementedError("tm-models statistics are not part of the B200 hot path (SURVEY.md section 8f)")
+    models = [flag for flag, k in (("-glm", "generalizedlinearmodel"), ("-ofa", "onebetweenssubjectfactor"),
+                                   ("-tfa", "twobetweenssubjectfactor"), ("-cos", "cosinor"), ("-med", "modelmediation"),
+                                   ("-mcos", "cosinormediation")) if getattr(opts, k)]
+    if models:
+        # :142: the shuffle count doubles for -ofa, -tfa, -cos, -mcos (and -m), not for -glm / -med
+        last = rounded_shuffles(opts.numperm[0], models[0] in ("-ofa", "-tfa", "-cos", "-mcos"))
+        argv = ["-r", "1", str(last)] + (["-v"] if opts.voxel else ["-s", opts.vertex[0]]) + models
+        if opts.exchangeblock:
+            argv += ["-e", opts.exchangeblock[0]]
+        if opts.seed is not None:
+            argv += ["--seed", str(opts.seed)]
+        return "tm_models_randomise", argv
     last = rounded_shuffles(opts.numperm[0], bool(opts.mediation))
     argv = ["-r", "1", str(last)]
     if opts.voxel:
