@@ -617,6 +617,10 @@ __global__ void __launch_bounds__(256) pipe_count_wide_kernel(PipeParams P, int 
         // coalesced 16-byte load per group and lane, basin lookups only where the bit is set) was measured twice and is
         // slower (10.9 against 6.7 ms per 512 maps): the kernel is bound by the number of warp-level memory instructions
         // with few active lanes, and lockstep issues one predicated shared AND one predicated global lookup per slot.
+        // Also measured and rejected: queueing the candidate unions per warp (ballot-compacted) and inserting 32 at a
+        // time with every lane busy -- 26.5 against 24.5 ms per 1,024 maps for the stage: the walk already costs only
+        // ~12 warp instructions per step (ncu: 2,260 per warp over 4 vertices per lane and ~45 steps each), the hash
+        // path is not where the time goes, and the votes cost more than they save.
 #pragma unroll
         for (int w = 0; w < kWords; ++w) {
             unsigned m = __ldg(emw[w] + v);
