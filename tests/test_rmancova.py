@@ -224,3 +224,49 @@ def test_tm_models_randomise_rm_ancova_driver_rows(tmp_path, monkeypatch, kind):
     out = "output_%s_area/perm_%s" % (name, name)
     for j, nm in enumerate(names):
         assert np.allclose(_rows("%s/perm_Fstat_%s_TFCE_maxVertex.csv" % (out, nm)), want[:, j], rtol=1e-5, atol=6e-5)
+
+
+@pytest.mark.gpu
+def test_rm_ancova_driver_under_torchrun_gives_the_single_process_rows(tmp_path):
+    """Two ranks (torchrun; both on GPU 0 over gloo when the box has one GPU): the range is sharded, every rank replays
+    the cumulative shuffles from the first permutation of the range, rank 0 writes the rows in order -- the same rows
+    as one process, which the test above checks against the oracle pipeline."""
+    import subprocess
+    import sys
+    import torch
+    st = _state()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for ranks in (1, 2):
+        wd = os.path.join(str(tmp_path), "r%d" % ranks)
+        d = os.path.join(wd, "tmtemp_rmANCOVA1BS_area")
+        os.makedirs(d)
+        adj = synth.csr_to_lists(st["csr"])
+        np.save(d + "/data.npy", st["y"]); np.save(d + "/optstfce.npy", np.array([2, 0.67]))
+        np.save(d + "/num_vertex_lh.npy", int(st["keep_lh"].sum()))
+        np.save(d + "/mask_lh.npy", st["keep_lh"]); np.save(d + "/mask_rh.npy", st["keep_rh"])
+        np.save(d + "/adjac_lh.npy", _obj(adj), allow_pickle=True); np.save(d + "/adjac_rh.npy", _obj(adj), allow_pickle=True)
+        np.save(d + "/vdensity_lh.npy", st["dens"]); np.save(d + "/vdensity_rh.npy", st["dens"])
+        np.save(d + "/dmy_factor1.npy", st["f1"]); np.save(d + "/dmy_subjects.npy", st["subjects"])
+        np.save(d + "/dformat.npy", np.array(["short"])); np.save(d + "/dmy_covariates.npy", st["cov"])
+        np.save(d + "/factors.npy", np.array(["sex", "d"]))
+        script = os.path.join(wd, "run.py")
+        with open(script, "w") as f:
+            f.write("import sys, argparse\nsys.path.insert(0, %r)\n"
+                    "from tfce_mediation_b200.tmanalysis import tm_models_randomise as drv\n"
+                    "from tfce_mediation_b200.tmanalysis import _common as C\n"
+                    "C.BLOCK = 2\n"
+                    "drv.run(drv.getArgumentParser(argparse.ArgumentParser()).parse_args("
+                    "['-r', '1', '6', '-s', 'area', '-ofa', '--seed', '9']))\n" % root)
+        env = dict(os.environ)
+        if ranks == 1:
+            cmd = [sys.executable, script]
+        else:
+            if torch.cuda.device_count() < 2:
+                env["TMB_ALLOW_SHARED_GPU"] = "1"
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                   "--master-addr", "127.0.0.1", "--master-port", "29647", script]
+        subprocess.run(cmd, cwd=wd, env=env, check=True, timeout=600)
+        out = os.path.join(wd, "output_rmANCOVA1BS_area/perm_rmANCOVA1BS")
+        outs.append([open("%s/perm_Fstat_%s_TFCE_maxVertex.csv" % (out, nm)).read() for nm in ("sex", "time", "sex.X.time")])
+    assert outs[0] == outs[1] and len(outs[0][0].splitlines()) == 6
