@@ -138,9 +138,16 @@ def test_rm_ancova_kernels_match_reference_golden(kind, tag):
     # SS_Total follows numpy's float32 accumulation in the shuffled row order, so every row agrees to float64 accuracy
     assert _close64(f64, g["perm_%s_%s" % (kind, tag)], 1e-9)
     assert np.array_equal(f32, f64.astype(np.float32))
-    # chunked evaluation (a budget that holds one shuffle per chunk) gives the same bits
+    # chunked evaluation (a budget that holds one shuffle per chunk: the unstaged totals kernel) gives the same bits, and
+    # so does the unstaged kernel on the whole block
     g32 = eng.rm_ancova_stats(model, [d[0] for d in draws], [d[1] for d in draws], budget=1.0)
     assert np.array_equal(g32.cpu().numpy()[:, :, :V], f32)
+    os.environ["TMB_RM_TOTALS"] = "global"
+    try:
+        h32 = eng.rm_ancova_stats(model, [d[0] for d in draws], [d[1] for d in draws])
+    finally:
+        del os.environ["TMB_RM_TOTALS"]
+    assert np.array_equal(h32.cpu().numpy()[:, :, :V], f32)
 
 
 def _state(n=24, s=3, seed=33):

@@ -529,6 +529,21 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_kernel(GlmParams p, int mtile
         if (lane == 0) mbar_arrive(empty + s);
     }
     // epilogue (r == 1): element (i, j, e) is design m0 + wm*32 + i*8 + g, vertex v0 + wn*32 + j*8 + t4*2 + e
+    if (p.mode == 1) { // the plain contraction (tmb_glm_beta): row m of the output is column m of At
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = m0 + wm * 32 + i * 8 + g;
+            if (row >= p.P) continue;
+            double *dst = p.t64 + (size_t)row * p.ldt;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t v = v0 + wn * 32 + j * 8 + t4 * 2;
+                if (v < p.V) dst[v] = acc[i][j][0];
+                if (v + 1 < p.V) dst[v + 1] = acc[i][j][1];
+            }
+        }
+        return;
+    }
     const bool fast = p.t64 == nullptr && !p.exact_epilogue; // fp32 output only
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1209,6 +1224,11 @@ int launch_glm(const GlmParams &p, cudaStream_t stream) {
         // t-statistic (the headline case) has its own kernel with the cheap fp32-seeded epilogue; everything else --
         // several regressors, partial F, Sobel z -- runs on glm_dmma_multi_kernel.
         // (float64 data: the doubled Y stage halves the resident CTAs and DFMA wins, measured in round 1.)
+        if (p.mode == 1 && glm_uses_dmma(p.y_is_f64, 1) && p.ldA >= (p.P + DM - 1) / DM * DM) {
+            // stored betas (designs with more than 8 regressors, cosinor, repeated-measures cross-products): the same
+            // tensor-core contraction with a store-only epilogue
+            return launch_dmma<float>(p, stream);
+        }
         if (glm_uses_dmma(p.y_is_f64, p.rp) && p.mode != 1) {
             TMB_REQUIRE(p.layout == 1 || p.rp == 1, "glm: the DMMA kernels need the tile8 column order of At (tmb_glm_layout)");
             TMB_REQUIRE(p.ldA >= glm_packed_columns(p.y_is_f64, p.P, p.rp), "glm: ldA must be at least tmb_glm_packed_columns() = %lld",

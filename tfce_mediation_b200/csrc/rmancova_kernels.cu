@@ -13,6 +13,8 @@
 //     divisions (the two functions differ only in their designs and program).
 #include "common.cuh"
 #include "../../include/tfce_b200.h"
+#include <cstdlib>
+#include <cstring>
 
 namespace tmb {
 
@@ -62,6 +64,95 @@ __global__ void __launch_bounds__(128) rm_totals_kernel(const YT *__restrict__ Y
         at += sz;
     }
     ssw[(size_t)perm * ldo + v] = w;
+}
+
+// The same, with the CTA's data columns staged in shared memory once and reused by all P shuffles: every shuffle reads
+// every row four times (mean and squares of the total, mean and squares per subject) in its own order, so the global
+// kernel above moves 4*P*N*V elements through L2/HBM while this one moves N*V.  TV vertices per CTA (1,024 threads =
+// 1024/TV shuffles in flight x TV vertices: one CTA per SM, and the serial, latency-bound walks need the warps); dynamic
+// shared memory N*TV elements.
+template <typename YT, int TV>
+__global__ void __launch_bounds__(1024) rm_totals_tile_kernel(const YT *__restrict__ Y, int N, int64_t V, int64_t ldy,
+                                                             const int32_t *__restrict__ order,
+                                                             const int32_t *__restrict__ grp_rows,
+                                                             const int32_t *__restrict__ grp_size, int ngroups, int P,
+                                                             double *__restrict__ sstot, double *__restrict__ ssw,
+                                                             int64_t ldo) {
+    extern __shared__ __align__(16) unsigned char rm_smem[];
+    YT *tile = reinterpret_cast<YT *>(rm_smem);
+    constexpr int kLanes = 1024 / TV;                      // shuffles in flight
+    const int c = threadIdx.x % TV, sp = threadIdx.x / TV;
+    const int64_t v = (int64_t)blockIdx.x * TV + c;
+    for (int row = sp; row < N; row += kLanes) tile[(size_t)row * TV + c] = (v < V) ? Y[(size_t)row * ldy + v] : (YT)0;
+    __syncthreads();
+    if (v >= ldo) return;
+    const YT *col = tile + c;
+    for (int perm = blockIdx.y * kLanes + sp; perm < P; perm += gridDim.y * kLanes) {
+        if (v >= V) {
+            sstot[(size_t)perm * ldo + v] = 0.0;
+            if (ssw) ssw[(size_t)perm * ldo + v] = 0.0;
+            continue;
+        }
+        const int32_t *ord = order ? order + (size_t)perm * N : nullptr;
+        YT acc = (YT)0;
+        for (int i = 0; i < N; ++i) acc = acc + col[(size_t)(ord ? __ldg(ord + i) : i) * TV];
+        const YT mean = acc / (YT)N;
+        YT ss = (YT)0;
+        for (int i = 0; i < N; ++i) {
+            const YT d = col[(size_t)(ord ? __ldg(ord + i) : i) * TV] - mean;
+            ss = ss + d * d;
+        }
+        sstot[(size_t)perm * ldo + v] = (double)ss;
+        if (!ssw) continue;
+        const int32_t *gr = grp_rows + (size_t)perm * N;
+        double w = 0.0;
+        int at = 0;
+        for (int g = 0; g < ngroups; ++g) {
+            const int sz = __ldg(grp_size + g);
+            double sg = 0.0;
+            for (int j = 0; j < sz; ++j) sg += (double)col[(size_t)__ldg(gr + at + j) * TV];
+            const double mg = sg / (double)sz;
+            for (int j = 0; j < sz; ++j) {
+                const double d = (double)col[(size_t)__ldg(gr + at + j) * TV] - mg;
+                w += d * d;
+            }
+            at += sz;
+        }
+        ssw[(size_t)perm * ldo + v] = w;
+    }
+}
+
+template <typename YT, int TV>
+static int launch_rm_totals_tile(const YT *Y, int N, int64_t V, int64_t ldy, const int32_t *order, const int32_t *grp_rows,
+                                 const int32_t *grp_size, int ngroups, int P, double *sstot, double *ssw, int64_t ldo,
+                                 cudaStream_t stream) {
+    const size_t smem = (size_t)N * TV * sizeof(YT);
+    TMB_CUDA(cudaFuncSetAttribute(rm_totals_tile_kernel<YT, TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t xtiles = (ldo + TV - 1) / TV;
+    // enough CTAs for a few waves: split the shuffles when there are few column tiles
+    int ysplit = 1;
+    constexpr int kLanes = 1024 / TV;
+    while (xtiles * ysplit < 4 * 148 && ysplit * kLanes * 2 <= P) ysplit *= 2;
+    rm_totals_tile_kernel<YT, TV><<<dim3((unsigned)xtiles, (unsigned)ysplit), 1024, smem, stream>>>(
+        Y, N, V, ldy, order, grp_rows, grp_size, ngroups, P, sstot, ssw, ldo);
+    return 0;
+}
+
+template <typename YT>
+static int launch_rm_totals(const YT *Y, int N, int64_t V, int64_t ldy, const int32_t *order, const int32_t *grp_rows,
+                            const int32_t *grp_size, int ngroups, int P, double *sstot, double *ssw, int64_t ldo,
+                            cudaStream_t stream) {
+    const size_t budget = 200 * 1024, row = (size_t)N * sizeof(YT);
+    const char *force = getenv("TMB_RM_TOTALS");            // "global": the unstaged kernel (A/B measurements, tests)
+    const bool global_only = force && strcmp(force, "global") == 0;
+    if (!global_only && P >= 4) {
+        if (row * 128 <= budget) return launch_rm_totals_tile<YT, 128>(Y, N, V, ldy, order, grp_rows, grp_size, ngroups, P, sstot, ssw, ldo, stream);
+        if (row * 64 <= budget) return launch_rm_totals_tile<YT, 64>(Y, N, V, ldy, order, grp_rows, grp_size, ngroups, P, sstot, ssw, ldo, stream);
+        if (row * 32 <= budget) return launch_rm_totals_tile<YT, 32>(Y, N, V, ldy, order, grp_rows, grp_size, ngroups, P, sstot, ssw, ldo, stream);
+    }
+    const dim3 grid((unsigned)((ldo + 127) / 128), (unsigned)P);
+    rm_totals_kernel<YT><<<grid, 128, 0, stream>>>(Y, N, V, ldy, order, grp_rows, grp_size, ngroups, sstot, ssw, ldo);
+    return 0;
 }
 
 static constexpr int kRmMaxCols = 64;      // columns of the union design
@@ -145,13 +236,12 @@ extern "C" int tmb_rm_totals(const void *Y_dev, int ydtype, int N, int64_t V, in
     TMB_REQUIRE(N > 0 && V > 0 && ldy >= V && ldo >= V && P >= 1 && P <= 65535,
                 "tmb_rm_totals: bad shape (N=%d V=%lld groups=%d P=%d)", N, (long long)V, ngroups, P);
     TMB_DEVICE_OF(Y_dev, "tmb_rm_totals");
-    const dim3 grid((unsigned)((ldo + 127) / 128), (unsigned)P);
-    if (ydtype == TMB_F64)
-        rm_totals_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>((const double *)Y_dev, N, V, ldy, order_dev, grp_rows_dev,
-                                                                        grp_size_dev, ngroups, sstotal_dev, sswithin_dev, ldo);
-    else
-        rm_totals_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float *)Y_dev, N, V, ldy, order_dev, grp_rows_dev,
-                                                                       grp_size_dev, ngroups, sstotal_dev, sswithin_dev, ldo);
+    const int rc = ydtype == TMB_F64
+                       ? launch_rm_totals<double>((const double *)Y_dev, N, V, ldy, order_dev, grp_rows_dev, grp_size_dev, ngroups, P,
+                                                  sstotal_dev, sswithin_dev, ldo, (cudaStream_t)stream)
+                       : launch_rm_totals<float>((const float *)Y_dev, N, V, ldy, order_dev, grp_rows_dev, grp_size_dev, ngroups, P,
+                                                 sstotal_dev, sswithin_dev, ldo, (cudaStream_t)stream);
+    if (rc) return rc;
     count_launch();
     TMB_CUDA(cudaGetLastError());
     return 0;
