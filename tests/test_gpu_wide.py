@@ -50,9 +50,14 @@ def test_wide_rows_maps_bitexact():
         assert np.array_equal(pos[b], wp) and np.array_equal(neg[b], wn)
 
 
-def test_mixed_plan_narrow_and_wide_surfaces():
-    """One plan with a 1-ring mesh, a 4-ring mesh and different (H, E): every surface then runs on sliced rows."""
+@pytest.mark.parametrize("mixed", ["1", "0"])
+def test_mixed_plan_narrow_and_wide_surfaces(monkeypatch, mixed):
+    """One plan with two 1-ring meshes, a 4-ring mesh and different (H, E).  Default: the meshes keep their fixed-width
+    rows and only the 4-ring surface runs on sliced rows, each group in its own launch over its surface-slot range (the
+    slots are issued meshes first); TMB_PIPE_MIXED=0: every surface on sliced rows.  Maxima and full maps against the oracle."""
+    import torch
     from tfce_mediation_b200.engine import Surface, TfcePlan
+    monkeypatch.setenv("TMB_PIPE_MIXED", mixed)
     csr1, csr4 = _kring(5, 4)
     _, _, csr_small = helpers.ico(4)
     V5, V4 = csr1[0].shape[0] - 1, csr_small[0].shape[0] - 1
@@ -66,6 +71,14 @@ def test_mixed_plan_narrow_and_wide_surfaces():
     stat[:, V5 + V4:2 * V5 + V4] = _maps(csr1, B, 1320)[::-1]
     spec = [(csr4, 0, V5, 2, 0.67, w4), (csr_small, V5, V4, 2, 1.0, None), (csr1, V5 + V4, V5, 2, 0.5, None)]
     _check_max(plan, stat, spec, two_sided=True)
+    _, _, (pos, neg) = plan.run(torch.from_numpy(stat).cuda(), two_sided=True, want_maps=True)
+    pos, neg = pos.cpu().numpy(), neg.cpu().numpy()
+    for csr, off, V, H, E, _ in spec:
+        for b in range(3):
+            seg = np.ascontiguousarray(stat[b, off:off + V])
+            wp = oracle.tfce_run(H, E, csr, seg) if seg.max() > 0 else np.zeros_like(seg)
+            wn = oracle.tfce_run(H, E, csr, -seg) if (-seg).max() > 0 else np.zeros_like(seg)
+            assert np.array_equal(pos[b, off:off + V], wp) and np.array_equal(neg[b, off:off + V], wn)
 
 
 def test_forced_sliced_rows_equal_fixed_width_rows(monkeypatch):

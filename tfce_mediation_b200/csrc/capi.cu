@@ -83,6 +83,8 @@ struct tmb_plan {
     int pipe_ok = 0;            // basin path and every surface has fixed-width rows of at most 32 slots
     int pipe_weights = 0;       // some surface carries vertex weights (scaled maxima then need the per-vertex pass)
     int pipe_words = 0;         // 0: fixed-width rows; W > 0: sliced rows, W mask words per vertex (wide pipeline kernels)
+    int pipe_narrow = 0;        // mixed plans (pipe_words > 0): leading surface slots that stay on fixed-width rows
+    int pipe_narrow_degree = 0; // largest degree among them
     int pipe_items = 0;
     int pipe_has_table = 0;     // the per-item buffers include the class path's [level][basin] table (32 B per vertex)
     int64_t pipe_vstride = 0, pipe_tabcap = 0;
@@ -408,10 +410,30 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
             if (graphs[s]->sell_words == 0) all_sell = false;
             words = std::max(words, (int)graphs[s]->sell_words);
         }
-        if (fs && strcmp(fs, "sell") == 0 && all_sell) all_ell = false;
+        const bool force_sell = fs && strcmp(fs, "sell") == 0;
+        if (force_sell && all_sell) all_ell = false;
         if (all_ell) p->pipe_words = 0;
-        else if (all_sell) p->pipe_words = words <= 1 ? 1 : words <= 2 ? 2 : words <= 4 ? 4 : 8;
-        else p->pipe_ok = 0;
+        else if (all_sell) {
+            // Mixed plans (mmr: triangle meshes next to voxel graphs): the meshes keep their fixed-width rows.  The
+            // surface slots are issued meshes first (each group still by descending size), so that every group is one
+            // contiguous slot range of the streaming kernels' grids.  TMB_PIPE_MIXED=0: sliced rows for all surfaces.
+            const char *mx = getenv("TMB_PIPE_MIXED");
+            std::vector<char> narrow((size_t)S, 0);
+            int nn = 0;
+            if (!force_sell && !(mx && mx[0] == '0'))
+                for (int s = 0; s < S; ++s)
+                    if (graphs[s]->d_ell && graphs[s]->ell_width == 8 && graphs[s]->d_ell_self) { narrow[s] = 1; ++nn; }
+            if (nn > 0 && nn < S) {
+                std::stable_partition(order.begin(), order.end(), [&](int s) { return narrow[s] != 0; });
+                p->pipe_narrow = nn;
+                words = 1;
+                for (int s = 0; s < S; ++s) {
+                    if (narrow[s]) p->pipe_narrow_degree = std::max(p->pipe_narrow_degree, (int)graphs[s]->max_degree);
+                    else words = std::max(words, (int)graphs[s]->sell_words);
+                }
+            }
+            p->pipe_words = words <= 1 ? 1 : words <= 2 ? 2 : words <= 4 ? 4 : 8;
+        } else p->pipe_ok = 0;
         if (p->pipe_ok && p->pipe_words)
             for (int s = 0; s < S; ++s) {
                 tmb_graph *g = graphs[s];
@@ -714,6 +736,7 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
         pp.timing = p->d_timing;
         pp.max_degree = 0;
         pp.sell_words = p->pipe_words;
+        pp.narrow_slots = p->pipe_narrow; pp.narrow_max_degree = p->pipe_narrow_degree; pp.z0 = 0;
         pp.ell_self = 1;
         for (int s = 0; s < p->S; ++s) if (!p->graphs[s]->d_ell_self) pp.ell_self = 0;
         for (int s = 0; s < p->S; ++s) pp.max_degree = std::max(pp.max_degree, (int)p->graphs[s]->max_degree);

@@ -162,6 +162,10 @@ struct PipeParams {
     int max_degree;         // largest vertex degree over the plan's graphs (triangle meshes: 6 -> the ascent kernel skips the two pad slots)
     int ell_self;           // every surface has self-padded width-8 rows (SurfDesc::ell_self)
     int sell_words;         // 0: fixed-width rows (ell); W > 0: sliced rows (sell) with W 32-bit words of earlier-neighbour mask per vertex
+    int narrow_slots;       // mixed plans (sell_words > 0): the first narrow_slots surface slots of surf_order are triangle meshes
+                            // with self-padded width-8 rows and run the fixed-width ascent / count kernels, the rest the sliced ones
+    int narrow_max_degree;  // largest degree among those
+    int z0;                 // surface-slot offset of this launch's grid (blockIdx.z + z0 indexes surf_order)
     int32_t Vmax;
     // per-item buffers
     int64_t vstride;        // elements per work item in the per-vertex arrays
