@@ -46,7 +46,7 @@ METRIC = "permutations/sec (regression+TFCE+max)"
 TFCE_STAGE = "tfce pipeline (pipe_levels + pipe_ascent + pipe_basin + pipe_count + pipe_sweep_max kernels)"
 UNIT = "permutations/s"
 DEFAULT_BLOCK = {"config1": 4096, "config2": 1024, "config2_3mm": 512, "config3": 1024, "config4": 1024,
-                 "config5": 64, "tiny": 64}
+                 "config5": 128, "tiny": 64}
 
 
 # ----------------------------------------------------------------------------------------- workloads
