@@ -536,8 +536,12 @@ def run_b200(args):
     yy = eng.Y.sumsq(True)
     L = _lib.lib()
     stacks = []
+    # medtype 'M' / 'I': one contraction row per shuffle (dep'y is fitted once), else path A's row + path B's two rows
+    cross = w["kind"] == "mediation" and eng.sobelz_cross_ok(w["medtype"])
     for s in range(total_steps):
-        if w["kind"] == "mediation":
+        if w["kind"] == "mediation" and cross:
+            stacks.append(idx_all[s])       # the index rows: the predictor columns are gathered on the device
+        elif w["kind"] == "mediation":
             XA, XB, ta = eng.mediation_designs(w["medtype"], w["pred_x"], w["depend_y"], idx_all[s])
             stacks.append(eng.sobelz_operands(XA, XB, ta, "aroian", resident=True))
         else:
@@ -545,7 +549,7 @@ def run_b200(args):
             At, ldA = E.pack_At(st["pinv"], 1)
             stacks.append((torch.from_numpy(At).to(dev), ldA, torch.from_numpy(st["G"]).to(dev),
                            torch.from_numpy(st["d"]).to(dev), st["dof"]))
-    fit_rows = 3 if w["kind"] == "mediation" else 1             # pseudo-inverse rows per shuffle (path A: 1, path B: 2)
+    fit_rows = 3 if (w["kind"] == "mediation" and not cross) else 1   # contraction rows per shuffle
     t32b = [torch.empty((P, C, ld), dtype=torch.float32, device=dev) for _ in range(2)]
     out_max = torch.empty((P * C, S, 2), dtype=torch.float32, device=dev)
     comm = None
@@ -559,7 +563,9 @@ def run_b200(args):
         if len(fit_events) < 64:
             fa = torch.cuda.Event(enable_timing=True); fb = torch.cuda.Event(enable_timing=True)
             fa.record()
-        if w["kind"] == "mediation":
+        if w["kind"] == "mediation" and cross:
+            eng.sobelz_cross(w["medtype"], w["pred_x"], w["depend_y"], stacks[s], "aroian", out=buf.view(P, ld))
+        elif w["kind"] == "mediation":
             eng.sobelz_launch(stacks[s], out=buf.view(P, ld))
         else:
             At_d, ldA, G_d, d_d, dof = stacks[s]
@@ -719,7 +725,8 @@ def run_b200(args):
                          "algorithmic_bytes_per_launch": bytes_tfce * P, "kernel_ms_per_launch": tfce_ms,
                          "kernel_share_of_step": tfce_ms / (dev_ms / args.steps),
                          "fit": None if fit_ms is None else {
-                             "kernel": "tmb_sobelz (glm fit x2 + Sobel epilogue)" if w["kind"] == "mediation" else "glm_dmma_kernel",
+                             "kernel": ("tmb_sobelz_cross (one contraction row per shuffle + two-path Sobel epilogue)" if cross else
+                                        "tmb_sobelz (glm fit x2 + Sobel epilogue)" if w["kind"] == "mediation" else "glm_dmma_kernel"),
                              "bound": "tensor (fp64 DMMA)", "ms_per_launch": fit_ms,
                              "achieved": fit_flops / (fit_ms / 1e3) / 1e12, "unit": "TFLOP/s",
                              "peak": fp64_peak, "frac": fit_flops / (fit_ms / 1e3) / 1e12 / fp64_peak,

@@ -183,6 +183,18 @@ int tmb_glm_fstat(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, 
 int tmb_glm_pack_rowperm(const double *pinv_dev, int r, int n, const int32_t *perm_idx_dev, int P, int rp,
                          double *At_dev, int64_t ldA, int layout, void *stream);
 
+/* Sobel z for medtype 'M' / 'I' (pyfunc.py:130-162 under the drivers' rule that only pred_x is permuted,
+ * vertex_tfce_mediation_randomise.py:82-90) from ONE contraction row per shuffle instead of three.  At_dev float64
+ * [n, ldA]: column p = the centred, permuted predictor of shuffle p (tmb_glm_pack_rowperm with r = 1 on the centred
+ * predictor; ldA = tmb_glm_packed_columns(TMB_F32, P, 1)).  cd_dev float64 [V]: the centred cross-product dep'y of the
+ * un-permuted second variable (one tmb_glm_beta row, once).  xx = x'x (centred).  CB_dev float64 [P, 8]: per shuffle the
+ * inverse C of the centred Gram matrix of path B's two regressors in design order (C00, C01, C10, C11), then
+ * C[rowB][rowB] / dofB, then padding; xpos = position of the predictor among the two (1 for 'M': [dep, x]; 0 for 'I':
+ * [x, dep]); rowB = the tested one (0 for both).  float32 data only. */
+int tmb_sobelz_cross(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev, int64_t ldA,
+                     const double *cd_dev, double xx, double dofA, const double *CB_dev, int xpos, int rowB, double dofB,
+                     const double *yy_dev, int P, int alg, float *z32_dev, double *z64_dev, int64_t ldt, void *stream);
+
 /* Designs with MORE than 8 non-intercept regressors (the reference accepts any k: cynumstats.pyx:28-29,59-64 -- e.g.
  * dummy-coded sites plus covariates): the betas are formed first by tmb_glm_beta (every pseudo-inverse row of every
  * design is one column of At_dev and one output row, design-major: row p*r + i), then these evaluate the same statistics

@@ -145,3 +145,43 @@ def test_mediation_blocks_pipelined_equals_block_by_block():
         run(np.ascontiguousarray(z), tf)
         want = np.float32((tf * (z.max() / 100)).max())
         assert "%.4f" % whole[p, 0] == "%.4f" % want
+
+
+@pytest.mark.parametrize("medtype", ["M", "I"])
+@pytest.mark.parametrize("alg", ["aroian", "sobel", "goodman"])
+def test_sobelz_from_cross_products_fast_epilogue_is_bit_identical_to_exact(monkeypatch, medtype, alg):
+    """Medtype 'M' / 'I' run from one contraction row per shuffle (tmb_sobelz_cross).  Its float32 epilogue takes float32
+    seeds + Newton steps and falls back to the exact sequence near rounding boundaries: same bits as TMB_GLM_EPILOGUE=exact
+    on 2.6 M values; and the float64 z agrees with the two-design formulation (tmb_sobelz, TMB_SOBEL=designs) and with the
+    oracle to 1e-10."""
+    from tfce_mediation_b200.engine import PermutationEngine
+    n, P = 60, 128
+    csr, V, y, X, surfs, _ = _two_hemi_setup(5, n, 2, 31)
+    rs = np.random.RandomState(17)
+    pred_x = rs.standard_normal(n)
+    dep = 0.4 * pred_x + rs.standard_normal(n)
+    y = (y + 0.25 * pred_x[:, None] + 0.2 * dep[:, None]).astype(np.float32)
+    y[:, 7] = 0.0                                   # a constant column: NaN in the reference, NaN here
+    eng = PermutationEngine(y, surfs, two_sided=False)
+    idx = np.stack([oracle.permutation_indices(7000 + p, n) for p in range(P)])
+    assert eng.sobelz_cross_ok(medtype)
+    fast = eng.sobelz(medtype, pred_x, dep, idx, alg).cpu().numpy()
+    monkeypatch.setenv("TMB_GLM_EPILOGUE", "exact")
+    exact = eng.sobelz(medtype, pred_x, dep, idx, alg).cpu().numpy()
+    monkeypatch.delenv("TMB_GLM_EPILOGUE")
+    assert fast.shape[0] == P and np.array_equal(fast, exact, equal_nan=True)
+    z32, z64 = eng.sobelz(medtype, pred_x, dep, idx[:6], alg, want_f64=True)
+    z32, z64 = z32.cpu().numpy()[:, :2 * V], z64.cpu().numpy()[:, :2 * V]
+    assert np.array_equal(z32, fast[:6, :2 * V], equal_nan=True)
+    monkeypatch.setenv("TMB_SOBEL", "designs")
+    assert not eng.sobelz_cross_ok(medtype)
+    _, d64 = eng.sobelz(medtype, pred_x, dep, idx[:6], alg, want_f64=True)
+    d64 = d64.cpu().numpy()[:, :2 * V]
+    ok = np.isfinite(d64)
+    assert np.array_equal(ok, np.isfinite(z64))
+    assert np.all(np.abs(z64[ok] - d64[ok]) <= 1e-10 * np.maximum(1.0, np.abs(d64[ok])))
+    for p in range(3):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            want = oracle.sobelz(medtype, pred_x[idx[p]], dep, y, n, 2 * V, alg=alg)
+        okp = np.isfinite(want)
+        assert np.all(np.abs(z64[p][okp] - want[okp]) <= 1e-10 * np.maximum(1.0, np.abs(want[okp])))

@@ -85,11 +85,12 @@ struct GlmParams {
     const double *yy;
     float *t32; double *t64; int64_t ldt;
     int nan_to_zero;
-    int mode;                           // 0 t-stat, 1 betas, 2 sobel, 3 F statistics, 4 cosinor (stored betas only)
+    int mode;                           // 0 t-stat, 1 betas, 2 sobel, 3 F statistics, 4 cosinor (stored betas only), 5 sobel from cross-products (DMMA, one row per design)
     // sobel: rows [0, rA) of each design group are path A, rows [rA, rA+rB) path B
     const double *GB; const double *dB; int rA, rB, rowA, rowB; double dofB;
     const double *ta_scalar; int alg;
     const double *sstot;                                         // the reference's own SS_Total (model F numerator) or null
+    const double *cfix; double xx; int xpos;                     // mode 5 (Sobel from cross-products): dep'Y per vertex, x'x, position of x in path B
     int cos_nexog, cos_mediation; double cos_ta;                 // mode 4 (cosinor): tested columns, mediation row, path-A t
     // F statistics (mode 3): per design the inverse blocks M_i = inv((X'X)^-1[S_i, S_i]) of every tested variable,
     // stored one after the other (k_i x k_i each, msz doubles per design); variable i covers rows [var_lo[i], +var_k[i])
@@ -183,6 +184,64 @@ __device__ __forceinline__ float t32_fast(double beta, double sse, double d_over
     const unsigned ex = ((unsigned)__double2hiint(q) >> 20) & 0x7ffu;  // fp32-normal quotient (or exactly zero) only
     slow |= !((ex - (1023u - 120u)) <= 240u || q == 0.0);
     return __double2float_rn(q);
+}
+
+// beta / fl32(sqrt(sse * dscale)) in float64 with relative error < 2^-44 (the float32 rounding of se is exact: `slow` is set
+// when the square root lies within 2^12 ulp64 of a float32 rounding boundary or outside the float32 normal range).  Same
+// seeds and Newton steps as t32_fast.
+__device__ __forceinline__ double t64_fast(double beta, double sse, double dscale, bool &slow) {
+    if (sse < 0.0) sse = 0.0;
+    const double s = __dmul_rn(sse, dscale);
+    const float sf = __double2float_rn(s);
+    const bool bad = !(sf > 1e-30f && sf < 1e30f);
+    slow |= bad;
+    float y32;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y32) : "f"(bad ? 1.0f : sf));
+    const double y = widen_pos_normal(y32);
+    const double g = __dmul_rn(s, y);
+    const double h = __dmul_rn(0.5, y);
+    const double e = __fma_rn(-h, g, 0.5);
+    const double g1 = __fma_rn(g, e, g);                     // sqrt(s): rel. error < 2^-43
+    const unsigned lowg = (unsigned)__double2loint(g1) & 0x1FFFFFFFu;
+    slow |= (lowg - (0x10000000u - 4096u)) < 8192u;
+    const float se = __double2float_rn(g1);
+    const bool bad2 = !(se > 1e-30f && se < 1e30f);
+    slow |= bad2;
+    float r32;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r32) : "f"(bad2 ? 1.0f : se));
+    const double sed = widen_pos_normal(bad2 ? 1.0f : se);
+    const double r = widen_pos_normal(r32);
+    const double e2 = __fma_rn(-sed, r, 1.0);
+    const double r1 = __fma_rn(r, e2, r);                    // 1 / se: rel. error < 2^-45
+    return __dmul_rn(beta, r1);
+}
+
+// fl32(sqrt(num / den)) for positive operands known to ~2^-42: float32 seeds + one Newton step each, accepted unless the
+// result lies within 2^14 ulp64 of a float32 rounding boundary (accumulated relative error of the caller < 2^-41.5) or
+// outside the float32 normal range.
+__device__ __forceinline__ float sqrt_ratio32_fast(double num, double den, bool &slow) {
+    const float df = __double2float_rn(den);
+    const bool bad = !(df > 1e-30f && df < 1e30f);
+    slow |= bad;
+    float r32;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r32) : "f"(bad ? 1.0f : df));
+    const double r = widen_pos_normal(r32);
+    const double e = __fma_rn(-den, r, 1.0);
+    const double r1 = __fma_rn(r, e, r);                     // 1 / den: rel. error < 2^-44
+    const double w = __dmul_rn(num, r1);
+    const float wf = __double2float_rn(w);
+    const bool bad2 = !(wf > 1e-30f && wf < 1e30f);
+    slow |= bad2;
+    float y32;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y32) : "f"(bad2 ? 1.0f : wf));
+    const double y = widen_pos_normal(y32);
+    const double g = __dmul_rn(w, y);
+    const double h = __dmul_rn(0.5, y);
+    const double e2 = __fma_rn(-h, g, 0.5);
+    const double g1 = __fma_rn(g, e2, g);                    // sqrt(w): rel. error < 2^-43
+    const unsigned low = (unsigned)__double2loint(g1) & 0x1FFFFFFFu;
+    slow |= (low - (0x10000000u - 16384u)) < 32768u;
+    return __double2float_rn(g1);
 }
 
 // one output row of a thread's tile: two 128-bit stores (float) / eight scalar stores (double)
@@ -730,6 +789,63 @@ __device__ __forceinline__ void dmma_vertex_stats(const GlmParams &p, int perm, 
             if (p.t64) p.t64[off] = f;
             M += ki * ki;
         }
+    } else if (p.mode == 5) {
+        // Sobel z of pyfunc.py:130-162 for medtype 'M' / 'I' from ONE contraction row per shuffle.  Only pred_x is permuted
+        // (vertex_tfce_mediation_randomise.py:82-90), so of the centred cross-products c_x = x_p'y and c_d = dep'y only c_x
+        // changes with the shuffle; c_d comes from one extra row fitted once (p.cfix).  Path A, y ~ [1, x_p]:
+        // beta = c_x / x'x, SSE = yy - c_x beta.  Path B, y ~ [1, dep, x_p] ('M', xpos 1) or [1, x_p, dep] ('I', xpos 0):
+        // beta = C c with C = inverse of the shuffle's centred 2 x 2 Gram matrix (p.GB), SSE = yy - c'beta.
+        // The epilogue shares the fp64 pipe with the DMMAs, so it is kept to three divisions and three square roots per
+        // value: 1 / x'x and d / dof are formed on the host (the k = 2 kernel does the same: <= 1 ulp in float64 before
+        // the reference's own rounding of se to float32), and z = 1 / sqrt(1/tb^2 + 1/ta^2 + 1/(ta^2 tb^2)) is evaluated as
+        // sqrt(ta^2 tb^2 / (ta^2 + tb^2 + 1)) unless a square is zero, subnormal or overflowing -- then the reference's own
+        // sequence runs, for its inf / NaN results.
+        const double cx = b[0], cd = inside ? __ldg(p.cfix + v) : 0.0;
+        const double bA = __dmul_rn(cx, p.xx);                               // p.xx = 1 / x'x
+        const double sseA = yyv - __dmul_rn(cx, bA);
+        const double *C = p.GB + (size_t)perm * 8;
+        const double c0 = p.xpos == 0 ? cx : cd, c1 = p.xpos == 0 ? cd : cx;
+        const double b0 = __fma_rn(__ldg(C + 1), c1, __dmul_rn(__ldg(C), c0));
+        const double b1 = __fma_rn(__ldg(C + 3), c1, __dmul_rn(__ldg(C + 2), c0));
+        const double sseB = yyv - __fma_rn(c1, b1, __dmul_rn(c0, b0));
+        const double bB = p.rowB ? b1 : b0, dsB = __ldg(C + 4);              // C[4] = C[rowB][rowB] / dofB
+        if (p.t64 == nullptr && !p.exact_epilogue) {
+            // float32 output only: the two t values and the square root of the ratio from float32 seeds plus one Newton
+            // step each (t64_fast, sqrt_ratio32_fast); accepted unless an intermediate float32 rounding (se of either
+            // path, z itself) is too close to call -- then the exact sequence below runs.  Bit-identical to it by
+            // construction (tests compare the two on whole blocks).
+            bool slow = false;
+            const double fa = t64_fast(bA, sseA, p.dof, slow), fb = t64_fast(bB, sseB, dsB, slow);
+            const double fa2 = __dmul_rn(fa, fa), fb2 = __dmul_rn(fb, fb);
+            const double fsum = __dadd_rn(fa2, fb2);
+            const double fden = p.alg == 0 ? __dadd_rn(fsum, 1.0) : p.alg == 2 ? __dsub_rn(fsum, 1.0) : fsum;
+            if (p.alg == 2 && !(fsum > 2.0)) slow = true;       // Goodman: ta^2 + tb^2 - 1 cancels, the error bound does not hold
+            const float zf = sqrt_ratio32_fast(__dmul_rn(fa2, fb2), fden, slow);
+            if (!slow) {
+                p.t32[(size_t)perm * p.ldt + v] = inside ? zf : 0.f;
+                return;
+            }
+        }
+        const double ta = t_from_scaled(bA, sseA, p.dof);                    // p.dof = (1 / x'x) / dofA
+        const double tb = t_from_scaled(bB, sseB, dsB);
+        const double ta2 = __dmul_rn(ta, ta), tb2 = __dmul_rn(tb, tb);
+        const double prod = __dmul_rn(ta2, tb2);
+        double z;
+        if (prod > 1e-280 && prod < 1e280) {
+            const double sum = __dadd_rn(ta2, tb2);
+            const double den = p.alg == 0 ? __dadd_rn(sum, 1.0) : p.alg == 2 ? __dsub_rn(sum, 1.0) : sum;
+            z = __dsqrt_rn(__ddiv_rn(prod, den));
+        } else {
+            double s = __dadd_rn(__ddiv_rn(1.0, tb2), __ddiv_rn(1.0, ta2));
+            const double cross = __ddiv_rn(1.0, prod);
+            if (p.alg == 0) s = __dadd_rn(s, cross);
+            else if (p.alg == 2) s = __dsub_rn(s, cross);
+            z = __ddiv_rn(1.0, __dsqrt_rn(s));
+        }
+        if (!inside) z = 0.0;
+        const size_t off = (size_t)perm * p.ldt + v;
+        if (p.t32) p.t32[off] = __double2float_rn(z);
+        if (p.t64) p.t64[off] = z;
     } else { // sobel (pyfunc.py:130-162)
         const int rA = p.rA, rB = p.rB;
         double ta;
@@ -1233,6 +1349,12 @@ int launch_glm(const GlmParams &p, cudaStream_t stream) {
             TMB_REQUIRE(p.layout == 1 || p.rp == 1, "glm: the DMMA kernels need the tile8 column order of At (tmb_glm_layout)");
             TMB_REQUIRE(p.ldA >= glm_packed_columns(p.y_is_f64, p.P, p.rp), "glm: ldA must be at least tmb_glm_packed_columns() = %lld",
                         (long long)glm_packed_columns(p.y_is_f64, p.P, p.rp));
+            if (p.mode == 5) {
+                const char *ep = getenv("TMB_GLM_EPILOGUE");
+                GlmParams q = p;
+                q.exact_epilogue = ep && strcmp(ep, "exact") == 0 ? 1 : 0;
+                return launch_dmma_multi<1, float>(q, stream);
+            }
             if (p.mode == 0 && p.r == 1 && p.rp == 1 && p.row0 == 0 && p.nrows == 1) {
                 const char *ep = getenv("TMB_GLM_EPILOGUE");
                 GlmParams q = p;
@@ -1414,6 +1536,25 @@ extern "C" int tmb_sobelz(const void *Y_dev, int ydtype, int n, int64_t V, int64
     p.P = P; p.r = rA + rB; p.rp = rp; p.dof = dofA; p.yy = yy_dev; p.t32 = z32_dev; p.t64 = z64_dev; p.ldt = ldt;
     p.mode = 2; p.GB = GB_dev; p.dB = dB_dev; p.rA = rA; p.rB = rB; p.rowA = rowA; p.rowB = rowB; p.dofB = dofB;
     p.ta_scalar = ta_scalar_dev; p.alg = alg; p.layout = layout;
+    return launch_glm(p, (cudaStream_t)stream);
+}
+
+extern "C" int tmb_sobelz_cross(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ldy, const double *At_dev,
+                                int64_t ldA, const double *cd_dev, double xx, double dofA, const double *CB_dev, int xpos,
+                                int rowB, double dofB, const double *yy_dev, int P, int alg, float *z32_dev,
+                                double *z64_dev, int64_t ldt, void *stream) {
+    TMB_REQUIRE(Y_dev && At_dev && cd_dev && CB_dev && yy_dev && (z32_dev || z64_dev), "tmb_sobelz_cross: null pointer");
+    TMB_REQUIRE(n > 0 && V > 0 && P > 0 && xx > 0.0 && (xpos == 0 || xpos == 1) && (rowB == 0 || rowB == 1),
+                "tmb_sobelz_cross: bad shape (n=%d V=%lld P=%d x'x=%g)", n, (long long)V, P, xx);
+    TMB_REQUIRE(alg >= 0 && alg <= 2, "tmb_sobelz_cross: alg must be 0 (aroian), 1 (sobel) or 2 (goodman)");
+    TMB_REQUIRE(ydtype == TMB_F32, "tmb_sobelz_cross: float32 data only (tmb_sobelz serves float64 data)");
+    TMB_DEVICE_OF(Y_dev, "tmb_sobelz_cross");
+    GlmParams p{};
+    if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
+    TMB_REQUIRE(glm_uses_dmma(p.y_is_f64, 1), "tmb_sobelz_cross: needs the tensor-core fit (TMB_GLM=dfma is set)");
+    p.Y = Y_dev; p.n = n; p.V = V; p.ldy = ldy; p.At = At_dev; p.ldA = ldA; p.P = P; p.r = 1; p.rp = 1;
+    p.yy = yy_dev; p.t32 = z32_dev; p.t64 = z64_dev; p.ldt = ldt; p.mode = 5; p.GB = CB_dev; p.rowB = rowB; p.dofB = dofB;
+    p.cfix = cd_dev; p.xx = 1.0 / xx; p.dof = (1.0 / xx) / dofA; p.xpos = xpos; p.alg = alg; p.layout = 1;
     return launch_glm(p, (cudaStream_t)stream);
 }
 

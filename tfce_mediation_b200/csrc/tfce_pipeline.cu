@@ -1206,7 +1206,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pipe_sweep_max_kernel(Pi
         const SurfDesc sd = P.surfs[s];
         int *meta = P.meta + (size_t)item * 4;
         const int NB = meta[0], NP = meta[1];
-        const int V = sd.V;
         const size_t e0 = ((size_t)b * P.S + s) * 2;
         long long tk = P.timing ? clock64() : 0;
 #define PIPE_TICK(i)                                                                 \

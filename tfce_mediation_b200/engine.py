@@ -734,8 +734,71 @@ class PermutationEngine(object):
     def sobelz(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", want_f64=False, caller_order=True):
         """Fused two-fit Sobel-family z for a block of shuffles (pyfunc.py:130-162).
         Returns CUDA float32 [P, ld] (and float64 when want_f64)."""
+        if self.sobelz_cross_ok(medtype):
+            z32, z64 = self.sobelz_cross(medtype, pred_x, depend_y, perm_idx, alg, want_f64=want_f64)
+            if caller_order and self.colperm is not None:
+                z32 = self.to_caller_order(z32)
+                z64 = self.to_caller_order(z64) if z64 is not None else None
+            return (z32, z64) if want_f64 else z32
         XA, XB, ta_scalar = self.mediation_designs(medtype, pred_x, depend_y, perm_idx)
         return self.sobelz_designs(XA, XB, ta_scalar, alg, want_f64, caller_order)
+
+    def sobelz_cross_ok(self, medtype):
+        """Medtype 'M' / 'I' on float32 data with the tensor-core fit: one contraction row per shuffle (sobelz_cross)."""
+        return (medtype in ("M", "I") and self.Y.dtype_code == 0 and self._layout(1) == 1
+                and _os.environ.get("TMB_SOBEL", "") != "designs")
+
+    def sobelz_cross(self, medtype, pred_x, depend_y, perm_idx, alg="aroian", want_f64=False, out=None):
+        """Sobel z for medtype 'M' / 'I' from ONE fitted row per shuffle (tmb_sobelz_cross).  Only pred_x is permuted in
+        these two types (vertex_tfce_mediation_randomise.py:82-90), so of the centred cross-products with the data,
+        x_p'y and dep'y, only the first changes: dep'y is one row fitted once per (engine, depend_y), and path A's and
+        path B's betas and residual sums of squares follow per vertex from the two cross-products and the shuffle's 2 x 2
+        Gram matrix.  The host ships the index rows and 4 doubles per shuffle; the permuted predictor columns are gathered
+        on the device.  Returns (CUDA float32 [P, ld], float64 or None), internal column order."""
+        import torch
+        n = self.Y.n
+        x = np.asarray(pred_x, dtype=np.float64).reshape(n)
+        dep = np.asarray(depend_y, dtype=np.float64).reshape(n)
+        perm_idx = np.ascontiguousarray(perm_idx, dtype=np.int32)
+        P = perm_idx.shape[0]
+        algc = {"aroian": 0, "sobel": 1, "goodman": 2}.get(alg)
+        if algc is None:
+            raise ValueError("Unknown indirect test algorithm")
+        xc, dc = x - x.mean(), dep - dep.mean()
+        key = (x.tobytes(), dep.tobytes())
+        fixed = getattr(self, "_sobel_fixed", None)
+        if fixed is None or fixed[0] != key:
+            At = np.zeros((n, TILE_M), dtype=np.float64)
+            At[:, 0] = dc
+            cd = torch.empty((1, self.Y.ld), dtype=torch.float64, device=self.device)
+            At_d = torch.from_numpy(At).to(self.device)
+            _lib.check(_lib.lib().tmb_glm_beta(_lib.ptr(self.Y.t), self.Y.dtype_code, n, self.Y.V, self.Y.ld, _lib.ptr(At_d),
+                                               TILE_M, 1, _lib.ptr(cd), self.Y.ld, _lib.current_stream()))
+            fixed = (key, cd, torch.from_numpy(np.ascontiguousarray(xc[None, :])).to(self.device))
+            self._sobel_fixed = fixed
+        _, cd, xc_d = fixed
+        xx, dd = float(xc @ xc), float(dc @ dc)
+        sxd = xc[perm_idx] @ dc                                        # [P]: x_p'dep, the only entry that changes
+        xpos = 1 if medtype == "M" else 0
+        G = np.empty((P, 2, 2))
+        G[:, xpos, xpos], G[:, 1 - xpos, 1 - xpos] = xx, dd
+        G[:, 0, 1] = G[:, 1, 0] = sxd
+        CB = np.zeros((P, 8))
+        CB[:, :4] = np.linalg.inv(G).reshape(P, 4)
+        CB[:, 4] = CB[:, 0] / float(n - 3)                            # tested row 0: C[0][0] / dofB
+        CB_d = self._upload("sobel_CB", CB)
+        idx_d = self._upload("perm_idx", perm_idx)
+        ldA = int(_lib.lib().tmb_glm_packed_columns(self.Y.dtype_code, P, 1))
+        At_d = self._ring("At", (n, ldA), torch.float64)
+        lib, st = _lib.lib(), _lib.current_stream()
+        _lib.check(lib.tmb_glm_pack_rowperm(_lib.ptr(xc_d), 1, n, _lib.ptr(idx_d), P, 1, _lib.ptr(At_d), ldA, 1, st))
+        yy = self.Y.sumsq(True)
+        z32 = out if out is not None else torch.empty((P, self.Y.ld), dtype=torch.float32, device=self.device)
+        z64 = torch.empty((P, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
+        _lib.check(lib.tmb_sobelz_cross(_lib.ptr(self.Y.t), self.Y.dtype_code, n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA,
+                                        _lib.ptr(cd), xx, float(n - 2), _lib.ptr(CB_d), xpos, 0, float(n - 3), _lib.ptr(yy),
+                                        P, algc, _lib.ptr(z32), _lib.ptr(z64), self.Y.ld, st))
+        return z32, z64
 
     def mediation_designs(self, medtype, pred_x, depend_y, perm_idx):
         """Per-shuffle designs of calc_sobelz (pyfunc.py:130-162) under the drivers' permutation rule
@@ -1013,10 +1076,14 @@ class PermutationEngine(object):
         host = torch.empty((N, self.plan.S, 2), dtype=torch.float32).pin_memory()
 
         def stage1(a, b):
-            XA, XB, ta = self.mediation_designs(medtype, pred_x, depend_y, perm_idx[a:b])
-            ops = self.sobelz_operands(XA, XB, ta, alg)
             z32 = self._ring("z32", (b - a, self.Y.ld), torch.float32)
-            self.sobelz_launch(ops, out=z32)
+            if self.sobelz_cross_ok(medtype):
+                self.sobelz_cross(medtype, pred_x, depend_y, perm_idx[a:b], alg, out=z32)
+                ops = None
+            else:
+                XA, XB, ta = self.mediation_designs(medtype, pred_x, depend_y, perm_idx[a:b])
+                ops = self.sobelz_operands(XA, XB, ta, alg)
+                self.sobelz_launch(ops, out=z32)
             return z32, (self.plan.prepare(z32) if self.plan.exact_pow else None), ops
 
         nxt = stage1(*chunks[0]) if chunks else None
