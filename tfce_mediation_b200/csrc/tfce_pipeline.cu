@@ -621,7 +621,10 @@ __global__ void __launch_bounds__(256) pipe_count_wide_kernel(PipeParams P, int 
         // Also measured and rejected: queueing the candidate unions per warp (ballot-compacted) and inserting 32 at a
         // time with every lane busy -- 26.5 against 24.5 ms per 1,024 maps for the stage: the walk already costs only
         // ~12 warp instructions per step (ncu: 2,260 per warp over 4 vertices per lane and ~45 steps each), the hash
-        // path is not where the time goes, and the votes cost more than they save.
+        // path is not where the time goes, and the votes cost more than they save.  Upper bound for staging a wider
+        // window of basin ids in shared memory: with every out-of-chunk lookup skipped outright (wrong results, timing
+        // only) the stage drops from 25.1 to 22.7 ms per 1,024 maps; a 16-bit window of +-4,096 vertices would cover 91 %
+        // of them (scripts/probe_locality.py) at the price of the staging loads -- not built.
 #pragma unroll
         for (int w = 0; w < kWords; ++w) {
             unsigned m = __ldg(emw[w] + v);
