@@ -195,6 +195,19 @@ int tmb_sobelz_cross(const void *Y_dev, int ydtype, int n, int64_t V, int64_t ld
                      const double *cd_dev, double xx, double dofA, const double *CB_dev, int xpos, int rowB, double dofB,
                      const double *yy_dev, int P, int alg, float *z32_dev, double *z64_dev, int64_t ldt, void *stream);
 
+/* Sobel z for two paths whose designs share a set of PERMUTED columns and a set of FIXED columns (tm-models mediation,
+ * tm_models_randomise.py:430-520: left variable permuted; right variable and covariates fixed -- or permuted too for
+ * medtype 'Y'), from centred cross-products c = Z'y: cperm_dev float64 [P*m, ldb] = the m permuted columns' rows of every
+ * shuffle (tmb_glm_beta with the centred, permuted columns as At), cfix_dev float64 [f, ldf] = the fixed columns' rows
+ * (once).  CA_dev [P, rA, rA] / CB_dev [P, rB, rB]: INVERSE centred Gram matrices of the shuffle's designs (rA, rB <= 16);
+ * colmap (the same int32 array on the device and on the host): for path A's rA, then path B's rB regressors in design
+ * order the source row (< m: permuted row, else m + fixed row).  ta_scalar_dev replaces path A as in tmb_sobelz. */
+int tmb_sobelz_cross_rows(const double *cperm_dev, int64_t ldb, int m, const double *cfix_dev, int64_t ldf, int f, int64_t V,
+                          const double *CA_dev, int rA, int rowA, double dofA, const double *CB_dev, int rB, int rowB,
+                          double dofB, const int32_t *colmap_dev, const int32_t *colmap_host, const double *yy_dev,
+                          const double *ta_scalar_dev, int P, int alg, float *z32_dev, double *z64_dev, int64_t ldt,
+                          void *stream);
+
 /* Designs with MORE than 8 non-intercept regressors (the reference accepts any k: cynumstats.pyx:28-29,59-64 -- e.g.
  * dummy-coded sites plus covariates): the betas are formed first by tmb_glm_beta (every pseudo-inverse row of every
  * design is one column of At_dev and one output row, design-major: row p*r + i), then these evaluate the same statistics

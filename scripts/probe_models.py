@@ -41,6 +41,16 @@ print("cosinor (1 period, 1 tested, 2 cov): %.1f ms per %d shuffles = %.0f shuff
 med = rs.standard_normal(n)
 t = timed(lambda: eng.cosinor_mediation_block(time_var, [24.0], med - med.mean(), perms))
 print("cosinor mediation:                 %.1f ms per %d shuffles = %.0f shuffles/s" % (t * 1e3, P, P / t))
+left = rs.standard_normal((n, 1))
+right = 0.5 * left + rs.standard_normal((n, 1))
+for mt in ("I", "Y"):
+    t = timed(lambda: eng.tm_models_mediation_block(mt, left, right, cov, perms))
+    print("tm-models mediation %s (2 covariates): %.1f ms per %d shuffles = %.0f shuffles/s" % (mt, t * 1e3, P, P / t))
+import os
+os.environ["TMB_SOBEL"] = "designs"
+t = timed(lambda: eng.tm_models_mediation_block("I", left, right, cov, perms))
+print("   the same from two whole designs (7 rows per shuffle): %.1f ms" % (t * 1e3))
+del os.environ["TMB_SOBEL"]
 s, ns = 3, n // 3
 g2 = np.arange(ns) % 2
 f1 = (g2 - g2.mean()).astype(np.float64)

@@ -256,6 +256,31 @@ def test_sobelz_designs_matches_reference_golden(medtype):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("medtype", ["I", "M", "Y"])
+def test_tm_models_sobelz_from_cross_products_matches_reference_golden(medtype):
+    """The tm-models mediation block contracts only the PERMUTED columns with the data (tmb_sobelz_cross_rows; the fixed
+    columns' cross-products are fitted once): float64 z against the reference's glm_typeI t-values + calc_indirect."""
+    from tfce_mediation_b200.engine import PermutationEngine
+    g, _ = _golden()
+    data, cov, left, right = g["data"], g["cov"], g["med_left"], g["med_right"]
+    n = data.shape[0]
+    eng = PermutationEngine(data, None)
+    perms = g["perms"][:3]
+    ones = np.ones((3, n, 1))
+    lv = left[perms]
+    rv = right[perms] if medtype == "Y" else np.broadcast_to(right, (3,) + right.shape)
+    cv = np.broadcast_to(cov, (3,) + cov.shape)
+    XB = np.concatenate([ones, lv, rv, cv], axis=2) if medtype == "I" else np.concatenate([ones, rv, lv, cv], axis=2)
+    ta = None
+    if medtype == "Y":
+        ta = np.array([oracle.glm_typeI(rv[p], [lv[p]], cov, output_fvalues=False, output_tvalues=True)[1][0] for p in range(3)])
+    z32, z64 = eng._tm_models_sobelz_cross(medtype, left, right, cov, perms, XB, ta, "aroian", want_f64=True)
+    z = z64[:, :data.shape[1]].cpu().numpy()
+    assert np.all(np.abs(z - g["med_%s" % medtype]) <= 1e-9 * np.maximum(1.0, np.abs(g["med_%s" % medtype])))
+    assert np.array_equal(z32[:, :data.shape[1]].cpu().numpy(), z.astype(np.float32))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("medtype", ["M", "Y"])
 def test_tm_models_randomise_mediation_driver_rows(tmp_path, monkeypatch, medtype):
     from tfce_mediation_b200.tmanalysis import tm_models_randomise as drv

@@ -85,12 +85,13 @@ struct GlmParams {
     const double *yy;
     float *t32; double *t64; int64_t ldt;
     int nan_to_zero;
-    int mode;                           // 0 t-stat, 1 betas, 2 sobel, 3 F statistics, 4 cosinor (stored betas only), 5 sobel from cross-products (DMMA, one row per design)
+    int mode;                           // 0 t-stat, 1 betas, 2 sobel, 3 F statistics, 4 cosinor (stored betas only), 5 sobel from cross-products (DMMA, one row per design), 6 the same for any designs (stored rows)
     // sobel: rows [0, rA) of each design group are path A, rows [rA, rA+rB) path B
     const double *GB; const double *dB; int rA, rB, rowA, rowB; double dofB;
     const double *ta_scalar; int alg;
     const double *sstot;                                         // the reference's own SS_Total (model F numerator) or null
-    const double *cfix; double xx; int xpos;                     // mode 5 (Sobel from cross-products): dep'Y per vertex, x'x, position of x in path B
+    const double *cfix; double xx; int xpos;
+    const int32_t *colmap; int cross_m, cross_f; int64_t ldf;    // mode 6: column sources of the two paths, permuted / fixed cross-product rows                     // mode 5 (Sobel from cross-products): dep'Y per vertex, x'x, position of x in path B
     int cos_nexog, cos_mediation; double cos_ta;                 // mode 4 (cosinor): tested columns, mediation row, path-A t
     // F statistics (mode 3): per design the inverse blocks M_i = inv((X'X)^-1[S_i, S_i]) of every tested variable,
     // stored one after the other (k_i x k_i each, msz doubles per design); variable i covers rows [var_lo[i], +var_k[i])
@@ -1166,7 +1167,7 @@ __global__ void __launch_bounds__(128) glm_stats_from_beta_kernel(GlmParams p, c
     const int perm = blockIdx.y;
     if (v >= p.ldt) return;
     const bool inside = v < p.V;
-    const int rt = p.mode == 2 ? p.rA + p.rB : p.r;
+    const int rt = p.mode == 2 ? p.rA + p.rB : p.mode == 6 ? p.cross_m : p.r;
     double b[kMaxGenericR];
     for (int i = 0; i < rt; ++i) b[i] = inside ? beta[((size_t)perm * rt + i) * ldb + v] : 0.0;
     const double yyv = inside ? p.yy[v] : 0.0;
@@ -1206,6 +1207,38 @@ __global__ void __launch_bounds__(128) glm_stats_from_beta_kernel(GlmParams p, c
             if (p.t64) p.t64[off] = f;
             M += ki * ki;
         }
+    } else if (p.mode == 6) {
+        // Sobel z from centred CROSS-PRODUCTS c = Z'y instead of betas, for designs of which only some columns are
+        // permuted (tm-models mediation, tm_models_randomise.py:430-520: the left variable; covariates and the right
+        // variable stay): the permuted columns' cross-products come from the contraction (b[0 .. m)), the fixed columns'
+        // from p.cfix (f rows, fitted once).  colmap lists, for path A's rA and then path B's rB regressors in design
+        // order, the source row (< m: permuted, else fixed row - m).  p.G / p.GB hold the INVERSE centred Gram matrices of
+        // the shuffle's two designs: beta = C c, SSE = yy - c'beta.
+        const int m = p.cross_m, rA = p.rA, rB = p.rB;
+        auto source = [&](int idx) { return idx < m ? b[idx] : (inside ? __ldg(p.cfix + (size_t)(idx - m) * p.ldf + v) : 0.0); };
+        auto path_t = [&](const double *C, const int32_t *map, int r, int row, double dof) {
+            double c[16], brow = 0.0, q = 0.0;
+            for (int i = 0; i < r; ++i) c[i] = source(__ldg(map + i));
+            for (int a = 0; a < r; ++a) {
+                double bi = 0.0;
+                for (int j = 0; j < r; ++j) bi = __fma_rn(__ldg(C + a * r + j), c[j], bi);
+                q = __fma_rn(c[a], bi, q);
+                if (a == row) brow = bi;
+            }
+            return t_from(brow, yyv - q, dof, __ldg(C + row * r + row));
+        };
+        const double ta = p.ta_scalar ? p.ta_scalar[perm] : path_t(p.G + (size_t)perm * rA * rA, p.colmap, rA, p.rowA, p.dof);
+        const double tb = path_t(p.GB + (size_t)perm * rB * rB, p.colmap + rA, rB, p.rowB, p.dofB);
+        const double ta2 = __dmul_rn(ta, ta), tb2 = __dmul_rn(tb, tb);
+        double s = __dadd_rn(__ddiv_rn(1.0, tb2), __ddiv_rn(1.0, ta2));
+        const double cross = __ddiv_rn(1.0, __dmul_rn(ta2, tb2));
+        if (p.alg == 0) s = __dadd_rn(s, cross);
+        else if (p.alg == 2) s = __dsub_rn(s, cross);
+        double z = __ddiv_rn(1.0, __dsqrt_rn(s));
+        if (!inside) z = 0.0;
+        const size_t off = (size_t)perm * p.ldt + v;
+        if (p.t32) p.t32[off] = __double2float_rn(z);
+        if (p.t64) p.t64[off] = z;
     } else if (p.mode == 4) {
         // Cosinor statistics of pyfunc.py:2406-2563 glm_cosinor (permutation branch): regressors 2i, 2i+1 are the
         // cos / sin pair of period i, then nexog tested columns, then covariates.  C = inv(G) (= the slope block of
@@ -1288,7 +1321,7 @@ __global__ void __launch_bounds__(128) glm_stats_from_beta_kernel(GlmParams p, c
 }
 
 static int launch_stats_from_beta(const GlmParams &p, const double *beta, int64_t ldb, cudaStream_t stream) {
-    const int rt = p.mode == 2 ? p.rA + p.rB : p.r;
+    const int rt = p.mode == 2 ? p.rA + p.rB : p.mode == 6 ? p.cross_m : p.r;
     TMB_REQUIRE(rt >= 1 && rt <= kMaxGenericR, "glm: at most %d non-intercept regressors per design (got %d)", kMaxGenericR, rt);
     TMB_REQUIRE(p.P >= 1 && p.P <= 65535, "glm (stored betas): 1..65535 designs per call (got %d)", p.P);
     const dim3 grid((unsigned)((p.ldt + 127) / 128), (unsigned)p.P);
@@ -1556,6 +1589,27 @@ extern "C" int tmb_sobelz_cross(const void *Y_dev, int ydtype, int n, int64_t V,
     p.yy = yy_dev; p.t32 = z32_dev; p.t64 = z64_dev; p.ldt = ldt; p.mode = 5; p.GB = CB_dev; p.rowB = rowB; p.dofB = dofB;
     p.cfix = cd_dev; p.xx = 1.0 / xx; p.dof = (1.0 / xx) / dofA; p.xpos = xpos; p.alg = alg; p.layout = 1;
     return launch_glm(p, (cudaStream_t)stream);
+}
+
+extern "C" int tmb_sobelz_cross_rows(const double *cperm_dev, int64_t ldb, int m, const double *cfix_dev, int64_t ldf, int f,
+                                     int64_t V, const double *CA_dev, int rA, int rowA, double dofA, const double *CB_dev,
+                                     int rB, int rowB, double dofB, const int32_t *colmap_dev, const int32_t *colmap_host,
+                                     const double *yy_dev, const double *ta_scalar_dev, int P, int alg, float *z32_dev,
+                                     double *z64_dev, int64_t ldt, void *stream) {
+    TMB_REQUIRE(cperm_dev && CB_dev && colmap_dev && colmap_host && yy_dev && (z32_dev || z64_dev), "tmb_sobelz_cross_rows: null pointer");
+    TMB_REQUIRE(m >= 1 && m <= kMaxGenericR && f >= 0 && (f == 0 || cfix_dev) && rA >= 0 && rA <= 16 && rB >= 1 && rB <= 16 &&
+                    rowB >= 0 && rowB < rB && (ta_scalar_dev || (rA >= 1 && rowA >= 0 && rowA < rA && CA_dev)) && ldb >= V &&
+                    ldt >= V && (f == 0 || ldf >= V),
+                "tmb_sobelz_cross_rows: bad shape (m=%d f=%d rA=%d rB=%d; at most 16 regressors per path)", m, f, rA, rB);
+    TMB_REQUIRE(alg >= 0 && alg <= 2, "tmb_sobelz_cross_rows: alg must be 0 (aroian), 1 (sobel) or 2 (goodman)");
+    for (int i = 0; i < rA + rB; ++i)
+        TMB_REQUIRE(colmap_host[i] >= 0 && colmap_host[i] < m + f, "tmb_sobelz_cross_rows: column source %d out of range", colmap_host[i]);
+    TMB_DEVICE_OF(cperm_dev, "tmb_sobelz_cross_rows");
+    GlmParams p{};
+    p.V = V; p.G = CA_dev; p.GB = CB_dev; p.rA = rA; p.rB = rB; p.rowA = rowA; p.rowB = rowB; p.dof = dofA; p.dofB = dofB;
+    p.cfix = cfix_dev; p.ldf = ldf; p.cross_m = m; p.cross_f = f; p.colmap = colmap_dev; p.yy = yy_dev; p.ta_scalar = ta_scalar_dev;
+    p.P = P; p.alg = alg; p.t32 = z32_dev; p.t64 = z64_dev; p.ldt = ldt; p.mode = 6;
+    return launch_stats_from_beta(p, cperm_dev, ldb, (cudaStream_t)stream);
 }
 
 // ---- statistics from stored betas (designs with more than 8 regressors; see glm_stats_from_beta_kernel) ----------

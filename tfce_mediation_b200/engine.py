@@ -932,11 +932,95 @@ class PermutationEngine(object):
                 se = np.float32(np.sqrt(sigma2[0] * invXX[1, 1]))
                 ta_scalar[p] = a[1, 0] / se
             XA = None
-        z32 = self.sobelz_designs(XA, XB, ta_scalar, alg, caller_order=False)
+        kL, kR, kC = left.shape[1], right.shape[1], (0 if cov is None else cov.shape[1])
+        if (_os.environ.get("TMB_SOBEL", "") != "designs" and kL + (kR if medtype == "Y" else 0) <= MAX_REGRESSORS
+                and XB.shape[2] - 1 <= 16):
+            z32 = self._tm_models_sobelz_cross(medtype, left, right, cov, perm_idx, XB, ta_scalar, alg)
+        else:
+            z32 = self.sobelz_designs(XA, XB, ta_scalar, alg, caller_order=False)
         mx, status, _ = self.plan.run(z32, two_sided=False)
         self.last_status = status
         mx = mx[:, :, 0]
         return self._download(mx.contiguous()) if download else mx
+
+    def _tm_models_sobelz_cross(self, medtype, left, right, cov, perm_idx, XB, ta_scalar, alg, want_f64=False):
+        """tm-models Sobel z from centred cross-products (tmb_sobelz_cross_rows): only the permuted columns -- the left
+        variable; for 'Y' the right one too -- are contracted with the data per shuffle; the rows of the fixed columns
+        (right variable, covariates) are fitted once.  XB float64 [P, n, 1 + rB]: path B's designs (path A's columns are
+        a subset), used for the k x k Gram matrices only.  CUDA float32 [P, ld], internal column order."""
+        import torch
+        n = self.Y.n
+        P = perm_idx.shape[0]
+        kL, kR, kC = left.shape[1], right.shape[1], (0 if cov is None else cov.shape[1])
+        centre = lambda a: a - a.mean(axis=0, keepdims=True)   # noqa: E731
+        perm_cols = centre(left) if medtype != "Y" else np.column_stack([centre(left), centre(right)])
+        fixed = [centre(right)] if medtype != "Y" else []
+        if cov is not None:
+            fixed.append(centre(cov))
+        fixed = np.column_stack(fixed) if fixed else np.zeros((n, 0))
+        m, f = perm_cols.shape[1], fixed.shape[1]
+        L = list(range(kL))                                                   # sources: permuted rows first, then fixed
+        R = list(range(kL, kL + kR)) if medtype == "Y" else list(range(m, m + kR))
+        Cv = list(range(m + (0 if medtype == "Y" else kR), m + f))
+        mapA = L + Cv
+        mapB = (L + R + Cv) if medtype == "I" else (R + L + Cv)
+        rA, rB = (0 if ta_scalar is not None else len(mapA)), len(mapB)
+        colmap = np.asarray((mapA if rA else []) + mapB, dtype=np.int32)
+        # Gram matrices from the centred designs of path B; path A's columns are a subset of them
+        ZB = XB[:, :, 1:] - XB[:, :, 1:].mean(axis=1, keepdims=True)
+        GB = np.einsum("pni,pnj->pij", ZB, ZB)
+        CB = np.ascontiguousarray(np.linalg.inv(GB))
+        CA = None
+        if rA:
+            posB = {src: i for i, src in enumerate(mapB)}
+            ia = [posB[src] for src in mapA]
+            CA = np.ascontiguousarray(np.linalg.inv(GB[:, ia][:, :, ia]))
+        key = (medtype, perm_cols.tobytes(), fixed.tobytes())
+        st = getattr(self, "_tmm_fixed", None)
+        if st is None or st[0] != key:
+            cfix = None
+            if f:
+                ldF = round_up(f, TILE_M)
+                At = np.zeros((n, ldF))
+                At[:, :f] = fixed
+                cfix = torch.empty((f, self.Y.ld), dtype=torch.float64, device=self.device)
+                At_d = torch.from_numpy(At).to(self.device)
+                _lib.check(_lib.lib().tmb_glm_beta(_lib.ptr(self.Y.t), self.Y.dtype_code, n, self.Y.V, self.Y.ld, _lib.ptr(At_d),
+                                                   ldF, f, _lib.ptr(cfix), self.Y.ld, _lib.current_stream()))
+            st = (key, cfix, torch.from_numpy(np.ascontiguousarray(perm_cols.T)).to(self.device))
+            self._tmm_fixed = st
+        _, cfix, pc_d = st
+        algc = {"aroian": 0, "sobel": 1, "goodman": 2}.get(alg)
+        if algc is None:
+            raise ValueError("Unknown indirect test algorithm")
+        yy = self.Y.sumsq(True)
+        z32 = torch.empty((P, self.Y.ld), dtype=torch.float32, device=self.device)
+        z64 = torch.empty((P, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
+        colmap_d = self._upload("tmm_colmap", colmap)
+        CA_d = self._upload("tmm_CA", CA) if CA is not None else None
+        CB_d = self._upload("tmm_CB", CB)
+        ta_d = self._upload("tmm_ta", ta_scalar) if ta_scalar is not None else None
+        idx_all = np.ascontiguousarray(perm_idx, dtype=np.int32)
+        lib, stream = _lib.lib(), _lib.current_stream()
+        per = max(1, int(1.5e9 // (m * self.Y.ld * 8)))
+        for a in range(0, P, per):
+            b = min(P, a + per)
+            cnt = b - a
+            rows = cnt * m
+            ldA = round_up(rows, TILE_M)
+            idx_d = self._upload("perm_idx", idx_all[a:b])
+            At_d = self._ring("tmm_At", (n, ldA), torch.float64)
+            _lib.check(lib.tmb_glm_pack_rowperm(_lib.ptr(pc_d), m, n, _lib.ptr(idx_d), cnt, m, _lib.ptr(At_d), ldA, 0, stream))
+            cperm = self._ring("tmm_cperm", (rows, self.Y.ld), torch.float64)
+            _lib.check(lib.tmb_glm_beta(_lib.ptr(self.Y.t), self.Y.dtype_code, n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA, rows,
+                                        _lib.ptr(cperm), self.Y.ld, stream))
+            _lib.check(lib.tmb_sobelz_cross_rows(
+                _lib.ptr(cperm), self.Y.ld, m, _lib.ptr(cfix), self.Y.ld, f, self.Y.V,
+                _lib.ptr(CA_d[a:b]) if CA_d is not None else None, rA, 0, float(n - 1 - len(mapA)), _lib.ptr(CB_d[a:b]), rB, 0,
+                float(n - 1 - rB), _lib.ptr(colmap_d), _lib.ptr(colmap), _lib.ptr(yy),
+                _lib.ptr(ta_d[a:b]) if ta_d is not None else None, cnt, algc, _lib.ptr(z32[a:b]),
+                _lib.ptr(z64[a:b]) if z64 is not None else None, self.Y.ld, stream))
+        return (z32, z64) if want_f64 else z32
 
     # -- tm-models cosinor ------------------------------------------------------------------------
     def cosinor_stats(self, X, nper, nexog, perm_idx, mediation_ta=None, alg="aroian", want_f64=False, caller_order=True):
