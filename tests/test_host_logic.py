@@ -179,3 +179,15 @@ def test_bench_reads_measured_hbm_peak_tolerantly(tmp_path, monkeypatch):
     (tmp_path / "MEASURED_PEAKS.json").write_text("not json")
     val, src = bench.measured_hbm_peak()
     assert val == 6650.0 and "unreadable" in src
+
+
+def test_linregress_t_vectorised_equals_scipy_per_shuffle():
+    """The scalar path A of medtype 'Y' (pyfunc.py:142 scipy.stats.linregress per shuffle) is evaluated for all shuffles
+    at once with scipy's own formulas; a few ulp from the per-call values."""
+    from scipy.stats import linregress
+    from tfce_mediation_b200.engine import linregress_t
+    rs = np.random.RandomState(3)
+    x = rs.standard_normal((40, 120))
+    y = 0.3 * x + rs.standard_normal((40, 120))
+    want = np.array([linregress(x[p], y[p])[0] / linregress(x[p], y[p])[4] for p in range(40)])
+    assert np.all(np.abs(linregress_t(x, y) - want) <= 1e-13 * np.abs(want))

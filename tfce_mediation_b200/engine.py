@@ -320,6 +320,23 @@ def cosinor_amplitude_t(y, time_var, period):
     return out
 
 
+def linregress_t(x, y):
+    """slope / stderr of scipy.stats.linregress(x[p], y[p]) for every row p at once (the scalar path A of medtype 'Y',
+    pyfunc.py:142): scipy's own formulas -- biased covariances, r, slope = ssxym / ssxm,
+    stderr = sqrt((1 - r^2) ssym / ssxm / (n - 2)) -- vectorised over the shuffles (a per-shuffle scipy call costs
+    ~0.1 ms, more than the GPU needs for the whole shuffle); agrees with the per-call result to a few ulp."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = x.shape[1]
+    xm = x - x.mean(axis=1, keepdims=True)
+    ym = y - y.mean(axis=1, keepdims=True)
+    ssxm, ssym, ssxym = (xm * xm).sum(axis=1) / n, (ym * ym).sum(axis=1) / n, (xm * ym).sum(axis=1) / n
+    r = np.clip(ssxym / np.sqrt(ssxm * ssym), -1.0, 1.0)
+    slope = ssxym / ssxm
+    stderr = np.sqrt((1 - r ** 2) * ssym / ssxm / (n - 2))
+    return slope / stderr
+
+
 def pack_At(pinv, rp, layout=0, ldA=None):
     """[P, r, n] pseudo-inverse rows -> At float64 [n, ldA]; row i of design p goes to column p*rp + i (layout 0, the
     fp64 vector kernel) or (p // 8)*8*rp + i*8 + p % 8 (layout 1, "tile8", the tensor-core kernels: include/tfce_b200.h).
@@ -816,12 +833,8 @@ class PermutationEngine(object):
             XA = np.stack([ones, xp], axis=2)
             XB = np.stack([ones, dep, xp], axis=2) if medtype == "M" else np.stack([ones, xp, dep], axis=2)
         elif medtype == "Y":
-            from scipy.stats import linregress
             dep = depend_y[perm_idx]
-            ta_scalar = np.empty(P, dtype=np.float64)
-            for p in range(P):                                       # scalar path A, pyfunc.py:142
-                res = linregress(xp[p], dep[p])
-                ta_scalar[p] = res[0] / res[4]
+            ta_scalar = linregress_t(xp, dep)                        # scalar path A, pyfunc.py:142
             XA = None
             XB = np.stack([ones, dep, xp], axis=2)
         else:
@@ -922,15 +935,15 @@ class PermutationEngine(object):
         if medtype == "Y":
             if right.shape[1] != 1:
                 raise ValueError("medtype 'Y' needs a single-column dependent variable")
+            # n x 1 regressions of the permuted right variable on [1, left_p, cov], all shuffles at once on the host
+            # (tval_int's arithmetic, cynumstats.pyx:59-64: explicit residuals, se rounded to float32)
             k = XA.shape[2]
-            ta_scalar = np.empty(P, dtype=np.float64)
-            for p in range(P):                       # n x 1 regressions on the host (tval_int's arithmetic, cynumstats.pyx:59-64)
-                X = XA[p]
-                invXX = np.linalg.inv(X.T @ X)
-                a = (invXX @ X.T) @ rv[p]
-                sigma2 = np.sum((rv[p] - X @ a) ** 2, axis=0) / (n - k)
-                se = np.float32(np.sqrt(sigma2[0] * invXX[1, 1]))
-                ta_scalar[p] = a[1, 0] / se
+            invXX = np.linalg.inv(np.einsum("pni,pnj->pij", XA, XA))
+            a = np.einsum("pij,pj->pi", invXX, np.einsum("pni,pn->pi", XA, rv[:, :, 0]))
+            resid = rv[:, :, 0] - np.einsum("pni,pi->pn", XA, a)
+            sigma2 = np.sum(resid ** 2, axis=1) / (n - k)
+            se = np.sqrt(sigma2 * invXX[:, 1, 1]).astype(np.float32)
+            ta_scalar = a[:, 1] / se
             XA = None
         kL, kR, kC = left.shape[1], right.shape[1], (0 if cov is None else cov.shape[1])
         if (_os.environ.get("TMB_SOBEL", "") != "designs" and kL + (kR if medtype == "Y" else 0) <= MAX_REGRESSORS
