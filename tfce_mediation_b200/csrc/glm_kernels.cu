@@ -746,6 +746,65 @@ __device__ __forceinline__ double dpick(const double (&b)[RP], int idx) {
     return v;
 }
 
+// Sobel z of pyfunc.py:130-162 for medtype 'M' / 'I' from ONE contraction row per shuffle (mode 5, tmb_sobelz_cross).  Only
+// pred_x is permuted (vertex_tfce_mediation_randomise.py:82-90), so of the centred cross-products c_x = x_p'y and
+// c_d = dep'y only c_x changes with the shuffle; c_d comes from one extra row fitted once (p.cfix).  Path A, y ~ [1, x_p]:
+// beta = c_x / x'x, SSE = yy - c_x beta.  Path B, y ~ [1, dep, x_p] ('M', xpos 1) or [1, x_p, dep] ('I', xpos 0):
+// beta = C c with C = inverse of the shuffle's centred 2 x 2 Gram matrix, SSE = yy - c'beta.  The per-design constants
+// (C00, C01, C10, C11, C[rowB][rowB] / dofB) are loaded once per design by the caller.
+// The epilogue shares the fp64 pipe with the DMMAs, so it is kept to three divisions and three square roots per value:
+// 1 / x'x and d / dof are formed on the host (the k = 2 kernel does the same: <= 1 ulp in float64 before the reference's
+// own rounding of se to float32), and z = 1 / sqrt(1/tb^2 + 1/ta^2 + 1/(ta^2 tb^2)) is evaluated as
+// sqrt(ta^2 tb^2 / (ta^2 + tb^2 + 1)) unless a square is zero, subnormal or overflowing -- then the reference's own sequence
+// runs, for its inf / NaN results.  float32 output only: the two t values and the square root of the ratio come from
+// float32 seeds plus one Newton step each (t64_fast, sqrt_ratio32_fast), accepted unless an intermediate float32 rounding
+// (se of either path, z itself) is too close to call -- then the exact sequence runs.  Bit-identical to it by construction
+// (tests compare the two on whole blocks).
+__device__ __forceinline__ void sobel_cross_value(const GlmParams &p, int perm, double cx, double cd, double yyv, int64_t v,
+                                                  double C00, double C01, double C10, double C11, double dsB) {
+    const bool inside = v < p.V;
+    const double bA = __dmul_rn(cx, p.xx);                               // p.xx = 1 / x'x
+    const double sseA = yyv - __dmul_rn(cx, bA);
+    const double c0 = p.xpos == 0 ? cx : cd, c1 = p.xpos == 0 ? cd : cx;
+    const double b0 = __fma_rn(C01, c1, __dmul_rn(C00, c0));
+    const double b1 = __fma_rn(C11, c1, __dmul_rn(C10, c0));
+    const double sseB = yyv - __fma_rn(c1, b1, __dmul_rn(c0, b0));
+    const double bB = p.rowB ? b1 : b0;
+    if (p.t64 == nullptr && !p.exact_epilogue) {
+        bool slow = false;
+        const double fa = t64_fast(bA, sseA, p.dof, slow), fb = t64_fast(bB, sseB, dsB, slow);
+        const double fa2 = __dmul_rn(fa, fa), fb2 = __dmul_rn(fb, fb);
+        const double fsum = __dadd_rn(fa2, fb2);
+        const double fden = p.alg == 0 ? __dadd_rn(fsum, 1.0) : p.alg == 2 ? __dsub_rn(fsum, 1.0) : fsum;
+        if (p.alg == 2 && !(fsum > 2.0)) slow = true;       // Goodman: ta^2 + tb^2 - 1 cancels, the error bound does not hold
+        const float zf = sqrt_ratio32_fast(__dmul_rn(fa2, fb2), fden, slow);
+        if (!slow) {
+            p.t32[(size_t)perm * p.ldt + v] = inside ? zf : 0.f;
+            return;
+        }
+    }
+    const double ta = t_from_scaled(bA, sseA, p.dof);                    // p.dof = (1 / x'x) / dofA
+    const double tb = t_from_scaled(bB, sseB, dsB);
+    const double ta2 = __dmul_rn(ta, ta), tb2 = __dmul_rn(tb, tb);
+    const double prod = __dmul_rn(ta2, tb2);
+    double z;
+    if (prod > 1e-280 && prod < 1e280) {
+        const double sum = __dadd_rn(ta2, tb2);
+        const double den = p.alg == 0 ? __dadd_rn(sum, 1.0) : p.alg == 2 ? __dsub_rn(sum, 1.0) : sum;
+        z = __dsqrt_rn(__ddiv_rn(prod, den));
+    } else {
+        double s = __dadd_rn(__ddiv_rn(1.0, tb2), __ddiv_rn(1.0, ta2));
+        const double cross = __ddiv_rn(1.0, prod);
+        if (p.alg == 0) s = __dadd_rn(s, cross);
+        else if (p.alg == 2) s = __dsub_rn(s, cross);
+        z = __ddiv_rn(1.0, __dsqrt_rn(s));
+    }
+    if (!inside) z = 0.0;
+    const size_t off = (size_t)perm * p.ldt + v;
+    if (p.t32) p.t32[off] = __double2float_rn(z);
+    if (p.t64) p.t64[off] = z;
+}
+
 // all statistics of one (design, vertex) from its RP betas; same arithmetic as epilogue<RP> of the DFMA kernel
 template <int RP>
 __device__ __forceinline__ void dmma_vertex_stats(const GlmParams &p, int perm, const double (&b)[RP], double yyv, int64_t v) {
@@ -790,63 +849,6 @@ __device__ __forceinline__ void dmma_vertex_stats(const GlmParams &p, int perm, 
             if (p.t64) p.t64[off] = f;
             M += ki * ki;
         }
-    } else if (p.mode == 5) {
-        // Sobel z of pyfunc.py:130-162 for medtype 'M' / 'I' from ONE contraction row per shuffle.  Only pred_x is permuted
-        // (vertex_tfce_mediation_randomise.py:82-90), so of the centred cross-products c_x = x_p'y and c_d = dep'y only c_x
-        // changes with the shuffle; c_d comes from one extra row fitted once (p.cfix).  Path A, y ~ [1, x_p]:
-        // beta = c_x / x'x, SSE = yy - c_x beta.  Path B, y ~ [1, dep, x_p] ('M', xpos 1) or [1, x_p, dep] ('I', xpos 0):
-        // beta = C c with C = inverse of the shuffle's centred 2 x 2 Gram matrix (p.GB), SSE = yy - c'beta.
-        // The epilogue shares the fp64 pipe with the DMMAs, so it is kept to three divisions and three square roots per
-        // value: 1 / x'x and d / dof are formed on the host (the k = 2 kernel does the same: <= 1 ulp in float64 before
-        // the reference's own rounding of se to float32), and z = 1 / sqrt(1/tb^2 + 1/ta^2 + 1/(ta^2 tb^2)) is evaluated as
-        // sqrt(ta^2 tb^2 / (ta^2 + tb^2 + 1)) unless a square is zero, subnormal or overflowing -- then the reference's own
-        // sequence runs, for its inf / NaN results.
-        const double cx = b[0], cd = inside ? __ldg(p.cfix + v) : 0.0;
-        const double bA = __dmul_rn(cx, p.xx);                               // p.xx = 1 / x'x
-        const double sseA = yyv - __dmul_rn(cx, bA);
-        const double *C = p.GB + (size_t)perm * 8;
-        const double c0 = p.xpos == 0 ? cx : cd, c1 = p.xpos == 0 ? cd : cx;
-        const double b0 = __fma_rn(__ldg(C + 1), c1, __dmul_rn(__ldg(C), c0));
-        const double b1 = __fma_rn(__ldg(C + 3), c1, __dmul_rn(__ldg(C + 2), c0));
-        const double sseB = yyv - __fma_rn(c1, b1, __dmul_rn(c0, b0));
-        const double bB = p.rowB ? b1 : b0, dsB = __ldg(C + 4);              // C[4] = C[rowB][rowB] / dofB
-        if (p.t64 == nullptr && !p.exact_epilogue) {
-            // float32 output only: the two t values and the square root of the ratio from float32 seeds plus one Newton
-            // step each (t64_fast, sqrt_ratio32_fast); accepted unless an intermediate float32 rounding (se of either
-            // path, z itself) is too close to call -- then the exact sequence below runs.  Bit-identical to it by
-            // construction (tests compare the two on whole blocks).
-            bool slow = false;
-            const double fa = t64_fast(bA, sseA, p.dof, slow), fb = t64_fast(bB, sseB, dsB, slow);
-            const double fa2 = __dmul_rn(fa, fa), fb2 = __dmul_rn(fb, fb);
-            const double fsum = __dadd_rn(fa2, fb2);
-            const double fden = p.alg == 0 ? __dadd_rn(fsum, 1.0) : p.alg == 2 ? __dsub_rn(fsum, 1.0) : fsum;
-            if (p.alg == 2 && !(fsum > 2.0)) slow = true;       // Goodman: ta^2 + tb^2 - 1 cancels, the error bound does not hold
-            const float zf = sqrt_ratio32_fast(__dmul_rn(fa2, fb2), fden, slow);
-            if (!slow) {
-                p.t32[(size_t)perm * p.ldt + v] = inside ? zf : 0.f;
-                return;
-            }
-        }
-        const double ta = t_from_scaled(bA, sseA, p.dof);                    // p.dof = (1 / x'x) / dofA
-        const double tb = t_from_scaled(bB, sseB, dsB);
-        const double ta2 = __dmul_rn(ta, ta), tb2 = __dmul_rn(tb, tb);
-        const double prod = __dmul_rn(ta2, tb2);
-        double z;
-        if (prod > 1e-280 && prod < 1e280) {
-            const double sum = __dadd_rn(ta2, tb2);
-            const double den = p.alg == 0 ? __dadd_rn(sum, 1.0) : p.alg == 2 ? __dsub_rn(sum, 1.0) : sum;
-            z = __dsqrt_rn(__ddiv_rn(prod, den));
-        } else {
-            double s = __dadd_rn(__ddiv_rn(1.0, tb2), __ddiv_rn(1.0, ta2));
-            const double cross = __ddiv_rn(1.0, prod);
-            if (p.alg == 0) s = __dadd_rn(s, cross);
-            else if (p.alg == 2) s = __dsub_rn(s, cross);
-            z = __ddiv_rn(1.0, __dsqrt_rn(s));
-        }
-        if (!inside) z = 0.0;
-        const size_t off = (size_t)perm * p.ldt + v;
-        if (p.t32) p.t32[off] = __double2float_rn(z);
-        if (p.t64) p.t64[off] = z;
     } else { // sobel (pyfunc.py:130-162)
         const int rA = p.rA, rB = p.rB;
         double ta;
@@ -958,6 +960,23 @@ __global__ void __launch_bounds__(256, 2) glm_dmma_multi_kernel(GlmParams p, int
     for (int gi = 0; gi < MT / RP; ++gi) {
         const int perm = ((m0 / 8 + wm * MT) / RP + gi) * 8 + g;
         if (perm >= p.P) continue;
+        if (RP == 1 && p.mode == 5) { // Sobel from cross-products: the design's five constants once, then its 8 values
+            const double *C = p.GB + (size_t)perm * 8;
+            const double C00 = __ldg(C), C01 = __ldg(C + 1), C10 = __ldg(C + 2), C11 = __ldg(C + 3), dsB = __ldg(C + 4);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int64_t v = v0 + wn * (NT * 8) + j * 8 + t4 * 2;
+                if (v >= p.ldt) continue;
+                // v is even and ldt a multiple of 4: the pair (v, v + 1) is inside the padded row
+                const double2 cd = (v + 1 < p.V) ? __ldg(reinterpret_cast<const double2 *>(p.cfix + v))
+                                                 : make_double2(v < p.V ? __ldg(p.cfix + v) : 0.0, 0.0);
+                const double2 yv = (v + 1 < p.V) ? __ldg(reinterpret_cast<const double2 *>(p.yy + v))
+                                                 : make_double2(v < p.V ? __ldg(p.yy + v) : 0.0, 0.0);
+                sobel_cross_value(p, perm, acc[gi][j][0], cd.x, yv.x, v, C00, C01, C10, C11, dsB);
+                sobel_cross_value(p, perm, acc[gi][j][1], cd.y, yv.y, v + 1, C00, C01, C10, C11, dsB);
+            }
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
 #pragma unroll
@@ -1581,6 +1600,8 @@ extern "C" int tmb_sobelz_cross(const void *Y_dev, int ydtype, int n, int64_t V,
                 "tmb_sobelz_cross: bad shape (n=%d V=%lld P=%d x'x=%g)", n, (long long)V, P, xx);
     TMB_REQUIRE(alg >= 0 && alg <= 2, "tmb_sobelz_cross: alg must be 0 (aroian), 1 (sobel) or 2 (goodman)");
     TMB_REQUIRE(ydtype == TMB_F32, "tmb_sobelz_cross: float32 data only (tmb_sobelz serves float64 data)");
+    TMB_REQUIRE(((reinterpret_cast<uintptr_t>(cd_dev) | reinterpret_cast<uintptr_t>(yy_dev)) & 15) == 0 && ldt % 4 == 0,
+                "tmb_sobelz_cross: cd_dev and yy_dev must be 16-byte aligned, ldt a multiple of 4");
     TMB_DEVICE_OF(Y_dev, "tmb_sobelz_cross");
     GlmParams p{};
     if (dtype_is_f64(ydtype, &p.y_is_f64)) return 1;
