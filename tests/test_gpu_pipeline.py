@@ -132,18 +132,24 @@ def test_voxel_adjacency_wide_rows():
     _check_max(plan, stat, [(csr, 0, V, 2, 0.5, None)])
 
 
-@pytest.mark.parametrize("geom", ["1", "2"])
-def test_max_only_both_sweep_geometries(monkeypatch, geom):
-    """TMB_PIPE_GEOM: one 1,024-thread sweep CTA per SM, or two 512-thread CTAs per SM with the large geometry taking
-    the maps the small one cannot hold (rough maps: thousands of basins).  Both bit-exact against the oracle."""
+@pytest.mark.parametrize("level,geom", [(6, "1"), (6, "2"), (5, "1"), (5, "2"), (5, "3"), (5, "4"), (5, "0"), (4, "0")])
+def test_max_only_sweep_geometries(monkeypatch, level, geom):
+    """TMB_PIPE_GEOM: one 1,024-thread sweep CTA per SM (1), two of 512 (2), four of 256 (3), eight of 128 (4), the large
+    geometry taking the maps a smaller one cannot hold (rough maps: thousands of basins); 0 = chosen by surface size (two
+    CTAs per SM above 40,000 vertices, four up to that, eight up to 16,000).  All bit-exact against the oracle, with and
+    without vertex weights."""
     from tfce_mediation_b200.engine import Surface, TfcePlan
     monkeypatch.setenv("TMB_PIPE_GEOM", geom)
-    _, _, csr6 = helpers.ico(6)
-    V6 = csr6[0].shape[0] - 1
-    plan = TfcePlan([Surface(_adjset(2, 0.67, csr6), 0)])
+    _, _, csr = helpers.ico(level)
+    V = csr[0].shape[0] - 1
+    plan = TfcePlan([Surface(_adjset(2, 0.67, csr), 0)])
     rs = np.random.RandomState(77)
-    rows = [helpers.smooth_map(csr6, 900 + b, b) for b in range(3)]           # white noise, then smoother
-    rows.append(rs.standard_normal(V6).astype(np.float32))                    # ~ one basin per 7 vertices
-    rows.append(np.abs(rs.standard_normal(V6)).astype(np.float32))            # one sign only
+    rows = [helpers.smooth_map(csr, 900 + b, b) for b in range(3)]            # white noise, then smoother
+    rows.append(rs.standard_normal(V).astype(np.float32))                     # ~ one basin per 7 vertices
+    rows.append(np.abs(rs.standard_normal(V)).astype(np.float32))             # one sign only
     stat = np.ascontiguousarray(np.stack(rows), dtype=np.float32)
-    _check_max(plan, stat, [(csr6, 0, V6, 2, 0.67, None)], two_sided=True)
+    _check_max(plan, stat, [(csr, 0, V, 2, 0.67, None)], two_sided=True)
+    if level == 5:
+        w = (0.5 + rs.rand(V)).astype(np.float32)
+        planw = TfcePlan([Surface(_adjset(2, 0.67, csr), 0, w)])
+        _check_max(planw, stat, [(csr, 0, V, 2, 0.67, w)], two_sided=True)

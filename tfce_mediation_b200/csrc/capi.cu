@@ -93,6 +93,7 @@ struct tmb_plan {
     char *d_pipe_slots = nullptr;
     size_t pipe_slot_stride = 0;
     int pipe_slots = 0;
+    int pipe_sms = 0;           // SMs of the device (the sweep grids are multiples of it)
     // device-built threshold tables (exact_pow = False) for `tab_items` work items
     int tab_items = 0;
     char *d_tabs = nullptr;     // maxima | ns | status | delta | T | HH
@@ -445,7 +446,9 @@ extern "C" int tmb_plan_create(int device, int S, tmb_graph *const *graphs, cons
                 if ((e = cudaMemcpy(g->d_sell_off, g->sell_off_host.data(), sizeof(int32_t) * g->sell_off_host.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
                     return fail("memcpy", e);
             }
-        p->pipe_slots = 2 * prop.multiProcessorCount; // up to two sweep CTAs per SM
+        // sweep CTAs per SM: two of 512 threads; four of 256 / eight of 128 for plans of small surfaces (launch_tfce_pipeline)
+        p->pipe_sms = prop.multiProcessorCount;
+        p->pipe_slots = pipe_slots_per_sm(p->Vmax) * prop.multiProcessorCount;
     }
     bool wfast_ok = true;
     for (int s = 0; s < S; ++s) {
@@ -740,7 +743,7 @@ static int plan_launch(tmb_plan *p, const float *stat, int64_t ld, int B, int tw
         pp.ell_self = 1;
         for (int s = 0; s < p->S; ++s) if (!p->graphs[s]->d_ell_self) pp.ell_self = 0;
         for (int s = 0; s < p->S; ++s) pp.max_degree = std::max(pp.max_degree, (int)p->graphs[s]->max_degree);
-        if (launch_tfce_pipeline(pp, p->pipe_slots, stream)) return 1;
+        if (launch_tfce_pipeline(pp, p->pipe_slots, p->pipe_sms, stream)) return 1;
         TableSet sub;
         sub.ns = pp.tab_ns; sub.delta = pp.tab_delta; sub.T = pp.tab_T; sub.HH = pp.tab_HH; sub.status = pp.tab_status;
         sub.scale = pp.tab_scale;

@@ -205,7 +205,8 @@ int launch_tfce_sweep(const SweepParams &p, int num_slots, cudaStream_t stream);
 int launch_tfce_maxima(const SurfDesc *surfs, int S, const float *stat, int64_t ld, int B, float *max_out,
                        cudaStream_t stream);
 size_t tfce_slot_bytes_for(int32_t Vmax, int use_basin);
-int launch_tfce_pipeline(const PipeParams &p, int num_slots, cudaStream_t stream);
+int launch_tfce_pipeline(const PipeParams &p, int num_slots, int sm_count, cudaStream_t stream);
+int pipe_slots_per_sm(int Vmax); // sweep CTAs per SM for a plan whose largest surface has Vmax vertices (2, 4 or 8)
 int launch_tfce_tables(const SurfDesc *surfs, int S, int count, const float *maxima, int two_sided, int32_t *ns,
                        float *delta, float *T, float *HH, int32_t *st, cudaStream_t stream);
 size_t pipe_slot_bytes(int32_t Vmax, int nbcap, int paircap);

@@ -1700,6 +1700,14 @@ __global__ void __launch_bounds__(256) pipe_output_kernel(PipeParams P, int chun
 }
 
 // ------------------------------------------------------------------------------------------- host
+// Sweep geometry by surface size.  A map's ~100 levels are a chain of short barrier intervals bound by memory latency, so
+// small maps -- whose basin state needs little shared memory -- run with more, smaller CTAs per SM, i.e. more maps in
+// flight: BASELINE config 1 (10,242 vertices, 4,096 maps per step): 6.23 ms with two 512-thread CTAs per SM, 4.41 ms with
+// four of 256, 3.37 ms with eight of 128.
+static constexpr int kTinyVmax = 40000;  // up to this many vertices: four 256-thread CTAs per SM (36 KB of basin state each)
+static constexpr int kMicroVmax = 16000; // up to this many: eight 128-thread CTAs per SM (11 KB each)
+int pipe_slots_per_sm(int Vmax) { return Vmax <= kMicroVmax ? 8 : Vmax <= kTinyVmax ? 4 : 2; }
+
 int pipe_sweep_max_smem() {
     int v = 200 * 1024;
     if (const char *g = getenv("TMB_PIPE_SMEM_KB")) { const int kb = atoi(g); if (kb >= 16 && kb <= 224) v = kb * 1024; }
@@ -1715,7 +1723,7 @@ int launch_tfce_tables(const SurfDesc *surfs, int S, int count, const float *max
     return 0;
 }
 
-int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t stream) {
+int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, int sm_count, cudaStream_t stream) {
     PipeParams p = p_in;
     if (const char *d = getenv("TMB_PIPE_DEBUG")) p.flags |= atoi(d) & ~7; // timing experiments only (results invalid)
     const int items = p.B * p.S;
@@ -1781,23 +1789,40 @@ int launch_tfce_pipeline(const PipeParams &p_in, int num_slots, cudaStream_t str
         // class path (values per vertex): one 1024-thread CTA per SM
         const int smem = pipe_sweep_max_smem();
         TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_kernel<1024, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        const int grid = items < num_slots / 2 ? items : num_slots / 2;
+        const int grid = items < sm_count ? items : sm_count;
         pipe_sweep_kernel<1024, 1, false><<<grid, 1024, smem, stream>>>(p, smem);
     } else {
-        // max-only path.  Default (TMB_PIPE_GEOM=2): two 512-thread CTAs per SM (small geometry) that hide each other's
+        // max-only path.  Default for surfaces above kTinyVmax vertices (TMB_PIPE_GEOM=2): two 512-thread CTAs per SM (small geometry) that hide each other's
         // barrier intervals, then one launch of the large geometry (one 1,024-thread CTA per SM) for the maps the small
         // one could not hold.  TMB_PIPE_GEOM=1: large geometry only.  Measured on config 2 (B200, whole TFCE stage):
         // 1,024 maps 9.15 -> 9.04 ms, 2,048 maps 18.05 -> 17.20 ms (the small geometry's longer maps cost more at the
         // tail of a launch, so it pays with more maps per launch).
-        int geom = 2;
+        int geom = 0;                                               // 0: choose by surface size
         if (const char *g = getenv("TMB_PIPE_GEOM")) geom = atoi(g);
-        const int smem_large = 196 * 1024, smem_small = 94 * 1024;
-        const int grid_large = items < num_slots / 2 ? items : num_slots / 2;
-        const int grid_small = items < num_slots ? items : num_slots;
+        const int smem_large = 196 * 1024, smem_small = 94 * 1024, smem_tiny = 36 * 1024;
+        const int grid_large = items < sm_count ? items : sm_count;
+        const int grid_small = items < 2 * sm_count ? items : 2 * sm_count;
+        const int grid_tiny = items < 4 * sm_count ? items : 4 * sm_count;
+        // Small surfaces: geometry 3 (four 256-thread CTAs per SM) or 4 (eight of 128), see kTinyVmax / kMicroVmax.
+        if (geom < 1 || geom > 4) geom = p.Vmax <= kMicroVmax ? 4 : p.Vmax <= kTinyVmax ? 3 : 2;
+        if (geom == 4 && num_slots < 8 * sm_count) geom = 3;
+        if (geom == 3 && num_slots < 4 * sm_count) geom = 2;
 #define TMB_SWEEP_MAX(W)                                                                                                   \
         TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<1024, 1, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_large)); \
         if (geom == 1) {                                                                                                   \
             pipe_sweep_max_kernel<1024, 1, false, W><<<grid_large, 1024, smem_large, stream>>>(p, smem_large, 0);          \
+        } else if (geom == 4) {                                                                                            \
+            TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<128, 8, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * 1024)); \
+            pipe_sweep_max_kernel<128, 8, true, W><<<(items < 8 * sm_count ? items : 8 * sm_count), 128, 11 * 1024, stream>>>(p, 11 * 1024, 1); \
+            TMB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));                                             \
+            pipe_sweep_max_kernel<1024, 1, false, W><<<grid_large, 1024, smem_large, stream>>>(p, smem_large, 2);          \
+            count_launch();                                                                                                \
+        } else if (geom == 3) {                                                                                            \
+            TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<256, 4, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tiny)); \
+            pipe_sweep_max_kernel<256, 4, true, W><<<grid_tiny, 256, smem_tiny, stream>>>(p, smem_tiny, 1);                \
+            TMB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));                                             \
+            pipe_sweep_max_kernel<1024, 1, false, W><<<grid_large, 1024, smem_large, stream>>>(p, smem_large, 2);          \
+            count_launch();                                                                                                \
         } else {                                                                                                           \
             TMB_CUDA(cudaFuncSetAttribute(pipe_sweep_max_kernel<512, 2, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_small)); \
             pipe_sweep_max_kernel<512, 2, true, W><<<grid_small, 512, smem_small, stream>>>(p, smem_small, 1);             \
