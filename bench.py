@@ -45,7 +45,7 @@ sys.path.insert(0, ROOT)
 METRIC = "permutations/sec (regression+TFCE+max)"
 TFCE_STAGE = "tfce pipeline (pipe_levels + pipe_ascent + pipe_basin + pipe_count + pipe_sweep_max kernels)"
 UNIT = "permutations/s"
-DEFAULT_BLOCK = {"config1": 4096, "config2": 1024, "config2_3mm": 512, "config3": 1024, "config4": 1024,
+DEFAULT_BLOCK = {"config1": 8192, "config2": 1024, "config2_3mm": 512, "config3": 1024, "config4": 1024,
                  "config5": 128, "tiny": 64}
 
 
