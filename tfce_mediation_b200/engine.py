@@ -945,7 +945,7 @@ class PermutationEngine(object):
             se = np.sqrt(sigma2 * invXX[:, 1, 1]).astype(np.float32)
             ta_scalar = a[:, 1] / se
             XA = None
-        kL, kR, kC = left.shape[1], right.shape[1], (0 if cov is None else cov.shape[1])
+        kL, kR = left.shape[1], right.shape[1]
         if (_os.environ.get("TMB_SOBEL", "") != "designs" and kL + (kR if medtype == "Y" else 0) <= MAX_REGRESSORS
                 and XB.shape[2] - 1 <= 16):
             z32 = self._tm_models_sobelz_cross(medtype, left, right, cov, perm_idx, XB, ta_scalar, alg)
@@ -964,7 +964,7 @@ class PermutationEngine(object):
         import torch
         n = self.Y.n
         P = perm_idx.shape[0]
-        kL, kR, kC = left.shape[1], right.shape[1], (0 if cov is None else cov.shape[1])
+        kL, kR = left.shape[1], right.shape[1]
         centre = lambda a: a - a.mean(axis=0, keepdims=True)   # noqa: E731
         perm_cols = centre(left) if medtype != "Y" else np.column_stack([centre(left), centre(right)])
         fixed = [centre(right)] if medtype != "Y" else []
