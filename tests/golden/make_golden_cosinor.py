@@ -47,6 +47,14 @@ def main():
         out["F_" + tag], out["tamp_" + tag], out["tacr_" + tag] = np.stack(F), np.stack(TA), np.stack(TC)
         if ex is not None:
             out["texog_" + tag] = np.stack(TE)
+    # the un-permuted call of STEP_1_tm_models.py (all twelve outputs) and the fit-only form
+    names = ("R2", "MESOR", "SE_MESOR", "AMPLITUDE", "SE_AMPLITUDE", "ACROPHASE", "SE_ACROPHASE", "Fmodel", "tMESOR",
+             "tAMPLITUDE", "tACROPHASE", "tEXOG")
+    full = pyfunc.glm_cosinor(endog=data, time_var=time_var, exog=exog, dmy_covariates=cov, rand_array=None, period=period)
+    for nm, val in zip(names, full):
+        out["obs_" + nm] = np.asarray(val, dtype=np.float64)
+    fit = pyfunc.glm_cosinor(endog=data, time_var=time_var, exog=exog, dmy_covariates=cov, period=period, output_fit_only=True)
+    out["fit_MESOR"], out["fit_AMPLITUDE"], out["fit_ACROPHASE"] = (np.asarray(v, dtype=np.float64) for v in fit)
     # cosinor mediation (tm_models_randomise.py:383-412)
     mediator = 0.8 * np.cos(2 * np.pi * (time_var - 3.0) / 24.0) + 0.5 * rs.standard_normal(n)
     mediator = mediator - mediator.mean()

@@ -243,3 +243,33 @@ def test_tm_models_randomise_cosinor_mediation_driver_rows(tmp_path, monkeypatch
     perms = [oracle.permutation_indices(p * 1000 + 5, st["n"]) for p in range(1, 5)]
     got = _rows("output_medcosinor_area/perm_cosinor/perm_Zstat_M_TFCE_maxVertex.csv")
     assert np.allclose(got, _oracle_mediation_rows(st, perms, [24.0]), rtol=1e-5, atol=6e-5)
+
+
+@pytest.mark.gpu
+def test_glm_cosinor_dropin_matches_reference_golden():
+    """pyfunc.glm_cosinor with the reference's signature: all twelve outputs of the un-permuted call, the fit-only form, a
+    permuted call, and the 1-D path-A call of the cosinor mediation, against the real reference (golden)."""
+    from tfce_mediation_b200 import pyfunc
+    g = _golden()
+    exog, cov, period = _case(g, "full")
+    names = ("R2", "MESOR", "SE_MESOR", "AMPLITUDE", "SE_AMPLITUDE", "ACROPHASE", "SE_ACROPHASE", "Fmodel", "tMESOR",
+             "tAMPLITUDE", "tACROPHASE", "tEXOG")
+    got = pyfunc.glm_cosinor(endog=g["data"], time_var=g["time_var"], exog=exog, dmy_covariates=cov, period=period)
+    assert len(got) == 12
+    for nm, val in zip(names, got):
+        want = g["obs_" + nm]
+        val = np.asarray(val, dtype=np.float64)
+        assert val.shape == want.shape, nm
+        # SE_MESOR is float32 in the reference (se_of_slope); R2 and Fmodel carry its float32 SS_Total, restated on the host
+        assert _close64(val, want, 1e-9), nm
+    fit = pyfunc.glm_cosinor(endog=g["data"], time_var=g["time_var"], exog=exog, dmy_covariates=cov, period=period,
+                             output_fit_only=True)
+    for nm, val in zip(("MESOR", "AMPLITUDE", "ACROPHASE"), fit):
+        assert _close64(np.asarray(val), g["fit_" + nm], 1e-9), nm
+    r = g["perms"][2]
+    perm = pyfunc.glm_cosinor(endog=g["data"], time_var=g["time_var"], exog=exog, dmy_covariates=cov, rand_array=r,
+                              period=period, calc_MESOR=False)
+    assert perm[0] is None and _close64(perm[7], g["F_full"][2], 1e-9) and _close64(perm[9], g["tamp_full"][2], 1e-9)
+    assert _close64(perm[10], g["tacr_full"][2], 1e-9) and _close64(perm[11], g["texog_full"][2], 1e-9)
+    ta = pyfunc.glm_cosinor(endog=g["mediator"], time_var=g["time_var"], period=[24.0])[9]
+    assert _close64(np.asarray(ta), g["med_ta"], 1e-9)

@@ -277,3 +277,40 @@ def test_rm_ancova_driver_under_torchrun_gives_the_single_process_rows(tmp_path)
         out = os.path.join(wd, "output_rmANCOVA1BS_area/perm_rmANCOVA1BS")
         outs.append([open("%s/perm_Fstat_%s_TFCE_maxVertex.csv" % (out, nm)).read() for nm in ("sex", "time", "sex.X.time")])
     assert outs[0] == outs[1] and len(outs[0][0].splitlines()) == 6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["one", "two"])
+@pytest.mark.parametrize("tag", ["cov", "nocov"])
+def test_reg_rm_ancova_dropins_match_reference_golden(kind, tag):
+    """pyfunc.reg_rm_ancova_{one,two}_bs_factor with the reference's signatures: un-permuted, p-values, and the permutation
+    form with its side effect -- the caller's data are shuffled in place with the global numpy stream, cumulatively."""
+    from scipy.stats import f as f_dist
+    from tfce_mediation_b200 import pyfunc
+    g = _golden()
+    cov = g["cov"] if tag == "cov" else None
+    n = g["f1"].shape[0]
+
+    def call(data, **kw):
+        if kind == "one":
+            return pyfunc.reg_rm_ancova_one_bs_factor(data, g["f1"], g["subjects"], dmy_covariates=cov, verbose=False, **kw)
+        return pyfunc.reg_rm_ancova_two_bs_factor(data, g["f1"], g["f2"], g["subjects"], dmy_covariates=cov, verbose=False, **kw)
+
+    want = g["%s_%s" % (kind, tag)]
+    got = call(g["data"].copy())
+    assert len(got) == want.shape[0] and _close64(np.stack(got), want, 1e-9)
+    sig = call(g["data"].copy(), output_sig=True)
+    assert len(sig) == 2 * want.shape[0]
+    s_, c = 3, (0 if cov is None else cov.shape[1])
+    df_a, df_b = 2, 1
+    df_w = (n - 1) - df_a - c - ((df_b + df_a * df_b) if kind == "two" else 0)
+    assert np.allclose(sig[want.shape[0]], 1 - f_dist.cdf(want[0], df_a, df_w), rtol=0, atol=1e-9)       # P of the first factor
+    assert np.allclose(sig[-1], 1 - f_dist.cdf(want[-1], (df_a * df_b if kind == "two" else df_a) * (s_ - 1), df_w * (s_ - 1)),
+                       rtol=0, atol=1e-9)
+    work = g["data"].copy()
+    np.random.seed(int(g["seed"]))
+    for it in range(ITERS):
+        rand_array = np.random.permutation(list(range(n)))
+        got = call(work, rand_array=rand_array)
+        assert _close64(np.stack(got), g["perm_%s_%s" % (kind, tag)][it], 1e-9), it
+    assert not np.array_equal(work, g["data"])           # shuffled in place, like the reference

@@ -207,6 +207,141 @@ def glm_typeI(endog, exog, dmy_covariates=None, output_fvalues=True, output_tval
     print("No output has been selected")
 
 
+def _rm_ancova(data, factors, dmy_subjects, dmy_covariates, data_format, output_sig, verbose, rand_array,
+               use_reduced_residuals, output_reduced_residuals, labels):
+    """Body of the two repeated-measures ANCOVA drop-ins: long-format view, the reference's side effects on `data`, the GPU
+    statistics (engine.rm_ancova_stats), degrees of freedom, optional p-values / residuals."""
+    from . import cynumstats
+    from .engine import PermutationEngine, to_host
+    from .rmancova import RmAncovaModel
+    n = len(factors[0])
+    if data_format == "short":
+        if data.ndim == 2:
+            data = data[:, :, np.newaxis]
+        s = data.shape[0]
+        endog = data.reshape(s * n, data.shape[2])          # a view of the caller's array when it is contiguous
+    elif data_format == "long":
+        s = int(len(data) // n)                             # the reference's len(data)/n is a float under Python 3
+        endog = data if data.ndim == 2 else data[:, np.newaxis]
+    else:
+        raise ValueError("data format must be short or long")
+    def between_design(order):
+        """[1, factors(, interaction), covariates] in long format, subjects taken in `order` (pyfunc.py:1810-1823, 1866-1870,
+        2142-2146, 2176-2178)."""
+        long_ = lambda x: np.concatenate([np.asarray(x, dtype=np.float64).reshape(n, -1)[order]] * s, 0)   # noqa: E731
+        cols = [long_(f) for f in factors]
+        if len(factors) == 2:
+            f1, f2 = (np.asarray(f, dtype=np.float64).reshape(n, -1) for f in factors)
+            cols.append(long_(np.concatenate([f1[:, i:i + 1] * f2 for i in range(f1.shape[1])], axis=1)))
+        if dmy_covariates is not None:
+            cols.append(long_(dmy_covariates))
+        return np.column_stack([np.ones(s * n)] + cols)
+
+    if rand_array is not None:
+        if use_reduced_residuals:
+            endog = np.asarray(cynumstats.resid_covars(between_design(np.arange(n)), np.asarray(endog).T))
+        order = np.arange(s * n)
+        np.random.shuffle(order)                            # the draws of np.random.shuffle(endog_arr), pyfunc.py:1826 / 2148
+        endog[:] = endog[order]                             # in place, like the reference: the caller's data stay shuffled
+    model = RmAncovaModel(n, s, factors, dmy_subjects, dmy_covariates)
+    eng = PermutationEngine(np.ascontiguousarray(endog), None)
+    _, f64 = eng.rm_ancova_stats(model, None, [np.arange(n) if rand_array is None else np.asarray(rand_array)], want_f64=True)
+    F = to_host(f64[0, :, :endog.shape[1]])
+    df_w, df_s = model.df["within_factors"], model.df["s"]
+    dfs = [(model.df[k], df_w) if "s" not in k else (df_s if k == "s" else model.df[k[1:]] * df_s, df_w * df_s)
+           for k in model.names]
+    if verbose:
+        print("Source\t\tDF\tF(Max)")
+        for lab, (d1, d2), f in zip(labels, dfs, F):
+            print("%s\t(%d,%d)\t%.2f" % (lab, d1, d2, f.max()))
+    out = tuple(F)
+    if output_sig:
+        from scipy.stats import f as f_dist
+        return out + tuple(1 - f_dist.cdf(f, d1, d2) for f, (d1, d2) in zip(F, dfs))
+    if output_reduced_residuals:
+        order = np.arange(n) if rand_array is None else np.asarray(rand_array)
+        return out + (np.asarray(cynumstats.resid_covars(between_design(order), np.asarray(endog).T)),)
+    return out
+
+
+def reg_rm_ancova_one_bs_factor(data, dmy_factor1, dmy_subjects, data_format="short", dmy_covariates=None, output_sig=False,
+                                verbose=True, rand_array=None, use_reduced_residuals=False, output_reduced_residuals=False):
+    """pyfunc.py:2068-2280: repeated-measures ANCOVA with one between-subject factor -> (F_a, F_s, F_sa[, P... | residuals]).
+    Same arguments and side effects (with rand_array the rows of the long-format `data` are shuffled in place with the global
+    numpy stream); the statistics run on the GPU (csrc/rmancova_kernels.cu)."""
+    return _rm_ancova(data, [dmy_factor1], dmy_subjects, dmy_covariates, data_format, output_sig, verbose, rand_array,
+                      use_reduced_residuals, output_reduced_residuals, ["Factor\t", "Time\t", "Factor*Time"])
+
+
+def reg_rm_ancova_two_bs_factor(data, dmy_factor1, dmy_factor2, dmy_subjects, dmy_covariates=None, data_format="short",
+                                output_sig=False, verbose=True, rand_array=None, use_reduced_residuals=False,
+                                output_reduced_residuals=False):
+    """pyfunc.py:1712-2052: two between-subject factors -> (F_a, F_b, F_ab, F_s, F_sa, F_sb, F_sab[, P... | residuals])."""
+    return _rm_ancova(data, [dmy_factor1, dmy_factor2], dmy_subjects, dmy_covariates, data_format, output_sig, verbose,
+                      rand_array, use_reduced_residuals, output_reduced_residuals,
+                      ["Factor1\t", "Factor2\t", "F1*F2\t", "Time\t", "F1*Time\t", "F2*Time\t", "F1*F2*Time"])
+
+
+def glm_cosinor(endog, time_var, exog=None, dmy_covariates=None, rand_array=None, interaction_var=None, period=[24.0],
+                calc_MESOR=True, output_fit_only=False):
+    """pyfunc.py:2406-2563: cosinor model -> (R2, MESOR, SE_MESOR, AMPLITUDE, SE_AMPLITUDE, ACROPHASE, SE_ACROPHASE, Fmodel,
+    tMESOR, |tAMPLITUDE|, |tACROPHASE|, tEXOG), or (MESOR, AMPLITUDE, ACROPHASE) with output_fit_only.  The fit, the
+    residual sums of squares and the standard errors come from the cynumstats drop-ins (GPU); the closed-form amplitude /
+    acrophase algebra on [periods, V] arrays stays on the host.  (interaction_var: the reference multiplies a ROW of the
+    design with it, pyfunc.py:2443-2445, which only works by accident of shapes; not supported.)"""
+    from . import cynumstats
+    from .engine import cosinor_design
+    if interaction_var is not None:
+        raise NotImplementedError("glm_cosinor: interaction_var is not supported (see the docstring)")
+    endog = np.asarray(endog)
+    one_d = endog.ndim == 1
+    n = endog.shape[0]
+    X, nper, _ = cosinor_design(time_var, period, exog, dmy_covariates)
+    if rand_array is not None:
+        X = X[rand_array]
+    k = X.shape[1]
+    a, ss_res = cynumstats.cy_lin_lstsqr_mat_residual(X, endog)
+    a2 = a[:, None] if one_d else a
+    cosr, sinr = a2[1:1 + 2 * nper:2], a2[2:2 + 2 * nper:2]             # [periods, V]
+    amplitude = np.sqrt(cosr ** 2 + sinr ** 2)
+    acro = np.arctan(np.abs(np.divide(-sinr, cosr)))
+
+    def quadrant(phi):
+        """Acrophase in (-2 pi, 0] from the signs of the two coefficients (pyfunc.py:2477-2481)."""
+        out = phi.copy()
+        out[(sinr > 0) & (cosr >= 0)] = -phi[(sinr > 0) & (cosr >= 0)]
+        out[(sinr > 0) & (cosr < 0)] = -np.pi + phi[(sinr > 0) & (cosr < 0)]
+        out[(sinr < 0) & (cosr <= 0)] = -np.pi - phi[(sinr < 0) & (cosr <= 0)]
+        out[(sinr <= 0) & (cosr > 0)] = -2 * np.pi + phi[(sinr <= 0) & (cosr > 0)]
+        return out
+
+    if output_fit_only:
+        return a[0], amplitude, quadrant(acro)
+    ss_total = np.sum((endog - np.mean(endog, 0)) ** 2, 0)
+    ms_res = ss_res / (n - k)
+    fmodel = ((ss_total - ss_res) / (k - 1)) / ms_res
+    sigma = np.sqrt(ss_res / (n - k))
+    invXX = np.linalg.inv(np.dot(X.T, X))
+    mesor = t_mesor = se_mesor = t_exog = None
+    if calc_MESOR or exog is not None:
+        if one_d:
+            se = np.sqrt(np.diag(sigma * sigma * invXX))
+        else:
+            se = cynumstats.se_of_slope(endog.shape[1], invXX, sigma ** 2, k)
+        tvalues = a / se
+        mesor, t_mesor, se_mesor = a[0], tvalues[0], se[0]
+        if exog is not None:
+            t_exog = (tvalues[:, None] if one_d else tvalues)[1 + 2 * nper:]
+    ci = 1 + 2 * np.arange(nper)
+    c11, c12, c22 = invXX[ci, ci][:, None], invXX[ci, ci + 1][:, None], invXX[ci + 1, ci + 1][:, None]
+    sn, cs = np.sin(acro), np.cos(acro)
+    se_acro = sigma * np.sqrt((c11 * sn ** 2) + (2 * c12 * sn * cs) + (c22 * cs ** 2)) / amplitude
+    se_amp = sigma * np.sqrt((c11 * cs ** 2) - (2 * c12 * sn * cs) + (c22 * sn ** 2))
+    r2 = (1 - ss_res / ss_total) if rand_array is None else None
+    return (r2, mesor, se_mesor, amplitude, se_amp, quadrant(acro) if rand_array is None else acro, se_acro, fmodel, t_mesor,
+            np.abs(amplitude / se_amp), np.abs(1.0 / se_acro), np.array(t_exog))
+
+
 def check_blocks(block_list):
     """pyfunc.py:2711-2731."""
     unique_blocks = np.unique(block_list)

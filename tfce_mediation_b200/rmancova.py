@@ -187,6 +187,8 @@ class RmAncovaModel(object):
         self.mats = np.ascontiguousarray(np.concatenate(mats))
         self.consts = np.asarray(p.consts, dtype=np.float64)
         self.df = dict(a=df_a, s=df_s, within_factors=df_wf, covariates=df_cov)
+        if self.two:
+            self.df.update(b=df_b, ab=df_ab)
 
     # -- per shuffle ---------------------------------------------------------------------------------
     def operands(self, shuffles, rand_arrays):
