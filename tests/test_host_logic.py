@@ -191,3 +191,23 @@ def test_linregress_t_vectorised_equals_scipy_per_shuffle():
     y = 0.3 * x + rs.standard_normal((40, 120))
     want = np.array([linregress(x[p], y[p])[0] / linregress(x[p], y[p])[4] for p in range(40)])
     assert np.all(np.abs(linregress_t(x, y) - want) <= 1e-13 * np.abs(want))
+
+
+def test_tm_models_design_helpers_equal_reference_golden():
+    """pyfunc.dummy_code / dummy_code_cosine / column_product / stack_ones / calc_indirect (pyfunc.py:2565-2709): host
+    helpers of the tm-models scripts, against outputs of the real reference (tests/golden/make_golden_helpers.py)."""
+    import os
+    from tfce_mediation_b200 import pyfunc
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tm_models_helpers.npz"))
+    eq = lambda a, b: np.array_equal(np.asarray(a), b, equal_nan=True) and np.asarray(a).shape == b.shape  # noqa: E731
+    assert eq(pyfunc.dummy_code(g["grp"]), g["dc_grp"]) and eq(pyfunc.dummy_code(g["grp"], demean=False), g["dc_grp_raw"])
+    assert eq(pyfunc.dummy_code(g["two"]), g["dc_two"])
+    assert eq(pyfunc.dummy_code(g["cont"], iscontinous=True), g["dc_cont"])
+    assert eq(pyfunc.dummy_code(g["cont"], iscontinous=True, demean=False), g["dc_cont_raw"])
+    assert eq(pyfunc.dummy_code_cosine(g["t"], 12.0), g["dcc"])
+    assert eq(pyfunc.column_product(g["a2"], g["b3"]), g["cp_22"]) and eq(pyfunc.column_product(g["cont"], g["b3"]), g["cp_12"])
+    assert eq(pyfunc.column_product(g["a2"], g["cont"]), g["cp_21"]) and eq(pyfunc.column_product(g["cont"], g["t"]), g["cp_11"])
+    assert eq(pyfunc.stack_ones(g["a2"]), g["so"])
+    with np.errstate(invalid="ignore"):
+        for alg, key in (("aroian", "ci_a"), ("sobel", "ci_s"), ("goodman", "ci_g")):
+            assert eq(pyfunc.calc_indirect(g["ta"], g["tb"], alg=alg), g[key])

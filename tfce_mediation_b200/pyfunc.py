@@ -342,6 +342,54 @@ def glm_cosinor(endog, time_var, exog=None, dmy_covariates=None, rand_array=None
             np.abs(amplitude / se_amp), np.abs(1.0 / se_acro), np.array(t_exog))
 
 
+# ---- small host helpers of the tm-models scripts (design coding; pyfunc.py:2565-2709), k x n work only -------------------
+def calc_indirect(ta, tb, alg="aroian"):
+    """Sobel-family z of two t maps (pyfunc.py:2678-2709): aroian 1/sqrt(1/tb^2 + 1/ta^2 + 1/(ta^2 tb^2)), sobel without the
+    product term, goodman with it subtracted."""
+    ta2, tb2 = np.square(ta), np.square(tb)
+    terms = (1 / tb2) + (1 / ta2)
+    if alg == "aroian":
+        return 1 / np.sqrt(terms + (1 / (ta2 * tb2)))
+    if alg == "sobel":
+        return 1 / np.sqrt(terms)
+    if alg == "goodman":
+        return 1 / np.sqrt(terms - (1 / (ta2 * tb2)))
+    raise ValueError("Unknown indirect test algorithm")
+
+
+def dummy_code(variable, iscontinous=False, demean=True):
+    """One indicator column per level except the first (int, squeezed; pyfunc.py:2565-2595), or the variable itself when
+    continuous; optionally centred."""
+    variable = np.asarray(variable)
+    if iscontinous:
+        return variable - np.mean(variable, 0) if demean else variable
+    levels = np.unique(variable)[1:]
+    coded = np.squeeze(np.array([(variable == lv) for lv in levels]).astype(int)).T
+    return coded - np.mean(coded, 0) if demean else coded
+
+
+def dummy_code_cosine(time, period=24.0):
+    """[cos(2 pi t / T), sin(2 pi t / T)] (pyfunc.py:2597-2620)."""
+    angle = np.divide(2.0 * np.pi * np.asarray(time), period)
+    return np.column_stack((np.cos(angle), np.sin(angle)))
+
+
+def column_product(arr1, arr2):
+    """Every column of arr1 times every column of arr2, arr1-major (pyfunc.py:2622-2660)."""
+    arr1, arr2 = np.array(arr1), np.array(arr2)
+    if len(arr1) != len(arr2):
+        raise ValueError("arrays must be of same length")
+    if arr1.ndim == 1 or arr2.ndim == 1:
+        a, b = (arr1, arr2) if arr1.ndim == 1 else (arr2, arr1)
+        return (a * b.T).T + 0
+    return np.concatenate([arr1[:, i:i + 1] * arr2 for i in range(arr1.shape[1])], axis=1) + 0
+
+
+def stack_ones(arr):
+    """The array with a leading column of ones (pyfunc.py:2662-2676)."""
+    return np.column_stack([np.ones(len(arr)), arr])
+
+
 def check_blocks(block_list):
     """pyfunc.py:2711-2731."""
     unique_blocks = np.unique(block_list)
