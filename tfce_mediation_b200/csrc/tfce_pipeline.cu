@@ -281,6 +281,10 @@ __global__ void __launch_bounds__(256) pipe_ascent_kernel(PipeParams P, int chun
 // adjacency sets, ~60 per vertex) or very uneven degrees.  One thread per vertex as above; the 32 lanes of a warp own
 // the 32 vertices of one slice, so slot group j4 of the slice is ONE coalesced 512-byte load for the warp and the trip
 // count is warp-uniform.  kWords 32-bit words of earlier-neighbour mask per vertex (slot j -> bit j & 31 of word j >> 5).
+// Measured and rejected: taking each vertex through 2 or 4 maps per thread, so that every slot group is loaded once and
+// serves 8 / 16 level gathers (the rows are 77 % of the kernel's L2 sectors, which run at 7.5 TB/s): correct, and not
+// faster -- 24.2 / 24.2 / 24.6 ms per 1,024 maps for the stage with 1 / 2 / 4 maps per thread (config 3: 10.47 / 10.59).
+// The byte gathers, not the row stream, set the pace.
 template <int kWords>
 __global__ void __launch_bounds__(256) pipe_ascent_wide_kernel(PipeParams P, int chunks) {
     __shared__ int sPeaks, sBase;
