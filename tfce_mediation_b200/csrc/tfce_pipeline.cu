@@ -285,6 +285,10 @@ __global__ void __launch_bounds__(256) pipe_ascent_kernel(PipeParams P, int chun
 // serves 8 / 16 level gathers (the rows are 77 % of the kernel's L2 sectors, which run at 7.5 TB/s): correct, and not
 // faster -- 24.2 / 24.2 / 24.6 ms per 1,024 maps for the stage with 1 / 2 / 4 maps per thread (config 3: 10.47 / 10.59).
 // The byte gathers, not the row stream, set the pace.
+// Also rejected: staging the map's level bytes of the chunk's neighbourhood in shared memory (1,024 vertices per CTA, a
+// window of +-8,192 vertices = 17 KB, which holds 99.9 % of the neighbours; the rest read from global memory): correct,
+// slower -- 26.3 against 24.3 ms (config 3: 11.17 against 10.48).  L1 serves these semi-coherent byte gathers better
+// than shared memory plus the staging copy and the two-path select.
 template <int kWords>
 __global__ void __launch_bounds__(256) pipe_ascent_wide_kernel(PipeParams P, int chunks) {
     __shared__ int sPeaks, sBase;
