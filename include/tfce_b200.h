@@ -208,6 +208,17 @@ int tmb_sobelz_cross_rows(const double *cperm_dev, int64_t ldb, int m, const dou
                           const double *ta_scalar_dev, int P, int alg, float *z32_dev, double *z64_dev, int64_t ldt,
                           void *stream);
 
+/* t statistics of designs of which only SOME columns change between shuffles (the randomise drivers' `-v first last`:
+ * vertex_tfce_multiple_regression_randomise.py:84-97 permutes the chosen regressors and leaves the covariates alone), from
+ * centred cross-products: cperm_dev float64 [P*m, ldb] = the rows of the m changing columns of every shuffle (tmb_glm_beta),
+ * cfix_dev [f, ldf] = the rows of the fixed columns (once), C_dev [P, r, r] = the shuffle's INVERSE centred Gram matrix
+ * (r <= 16), colmap: source row of each regressor in design order (< m: changing, else m + fixed row).  Output rows
+ * row0 .. row0+nrows-1 per shuffle, as tmb_glm_tstat. */
+int tmb_glm_tstat_cross_rows(const double *cperm_dev, int64_t ldb, int m, const double *cfix_dev, int64_t ldf, int f, int64_t V,
+                             const double *C_dev, int r, const int32_t *colmap_dev, const int32_t *colmap_host, int row0,
+                             int nrows, double dof, const double *yy_dev, int P, float *t32_dev, double *t64_dev, int64_t ldt,
+                             int nan_to_zero, void *stream);
+
 /* Designs with MORE than 8 non-intercept regressors (the reference accepts any k: cynumstats.pyx:28-29,59-64 -- e.g.
  * dummy-coded sites plus covariates): the betas are formed first by tmb_glm_beta (every pseudo-inverse row of every
  * design is one column of At_dev and one output row, design-major: row p*r + i), then these evaluate the same statistics

@@ -196,3 +196,42 @@ def test_regression_block_with_twenty_regressors_end_to_end():
         for c in (0, 7, k - 2):
             want = helpers.oracle_signed_max(2, 0.67, csr, t[c + 1].astype(np.float32))
             assert "%.4f" % got[p, c, 0, 0] == "%.4f" % want[0] and "%.4f" % got[p, c, 0, 1] == "%.4f" % want[1]
+
+
+@pytest.mark.parametrize("k,first,last", [(5, 1, 2), (4, 3, 3), (3, 1, 1)])
+def test_partial_column_permutation_from_cross_products(monkeypatch, k, first, last):
+    """The drivers' `-v first last` mode (vertex_tfce_multiple_regression_randomise.py:84-97): only regressors first..last
+    are permuted, cumulatively; the other columns stay.  The engine contracts only the changing columns with the data
+    (tmb_glm_tstat_cross_rows): float64 t within 1e-10 of the whole-design fit and of the oracle's tval_int, float32 maps
+    equal to the float64 ones rounded, and the block's maxima equal those of the whole-design path."""
+    from tests import helpers
+    from tfce_mediation_b200.engine import PermutationEngine, Surface, design_stack
+    from tfce_mediation_b200.tfce import CreateAdjSet
+    n, P = 60, 12
+    _, _, csr = helpers.ico(4)
+    V = csr[0].shape[0] - 1
+    rs = np.random.RandomState(k * 10 + first)
+    X = np.column_stack([np.ones(n), rs.standard_normal((n, k - 1))])
+    y = (rs.standard_normal((n, V)) + 0.3 * X[:, first][:, None]).astype(np.float32)
+    designs = []
+    for p in range(P):                                     # the reference permutes the chosen columns in place
+        X[:, first:last + 1] = X[oracle.permutation_indices(5000 + p, n), first:last + 1]
+        designs.append(X.copy())
+    designs = np.stack(designs)
+    eng = PermutationEngine(y, [Surface(CreateAdjSet(2, 0.67, csr), 0)], two_sided=True)
+    changing = eng._partial_columns(designs)
+    assert changing is not None and list(changing) == list(range(first - 1, last))
+    t32, t64 = eng.tstat_partial(designs, changing, want_f64=True)
+    t32, t64 = eng.to_caller_order(t32).cpu().numpy()[:, :, :V], eng.to_caller_order(t64).cpu().numpy()[:, :, :V]
+    _, w64 = eng.tstat(design_stack(designs, center=True), want_f64=True)
+    w64 = w64.cpu().numpy()[:, :, :V]
+    tol = lambda a, b: np.all(np.abs(a - b) <= 1e-10 * np.maximum(1.0, np.abs(b)))  # noqa: E731
+    assert tol(t64, w64) and np.array_equal(t32, t64.astype(np.float32))
+    for p in (0, P - 1):
+        nx = designs[p]
+        assert tol(t64[p], oracle.tval_int(nx, np.linalg.inv(nx.T @ nx), y, n, k, V)[1:])
+    got = eng.regression_block(None, designs=designs)
+    monkeypatch.setenv("TMB_GLM_PARTIAL", "0")
+    assert eng._partial_columns(designs) is None
+    want = eng.regression_block(None, designs=designs)
+    assert got.shape == (P, k - 1, 1, 2) and np.allclose(got, want, rtol=1e-6, atol=0)

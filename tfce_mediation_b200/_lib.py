@@ -71,6 +71,8 @@ SIGNATURES = {
                                 _vp, _vp, _i64, _vp]),
     "tmb_sobelz_cross_rows": (_int, [_vp, _i64, _int, _vp, _i64, _int, _i64, _vp, _int, _int, _f64, _vp, _int, _int, _f64, _vp,
                                      _vp, _vp, _vp, _int, _int, _vp, _vp, _i64, _vp]),
+    "tmb_glm_tstat_cross_rows": (_int, [_vp, _i64, _int, _vp, _i64, _int, _i64, _vp, _int, _vp, _vp, _int, _int, _f64, _vp, _int,
+                                        _vp, _vp, _i64, _int, _vp]),
     "tmb_fwe_lookup": (_int, [_vp, _int, _vp, _i64, _vp, _vp]),
     "tmb_comm_unique_id": (_int, [_vp]),
     "tmb_comm_create": (_int, [_vp, _int, _int, _int, _c.POINTER(_vp)]),

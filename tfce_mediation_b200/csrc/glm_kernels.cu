@@ -85,7 +85,7 @@ struct GlmParams {
     const double *yy;
     float *t32; double *t64; int64_t ldt;
     int nan_to_zero;
-    int mode;                           // 0 t-stat, 1 betas, 2 sobel, 3 F statistics, 4 cosinor (stored betas only), 5 sobel from cross-products (DMMA, one row per design), 6 the same for any designs (stored rows)
+    int mode;                           // 0 t-stat, 1 betas, 2 sobel, 3 F statistics, 4 cosinor (stored betas only), 5 sobel from cross-products (DMMA, one row per design), 6 the same for any designs (stored rows), 7 t from cross-products (stored rows)
     // sobel: rows [0, rA) of each design group are path A, rows [rA, rA+rB) path B
     const double *GB; const double *dB; int rA, rB, rowA, rowB; double dofB;
     const double *ta_scalar; int alg;
@@ -1186,7 +1186,7 @@ __global__ void __launch_bounds__(128) glm_stats_from_beta_kernel(GlmParams p, c
     const int perm = blockIdx.y;
     if (v >= p.ldt) return;
     const bool inside = v < p.V;
-    const int rt = p.mode == 2 ? p.rA + p.rB : p.mode == 6 ? p.cross_m : p.r;
+    const int rt = p.mode == 2 ? p.rA + p.rB : (p.mode == 6 || p.mode == 7) ? p.cross_m : p.r;
     double b[kMaxGenericR];
     for (int i = 0; i < rt; ++i) b[i] = inside ? beta[((size_t)perm * rt + i) * ldb + v] : 0.0;
     const double yyv = inside ? p.yy[v] : 0.0;
@@ -1225,6 +1225,33 @@ __global__ void __launch_bounds__(128) glm_stats_from_beta_kernel(GlmParams p, c
             if (p.t32) p.t32[off] = __double2float_rn(f);
             if (p.t64) p.t64[off] = f;
             M += ki * ki;
+        }
+    } else if (p.mode == 7) {
+        // t statistics of a design of which only some columns are permuted (the drivers' -v mode,
+        // vertex_tfce_multiple_regression_randomise.py:84-97): centred cross-products of the permuted columns from the
+        // contraction (b[0 .. m)), of the fixed columns from p.cfix (fitted once); colmap: source row of each of the r
+        // regressors in design order; p.G: the shuffle's INVERSE centred Gram matrix.  beta = C c, SSE = yy - c'beta.
+        const int m = p.cross_m, r = p.r;
+        const double *C = p.G + (size_t)perm * r * r;
+        double c[16], bt[16], q = 0.0;
+        for (int i = 0; i < r; ++i) {
+            const int src = __ldg(p.colmap + i);
+            c[i] = src < m ? b[src] : (inside ? __ldg(p.cfix + (size_t)(src - m) * p.ldf + v) : 0.0);
+        }
+        for (int a = 0; a < r; ++a) {
+            double bi = 0.0;
+            for (int j = 0; j < r; ++j) bi = __fma_rn(__ldg(C + a * r + j), c[j], bi);
+            bt[a] = bi;
+            q = __fma_rn(c[a], bi, q);
+        }
+        const double sse = yyv - q;
+        for (int a = p.row0; a < p.row0 + p.nrows; ++a) {
+            double t = t_from(bt[a], sse, p.dof, __ldg(C + a * r + a));
+            if (p.nan_to_zero && t != t) t = 0.0;
+            if (!inside) t = 0.0;
+            const size_t off = ((size_t)perm * p.nrows + (a - p.row0)) * p.ldt + v;
+            if (p.t32) p.t32[off] = __double2float_rn(t);
+            if (p.t64) p.t64[off] = t;
         }
     } else if (p.mode == 6) {
         // Sobel z from centred CROSS-PRODUCTS c = Z'y instead of betas, for designs of which only some columns are
@@ -1340,7 +1367,7 @@ __global__ void __launch_bounds__(128) glm_stats_from_beta_kernel(GlmParams p, c
 }
 
 static int launch_stats_from_beta(const GlmParams &p, const double *beta, int64_t ldb, cudaStream_t stream) {
-    const int rt = p.mode == 2 ? p.rA + p.rB : p.mode == 6 ? p.cross_m : p.r;
+    const int rt = p.mode == 2 ? p.rA + p.rB : (p.mode == 6 || p.mode == 7) ? p.cross_m : p.r;
     TMB_REQUIRE(rt >= 1 && rt <= kMaxGenericR, "glm: at most %d non-intercept regressors per design (got %d)", kMaxGenericR, rt);
     TMB_REQUIRE(p.P >= 1 && p.P <= 65535, "glm (stored betas): 1..65535 designs per call (got %d)", p.P);
     const dim3 grid((unsigned)((p.ldt + 127) / 128), (unsigned)p.P);
@@ -1610,6 +1637,24 @@ extern "C" int tmb_sobelz_cross(const void *Y_dev, int ydtype, int n, int64_t V,
     p.yy = yy_dev; p.t32 = z32_dev; p.t64 = z64_dev; p.ldt = ldt; p.mode = 5; p.GB = CB_dev; p.rowB = rowB; p.dofB = dofB;
     p.cfix = cd_dev; p.xx = 1.0 / xx; p.dof = (1.0 / xx) / dofA; p.xpos = xpos; p.alg = alg; p.layout = 1;
     return launch_glm(p, (cudaStream_t)stream);
+}
+
+extern "C" int tmb_glm_tstat_cross_rows(const double *cperm_dev, int64_t ldb, int m, const double *cfix_dev, int64_t ldf, int f,
+                                        int64_t V, const double *C_dev, int r, const int32_t *colmap_dev,
+                                        const int32_t *colmap_host, int row0, int nrows, double dof, const double *yy_dev,
+                                        int P, float *t32_dev, double *t64_dev, int64_t ldt, int nan_to_zero, void *stream) {
+    TMB_REQUIRE(cperm_dev && C_dev && colmap_dev && colmap_host && yy_dev && (t32_dev || t64_dev), "tmb_glm_tstat_cross_rows: null pointer");
+    TMB_REQUIRE(m >= 1 && m <= kMaxGenericR && f >= 0 && (f == 0 || cfix_dev) && r >= 1 && r <= 16 && row0 >= 0 && nrows >= 1 &&
+                    row0 + nrows <= r && ldb >= V && ldt >= V && (f == 0 || ldf >= V),
+                "tmb_glm_tstat_cross_rows: bad shape (m=%d f=%d r=%d rows %d..%d; at most 16 regressors)", m, f, r, row0, row0 + nrows);
+    for (int i = 0; i < r; ++i)
+        TMB_REQUIRE(colmap_host[i] >= 0 && colmap_host[i] < m + f, "tmb_glm_tstat_cross_rows: column source %d out of range", colmap_host[i]);
+    TMB_DEVICE_OF(cperm_dev, "tmb_glm_tstat_cross_rows");
+    GlmParams p{};
+    p.V = V; p.G = C_dev; p.r = r; p.row0 = row0; p.nrows = nrows; p.dof = dof; p.cfix = cfix_dev; p.ldf = ldf; p.cross_m = m;
+    p.cross_f = f; p.colmap = colmap_dev; p.yy = yy_dev; p.P = P; p.t32 = t32_dev; p.t64 = t64_dev; p.ldt = ldt;
+    p.nan_to_zero = nan_to_zero; p.mode = 7;
+    return launch_stats_from_beta(p, cperm_dev, ldb, (cudaStream_t)stream);
 }
 
 extern "C" int tmb_sobelz_cross_rows(const double *cperm_dev, int64_t ldb, int m, const double *cfix_dev, int64_t ldf, int f,

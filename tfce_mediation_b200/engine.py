@@ -654,6 +654,72 @@ class PermutationEngine(object):
             out_t = self._download(out_t) if download else out_t
         return out_f if stat == "f" else out_t if stat == "t" else (out_f, out_t)
 
+    # -- designs of which only some columns change between shuffles (the drivers' -v mode) -----------
+    def _partial_columns(self, designs):
+        """Indices (among the non-intercept columns) of the columns that differ between the designs of a block, or None
+        when the cross-product path does not apply (all columns change, float64 data kept on the established path,
+        more than 16 regressors, TMB_GLM_PARTIAL=0)."""
+        P, n, k = designs.shape
+        r = k - 1
+        if P < 2 or r < 2 or r > 16 or _os.environ.get("TMB_GLM_PARTIAL", "") == "0":
+            return None
+        changing = np.flatnonzero(np.any(designs[:, :, 1:] != designs[:1, :, 1:], axis=(0, 1)))
+        if changing.size == 0 or changing.size == r:
+            return None
+        return changing
+
+    def tstat_partial(self, designs, changing, want_f64=False):
+        """t of every regressor for designs [P, n, k] whose columns `changing` (indices among the k-1 regressors) differ
+        between shuffles while the others are fixed -- vertex_tfce_multiple_regression_randomise.py:84-97 (`-v first
+        last`): only the changing columns are contracted with the data per shuffle, the fixed columns' cross-products are
+        fitted once (tmb_glm_tstat_cross_rows).  CUDA float32 [P, k-1, ld] (internal column order)."""
+        import torch
+        P, n, k = designs.shape
+        r = k - 1
+        Z = designs[:, :, 1:] - designs[:, :, 1:].mean(axis=1, keepdims=True)             # centred regressors [P, n, r]
+        C = np.ascontiguousarray(np.linalg.inv(np.einsum("pni,pnj->pij", Z, Z)))
+        fixed_idx = np.setdiff1d(np.arange(r), changing)
+        m, f = int(changing.size), int(fixed_idx.size)
+        colmap = np.empty(r, dtype=np.int32)
+        colmap[changing] = np.arange(m)
+        colmap[fixed_idx] = m + np.arange(f)
+        fixed = np.ascontiguousarray(Z[0][:, fixed_idx])
+        key = fixed.tobytes()
+        st = getattr(self, "_partial_fixed", None)
+        if st is None or st[0] != key:
+            ldF = round_up(f, TILE_M)
+            At = np.zeros((n, ldF))
+            At[:, :f] = fixed
+            cfix = torch.empty((f, self.Y.ld), dtype=torch.float64, device=self.device)
+            At_d = torch.from_numpy(At).to(self.device)
+            _lib.check(_lib.lib().tmb_glm_beta(_lib.ptr(self.Y.t), self.Y.dtype_code, n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldF,
+                                               f, _lib.ptr(cfix), self.Y.ld, _lib.current_stream()))
+            st = (key, cfix)
+            self._partial_fixed = st
+        cfix = st[1]
+        yy = self.Y.sumsq(True)
+        t32 = torch.empty((P, r, self.Y.ld), dtype=torch.float32, device=self.device)
+        t64 = torch.empty((P, r, self.Y.ld), dtype=torch.float64, device=self.device) if want_f64 else None
+        colmap_d = self._upload("part_colmap", colmap)
+        C_d = self._upload("part_C", C)
+        lib, stream = _lib.lib(), _lib.current_stream()
+        per = max(1, int(1.5e9 // (m * self.Y.ld * 8)))
+        for a in range(0, P, per):
+            b = min(P, a + per)
+            rows = (b - a) * m
+            ldA = round_up(rows, TILE_M)
+            At = np.zeros((n, ldA))
+            At[:, :rows] = Z[a:b][:, :, changing].transpose(1, 0, 2).reshape(n, rows)      # column p*m + i
+            At_d = self._upload("part_At", At)
+            cperm = self._ring("part_cperm", (rows, self.Y.ld), torch.float64)
+            _lib.check(lib.tmb_glm_beta(_lib.ptr(self.Y.t), self.Y.dtype_code, n, self.Y.V, self.Y.ld, _lib.ptr(At_d), ldA, rows,
+                                        _lib.ptr(cperm), self.Y.ld, stream))
+            _lib.check(lib.tmb_glm_tstat_cross_rows(
+                _lib.ptr(cperm), self.Y.ld, m, _lib.ptr(cfix), self.Y.ld, f, self.Y.V, _lib.ptr(C_d[a:b]), r, _lib.ptr(colmap_d),
+                _lib.ptr(colmap), 0, r, float(n - k), _lib.ptr(yy), b - a, _lib.ptr(t32[a:b]),
+                _lib.ptr(t64[a:b]) if t64 is not None else None, self.Y.ld, 1 if self.nan_to_zero else 0, stream))
+        return (t32, t64) if want_f64 else t32
+
     # -- whole shuffles --------------------------------------------------------------------------
     def regression_block(self, X, perm_idx=None, designs=None, want_maps=False, download=True):
         """Regression + TFCE + scaled max for a block of shuffles.
@@ -668,6 +734,10 @@ class PermutationEngine(object):
             designs = np.asarray(designs, dtype=np.float64)
             if not has_intercept(designs):
                 raise ValueError("designs must have the intercept in column 0")
+            part = self._partial_columns(designs)
+            if part is not None:
+                t32 = self.tstat_partial(designs, part)
+                return self._finish_regression(t32, want_maps, download)
             stack = design_stack(designs, center=True)
         else:
             X = np.asarray(X, dtype=np.float64)
@@ -675,6 +745,10 @@ class PermutationEngine(object):
                 raise ValueError("X must have the intercept in column 0")
             stack = None
         t32 = self.tstat(stack, caller_order=False) if stack is not None else self.tstat_rowperm(X, perm_idx)
+        return self._finish_regression(t32, want_maps, download)
+
+    def _finish_regression(self, t32, want_maps, download):
+        """TFCE + scaled maxima of a block of t maps [P, C, ld] (internal column order)."""
         P, C, ld = t32.shape
         mx, status, maps = self.plan.run(t32.view(P * C, ld), two_sided=self.two_sided, want_maps=want_maps)
         mx = mx.view(P, C, self.plan.S, 2)
