@@ -180,7 +180,7 @@ def run(opts):
     idx = np.stack(idx) if idx else np.zeros((0, n), dtype=np.int64)
     for eng, members in engines:
         if opts.inputmediation:
-            local = (eng.mediation_blocks(medtype, pred_x, depend_y, idx, block=C.BLOCK) if len(idx)
+            local = (eng.mediation_blocks(medtype, pred_x, depend_y, idx, block=C.block_for(eng)) if len(idx)
                      else np.zeros((0, len(members)), dtype=np.float32))
             allrows = C.gather(local.reshape(local.shape[0], 1, -1))
             if rank == 0:
@@ -188,7 +188,7 @@ def run(opts):
                     C.append_rows("%s/perm_maxTFCE_surf%d_%s_zstat.csv" % (outdir, s, medtype), allrows[:, 0, si], "%f")
         else:
             X = np.column_stack([np.ones(n), pred_x])
-            local = (eng.regression_blocks(X, idx, block=C.BLOCK) if len(idx)
+            local = (eng.regression_blocks(X, idx, block=C.block_for(eng)) if len(idx)
                      else np.zeros((0, X.shape[1] - 1, len(members), 2), dtype=np.float32))
             allrows = C.gather(local)
             if rank == 0:

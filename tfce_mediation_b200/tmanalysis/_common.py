@@ -7,7 +7,19 @@ import numpy as np
 from .. import parallel
 from .._graph import adjacency_to_csr, induced_subgraph
 
-BLOCK = 512      # shuffles per engine call
+BLOCK = 512      # shuffles per engine call when the data size is unknown (block_for adapts it); tests override it
+_DEFAULT_BLOCK = BLOCK
+
+
+def block_for(eng):
+    """Shuffles per pipelined engine call for this engine's data: about 6e8 vertex-maps per call, a power of two in
+    [64, 8192] -- small surfaces need many shuffles per launch to fill the GPU (BASELINE config 1: 8,192), large
+    multi-surface rows few (config 5: 128 at most).  An explicitly changed C.BLOCK wins."""
+    if BLOCK != _DEFAULT_BLOCK:
+        return BLOCK
+    per = max(1.0, 6e8 / max(1, int(eng.Y.V)))
+    return int(min(8192, max(64, 2 ** int(np.floor(np.log2(per))))))
+
 
 # wall-clock marks of the last driver run: [(label, seconds since the previous mark)], read by tmanalysis/job.py
 TIMINGS = []

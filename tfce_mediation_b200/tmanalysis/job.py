@@ -125,7 +125,7 @@ def run_job(numperm, workload="config2", gpus=1, t_process_start=None, check=200
             "metric": "wall-clock seconds, %d-permutation vertex-wise regression + TFCE + FWER p-map (%s)" % (numperm, workload),
             "value": wall, "unit": "s", "n_gpus": ws, "higher_is_better": False, "target_s": 60.0,
             "data": "synthetic", "config": {"workload": workload, "permutations": numperm, "shuffles": shuffles,
-                                            "driver_block": C.BLOCK, "seed": SEED},
+                                            "driver_block": "C.block_for(engine): about 6e8 vertex-maps per engine call", "seed": SEED},
             "breakdown_s": dict([("process start -> job entry (interpreter, imports)", startup)] +
                                 [(k, v) for k, v in phases] +
                                 [("observed statistic + FWER p-maps (rank 0)", t_done - t_rand)]),

@@ -82,7 +82,7 @@ def run(opts):
                        else C.draw_row_permutation(n))
         C.tick("permutation index stream (numpy RNG)")
         if idx:
-            results.append(eng.regression_blocks(X, np.stack(idx), block=C.BLOCK).max(axis=2))
+            results.append(eng.regression_blocks(X, np.stack(idx), block=C.block_for(eng)).max(axis=2))
         C.tick("shuffles (fit + TFCE + max)")
     else:
         # the reference permutes the chosen columns of X IN PLACE, so shuffle i sees the composition of all draws since

@@ -43,14 +43,13 @@ def run(opts):
     rank, ws, a, b = C.shard(first, last)
     if rank == 0:
         os.makedirs(outdir, exist_ok=True)
-    results = []
-    for p0, p1 in C.chunks(a, b):
-        idx = []
-        for iter_perm in range(p0, p1 + 1):
-            np.random.seed(C.reference_seed(iter_perm, opts.seed))
-            idx.append(C.draw_row_permutation(n))
-        results.append(eng.mediation_block(medtype, pred_x, depend_y, np.stack(idx))[:, 0])
-    local = np.concatenate(results) if results else np.zeros((0,), dtype=np.float32)
+    # the index stream with the reference's RNG calls, then the whole slice through the pipelined engine
+    idx = []
+    for iter_perm in range(a, b + 1):
+        np.random.seed(C.reference_seed(iter_perm, opts.seed))
+        idx.append(C.draw_row_permutation(n))
+    local = (eng.mediation_blocks(medtype, pred_x, depend_y, np.stack(idx), block=C.block_for(eng))[:, 0]
+             if idx else np.zeros((0,), dtype=np.float32))
     allrows = C.gather(local.reshape(-1, 1))
     if rank == 0:
         C.append_rows("%s/perm_Zstat_%s_TFCE_maxVoxel.csv" % (outdir, medtype), allrows.reshape(-1), "%1.4f")

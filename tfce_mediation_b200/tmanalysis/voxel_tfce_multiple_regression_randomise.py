@@ -89,7 +89,7 @@ def run(opts):
             idx.append(C.draw_block_permutation(block_list, indexer) if opts.exchangeblock
                        else C.draw_row_permutation(n))
         if idx:
-            results.append(eng.regression_blocks(X, np.stack(idx), block=C.BLOCK)[:, :, 0, :])
+            results.append(eng.regression_blocks(X, np.stack(idx), block=C.block_for(eng))[:, :, 0, :])
     else:
         # the reference permutes the chosen columns of X IN PLACE, so shuffle i sees the composition of all draws since
         # the start of the range (:93-97); a rank whose slice starts later replays the draws it skipped (RNG calls and
