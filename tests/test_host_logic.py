@@ -211,3 +211,24 @@ def test_tm_models_design_helpers_equal_reference_golden():
     with np.errstate(invalid="ignore"):
         for alg, key in (("aroian", "ci_a"), ("sobel", "ci_s"), ("goodman", "ci_g")):
             assert eq(pyfunc.calc_indirect(g["ta"], g["tb"], alg=alg), g[key])
+
+
+def test_block_for_scales_with_the_data_size():
+    """tmanalysis/_common.block_for: about 6e8 vertex-maps per engine call, a power of two in [64, 8192]; an explicit C.BLOCK wins."""
+    from tfce_mediation_b200.tmanalysis import _common as C
+
+    class Eng(object):
+        class Y(object):
+            V = 0
+
+    def blk(V):
+        Eng.Y.V = V
+        return C.block_for(Eng)
+
+    assert blk(10242) == 8192 and blk(299881) == 1024 and blk(130781) == 4096 and blk(7000000) == 64 and blk(50000000) == 64
+    old = C.BLOCK
+    try:
+        C.BLOCK = 2
+        assert blk(299881) == 2
+    finally:
+        C.BLOCK = old
